@@ -1,0 +1,207 @@
+/*
+ * tasu_bridge.h — C ABI of libtasu_bridge.so: the B200 (sm_100a) implementation of the
+ * TASU speech→LLM bridge hot path of PigeonDan1/ps-slm.
+ *
+ * The reference is pure Python/PyTorch and has NO FFI; these entry points are what a
+ * ctypes binding placed in the reference's own methods would call (INTEGRATION.md shows
+ * the stubs).  Every function cites the reference lines (relative to /root/reference/)
+ * whose work it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - strides are in ELEMENTS, sizes in elements/rows; dtype codes are TASU_F32/TASU_BF16;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *    synchronises the device, allocates or frees — the caller owns every buffer;
+ *  - return value: TASU_OK (0) or a negative TASU_ERR_*; tasu_last_error() gives the
+ *    thread-local message.  Data-dependent error conditions (the two ValueErrors of
+ *    ps-slm.py:783-785 and :861-865) are reported through the splice header words so the
+ *    host can raise after its single read-back.
+ */
+#ifndef TASU_BRIDGE_H_
+#define TASU_BRIDGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TASU_ABI_VERSION 1
+
+enum { TASU_OK = 0, TASU_ERR_INVALID_ARG = -1, TASU_ERR_CUDA = -2, TASU_ERR_UNSUPPORTED = -3 };
+enum { TASU_F32 = 0, TASU_BF16 = 1 };
+
+/* frame-stats / collapse input kinds */
+enum { TASU_INPUT_PROBS = 0,  /* probabilities or log-probabilities; auto-detected like ps-slm.py:256 */
+       TASU_INPUT_LOGITS = 1  /* raw ctc_lo logits; softmax is fused (replaces ps-slm.py:451,582) */ };
+
+/* GEMM epilogues */
+enum { TASU_EPI_NONE = 0, TASU_EPI_BIAS = 1, TASU_EPI_BIAS_SILU = 2, TASU_EPI_BIAS_RELU = 3,
+       TASU_EPI_LNFOLD_SILU = 4 /* silu(rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]) */ };
+
+/* splice header words (int64) written by tasu_splice_header */
+enum { TASU_SH_SPLICED_LEN = 0,   /* S' = max_b sum(placeholders)            ps-slm.py:809 */
+       TASU_SH_LEFT_PADDING = 1,  /* 1 = left padding                         ps-slm.py:771-785 */
+       TASU_SH_ERR_BOTH_SIDES = 2,/* 1 → ValueError of ps-slm.py:783-785 */
+       TASU_SH_TOTAL_SLOTS = 3,   /* number of audio slots found              ps-slm.py:861 */
+       TASU_SH_TOTAL_AUDIO = 4,   /* sum(num_audio_tokens)                    ps-slm.py:861 */
+       TASU_SH_N_SPEECH = 5,      /* number of <speech> tokens in input_ids */
+       TASU_SH_WORDS = 8 };
+
+/* collapse header words (int64) written by tasu_collapse_scan */
+enum { TASU_CH_N_OUT = 0,         /* total compressed rows  sum_b M_b */
+       TASU_CH_MAX_LEN = 1,       /* max_b M_b              ps-slm.py:303 */
+       TASU_CH_IS_LOGPROB = 2,    /* 1 if input was detected as log-probs  ps-slm.py:256 */
+       TASU_CH_WORDS = 4 };
+
+int tasu_abi_version(void);
+const char* tasu_last_error(void);
+/* sm_count, compute capability of the current device */
+int tasu_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 2a — per-frame greedy statistics over the vocab axis, one warp per frame.
+ * Replaces torch.softmax (ps-slm.py:451,582), ctc_posterior.max() (:256) and
+ * ctc_probs[b,:L].argmax(-1) (:265).
+ *   x           [B, T, V] view: element (b,t,v) at x[b*batch_stride + t*row_stride + v]
+ *   argmax      [B*T] int32   first index of the row maximum (torch tie rule)
+ *   x_blank     [B*T] float   x[b,t,blank_id] as given (prob, log-prob or logit)
+ *   row_max     [B*T] float
+ *   row_sumexp  [B*T] float   sum_v exp(x - row_max); only for TASU_INPUT_LOGITS (else may be NULL)
+ *   global_max_enc [1] uint32 order-preserving encoding of max over the WHOLE tensor;
+ *               zero-initialised by this call (stream-ordered) before the kernel runs.
+ *   lens        [B] int64 or NULL: with TASU_INPUT_LOGITS rows t >= lens[b] are skipped;
+ *               with TASU_INPUT_PROBS every row is scanned (the reference's max is global).
+ */
+int tasu_frame_stats(const void* x, int dtype, int input_kind, int B, int T, int V,
+                     int64_t batch_stride, int64_t row_stride, int blank_id, const int64_t* lens,
+                     int32_t* argmax, float* x_blank, float* row_max, float* row_sumexp,
+                     uint32_t* global_max_enc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 2b — collapse plan: runs of equal greedy ids, blank frames kept one by one,
+ * candidate score = mean blank probability, keep iff score < threshold (strict, fp32),
+ * compaction by block scan.  Replaces the Python loop ps-slm.py:259-301.
+ *   seg_start/seg_len/seg_score [B*T]  kept candidates of utterance b at [b*T, b*T+M_b)
+ *   new_lens   [B] int64  M_b  (ps-slm.py:315)
+ */
+int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float* row_max,
+                       const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
+                       const int64_t* lens, int B, int T, int blank_id, float threshold,
+                       int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
+                       void* stream);
+
+/* exclusive scan of new_lens → row_off [B+1] int32, header [TASU_CH_WORDS] int64 */
+int tasu_collapse_scan(const int64_t* new_lens, const uint32_t* global_max_enc, int B,
+                       int32_t* row_off, int64_t* header, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,
+ * :303-314).  feats is a [B, T, D] view (same tensor as the posterior on the default path).
+ *   softmax_max/softmax_sumexp: NULL → pool feats as given; else feats are logits and
+ *               exp(x - max[b,t]) / sumexp[b,t] is pooled (fused softmax).
+ *   layout 0 (packed):  out row r in [0, N_out) at out + r*out_row_stride      (N_out = row_off[B])
+ *   layout 1 (padded):  out row (b, j<max_len) at out + (b*max_len + j)*out_row_stride, rows
+ *               j >= M_b are zero-filled (ps-slm.py:308-314)
+ *   ln_mean/ln_rstd [rows] optional LayerNorm statistics of every pooled row (fp32, biased
+ *               variance, eps) consumed by TASU_EPI_LNFOLD_SILU (projector.py:139,150).
+ */
+int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int T, int D,
+                          int64_t batch_stride, int64_t row_stride,
+                          const float* softmax_max, const float* softmax_sumexp,
+                          const int32_t* seg_start, const int32_t* seg_len, const int32_t* row_off,
+                          int layout, int64_t max_len, int64_t max_rows,
+                          void* out, int out_dtype, int64_t out_row_stride,
+                          float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 1a — simulated posterior rows (ps-slm.py:346-358 clean, :380-408 noisy).  The random
+ * decisions are drawn on the host in the reference's order; each output row r is
+ *   tok[r] <  0 : all zeros (padding, :403-408)
+ *   else        : base[r] everywhere, hot[r] at column tok[r]
+ * written to out + dst_row[r]*out_row_stride (dst_row NULL → r).  Optional LayerNorm stats.
+ */
+int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, const float* base,
+                            const int64_t* dst_row, int64_t n_rows, int V,
+                            void* out, int out_dtype, int64_t out_row_stride,
+                            float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 3 helpers — operand preparation for the tensor-core GEMMs.
+ * tasu_cast_rows: [rows, cols] src → dst (dtype conversion, arbitrary row strides) with optional
+ *   per-row LayerNorm statistics (the generic A-operand producer for projector.py:150).
+ * tasu_fold_layernorm: W1g[n,k] = bf16(W1[n,k]*gamma[k]); colsum[n] = sum_k W1g[n,k];
+ *   dbias[n] = sum_k W1[n,k]*beta[k] + b1[n]  — folds nn.LayerNorm (projector.py:139) into
+ *   nn.Linear (projector.py:141) so GEMM-1 runs directly on the pooled posterior.
+ */
+int tasu_cast_rows(const void* src, int src_dtype, int64_t rows, int cols, int64_t src_stride,
+                   void* dst, int dst_dtype, int64_t dst_stride,
+                   float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+int tasu_fold_layernorm(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                        const float* b1, int N, int K, void* w1g_bf16, int64_t w1g_stride,
+                        float* colsum, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 3 — C[M,N] = epilogue(A[M,K] · B[N,K]^T), bf16 operands (both K-major), fp32
+ * accumulation in TMEM, tcgen05.mma fed by TMA, persistent over 148 SMs.  Replaces
+ * ctc_lo (ps-slm.py:450,581), nn.Linear(25055,2048)+SiLU and nn.Linear(2048,1536)
+ * (projector.py:141-143), the Linear/ReLU of projector.py:35-37 and :16.
+ *   lda/ldb/ldc in elements; A, B and C base pointers and row pitches must be 16-byte aligned.
+ *   bias [N] fp32 (EPI_BIAS*, LNFOLD), row_rstd/row_mean [M] and colsum [N] (LNFOLD only).
+ */
+int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
+                      void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
+                      const float* bias, const float* row_rstd, const float* row_mean,
+                      const float* colsum, void* stream);
+/* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
+int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
+                           void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
+                           const float* bias, const float* row_rstd, const float* row_mean,
+                           const float* colsum, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.
+ *   input_ids [B,S] int64; attention_mask [B,S] uint8/bool (mask_dtype 0) or int64 (1);
+ *   num_audio [n_audio] int64 (compressed lengths), divided by div_k on device
+ *   (projector_feature_length = len // k, ps-slm.py:483).
+ * tasu_splice_rowstat : per-row counts                                   (:771-772, :788-789)
+ * tasu_splice_plan    : placeholders, cumsum, per-token slot ordinals    (:805-812, :842-859)
+ * tasu_splice_header  : S', padding side, error words, per-row bases     (:809, :861)
+ * tasu_splice_scatter : writes inputs_embeds / mask / labels / position_ids / final ids
+ *                       (:821-840, :867-871); text rows come from `text_src`:
+ *                       text_mode 0 = inputs_embeds [B,S,H]; 1 = embedding table indexed by
+ *                       token id (fuses embed_tokens, ps-slm.py:525,654).
+ *   audio rows: audio_layout 0 = packed [sum M, H]; 1 = padded [n_audio, audio_max_len, H].
+ */
+int tasu_splice_rowstat(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                        int B, int S, int64_t speech_id, int32_t* rowstat /*[B,8]*/, void* stream);
+int tasu_splice_plan(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                     int B, int S, int64_t speech_id, const int64_t* num_audio, int n_audio,
+                     int64_t div_k, int32_t* rowstat, int32_t* new_pos /*[B,S]*/,
+                     int32_t* text_prefix /*[B,S]*/, int32_t* slot_ord /*[B,S]*/, void* stream);
+int tasu_splice_header(const int32_t* rowstat, const int64_t* num_audio, int n_audio, int64_t div_k,
+                       int B, int S, int64_t* header /*[TASU_SH_WORDS]*/, int32_t* slot_base /*[B]*/,
+                       int32_t* audio_off /*[n_audio+1]*/, void* stream);
+int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                        const int64_t* labels, int B, int S, int spliced_len, int H, int64_t speech_id,
+                        const void* text_src, int text_mode, int64_t text_row_stride,
+                        const void* audio_rows, int audio_layout, int64_t audio_row_stride,
+                        int64_t audio_max_len, int n_audio, int emb_dtype,
+                        const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
+                        const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
+                        const int64_t* header, int64_t pad_id, int64_t ignore_id,
+                        void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
+                        int64_t* out_ids, void* stream);
+/* backward of the audio part of the splice: grad_audio[a,:] = grad_emb[slot(a),:] (training) */
+int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const int64_t* input_ids,
+                           const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
+                           int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
+                           const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
+                           const int32_t* audio_off, const int64_t* header, int audio_layout,
+                           int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
+                           void* grad_audio, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TASU_BRIDGE_H_ */

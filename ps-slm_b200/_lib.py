@@ -1,0 +1,87 @@
+"""ctypes binding of libtasu_bridge.so (the C ABI declared in include/tasu_bridge.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails the
+caller gets an exception, never a silent PyTorch/CPU substitute.
+"""
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtasu_bridge.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+TASU_OK = 0
+F32, BF16 = 0, 1
+INPUT_PROBS, INPUT_LOGITS = 0, 1
+EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU = 0, 1, 2, 3, 4
+SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
+CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_WORDS = 0, 1, 2, 4
+
+# name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+SIGNATURES = {
+    "tasu_abi_version": (_I, []),
+    "tasu_last_error": (c_char_p, []),
+    "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "tasu_collapse_scan": (_I, [_P, _P, _I, _P, _P, _P]),
+    "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
+    "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_gemm_bf16_tn_simt": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_splice_rowstat": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
+    "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
+    "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),
+    "tasu_splice_scatter": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _L, _L, _I, _I,
+                                 _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
+    "tasu_splice_audio_grad": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P,
+                                    _I, _L, _L, _I, _P, _P]),
+}
+
+_lib = None
+
+
+class TasuError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libtasu_bridge.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-j8", "-C", CSRC_DIR], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise TasuError("building libtasu_bridge.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library (once). Raises TasuError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise TasuError(
+            "libtasu_bridge.so not found at %s — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU/PyTorch fallback for the bridge path)" % LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)          # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    if handle.tasu_abi_version() != 1:
+        raise TasuError("libtasu_bridge.so ABI version mismatch")
+    _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != TASU_OK:
+        msg = lib().tasu_last_error()
+        raise TasuError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))

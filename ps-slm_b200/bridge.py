@@ -1,0 +1,213 @@
+"""Host side of the bridge: the reference's method-level API on top of the C ABI.
+
+Function names, argument meaning, return tuples and error behaviour mirror
+``slam_model_asr`` in Multitask/model/ps-slm.py (paths relative to /root/reference/):
+
+* ``psd``                                   ← ps-slm.py:237-317
+* ``merge_input_ids_with_audio_features``   ← ps-slm.py:679-873
+* ``ctc_head_psd_project_splice`` (class ``TasuBridge``) ← the dispatch of
+  ps-slm.py:581-658 with the shipped inference flags (ctc_posterior, do_psd,
+  linear-silu projector), fused so that the [B,T,25055] posterior is never
+  materialised and the host reads back exactly one 96-byte header per batch.
+
+Everything here is tensor plumbing; the arithmetic lives in libtasu_bridge.so.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+BLANK_THRESHOLD = 0.90
+
+
+def _as_compute(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype in (torch.float32, torch.bfloat16):
+        return x
+    return x.float()
+
+
+def psd(encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, ctc_posterior: torch.Tensor,
+        blank_id: int = 0, blank_threshold: float = BLANK_THRESHOLD) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for ``slam_model_asr.psd`` (ps-slm.py:237-317).
+
+    Returns ``(encoder_outs [B, max_b M_b, D], new_lens [B] int64 on device)``; padded rows
+    are zeros; all-empty input gives ``[B, 0, D]`` (ps-slm.py:304-306).  One device→host
+    read (the 32-byte collapse header) instead of the reference's O(B·T) syncs."""
+    encoder_out = _as_compute(encoder_out)
+    ctc_posterior = _as_compute(ctc_posterior)
+    B, T, D = encoder_out.shape
+    if ctc_posterior.shape[0] != B or ctc_posterior.shape[1] != T:
+        raise ValueError("encoder_out and ctc_posterior must agree on [B, T]")
+    lens = encoder_out_lens.to(device=encoder_out.device, dtype=torch.int64)
+    st = ops.frame_stats(ctc_posterior, L.INPUT_PROBS, blank_id)
+    plan = ops.collapse_plan(st, lens, blank_id, blank_threshold)
+    hdr = plan.header.cpu()
+    max_len = int(hdr[L.CH_MAX_LEN])
+    if max_len == 0:
+        return encoder_out.new_zeros(B, 0, D), torch.zeros(B, dtype=torch.long, device=encoder_out.device)
+    out = torch.empty(B, max_len, D, dtype=encoder_out.dtype, device=encoder_out.device)
+    ops.segment_meanpool(encoder_out, plan, 1, max_len, B * max_len, out, D)
+    return out, plan.new_lens
+
+
+def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_tokens: torch.Tensor,
+                                        inputs_embeds: torch.Tensor, input_ids: torch.Tensor,
+                                        attention_mask: torch.Tensor, labels: Optional[torch.Tensor],
+                                        speech_id: int, pad_id: int, ignore_id: int = -100):
+    """Drop-in for ``slam_model_asr._merge_input_ids_with_audio_features`` (ps-slm.py:679-873).
+
+    Same 5-tuple ``(final_embedding, final_attention_mask, final_labels|None, position_ids,
+    final_input_ids)`` and the same two ``ValueError``s (:783-785, :861-865)."""
+    if audio_features.dim() != 3:
+        raise ValueError("audio_features must be [num_audios, max_audio_tokens, embed_dim]")
+    if audio_features.dtype != inputs_embeds.dtype:
+        audio_features = audio_features.to(inputs_embeds.dtype)
+    p = ops.splice_rowstat(input_ids, attention_mask, speech_id)
+    ops.splice_plan(p, num_audio_tokens, 1)
+    hdr = p.header.cpu()
+    _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
+    return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds, 0, audio_features, 1,
+                              audio_features.shape[1], labels, pad_id, ignore_id)
+
+
+def _raise_splice_errors(hdr, attention_mask, num_audios):
+    if int(hdr[L.SH_ERR_BOTH_SIDES]):
+        raise ValueError(f"both side of attention_mask has zero, invalid. {attention_mask}")
+    if int(hdr[L.SH_N_SPEECH]) != num_audios and num_audios != 1:
+        raise ValueError("shape mismatch: %d <speech> tokens for %d audios" % (int(hdr[L.SH_N_SPEECH]), num_audios))
+    if int(hdr[L.SH_TOTAL_SLOTS]) != int(hdr[L.SH_TOTAL_AUDIO]):
+        raise ValueError(
+            f"The input provided to the model are wrong. The number of audio tokens is {int(hdr[L.SH_N_SPEECH])} while"
+            f" the number of audio given to the model is {num_audios}. This prevents correct indexing and breaks batch generation.")
+
+
+class ProjectorCache:
+    """bf16 / folded copies of the projector weights, rebuilt only when a parameter changes
+    (tracked through torch's per-tensor version counter, so optimizer steps are seen)."""
+
+    def __init__(self):
+        self._key = None
+        self.data = None
+
+    def get(self, params, builder):
+        key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params if p is not None)
+        if key != self._key:
+            self.data = builder()
+            self._key = key
+        return self.data
+
+
+def cast_weight_bf16(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] weight → bf16 with a 64-element-padded pitch (zero padded)."""
+    N, K = w.shape
+    ld = ops.pad_to(K)
+    if ld == K:
+        out, _, _ = ops.cast_rows(w.detach(), torch.bfloat16)
+        return out
+    out = torch.zeros(N, ld, dtype=torch.bfloat16, device=w.device)
+    tmp, _, _ = ops.cast_rows(w.detach(), torch.bfloat16)
+    out[:, :K] = tmp
+    return out
+
+
+def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Tensor, rstd: torch.Tensor,
+                        w1g: torch.Tensor, colsum: torch.Tensor, dbias: torch.Tensor, w2: torch.Tensor,
+                        b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False) -> torch.Tensor:
+    """LayerNorm → Linear → SiLU → Linear of projector.py:149-151 as two tensor-core GEMMs:
+    GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue."""
+    Hb, H = w1g.shape[0], w2.shape[0]
+    dev = x_bf16.device
+    h1 = torch.empty(rows, Hb, dtype=torch.bfloat16, device=dev)
+    ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt)
+    y = torch.empty(rows, H, dtype=out_dtype, device=dev)
+    ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt)
+    return y
+
+
+class TasuBridge:
+    """Fused inference bridge: encoder output → inputs_embeds.
+
+    ``raw_encoder_out [B, T+4, 512]`` → ctc_lo GEMM (tcgen05) → per-frame softmax stats /
+    argmax → collapse plan → splice plan → ONE header read-back → softmax + segmented
+    mean-pool of the kept frames (bf16, LayerNorm stats fused) → LN-folded GEMM-1 + SiLU →
+    GEMM-2 → gather/scatter splice with the embed_tokens lookup fused.
+    Restates the dispatch of ps-slm.py:581-658 for ctc_posterior=True, voca_trans=False,
+    gt_emb=False, do_psd=True, encoder_projector='linear-silu'."""
+
+    N_PREFIX = 4     # language / event / emotion / textnorm query frames (ps-slm.py:442-443,452-454)
+
+    def __init__(self, w_ctc: torch.Tensor, b_ctc: Optional[torch.Tensor], projector, embed_table: torch.Tensor,
+                 speech_id: int, pad_id: int, ignore_id: int = -100, blank_id: int = 0,
+                 blank_threshold: float = BLANK_THRESHOLD, ln_eps: float = 1e-5):
+        self.w_ctc, self.b_ctc = w_ctc, b_ctc
+        self.projector = projector
+        self.embed_table = embed_table
+        self.speech_id, self.pad_id, self.ignore_id = int(speech_id), int(pad_id), int(ignore_id)
+        self.blank_id, self.blank_threshold, self.ln_eps = int(blank_id), float(blank_threshold), float(ln_eps)
+        self._ctc_cache = ProjectorCache()
+        self.last_counts = {}
+
+    def _ctc_weights(self):
+        def build():
+            w = cast_weight_bf16(self.w_ctc)
+            b = (self.b_ctc.detach().float().contiguous() if self.b_ctc is not None
+                 else torch.zeros(self.w_ctc.shape[0], dtype=torch.float32, device=self.w_ctc.device))
+            return w, b
+        return self._ctc_cache.get([self.w_ctc, self.b_ctc], build)
+
+    @torch.no_grad()
+    def __call__(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor,
+                 input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                 want_ids: bool = False):
+        B, T4, Denc = raw_encoder_out.shape
+        T = T4 - self.N_PREFIX
+        V = self.w_ctc.shape[0]
+        dev = raw_encoder_out.device
+        w_ctc, b_ctc = self._ctc_weights()
+        w1g, colsum, dbias, w2, b2 = self.projector.folded_weights()
+        out_dtype = self.embed_table.dtype
+
+        # splice row statistics only depend on the prompt: issue them first
+        sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
+
+        # (a1) ctc_lo on the tensor cores: logits [B*(T+4), ldv] fp32
+        x2 = raw_encoder_out.reshape(B * T4, Denc)
+        if x2.dtype != torch.bfloat16:
+            x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+        ldv = ops.pad_to(V, 4)
+        logits = torch.empty(B * T4, ldv, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(x2, w_ctc, B * T4, V, Denc, logits, L.EPI_BIAS, b_ctc)
+        lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
+        post_view = logits.view(B, T4, ldv)[:, self.N_PREFIX:, :V]      # ps-slm.py:583 (logits, not probs)
+
+        # (a2) stats + collapse plan, (a8) splice plan; one header for both
+        header = torch.empty(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64, device=dev)
+        st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
+        plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
+        ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
+        hdr = header.cpu()                                              # the single device→host read
+        n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
+        shdr = hdr[L.CH_WORDS:]
+        _raise_splice_errors(shdr, attention_mask, B)
+        spliced_len = int(shdr[L.SH_SPLICED_LEN])
+
+        # (a2) softmax + segmented mean-pool of the kept frames → packed bf16 rows + LN stats
+        ldk = ops.pad_to(V)
+        if n_out > 0:
+            pooled = torch.empty(n_out, ldk, dtype=torch.bfloat16, device=dev)
+            mean = torch.empty(n_out, dtype=torch.float32, device=dev)
+            rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
+            ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
+                                 ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
+            # (a5) projector
+            audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype)
+        else:
+            audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
+        # (a7+a8) splice with the embedding lookup fused
+        emb, mask, out_labels, pos, fids = ops.splice_scatter(
+            sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
+            want_ids=want_ids)
+        self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len}
+        return emb, mask, out_labels, pos, plan.new_lens

@@ -1,0 +1,443 @@
+// Step 3: C[M,N] = epilogue(A[M,K] · B[N,K]^T) on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces cuBLAS addmm at Multitask/model/ps-slm.py:450,581 (ctc_lo, K=512, N=25055) and
+// Multitask/model/projector.py:141-143 (Linear(25055,2048)+SiLU with the LayerNorm of :139
+// folded into the epilogue, Linear(2048,1536)), :35-37 and :16.
+//
+// Design (hand-written, no CUTLASS):
+//   * persistent: one CTA per SM, static round-robin over 128x256 output tiles, n fastest so
+//     the CTAs running at the same time share A tiles and stream the same weight K-slices in L2;
+//   * warp 0 = TMA producer (cp.async.bulk.tensor 2D, 128B swizzle, OOB zero-fill handles the
+//     ragged M, N=25055 and K=25055 edges), 4-stage mbarrier ring of {A 128x64, B 256x64} bf16;
+//   * warp 1 = MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//     (M=128, N=256, K=16) from shared-memory descriptors, accumulating fp32 in TMEM;
+//     tcgen05.commit releases smem stages and publishes finished accumulators;
+//   * TMEM holds two 128x256 fp32 accumulators (all 512 columns) so the epilogue of tile i
+//     overlaps the main loop of tile i+1;
+//   * warps 4-7 = epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / SiLU / ReLU /
+//     LayerNorm-fold math in registers, swizzled st.shared into a 128-byte-wide staging tile,
+//     TMA store (clips the ragged edges) double-buffered against the next chunk.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace tasu {
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BK = 64;          // bf16: BK*2 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 256;                        // warps 0-3 control, warps 4-7 epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kABytes = BM * BK * 2;                 // 16 KB
+constexpr int kBBytes = BN * BK * 2;                 // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
+constexpr int kStagingBytes = BM * 128;              // one 128-byte-wide column chunk of the C tile
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 UMMA format):
+// bits [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024 B
+// between 8-row groups, [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+
+struct Params {
+    int M, N, K;
+    int epilogue;
+    const float* bias;
+    const float* row_rstd;
+    const float* row_mean;
+    const float* colsum;
+};
+
+// kOutBf16: C is bf16 (64 columns per 128-byte staging row) else fp32 (32 columns)
+template <bool kOutBf16>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* staging = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+    uint64_t* full_bar = bars;                           // [kStages]
+    uint64_t* empty_bar = bars + kStages;                // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages;            // [kAccStages]
+    uint64_t* tmem_empty = bars + 2 * kStages + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {   // whole warp allocates all 512 TMEM columns (1 CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    mbar_expect_tx(&full_bar[stage], kStageBytes);
+                    tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                    tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                                   // TMEM lanes [32*ew, 32*ew+32)
+        const int row_in_tile = ew * 32 + lane;
+        constexpr int kColsPerChunk = kOutBf16 ? 64 : 32;          // 128 bytes of C per row
+        constexpr int kChunks = BN / kColsPerChunk;
+        int acc = 0; uint32_t acc_phase = 0;
+        int sbuf = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            const int grow = m0 + row_in_tile;
+            float rstd = 1.f, mean = 0.f;
+            if (p.epilogue == TASU_EPI_LNFOLD_SILU && grow < p.M) { rstd = p.row_rstd[grow]; mean = p.row_mean[grow]; }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int ch = 0; ch < kChunks; ++ch) {
+                const int c0 = n0 + ch * kColsPerChunk;
+                if (c0 >= p.N) break;                               // warp-uniform: fully clipped chunk
+                uint8_t* stg = staging + sbuf * kStagingBytes;
+                // the TMA store that last read this staging buffer must have finished reading
+                if (threadIdx.x == kThreads - kEpiThreads) tma_store_wait_read<1>();
+                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                uint8_t* srow = stg + row_in_tile * 128;
+                const int sw = row_in_tile & 7;
+#pragma unroll
+                for (int h = 0; h < kColsPerChunk / 32; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(ch * kColsPerChunk + h * 32), v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(v[i]);
+                        const int col = c0 + h * 32 + i;
+                        const bool ok = col < p.N;
+                        if (p.epilogue == TASU_EPI_LNFOLD_SILU) {
+                            const float cs = ok ? __ldg(p.colsum + col) : 0.f;
+                            const float bb = ok ? __ldg(p.bias + col) : 0.f;
+                            x = silu_f(fmaf(rstd, x - mean * cs, bb));
+                        } else if (p.epilogue != TASU_EPI_NONE) {
+                            x += ok ? __ldg(p.bias + col) : 0.f;
+                            if (p.epilogue == TASU_EPI_BIAS_SILU) x = silu_f(x);
+                            else if (p.epilogue == TASU_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
+                        }
+                        f[i] = x;
+                    }
+                    if (kOutBf16) {
+                        // 32 columns → 64 bytes → 16-byte pieces 4h .. 4h+3 of the 128-byte row
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int piece = (h * 4 + q) ^ sw;
+                            uint4 o = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                                 pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+                            *reinterpret_cast<uint4*>(srow + piece * 16) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int piece = q ^ sw;
+                            uint4 o = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                                 __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+                            *reinterpret_cast<uint4*>(srow + piece * 16) = o;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                if (threadIdx.x == kThreads - kEpiThreads) {
+                    tma_store_2d(&tmap_c, stg, c0, m0);
+                    tma_store_commit();
+                }
+                sbuf ^= 1;
+            }
+            // all tcgen05.ld of this accumulator are complete → hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+        if (threadIdx.x == kThreads - kEpiThreads) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ CUDA-core cross-check
+template <typename TC>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
+                 TC* __restrict__ C, int64_t ldc, Params p) {
+    __shared__ float sa[16][17], sb[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        const int am = blockIdx.y * 16 + ty, bn = blockIdx.x * 16 + ty, kk = k0 + tx;
+        sa[ty][tx] = (am < p.M && kk < p.K) ? __bfloat162float(A[(int64_t)am * lda + kk]) : 0.f;
+        sb[ty][tx] = (bn < p.N && kk < p.K) ? __bfloat162float(B[(int64_t)bn * ldb + kk]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
+        __syncthreads();
+    }
+    if (m < p.M && n < p.N) {
+        float x = acc;
+        if (p.epilogue == TASU_EPI_LNFOLD_SILU) x = silu_f(fmaf(p.row_rstd[m], x - p.row_mean[m] * p.colsum[n], p.bias[n]));
+        else if (p.epilogue != TASU_EPI_NONE) {
+            x += p.bias[n];
+            if (p.epilogue == TASU_EPI_BIAS_SILU) x = silu_f(x);
+            else if (p.epilogue == TASU_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
+        }
+        C[(int64_t)m * ldc + n] = from_f32<TC>(x);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols], 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esz, int64_t rows, int64_t cols,
+                    int64_t ld, int box_rows, int box_cols, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TASU_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TASU_ERR_CUDA; }
+    return TASU_OK;
+}
+
+static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype, int64_t ldc,
+                        int M, int N, int K, int epilogue, const float* bias, const float* row_rstd,
+                        const float* row_mean, const float* colsum) {
+    TASU_CHECK_ARG(M >= 0 && N > 0 && K > 0, "M >= 0, N,K > 0");
+    TASU_CHECK_ARG(c_dtype == TASU_F32 || c_dtype == TASU_BF16, "c_dtype");
+    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_LNFOLD_SILU, "epilogue");
+    TASU_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
+    if (M == 0) return TASU_OK;
+    TASU_CHECK_ARG(A && B && C, "null pointer");
+    TASU_CHECK_ARG(epilogue == TASU_EPI_NONE || bias, "bias required");
+    TASU_CHECK_ARG(epilogue != TASU_EPI_LNFOLD_SILU || (row_rstd && row_mean && colsum), "LN-fold vectors required");
+    return TASU_OK;
+}
+
+}  // namespace gemm
+}  // namespace tasu
+
+using namespace tasu;
+using namespace tasu::gemm;
+
+extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
+                                 int64_t ldc, int M, int N, int K, int epilogue, const float* bias,
+                                 const float* row_rstd, const float* row_mean, const float* colsum, void* stream) {
+    int rc = check_common(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, row_rstd, row_mean, colsum);
+    if (rc != TASU_OK || M == 0) return rc;
+    const int csz = c_dtype == TASU_F32 ? 4 : 2;
+    TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
+    TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
+    CUtensorMap ma, mb, mc;
+    rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    rc = make_map(&mc, C, c_dtype == TASU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, csz,
+                  M, N, ldc, BM, c_dtype == TASU_F32 ? 32 : 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    Params p{M, N, K, epilogue, bias, row_rstd, row_mean, colsum};
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    });
+    TASU_CHECK_CUDA(attr_err);
+    if (c_dtype == TASU_BF16) gemm_bf16_tn_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
+    else gemm_bf16_tn_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
+                                      int64_t ldc, int M, int N, int K, int epilogue, const float* bias,
+                                      const float* row_rstd, const float* row_mean, const float* colsum, void* stream) {
+    int rc = check_common(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, row_rstd, row_mean, colsum);
+    if (rc != TASU_OK || M == 0) return rc;
+    Params p{M, N, K, epilogue, bias, row_rstd, row_mean, colsum};
+    dim3 grid((N + 15) / 16, (M + 15) / 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c_dtype == TASU_F32)
+        gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (float*)C, ldc, p);
+    else
+        gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (__nv_bfloat16*)C, ldc, p);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -1,0 +1,162 @@
+// Operand producers for the projector GEMMs and the simulated-posterior constructor.
+//  * cast_rows        generic [rows, cols] dtype conversion (+ LayerNorm statistics per row):
+//                     the A-operand producer for EncoderProjectorLinearSiLU (projector.py:150)
+//  * fold_layernorm   W1g = bf16(W1 * gamma), colsum, dbias: folds nn.LayerNorm(25055)
+//                     (projector.py:139) into nn.Linear(25055, 2048) (projector.py:141)
+//  * sim_posterior    rows (1-alpha)*onehot + alpha/V / hard blank / zero pad
+//                     (ps-slm.py:346-358, :380-408) written straight in HBM.
+#include "common.cuh"
+
+namespace tasu {
+
+template <typename Ti, typename To>
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const Ti* __restrict__ src, int64_t rows, int cols, int64_t sstride, To* __restrict__ dst,
+                 int64_t dstride, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
+    __shared__ float red[2][8];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const Ti* s = src + r * sstride;
+        To* d = dst + r * dstride;
+        float acc_s = 0.f, acc_q = 0.f;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+            const float v = to_f32(s[c]);
+            acc_s += v;
+            acc_q += v * v;
+            d[c] = from_f32<To>(v);
+        }
+        if (ln_mean != nullptr) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            acc_s = warp_sum(acc_s);
+            acc_q = warp_sum(acc_q);
+            __syncthreads();
+            if (lane == 0) { red[0][warp] = acc_s; red[1][warp] = acc_q; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float sm = 0.f, q = 0.f;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sm += red[0][w]; q += red[1][w]; }
+                const float mean = sm / (float)cols;
+                float var = q / (float)cols - mean * mean;
+                var = var < 0.f ? 0.f : var;
+                ln_mean[r] = mean;
+                ln_rstd[r] = rsqrtf(var + eps);
+            }
+        }
+    }
+}
+
+// one CTA per output feature n (row of W1)
+__global__ void __launch_bounds__(256)
+fold_layernorm_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ b1, int K,
+                      __nv_bfloat16* __restrict__ w1g, int64_t gstride, float* __restrict__ colsum,
+                      float* __restrict__ dbias) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    const float* w = w1 + (int64_t)n * wstride;
+    __nv_bfloat16* g = w1g + (int64_t)n * gstride;
+    float cs = 0.f, db = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float wv = w[k];
+        const __nv_bfloat16 q = __float2bfloat16_rn(wv * gamma[k]);
+        g[k] = q;
+        cs += __bfloat162float(q);            // sum of the ROUNDED values: what the tensor core multiplies
+        db += wv * beta[k];
+    }
+    // zero the pitch padding so a K-padded TMA box never sees garbage
+    for (int64_t k = K + threadIdx.x; k < gstride; k += blockDim.x) g[k] = __float2bfloat16_rn(0.f);
+    cs = block_sum_f(cs, red);
+    db = block_sum_f(db, red);
+    if (threadIdx.x == 0) {
+        colsum[n] = cs;
+        dbias[n] = db + (b1 ? b1[n] : 0.f);
+    }
+}
+
+template <typename To>
+__global__ void __launch_bounds__(256)
+sim_rows_kernel(const int32_t* __restrict__ tok, const float* __restrict__ hot, const float* __restrict__ base,
+                const int64_t* __restrict__ dst_row, int64_t n_rows, int V, To* __restrict__ out, int64_t ostride,
+                float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int id = tok[r];
+        const float bv = id < 0 ? 0.f : base[r];
+        const float hv = id < 0 ? 0.f : hot[r];
+        const int64_t dr = dst_row ? dst_row[r] : r;
+        To* o = out + dr * ostride;
+        const To bq = from_f32<To>(bv);
+        for (int c = threadIdx.x; c < V; c += blockDim.x) o[c] = (c == id) ? from_f32<To>(hv) : bq;
+        if (ln_mean != nullptr && threadIdx.x == 0) {
+            // closed form: one element hv, V-1 elements bv (double: no cancellation issues)
+            const double s = (id < 0) ? 0.0 : (double)hv + (double)(V - 1) * (double)bv;
+            const double q = (id < 0) ? 0.0 : (double)hv * hv + (double)(V - 1) * (double)bv * bv;
+            const double mean = s / V;
+            double var = q / V - mean * mean;
+            var = var < 0 ? 0 : var;
+            ln_mean[dr] = (float)mean;
+            ln_rstd[dr] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+}
+
+}  // namespace tasu
+
+using namespace tasu;
+
+static unsigned row_grid(int64_t rows) {
+    int64_t g = (int64_t)tasu::sm_count() * 8;
+    if (g > rows) g = rows;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+extern "C" int tasu_cast_rows(const void* src, int src_dtype, int64_t rows, int cols, int64_t src_stride,
+                              void* dst, int dst_dtype, int64_t dst_stride, float* ln_mean, float* ln_rstd,
+                              float ln_eps, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && cols > 0, "rows >= 0, cols > 0");
+    TASU_CHECK_ARG(src_dtype == TASU_F32 || src_dtype == TASU_BF16, "src_dtype");
+    TASU_CHECK_ARG(dst_dtype == TASU_F32 || dst_dtype == TASU_BF16, "dst_dtype");
+    TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && dst, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = row_grid(rows);
+#define LAUNCH(TI, TO) cast_rows_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, rows, cols, src_stride, (TO*)dst, dst_stride, ln_mean, ln_rstd, ln_eps)
+    if (src_dtype == TASU_F32 && dst_dtype == TASU_BF16) LAUNCH(float, __nv_bfloat16);
+    else if (src_dtype == TASU_F32) LAUNCH(float, float);
+    else if (dst_dtype == TASU_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else LAUNCH(__nv_bfloat16, float);
+#undef LAUNCH
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_fold_layernorm(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                                   const float* b1, int N, int K, void* w1g_bf16, int64_t w1g_stride,
+                                   float* colsum, float* dbias, void* stream) {
+    TASU_CHECK_ARG(N > 0 && K > 0, "N,K > 0");
+    TASU_CHECK_ARG(w1 && gamma && beta && w1g_bf16 && colsum && dbias, "null pointer");
+    TASU_CHECK_ARG(w1g_stride >= K && w1_stride >= K, "stride < K");
+    fold_layernorm_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(w1, w1_stride, gamma, beta, b1, K,
+                                                              (__nv_bfloat16*)w1g_bf16, w1g_stride, colsum, dbias);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, const float* base,
+                                       const int64_t* dst_row, int64_t n_rows, int V, void* out, int out_dtype,
+                                       int64_t out_row_stride, float* ln_mean, float* ln_rstd, float ln_eps,
+                                       void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && V > 0, "n_rows >= 0, V > 0");
+    TASU_CHECK_ARG(out_dtype == TASU_F32 || out_dtype == TASU_BF16, "out_dtype");
+    TASU_CHECK_ARG(out_row_stride >= V, "out_row_stride < V");
+    TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
+    if (n_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(tok && hot && base && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = row_grid(n_rows);
+    if (out_dtype == TASU_F32)
+        sim_rows_kernel<float><<<grid, 256, 0, st>>>(tok, hot, base, dst_row, n_rows, V, (float*)out, out_row_stride, ln_mean, ln_rstd, ln_eps);
+    else
+        sim_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tok, hot, base, dst_row, n_rows, V, (__nv_bfloat16*)out, out_row_stride, ln_mean, ln_rstd, ln_eps);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -1,0 +1,453 @@
+// Step 4: splice compressed audio embeddings into the prompt-token embeddings —
+// Multitask/model/ps-slm.py:765-871 (_merge_input_ids_with_audio_features), with the
+// embed_tokens gather of ps-slm.py:525,654 optionally fused.
+//
+// The reference plans with ~25 ATen calls and ≥5 host syncs and then makes three full passes
+// over [B, S', H].  Here: three tiny integer kernels produce per-TOKEN tables (new position,
+// number of text tokens before it, number of audio slots before it) from which every
+// destination row finds its source with one binary search, and ONE vectorised gather/scatter
+// pass writes embeddings, mask, labels, position ids and final ids.
+//
+// Token j of row b owns the destination range (new_pos[j-1], new_pos[j]] (length = its
+// placeholder count, :805-808).  Text tokens (not <speech>, mask == 1, :797-799) own exactly one
+// position and are copied there (:833-840).  Every other position is an audio slot iff it lies
+// in the non-pad span (:842-859); slots are numbered row-major over the batch (:867-869).
+#include "common.cuh"
+
+namespace tasu {
+
+enum { RS_NSPEECH = 0, RS_NPAD = 1, RS_FIRST0 = 2, RS_LAST0 = 3, RS_NTEXT = 4, RS_TOT = 5, RS_SLOTS = 6, RS_WORDS = 8 };
+
+__device__ __forceinline__ int mask_at(const void* m, int dtype, int64_t i) {
+    // returns 1 for ==1, 0 for ==0, 2 for anything else (neither text nor pad in the reference)
+    if (dtype == 0) { const uint8_t v = reinterpret_cast<const uint8_t*>(m)[i]; return v == 0 ? 0 : 1; }
+    const int64_t v = reinterpret_cast<const int64_t*>(m)[i];
+    return v == 0 ? 0 : (v == 1 ? 1 : 2);
+}
+
+__global__ void __launch_bounds__(256)
+splice_rowstat_kernel(const int64_t* __restrict__ ids, const void* __restrict__ mask, int mdt, int S,
+                      int64_t speech, int32_t* __restrict__ rowstat) {
+    __shared__ int scratch[33];
+    const int b = blockIdx.x;
+    int nsp = 0, npad = 0, ntext = 0;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const int64_t i = (int64_t)b * S + j;
+        const bool sp = ids[i] == speech;
+        const int m = mask_at(mask, mdt, i);
+        nsp += sp;
+        npad += (m == 0);
+        ntext += (!sp && m == 1);
+    }
+    nsp = block_sum_i(nsp, scratch);
+    npad = block_sum_i(npad, scratch);
+    ntext = block_sum_i(ntext, scratch);
+    if (threadIdx.x == 0) {
+        int32_t* rs = rowstat + (int64_t)b * RS_WORDS;
+        rs[RS_NSPEECH] = nsp;
+        rs[RS_NPAD] = npad;
+        rs[RS_FIRST0] = S > 0 ? (mask_at(mask, mdt, (int64_t)b * S) == 0) : 0;
+        rs[RS_LAST0] = S > 0 ? (mask_at(mask, mdt, (int64_t)b * S + S - 1) == 0) : 0;
+        rs[RS_NTEXT] = ntext;
+        rs[RS_TOT] = 0; rs[RS_SLOTS] = 0; rs[7] = 0;
+    }
+}
+
+// padding side of the whole batch (ps-slm.py:771-785); both sides → treated as left, error flagged by header
+__device__ __forceinline__ bool batch_left_padding(const int32_t* __restrict__ rowstat, int B, int* scratch, bool* both) {
+    int l = 0, r = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        l |= rowstat[(int64_t)i * RS_WORDS + RS_FIRST0];
+        r |= rowstat[(int64_t)i * RS_WORDS + RS_LAST0];
+    }
+    l = block_max_i(l, scratch);
+    r = block_max_i(r, scratch);
+    bool left = true;
+    *both = false;
+    if (B > 1) {
+        if (l && r) *both = true;
+        else if (!l && r) left = false;
+    }
+    return left;
+}
+
+__global__ void __launch_bounds__(256)
+splice_plan_kernel(const int64_t* __restrict__ ids, const void* __restrict__ mask, int mdt, int B, int S,
+                   int64_t speech, const int64_t* __restrict__ num_audio, int n_audio, int64_t div_k,
+                   int32_t* __restrict__ rowstat, int32_t* __restrict__ new_pos, int32_t* __restrict__ text_prefix,
+                   int32_t* __restrict__ slot_ord) {
+    __shared__ int scratch[33];
+    const int b = blockIdx.x;
+    bool both;
+    const bool left = batch_left_padding(rowstat, B, scratch, &both);
+    // global ordinal of this row's first <speech> token (row-major mask assignment, :806)
+    int base = 0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) base += rowstat[(int64_t)i * RS_WORDS + RS_NSPEECH];
+    base = block_sum_i(base, scratch);
+    const int n_pad = rowstat[(int64_t)b * RS_WORDS + RS_NPAD];
+
+    // pass 1: placeholders → inclusive cumsum - 1, text prefix
+    int c_sp = 0, c_ph = 0, c_tx = 0;
+    for (int j0 = 0; j0 < S; j0 += blockDim.x) {
+        const int j = j0 + threadIdx.x;
+        int sp = 0, tx = 0;
+        if (j < S) {
+            const int64_t i = (int64_t)b * S + j;
+            sp = ids[i] == speech;
+            tx = (!sp && mask_at(mask, mdt, i) == 1);
+        }
+        int tot_sp, tot_tx, tot_ph;
+        const int e_sp = block_excl_scan_i(sp, scratch, &tot_sp);
+        const int e_tx = block_excl_scan_i(tx, scratch, &tot_tx);
+        int ph = 0;
+        if (j < S) {
+            ph = 1;
+            if (sp) {
+                const int ord = base + c_sp + e_sp;
+                int64_t m = 0;
+                if (n_audio == 1) m = num_audio[0];
+                else if (ord < n_audio) m = num_audio[ord];
+                m = m / div_k;
+                ph = (int)(m < 0 ? 0 : m);
+            }
+        }
+        const int e_ph = block_excl_scan_i(ph, scratch, &tot_ph);
+        if (j < S) {
+            const int64_t i = (int64_t)b * S + j;
+            new_pos[i] = c_ph + e_ph + ph - 1;
+            text_prefix[i] = c_tx + e_tx;
+        }
+        c_sp += tot_sp; c_tx += tot_tx; c_ph += tot_ph;
+    }
+    const int tot = c_ph;
+    __syncthreads();
+    // pass 2: audio slots owned by every non-text token, restricted to the non-pad span
+    const int span_lo = left ? n_pad : 0;
+    const int span_hi = left ? tot : tot - n_pad;
+    int c_sl = 0;
+    for (int j0 = 0; j0 < S; j0 += blockDim.x) {
+        const int j = j0 + threadIdx.x;
+        int ns = 0;
+        if (j < S) {
+            const int64_t i = (int64_t)b * S + j;
+            const bool sp = ids[i] == speech;
+            const bool tx = (!sp && mask_at(mask, mdt, i) == 1);
+            if (!tx) {
+                const int q1 = new_pos[i] + 1;                                  // exclusive end
+                const int q0 = (j == 0) ? 0 : new_pos[i - 1] + 1;               // inclusive start
+                const int lo = max(q0, span_lo), hi = min(q1, span_hi);
+                ns = max(0, hi - lo);
+            }
+        }
+        int tot_sl;
+        const int e_sl = block_excl_scan_i(ns, scratch, &tot_sl);
+        if (j < S) slot_ord[(int64_t)b * S + j] = c_sl + e_sl;
+        c_sl += tot_sl;
+    }
+    if (threadIdx.x == 0) {
+        rowstat[(int64_t)b * RS_WORDS + RS_TOT] = tot;
+        rowstat[(int64_t)b * RS_WORDS + RS_SLOTS] = c_sl;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+splice_header_kernel(const int32_t* __restrict__ rowstat, const int64_t* __restrict__ num_audio, int n_audio,
+                     int64_t div_k, int B, int64_t* __restrict__ header, int32_t* __restrict__ slot_base,
+                     int32_t* __restrict__ audio_off) {
+    __shared__ int scratch[33];
+    bool both;
+    const bool left = batch_left_padding(rowstat, B, scratch, &both);
+    int carry = 0, mx = 0, nsp = 0;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < B ? rowstat[(int64_t)b * RS_WORDS + RS_SLOTS] : 0;
+        int total;
+        const int excl = block_excl_scan_i(v, scratch, &total);
+        if (b < B) {
+            slot_base[b] = carry + excl;
+            mx = max(mx, rowstat[(int64_t)b * RS_WORDS + RS_TOT]);
+            nsp += rowstat[(int64_t)b * RS_WORDS + RS_NSPEECH];
+        }
+        carry += total;
+    }
+    const int total_slots = carry;
+    mx = block_max_i(mx, scratch);
+    nsp = block_sum_i(nsp, scratch);
+    int acarry = 0;
+    for (int a0 = 0; a0 < n_audio; a0 += blockDim.x) {
+        const int a = a0 + threadIdx.x;
+        int v = 0;
+        if (a < n_audio) { int64_t m = num_audio[a] / div_k; v = (int)(m < 0 ? 0 : m); }
+        int total;
+        const int excl = block_excl_scan_i(v, scratch, &total);
+        if (a < n_audio) audio_off[a] = acarry + excl;
+        acarry += total;
+    }
+    if (threadIdx.x == 0) {
+        audio_off[n_audio] = acarry;
+        header[TASU_SH_SPLICED_LEN] = mx;
+        header[TASU_SH_LEFT_PADDING] = left ? 1 : 0;
+        header[TASU_SH_ERR_BOTH_SIDES] = both ? 1 : 0;
+        header[TASU_SH_TOTAL_SLOTS] = total_slots;
+        header[TASU_SH_TOTAL_AUDIO] = acarry;
+        header[TASU_SH_N_SPEECH] = nsp;
+        header[6] = 0; header[7] = 0;
+    }
+}
+
+struct Dest {           // what lands on destination position (b, p)
+    int kind;           // 0 pad, 1 text, 2 audio
+    int j;              // source token (text)
+    int a;              // global audio ordinal (audio)
+    int pos;            // position id
+};
+
+__device__ __forceinline__ Dest resolve_dest(int b, int p, int S, int Sp, bool left, const int32_t* __restrict__ rowstat,
+                                             const int64_t* __restrict__ ids, const void* __restrict__ mask, int mdt,
+                                             int64_t speech, const int32_t* __restrict__ new_pos,
+                                             const int32_t* __restrict__ text_prefix, const int32_t* __restrict__ slot_ord,
+                                             const int32_t* __restrict__ slot_base) {
+    Dest d{0, 0, 0, 1};
+    const int32_t* rs = rowstat + (int64_t)b * RS_WORDS;
+    const int tot = rs[RS_TOT], n_pad = rs[RS_NPAD];
+    const int q = p - (left ? (Sp - tot) : 0);
+    if (q < 0 || q >= tot) return d;
+    const int32_t* np = new_pos + (int64_t)b * S;
+    int lo = 0, hi = S - 1;                      // smallest j with np[j] >= q (exists because q < tot)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (np[mid] >= q) hi = mid; else lo = mid + 1;
+    }
+    const int j = lo;
+    const int64_t i = (int64_t)b * S + j;
+    const bool sp = ids[i] == speech;
+    const bool tx = (!sp && mask_at(mask, mdt, i) == 1);
+    if (tx) {
+        d.kind = 1; d.j = j; d.pos = text_prefix[i] + slot_ord[i];
+        return d;
+    }
+    const int span_lo = left ? n_pad : 0, span_hi = left ? tot : tot - n_pad;
+    if (q < span_lo || q >= span_hi) return d;
+    const int q0 = (j == 0) ? 0 : np[j - 1] + 1;
+    const int k_in = q - max(q0, span_lo);
+    d.kind = 2;
+    d.a = slot_base[b] + slot_ord[i] + k_in;
+    d.pos = text_prefix[i] + slot_ord[i] + k_in;
+    return d;
+}
+
+__device__ __forceinline__ int64_t audio_row_of(int a, int layout, int64_t max_len, int n_audio,
+                                                const int32_t* __restrict__ audio_off) {
+    if (a >= audio_off[n_audio]) return -1;
+    if (layout == 0) return a;
+    int lo = 0, hi = n_audio;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (audio_off[mid] <= a) lo = mid; else hi = mid;
+    }
+    return (int64_t)lo * max_len + (a - audio_off[lo]);
+}
+
+struct ScatterArgs {
+    const int64_t* ids; const void* mask; int mdt; const int64_t* labels;
+    int B, S, Sp, H;
+    const void* text_src; int text_mode; int64_t text_stride;
+    const void* audio; int audio_layout; int64_t audio_stride; int64_t audio_max_len; int n_audio;
+    const int32_t* rowstat; const int32_t* new_pos; const int32_t* text_prefix; const int32_t* slot_ord;
+    const int32_t* slot_base; const int32_t* audio_off; const int64_t* header;
+    int64_t speech, pad_id, ignore_id;
+    void* out_emb; void* out_mask; int64_t* out_labels; int64_t* out_pos; int64_t* out_ids;
+};
+
+// one warp per destination row; ESZ = bytes per embedding element
+template <int ESZ>
+__global__ void __launch_bounds__(256)
+splice_scatter_kernel(ScatterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (int64_t)a.B * a.Sp) return;
+    const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
+    const bool left = a.header[TASU_SH_LEFT_PADDING] != 0;
+    const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
+                                a.text_prefix, a.slot_ord, a.slot_base);
+    const char* src = nullptr;
+    int64_t lab = a.ignore_id, fid = a.pad_id;
+    int mval = 0;
+    if (d.kind == 1) {
+        const int64_t i = (int64_t)b * a.S + d.j;
+        const int64_t srow = a.text_mode == 1 ? a.ids[i] : i;
+        src = reinterpret_cast<const char*>(a.text_src) + srow * a.text_stride * ESZ;
+        if (a.labels) lab = a.labels[i];
+        fid = a.ids[i];
+        mval = 1;
+    } else if (d.kind == 2) {
+        const int64_t ar = audio_row_of(d.a, a.audio_layout, a.audio_max_len, a.n_audio, a.audio_off);
+        if (ar >= 0) src = reinterpret_cast<const char*>(a.audio) + ar * a.audio_stride * ESZ;
+        mval = 1;
+    }
+    char* dst = reinterpret_cast<char*>(a.out_emb) + row * (int64_t)a.H * ESZ;
+    const int64_t nbytes = (int64_t)a.H * ESZ;
+    const bool vec = (nbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (src == nullptr || (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (vec) {
+        const int nv = (int)(nbytes / 16);
+        if (src) {
+            for (int c = lane; c < nv; c += 128) {        // 4 independent 16-byte loads in flight per lane
+                uint4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c + 32 * u < nv) q[u] = ld_stream_u4(reinterpret_cast<const uint4*>(src) + c + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c + 32 * u < nv) st_stream_u4(reinterpret_cast<uint4*>(dst) + c + 32 * u, q[u]);
+            }
+        } else {
+            for (int c = lane; c < nv; c += 32) st_stream_u4(reinterpret_cast<uint4*>(dst) + c, make_uint4(0, 0, 0, 0));
+        }
+    } else {
+        for (int64_t c = lane; c < nbytes; c += 32) dst[c] = src ? src[c] : 0;
+    }
+    if (lane == 0) {
+        if (a.mdt == 0) reinterpret_cast<uint8_t*>(a.out_mask)[row] = (uint8_t)mval;
+        else reinterpret_cast<int64_t*>(a.out_mask)[row] = mval;
+        if (a.out_labels) a.out_labels[row] = lab;
+        a.out_pos[row] = mval ? d.pos : 1;
+        if (a.out_ids) a.out_ids[row] = fid;
+    }
+}
+
+template <int ESZ>
+__global__ void __launch_bounds__(256)
+splice_audio_grad_kernel(ScatterArgs a, const void* grad_emb, void* grad_audio) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (int64_t)a.B * a.Sp) return;
+    const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
+    const bool left = a.header[TASU_SH_LEFT_PADDING] != 0;
+    const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
+                                a.text_prefix, a.slot_ord, a.slot_base);
+    if (d.kind != 2) return;
+    const int64_t ar = audio_row_of(d.a, a.audio_layout, a.audio_max_len, a.n_audio, a.audio_off);
+    if (ar < 0) return;
+    const char* src = reinterpret_cast<const char*>(grad_emb) + row * (int64_t)a.H * ESZ;
+    char* dst = reinterpret_cast<char*>(grad_audio) + ar * a.audio_stride * ESZ;
+    const int64_t nbytes = (int64_t)a.H * ESZ;
+    if ((nbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        for (int c = lane; c < nbytes / 16; c += 32)
+            reinterpret_cast<uint4*>(dst)[c] = ld_stream_u4(reinterpret_cast<const uint4*>(src) + c);
+    } else {
+        for (int64_t c = lane; c < nbytes; c += 32) dst[c] = src[c];
+    }
+}
+
+}  // namespace tasu
+
+using namespace tasu;
+
+extern "C" int tasu_splice_rowstat(const int64_t* input_ids, const void* attention_mask, int mask_dtype, int B, int S,
+                                   int64_t speech_id, int32_t* rowstat, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && S >= 0, "B,S >= 0");
+    TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
+    if (B == 0) return TASU_OK;
+    TASU_CHECK_ARG(input_ids && attention_mask && rowstat, "null pointer");
+    splice_rowstat_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(input_ids, attention_mask, mask_dtype, S, speech_id, rowstat);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_splice_plan(const int64_t* input_ids, const void* attention_mask, int mask_dtype, int B, int S,
+                                int64_t speech_id, const int64_t* num_audio, int n_audio, int64_t div_k,
+                                int32_t* rowstat, int32_t* new_pos, int32_t* text_prefix, int32_t* slot_ord,
+                                void* stream) {
+    TASU_CHECK_ARG(B >= 0 && S >= 0 && n_audio >= 0 && div_k >= 1, "B,S,n_audio >= 0, div_k >= 1");
+    TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
+    if (B == 0) return TASU_OK;
+    TASU_CHECK_ARG(input_ids && attention_mask && rowstat && new_pos && text_prefix && slot_ord, "null pointer");
+    TASU_CHECK_ARG(n_audio == 0 || num_audio, "null num_audio");
+    splice_plan_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(input_ids, attention_mask, mask_dtype, B, S, speech_id,
+                                                            num_audio, n_audio, div_k, rowstat, new_pos, text_prefix,
+                                                            slot_ord);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_splice_header(const int32_t* rowstat, const int64_t* num_audio, int n_audio, int64_t div_k,
+                                  int B, int S, int64_t* header, int32_t* slot_base, int32_t* audio_off, void* stream) {
+    (void)S;
+    TASU_CHECK_ARG(B >= 0 && n_audio >= 0 && div_k >= 1, "B,n_audio >= 0, div_k >= 1");
+    TASU_CHECK_ARG(header && audio_off && (B == 0 || (rowstat && slot_base)), "null pointer");
+    splice_header_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowstat, num_audio, n_audio, div_k, B, header, slot_base, audio_off);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+static int launch_rows(int64_t rows, unsigned* grid) {
+    const int64_t g = (rows + 7) / 8;
+    if (g > 0x7fffffffLL) return -1;
+    *grid = (unsigned)g;
+    return 0;
+}
+
+extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                                   const int64_t* labels, int B, int S, int spliced_len, int H, int64_t speech_id,
+                                   const void* text_src, int text_mode, int64_t text_row_stride,
+                                   const void* audio_rows, int audio_layout, int64_t audio_row_stride,
+                                   int64_t audio_max_len, int n_audio, int emb_dtype,
+                                   const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
+                                   const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
+                                   const int64_t* header, int64_t pad_id, int64_t ignore_id,
+                                   void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
+                                   int64_t* out_ids, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
+    TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
+    TASU_CHECK_ARG(text_mode == 0 || text_mode == 1, "text_mode");
+    TASU_CHECK_ARG(audio_layout == 0 || audio_layout == 1, "audio_layout");
+    TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
+    if ((int64_t)B * spliced_len == 0) return TASU_OK;
+    TASU_CHECK_ARG(input_ids && attention_mask && text_src && rowstat && new_pos && text_prefix && slot_ord &&
+                   slot_base && audio_off && header && out_emb && out_mask && out_pos, "null pointer");
+    ScatterArgs a{};
+    a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype; a.labels = labels;
+    a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
+    a.text_src = text_src; a.text_mode = text_mode; a.text_stride = text_row_stride;
+    a.audio = audio_rows; a.audio_layout = audio_layout; a.audio_stride = audio_row_stride;
+    a.audio_max_len = audio_max_len; a.n_audio = n_audio;
+    a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
+    a.slot_base = slot_base; a.audio_off = audio_off; a.header = header;
+    a.speech = speech_id; a.pad_id = pad_id; a.ignore_id = ignore_id;
+    a.out_emb = out_emb; a.out_mask = out_mask; a.out_labels = out_labels; a.out_pos = out_pos; a.out_ids = out_ids;
+    unsigned grid;
+    TASU_CHECK_ARG(launch_rows((int64_t)B * spliced_len, &grid) == 0, "too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (emb_dtype == TASU_F32) splice_scatter_kernel<4><<<grid, 256, 0, st>>>(a);
+    else splice_scatter_kernel<2><<<grid, 256, 0, st>>>(a);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const int64_t* input_ids,
+                                      const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
+                                      int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
+                                      const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
+                                      const int32_t* audio_off, const int64_t* header, int audio_layout,
+                                      int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
+                                      void* grad_audio, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
+    TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
+    if ((int64_t)B * spliced_len == 0) return TASU_OK;
+    TASU_CHECK_ARG(grad_emb && input_ids && attention_mask && rowstat && new_pos && text_prefix && slot_ord &&
+                   slot_base && audio_off && header && grad_audio, "null pointer");
+    ScatterArgs a{};
+    a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype;
+    a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
+    a.audio_layout = audio_layout; a.audio_stride = audio_row_stride; a.audio_max_len = audio_max_len; a.n_audio = n_audio;
+    a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
+    a.slot_base = slot_base; a.audio_off = audio_off; a.header = header; a.speech = speech_id;
+    unsigned grid;
+    TASU_CHECK_ARG(launch_rows((int64_t)B * spliced_len, &grid) == 0, "too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (emb_dtype == TASU_F32) splice_audio_grad_kernel<4><<<grid, 256, 0, st>>>(a, grad_emb, grad_audio);
+    else splice_audio_grad_kernel<2><<<grid, 256, 0, st>>>(a, grad_emb, grad_audio);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -1,0 +1,296 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every byte of the
+bridge's arithmetic happens inside libtasu_bridge.so.  All wrappers enqueue on
+``torch.cuda.current_stream()`` and never synchronise.
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+V_ALIGN = 64          # leading dimension padding (elements) of buffers this package owns
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    raise TypeError("tasu bridge supports float32 and bfloat16 tensors, got %s" % t.dtype)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.TasuError("tasu bridge ops need CUDA tensors (no CPU fallback exists)")
+
+
+def pad_to(n: int, a: int = V_ALIGN) -> int:
+    return (n + a - 1) // a * a
+
+
+def view3(x: torch.Tensor):
+    """(batch_stride, row_stride) of a [B,T,V] view whose last dim is contiguous."""
+    if x.dim() != 3:
+        raise ValueError("expected a [B, T, V] tensor")
+    if x.shape[-1] > 1 and x.stride(-1) != 1:
+        x = x.contiguous()
+    return x, x.stride(0), x.stride(1)
+
+
+class FrameStats:
+    __slots__ = ("argmax", "x_blank", "row_max", "row_sumexp", "gmax", "kind", "B", "T")
+
+
+def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[torch.Tensor] = None) -> FrameStats:
+    """tasu_frame_stats on a [B,T,V] view (any batch/row stride, last dim contiguous)."""
+    _need_cuda(x, lens)
+    x, bs, rs = view3(x)
+    B, T, V = x.shape
+    dev = x.device
+    st = FrameStats()
+    st.kind, st.B, st.T = input_kind, B, T
+    st.argmax = torch.empty(B * T, dtype=torch.int32, device=dev)
+    st.x_blank = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.row_max = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.row_sumexp = torch.empty(B * T, dtype=torch.float32, device=dev) if input_kind == L.INPUT_LOGITS else None
+    st.gmax = torch.empty(1, dtype=torch.int32, device=dev)
+    if lens is not None:
+        lens = lens.to(torch.int64)
+    L.check(L.lib().tasu_frame_stats(x.data_ptr(), _dt(x), input_kind, B, T, V, bs, rs, blank_id, _ptr(lens),
+                                     st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
+                                     _ptr(st.row_sumexp), st.gmax.data_ptr(), _stream()), "tasu_frame_stats")
+    return st
+
+
+class CollapsePlan:
+    __slots__ = ("seg_start", "seg_len", "seg_score", "new_lens", "row_off", "header", "B", "T")
+
+
+def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: float,
+                  header: Optional[torch.Tensor] = None, want_scores: bool = False) -> CollapsePlan:
+    """tasu_collapse_plan + tasu_collapse_scan. ``header`` (int64[>=4]) may be caller-provided so
+    several plans share one device→host read."""
+    B, T = st.B, st.T
+    dev = st.argmax.device
+    lens = lens.to(device=dev, dtype=torch.int64).contiguous()
+    p = CollapsePlan()
+    p.B, p.T = B, T
+    p.seg_start = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
+    p.seg_len = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
+    p.seg_score = torch.empty(max(B * T, 1), dtype=torch.float32, device=dev) if want_scores else None
+    p.new_lens = torch.empty(B, dtype=torch.int64, device=dev)
+    p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
+    lib = L.lib()
+    L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
+                                   _ptr(st.row_sumexp), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
+                                   blank_id, float(threshold), p.seg_start.data_ptr(), p.seg_len.data_ptr(),
+                                   _ptr(p.seg_score), p.new_lens.data_ptr(), _stream()), "tasu_collapse_plan")
+    L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
+                                   B, p.row_off.data_ptr(), p.header.data_ptr(), _stream()), "tasu_collapse_scan")
+    return p
+
+
+def segment_meanpool(feats: torch.Tensor, plan: CollapsePlan, layout: int, max_len: int, max_rows: int,
+                     out: torch.Tensor, out_row_stride: int, softmax: Optional[FrameStats] = None,
+                     ln_mean: Optional[torch.Tensor] = None, ln_rstd: Optional[torch.Tensor] = None,
+                     ln_eps: float = 1e-5):
+    _need_cuda(feats, out)
+    feats, bs, rs = view3(feats)
+    B, T, D = feats.shape
+    L.check(L.lib().tasu_segment_meanpool(
+        feats.data_ptr(), _dt(feats), B, T, D, bs, rs,
+        _ptr(softmax.row_max) if softmax is not None else None,
+        _ptr(softmax.row_sumexp) if softmax is not None else None,
+        plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.row_off.data_ptr(),
+        layout, max_len, max_rows, out.data_ptr(), _dt(out), out_row_stride,
+        _ptr(ln_mean), _ptr(ln_rstd), float(ln_eps), _stream()), "tasu_segment_meanpool")
+    return out
+
+
+def cast_rows(src: torch.Tensor, dst_dtype: torch.dtype, dst_stride: Optional[int] = None, want_ln: bool = False,
+              ln_eps: float = 1e-5):
+    """[rows, cols] → dst dtype with pitch ``dst_stride`` (+ LayerNorm stats per row)."""
+    _need_cuda(src)
+    if src.dim() != 2:
+        raise ValueError("cast_rows expects a 2-D tensor")
+    if src.shape[1] > 1 and src.stride(1) != 1:
+        src = src.contiguous()
+    rows, cols = src.shape
+    dst_stride = cols if dst_stride is None else dst_stride
+    dst = torch.empty(rows, dst_stride, dtype=dst_dtype, device=src.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=src.device) if want_ln else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=src.device) if want_ln else None
+    L.check(L.lib().tasu_cast_rows(src.data_ptr(), _dt(src), rows, cols, src.stride(0) if rows > 1 else cols,
+                                   dst.data_ptr(), _dt(dst), dst_stride, _ptr(mean), _ptr(rstd), float(ln_eps),
+                                   _stream()), "tasu_cast_rows")
+    return dst, mean, rstd
+
+
+def fold_layernorm(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1: Optional[torch.Tensor]):
+    """(W1g bf16 [N, pad64(K)], colsum [N], dbias [N]) — LayerNorm folded into the first Linear."""
+    _need_cuda(w1, gamma, beta, b1)
+    N, K = w1.shape
+    w1 = w1.float().contiguous()
+    ld = pad_to(K)
+    w1g = torch.empty(N, ld, dtype=torch.bfloat16, device=w1.device)
+    colsum = torch.empty(N, dtype=torch.float32, device=w1.device)
+    dbias = torch.empty(N, dtype=torch.float32, device=w1.device)
+    L.check(L.lib().tasu_fold_layernorm(w1.data_ptr(), K, gamma.float().contiguous().data_ptr(),
+                                        beta.float().contiguous().data_ptr(),
+                                        _ptr(b1.float().contiguous()) if b1 is not None else None, N, K,
+                                        w1g.data_ptr(), ld, colsum.data_ptr(), dbias.data_ptr(), _stream()),
+            "tasu_fold_layernorm")
+    return w1g, colsum, dbias
+
+
+def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor,
+                 epilogue: int = L.EPI_NONE, bias: Optional[torch.Tensor] = None,
+                 row_rstd: Optional[torch.Tensor] = None, row_mean: Optional[torch.Tensor] = None,
+                 colsum: Optional[torch.Tensor] = None, simt: bool = False):
+    """out[M,N] = epilogue(A[M,K] · Bw[N,K]^T); A/Bw bf16 with pitch = stride(0); out bf16|fp32."""
+    _need_cuda(A, Bw, out)
+    if A.dtype != torch.bfloat16 or Bw.dtype != torch.bfloat16:
+        raise TypeError("GEMM operands must be bfloat16")
+    fn = L.lib().tasu_gemm_bf16_tn_simt if simt else L.lib().tasu_gemm_bf16_tn
+    lda = A.stride(0) if A.dim() == 2 and A.shape[0] > 1 else max(K, A.shape[-1])
+    ldb = Bw.stride(0) if Bw.shape[0] > 1 else max(K, Bw.shape[-1])
+    ldc = out.stride(0) if out.shape[0] > 1 else max(N, out.shape[-1])
+    L.check(fn(A.data_ptr(), lda, Bw.data_ptr(), ldb, out.data_ptr(), _dt(out), ldc, M, N, K, epilogue,
+               _ptr(bias), _ptr(row_rstd), _ptr(row_mean), _ptr(colsum), _stream()),
+            "tasu_gemm_bf16_tn_simt" if simt else "tasu_gemm_bf16_tn")
+    return out
+
+
+def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor, V: int, out: torch.Tensor,
+                       out_row_stride: int, dst_row: Optional[torch.Tensor] = None,
+                       ln_mean: Optional[torch.Tensor] = None, ln_rstd: Optional[torch.Tensor] = None,
+                       ln_eps: float = 1e-5):
+    _need_cuda(tok, hot, base, out)
+    L.check(L.lib().tasu_sim_posterior_rows(tok.data_ptr(), hot.data_ptr(), base.data_ptr(), _ptr(dst_row),
+                                            tok.numel(), V, out.data_ptr(), _dt(out), out_row_stride,
+                                            _ptr(ln_mean), _ptr(ln_rstd), float(ln_eps), _stream()),
+            "tasu_sim_posterior_rows")
+    return out
+
+
+class SplicePlan:
+    __slots__ = ("rowstat", "new_pos", "text_prefix", "slot_ord", "slot_base", "audio_off", "header",
+                 "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask")
+
+
+def _mask_arg(attention_mask: torch.Tensor):
+    if attention_mask.dtype == torch.bool:
+        return attention_mask.contiguous(), 0
+    if attention_mask.dtype == torch.uint8:
+        return attention_mask.contiguous(), 0
+    return attention_mask.to(torch.int64).contiguous(), 1
+
+
+def splice_rowstat(input_ids: torch.Tensor, attention_mask: torch.Tensor, speech_id: int) -> SplicePlan:
+    _need_cuda(input_ids, attention_mask)
+    B, S = input_ids.shape
+    dev = input_ids.device
+    p = SplicePlan()
+    p.B, p.S, p.speech_id = B, S, int(speech_id)
+    p.input_ids = input_ids.to(torch.int64).contiguous()
+    p.attention_mask, p.mask_dtype = _mask_arg(attention_mask)
+    p.rowstat = torch.empty(max(B, 1), 8, dtype=torch.int32, device=dev)
+    L.check(L.lib().tasu_splice_rowstat(p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, B, S,
+                                        p.speech_id, p.rowstat.data_ptr(), _stream()), "tasu_splice_rowstat")
+    return p
+
+
+def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: Optional[torch.Tensor] = None):
+    dev = p.input_ids.device
+    num_audio = num_audio.to(device=dev, dtype=torch.int64).contiguous()
+    B, S = p.B, p.S
+    p.n_audio = num_audio.numel()
+    p.new_pos = torch.empty(max(B * S, 1), dtype=torch.int32, device=dev)
+    p.text_prefix = torch.empty(max(B * S, 1), dtype=torch.int32, device=dev)
+    p.slot_ord = torch.empty(max(B * S, 1), dtype=torch.int32, device=dev)
+    p.slot_base = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+    p.audio_off = torch.empty(p.n_audio + 1, dtype=torch.int32, device=dev)
+    p.header = header if header is not None else torch.empty(L.SH_WORDS, dtype=torch.int64, device=dev)
+    lib = L.lib()
+    L.check(lib.tasu_splice_plan(p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, B, S,
+                                 p.speech_id, num_audio.data_ptr(), p.n_audio, div_k, p.rowstat.data_ptr(),
+                                 p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(), _stream()),
+            "tasu_splice_plan")
+    L.check(lib.tasu_splice_header(p.rowstat.data_ptr(), num_audio.data_ptr(), p.n_audio, div_k, B, S,
+                                   p.header.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), _stream()),
+            "tasu_splice_header")
+    return p
+
+
+def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text_mode: int,
+                   audio_rows: torch.Tensor, audio_layout: int, audio_max_len: int,
+                   labels: Optional[torch.Tensor], pad_id: int, ignore_id: int, want_ids: bool = True):
+    """One gather/scatter pass → (emb [B,S',H], mask [B,S'], labels|None, position_ids, final_ids|None)."""
+    _need_cuda(text_src, audio_rows, labels)
+    B, S = p.B, p.S
+    dev = p.input_ids.device
+    H = text_src.shape[-1]
+    if audio_rows.dtype != text_src.dtype:
+        raise TypeError("audio rows (%s) and text embeddings (%s) must share a dtype" % (audio_rows.dtype, text_src.dtype))
+    if text_src.stride(-1) != 1:
+        text_src = text_src.contiguous()
+    if audio_rows.numel() and audio_rows.stride(-1) != 1:
+        audio_rows = audio_rows.contiguous()
+    if text_mode == 0:
+        text2 = text_src.reshape(B * S, H)
+        text_stride = text2.stride(0) if B * S > 1 else H
+    else:
+        text2 = text_src
+        text_stride = text2.stride(0)
+    if audio_layout == 1:
+        audio_rows = audio_rows.contiguous()
+        audio_stride = H
+    else:
+        audio_stride = audio_rows.stride(0) if audio_rows.dim() == 2 and audio_rows.shape[0] > 1 else H
+    emb = torch.empty(B, spliced_len, H, dtype=text_src.dtype, device=dev)
+    mask = torch.empty(B, spliced_len, dtype=torch.bool if p.mask_dtype == 0 else torch.int64, device=dev)
+    out_labels = None
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+        out_labels = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
+    pos = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
+    fids = torch.empty(B, spliced_len, dtype=torch.int64, device=dev) if want_ids else None
+    L.check(L.lib().tasu_splice_scatter(
+        p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, _ptr(labels), B, S, spliced_len, H,
+        p.speech_id, text2.data_ptr(), text_mode, text_stride, audio_rows.data_ptr() if audio_rows.numel() else None,
+        audio_layout, audio_stride, audio_max_len, p.n_audio, _dt(emb),
+        p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(),
+        p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(), pad_id, ignore_id,
+        emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), _stream()),
+        "tasu_splice_scatter")
+    return emb, mask, out_labels, pos, fids
+
+
+def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, audio_max_len: int,
+                      n_rows: int):
+    """grad wrt the audio rows = gather of grad_emb at the audio slots (backward of splice_scatter)."""
+    _need_cuda(grad_emb)
+    grad_emb = grad_emb.contiguous()
+    B, Sp, H = grad_emb.shape
+    if audio_layout == 1:
+        ga = torch.zeros(p.n_audio, audio_max_len, H, dtype=grad_emb.dtype, device=grad_emb.device)
+    else:
+        ga = torch.zeros(n_rows, H, dtype=grad_emb.dtype, device=grad_emb.device)
+    L.check(L.lib().tasu_splice_audio_grad(
+        grad_emb.data_ptr(), _dt(grad_emb), p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype,
+        B, p.S, Sp, H, p.speech_id, p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(),
+        p.slot_ord.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(),
+        audio_layout, H, audio_max_len, p.n_audio, ga.data_ptr(), _stream()), "tasu_splice_audio_grad")
+    return ga

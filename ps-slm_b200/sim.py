@@ -1,0 +1,110 @@
+"""Text-simulated CTC posteriors (step 1a of the bridge), device-side construction.
+
+* ``ctc_pseudo_posterior``        ← slam_model_asr.ctc_pseudo_posterior        (ps-slm.py:337-358)
+* ``ctc_pseudo_posterior_noise``  ← slam_model_asr.ctc_pseudo_posterior_noise  (ps-slm.py:360-409)
+
+The reference builds ``[B, L_max, 25055]`` fp32 on the CPU (one_hot, boolean gathers, O(n_insert)
+``torch.cat`` reallocations) and then copies ~100 KB per token over PCIe.  Here only the random
+DECISIONS are made on the host — drawn from torch's CPU global generator in exactly the
+reference's order so results are reproducible bit for bit — and a few bytes per row go to the
+device, where one kernel writes the rows at HBM speed (or, for the fused training path, writes
+bf16 rows plus closed-form LayerNorm statistics).
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def draw_noise_decisions(ids_list: Sequence[Sequence[int]], blank_id: int = 0, drop_prob: float = 0.05,
+                         insert_prob: float = 0.0, smooth_low: float = 0.0, smooth_high: float = 0.1):
+    """Per utterance ``(alpha, rows)``, rows = [(token_id, is_hard_blank)].  RNG order of the
+    reference: one ``uniform_`` (:384), ``rand(L)`` (:387), then per insert ``randint(0, len+1)`` and
+    ``rand(1)`` (:391-392)."""
+    out = []
+    for ids in ids_list:
+        alpha = torch.empty(()).uniform_(smooth_low, smooth_high).item()
+        keep = (torch.rand(len(ids)) > drop_prob).tolist()
+        rows = [(int(v), False) for v, k in zip(ids, keep) if k]
+        for _ in range(int(len(rows) * insert_prob)):
+            pos = torch.randint(0, len(rows) + 1, (1,)).item()
+            if torch.rand(1) < 0.5 and len(rows) > 0:
+                rows.insert(pos, rows[pos - 1] if pos > 0 else rows[0])     # duplicate the left neighbour (:394)
+            else:
+                rows.insert(pos, (blank_id, True))                          # exact one-hot blank (:397-399)
+        out.append((alpha, rows))
+    return out
+
+
+def soft_row_values(alpha: float, vocab_size: int) -> Tuple[np.float32, np.float32]:
+    """fp32 (hot, base) of ``(1 - alpha) * onehot + alpha / V`` as torch evaluates it (:385)."""
+    a = np.float32(1.0 - alpha)
+    c = np.float32(alpha / vocab_size)
+    return np.float32(a + c), c
+
+
+def _descriptors(decisions, vocab_size: int, pad_to_max: bool):
+    lens = [len(r) for _, r in decisions]
+    lmax = max(lens) if lens else 0
+    tok, hot, base = [], [], []
+    for (alpha, rows), n in zip(decisions, lens):
+        h, c = soft_row_values(alpha, vocab_size)
+        for v, hard in rows:
+            tok.append(v)
+            hot.append(1.0 if hard else float(h))
+            base.append(0.0 if hard else float(c))
+        if pad_to_max:
+            tok.extend([-1] * (lmax - n)); hot.extend([0.0] * (lmax - n)); base.extend([0.0] * (lmax - n))
+    return (np.asarray(tok, dtype=np.int32), np.asarray(hot, dtype=np.float32), np.asarray(base, dtype=np.float32),
+            lens, lmax)
+
+
+def _to_dev(a: np.ndarray, device):
+    t = torch.from_numpy(a)
+    if t.numel():
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+def build_dense(decisions, vocab_size: int, device, dtype=torch.float32):
+    """[B, L_max, V] posterior + lens (int64, on device) from decisions — the reference's return contract."""
+    tok, hot, base, lens, lmax = _descriptors(decisions, vocab_size, True)
+    B = len(decisions)
+    out = torch.empty(B, lmax, vocab_size, dtype=dtype, device=device)
+    if B * lmax:
+        ops.sim_posterior_rows(_to_dev(tok, device), _to_dev(hot, device), _to_dev(base, device), vocab_size,
+                               out, vocab_size)
+    return out, torch.tensor(lens, dtype=torch.long, device=device)
+
+
+def build_packed_bf16(decisions, vocab_size: int, device, ln_eps: float = 1e-5):
+    """Packed bf16 rows [sum L_b, pad64(V)] + LayerNorm stats + lens: the A operand of the folded
+    projector GEMM for the text-only training step (never materialises the fp32 posterior)."""
+    tok, hot, base, lens, _ = _descriptors(decisions, vocab_size, False)
+    n = int(tok.shape[0])
+    ld = ops.pad_to(vocab_size)
+    rows = torch.empty(n, ld, dtype=torch.bfloat16, device=device)
+    mean = torch.empty(n, dtype=torch.float32, device=device)
+    rstd = torch.empty(n, dtype=torch.float32, device=device)
+    if n:
+        ops.sim_posterior_rows(_to_dev(tok, device), _to_dev(hot, device), _to_dev(base, device), vocab_size,
+                               rows, ld, ln_mean=mean, ln_rstd=rstd, ln_eps=ln_eps)
+    return rows, mean, rstd, torch.tensor(lens, dtype=torch.long, device=device)
+
+
+def ctc_pseudo_posterior(ids_list: List[List[int]], vocab_size: int, device):
+    """One-hot posterior [B, L_max, V] fp32 and lens (ps-slm.py:337-358).  The reference returns CPU
+    tensors which its caller moves to the device (:467-468, :597-598); this returns them there."""
+    dec = [(0.0, [(int(v), True) for v in ids]) for ids in ids_list]
+    # hard rows: exactly 1.0 at the token, 0 elsewhere (here "hard" just means no smoothing)
+    return build_dense(dec, vocab_size, device)
+
+
+def ctc_pseudo_posterior_noise(ids_list: List[List[int]], vocab_size: int, device, blank_id: int = 0,
+                               drop_prob: float = 0.05, insert_prob: float = 0.0, smooth_low: float = 0.0,
+                               smooth_high: float = 0.1):
+    """Smoothed / dropped / inserted pseudo-posterior and lens on ``device`` (ps-slm.py:360-409)."""
+    dec = draw_noise_decisions(ids_list, blank_id, drop_prob, insert_prob, smooth_low, smooth_high)
+    return build_dense(dec, vocab_size, device)

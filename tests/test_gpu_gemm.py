@@ -1,0 +1,179 @@
+"""GPU parity tests for the tcgen05/TMEM/TMA GEMM, the projector plugins and the fused bridge."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tasu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _ref_gemm(A, B, epi, bias, rstd, mean, colsum):
+    acc = A.float().double() @ B.float().double().T
+    if epi == 4:
+        z = rstd.double()[:, None] * (acc - mean.double()[:, None] * colsum.double()[None, :]) + bias.double()[None, :]
+        return torch.nn.functional.silu(z)
+    if epi >= 1:
+        acc = acc + bias.double()[None, :]
+    if epi == 2:
+        acc = torch.nn.functional.silu(acc)
+    if epi == 3:
+        acc = torch.relu(acc)
+    return acc
+
+
+SHAPES = [
+    (128, 256, 64), (1, 8, 8), (130, 260, 72), (200, 300, 1000), (257, 1536, 2048), (1000, 2048, 25055),
+    (900, 25055, 512), (5, 40, 136),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16),
+                                           (3, torch.bfloat16), (4, torch.bfloat16)])
+def test_gemm_tcgen05(dev, M, N, K, epi, out_dtype):
+    import ps_slm_b200.ops as ops
+    if (M, N, K) in [(1000, 2048, 25055), (900, 25055, 512)] and epi in (0, 3):
+        pytest.skip("large shapes: a subset of epilogues is enough")
+    torch.manual_seed(M * 7 + N * 3 + K + epi)
+    lda, ldb = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8)
+    ldc = ops.pad_to(N, 8)
+    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16()
+    A[:, K:] = 7.0                                     # garbage beyond K must never be read
+    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16()
+    B[:, K:] = 7.0
+    bias, rstd, mean, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(M) * 0.1, torch.randn(N)
+    C = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+    Ad, Bd = A.to(dev), B.to(dev)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C, epi, bias.to(dev), rstd.to(dev), mean.to(dev), colsum.to(dev))
+    torch.cuda.synchronize()
+    ref = _ref_gemm(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    got = C.cpu()
+    assert bool((got[:, N:] == -777.0).all()), "stores must be clipped at N"
+    scale = ref.abs().max().item() + 1e-6
+    tol = 2e-5 if out_dtype == torch.float32 else 6e-3
+    err = (got[:, :N].double() - ref).abs().max().item() / scale
+    assert err < tol, f"tcgen05 GEMM max error {err} (scaled) for {(M, N, K, epi)}"
+    # cross-check against the CUDA-core kernel of the same contract
+    C2 = torch.empty_like(C)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C2, epi, bias.to(dev), rstd.to(dev), mean.to(dev), colsum.to(dev), simt=True)
+    err2 = (C2.cpu()[:, :N].double() - ref).abs().max().item() / scale
+    assert err2 < tol
+
+
+def test_gemm_back_to_back_is_deterministic(dev):
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(5)
+    M, N, K = 3000, 2048, 4096
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    C1 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    C2 = torch.empty_like(C1)
+    for _ in range(3):
+        ops.gemm_bf16_tn(A, B, M, N, K, C1)
+    ops.gemm_bf16_tn(A, B, M, N, K, C2)
+    assert torch.equal(C1, C2)
+    ref = A.float() @ B.float().T
+    assert (C1 - ref).abs().max().item() / ref.abs().max().item() < 1e-4
+
+
+def _cfg(D, H, k=1):
+    return types.SimpleNamespace(encoder_dim=D, llm_dim=H, encoder_projector_ds_rate=k)
+
+
+def test_projector_golden(dev, golden):
+    import ps_slm_b200.projector as P
+    g = golden["projector"]
+    for kind, cls, k, key in (("linear-silu", P.EncoderProjectorLinearSiLU, 1, "linear_silu"),
+                              ("linear", P.EncoderProjectorConcat, 2, "linear"),
+                              ("simple_linear", P.EncoderProjectorLinear, 3, "simple_linear")):
+        x = _t(g[f"{key}_x"])
+        D = x.shape[-1]
+        m = cls(_cfg(D, 32, k))
+        sd = {n[len(key) + 3:]: _t(g[n]) for n in g.files if n.startswith(key + "_p_")}
+        missing, unexpected = m.load_state_dict(sd, strict=True)          # same parameter names as the reference
+        assert not missing and not unexpected and m.k == k
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            y = m(x.to(dev)).cpu()
+        ref = _t(g[f"{key}_ref_y"])
+        assert y.shape == ref.shape and y.dtype == torch.float32
+        err = (y - ref).norm() / ref.norm()
+        assert err < 1e-2, f"{kind}: relative error {err}"           # bf16 tolerance of the north star
+
+
+def test_projector_linear_silu_full_width(dev):
+    """V=25055 → 2048 → 1536 on peaky posterior rows (plus a zero pad row) vs the fp32 oracle."""
+    import ps_slm_b200.projector as P
+    torch.manual_seed(0)
+    m = P.EncoderProjectorLinearSiLU(_cfg(25055, 1536))
+    with torch.no_grad():
+        m.norm.weight.uniform_(0.8, 1.2); m.norm.bias.uniform_(-0.05, 0.05); m.ffn[2].bias.uniform_(-0.1, 0.1)
+    x = torch.softmax(torch.randn(2, 40, 25055) * 6, -1)
+    x[1, 30:] = 0
+    sd = m.state_dict()
+    ref = O.projector_linear_silu(x, sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"],
+                                  sd["ffn.2.weight"], sd["ffn.2.bias"])
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    err = (y - ref).norm() / ref.norm()
+    assert err < 1e-2, f"relative error {err}"
+    rowerr = ((y - ref).norm(dim=-1) / ref.norm(dim=-1)).max()
+    assert rowerr < 2e-2, f"worst row relative error {rowerr}"
+
+
+@pytest.mark.parametrize("ragged,labels", [(False, False), (True, True)])
+def test_bridge_inference_vs_oracle(dev, ragged, labels):
+    """Whole fused path (ctc_lo → softmax/argmax → collapse → pool → projector → splice) against the
+    fp32 oracle on planted-label input: every integer bit-exact, embeddings within 1e-2."""
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(1)
+    B, T = 5, 120
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=7, ragged=ragged)
+    if labels:
+        ids, mask, lab = S.make_prompts(B, seed=3, left_pad=False, target_lens=[5, 9, 1, 30, 12])
+    else:
+        ids, mask, lab = S.make_prompts(B, seed=3, left_pad=True)
+    proj = P.EncoderProjectorLinearSiLU(_cfg(S.V_CTC, S.H_LLM))
+    with torch.no_grad():
+        proj.norm.weight.uniform_(0.8, 1.2); proj.norm.bias.uniform_(-0.05, 0.05)
+    table = S.make_embed_table(dtype=torch.float32)
+    sd = proj.state_dict()
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    (e_r, m_r, l_r, p_r, f_r), nl_r = O.bridge_inference(raw, raw_lens, w, b, pp, table, ids, mask, lab,
+                                                        S.SPEECH_ID, S.PAD_ID)
+    proj = proj.to(dev).eval()
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table.to(dev), S.SPEECH_ID, S.PAD_ID)
+    e, m, l, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev), None if lab is None else lab.to(dev))
+    assert torch.equal(nl.cpu(), nl_r)
+    assert e.shape == e_r.shape
+    assert torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    if lab is None:
+        assert l is None
+    else:
+        assert torch.equal(l.cpu(), l_r)
+    e = e.cpu().float()
+    text = ~torch.isin(torch.arange(e.shape[1])[None].expand(B, -1), torch.tensor([-1]))  # all positions
+    err = (e - e_r).norm() / e_r.norm()
+    assert err < 1e-2, f"inputs_embeds relative error {err}"
+    # audio rows alone (text rows are exact copies and would dilute the norm)
+    audio = m_r & (f_r == S.PAD_ID)
+    aerr = (e[audio] - e_r[audio]).norm() / e_r[audio].norm()
+    assert aerr < 1e-2, f"audio embedding relative error {aerr}"
+    assert torch.equal(e[~audio], e_r[~audio])
