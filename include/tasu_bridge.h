@@ -147,6 +147,8 @@ int tasu_fold_layernorm(const float* w1, int64_t w1_stride, const float* gamma, 
  * ctc_lo (ps-slm.py:450,581), nn.Linear(25055,2048)+SiLU and nn.Linear(2048,1536)
  * (projector.py:141-143), the Linear/ReLU of projector.py:35-37 and :16.
  *   lda/ldb/ldc in elements; A, B and C base pointers and row pitches must be 16-byte aligned.
+ *   Stores are clipped at row M and at column N rounded up to the next 16-byte boundary of the
+ *   row: pad columns inside the pitch may be written with zeros, nothing is written past it.
  *   bias [N] fp32 (EPI_BIAS*, LNFOLD), row_rstd/row_mean [M] and colsum [N] (LNFOLD only).
  */
 int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,

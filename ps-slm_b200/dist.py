@@ -1,0 +1,118 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the box,
+gloo in CPU tests).  The bridge shards by utterance with no data-path collective; NCCL is used
+only to all-gather per-rank compressed lengths + packed outputs for cross-rank packing and to
+all-reduce the projector gradients in training.
+
+* utterance sharding follows the reference's sample sharding ``i % world == rank``
+  (Multitask/dataset/speech_dataset_large.py:80-91);
+* the gradient all-reduce replaces DeepSpeed ZeRO-2's reduce-scatter of the 54.5 M trainable
+  projector parameters (Multitask/conf/ds_config.json:15-21, finetune_deepspeed.py:147-149).
+"""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(n: int, rank: int, world_size: int) -> List[int]:
+    """Global utterance indices owned by ``rank`` (utterance i → rank i % W)."""
+    return list(range(rank, n, world_size))
+
+
+def global_order(n: int, world_size: int) -> List[Tuple[int, int]]:
+    """For every global utterance i: (owner rank, local index)."""
+    return [(i % world_size, i // world_size) for i in range(n)]
+
+
+def all_gather_lengths(lens: torch.Tensor, group=None) -> List[torch.Tensor]:
+    """All-gather of the per-rank compressed lengths (ragged: ranks may own different counts)."""
+    rank, W = world()
+    if W == 1:
+        return [lens]
+    n = torch.tensor([lens.numel()], dtype=torch.int64, device=lens.device)
+    counts = [torch.zeros_like(n) for _ in range(W)]
+    dist.all_gather(counts, n, group=group)
+    m = int(max(int(c) for c in counts))
+    pad = torch.zeros(m, dtype=lens.dtype, device=lens.device)
+    pad[:lens.numel()] = lens
+    bufs = [torch.zeros_like(pad) for _ in range(W)]
+    dist.all_gather(bufs, pad, group=group)
+    return [b[:int(c)] for b, c in zip(bufs, counts)]
+
+
+def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None):
+    """Gather every rank's packed compressed rows ``[sum M_b, H]`` and lengths.
+
+    Returns ``(rows_global [sum over all utterances, H], lens_global [n_utts])`` in GLOBAL utterance
+    order (utterance i lives on rank i % W).  Lengths go first, then one padded-to-max all-gather of
+    the payload: on NVSwitch a flat all-gather is bandwidth-optimal, no topology-aware ring needed."""
+    rank, W = world()
+    if W == 1:
+        return rows, lens
+    all_lens = all_gather_lengths(lens, group)
+    totals = [int(l.sum()) for l in all_lens]
+    m = max(totals + [1])
+    H = rows.shape[1]
+    pad = torch.zeros(m, H, dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    bufs = [torch.empty_like(pad) for _ in range(W)]
+    dist.all_gather(bufs, pad, group=group)
+    n = sum(l.numel() for l in all_lens)
+    offs = [torch.cat([torch.zeros(1, dtype=torch.int64, device=l.device), torch.cumsum(l, 0)]) for l in all_lens]
+    pieces, glens = [], []
+    for r, j in global_order(n, W):
+        s, e = int(offs[r][j]), int(offs[r][j + 1])
+        pieces.append(bufs[r][s:e])
+        glens.append(all_lens[r][j])
+    rows_g = torch.cat(pieces, 0) if pieces else rows[:0]
+    return rows_g, torch.stack(glens) if glens else lens[:0]
+
+
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20, average: bool = True,
+                        group=None, async_op: bool = False):
+    """Bucketed gradient all-reduce of the projector parameters (54 512 062 params = 218 MB fp32 for
+    linear-silu).  Buckets are sized for launch latency/overlap, not link count: NVSwitch gives every
+    GPU full bandwidth to every peer.  Returns the list of (work, flat, grads) handles when async."""
+    rank, W = world()
+    if W == 1:
+        return []
+    grads = [p.grad for p in params if p.grad is not None]
+    handles, bucket, size = [], [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        handles.append((work, flat, bucket))
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    if async_op:
+        return handles
+    finish_allreduce(handles, W if average else 1)
+    return []
+
+
+def finish_allreduce(handles, divisor: int):
+    for work, flat, bucket in handles:
+        work.wait()
+        if divisor != 1:
+            flat.div_(divisor)
+        o = 0
+        for g in bucket:
+            n = g.numel()
+            g.copy_(flat[o:o + n].view_as(g))
+            o += n
