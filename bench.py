@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the TASU bridge hot path (BASELINE.json configs[1]: inference bridge).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host CPUs
+
+A step = one pass of ctc_lo → softmax/argmax → collapse compression → linear-silu projector →
+splice over one batch of B=64 synthetic 30-s utterances (T=500 frames of 512-d encoder output,
+V=25055) per GPU.  `value` = encoder frames consumed per second, whole job, inputs resident in
+HBM; `e2e` = the same through the public call with HOST buffers (pinned H2D of the inputs and
+D2H of inputs_embeds/mask/position ids inside the timed region).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "compressed audio frames/sec (encoder frames consumed by the posterior->compress->project->splice bridge)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=30.0, help="utterance length (60 ms frames)")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (defeats L2 reuse)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_workload(B, T, seed):
+    import torch
+    import ps_slm_b200.synth as S
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=seed)
+    ids, mask, _ = S.make_prompts(B, seed=seed, left_pad=True)
+    torch.manual_seed(0)
+    from oracle import tasu_oracle as O  # noqa: F401  (checker / CPU baseline only)
+    import torch.nn as nn
+    norm = nn.LayerNorm(S.V_CTC)
+    l1, l2 = nn.Linear(S.V_CTC, 2048), nn.Linear(2048, S.H_LLM)
+    pp = tuple(t.detach() for t in (norm.weight, norm.bias, l1.weight, l1.bias, l2.weight, l2.bias))
+    table = S.make_embed_table(dtype=torch.float32)
+    return dict(raw=raw, raw_lens=raw_lens, w=w, b=b, ids=ids, mask=mask, pp=pp, table=table)
+
+
+def cpu_step(wl):
+    """Reference algorithm, restated (oracle/tasu_oracle.py): softmax(ctc_lo) → per-frame psd loop
+    → LayerNorm/Linear/SiLU/Linear → merge, fp32, all host threads torch can use."""
+    import ps_slm_b200.synth as S
+    from oracle import tasu_oracle as O
+    return O.bridge_inference(wl["raw"], wl["raw_lens"], wl["w"], wl["b"], wl["pp"], wl["table"], wl["ids"],
+                              wl["mask"], None, S.SPEECH_ID, S.PAD_ID, vectorised=False)
+
+
+def run_cpu_baseline(sample_b, T, reps=1):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = cpu_workload(sample_b, T, seed=4242)
+    small = {k: (v[:1] if k in ("raw", "raw_lens", "ids", "mask") else v) for k, v in wl.items()}
+    with torch.no_grad():
+        cpu_step(small)                                   # warm the thread pool / allocator
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_step(wl)
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_b * T / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_b} utterances x {T} frames, fp32 torch-CPU port of the reference algorithm "
+                      f"(per-frame psd loop), {dt:.2f} s per pass"}, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port — the reference itself is a Python
+    tree that does not exist on the GPU box) timed on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    T = int(round(args.seconds / 0.06))
+    sample_b = min(args.cpu_sample, 4)
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = cpu_workload(sample_b, T, seed=4242)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            cpu_step({k: (v[:1] if k in ("raw", "raw_lens", "ids", "mask") else v) for k, v in wl.items()})
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step(wl)
+        dt = time.perf_counter() - t0
+    value = args.steps * sample_b * T / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] inference bridge, bounded sample: %d utterances x %d frames per step on host CPUs"
+                               % (sample_b, T), "batch_per_step": sample_b, "frames_per_utt": T, "V": 25055},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample_b} utterances x {T} frames per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) — runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, int(round(args.seconds / 0.06))
+    pk = peaks()
+
+    # ---- workload: rotating set of distinct input batches (utterance shard of this rank)
+    w, b = S.make_ctc_head()
+    torch.manual_seed(0)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    bridge = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    host, devb = [], []
+    for r in range(args.rotate):
+        raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=1000 * rank + r)
+        ids, mask, _ = S.make_prompts(B, seed=1000 * rank + r, left_pad=True)
+        hb = tuple(t.pin_memory() for t in (raw, raw_lens, ids, mask))
+        host.append(hb)
+        devb.append(tuple(t.to(dev) for t in hb))
+    in_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step_dev(i):
+        raw, raw_lens, ids, mask = devb[i % args.rotate]
+        return bridge(raw, raw_lens, ids, mask)
+
+    out_host = {}
+
+    def step_e2e(i):
+        hb = host[i % args.rotate]
+        raw, raw_lens, ids, mask = (t.to(dev, non_blocking=True) for t in hb)
+        emb, m, _, pos, nl = bridge(raw, raw_lens, ids, mask)
+        outs = (emb, m, pos, nl)
+        key = tuple(tuple(o.shape) for o in outs)
+        if key not in out_host:
+            out_host[key] = tuple(torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs)
+        for o, h in zip(outs, out_host[key]):
+            h.copy_(o, non_blocking=True)
+        return sum(o.numel() * o.element_size() for o in outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+        step_e2e(i)
+    # ---- device-resident timed region (value) with per-stage events
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    bridge.profile, bridge.events = True, []
+    launches0 = ops.COUNTERS["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.COUNTERS["launches"] - launches0
+    bridge.profile = False
+    stage_ms = {}
+    for name, a, z in bridge.events:
+        stage_ms.setdefault(name, []).append(a.elapsed_time(z))
+    counts = dict(bridge.last_counts)
+    # ---- end-to-end timed region (host buffers in, host buffers out)
+    barrier()
+    e0.record()
+    d2h = 0
+    for i in range(args.steps):
+        d2h = step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+
+    frames_per_step = B * T * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+    e2e_value = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline per stage (algorithmic bytes / flops)
+    V, D, Hb, H = S.V_CTC, S.D_ENC, 2048, S.H_LLM
+    n_in, n_out, sp_len = B * T, counts["n_out"], counts["spliced_len"]
+    n_text = int(devb[0][3].sum().item()) - B
+    kept_frames = None
+    avg = {k: sum(v) / len(v) * (len(v) / args.steps) for k, v in stage_ms.items()}   # ms per step
+    algo = {
+        "ctc_lo_gemm": ("tensor", 2.0 * B * (T + 4) * V * D),
+        "frame_stats": ("hbm", n_in * V * 4.0 + n_in * 16.0),
+        "softmax_meanpool": ("hbm", n_out * V * 4.0 + n_out * V * 2.0),     # ≥1 frame per kept row (lower bound)
+        "projector_gemm1": ("tensor", 2.0 * n_out * V * Hb),
+        "projector_gemm2": ("tensor", 2.0 * n_out * Hb * H),
+        "splice_scatter": ("hbm", (n_out + n_text + B * sp_len) * H * 2.0 + B * sp_len * 17.0),
+    }
+    kernels = {}
+    for name, (bound, work) in algo.items():
+        if name not in avg or avg[name] <= 0:
+            continue
+        t = avg[name] / 1e3
+        if bound == "hbm":
+            ach, peak, unit = work / t / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = work / t / 1e12, pk["bf16_tflops"], "TFLOP/s"
+        kernels[name] = {"bound": bound, "ms": avg[name], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+    for name in avg:
+        if name not in kernels:
+            kernels[name] = {"ms": avg[name]}
+    dominant = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms"])
+    roof = dict(kernels[dominant])
+    roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["source"] + " (MEASURED_PEAKS.json, sustained bf16 / copy HBM)"})
+    roof.pop("ms", None)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _ = run_cpu_baseline(args.cpu_sample, T)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1] inference bridge: %d utterances/GPU x %.0f s (T=%d frames, 512-d synthetic encoder "
+                               "output) -> ctc_lo -> softmax/argmax -> collapse -> linear-silu projector (25055->2048->1536) "
+                               "-> splice with Qwen2.5-1.5B-shaped embed table" % (B, args.seconds, T),
+                   "batch_per_gpu": B, "frames_per_utt": T, "V": V, "compressed_rows_per_step": n_out,
+                   "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
+                   "l2": "rotating %d distinct input batches (%.0f MB) and a 3.2 GB logits intermediate per step (> 126 MB L2)"
+                         % (args.rotate, args.rotate * in_bytes / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kernels,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,16 +114,40 @@ def cast_weight_bf16(w: torch.Tensor) -> torch.Tensor:
 
 def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Tensor, rstd: torch.Tensor,
                         w1g: torch.Tensor, colsum: torch.Tensor, dbias: torch.Tensor, w2: torch.Tensor,
-                        b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False) -> torch.Tensor:
+                        b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False, stage=None) -> torch.Tensor:
     """LayerNorm → Linear → SiLU → Linear of projector.py:149-151 as two tensor-core GEMMs:
     GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue."""
     Hb, H = w1g.shape[0], w2.shape[0]
     dev = x_bf16.device
+    import contextlib
+    stage = stage or (lambda name: contextlib.nullcontext())
     h1 = torch.empty(rows, Hb, dtype=torch.bfloat16, device=dev)
-    ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt)
+    with stage("projector_gemm1"):
+        ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt)
     y = torch.empty(rows, H, dtype=out_dtype, device=dev)
-    ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt)
+    with stage("projector_gemm2"):
+        ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt)
     return y
+
+
+class _Stage:
+    """Context manager recording a CUDA-event pair on the current stream around one stage."""
+
+    def __init__(self, owner, name):
+        self.owner, self.name = owner, name
+
+    def __enter__(self):
+        if self.owner.profile:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.owner.profile:
+            self.t1.record()
+            self.owner.events.append((self.name, self.t0, self.t1))
+        return False
 
 
 class TasuBridge:
@@ -148,6 +172,11 @@ class TasuBridge:
         self.blank_id, self.blank_threshold, self.ln_eps = int(blank_id), float(blank_threshold), float(ln_eps)
         self._ctc_cache = ProjectorCache()
         self.last_counts = {}
+        self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
+        self.events = []              # [(stage name, start event, end event)] of the profiled calls
+
+    def _stage(self, name):
+        return _Stage(self, name)
 
     def _ctc_weights(self):
         def build():
@@ -170,23 +199,29 @@ class TasuBridge:
         out_dtype = self.embed_table.dtype
 
         # splice row statistics only depend on the prompt: issue them first
-        sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
+        with self._stage("splice_plan"):
+            sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
 
         # (a1) ctc_lo on the tensor cores: logits [B*(T+4), ldv] fp32
         x2 = raw_encoder_out.reshape(B * T4, Denc)
         if x2.dtype != torch.bfloat16:
-            x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+            with self._stage("cast_encoder_out"):
+                x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
         ldv = ops.pad_to(V, 4)
         logits = torch.empty(B * T4, ldv, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_tn(x2, w_ctc, B * T4, V, Denc, logits, L.EPI_BIAS, b_ctc)
+        with self._stage("ctc_lo_gemm"):
+            ops.gemm_bf16_tn(x2, w_ctc, B * T4, V, Denc, logits, L.EPI_BIAS, b_ctc)
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
         post_view = logits.view(B, T4, ldv)[:, self.N_PREFIX:, :V]      # ps-slm.py:583 (logits, not probs)
 
         # (a2) stats + collapse plan, (a8) splice plan; one header for both
         header = torch.empty(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64, device=dev)
-        st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
-        plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
-        ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
+        with self._stage("frame_stats"):
+            st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
+        with self._stage("collapse_plan"):
+            plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
+        with self._stage("splice_plan"):
+            ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
         hdr = header.cpu()                                              # the single device→host read
         n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
         shdr = hdr[L.CH_WORDS:]
@@ -199,15 +234,18 @@ class TasuBridge:
             pooled = torch.empty(n_out, ldk, dtype=torch.bfloat16, device=dev)
             mean = torch.empty(n_out, dtype=torch.float32, device=dev)
             rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
-            ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
-                                 ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
+            with self._stage("softmax_meanpool"):
+                ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
+                                     ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
             # (a5) projector
-            audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype)
+            audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
+                                        stage=self._stage)
         else:
             audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
         # (a7+a8) splice with the embedding lookup fused
-        emb, mask, out_labels, pos, fids = ops.splice_scatter(
-            sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
-            want_ids=want_ids)
+        with self._stage("splice_scatter"):
+            emb, mask, out_labels, pos, fids = ops.splice_scatter(
+                sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
+                want_ids=want_ids)
         self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len}
         return emb, mask, out_labels, pos, plan.new_lens

@@ -1,0 +1,262 @@
+"""Drop-in plugin surface: ``model_factory`` / ``slam_model_asr`` with the bridge on B200 kernels.
+
+Select it from the reference's launch scripts with
+``++model_config.file=<repo>/ps-slm_b200/model.py:model_factory`` — the loader
+(Multitask/utils/model_utils.py:9-33) only needs a ``.py`` path and a function name, and calls
+``model_factory(train_config, model_config, **kwargs) -> (model, tokenizer)``
+(Multitask/finetune_deepspeed.py:127-128, Multitask/inference_batch.py:113-114).
+
+Only the bridge is replaced.  Tokenizer, LLM and SenseVoice encoder are still built by the
+reference's own ``setup_tokenizer / setup_llm / setup_encoder`` (Multitask/model/ps-slm.py:25-40,
+:89-127), found through ``TASU_REFERENCE_ROOT`` or the current working directory (the reference's
+entry points run from ``Multitask/``).  ``slam_model_asr`` below keeps the reference's method
+names, signatures, return tuples, flags and printed-nothing behaviour for:
+
+* ``psd``                                   (ps-slm.py:237-317)
+* ``ctc_pseudo_posterior`` / ``_noise``     (ps-slm.py:337-409)
+* ``_merge_input_ids_with_audio_features``  (ps-slm.py:679-873)
+* ``forward`` / ``generate`` dispatch       (ps-slm.py:411-537, :539-677)
+"""
+import importlib.util
+import os
+import re
+import sys
+import types
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+try:  # imported as part of the package …
+    from . import bridge as _bridge, sim as _sim
+    from .projector import PROJECTORS
+except ImportError:  # … or loaded by file path through the reference's plugin loader
+    _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if _root not in sys.path:
+        sys.path.insert(0, _root)
+    import ps_slm_b200.bridge as _bridge
+    import ps_slm_b200.sim as _sim
+    from ps_slm_b200.projector import PROJECTORS
+
+
+def _load_reference_module():
+    """The reference's model/ps-slm.py (for setup_tokenizer / setup_llm / setup_encoder only)."""
+    root = os.environ.get("TASU_REFERENCE_ROOT", os.getcwd())
+    path = os.path.join(root, "model", "ps-slm.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(
+            "reference tree not found (looked for %s); run from the reference's Multitask/ directory or set "
+            "TASU_REFERENCE_ROOT" % path)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    spec = importlib.util.spec_from_file_location("tasu_reference_ps_slm", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def setup_encoder_projector(train_config, model_config, **kwargs):
+    """String → class dispatch of ps-slm.py:43-86 for the in-scope plugins."""
+    name = model_config.encoder_projector
+    if name not in PROJECTORS:
+        raise NotImplementedError(
+            "encoder_projector=%r is outside the B200 bridge scope (have: %s)" % (name, sorted(PROJECTORS)))
+    encoder_projector = PROJECTORS[name](model_config)
+    if name == "linear-silu" and getattr(train_config, "freeze_projector", False):
+        for _, param in encoder_projector.named_parameters():
+            param.requires_grad = False
+        encoder_projector.eval()
+    if name == "simple_linear" and getattr(model_config, "ctc_linear", None):
+        # pretrained CTC head over the LLM vocab (ps-slm.py:67-85)
+        ckpt = torch.load(model_config.ctc_linear, map_location="cpu")
+        w, b = ckpt.get("ctc_lo.weight"), ckpt.get("ctc_lo.bias")
+        if w is None or b is None:
+            raise KeyError("ctc_linear checkpoint needs ctc_lo.weight / ctc_lo.bias")
+        with torch.no_grad():
+            encoder_projector.map.weight.copy_(w)
+            encoder_projector.map.bias.copy_(b)
+    return encoder_projector
+
+
+def model_factory(train_config, model_config, **kwargs):
+    ref = _load_reference_module()
+    tokenizer = ref.setup_tokenizer(train_config, model_config, **kwargs)
+    tokenizer.add_special_tokens({"additional_special_tokens": ["<speech>"]})
+    tokenizer.default_ignore_token = -100
+    tokenizer.default_speech_token = tokenizer.convert_tokens_to_ids("<speech>")
+    llm = ref.setup_llm(train_config, model_config, **kwargs)
+    encoder = ref.setup_encoder(train_config, model_config, **kwargs)
+    encoder_projector = setup_encoder_projector(train_config, model_config, **kwargs)
+    model = slam_model_asr(encoder, llm, encoder_projector, tokenizer, train_config, model_config, **kwargs)
+    ckpt_path = kwargs.get("ckpt_path", None)
+    if ckpt_path is not None:                       # ps-slm.py:163-170: overlay, strict=False
+        model.load_state_dict(torch.load(ckpt_path, map_location="cpu"), strict=False)
+    return model, tokenizer
+
+
+def _cfg_get(cfg, name, default=None):
+    if hasattr(cfg, "get"):
+        try:
+            return cfg.get(name, default)
+        except Exception:
+            pass
+    return getattr(cfg, name, default)
+
+
+class slam_model_asr(nn.Module):
+    def __init__(self, encoder, llm, encoder_projector, tokenizer, train_config, model_config, **kwargs):
+        super().__init__()
+        self.encoder = encoder
+        self.llm = llm
+        self.encoder_projector = encoder_projector
+        self.tokenizer = tokenizer
+        self.metric = kwargs.get("metric", "acc")
+        self.train_config = train_config
+        self.model_config = model_config
+        self.ctc_posterior = _cfg_get(train_config, "ctc_posterior", False)
+        self.do_psd = _cfg_get(train_config, "do_psd", False)
+        self.voca_trans = _cfg_get(train_config, "voca_trans", False)
+        self.gt_emb = _cfg_get(train_config, "gt_emb", False)
+        self.gt_emb_noise = _cfg_get(train_config, "gt_emb_noise", False)
+        self.top1_emb = _cfg_get(train_config, "top1_emb", False)
+        self.cross_attn = model_config.encoder_projector == "cross-attention"
+        if self.voca_trans or self.cross_attn:
+            raise NotImplementedError("voca_trans / cross-attention are 'next' rows of the scope table (SURVEY §8f)")
+        self.encoder_tokenizer = kwargs.get("encoder_tokenizer", None)
+        if self.encoder_tokenizer is None and (self.gt_emb or kwargs.get("need_encoder_tokenizer", False)):
+            ref = _load_reference_module()           # SentencePiece wrapper of the reference (host-side, out of scope)
+            from model.tokenizer import SenseVoiceTokenizer  # noqa: F401  (reference module on sys.path)
+            self.encoder_tokenizer = SenseVoiceTokenizer(model_config.encoder_path)
+            del ref
+        self._bridge = None
+
+    # ------------------------------------------------------------------ bridge methods
+    def psd(self, encoder_out, encoder_out_lens, ctc_posterior, blank_id: int = 0, blank_threshold: float = 0.90):
+        return _bridge.psd(encoder_out, encoder_out_lens, ctc_posterior, blank_id, blank_threshold)
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def ctc_pseudo_posterior(self, texts: List[str]):
+        ids_list = [self.encoder_tokenizer.encode(t) for t in texts]
+        return _sim.ctc_pseudo_posterior(ids_list, self.encoder_tokenizer.vocab_size, self._device())
+
+    def ctc_pseudo_posterior_noise(self, texts: List[str]):
+        ids_list = [self.encoder_tokenizer.encode(t) for t in texts]
+        return _sim.ctc_pseudo_posterior_noise(
+            ids_list, self.encoder_tokenizer.vocab_size, self._device(), blank_id=self.encoder.blank_id,
+            drop_prob=getattr(self, "drop_prob", 0.05), insert_prob=getattr(self, "insert_prob", 0.0),
+            smooth_low=getattr(self, "smooth_low", 0.0), smooth_high=getattr(self, "smooth_high", 0.1))
+
+    def _merge_input_ids_with_audio_features(self, audio_features, num_audio_tokens, inputs_embeds, input_ids,
+                                             attention_mask, labels):
+        return _bridge.merge_input_ids_with_audio_features(
+            audio_features, num_audio_tokens, inputs_embeds, input_ids, attention_mask, labels,
+            self.tokenizer.default_speech_token, self.tokenizer.pad_token_id, self.tokenizer.default_ignore_token)
+
+    # ------------------------------------------------------------------ shared front end
+    def _encode(self, input_features, input_feature_length):
+        """SenseVoice front end + encoder (ps-slm.py:427-447) — upstream of the bridge, unchanged."""
+        speech = input_features
+        B = speech.size(0)
+        q = lambda ids: self.encoder.embed(torch.tensor([ids], device=speech.device)).repeat(B, 1, 1)  # noqa: E731
+        speech = torch.cat([q([0]), q([1, 2]), q([2]), speech], dim=1)
+        out, out_lens = self.encoder.encoder(speech, input_feature_length + 4)
+        if isinstance(out, tuple):
+            out = out[0]
+        return out, out_lens
+
+    def _fused_bridge(self):
+        if self._bridge is None:
+            ctc_lo = self.encoder.ctc.ctc_lo
+            self._bridge = _bridge.TasuBridge(
+                ctc_lo.weight, ctc_lo.bias, self.encoder_projector, self.llm.get_input_embeddings().weight,
+                self.tokenizer.default_speech_token, self.tokenizer.pad_token_id, self.tokenizer.default_ignore_token,
+                blank_id=self.encoder.blank_id)
+        return self._bridge
+
+    def _bridge_outputs(self, raw_encoder_out, raw_encoder_out_lens, input_ids, attention_mask, labels, texts, noisy):
+        """Steps 1–4 of the hot path with the reference's flag dispatch (ps-slm.py:456-528 / :587-658)."""
+        table = self.llm.get_input_embeddings().weight
+        fused_ok = (self.ctc_posterior and not self.gt_emb and self.do_psd
+                    and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
+                    and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_projector.parameters()))
+                    and table.dtype in (torch.float32, torch.bfloat16))
+        if fused_ok:                                           # shipped inference configuration
+            emb, mask, out_labels, pos, _ = self._fused_bridge()(raw_encoder_out, raw_encoder_out_lens, input_ids,
+                                                                 attention_mask, labels)
+            return emb, mask, out_labels, pos
+        blank = self.encoder.blank_id
+        encoder_out = raw_encoder_out[:, 4:, :]
+        encoder_out_lens = torch.clamp(raw_encoder_out_lens - 4, min=0)
+        if self.ctc_posterior:
+            if self.gt_emb:
+                post, lens = (self.ctc_pseudo_posterior_noise(texts) if noisy else self.ctc_pseudo_posterior(texts))
+                encoder_outs, feat_len = post.to(input_ids.device), lens.to(input_ids.device)
+            else:
+                logits = self.encoder.ctc.ctc_lo(raw_encoder_out)
+                post = torch.softmax(logits, dim=-1)[:, 4:, :]
+                if self.do_psd:
+                    encoder_outs, feat_len = self.psd(post, encoder_out_lens, post, blank)
+                else:
+                    encoder_outs, feat_len = post, encoder_out_lens
+        else:
+            if self.do_psd:
+                logits = self.encoder.ctc.ctc_lo(raw_encoder_out)
+                post = torch.softmax(logits, dim=-1)[:, 4:, :]
+                encoder_outs, feat_len = self.psd(encoder_out, encoder_out_lens, post, blank)
+            else:
+                encoder_outs, feat_len = encoder_out, encoder_out_lens
+        projector_outs = self.encoder_projector(encoder_outs)
+        feat_len = feat_len // self.encoder_projector.k
+        inputs_embeds = self.llm.get_input_embeddings()(input_ids)
+        emb, mask, out_labels, pos, _ = self._merge_input_ids_with_audio_features(
+            projector_outs, feat_len, inputs_embeds, input_ids, attention_mask, labels)
+        return emb, mask, out_labels, pos
+
+    # ------------------------------------------------------------------ reference entry points
+    def forward(self, input_ids: torch.LongTensor = None, input_features: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None, input_feature_length: Optional[torch.Tensor] = None,
+                position_ids=None, past_key_values=None, inputs_embeds=None, GT: Optional[List[str]] = None,
+                labels: Optional[torch.LongTensor] = None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None):
+        if self.ctc_posterior and self.gt_emb:
+            # text-only branch: the encoder output is never used (ps-slm.py:459-468); skipping the dead
+            # encoder pass changes no result
+            raw, raw_lens = None, None
+        else:
+            raw, raw_lens = self._encode(input_features, input_feature_length)
+        inputs_embeds, attention_mask, labels, position_ids = self._bridge_outputs(
+            raw, raw_lens, input_ids, attention_mask, labels, GT, self.gt_emb_noise)
+        model_outputs = self.llm(inputs_embeds=inputs_embeds, attention_mask=attention_mask, labels=labels,
+                                 position_ids=position_ids)
+        acc = -1
+        if self.metric:
+            with torch.no_grad():
+                preds = torch.argmax(model_outputs.logits, -1)
+                tgt = labels.detach()[:, 1:]
+                keep = tgt != self.tokenizer.default_ignore_token
+                acc = ((preds.detach()[:, :-1][keep] == tgt[keep]).sum().float() / keep.sum().float())
+        return model_outputs, acc
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.LongTensor = None, input_features: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, input_feature_length: Optional[torch.Tensor] = None,
+                 position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
+                 output_attentions=None, output_hidden_states=None, return_dict=None, targets=None, **kwargs):
+        texts = None
+        if self.ctc_posterior and self.gt_emb:
+            texts = [re.sub(r"[^A-Za-z\s.,!?]+", "", t).lower().strip() for t in targets]   # ps-slm.py:592-594
+            raw, raw_lens = None, None
+        else:
+            raw, raw_lens = self._encode(input_features, input_feature_length)
+        inputs_embeds, attention_mask, labels, position_ids = self._bridge_outputs(
+            raw, raw_lens, input_ids, attention_mask, labels, texts, False)
+        return self.llm.generate(
+            inputs_embeds=inputs_embeds,
+            max_new_tokens=kwargs.get("max_new_tokens", 200), num_beams=kwargs.get("num_beams", 4),
+            do_sample=kwargs.get("do_sample", False), min_length=kwargs.get("min_length", 1),
+            top_p=kwargs.get("top_p", 1.0), repetition_penalty=kwargs.get("repetition_penalty", 1.0),
+            length_penalty=kwargs.get("length_penalty", 1.0), temperature=kwargs.get("temperature", 1.0),
+            attention_mask=attention_mask, bos_token_id=self.tokenizer.bos_token_id,
+            eos_token_id=self.tokenizer.eos_token_id, pad_token_id=self.tokenizer.pad_token_id)

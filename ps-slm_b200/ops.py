@@ -11,6 +11,11 @@ import torch
 from . import _lib as L
 
 V_ALIGN = 64          # leading dimension padding (elements) of buffers this package owns
+COUNTERS = {"launches": 0}   # kernels of libtasu_bridge.so launched through this module (bench's gpu_launches)
+
+
+def _count(n: int = 1):
+    COUNTERS["launches"] += n
 
 
 def _stream():
@@ -70,6 +75,7 @@ def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[
     L.check(L.lib().tasu_frame_stats(x.data_ptr(), _dt(x), input_kind, B, T, V, bs, rs, blank_id, _ptr(lens),
                                      st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
                                      _ptr(st.row_sumexp), st.gmax.data_ptr(), _stream()), "tasu_frame_stats")
+    _count(1)
     return st
 
 
@@ -99,6 +105,7 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
                                    _ptr(p.seg_score), p.new_lens.data_ptr(), _stream()), "tasu_collapse_plan")
     L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
                                    B, p.row_off.data_ptr(), p.header.data_ptr(), _stream()), "tasu_collapse_scan")
+    _count(2)
     return p
 
 
@@ -116,6 +123,7 @@ def segment_meanpool(feats: torch.Tensor, plan: CollapsePlan, layout: int, max_l
         plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.row_off.data_ptr(),
         layout, max_len, max_rows, out.data_ptr(), _dt(out), out_row_stride,
         _ptr(ln_mean), _ptr(ln_rstd), float(ln_eps), _stream()), "tasu_segment_meanpool")
+    _count(1)
     return out
 
 
@@ -135,6 +143,7 @@ def cast_rows(src: torch.Tensor, dst_dtype: torch.dtype, dst_stride: Optional[in
     L.check(L.lib().tasu_cast_rows(src.data_ptr(), _dt(src), rows, cols, src.stride(0) if rows > 1 else cols,
                                    dst.data_ptr(), _dt(dst), dst_stride, _ptr(mean), _ptr(rstd), float(ln_eps),
                                    _stream()), "tasu_cast_rows")
+    _count(1)
     return dst, mean, rstd
 
 
@@ -152,6 +161,7 @@ def fold_layernorm(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1
                                         _ptr(b1.float().contiguous()) if b1 is not None else None, N, K,
                                         w1g.data_ptr(), ld, colsum.data_ptr(), dbias.data_ptr(), _stream()),
             "tasu_fold_layernorm")
+    _count(1)
     return w1g, colsum, dbias
 
 
@@ -170,6 +180,7 @@ def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out:
     L.check(fn(A.data_ptr(), lda, Bw.data_ptr(), ldb, out.data_ptr(), _dt(out), ldc, M, N, K, epilogue,
                _ptr(bias), _ptr(row_rstd), _ptr(row_mean), _ptr(colsum), _stream()),
             "tasu_gemm_bf16_tn_simt" if simt else "tasu_gemm_bf16_tn")
+    _count(1)
     return out
 
 
@@ -182,6 +193,7 @@ def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor,
                                             tok.numel(), V, out.data_ptr(), _dt(out), out_row_stride,
                                             _ptr(ln_mean), _ptr(ln_rstd), float(ln_eps), _stream()),
             "tasu_sim_posterior_rows")
+    _count(1)
     return out
 
 
@@ -209,6 +221,7 @@ def splice_rowstat(input_ids: torch.Tensor, attention_mask: torch.Tensor, speech
     p.rowstat = torch.empty(max(B, 1), 8, dtype=torch.int32, device=dev)
     L.check(L.lib().tasu_splice_rowstat(p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, B, S,
                                         p.speech_id, p.rowstat.data_ptr(), _stream()), "tasu_splice_rowstat")
+    _count(1)
     return p
 
 
@@ -231,6 +244,7 @@ def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: 
     L.check(lib.tasu_splice_header(p.rowstat.data_ptr(), num_audio.data_ptr(), p.n_audio, div_k, B, S,
                                    p.header.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), _stream()),
             "tasu_splice_header")
+    _count(2)
     return p
 
 
@@ -275,6 +289,7 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
         p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(), pad_id, ignore_id,
         emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), _stream()),
         "tasu_splice_scatter")
+    _count(1)
     return emb, mask, out_labels, pos, fids
 
 
@@ -293,4 +308,5 @@ def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, 
         B, p.S, Sp, H, p.speech_id, p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(),
         p.slot_ord.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(),
         audio_layout, H, audio_max_len, p.n_audio, ga.data_ptr(), _stream()), "tasu_splice_audio_grad")
+    _count(1)
     return ga
