@@ -286,12 +286,11 @@ def b200_arm(args):
     V, D, Hb, H = S.V_CTC, S.D_ENC, 2048, S.H_LLM
     n_in, n_out, sp_len = B * T, counts["n_out"], counts["spliced_len"]
     n_text = int(devb[0][3].sum().item()) - B
-    kept_frames = None
     avg = {k: sum(v) / len(v) * (len(v) / args.steps) for k, v in stage_ms.items()}   # ms per step
     algo = {
         "ctc_lo_gemm": ("tensor", 2.0 * B * (T + 4) * V * D),
         "frame_stats": ("hbm", n_in * V * 4.0 + n_in * 16.0),
-        "softmax_meanpool": ("hbm", n_out * V * 4.0 + n_out * V * 2.0),     # ≥1 frame per kept row (lower bound)
+        "softmax_meanpool": ("hbm", counts["kept_frames"] * V * 4.0 + n_out * V * 2.0),
         "projector_gemm1": ("tensor", 2.0 * n_out * V * Hb),
         "projector_gemm2": ("tensor", 2.0 * n_out * Hb * H),
         "splice_scatter": ("hbm", (n_out + n_text + B * sp_len) * H * 2.0 + B * sp_len * 17.0),

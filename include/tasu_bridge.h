@@ -52,6 +52,7 @@ enum { TASU_SH_SPLICED_LEN = 0,   /* S' = max_b sum(placeholders)            ps-
 enum { TASU_CH_N_OUT = 0,         /* total compressed rows  sum_b M_b */
        TASU_CH_MAX_LEN = 1,       /* max_b M_b              ps-slm.py:303 */
        TASU_CH_IS_LOGPROB = 2,    /* 1 if input was detected as log-probs  ps-slm.py:256 */
+       TASU_CH_KEPT_FRAMES = 3,   /* input frames feeding the kept rows (sum of kept run lengths) */
        TASU_CH_WORDS = 4 };
 
 int tasu_abi_version(void);
@@ -84,16 +85,17 @@ int tasu_frame_stats(const void* x, int dtype, int input_kind, int B, int T, int
  * compaction by block scan.  Replaces the Python loop ps-slm.py:259-301.
  *   seg_start/seg_len/seg_score [B*T]  kept candidates of utterance b at [b*T, b*T+M_b)
  *   new_lens   [B] int64  M_b  (ps-slm.py:315)
+ *   kept_frames [B] int32 or NULL: number of input frames covered by the kept candidates
  */
 int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float* row_max,
                        const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
                        const int64_t* lens, int B, int T, int blank_id, float threshold,
                        int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
-                       void* stream);
+                       int32_t* kept_frames, void* stream);
 
 /* exclusive scan of new_lens → row_off [B+1] int32, header [TASU_CH_WORDS] int64 */
-int tasu_collapse_scan(const int64_t* new_lens, const uint32_t* global_max_enc, int B,
-                       int32_t* row_off, int64_t* header, void* stream);
+int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, const uint32_t* global_max_enc,
+                       int B, int32_t* row_off, int64_t* header, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,

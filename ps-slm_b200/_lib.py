@@ -17,7 +17,7 @@ F32, BF16 = 0, 1
 INPUT_PROBS, INPUT_LOGITS = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU = 0, 1, 2, 3, 4
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
-CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_WORDS = 0, 1, 2, 4
+CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
@@ -26,8 +26,8 @@ SIGNATURES = {
     "tasu_last_error": (c_char_p, []),
     "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
-    "tasu_collapse_scan": (_I, [_P, _P, _I, _P, _P, _P]),
+    "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),

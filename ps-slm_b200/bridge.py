@@ -247,5 +247,6 @@ class TasuBridge:
             emb, mask, out_labels, pos, fids = ops.splice_scatter(
                 sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
                 want_ids=want_ids)
-        self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len}
+        self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len,
+                            "kept_frames": int(hdr[L.CH_KEPT_FRAMES])}
         return emb, mask, out_labels, pos, plan.new_lens

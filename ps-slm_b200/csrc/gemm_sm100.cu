@@ -35,7 +35,8 @@ constexpr int kABytes = BM * BK * 2;                 // 16 KB
 constexpr int kBBytes = BN * BK * 2;                 // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
 constexpr int kStagingBytes = BM * 128;              // one 128-byte-wide column chunk of the C tile
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kAuxBytes = 2 * BN * 4;                // per-tile bias / colsum slices
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + kAuxBytes + 128 /*barriers*/;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,7 +123,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers are passed as in/out operands so the compiler cannot schedule their consumers above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
 
@@ -136,14 +148,16 @@ struct Params {
 };
 
 // kOutBf16: C is bf16 (64 columns per 128-byte staging row) else fp32 (32 columns)
-template <bool kOutBf16>
+template <bool kOutBf16, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];          // 128B-swizzle atoms need 1024-byte alignment
+    if ((smem_u32(smem) & 1023u) != 0) __trap();               // no static shared memory in this kernel → offset 0
     uint8_t* staging = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+    float* s_bias = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
+    float* s_colsum = s_bias + BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes + kAuxBytes);
     uint64_t* full_bar = bars;                           // [kStages]
     uint64_t* empty_bar = bars + kStages;                // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;            // [kAccStages]
@@ -220,84 +234,112 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int ew = warp - 4;                                   // TMEM lanes [32*ew, 32*ew+32)
-        const int row_in_tile = ew * 32 + lane;
-        constexpr int kColsPerChunk = kOutBf16 ? 64 : 32;          // 128 bytes of C per row
-        constexpr int kChunks = BN / kColsPerChunk;
+        const int et = threadIdx.x - (kThreads - kEpiThreads);     // 0..127 = row of the tile
+        constexpr int kSubs = BN / 32;                             // 32-column TMEM loads per tile
+        constexpr int kSubsPerChunk = kOutBf16 ? 2 : 1;            // one staging chunk = 128 bytes of C per row
+        constexpr int kColsPerChunk = 32 * kSubsPerChunk;
+        const uint32_t stg_u32 = smem_u32(staging);
+        const int sw = et & 7;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            const int grow = m0 + row_in_tile;
-            float rstd = 1.f, mean = 0.f;
-            if (p.epilogue == TASU_EPI_LNFOLD_SILU && grow < p.M) { rstd = p.row_rstd[grow]; mean = p.row_mean[grow]; }
+            const int grow = m0 + et;
+            // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
+            // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
+            if (kEpi != TASU_EPI_NONE) {
+                for (int c = et; c < BN; c += kEpiThreads) {
+                    const int col = n0 + c;
+                    s_bias[c] = col < p.N ? __ldg(p.bias + col) : 0.f;
+                    if (kEpi == TASU_EPI_LNFOLD_SILU) s_colsum[c] = col < p.N ? __ldg(p.colsum + col) : 0.f;
+                }
+            }
+            float rstd = 1.f, nmean = 0.f;
+            if (kEpi == TASU_EPI_LNFOLD_SILU && grow < p.M) { rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow); }
+            const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+
+            // one 32-column slab: epilogue math in registers, swizzled st.shared, TMA store per chunk
+            auto process = [&](uint32_t (&v)[32], int sub) {
+                const int ch = sub / kSubsPerChunk, h = sub % kSubsPerChunk;
+                if (ch >= n_chunks) return;                            // fully clipped (uniform over the 4 warps)
+                const uint32_t srow = stg_u32 + (uint32_t)(sbuf * kStagingBytes + et * 128);
+                if (h == 0) {
+                    // the TMA store that last read this staging buffer must have finished reading it
+                    if (et == 0) tma_store_wait_read<1>();
+                    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                }
+                float f[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + sub * 32);
+                const float4* c4 = reinterpret_cast<const float4*>(s_colsum + sub * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float x[4] = {__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                  __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])};
+                    if (kEpi != TASU_EPI_NONE) {
+                        const float4 bb = b4[q];
+                        const float b[4] = {bb.x, bb.y, bb.z, bb.w};
+                        if (kEpi == TASU_EPI_LNFOLD_SILU) {
+                            const float4 cc = c4[q];
+                            const float c[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = silu_f(fmaf(rstd, fmaf(nmean, c[e], x[e]), b[e]));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                x[e] += b[e];
+                                if (kEpi == TASU_EPI_BIAS_SILU) x[e] = silu_f(x[e]);
+                                if (kEpi == TASU_EPI_BIAS_RELU) x[e] = fmaxf(x[e], 0.f);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) f[4 * q + e] = x[e];
+                }
+                if (kOutBf16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)        // 32 columns → 64 bytes → 16-byte pieces 4h .. 4h+3
+                        st_shared_u4(srow + (uint32_t)((((h * 4 + q) ^ sw)) * 16),
+                                     pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                     pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        st_shared_u4(srow + (uint32_t)((q ^ sw) * 16), __float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                     __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+                }
+                if (h == kSubsPerChunk - 1) {
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                    if (et == 0) {
+                        tma_store_2d(&tmap_c, staging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        tma_store_commit();
+                    }
+                    sbuf ^= 1;
+                }
+            };
+
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
 #pragma unroll 1
-            for (int ch = 0; ch < kChunks; ++ch) {
-                const int c0 = n0 + ch * kColsPerChunk;
-                if (c0 >= p.N) break;                               // warp-uniform: fully clipped chunk
-                uint8_t* stg = staging + sbuf * kStagingBytes;
-                // the TMA store that last read this staging buffer must have finished reading
-                if (threadIdx.x == kThreads - kEpiThreads) tma_store_wait_read<1>();
-                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
-                uint8_t* srow = stg + row_in_tile * 128;
-                const int sw = row_in_tile & 7;
-#pragma unroll
-                for (int h = 0; h < kColsPerChunk / 32; ++h) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + (uint32_t)(ch * kColsPerChunk + h * 32), v);
-                    tmem_ld_wait();
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(v[i]);
-                        const int col = c0 + h * 32 + i;
-                        const bool ok = col < p.N;
-                        if (p.epilogue == TASU_EPI_LNFOLD_SILU) {
-                            const float cs = ok ? __ldg(p.colsum + col) : 0.f;
-                            const float bb = ok ? __ldg(p.bias + col) : 0.f;
-                            x = silu_f(fmaf(rstd, x - mean * cs, bb));
-                        } else if (p.epilogue != TASU_EPI_NONE) {
-                            x += ok ? __ldg(p.bias + col) : 0.f;
-                            if (p.epilogue == TASU_EPI_BIAS_SILU) x = silu_f(x);
-                            else if (p.epilogue == TASU_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
-                        }
-                        f[i] = x;
-                    }
-                    if (kOutBf16) {
-                        // 32 columns → 64 bytes → 16-byte pieces 4h .. 4h+3 of the 128-byte row
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int piece = (h * 4 + q) ^ sw;
-                            uint4 o = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
-                                                 pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
-                            *reinterpret_cast<uint4*>(srow + piece * 16) = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int piece = q ^ sw;
-                            uint4 o = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
-                                                 __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
-                            *reinterpret_cast<uint4*>(srow + piece * 16) = o;
-                        }
-                    }
+            for (int sub = 0; sub < kSubs; sub += 2) {
+                tmem_ld_wait(va);
+                tmem_ld32(t_row + (uint32_t)((sub + 1) * 32), vb);        // in flight while `va` is processed
+                process(va, sub);
+                tmem_ld_wait(vb);
+                if (sub + 2 < kSubs) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
+                else {
+                    // every tcgen05.ld of this accumulator has completed → hand it back to the MMA warp early
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[acc]);
                 }
-                fence_proxy_async_smem();
-                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
-                if (threadIdx.x == kThreads - kEpiThreads) {
-                    tma_store_2d(&tmap_c, stg, c0, m0);
-                    tma_store_commit();
-                }
-                sbuf ^= 1;
+                process(vb, sub + 1);
             }
-            // all tcgen05.ld of this accumulator are complete → hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
-        if (threadIdx.x == kThreads - kEpiThreads) tma_store_wait_all<0>();
+        if (et == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -385,6 +427,37 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
     return TASU_OK;
 }
 
+
+template <bool kOutBf16, int kEpi>
+static int launch_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                      const Params& p) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kOutBf16, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    });
+    TASU_CHECK_CUDA(attr_err);
+    gemm_bf16_tn_kernel<kOutBf16, kEpi><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
+    return TASU_OK;
+}
+
+template <bool kOutBf16>
+static int launch_epi(int epilogue, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+                      const CUtensorMap& mc, const Params& p) {
+    switch (epilogue) {
+        case TASU_EPI_NONE: return launch_one<kOutBf16, TASU_EPI_NONE>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS: return launch_one<kOutBf16, TASU_EPI_BIAS>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_SILU: return launch_one<kOutBf16, TASU_EPI_BIAS_SILU>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_RELU: return launch_one<kOutBf16, TASU_EPI_BIAS_RELU>(grid, st, ma, mb, mc, p);
+        default: return launch_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p);
+    }
+}
+
+static int launch_dispatch(bool out_bf16, int epilogue, int grid, cudaStream_t st, const CUtensorMap& ma,
+                           const CUtensorMap& mb, const CUtensorMap& mc, const Params& p) {
+    return out_bf16 ? launch_epi<true>(epilogue, grid, st, ma, mb, mc, p) : launch_epi<false>(epilogue, grid, st, ma, mb, mc, p);
+}
+
 }  // namespace gemm
 }  // namespace tasu
 
@@ -412,16 +485,8 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     int grid = sm_count();
     if (grid > tiles) grid = tiles;
     cudaStream_t st = (cudaStream_t)stream;
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    });
-    TASU_CHECK_CUDA(attr_err);
-    if (c_dtype == TASU_BF16) gemm_bf16_tn_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
-    else gemm_bf16_tn_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
+    rc = launch_dispatch(c_dtype == TASU_BF16, epilogue, grid, st, ma, mb, mc, p);
+    if (rc) return rc;
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -73,42 +73,57 @@ meanpool_kernel(PoolArgs a) {
         if (kVec) {
             // D-chunks of VI elements; output vector width follows the input chunk
             const int nchunk = a.D / VI;
-            for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
-                float v[VI];
+            constexpr int U = 4;                 // independent 16-byte loads in flight per thread and frame
+            for (int c0 = threadIdx.x; c0 < nchunk; c0 += U * blockDim.x) {
+                float v[U][VI];
 #pragma unroll
-                for (int e = 0; e < VI; ++e) v[e] = 0.f;
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < VI; ++e) v[u][e] = 0.f;
                 for (int f = 0; f < n; ++f) {
-                    const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(src + (int64_t)f * a.rstride) + c);
-                    float x[VI];
-                    unpack16(q, x, Tin());
+                    const uint4* srow = reinterpret_cast<const uint4*>(src + (int64_t)f * a.rstride);
+                    uint4 q[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (c0 + u * (int)blockDim.x < nchunk) q[u] = ld_stream_u4(srow + c0 + u * blockDim.x);
+                    float mx = 0.f, is = 1.f;
                     if (kSoftmax) {
                         const int64_t fr = (int64_t)b * a.T + t0 + f;
-                        const float mx = a.smax[fr], is = 1.f / a.ssum[fr];
+                        mx = a.smax[fr];
+                        is = 1.f / a.ssum[fr];
+                    }
 #pragma unroll
-                        for (int e = 0; e < VI; ++e) v[e] += __expf(x[e] - mx) * is;
-                    } else {
+                    for (int u = 0; u < U; ++u) {
+                        if (c0 + u * (int)blockDim.x < nchunk) {
+                            float x[VI];
+                            unpack16(q[u], x, Tin());
 #pragma unroll
-                        for (int e = 0; e < VI; ++e) v[e] += x[e];
+                            for (int e = 0; e < VI; ++e) v[u][e] += kSoftmax ? __expf(x[e] - mx) * is : x[e];
+                        }
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < VI; ++e) {
-                    if (n > 1) v[e] = v[e] / (float)n;
-                    acc_s += v[e];
-                    acc_q += v[e] * v[e];
-                }
-                Tout* o = orow + (int64_t)c * VI;
-                if constexpr (sizeof(Tout) == 4) {
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * blockDim.x;
+                    if (c >= nchunk) break;
 #pragma unroll
-                    for (int e = 0; e < VI; e += 4)
-                        st_stream_u4(o + e, make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]),
-                                                       __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
-                } else if constexpr (VI == 8) {
-                    st_stream_u4(o, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                               pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
-                } else {   // 4 fp32 in → 4 bf16 out (8 bytes)
-                    uint2 pk = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-                    *reinterpret_cast<uint2*>(o) = pk;
+                    for (int e = 0; e < VI; ++e) {
+                        if (n > 1) v[u][e] = v[u][e] / (float)n;
+                        acc_s += v[u][e];
+                        acc_q += v[u][e] * v[u][e];
+                    }
+                    Tout* o = orow + (int64_t)c * VI;
+                    if constexpr (sizeof(Tout) == 4) {
+#pragma unroll
+                        for (int e = 0; e < VI; e += 4)
+                            st_stream_u4(o + e, make_uint4(__float_as_uint(v[u][e]), __float_as_uint(v[u][e + 1]),
+                                                           __float_as_uint(v[u][e + 2]), __float_as_uint(v[u][e + 3])));
+                    } else if constexpr (VI == 8) {
+                        st_stream_u4(o, make_uint4(pack_bf16x2(v[u][0], v[u][1]), pack_bf16x2(v[u][2], v[u][3]),
+                                                   pack_bf16x2(v[u][4], v[u][5]), pack_bf16x2(v[u][6], v[u][7])));
+                    } else {   // 4 fp32 in → 4 bf16 out (8 bytes)
+                        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[u][0], v[u][1]), pack_bf16x2(v[u][2], v[u][3]));
+                    }
                 }
             }
             // scalar remainder D % VI

@@ -113,7 +113,7 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
                      const float* __restrict__ rmax_all, const float* __restrict__ rsum_all,
                      const uint32_t* __restrict__ gmax, const int64_t* __restrict__ lens, int T_,
                      int blank, float thr, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len,
-                     float* __restrict__ seg_score, int64_t* __restrict__ new_lens) {
+                     float* __restrict__ seg_score, int64_t* __restrict__ new_lens, int32_t* __restrict__ kept_frames) {
     __shared__ int scratch[33];
     const int b = blockIdx.x;
     int64_t L64 = lens[b];
@@ -127,7 +127,7 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
         if (kLogits) return expf(xb[t] - rmax[t]) / rsum[t];
         return is_log ? expf(xb[t]) : xb[t];
     };
-    int carry = 0;
+    int carry = 0, frames = 0;
     for (int t0 = 0; t0 < L; t0 += blockDim.x) {
         const int t = t0 + threadIdx.x;
         int flag = 0, n = 0;
@@ -153,15 +153,21 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
             if (seg_score) seg_score[j] = score;
         }
         carry += total;
+        if (flag) frames += n;
+    }
+    if (kept_frames != nullptr) {
+        frames = block_sum_i(frames, scratch);
+        if (threadIdx.x == 0) kept_frames[b] = frames;
     }
     if (threadIdx.x == 0) new_lens[b] = carry;
 }
 
 __global__ void __launch_bounds__(1024)
-collapse_scan_kernel(const int64_t* __restrict__ new_lens, const uint32_t* __restrict__ gmax, int B,
-                     int32_t* __restrict__ row_off, int64_t* __restrict__ header) {
+collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __restrict__ kept_frames,
+                     const uint32_t* __restrict__ gmax, int B, int32_t* __restrict__ row_off,
+                     int64_t* __restrict__ header) {
     __shared__ int scratch[33];
-    int carry = 0, mx = 0;
+    int carry = 0, mx = 0, frames = 0;
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
         const int b = b0 + threadIdx.x;
         const int v = b < B ? (int)new_lens[b] : 0;
@@ -170,14 +176,16 @@ collapse_scan_kernel(const int64_t* __restrict__ new_lens, const uint32_t* __res
         if (b < B) row_off[b] = carry + excl;
         carry += total;
         mx = max(mx, v);
+        if (kept_frames != nullptr && b < B) frames += kept_frames[b];
     }
     mx = block_max_i(mx, scratch);
+    frames = block_sum_i(frames, scratch);
     if (threadIdx.x == 0) {
         row_off[B] = carry;
         header[TASU_CH_N_OUT] = carry;
         header[TASU_CH_MAX_LEN] = mx;
         header[TASU_CH_IS_LOGPROB] = (gmax != nullptr && ordered_to_float(*gmax) <= 0.f) ? 1 : 0;
-        header[3] = 0;
+        header[TASU_CH_KEPT_FRAMES] = frames;
     }
 }
 
@@ -221,7 +229,7 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
                                   const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
                                   const int64_t* lens, int B, int T, int blank_id, float threshold,
                                   int32_t* seg_start, int32_t* seg_len, float* seg_score,
-                                  int64_t* new_lens, void* stream) {
+                                  int64_t* new_lens, int32_t* kept_frames, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0, "B,T >= 0");
     TASU_CHECK_ARG(input_kind == TASU_INPUT_PROBS || input_kind == TASU_INPUT_LOGITS, "input_kind");
     if (B == 0) return TASU_OK;
@@ -231,19 +239,20 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
     cudaStream_t st = (cudaStream_t)stream;
     if (input_kind == TASU_INPUT_LOGITS)
         collapse_plan_kernel<true><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                      blank_id, threshold, seg_start, seg_len, seg_score, new_lens);
+                                                      blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames);
     else
         collapse_plan_kernel<false><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                       blank_id, threshold, seg_start, seg_len, seg_score, new_lens);
+                                                       blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
 
-extern "C" int tasu_collapse_scan(const int64_t* new_lens, const uint32_t* global_max_enc, int B,
-                                  int32_t* row_off, int64_t* header, void* stream) {
+extern "C" int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames,
+                                  const uint32_t* global_max_enc, int B, int32_t* row_off, int64_t* header,
+                                  void* stream) {
     TASU_CHECK_ARG(B >= 0 && row_off && header, "B >= 0, non-null outputs");
     TASU_CHECK_ARG(B == 0 || new_lens, "null new_lens");
-    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, global_max_enc, B, row_off, header);
+    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, header);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

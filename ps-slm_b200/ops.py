@@ -80,7 +80,7 @@ def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[
 
 
 class CollapsePlan:
-    __slots__ = ("seg_start", "seg_len", "seg_score", "new_lens", "row_off", "header", "B", "T")
+    __slots__ = ("seg_start", "seg_len", "seg_score", "new_lens", "kept_frames", "row_off", "header", "B", "T")
 
 
 def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: float,
@@ -96,14 +96,17 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     p.seg_len = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
     p.seg_score = torch.empty(max(B * T, 1), dtype=torch.float32, device=dev) if want_scores else None
     p.new_lens = torch.empty(B, dtype=torch.int64, device=dev)
+    p.kept_frames = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
     lib = L.lib()
     L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
                                    _ptr(st.row_sumexp), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
                                    blank_id, float(threshold), p.seg_start.data_ptr(), p.seg_len.data_ptr(),
-                                   _ptr(p.seg_score), p.new_lens.data_ptr(), _stream()), "tasu_collapse_plan")
-    L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
+                                   _ptr(p.seg_score), p.new_lens.data_ptr(), p.kept_frames.data_ptr(), _stream()),
+            "tasu_collapse_plan")
+    L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
+                                   st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
                                    B, p.row_off.data_ptr(), p.header.data_ptr(), _stream()), "tasu_collapse_scan")
     _count(2)
     return p
