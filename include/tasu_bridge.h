@@ -37,7 +37,8 @@ enum { TASU_INPUT_PROBS = 0,  /* probabilities or log-probabilities; auto-detect
 
 /* GEMM epilogues */
 enum { TASU_EPI_NONE = 0, TASU_EPI_BIAS = 1, TASU_EPI_BIAS_SILU = 2, TASU_EPI_BIAS_RELU = 3,
-       TASU_EPI_LNFOLD_SILU = 4 /* silu(rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]) */ };
+       TASU_EPI_LNFOLD_SILU = 4, /* silu(rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]) */
+       TASU_EPI_LNFOLD = 5       /* the same without the SiLU (pre-activation kept for training) */ };
 
 /* splice header words (int64) written by tasu_splice_header */
 enum { TASU_SH_SPLICED_LEN = 0,   /* S' = max_b sum(placeholders)            ps-slm.py:809 */
@@ -162,6 +163,30 @@ int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ld
                            void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
                            const float* bias, const float* row_rstd, const float* row_mean,
                            const float* colsum, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Training side of the linear-silu projector: backward of projector.py:149-151 (autograd in the
+ * reference; trained by Multitask/utils/deepspeed_utils.py:235-236).  The big contractions reuse
+ * tasu_gemm_bf16_tn; these produce its K-major operands and the LayerNorm-fold algebra:
+ *   tasu_transpose_cast  dst[c, r] = bf16(row_scale[r] * src[r, c])       (row_scale may be NULL)
+ *   tasu_silu_fwd        h = bf16(silu(z))
+ *   tasu_silu_bwd        dz = dh*silu'(z); dzsT[j, n] = bf16(rstd[n]*dz[n, j]); db1[j] = sum_n dz;
+ *                        g0[j] = sum_n rstd[n]*mean[n]*dz[n, j]           (db1/g0 zeroed by the call)
+ *   tasu_colsum          out[c] = sum_r src[r, c]                          (zeroed by the call)
+ *   tasu_linear_silu_wgrad_finish   with G = dzsT · x  ([Hb, V], from tasu_gemm_bf16_tn):
+ *                        dW1 = gamma*(G - g0), dgamma = sum_j W1*(G - g0), dbeta = sum_j W1*db1
+ */
+int tasu_transpose_cast(const void* src, int src_dtype, int64_t rows, int64_t cols, int64_t src_stride,
+                        const float* row_scale, void* dst_bf16, int64_t dst_stride, void* stream);
+int tasu_silu_fwd(const float* z, int64_t n, void* h_bf16, void* stream);
+int tasu_silu_bwd(const float* dh, const float* z, int64_t N, int Hb, const float* row_rstd,
+                  const float* row_mean, void* dzsT_bf16, int64_t t_stride, float* db1, float* g0,
+                  void* stream);
+int tasu_colsum(const void* src, int src_dtype, int64_t rows, int cols, int64_t src_stride, float* out,
+                void* stream);
+int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float* w1, int64_t w1_stride,
+                                  const float* gamma, const float* g0, const float* db1, int Hb, int V,
+                                  float* dw1, int64_t dw1_stride, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.

@@ -15,7 +15,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 TASU_OK = 0
 F32, BF16 = 0, 1
 INPUT_PROBS, INPUT_LOGITS = 0, 1
-EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU = 0, 1, 2, 3, 4
+EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD = 0, 1, 2, 3, 4, 5
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
 
@@ -34,6 +34,11 @@ SIGNATURES = {
     "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "tasu_gemm_bf16_tn_simt": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_transpose_cast": (_I, [_P, _I, _L, _L, _L, _P, _P, _L, _P]),
+    "tasu_silu_fwd": (_I, [_P, _L, _P, _P]),
+    "tasu_silu_bwd": (_I, [_P, _P, _L, _I, _P, _P, _P, _L, _P, _P, _P]),
+    "tasu_colsum": (_I, [_P, _I, _L, _I, _L, _P, _P]),
+    "tasu_linear_silu_wgrad_finish": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "tasu_splice_rowstat": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
     "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),

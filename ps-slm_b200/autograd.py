@@ -1,0 +1,111 @@
+"""Training path of the bridge: autograd Functions over the C ABI.
+
+The reference trains the projector with plain autograd through nn.LayerNorm / nn.Linear / nn.SiLU
+(Multitask/model/projector.py:149-151) and through the index_put of the splice
+(Multitask/model/ps-slm.py:833-869); the loss comes back as the gradient of ``inputs_embeds``
+(Multitask/utils/deepspeed_utils.py:235).  Here:
+
+* ``LinearSiLUFunction``  — forward: LN-folded GEMM-1 (pre-activation kept in fp32), SiLU, GEMM-2;
+  backward: dW2 = dyᵀ·h, dh = dy·W2, dz = dh·silu'(z), G = (rstd·dz)ᵀ·x on the tensor cores, then
+  dW1/dγ/dβ from G by the LayerNorm-fold algebra (no third big GEMM), db1, db2.  The input (a
+  posterior) never needs a gradient.
+* ``SpliceFunction``      — forward: tasu_splice_scatter; backward: gather of the upstream gradient at
+  the audio slots (tasu_splice_audio_grad).  Text embeddings are treated as constants (frozen LLM,
+  scripts/finetune_deespeed_sensevoice.sh:84).
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .bridge import cast_weight_bf16
+
+
+class LinearSiLUFunction(torch.autograd.Function):
+    """y = W2·silu(W1·LN(x) + b1) + b2 on prepared operands (xb bf16 [N, pad64(V)], mean, rstd)."""
+
+    @staticmethod
+    def forward(ctx, xb, mean, rstd, n_rows, gamma, beta, w1, b1, w2, b2, out_dtype):
+        V = w1.shape[1]
+        Hb, H = w1.shape[0], w2.shape[0]
+        dev = xb.device
+        w1g, colsum, dbias = ops.fold_layernorm(w1.detach(), gamma.detach(), beta.detach(), b1.detach())
+        w2b = cast_weight_bf16(w2)
+        z = torch.empty(n_rows, Hb, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(xb, w1g, n_rows, Hb, V, z, L.EPI_LNFOLD, dbias, rstd, mean, colsum)
+        h = ops.silu_fwd(z)
+        y = torch.empty(n_rows, H, dtype=out_dtype, device=dev)
+        ops.gemm_bf16_tn(h, w2b, n_rows, H, Hb, y, L.EPI_BIAS, b2.detach().float().contiguous())
+        ctx.save_for_backward(xb, mean, rstd, z, h, gamma, w1, w2)
+        ctx.n_rows = n_rows
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, mean, rstd, z, h, gamma, w1, w2 = ctx.saved_tensors
+        N = ctx.n_rows
+        Hb, V = w1.shape
+        H = w2.shape[0]
+        dev = dy.device
+        dy = dy.contiguous()
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        db2 = ops.colsum(dy)
+        dyb, _, _ = ops.cast_rows(dy, torch.bfloat16) if dy.dtype != torch.bfloat16 else (dy, None, None)
+        dyT = ops.transpose_cast(dy, N, H)                        # [H, N]
+        hT = ops.transpose_cast(h, N, Hb)                         # [Hb, N]
+        dw2 = torch.empty(H, Hb, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(dyT, hT, H, Hb, N, dw2)                  # dW2 = dyᵀ·h
+        w2T = ops.transpose_cast(w2.detach(), H, Hb)              # [Hb, H]
+        dh = torch.empty(N, Hb, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(dyb, w2T, N, Hb, H, dh)                  # dh = dy·W2
+        dzsT, db1, g0 = ops.silu_bwd(dh, z, rstd, mean)           # [Hb, N] = (rstd·dz)ᵀ
+        xT = ops.transpose_cast(xb, N, V)                         # [V, N]
+        ldv = ops.pad_to(V, 4)
+        G = torch.empty(Hb, ldv, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(dzsT, xT, Hb, V, N, G)                   # G = (rstd·dz)ᵀ·x
+        dw1, dgamma, dbeta = ops.linear_silu_wgrad_finish(G, w1.detach().float().contiguous(),
+                                                          gamma.detach().float().contiguous(), g0, db1)
+        return (None, None, None, None, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), dw1.to(w1.dtype),
+                db1.to(w1.dtype), dw2.to(w2.dtype), db2.to(w2.dtype), None)
+
+
+def linear_silu_train_rows(module, xb, mean, rstd, n_rows, out_dtype=torch.float32):
+    """Trainable projector forward on prepared rows (used by the packed text-only training step)."""
+    return LinearSiLUFunction.apply(xb, mean, rstd, n_rows, module.norm.weight, module.norm.bias,
+                                    module.ffn[0].weight, module.ffn[0].bias, module.ffn[2].weight,
+                                    module.ffn[2].bias, out_dtype)
+
+
+def linear_silu_train(module, x):
+    """Trainable ``EncoderProjectorLinearSiLU.forward`` for a dense [B, T, V] input."""
+    if x.requires_grad:
+        raise NotImplementedError("the bridge projector does not propagate a gradient to its (posterior) input")
+    B, T, D = x.shape
+    xb, mean, rstd = ops.cast_rows(x.reshape(B * T, D), torch.bfloat16, ops.pad_to(D), want_ln=True,
+                                   ln_eps=module.norm.eps)
+    out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    y = linear_silu_train_rows(module, xb, mean, rstd, B * T, out_dtype)
+    return y.view(B, T, -1)
+
+
+class SpliceFunction(torch.autograd.Function):
+    """Differentiable splice: gradient flows to the audio rows only."""
+
+    @staticmethod
+    def forward(ctx, audio_rows, plan, spliced_len, text_src, text_mode, audio_layout, audio_max_len, labels,
+                pad_id, ignore_id):
+        emb, mask, out_labels, pos, fids = ops.splice_scatter(plan, spliced_len, text_src, text_mode,
+                                                              audio_rows.detach(), audio_layout, audio_max_len,
+                                                              labels, pad_id, ignore_id)
+        ctx.plan, ctx.layout, ctx.max_len = plan, audio_layout, audio_max_len
+        ctx.shape = tuple(audio_rows.shape)
+        ctx.mark_non_differentiable(mask, pos, fids)
+        if out_labels is not None:
+            ctx.mark_non_differentiable(out_labels)
+        return emb, mask, out_labels, pos, fids
+
+    @staticmethod
+    def backward(ctx, demb, *_):
+        n_rows = ctx.shape[0] if ctx.layout == 0 else 0
+        ga = ops.splice_audio_grad(ctx.plan, demb, ctx.layout, ctx.max_len, n_rows)
+        return (ga.view(ctx.shape), None, None, None, None, None, None, None, None, None)

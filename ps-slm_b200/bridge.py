@@ -68,6 +68,10 @@ def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_
     ops.splice_plan(p, num_audio_tokens, 1)
     hdr = p.header.cpu()
     _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
+    if torch.is_grad_enabled() and audio_features.requires_grad:
+        from .autograd import SpliceFunction            # gradient flows back to the projector output
+        return SpliceFunction.apply(audio_features, p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds.detach(), 0, 1,
+                                    audio_features.shape[1], labels, pad_id, ignore_id)
     return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds, 0, audio_features, 1,
                               audio_features.shape[1], labels, pad_id, ignore_id)
 

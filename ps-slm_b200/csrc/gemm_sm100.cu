@@ -251,11 +251,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int c = et; c < BN; c += kEpiThreads) {
                     const int col = n0 + c;
                     s_bias[c] = col < p.N ? __ldg(p.bias + col) : 0.f;
-                    if (kEpi == TASU_EPI_LNFOLD_SILU) s_colsum[c] = col < p.N ? __ldg(p.colsum + col) : 0.f;
+                    if (kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) s_colsum[c] = col < p.N ? __ldg(p.colsum + col) : 0.f;
                 }
             }
             float rstd = 1.f, nmean = 0.f;
-            if (kEpi == TASU_EPI_LNFOLD_SILU && grow < p.M) { rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow); }
+            if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) && grow < p.M) { rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow); }
             const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -281,11 +281,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (kEpi != TASU_EPI_NONE) {
                         const float4 bb = b4[q];
                         const float b[4] = {bb.x, bb.y, bb.z, bb.w};
-                        if (kEpi == TASU_EPI_LNFOLD_SILU) {
+                        if (kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) {
                             const float4 cc = c4[q];
                             const float c[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = silu_f(fmaf(rstd, fmaf(nmean, c[e], x[e]), b[e]));
+                            for (int e = 0; e < 4; ++e) {
+                                x[e] = fmaf(rstd, fmaf(nmean, c[e], x[e]), b[e]);
+                                if (kEpi == TASU_EPI_LNFOLD_SILU) x[e] = silu_f(x[e]);
+                            }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -371,6 +374,7 @@ gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bf
     if (m < p.M && n < p.N) {
         float x = acc;
         if (p.epilogue == TASU_EPI_LNFOLD_SILU) x = silu_f(fmaf(p.row_rstd[m], x - p.row_mean[m] * p.colsum[n], p.bias[n]));
+        else if (p.epilogue == TASU_EPI_LNFOLD) x = fmaf(p.row_rstd[m], x - p.row_mean[m] * p.colsum[n], p.bias[n]);
         else if (p.epilogue != TASU_EPI_NONE) {
             x += p.bias[n];
             if (p.epilogue == TASU_EPI_BIAS_SILU) x = silu_f(x);
@@ -418,12 +422,13 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
                         const float* row_mean, const float* colsum) {
     TASU_CHECK_ARG(M >= 0 && N > 0 && K > 0, "M >= 0, N,K > 0");
     TASU_CHECK_ARG(c_dtype == TASU_F32 || c_dtype == TASU_BF16, "c_dtype");
-    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_LNFOLD_SILU, "epilogue");
+    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_LNFOLD, "epilogue");
     TASU_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
     if (M == 0) return TASU_OK;
     TASU_CHECK_ARG(A && B && C, "null pointer");
     TASU_CHECK_ARG(epilogue == TASU_EPI_NONE || bias, "bias required");
-    TASU_CHECK_ARG(epilogue != TASU_EPI_LNFOLD_SILU || (row_rstd && row_mean && colsum), "LN-fold vectors required");
+    TASU_CHECK_ARG((epilogue != TASU_EPI_LNFOLD_SILU && epilogue != TASU_EPI_LNFOLD) || (row_rstd && row_mean && colsum),
+                   "LN-fold vectors required");
     return TASU_OK;
 }
 
@@ -449,7 +454,8 @@ static int launch_epi(int epilogue, int grid, cudaStream_t st, const CUtensorMap
         case TASU_EPI_BIAS: return launch_one<kOutBf16, TASU_EPI_BIAS>(grid, st, ma, mb, mc, p);
         case TASU_EPI_BIAS_SILU: return launch_one<kOutBf16, TASU_EPI_BIAS_SILU>(grid, st, ma, mb, mc, p);
         case TASU_EPI_BIAS_RELU: return launch_one<kOutBf16, TASU_EPI_BIAS_RELU>(grid, st, ma, mb, mc, p);
-        default: return launch_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD_SILU: return launch_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p);
+        default: return launch_one<kOutBf16, TASU_EPI_LNFOLD>(grid, st, ma, mb, mc, p);
     }
 }
 

@@ -1,0 +1,212 @@
+// Training-side helpers of the linear-silu projector (backward of Multitask/model/projector.py:149-151,
+// which the reference leaves to autograd; trained in Multitask/utils/deepspeed_utils.py:235-236).
+// The three large contractions (dW2, dh, G = (rstd·dz)^T·x) run on the tcgen05 GEMM; these kernels
+// produce its K-major operands (transposes), the SiLU forward/backward and the LayerNorm-fold
+// algebra that turns G into dW1 / dgamma / dbeta without the reference's third big GEMM
+// (dLN = dh1·W1): with x̂ = rstd·(x − μ),
+//   dW1[j,v]  = γ[v]·(G[j,v] − g0[j]),   G = Σ_n rstd_n dz[n,j] x[n,v],  g0[j] = Σ_n rstd_n μ_n dz[n,j]
+//   dγ[v]     = Σ_j W1[j,v]·(G[j,v] − g0[j])
+//   dβ[v]     = Σ_j W1[j,v]·db1[j],      db1[j] = Σ_n dz[n,j]
+#include "common.cuh"
+
+namespace tasu {
+
+// dst[c, r] = bf16(scale[r] * src[r, c]); 32x32 tiles through shared memory, coalesced both ways
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const Ti* __restrict__ src, int64_t R, int64_t C, int64_t sstride,
+                      const float* __restrict__ scale, __nv_bfloat16* __restrict__ dst, int64_t dstride) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < C) {
+            v = to_f32(src[r * sstride + c]);
+            if (scale) v *= scale[r];
+        }
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+        if (c < C && r < R) dst[c * dstride + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+silu_fwd_kernel(const float* __restrict__ z, int64_t n, __nv_bfloat16* __restrict__ h) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(z + i);
+        const float a = v.x / (1.f + __expf(-v.x)), b = v.y / (1.f + __expf(-v.y));
+        const float c = v.z / (1.f + __expf(-v.z)), d = v.w / (1.f + __expf(-v.w));
+        *reinterpret_cast<uint2*>(h + i) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+    } else {
+        for (int64_t k = i; k < n; ++k) { const float x = z[k]; h[k] = __float2bfloat16_rn(x / (1.f + __expf(-x))); }
+    }
+}
+
+// dz = dh * silu'(z); dzsT[j, n] = bf16(rstd[n] * dz[n, j]); db1[j] += Σ_n dz; g0[j] += Σ_n rstd μ dz
+__global__ void __launch_bounds__(256)
+silu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z, int64_t N, int Hb,
+                const float* __restrict__ rstd, const float* __restrict__ mean,
+                __nv_bfloat16* __restrict__ dzsT, int64_t tstride, float* __restrict__ db1, float* __restrict__ g0) {
+    __shared__ float tile[32][33];
+    __shared__ float s_db[8][32], s_g0[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.y * 32;
+    const int j0 = blockIdx.x * 32;
+    float a_db = 0.f, a_g0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t n = n0 + ty + 8 * i;
+        const int j = j0 + tx;
+        float v = 0.f;
+        if (n < N && j < Hb) {
+            const float zz = z[n * Hb + j], s = 1.f / (1.f + __expf(-zz));
+            const float dz = dh[n * Hb + j] * (s * (1.f + zz * (1.f - s)));
+            const float r = rstd ? rstd[n] : 1.f;
+            a_db += dz;
+            a_g0 += r * (mean ? mean[n] : 0.f) * dz;
+            v = r * dz;
+        }
+        tile[ty + 8 * i][tx] = v;
+    }
+    s_db[ty][tx] = a_db; s_g0[ty][tx] = a_g0;
+    __syncthreads();
+    if (ty == 0) {
+        float d = 0.f, g = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { d += s_db[k][tx]; g += s_g0[k][tx]; }
+        if (j0 + tx < Hb) { atomicAdd(db1 + j0 + tx, d); if (g0) atomicAdd(g0 + j0 + tx, g); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j0 + ty + 8 * i;
+        const int64_t n = n0 + tx;
+        if (j < Hb && n < N) dzsT[(int64_t)j * tstride + n] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+}
+
+// out[c] += Σ_r src[r, c]
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const Ti* __restrict__ src, int64_t R, int C, int64_t sstride, float* __restrict__ out, int rows_per_cta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+    float a = 0.f;
+    for (int64_t r = r0; r < r1; ++r) a += to_f32(src[r * sstride + c]);
+    atomicAdd(out + c, a);
+}
+
+__global__ void __launch_bounds__(128)
+wgrad_finish_kernel(const float* __restrict__ G, int64_t gstride, const float* __restrict__ w1, int64_t wstride,
+                    const float* __restrict__ gamma, const float* __restrict__ g0, const float* __restrict__ db1,
+                    int Hb, int V, int rows_per_cta, float* __restrict__ dw1, int64_t dstride,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int j0 = blockIdx.y * rows_per_cta;
+    const int j1 = min(j0 + rows_per_cta, Hb);
+    const float gm = gamma[v];
+    float ag = 0.f, ab = 0.f;
+    for (int j = j0; j < j1; ++j) {
+        const float d = G[(int64_t)j * gstride + v] - g0[j];
+        const float w = w1[(int64_t)j * wstride + v];
+        dw1[(int64_t)j * dstride + v] = gm * d;
+        ag = fmaf(w, d, ag);
+        ab = fmaf(w, db1[j], ab);
+    }
+    atomicAdd(dgamma + v, ag);
+    atomicAdd(dbeta + v, ab);
+}
+
+}  // namespace tasu
+
+using namespace tasu;
+
+extern "C" int tasu_transpose_cast(const void* src, int src_dtype, int64_t rows, int64_t cols, int64_t src_stride,
+                                   const float* row_scale, void* dst_bf16, int64_t dst_stride, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && cols >= 0, "rows, cols >= 0");
+    TASU_CHECK_ARG(src_dtype == TASU_F32 || src_dtype == TASU_BF16, "src_dtype");
+    TASU_CHECK_ARG(src_stride >= cols && dst_stride >= rows, "stride too small");
+    if (rows == 0 || cols == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && dst_bf16, "null pointer");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    TASU_CHECK_ARG(grid.y <= 65535u, "too many rows for one launch (max 2 097 120)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == TASU_F32)
+        transpose_cast_kernel<float><<<grid, 256, 0, st>>>((const float*)src, rows, cols, src_stride, row_scale, (__nv_bfloat16*)dst_bf16, dst_stride);
+    else
+        transpose_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, rows, cols, src_stride, row_scale, (__nv_bfloat16*)dst_bf16, dst_stride);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_silu_fwd(const float* z, int64_t n, void* h_bf16, void* stream) {
+    TASU_CHECK_ARG(n >= 0, "n >= 0");
+    if (n == 0) return TASU_OK;
+    TASU_CHECK_ARG(z && h_bf16, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)z % 16 == 0) && ((uintptr_t)h_bf16 % 8 == 0), "alignment");
+    const int64_t threads = (n + 3) / 4;
+    silu_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, n, (__nv_bfloat16*)h_bf16);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_silu_bwd(const float* dh, const float* z, int64_t N, int Hb, const float* row_rstd,
+                             const float* row_mean, void* dzsT_bf16, int64_t t_stride, float* db1, float* g0,
+                             void* stream) {
+    TASU_CHECK_ARG(N >= 0 && Hb > 0 && t_stride >= N, "shape");
+    TASU_CHECK_ARG(db1 != nullptr, "null db1");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASU_CHECK_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * Hb, st));
+    if (g0) TASU_CHECK_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * Hb, st));
+    if (N == 0) return TASU_OK;
+    TASU_CHECK_ARG(dh && z && dzsT_bf16, "null pointer");
+    dim3 grid((unsigned)((Hb + 31) / 32), (unsigned)((N + 31) / 32));
+    TASU_CHECK_ARG(grid.y <= 65535u, "too many rows for one launch");
+    silu_bwd_kernel<<<grid, 256, 0, st>>>(dh, z, N, Hb, row_rstd, row_mean, (__nv_bfloat16*)dzsT_bf16, t_stride, db1, g0);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_colsum(const void* src, int src_dtype, int64_t rows, int cols, int64_t src_stride, float* out,
+                           void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && cols > 0 && src_stride >= cols, "shape");
+    TASU_CHECK_ARG(src_dtype == TASU_F32 || src_dtype == TASU_BF16, "src_dtype");
+    TASU_CHECK_ARG(out != nullptr, "null out");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASU_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(src != nullptr, "null src");
+    const int rpc = 128;
+    dim3 grid((unsigned)((cols + 255) / 256), (unsigned)((rows + rpc - 1) / rpc));
+    TASU_CHECK_ARG(grid.y <= 65535u, "too many rows for one launch");
+    if (src_dtype == TASU_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)src, rows, cols, src_stride, out, rpc);
+    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, rows, cols, src_stride, out, rpc);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float* w1, int64_t w1_stride,
+                                             const float* gamma, const float* g0, const float* db1, int Hb, int V,
+                                             float* dw1, int64_t dw1_stride, float* dgamma, float* dbeta, void* stream) {
+    TASU_CHECK_ARG(Hb > 0 && V > 0, "shape");
+    TASU_CHECK_ARG(G && w1 && gamma && g0 && db1 && dw1 && dgamma && dbeta, "null pointer");
+    TASU_CHECK_ARG(g_stride >= V && w1_stride >= V && dw1_stride >= V, "stride too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * V, st));
+    TASU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * V, st));
+    const int rpc = 128;
+    dim3 grid((unsigned)((V + 127) / 128), (unsigned)((Hb + rpc - 1) / rpc));
+    wgrad_finish_kernel<<<grid, 128, 0, st>>>(G, g_stride, w1, w1_stride, gamma, g0, db1, Hb, V, rpc, dw1, dw1_stride, dgamma, dbeta);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -313,3 +313,63 @@ def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, 
         audio_layout, H, audio_max_len, p.n_audio, ga.data_ptr(), _stream()), "tasu_splice_audio_grad")
     _count(1)
     return ga
+
+
+# ----------------------------------------------------------------------------- training helpers
+def transpose_cast(src: torch.Tensor, rows: int, cols: int, row_scale: Optional[torch.Tensor] = None):
+    """[rows, cols] (pitch = stride(0)) → bf16 [cols, pad8(rows)] = (row_scale ⊙ src)^T."""
+    _need_cuda(src, row_scale)
+    ld = pad_to(rows, 8)
+    dst = torch.empty(cols, ld, dtype=torch.bfloat16, device=src.device)
+    sstride = src.stride(0) if src.shape[0] > 1 else max(cols, src.shape[-1])
+    L.check(L.lib().tasu_transpose_cast(src.data_ptr(), _dt(src), rows, cols, sstride, _ptr(row_scale),
+                                        dst.data_ptr(), ld, _stream()), "tasu_transpose_cast")
+    _count(1)
+    return dst
+
+
+def silu_fwd(z: torch.Tensor):
+    _need_cuda(z)
+    h = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device)
+    L.check(L.lib().tasu_silu_fwd(z.data_ptr(), z.numel(), h.data_ptr(), _stream()), "tasu_silu_fwd")
+    _count(1)
+    return h
+
+
+def silu_bwd(dh: torch.Tensor, z: torch.Tensor, rstd: Optional[torch.Tensor], mean: Optional[torch.Tensor]):
+    """→ (dzsT bf16 [Hb, pad8(N)], db1 [Hb], g0 [Hb])."""
+    _need_cuda(dh, z)
+    N, Hb = z.shape
+    ld = pad_to(N, 8)
+    dzsT = torch.empty(Hb, ld, dtype=torch.bfloat16, device=z.device)
+    db1 = torch.empty(Hb, dtype=torch.float32, device=z.device)
+    g0 = torch.empty(Hb, dtype=torch.float32, device=z.device)
+    L.check(L.lib().tasu_silu_bwd(dh.data_ptr(), z.data_ptr(), N, Hb, _ptr(rstd), _ptr(mean), dzsT.data_ptr(), ld,
+                                  db1.data_ptr(), g0.data_ptr(), _stream()), "tasu_silu_bwd")
+    _count(1)
+    return dzsT, db1, g0
+
+
+def colsum(src: torch.Tensor):
+    _need_cuda(src)
+    rows, cols = src.shape
+    out = torch.empty(cols, dtype=torch.float32, device=src.device)
+    L.check(L.lib().tasu_colsum(src.data_ptr(), _dt(src), rows, cols, src.stride(0) if rows > 1 else cols,
+                                out.data_ptr(), _stream()), "tasu_colsum")
+    _count(1)
+    return out
+
+
+def linear_silu_wgrad_finish(G: torch.Tensor, w1: torch.Tensor, gamma: torch.Tensor, g0: torch.Tensor,
+                             db1: torch.Tensor):
+    """(dW1 [Hb,V], dgamma [V], dbeta [V]) from G = dzsT·x (fp32 [Hb, ldV])."""
+    Hb, V = w1.shape
+    dw1 = torch.empty(Hb, V, dtype=torch.float32, device=w1.device)
+    dgamma = torch.empty(V, dtype=torch.float32, device=w1.device)
+    dbeta = torch.empty(V, dtype=torch.float32, device=w1.device)
+    L.check(L.lib().tasu_linear_silu_wgrad_finish(G.data_ptr(), G.stride(0), w1.data_ptr(), w1.stride(0),
+                                                  gamma.data_ptr(), g0.data_ptr(), db1.data_ptr(), Hb, V,
+                                                  dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+            "tasu_linear_silu_wgrad_finish")
+    _count(1)
+    return dw1, dgamma, dbeta
