@@ -174,7 +174,7 @@ int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ld
  *                        g0[j] = sum_n rstd[n]*mean[n]*dz[n, j]           (db1/g0 zeroed by the call)
  *   tasu_colsum          out[c] = sum_r src[r, c]                          (zeroed by the call)
  *   tasu_linear_silu_wgrad_finish   with G = dzsT · x  ([Hb, V], from tasu_gemm_bf16_tn):
- *                        dW1 = gamma*(G - g0), dgamma = sum_j W1*(G - g0), dbeta = sum_j W1*db1
+ *                        dW1 = gamma*(G - g0) + beta*db1, dgamma = sum_j W1*(G - g0), dbeta = sum_j W1*db1
  */
 int tasu_transpose_cast(const void* src, int src_dtype, int64_t rows, int64_t cols, int64_t src_stride,
                         const float* row_scale, void* dst_bf16, int64_t dst_stride, void* stream);
@@ -185,7 +185,8 @@ int tasu_silu_bwd(const float* dh, const float* z, int64_t N, int Hb, const floa
 int tasu_colsum(const void* src, int src_dtype, int64_t rows, int cols, int64_t src_stride, float* out,
                 void* stream);
 int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float* w1, int64_t w1_stride,
-                                  const float* gamma, const float* g0, const float* db1, int Hb, int V,
+                                  const float* gamma, const float* beta, const float* g0, const float* db1,
+                                  int Hb, int V,
                                   float* dw1, int64_t dw1_stride, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -193,6 +193,47 @@ def golden_merge():
     np.savez_compressed(os.path.join(OUT, "merge.npz"), **out)
 
 
+def golden_model():
+    """Drive the UNMODIFIED reference ``slam_model_asr.forward/generate`` (ps-slm.py:411-677) with the
+    fake encoder/LLM of tests/fakes.py and freeze what it hands to the LLM."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    import fakes as F
+    mod, pmod = R.load()
+    out = {}
+    for name in F.CASES:
+        inp = F.build_inputs(name)
+        cls = {"linear-silu": pmod.EncoderProjectorLinearSiLU, "linear": pmod.EncoderProjectorConcat}[inp["proj"]]
+        encoder, llm, projector, tok, train_config, model_config = F.build_parts(inp, cls)
+        m = mod.slam_model_asr.__new__(mod.slam_model_asr)
+        torch.nn.Module.__init__(m)
+        m.encoder, m.llm, m.encoder_projector, m.tokenizer = encoder, llm, projector, tok
+        m.metric = "acc"
+        m.train_config, m.model_config = train_config, model_config
+        for k, v in inp["flags"].items():
+            setattr(m, k, v)
+        m.cross_attn = False
+        m.encoder_tokenizer = F.FakeCTCTokenizer()
+        torch.manual_seed(4321)                         # RNG stream of the noisy simulator
+        with contextlib.redirect_stdout(io.StringIO()):
+            if inp["entry"] == "forward":
+                res, acc = m(**inp["batch"])
+                out[f"{name}_ref_loss"] = res.loss.detach().numpy()
+                out[f"{name}_ref_acc"] = np.asarray(float(acc))
+            else:
+                m.generate(**inp["batch"])
+        seen = llm.seen
+        out[f"{name}_ref_embeds"] = seen["inputs_embeds"].detach().numpy()
+        out[f"{name}_ref_mask"] = seen["attention_mask"].numpy()
+        if seen.get("labels") is not None:
+            out[f"{name}_ref_labels"] = seen["labels"].numpy()
+        if seen.get("position_ids") is not None:
+            out[f"{name}_ref_pos"] = seen["position_ids"].numpy()
+        out[f"{name}_wsum"] = np.asarray(sum(float(p.double().sum()) for p in m.parameters()))
+    np.savez_compressed(os.path.join(OUT, "model.npz"), **out)
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not present; golden vectors can only be regenerated in the build container")
@@ -201,6 +242,7 @@ def main():
     golden_sim()
     golden_projector()
     golden_merge()
+    golden_model()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

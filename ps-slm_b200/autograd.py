@@ -35,13 +35,13 @@ class LinearSiLUFunction(torch.autograd.Function):
         h = ops.silu_fwd(z)
         y = torch.empty(n_rows, H, dtype=out_dtype, device=dev)
         ops.gemm_bf16_tn(h, w2b, n_rows, H, Hb, y, L.EPI_BIAS, b2.detach().float().contiguous())
-        ctx.save_for_backward(xb, mean, rstd, z, h, gamma, w1, w2)
+        ctx.save_for_backward(xb, mean, rstd, z, h, gamma, beta, w1, w2)
         ctx.n_rows = n_rows
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xb, mean, rstd, z, h, gamma, w1, w2 = ctx.saved_tensors
+        xb, mean, rstd, z, h, gamma, beta, w1, w2 = ctx.saved_tensors
         N = ctx.n_rows
         Hb, V = w1.shape
         H = w2.shape[0]
@@ -64,7 +64,8 @@ class LinearSiLUFunction(torch.autograd.Function):
         G = torch.empty(Hb, ldv, dtype=torch.float32, device=dev)
         ops.gemm_bf16_tn(dzsT, xT, Hb, V, N, G)                   # G = (rstd·dz)ᵀ·x
         dw1, dgamma, dbeta = ops.linear_silu_wgrad_finish(G, w1.detach().float().contiguous(),
-                                                          gamma.detach().float().contiguous(), g0, db1)
+                                                          gamma.detach().float().contiguous(),
+                                                          beta.detach().float().contiguous(), g0, db1)
         return (None, None, None, None, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), dw1.to(w1.dtype),
                 db1.to(w1.dtype), dw2.to(w2.dtype), db2.to(w2.dtype), None)
 

@@ -4,7 +4,7 @@
 // produce its K-major operands (transposes), the SiLU forward/backward and the LayerNorm-fold
 // algebra that turns G into dW1 / dgamma / dbeta without the reference's third big GEMM
 // (dLN = dh1·W1): with x̂ = rstd·(x − μ),
-//   dW1[j,v]  = γ[v]·(G[j,v] − g0[j]),   G = Σ_n rstd_n dz[n,j] x[n,v],  g0[j] = Σ_n rstd_n μ_n dz[n,j]
+//   dW1[j,v]  = γ[v]·(G[j,v] − g0[j]) + β[v]·db1[j],   G = Σ_n rstd_n dz[n,j] x[n,v],  g0[j] = Σ_n rstd_n μ_n dz[n,j]
 //   dγ[v]     = Σ_j W1[j,v]·(G[j,v] − g0[j])
 //   dβ[v]     = Σ_j W1[j,v]·db1[j],      db1[j] = Σ_n dz[n,j]
 #include "common.cuh"
@@ -107,19 +107,19 @@ colsum_kernel(const Ti* __restrict__ src, int64_t R, int C, int64_t sstride, flo
 
 __global__ void __launch_bounds__(128)
 wgrad_finish_kernel(const float* __restrict__ G, int64_t gstride, const float* __restrict__ w1, int64_t wstride,
-                    const float* __restrict__ gamma, const float* __restrict__ g0, const float* __restrict__ db1,
-                    int Hb, int V, int rows_per_cta, float* __restrict__ dw1, int64_t dstride,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ g0,
+                    const float* __restrict__ db1, int Hb, int V, int rows_per_cta, float* __restrict__ dw1, int64_t dstride,
                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     const int j0 = blockIdx.y * rows_per_cta;
     const int j1 = min(j0 + rows_per_cta, Hb);
-    const float gm = gamma[v];
+    const float gm = gamma[v], bt = beta[v];
     float ag = 0.f, ab = 0.f;
     for (int j = j0; j < j1; ++j) {
         const float d = G[(int64_t)j * gstride + v] - g0[j];
         const float w = w1[(int64_t)j * wstride + v];
-        dw1[(int64_t)j * dstride + v] = gm * d;
+        dw1[(int64_t)j * dstride + v] = fmaf(gm, d, bt * db1[j]);
         ag = fmaf(w, d, ag);
         ab = fmaf(w, db1[j], ab);
     }
@@ -196,17 +196,18 @@ extern "C" int tasu_colsum(const void* src, int src_dtype, int64_t rows, int col
 }
 
 extern "C" int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float* w1, int64_t w1_stride,
-                                             const float* gamma, const float* g0, const float* db1, int Hb, int V,
+                                             const float* gamma, const float* beta, const float* g0, const float* db1,
+                                             int Hb, int V,
                                              float* dw1, int64_t dw1_stride, float* dgamma, float* dbeta, void* stream) {
     TASU_CHECK_ARG(Hb > 0 && V > 0, "shape");
-    TASU_CHECK_ARG(G && w1 && gamma && g0 && db1 && dw1 && dgamma && dbeta, "null pointer");
+    TASU_CHECK_ARG(G && w1 && gamma && beta && g0 && db1 && dw1 && dgamma && dbeta, "null pointer");
     TASU_CHECK_ARG(g_stride >= V && w1_stride >= V && dw1_stride >= V, "stride too small");
     cudaStream_t st = (cudaStream_t)stream;
     TASU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * V, st));
     TASU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * V, st));
     const int rpc = 128;
     dim3 grid((unsigned)((V + 127) / 128), (unsigned)((Hb + rpc - 1) / rpc));
-    wgrad_finish_kernel<<<grid, 128, 0, st>>>(G, g_stride, w1, w1_stride, gamma, g0, db1, Hb, V, rpc, dw1, dw1_stride, dgamma, dbeta);
+    wgrad_finish_kernel<<<grid, 128, 0, st>>>(G, g_stride, w1, w1_stride, gamma, beta, g0, db1, Hb, V, rpc, dw1, dw1_stride, dgamma, dbeta);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

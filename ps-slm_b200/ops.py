@@ -360,15 +360,15 @@ def colsum(src: torch.Tensor):
     return out
 
 
-def linear_silu_wgrad_finish(G: torch.Tensor, w1: torch.Tensor, gamma: torch.Tensor, g0: torch.Tensor,
-                             db1: torch.Tensor):
+def linear_silu_wgrad_finish(G: torch.Tensor, w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                             g0: torch.Tensor, db1: torch.Tensor):
     """(dW1 [Hb,V], dgamma [V], dbeta [V]) from G = dzsT·x (fp32 [Hb, ldV])."""
     Hb, V = w1.shape
     dw1 = torch.empty(Hb, V, dtype=torch.float32, device=w1.device)
     dgamma = torch.empty(V, dtype=torch.float32, device=w1.device)
     dbeta = torch.empty(V, dtype=torch.float32, device=w1.device)
     L.check(L.lib().tasu_linear_silu_wgrad_finish(G.data_ptr(), G.stride(0), w1.data_ptr(), w1.stride(0),
-                                                  gamma.data_ptr(), g0.data_ptr(), db1.data_ptr(), Hb, V,
+                                                  gamma.data_ptr(), beta.data_ptr(), g0.data_ptr(), db1.data_ptr(), Hb, V,
                                                   dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
             "tasu_linear_silu_wgrad_finish")
     _count(1)

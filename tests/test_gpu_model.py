@@ -1,0 +1,50 @@
+"""GPU drop-in test: ps_slm_b200.model.slam_model_asr driven exactly like the reference's
+forward()/generate() call sites (Multitask/utils/deepspeed_utils.py:205-208,
+Multitask/inference_batch.py:146) with the fake encoder/LLM of tests/fakes.py, against what the
+UNMODIFIED reference handed to the LLM for the same inputs (tests/golden/model.npz)."""
+import numpy as np
+import pytest
+import torch
+
+import fakes as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name", list(F.CASES))
+def test_model_dispatch_matches_reference(dev, golden, name):
+    import ps_slm_b200.model as M
+    import ps_slm_b200.projector as P
+    g = golden["model"]
+    inp = F.build_inputs(name)
+    encoder, llm, projector, tok, train_config, model_config = F.build_parts(inp, P.PROJECTORS[inp["proj"]])
+    model = M.slam_model_asr(encoder, llm, projector, tok, train_config, model_config,
+                             encoder_tokenizer=F.FakeCTCTokenizer())
+    wsum = sum(float(p.detach().double().sum()) for p in model.parameters())
+    assert abs(wsum - float(g[f"{name}_wsum"])) < 1e-6 * max(1.0, abs(wsum)), "seeded weights differ from the golden run"
+    model = model.to(dev)
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in inp["batch"].items()}
+    torch.manual_seed(4321)
+    if inp["entry"] == "forward":
+        out, acc = model(**batch)
+        assert abs(float(out.loss) - float(g[f"{name}_ref_loss"])) < 2e-2 * max(1.0, abs(float(g[f"{name}_ref_loss"])))
+        out.loss.backward()                       # the training call site back-propagates into the projector
+        assert all(p.grad is not None for p in model.encoder_projector.parameters())
+    else:
+        model.generate(**batch)
+    seen = llm.seen
+    assert np.array_equal(seen["attention_mask"].cpu().numpy(), g[f"{name}_ref_mask"])
+    if f"{name}_ref_labels" in g.files:
+        assert np.array_equal(seen["labels"].cpu().numpy(), g[f"{name}_ref_labels"])
+    if f"{name}_ref_pos" in g.files:
+        assert np.array_equal(seen["position_ids"].cpu().numpy(), g[f"{name}_ref_pos"])
+    e, r = seen["inputs_embeds"].detach().float().cpu(), torch.from_numpy(g[f"{name}_ref_embeds"])
+    assert e.shape == r.shape
+    err = ((e - r).norm() / r.norm()).item()
+    assert err < 1e-2, f"{name}: inputs_embeds relative error {err}"
