@@ -187,8 +187,9 @@ class slam_model_asr(nn.Module):
                                                                  attention_mask, labels)
             return emb, mask, out_labels, pos
         blank = self.encoder.blank_id
-        encoder_out = raw_encoder_out[:, 4:, :]
-        encoder_out_lens = torch.clamp(raw_encoder_out_lens - 4, min=0)
+        if raw_encoder_out is not None:                        # None on the text-only branch (encoder skipped)
+            encoder_out = raw_encoder_out[:, 4:, :]
+            encoder_out_lens = torch.clamp(raw_encoder_out_lens - 4, min=0)
         if self.ctc_posterior:
             if self.gt_emb:
                 post, lens = (self.ctc_pseudo_posterior_noise(texts) if noisy else self.ctc_pseudo_posterior(texts))
