@@ -38,7 +38,8 @@ enum { TASU_INPUT_PROBS = 0,  /* probabilities or log-probabilities; auto-detect
 /* GEMM epilogues */
 enum { TASU_EPI_NONE = 0, TASU_EPI_BIAS = 1, TASU_EPI_BIAS_SILU = 2, TASU_EPI_BIAS_RELU = 3,
        TASU_EPI_LNFOLD_SILU = 4, /* silu(rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]) */
-       TASU_EPI_LNFOLD = 5       /* the same without the SiLU (pre-activation kept for training) */ };
+       TASU_EPI_LNFOLD = 5,      /* the same without the SiLU (pre-activation kept for training) */
+       TASU_EPI_SOFTMAX = 6      /* exp(acc + bias[n] - row_mean[m]) * row_rstd[m]: softmax with known row max / 1/sum */ };
 
 /* splice header words (int64) written by tasu_splice_header */
 enum { TASU_SH_SPLICED_LEN = 0,   /* S' = max_b sum(placeholders)            ps-slm.py:809 */
@@ -87,22 +88,38 @@ int tasu_frame_stats(const void* x, int dtype, int input_kind, int B, int T, int
  *   seg_start/seg_len/seg_score [B*T]  kept candidates of utterance b at [b*T, b*T+M_b)
  *   new_lens   [B] int64  M_b  (ps-slm.py:315)
  *   kept_frames [B] int32 or NULL: number of input frames covered by the kept candidates
+ *   seg_frame_off [B*T] int32 or NULL: per kept candidate, offset of its first frame among the
+ *               utterance's kept frames (compact layout of tasu_gather_kept_rows)
  */
 int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float* row_max,
                        const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
                        const int64_t* lens, int B, int T, int blank_id, float threshold,
                        int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
-                       int32_t* kept_frames, void* stream);
+                       int32_t* kept_frames, int32_t* seg_frame_off, void* stream);
 
-/* exclusive scan of new_lens → row_off [B+1] int32, header [TASU_CH_WORDS] int64 */
+/* exclusive scans: new_lens → row_off [B+1] int32, kept_frames → frame_off [B+1] int32 (optional);
+ * header [TASU_CH_WORDS] int64 */
 int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, const uint32_t* global_max_enc,
-                       int B, int32_t* row_off, int64_t* header, void* stream);
+                       int B, int32_t* row_off, int32_t* frame_off, int64_t* header, void* stream);
+
+/* Gather the encoder rows of the kept frames into a compact [F_kept, K] bf16 matrix (frames of one
+ * candidate adjacent, candidates in packed order) together with their softmax scalars, so that a
+ * second, 3x smaller CTC-head GEMM (TASU_EPI_SOFTMAX) recomputes probabilities only where PSD keeps
+ * them.  seg_src [N_out] = compact row of every packed candidate's first frame. */
+int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K,
+                          const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
+                          const int32_t* row_off, const int32_t* frame_off, const float* row_max,
+                          const float* row_sumexp, int64_t max_rows, void* xg_bf16, int64_t ldg,
+                          float* g_max, float* g_inv_sum, int32_t* seg_src, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,
  * :303-314).  feats is a [B, T, D] view (same tensor as the posterior on the default path).
  *   softmax_max/softmax_sumexp: NULL → pool feats as given; else feats are logits and
  *               exp(x - max[b,t]) / sumexp[b,t] is pooled (fused softmax).
+ *   seg_src: NULL → candidate (b,j) starts at feats[b, seg_start, :]; else feats is the compact
+ *               [F_kept, D] matrix of tasu_gather_kept_rows and packed row r starts at row seg_src[r]
+ *               (layout 0 only).
  *   layout 0 (packed):  out row r in [0, N_out) at out + r*out_row_stride      (N_out = row_off[B])
  *   layout 1 (padded):  out row (b, j<max_len) at out + (b*max_len + j)*out_row_stride, rows
  *               j >= M_b are zero-filled (ps-slm.py:308-314)
@@ -113,7 +130,7 @@ int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int T, int D,
                           int64_t batch_stride, int64_t row_stride,
                           const float* softmax_max, const float* softmax_sumexp,
                           const int32_t* seg_start, const int32_t* seg_len, const int32_t* row_off,
-                          int layout, int64_t max_len, int64_t max_rows,
+                          const int32_t* seg_src, int layout, int64_t max_len, int64_t max_rows,
                           void* out, int out_dtype, int64_t out_row_stride,
                           float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 
@@ -158,6 +175,20 @@ int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                       void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
                       const float* bias, const float* row_rstd, const float* row_mean,
                       const float* colsum, void* stream);
+/* ---------------------------------------------------------------------------------------
+ * Steps 1b+2a fused — CTC head with the softmax statistics computed in the GEMM epilogue:
+ * logits = X·W^T + b live only in TMEM; per frame the running max / sum-exp / argmax / blank logit
+ * are kept in registers while the CTA sweeps the vocabulary.  Replaces ctc_lo + softmax
+ * (ps-slm.py:450-451, :581-582), .max() (:256) and .argmax (:265) without materialising the
+ * [B, T+P, V] tensor.  X is [B*(T+P), K] bf16 (P = n_prefix query frames, dropped like :452-454),
+ * W is [V, K] bf16; outputs are the same four [B*T] arrays tasu_frame_stats(TASU_INPUT_LOGITS) gives.
+ */
+int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix);
+int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
+                        int B, int T, int n_prefix, int V, int K, int blank_id, int32_t* argmax,
+                        float* x_blank, float* row_max, float* row_sumexp, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
                            void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,

@@ -15,7 +15,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 TASU_OK = 0
 F32, BF16 = 0, 1
 INPUT_PROBS, INPUT_LOGITS = 0, 1
-EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, EPI_SOFTMAX = 0, 1, 2, 3, 4, 5, 6
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
 
@@ -26,13 +26,16 @@ SIGNATURES = {
     "tasu_last_error": (c_char_p, []),
     "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
-    "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P]),
-    "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _P]),
+    "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_ctc_head_stats_workspace": (_L, [_I, _I, _I]),
+    "tasu_ctc_head_stats": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_gemm_bf16_tn_simt": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "tasu_transpose_cast": (_I, [_P, _I, _L, _L, _L, _P, _P, _L, _P]),
     "tasu_silu_fwd": (_I, [_P, _L, _P, _P]),

@@ -176,6 +176,7 @@ class TasuBridge:
         self.blank_id, self.blank_threshold, self.ln_eps = int(blank_id), float(blank_threshold), float(ln_eps)
         self._ctc_cache = ProjectorCache()
         self.last_counts = {}
+        self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
         self.events = []              # [(stage name, start event, end event)] of the profiled calls
 
@@ -206,41 +207,59 @@ class TasuBridge:
         with self._stage("splice_plan"):
             sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
 
-        # (a1) ctc_lo on the tensor cores: logits [B*(T+4), ldv] fp32
         x2 = raw_encoder_out.reshape(B * T4, Denc)
         if x2.dtype != torch.bfloat16:
             with self._stage("cast_encoder_out"):
                 x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
-        ldv = ops.pad_to(V, 4)
-        logits = torch.empty(B * T4, ldv, dtype=torch.float32, device=dev)
-        with self._stage("ctc_lo_gemm"):
-            ops.gemm_bf16_tn(x2, w_ctc, B * T4, V, Denc, logits, L.EPI_BIAS, b_ctc)
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
-        post_view = logits.view(B, T4, ldv)[:, self.N_PREFIX:, :V]      # ps-slm.py:583 (logits, not probs)
-
-        # (a2) stats + collapse plan, (a8) splice plan; one header for both
         header = torch.empty(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64, device=dev)
-        with self._stage("frame_stats"):
-            st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
+        ldk = ops.pad_to(V)
+
+        if self.materialize_logits:
+            # (a1) ctc_lo on the tensor cores: logits [B*(T+4), ldv] fp32, then one streaming stats pass
+            ldv = ops.pad_to(V, 4)
+            logits = torch.empty(B * T4, ldv, dtype=torch.float32, device=dev)
+            with self._stage("ctc_lo_gemm"):
+                ops.gemm_bf16_tn(x2, w_ctc, B * T4, V, Denc, logits, L.EPI_BIAS, b_ctc)
+            post_view = logits.view(B, T4, ldv)[:, self.N_PREFIX:, :V]      # ps-slm.py:583 (logits, not probs)
+            with self._stage("frame_stats"):
+                st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
+        else:
+            # (a1+a2) fused: logits live only in TMEM, softmax statistics come out of the GEMM epilogue
+            with self._stage("ctc_head_stats"):
+                st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
+
+        # (a2) collapse plan, (a8) splice plan; one header for both
         with self._stage("collapse_plan"):
             plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
         with self._stage("splice_plan"):
             ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
         hdr = header.cpu()                                              # the single device→host read
         n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
+        n_frames = int(hdr[L.CH_KEPT_FRAMES])
         shdr = hdr[L.CH_WORDS:]
         _raise_splice_errors(shdr, attention_mask, B)
         spliced_len = int(shdr[L.SH_SPLICED_LEN])
 
-        # (a2) softmax + segmented mean-pool of the kept frames → packed bf16 rows + LN stats
-        ldk = ops.pad_to(V)
         if n_out > 0:
             pooled = torch.empty(n_out, ldk, dtype=torch.bfloat16, device=dev)
             mean = torch.empty(n_out, dtype=torch.float32, device=dev)
             rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
-            with self._stage("softmax_meanpool"):
-                ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
-                                     ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
+            if self.materialize_logits:
+                with self._stage("softmax_meanpool"):
+                    ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
+                                         ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
+            else:
+                # second, ~3x smaller CTC-head pass over the kept frames only: probabilities in bf16
+                with self._stage("gather_kept_rows"):
+                    xg, g_max, g_inv, seg_src = ops.gather_kept_rows(x2, B, T, self.N_PREFIX, Denc, plan, st,
+                                                                     n_frames, n_out)
+                probs = torch.empty(n_frames, ldk, dtype=torch.bfloat16, device=dev)
+                with self._stage("ctc_softmax_gemm"):
+                    ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, probs, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
+                with self._stage("meanpool"):
+                    ops.segment_meanpool(probs, plan, 0, max_len, n_out, pooled, ldk, ln_mean=mean, ln_rstd=rstd,
+                                         ln_eps=self.ln_eps, seg_src=seg_src, feat_dim=V)
             # (a5) projector
             audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                         stage=self._stage)
@@ -254,3 +273,82 @@ class TasuBridge:
         self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len,
                             "kept_frames": int(hdr[L.CH_KEPT_FRAMES])}
         return emb, mask, out_labels, pos, plan.new_lens
+
+
+class HostPipeline:
+    """End-to-end entry for HOST buffers (the call a serving loop makes): pinned host batches in,
+    pinned host results out, with the H2D copy of batch i+1 and the D2H copy of batch i-1 overlapped
+    with the kernels of batch i on three CUDA streams.
+
+        pipe = HostPipeline(bridge)
+        for emb, mask, pos, new_lens in pipe.run(batches):   # batches: (raw, raw_lens, input_ids, attention_mask)
+            ...                                              # pinned CPU tensors, valid until the next iteration
+    """
+
+    def __init__(self, bridge: "TasuBridge", device=None):
+        self.bridge = bridge
+        self.device = device if device is not None else bridge.embed_table.device
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_comp = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self._host_out = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _upload(self, batch):
+        with torch.cuda.stream(self.s_in):
+            dev = []
+            for t in batch:
+                if not t.is_pinned():
+                    t = t.pin_memory()
+                d = t.to(self.device, non_blocking=True)
+                d.record_stream(self.s_comp)
+                dev.append(d)
+            ev = torch.cuda.Event()
+            ev.record(self.s_in)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in batch)
+        return dev, ev
+
+    def _download(self, outs, slot):
+        key = (slot,) + tuple((tuple(o.shape), o.dtype) for o in outs)
+        if key not in self._host_out:
+            self._host_out[key] = tuple(torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs)
+        host = self._host_out[key]
+        ev_c = torch.cuda.Event()
+        ev_c.record(self.s_comp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_c)
+            for o, h in zip(outs, host):
+                o.record_stream(self.s_out)
+                h.copy_(o, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.s_out)
+        self.d2h_bytes = sum(o.numel() * o.element_size() for o in outs)
+        return host, ev
+
+    def run(self, batches):
+        it = iter(batches)
+        try:
+            nxt = self._upload(next(it))
+        except StopIteration:
+            return
+        pending = None
+        i = 0
+        while nxt is not None:
+            dev, ev_in = nxt
+            try:
+                nxt = self._upload(next(it))          # H2D of the next batch runs under this batch's kernels
+            except StopIteration:
+                nxt = None
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in)
+                emb, mask, _, pos, new_lens = self.bridge(*dev)
+            done = self._download((emb, mask, pos, new_lens), i & 1)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = done
+            i += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]

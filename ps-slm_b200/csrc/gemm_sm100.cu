@@ -255,7 +255,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             float rstd = 1.f, nmean = 0.f;
-            if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) && grow < p.M) { rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow); }
+            if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < p.M) {
+                rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow);
+            }
             const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -289,6 +291,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 x[e] = fmaf(rstd, fmaf(nmean, c[e], x[e]), b[e]);
                                 if (kEpi == TASU_EPI_LNFOLD_SILU) x[e] = silu_f(x[e]);
                             }
+                        } else if (kEpi == TASU_EPI_SOFTMAX) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)      // softmax with known row max (-nmean) and 1/sum (rstd)
+                                x[e] = exp2f((x[e] + b[e] + nmean) * 1.4426950408889634f) * rstd;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -353,6 +359,214 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------ fused CTC head + softmax statistics
+// logits = X·W^T + b are produced tile by tile in TMEM and consumed in place: every epilogue thread owns
+// one frame (TMEM lane) and keeps that frame's running max / sum-exp / argmax / blank logit in registers
+// while its CTA sweeps a contiguous range of vocabulary tiles.  Nothing of the [frames, 25055] logits
+// tensor ever reaches HBM (replaces ps-slm.py:450-451 / :581-582 + the argmax of :265).
+// Work item = (m_tile, vocab split); partial statistics of the S splits are merged by ctc_stats_combine_kernel.
+struct StatsParams {
+    int M, N, K;              // frames (raw rows incl. prefix), vocab, encoder width
+    int splits, nt_per;       // vocab splits and n-tiles per split
+    int blank;
+    const float* bias;
+    float* part_max; float* part_sum; int32_t* part_arg; float* xb_raw;
+};
+
+constexpr int kStatsSmemBytes = kStages * kStageBytes + 2 * BN * 4 + 128;
+
+__global__ void __launch_bounds__(kThreads, 1)
+ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const StatsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    float* s_bias = reinterpret_cast<float*>(smem + kStages * kStageBytes);       // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 2 * BN * 4);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tmem_full = bars + 2 * kStages;
+    uint64_t* tmem_empty = bars + 2 * kStages + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int num_items = m_tiles * p.splits;
+    const int k_blocks = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int m0 = (item / p.splits) * BM;
+                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+                for (int nt = nb; nt < ne; ++nt) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * kStageBytes;
+                        mbar_expect_tx(&full_bar[stage], kStageBytes);
+                        tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                        tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, nt * BN);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+                for (int nt = nb; nt < ne; ++nt) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int et = threadIdx.x - (kThreads - kEpiThreads);
+        constexpr float kL2e = 1.4426950408889634f;
+        int acc = 0; uint32_t acc_phase = 0;
+        int bbuf = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int m_tile = item / p.splits, split = item % p.splits;
+            const int row = m_tile * BM + et;
+            const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+            float rm = -INFINITY, rs = 0.f, xb = 0.f;
+            int best = 0x7fffffff;
+            for (int nt = nb; nt < ne; ++nt) {
+                const int n0 = nt * BN;
+                float* sb = s_bias + bbuf * BN;
+                for (int c = et; c < BN; c += kEpiThreads) {
+                    const int col = n0 + c;                       // -inf masks the columns beyond the vocabulary
+                    sb[c] = col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+
+                auto process = [&](uint32_t (&v)[32], int sub) {
+                    const int base = n0 + sub * 32;
+                    if (base >= p.N) return;
+                    const float4* b4 = reinterpret_cast<const float4*>(sb + sub * 32);
+                    float x[32];
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = b4[q];
+                        x[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
+                        x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+                        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+                        x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+                        cm = fmaxf(cm, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
+                    }
+                    if (cm > rm) {                                 // rare after the first slabs
+                        rs *= exp2f((rm - cm) * kL2e);
+                        rm = cm;
+                        int j0 = 31;
+#pragma unroll
+                        for (int j = 30; j >= 0; --j) j0 = (x[j] == cm) ? j : j0;
+                        best = base + j0;                          // first index of the maximum (torch tie rule)
+                    }
+                    const float mb = rm * kL2e;
+                    float acc_s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc_s += exp2f(fmaf(x[j], kL2e, -mb));
+                    rs += acc_s;
+                    if (p.blank >= base && p.blank < base + 32) {  // uniform branch: one slab of one tile
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) xb = (base + j == p.blank) ? x[j] : xb;
+                    }
+                };
+
+                uint32_t va[32], vb[32];
+                tmem_ld32(t_row, va);
+#pragma unroll 1
+                for (int sub = 0; sub < BN / 32; sub += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld32(t_row + (uint32_t)((sub + 1) * 32), vb);
+                    process(va, sub);
+                    tmem_ld_wait(vb);
+                    if (sub + 2 < BN / 32) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
+                    else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+                    process(vb, sub + 1);
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                bbuf ^= 1;
+            }
+            if (row < p.M) {
+                const int64_t o = (int64_t)split * p.M + row;
+                p.part_max[o] = rm;
+                p.part_sum[o] = rs;
+                p.part_arg[o] = best;
+                if (p.blank >= nb * BN && p.blank < ne * BN) p.xb_raw[row] = xb;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+// merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
+__global__ void __launch_bounds__(256)
+ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __restrict__ argmax,
+                         float* __restrict__ x_blank, float* __restrict__ row_max, float* __restrict__ row_sumexp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * T) return;
+    const int b = (int)(i / T), t = (int)(i % T);
+    const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
+    float m = -INFINITY; int a = 0x7fffffff;
+    for (int s = 0; s < p.splits; ++s) {
+        const float pm = p.part_max[(int64_t)s * p.M + r];
+        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower split = lower index
+    }
+    float sum = 0.f;
+    for (int s = 0; s < p.splits; ++s)
+        sum += p.part_sum[(int64_t)s * p.M + r] * exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
+    argmax[i] = a;
+    x_blank[i] = p.xb_raw[r];
+    row_max[i] = m;
+    row_sumexp[i] = sum;
+}
+
 // ------------------------------------------------------------------ CUDA-core cross-check
 template <typename TC>
 __global__ void __launch_bounds__(256)
@@ -375,7 +589,8 @@ gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bf
         float x = acc;
         if (p.epilogue == TASU_EPI_LNFOLD_SILU) x = silu_f(fmaf(p.row_rstd[m], x - p.row_mean[m] * p.colsum[n], p.bias[n]));
         else if (p.epilogue == TASU_EPI_LNFOLD) x = fmaf(p.row_rstd[m], x - p.row_mean[m] * p.colsum[n], p.bias[n]);
-        else if (p.epilogue != TASU_EPI_NONE) {
+        else if (p.epilogue == TASU_EPI_SOFTMAX) x = __expf(x + p.bias[n] - p.row_mean[m]) * p.row_rstd[m];
+        else if (p.epilogue != TASU_EPI_NONE && p.epilogue != TASU_EPI_SOFTMAX) {
             x += p.bias[n];
             if (p.epilogue == TASU_EPI_BIAS_SILU) x = silu_f(x);
             else if (p.epilogue == TASU_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
@@ -422,13 +637,14 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
                         const float* row_mean, const float* colsum) {
     TASU_CHECK_ARG(M >= 0 && N > 0 && K > 0, "M >= 0, N,K > 0");
     TASU_CHECK_ARG(c_dtype == TASU_F32 || c_dtype == TASU_BF16, "c_dtype");
-    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_LNFOLD, "epilogue");
+    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_SOFTMAX, "epilogue");
     TASU_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
     if (M == 0) return TASU_OK;
     TASU_CHECK_ARG(A && B && C, "null pointer");
     TASU_CHECK_ARG(epilogue == TASU_EPI_NONE || bias, "bias required");
     TASU_CHECK_ARG((epilogue != TASU_EPI_LNFOLD_SILU && epilogue != TASU_EPI_LNFOLD) || (row_rstd && row_mean && colsum),
                    "LN-fold vectors required");
+    TASU_CHECK_ARG(epilogue != TASU_EPI_SOFTMAX || (row_rstd && row_mean), "softmax row vectors required");
     return TASU_OK;
 }
 
@@ -455,7 +671,8 @@ static int launch_epi(int epilogue, int grid, cudaStream_t st, const CUtensorMap
         case TASU_EPI_BIAS_SILU: return launch_one<kOutBf16, TASU_EPI_BIAS_SILU>(grid, st, ma, mb, mc, p);
         case TASU_EPI_BIAS_RELU: return launch_one<kOutBf16, TASU_EPI_BIAS_RELU>(grid, st, ma, mb, mc, p);
         case TASU_EPI_LNFOLD_SILU: return launch_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p);
-        default: return launch_one<kOutBf16, TASU_EPI_LNFOLD>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD: return launch_one<kOutBf16, TASU_EPI_LNFOLD>(grid, st, ma, mb, mc, p);
+        default: return launch_one<kOutBf16, TASU_EPI_SOFTMAX>(grid, st, ma, mb, mc, p);
     }
 }
 
@@ -509,6 +726,70 @@ extern "C" int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B,
         gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (float*)C, ldc, p);
     else
         gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (__nv_bfloat16*)C, ldc, p);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+static void pick_splits(int m_tiles, int n_tiles, int grid, int* splits, int* nt_per) {
+    double best_eff = -1.0; int best_s = 1, best_per = n_tiles;
+    for (int s = 1; s <= 16 && s <= n_tiles; ++s) {
+        const int per = (n_tiles + s - 1) / s;
+        const int eff_s = (n_tiles + per - 1) / per;          // splits actually used with this tile count
+        const long items = (long)m_tiles * eff_s;
+        const long waves = (items + grid - 1) / grid;
+        const double eff = (double)items / (double)(waves * grid);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = eff_s; best_per = per; }
+    }
+    *splits = best_s; *nt_per = best_per;
+}
+
+extern "C" int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix) {
+    const int64_t rows = (int64_t)B * (T + n_prefix);
+    return rows * 16 * 12 + rows * 4 + 256;       // up to 16 splits x (max, sum, arg) + blank logits
+}
+
+extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
+                                   int B, int T, int n_prefix, int V, int K, int blank_id, int32_t* argmax,
+                                   float* x_blank, float* row_max, float* row_sumexp, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && V > 0 && K > 0, "shape");
+    TASU_CHECK_ARG(blank_id >= 0 && blank_id < V, "blank_id out of range");
+    TASU_CHECK_ARG(ldx >= K && ldw >= K, "leading dimension too small");
+    const int64_t rows64 = (int64_t)B * (T + n_prefix);
+    TASU_CHECK_ARG(rows64 < (1LL << 31), "too many frames for one call");
+    if ((int64_t)B * T == 0) return TASU_OK;
+    TASU_CHECK_ARG(x_bf16 && w_bf16 && argmax && x_blank && row_max && row_sumexp && workspace, "null pointer");
+    TASU_CHECK_ARG(workspace_bytes >= tasu_ctc_head_stats_workspace(B, T, n_prefix), "workspace too small");
+    TASU_CHECK_ARG(((uintptr_t)x_bf16 % 16 == 0) && ((uintptr_t)w_bf16 % 16 == 0) && ((uintptr_t)workspace % 16 == 0) &&
+                   (ldx * 2) % 16 == 0 && (ldw * 2) % 16 == 0, "16-byte alignment of operands");
+    const int M = (int)rows64;
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, x_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, ldx, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+    rc = make_map(&mb, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V, K, ldw, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
+    int grid = sm_count();
+    StatsParams p{};
+    p.M = M; p.N = V; p.K = K; p.blank = blank_id; p.bias = bias;
+    pick_splits(m_tiles, n_tiles, grid, &p.splits, &p.nt_per);
+    if (grid > m_tiles * p.splits) grid = m_tiles * p.splits;
+    float* ws = reinterpret_cast<float*>(workspace);
+    p.part_max = ws;
+    p.part_sum = ws + (int64_t)16 * M;
+    p.part_arg = reinterpret_cast<int32_t*>(ws + (int64_t)32 * M);
+    p.xb_raw = ws + (int64_t)48 * M;
+    cudaStream_t st = (cudaStream_t)stream;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(ctc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytes);
+    });
+    TASU_CHECK_CUDA(attr_err);
+    ctc_stats_kernel<<<grid, kThreads, kStatsSmemBytes, st>>>(ma, mb, p);
+    TASU_CHECK_LAUNCH();
+    const int64_t frames = (int64_t)B * T;
+    ctc_stats_combine_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max, row_sumexp);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -18,6 +18,7 @@ struct PoolArgs {
     const int32_t* seg_start;
     const int32_t* seg_len;
     const int32_t* row_off;
+    const int32_t* seg_src;
     int layout;
     int64_t max_len, max_rows;
     void* out;
@@ -67,7 +68,8 @@ meanpool_kernel(PoolArgs a) {
         __syncthreads();
         const int b = s_info[0], t0 = s_info[1], n = s_info[2];
         Tout* orow = out + r * a.ostride;
-        const Tin* src = feats + (int64_t)b * a.bstride + (int64_t)t0 * a.rstride;
+        const Tin* src = a.seg_src != nullptr ? feats + (int64_t)a.seg_src[r] * a.rstride
+                                              : feats + (int64_t)b * a.bstride + (int64_t)t0 * a.rstride;
         float acc_s = 0.f, acc_q = 0.f;
 
         if (kVec) {
@@ -185,7 +187,7 @@ extern "C" int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int
                                      int64_t batch_stride, int64_t row_stride,
                                      const float* softmax_max, const float* softmax_sumexp,
                                      const int32_t* seg_start, const int32_t* seg_len, const int32_t* row_off,
-                                     int layout, int64_t max_len, int64_t max_rows,
+                                     const int32_t* seg_src, int layout, int64_t max_len, int64_t max_rows,
                                      void* out, int out_dtype, int64_t out_row_stride,
                                      float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0 && D > 0, "B,T >= 0, D > 0");
@@ -195,6 +197,7 @@ extern "C" int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int
     TASU_CHECK_ARG((softmax_max == nullptr) == (softmax_sumexp == nullptr), "softmax stats come in pairs");
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
     TASU_CHECK_ARG(out_row_stride >= D, "out_row_stride < D");
+    TASU_CHECK_ARG(seg_src == nullptr || (layout == 0 && softmax_max == nullptr), "compact source needs packed layout, no softmax");
     if (B == 0 || max_rows <= 0 || (layout == 1 && max_len <= 0)) return TASU_OK;
     TASU_CHECK_ARG(feats && seg_start && seg_len && row_off && out, "null pointer");
     const int isz = in_dtype == TASU_F32 ? 4 : 2, osz = out_dtype == TASU_F32 ? 4 : 2;
@@ -203,7 +206,7 @@ extern "C" int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int
     const bool vec = ((uintptr_t)feats % 16 == 0) && ((batch_stride * isz) % 16 == 0) && ((row_stride * isz) % 16 == 0) &&
                      ((uintptr_t)out % 16 == 0) && ((out_row_stride * osz) % 16 == 0) && (D >= vi);
     PoolArgs a{feats, B, T, D, batch_stride, row_stride, softmax_max, softmax_sumexp, seg_start, seg_len, row_off,
-               layout, max_len, max_rows, out, out_row_stride, ln_mean, ln_rstd, ln_eps};
+               seg_src, layout, max_len, max_rows, out, out_row_stride, ln_mean, ln_rstd, ln_eps};
     int64_t rows_cap = layout == 0 ? max_rows : (int64_t)B * max_len;
     if (rows_cap > max_rows) rows_cap = max_rows;
     int64_t grid64 = (int64_t)sm_count() * 8;

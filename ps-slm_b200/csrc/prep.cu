@@ -98,6 +98,44 @@ sim_rows_kernel(const int32_t* __restrict__ tok, const float* __restrict__ hot, 
     }
 }
 
+// one warp per kept candidate: copy its frames' encoder rows (K bf16 each) into the compact matrix
+__global__ void __launch_bounds__(256)
+gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B, int T, int n_prefix, int K,
+                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
+                        const int32_t* __restrict__ seg_foff, const int32_t* __restrict__ row_off,
+                        const int32_t* __restrict__ frame_off, const float* __restrict__ row_max,
+                        const float* __restrict__ row_sumexp, int64_t max_rows, __nv_bfloat16* __restrict__ xg,
+                        int64_t ldg, float* __restrict__ g_max, float* __restrict__ g_inv, int32_t* __restrict__ seg_src) {
+    const int lane = threadIdx.x & 31;
+    const int n_out = row_off[B];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_out; r += warps) {
+        int lo = 0, hi = B;                                    // utterance of packed row r
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row_off[mid] <= r) lo = mid; else hi = mid; }
+        const int b = lo, j = r - row_off[b];
+        const int64_t pj = (int64_t)b * T + j;
+        const int t0 = seg_start[pj], n = seg_len[pj];
+        const int dst0 = frame_off[b] + seg_foff[pj];
+        if (lane == 0) seg_src[r] = dst0;
+        for (int f = 0; f < n; ++f) {
+            if (dst0 + f >= max_rows) break;
+            const __nv_bfloat16* src = x + ((int64_t)b * (T + n_prefix) + n_prefix + t0 + f) * ldx;
+            __nv_bfloat16* dst = xg + (int64_t)(dst0 + f) * ldg;
+            if ((K % 8 == 0) && ((ldx % 8) == 0) && ((ldg % 8) == 0)) {
+                for (int c = lane; c < K / 8; c += 32)
+                    reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+            } else {
+                for (int c = lane; c < K; c += 32) dst[c] = src[c];
+            }
+            if (lane == 0) {
+                const int64_t fr = (int64_t)b * T + t0 + f;
+                g_max[dst0 + f] = row_max[fr];
+                g_inv[dst0 + f] = 1.f / row_sumexp[fr];
+            }
+        }
+    }
+}
+
 }  // namespace tasu
 
 using namespace tasu;
@@ -157,6 +195,24 @@ extern "C" int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, con
         sim_rows_kernel<float><<<grid, 256, 0, st>>>(tok, hot, base, dst_row, n_rows, V, (float*)out, out_row_stride, ln_mean, ln_rstd, ln_eps);
     else
         sim_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tok, hot, base, dst_row, n_rows, V, (__nv_bfloat16*)out, out_row_stride, ln_mean, ln_rstd, ln_eps);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K,
+                                     const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
+                                     const int32_t* row_off, const int32_t* frame_off, const float* row_max,
+                                     const float* row_sumexp, int64_t max_rows, void* xg_bf16, int64_t ldg,
+                                     float* g_max, float* g_inv_sum, int32_t* seg_src, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && ldx >= K && ldg >= K, "shape");
+    if (B == 0 || max_rows <= 0) return TASU_OK;
+    TASU_CHECK_ARG(x_bf16 && seg_start && seg_len && seg_frame_off && row_off && frame_off && row_max && row_sumexp &&
+                   xg_bf16 && g_max && g_inv_sum && seg_src, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)x_bf16 % 16 == 0) && ((uintptr_t)xg_bf16 % 16 == 0), "16-byte alignment");
+    const unsigned grid = (unsigned)(tasu::sm_count() * 8);
+    gather_kept_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_bf16, ldx, B, T, n_prefix, K, seg_start, seg_len, seg_frame_off, row_off, frame_off,
+        row_max, row_sumexp, max_rows, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, seg_src);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -113,7 +113,8 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
                      const float* __restrict__ rmax_all, const float* __restrict__ rsum_all,
                      const uint32_t* __restrict__ gmax, const int64_t* __restrict__ lens, int T_,
                      int blank, float thr, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len,
-                     float* __restrict__ seg_score, int64_t* __restrict__ new_lens, int32_t* __restrict__ kept_frames) {
+                     float* __restrict__ seg_score, int64_t* __restrict__ new_lens, int32_t* __restrict__ kept_frames,
+                     int32_t* __restrict__ seg_foff) {
     __shared__ int scratch[33];
     const int b = blockIdx.x;
     int64_t L64 = lens[b];
@@ -144,28 +145,27 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
                 flag = score < thr;
             }
         }
-        int total;
+        int total, ftotal;
         const int excl = block_excl_scan_i(flag, scratch, &total);
+        const int fexcl = block_excl_scan_i(flag ? n : 0, scratch, &ftotal);
         if (flag) {
             const int64_t j = (int64_t)b * T_ + carry + excl;
             seg_start[j] = t;
             seg_len[j] = n;
             if (seg_score) seg_score[j] = score;
+            if (seg_foff) seg_foff[j] = frames + fexcl;     // kept-frame offset inside the utterance
         }
         carry += total;
-        if (flag) frames += n;
+        frames += ftotal;
     }
-    if (kept_frames != nullptr) {
-        frames = block_sum_i(frames, scratch);
-        if (threadIdx.x == 0) kept_frames[b] = frames;
-    }
+    if (kept_frames != nullptr && threadIdx.x == 0) kept_frames[b] = frames;
     if (threadIdx.x == 0) new_lens[b] = carry;
 }
 
 __global__ void __launch_bounds__(1024)
 collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __restrict__ kept_frames,
                      const uint32_t* __restrict__ gmax, int B, int32_t* __restrict__ row_off,
-                     int64_t* __restrict__ header) {
+                     int32_t* __restrict__ frame_off, int64_t* __restrict__ header) {
     __shared__ int scratch[33];
     int carry = 0, mx = 0, frames = 0;
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
@@ -176,10 +176,16 @@ collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __rest
         if (b < B) row_off[b] = carry + excl;
         carry += total;
         mx = max(mx, v);
-        if (kept_frames != nullptr && b < B) frames += kept_frames[b];
+        if (kept_frames != nullptr) {
+            const int kf = b < B ? kept_frames[b] : 0;
+            int ftotal;
+            const int fexcl = block_excl_scan_i(kf, scratch, &ftotal);
+            if (frame_off != nullptr && b < B) frame_off[b] = frames + fexcl;
+            frames += ftotal;
+        }
     }
     mx = block_max_i(mx, scratch);
-    frames = block_sum_i(frames, scratch);
+    if (frame_off != nullptr && threadIdx.x == 0) frame_off[B] = frames;
     if (threadIdx.x == 0) {
         row_off[B] = carry;
         header[TASU_CH_N_OUT] = carry;
@@ -229,7 +235,7 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
                                   const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
                                   const int64_t* lens, int B, int T, int blank_id, float threshold,
                                   int32_t* seg_start, int32_t* seg_len, float* seg_score,
-                                  int64_t* new_lens, int32_t* kept_frames, void* stream) {
+                                  int64_t* new_lens, int32_t* kept_frames, int32_t* seg_frame_off, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0, "B,T >= 0");
     TASU_CHECK_ARG(input_kind == TASU_INPUT_PROBS || input_kind == TASU_INPUT_LOGITS, "input_kind");
     if (B == 0) return TASU_OK;
@@ -239,20 +245,20 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
     cudaStream_t st = (cudaStream_t)stream;
     if (input_kind == TASU_INPUT_LOGITS)
         collapse_plan_kernel<true><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                      blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames);
+                                                      blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off);
     else
         collapse_plan_kernel<false><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                       blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames);
+                                                       blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
 
 extern "C" int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames,
-                                  const uint32_t* global_max_enc, int B, int32_t* row_off, int64_t* header,
-                                  void* stream) {
+                                  const uint32_t* global_max_enc, int B, int32_t* row_off, int32_t* frame_off,
+                                  int64_t* header, void* stream) {
     TASU_CHECK_ARG(B >= 0 && row_off && header, "B >= 0, non-null outputs");
     TASU_CHECK_ARG(B == 0 || new_lens, "null new_lens");
-    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, header);
+    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, frame_off, header);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

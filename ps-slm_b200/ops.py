@@ -79,8 +79,49 @@ def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[
     return st
 
 
+def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor], B: int, T: int,
+                   n_prefix: int, V: int, K: int, blank_id: int) -> FrameStats:
+    """Fused CTC head + softmax statistics (tasu_ctc_head_stats): x_bf16 [B*(T+P), ld], w_bf16 [V, ld]."""
+    _need_cuda(x_bf16, w_bf16, bias)
+    dev = x_bf16.device
+    st = FrameStats()
+    st.kind, st.B, st.T = L.INPUT_LOGITS, B, T
+    st.argmax = torch.empty(B * T, dtype=torch.int32, device=dev)
+    st.x_blank = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.row_max = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.row_sumexp = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.gmax = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = L.lib().tasu_ctc_head_stats_workspace(B, T, n_prefix)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(L.lib().tasu_ctc_head_stats(x_bf16.data_ptr(), x_bf16.stride(0), w_bf16.data_ptr(), w_bf16.stride(0),
+                                        _ptr(bias), B, T, n_prefix, V, K, blank_id, st.argmax.data_ptr(),
+                                        st.x_blank.data_ptr(), st.row_max.data_ptr(), st.row_sumexp.data_ptr(),
+                                        ws.data_ptr(), nbytes, _stream()), "tasu_ctc_head_stats")
+    _count(2)
+    return st
+
+
+def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, plan: "CollapsePlan",
+                     st: FrameStats, n_frames: int, n_out: int):
+    """→ (xg bf16 [n_frames, pad64(K)], g_max, g_inv_sum [n_frames], seg_src int32 [n_out])."""
+    dev = x_bf16.device
+    ldg = pad_to(K)
+    xg = torch.empty(max(n_frames, 1), ldg, dtype=torch.bfloat16, device=dev)
+    g_max = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
+    g_inv = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
+    seg_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+    L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K,
+                                          plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.seg_foff.data_ptr(),
+                                          plan.row_off.data_ptr(), plan.frame_off.data_ptr(), st.row_max.data_ptr(),
+                                          st.row_sumexp.data_ptr(), n_frames, xg.data_ptr(), ldg, g_max.data_ptr(),
+                                          g_inv.data_ptr(), seg_src.data_ptr(), _stream()), "tasu_gather_kept_rows")
+    _count(1)
+    return xg, g_max, g_inv, seg_src
+
+
 class CollapsePlan:
-    __slots__ = ("seg_start", "seg_len", "seg_score", "new_lens", "kept_frames", "row_off", "header", "B", "T")
+    __slots__ = ("seg_start", "seg_len", "seg_score", "seg_foff", "new_lens", "kept_frames", "row_off", "frame_off",
+                 "header", "B", "T")
 
 
 def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: float,
@@ -97,17 +138,20 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     p.seg_score = torch.empty(max(B * T, 1), dtype=torch.float32, device=dev) if want_scores else None
     p.new_lens = torch.empty(B, dtype=torch.int64, device=dev)
     p.kept_frames = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+    p.seg_foff = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
+    p.frame_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
     lib = L.lib()
     L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
                                    _ptr(st.row_sumexp), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
                                    blank_id, float(threshold), p.seg_start.data_ptr(), p.seg_len.data_ptr(),
-                                   _ptr(p.seg_score), p.new_lens.data_ptr(), p.kept_frames.data_ptr(), _stream()),
-            "tasu_collapse_plan")
+                                   _ptr(p.seg_score), p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
+                                   p.seg_foff.data_ptr(), _stream()), "tasu_collapse_plan")
     L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
                                    st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
-                                   B, p.row_off.data_ptr(), p.header.data_ptr(), _stream()), "tasu_collapse_scan")
+                                   B, p.row_off.data_ptr(), p.frame_off.data_ptr(), p.header.data_ptr(), _stream()),
+            "tasu_collapse_scan")
     _count(2)
     return p
 
@@ -115,15 +159,20 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
 def segment_meanpool(feats: torch.Tensor, plan: CollapsePlan, layout: int, max_len: int, max_rows: int,
                      out: torch.Tensor, out_row_stride: int, softmax: Optional[FrameStats] = None,
                      ln_mean: Optional[torch.Tensor] = None, ln_rstd: Optional[torch.Tensor] = None,
-                     ln_eps: float = 1e-5):
+                     ln_eps: float = 1e-5, seg_src: Optional[torch.Tensor] = None, feat_dim: Optional[int] = None):
+    """``seg_src`` given → ``feats`` is the compact [F_kept, pitch] matrix of gather_kept_rows (2-D)."""
     _need_cuda(feats, out)
-    feats, bs, rs = view3(feats)
-    B, T, D = feats.shape
+    if seg_src is not None:
+        B, T, D = plan.B, plan.T, feat_dim
+        bs, rs = 0, feats.stride(0)
+    else:
+        feats, bs, rs = view3(feats)
+        B, T, D = feats.shape
     L.check(L.lib().tasu_segment_meanpool(
         feats.data_ptr(), _dt(feats), B, T, D, bs, rs,
         _ptr(softmax.row_max) if softmax is not None else None,
         _ptr(softmax.row_sumexp) if softmax is not None else None,
-        plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.row_off.data_ptr(),
+        plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.row_off.data_ptr(), _ptr(seg_src),
         layout, max_len, max_rows, out.data_ptr(), _dt(out), out_row_stride,
         _ptr(ln_mean), _ptr(ln_rstd), float(ln_eps), _stream()), "tasu_segment_meanpool")
     _count(1)

@@ -15,7 +15,7 @@ def _header_functions():
     src = open(os.path.join(ROOT, "include", "tasu_bridge.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?:int|const char\*)\s+(tasu_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(?:int64_t|int|const char\*)\s+(tasu_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else args.count(",") + 1
         out[m.group(1)] = n
@@ -54,14 +54,14 @@ def test_argument_validation_without_gpu(lib):
     # LN-fold epilogue without its vectors
     rc = lib.tasu_gemm_bf16_tn(16, 8, 16, 8, 16, L.F32, 8, 4, 4, 8, L.EPI_LNFOLD_SILU, 16, None, None, None, None)
     assert rc == -1 and b"LN-fold" in lib.tasu_last_error()
-    rc = lib.tasu_segment_meanpool(None, 7, 1, 1, 1, 1, 1, None, None, None, None, None, 0, 1, 1, None, 0, 1, None, None, 1e-5, None)
+    rc = lib.tasu_segment_meanpool(None, 7, 1, 1, 1, 1, 1, None, None, None, None, None, None, 0, 1, 1, None, 0, 1, None, None, 1e-5, None)
     assert rc == -1
     rc = lib.tasu_splice_plan(None, None, 3, 1, 1, 0, None, 0, 1, None, None, None, None, None)
     assert rc == -1
     with pytest.raises(L.TasuError):
         L.check(rc, "tasu_splice_plan")
     # empty problems are fine without a device
-    assert lib.tasu_collapse_plan(None, None, None, None, None, 0, None, 0, 10, 0, 0.9, None, None, None, None, None, None) == 0
+    assert lib.tasu_collapse_plan(None, None, None, None, None, 0, None, 0, 10, 0, 0.9, None, None, None, None, None, None, None) == 0
     assert lib.tasu_cast_rows(None, 0, 0, 8, 8, None, 1, 8, None, None, 1e-5, None) == 0
 
 

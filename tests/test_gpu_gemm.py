@@ -92,6 +92,33 @@ def test_gemm_back_to_back_is_deterministic(dev):
     assert (C1 - ref).abs().max().item() / ref.abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("B,T,P,V,K,blank", [(3, 37, 4, 25055, 512, 0), (2, 130, 4, 300, 64, 7), (1, 9, 0, 61, 32, 60),
+                                             (5, 300, 4, 4099, 512, 0)])
+def test_ctc_head_stats_fused(dev, B, T, P, V, K, blank):
+    """Fused CTC head + softmax statistics (logits never leave TMEM) vs fp32 math on the same bf16 operands."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(V + T)
+    x = (torch.randn(B * (T + P), K) * 0.7).bfloat16()
+    w = (torch.randn(V, K) * 0.6).bfloat16()
+    lab = torch.randint(0, V, (B * (T + P),))
+    x += (4.0 * w[lab].float() / w[lab].float().norm(dim=1, keepdim=True)).bfloat16()     # a clear winner per frame
+    bias = torch.randn(V) * 0.1
+    ldx, ldw = ops.pad_to(K), ops.pad_to(K)
+    xd = torch.zeros(B * (T + P), ldx, dtype=torch.bfloat16); xd[:, :K] = x
+    wd = torch.zeros(V, ldw, dtype=torch.bfloat16); wd[:, :K] = w
+    st = ops.ctc_head_stats(xd.to(dev), wd.to(dev), bias.to(dev), B, T, P, V, K, blank)
+    torch.cuda.synchronize()
+    logits = (x.double() @ w.double().T + bias.double()).view(B, T + P, V)[:, P:, :].reshape(B * T, V)
+    ref_max, ref_arg = logits.max(-1)
+    top2 = logits.topk(2, -1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3                       # ties within accumulation noise are not comparable
+    assert torch.equal(st.argmax.cpu().long()[clear], ref_arg[clear])
+    np.testing.assert_allclose(st.row_max.cpu().double().numpy(), ref_max.numpy(), rtol=1e-4, atol=1e-4)
+    ref_sum = torch.exp(logits - ref_max[:, None]).sum(-1)
+    np.testing.assert_allclose(st.row_sumexp.cpu().double().numpy(), ref_sum.numpy(), rtol=2e-3)
+    np.testing.assert_allclose(st.x_blank.cpu().double().numpy(), logits[:, blank].numpy(), rtol=1e-4, atol=1e-4)
+
+
 def _cfg(D, H, k=1):
     return types.SimpleNamespace(encoder_dim=D, llm_dim=H, encoder_projector_ds_rate=k)
 
@@ -138,8 +165,9 @@ def test_projector_linear_silu_full_width(dev):
     assert rowerr < 2e-2, f"worst row relative error {rowerr}"
 
 
+@pytest.mark.parametrize("materialize", [False, True])
 @pytest.mark.parametrize("ragged,labels", [(False, False), (True, True)])
-def test_bridge_inference_vs_oracle(dev, ragged, labels):
+def test_bridge_inference_vs_oracle(dev, ragged, labels, materialize):
     """Whole fused path (ctc_lo → softmax/argmax → collapse → pool → projector → splice) against the
     fp32 oracle on planted-label input: every integer bit-exact, embeddings within 1e-2."""
     import ps_slm_b200.projector as P
@@ -163,6 +191,7 @@ def test_bridge_inference_vs_oracle(dev, ragged, labels):
                                                         S.SPEECH_ID, S.PAD_ID)
     proj = proj.to(dev).eval()
     br = TasuBridge(w.to(dev), b.to(dev), proj, table.to(dev), S.SPEECH_ID, S.PAD_ID)
+    br.materialize_logits = materialize           # False: fused stats + recompute of the kept frames (default)
     e, m, l, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev), None if lab is None else lab.to(dev))
     assert torch.equal(nl.cpu(), nl_r)
     assert e.shape == e_r.shape
