@@ -102,15 +102,23 @@ int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float*
 int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, const uint32_t* global_max_enc,
                        int B, int32_t* row_off, int32_t* frame_off, int64_t* header, void* stream);
 
-/* Gather the encoder rows of the kept frames into a compact [F_kept, K] bf16 matrix (frames of one
- * candidate adjacent, candidates in packed order) together with their softmax scalars, so that a
- * second, 3x smaller CTC-head GEMM (TASU_EPI_SOFTMAX) recomputes probabilities only where PSD keeps
- * them.  seg_src [N_out] = compact row of every packed candidate's first frame. */
-int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K,
+/* Gather the encoder rows of the kept frames into a compact [F_kept, K] bf16 matrix together with their
+ * softmax scalars, so that a second, ~3x smaller CTC-head GEMM (TASU_EPI_SOFTMAX) recomputes probabilities
+ * only where PSD keeps them.  Layout: row r < N_out = FIRST frame of packed candidate r (so the GEMM writes
+ * single-frame candidates — the majority — straight into their pooled row), rows >= N_out = the extra frames
+ * of multi-frame runs in candidate order.  pk_len [N_out] = run length, tail_src [N_out] = compact row of a
+ * candidate's second frame.  With row_sumexp2 given, LayerNorm statistics of the single-frame rows are
+ * emitted (mean = 1/V, rstd from sum p^2); multi-frame rows get theirs from tasu_pool_tail. */
+int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K, int V,
                           const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
                           const int32_t* row_off, const int32_t* frame_off, const float* row_max,
-                          const float* row_sumexp, int64_t max_rows, void* xg_bf16, int64_t ldg,
-                          float* g_max, float* g_inv_sum, int32_t* seg_src, void* stream);
+                          const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
+                          void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
+                          int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+/* In-place mean over the frames of every multi-frame candidate of the compact probability matrix
+ * (ps-slm.py:286): probs[r] = (probs[r] + sum of its tail rows) / n, plus LayerNorm statistics. */
+int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
+                   const int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,
@@ -181,13 +189,15 @@ int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
  * are kept in registers while the CTA sweeps the vocabulary.  Replaces ctc_lo + softmax
  * (ps-slm.py:450-451, :581-582), .max() (:256) and .argmax (:265) without materialising the
  * [B, T+P, V] tensor.  X is [B*(T+P), K] bf16 (P = n_prefix query frames, dropped like :452-454),
- * W is [V, K] bf16; outputs are the same four [B*T] arrays tasu_frame_stats(TASU_INPUT_LOGITS) gives.
+ * W is [V, K] bf16; outputs are the same four [B*T] arrays tasu_frame_stats(TASU_INPUT_LOGITS) gives,
+ * plus (optional) row_sumexp2 = sum_v exp(2(x - row_max)), from which sum_v p_v^2 = row_sumexp2/row_sumexp^2
+ * feeds the LayerNorm fold of single-frame rows without another pass.
  */
 int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix);
 int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
                         int B, int T, int n_prefix, int V, int K, int blank_id, int32_t* argmax,
-                        float* x_blank, float* row_max, float* row_sumexp, void* workspace,
-                        int64_t workspace_bytes, void* stream);
+                        float* x_blank, float* row_max, float* row_sumexp, float* row_sumexp2,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -228,6 +238,7 @@ int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float*
  * tasu_splice_rowstat : per-row counts                                   (:771-772, :788-789)
  * tasu_splice_plan    : placeholders, cumsum, per-token slot ordinals    (:805-812, :842-859)
  * tasu_splice_header  : S', padding side, error words, per-row bases     (:809, :861)
+ * (the caller reads the header — S', padding side, error words — and passes them back by value)
  * tasu_splice_scatter : writes inputs_embeds / mask / labels / position_ids / final ids
  *                       (:821-840, :867-871); text rows come from `text_src`:
  *                       text_mode 0 = inputs_embeds [B,S,H]; 1 = embedding table indexed by
@@ -250,7 +261,7 @@ int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, in
                         int64_t audio_max_len, int n_audio, int emb_dtype,
                         const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
                         const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
-                        const int64_t* header, int64_t pad_id, int64_t ignore_id,
+                        int left_padding, int64_t pad_id, int64_t ignore_id,
                         void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
                         int64_t* out_ids, void* stream);
 /* backward of the audio part of the splice: grad_audio[a,:] = grad_emb[slot(a),:] (training) */
@@ -258,7 +269,7 @@ int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const int64_t* i
                            const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
                            int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
                            const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
-                           const int32_t* audio_off, const int64_t* header, int audio_layout,
+                           const int32_t* audio_off, int left_padding, int audio_layout,
                            int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
                            void* grad_audio, void* stream);
 

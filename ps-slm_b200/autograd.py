@@ -97,7 +97,8 @@ class SpliceFunction(torch.autograd.Function):
                 pad_id, ignore_id):
         emb, mask, out_labels, pos, fids = ops.splice_scatter(plan, spliced_len, text_src, text_mode,
                                                               audio_rows.detach(), audio_layout, audio_max_len,
-                                                              labels, pad_id, ignore_id)
+                                                              labels, pad_id, ignore_id,
+                                                              left_padding=getattr(plan, "left_padding", None))
         ctx.plan, ctx.layout, ctx.max_len = plan, audio_layout, audio_max_len
         ctx.shape = tuple(audio_rows.shape)
         ctx.mark_non_differentiable(mask, pos, fids)

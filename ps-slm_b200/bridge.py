@@ -70,10 +70,12 @@ def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_
     _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
     if torch.is_grad_enabled() and audio_features.requires_grad:
         from .autograd import SpliceFunction            # gradient flows back to the projector output
+        p.left_padding = int(hdr[L.SH_LEFT_PADDING])
         return SpliceFunction.apply(audio_features, p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds.detach(), 0, 1,
                                     audio_features.shape[1], labels, pad_id, ignore_id)
     return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds, 0, audio_features, 1,
-                              audio_features.shape[1], labels, pad_id, ignore_id)
+                              audio_features.shape[1], labels, pad_id, ignore_id,
+                              left_padding=int(hdr[L.SH_LEFT_PADDING]))
 
 
 def _raise_splice_errors(hdr, attention_mask, num_audios):
@@ -183,6 +185,14 @@ class TasuBridge:
     def _stage(self, name):
         return _Stage(self, name)
 
+    def _header_slot(self):
+        """Ring of pinned host header buffers (collapse + splice words), one per in-flight call."""
+        if not hasattr(self, "_hdr_ring"):
+            self._hdr_ring = [torch.zeros(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64).pin_memory() for _ in range(4)]
+            self._hdr_i = 0
+        self._hdr_i = (self._hdr_i + 1) % len(self._hdr_ring)
+        return self._hdr_ring[self._hdr_i]
+
     def _ctc_weights(self):
         def build():
             w = cast_weight_bf16(self.w_ctc)
@@ -212,7 +222,10 @@ class TasuBridge:
             with self._stage("cast_encoder_out"):
                 x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
-        header = torch.empty(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64, device=dev)
+        # The plan headers are written by the kernels straight into pinned (UVA-mapped) host memory: the one
+        # device→host hand-off of the step needs no copy-engine transfer, so it cannot queue behind the bulk
+        # D2H of the previous batch when calls are pipelined (HostPipeline).
+        header = self._header_slot()
         ldk = ops.pad_to(V)
 
         if self.materialize_logits:
@@ -234,7 +247,10 @@ class TasuBridge:
             plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
         with self._stage("splice_plan"):
             ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
-        hdr = header.cpu()                                              # the single device→host read
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()                                                # the single device→host hand-off
+        hdr = header.clone()
         n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
         n_frames = int(hdr[L.CH_KEPT_FRAMES])
         shdr = hdr[L.CH_WORDS:]
@@ -242,24 +258,25 @@ class TasuBridge:
         spliced_len = int(shdr[L.SH_SPLICED_LEN])
 
         if n_out > 0:
-            pooled = torch.empty(n_out, ldk, dtype=torch.bfloat16, device=dev)
-            mean = torch.empty(n_out, dtype=torch.float32, device=dev)
-            rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
             if self.materialize_logits:
+                pooled = torch.empty(n_out, ldk, dtype=torch.bfloat16, device=dev)
+                mean = torch.empty(n_out, dtype=torch.float32, device=dev)
+                rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
                 with self._stage("softmax_meanpool"):
                     ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
                                          ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
             else:
-                # second, ~3x smaller CTC-head pass over the kept frames only: probabilities in bf16
+                # second, ~3x smaller CTC-head pass over the kept frames only: probabilities in bf16.  Row r of the
+                # compact matrix is the first frame of packed candidate r, so single-frame candidates (the majority)
+                # are final as the GEMM writes them; only multi-frame runs are averaged afterwards, in place.
                 with self._stage("gather_kept_rows"):
-                    xg, g_max, g_inv, seg_src = ops.gather_kept_rows(x2, B, T, self.N_PREFIX, Denc, plan, st,
-                                                                     n_frames, n_out)
-                probs = torch.empty(n_frames, ldk, dtype=torch.bfloat16, device=dev)
+                    xg, g_max, g_inv, pk_len, tail_src, mean, rstd = ops.gather_kept_rows(
+                        x2, B, T, self.N_PREFIX, Denc, V, plan, st, n_frames, n_out, self.ln_eps)
+                pooled = torch.empty(n_frames, ldk, dtype=torch.bfloat16, device=dev)
                 with self._stage("ctc_softmax_gemm"):
-                    ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, probs, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
-                with self._stage("meanpool"):
-                    ops.segment_meanpool(probs, plan, 0, max_len, n_out, pooled, ldk, ln_mean=mean, ln_rstd=rstd,
-                                         ln_eps=self.ln_eps, seg_src=seg_src, feat_dim=V)
+                    ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
+                with self._stage("pool_tail"):
+                    ops.pool_tail(pooled, V, n_out, pk_len, tail_src, mean, rstd, self.ln_eps)
             # (a5) projector
             audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                         stage=self._stage)
@@ -269,7 +286,7 @@ class TasuBridge:
         with self._stage("splice_scatter"):
             emb, mask, out_labels, pos, fids = ops.splice_scatter(
                 sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
-                want_ids=want_ids)
+                want_ids=want_ids, left_padding=int(shdr[L.SH_LEFT_PADDING]))
         self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len,
                             "kept_frames": int(hdr[L.CH_KEPT_FRAMES])}
         return emb, mask, out_labels, pos, plan.new_lens

@@ -370,7 +370,7 @@ struct StatsParams {
     int splits, nt_per;       // vocab splits and n-tiles per split
     int blank;
     const float* bias;
-    float* part_max; float* part_sum; int32_t* part_arg; float* xb_raw;
+    float* part_max; float* part_sum; float* part_sum2; int32_t* part_arg; float* xb_raw;
 };
 
 constexpr int kStatsSmemBytes = kStages * kStageBytes + 2 * BN * 4 + 128;
@@ -465,7 +465,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int m_tile = item / p.splits, split = item % p.splits;
             const int row = m_tile * BM + et;
             const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
-            float rm = -INFINITY, rs = 0.f, xb = 0.f;
+            float rm = -INFINITY, rs = 0.f, rs2 = 0.f, xb = 0.f;
             int best = 0x7fffffff;
             for (int nt = nb; nt < ne; ++nt) {
                 const int n0 = nt * BN;
@@ -495,7 +495,9 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         cm = fmaxf(cm, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
                     }
                     if (cm > rm) {                                 // rare after the first slabs
-                        rs *= exp2f((rm - cm) * kL2e);
+                        const float f = exp2f((rm - cm) * kL2e);
+                        rs *= f;
+                        rs2 *= f * f;
                         rm = cm;
                         int j0 = 31;
 #pragma unroll
@@ -503,10 +505,15 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         best = base + j0;                          // first index of the maximum (torch tie rule)
                     }
                     const float mb = rm * kL2e;
-                    float acc_s = 0.f;
+                    float acc_s = 0.f, acc_s2 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc_s += exp2f(fmaf(x[j], kL2e, -mb));
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = exp2f(fmaf(x[j], kL2e, -mb));
+                        acc_s += e;
+                        acc_s2 = fmaf(e, e, acc_s2);           // Σ exp(2(x-m)): gives Σ p² = s2/s² for the LayerNorm fold
+                    }
                     rs += acc_s;
+                    rs2 += acc_s2;
                     if (p.blank >= base && p.blank < base + 32) {  // uniform branch: one slab of one tile
 #pragma unroll
                         for (int j = 0; j < 32; ++j) xb = (base + j == p.blank) ? x[j] : xb;
@@ -532,6 +539,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int64_t o = (int64_t)split * p.M + row;
                 p.part_max[o] = rm;
                 p.part_sum[o] = rs;
+                p.part_sum2[o] = rs2;
                 p.part_arg[o] = best;
                 if (p.blank >= nb * BN && p.blank < ne * BN) p.xb_raw[row] = xb;
             }
@@ -548,7 +556,8 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
 __global__ void __launch_bounds__(256)
 ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __restrict__ argmax,
-                         float* __restrict__ x_blank, float* __restrict__ row_max, float* __restrict__ row_sumexp) {
+                         float* __restrict__ x_blank, float* __restrict__ row_max, float* __restrict__ row_sumexp,
+                         float* __restrict__ row_sumexp2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * T) return;
     const int b = (int)(i / T), t = (int)(i % T);
@@ -558,9 +567,13 @@ ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __r
         const float pm = p.part_max[(int64_t)s * p.M + r];
         if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower split = lower index
     }
-    float sum = 0.f;
-    for (int s = 0; s < p.splits; ++s)
-        sum += p.part_sum[(int64_t)s * p.M + r] * exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
+    float sum = 0.f, sum2 = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+        const float f = exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
+        sum += p.part_sum[(int64_t)s * p.M + r] * f;
+        sum2 += p.part_sum2[(int64_t)s * p.M + r] * f * f;
+    }
+    if (row_sumexp2) row_sumexp2[i] = sum2;
     argmax[i] = a;
     x_blank[i] = p.xb_raw[r];
     row_max[i] = m;
@@ -745,13 +758,13 @@ static void pick_splits(int m_tiles, int n_tiles, int grid, int* splits, int* nt
 
 extern "C" int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix) {
     const int64_t rows = (int64_t)B * (T + n_prefix);
-    return rows * 16 * 12 + rows * 4 + 256;       // up to 16 splits x (max, sum, arg) + blank logits
+    return rows * 16 * 16 + rows * 4 + 256;       // up to 16 splits x (max, sum, sum2, arg) + blank logits
 }
 
 extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
                                    int B, int T, int n_prefix, int V, int K, int blank_id, int32_t* argmax,
-                                   float* x_blank, float* row_max, float* row_sumexp, void* workspace,
-                                   int64_t workspace_bytes, void* stream) {
+                                   float* x_blank, float* row_max, float* row_sumexp, float* row_sumexp2,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && V > 0 && K > 0, "shape");
     TASU_CHECK_ARG(blank_id >= 0 && blank_id < V, "blank_id out of range");
     TASU_CHECK_ARG(ldx >= K && ldw >= K, "leading dimension too small");
@@ -777,8 +790,9 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     float* ws = reinterpret_cast<float*>(workspace);
     p.part_max = ws;
     p.part_sum = ws + (int64_t)16 * M;
-    p.part_arg = reinterpret_cast<int32_t*>(ws + (int64_t)32 * M);
-    p.xb_raw = ws + (int64_t)48 * M;
+    p.part_sum2 = ws + (int64_t)32 * M;
+    p.part_arg = reinterpret_cast<int32_t*>(ws + (int64_t)48 * M);
+    p.xb_raw = ws + (int64_t)64 * M;
     cudaStream_t st = (cudaStream_t)stream;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -789,7 +803,7 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     ctc_stats_kernel<<<grid, kThreads, kStatsSmemBytes, st>>>(ma, mb, p);
     TASU_CHECK_LAUNCH();
     const int64_t frames = (int64_t)B * T;
-    ctc_stats_combine_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max, row_sumexp);
+    ctc_stats_combine_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max, row_sumexp, row_sumexp2);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -98,30 +98,36 @@ sim_rows_kernel(const int32_t* __restrict__ tok, const float* __restrict__ hot, 
     }
 }
 
-// one warp per kept candidate: copy its frames' encoder rows (K bf16 each) into the compact matrix
+// one warp per kept candidate: copy its frames' encoder rows (K bf16 each) into the compact matrix.
+// Row r < n_out holds the candidate's first frame, extra frames of multi-frame runs go to the tail.
 __global__ void __launch_bounds__(256)
-gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B, int T, int n_prefix, int K,
+gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B, int T, int n_prefix, int K, int V,
                         const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
                         const int32_t* __restrict__ seg_foff, const int32_t* __restrict__ row_off,
                         const int32_t* __restrict__ frame_off, const float* __restrict__ row_max,
-                        const float* __restrict__ row_sumexp, int64_t max_rows, __nv_bfloat16* __restrict__ xg,
-                        int64_t ldg, float* __restrict__ g_max, float* __restrict__ g_inv, int32_t* __restrict__ seg_src) {
+                        const float* __restrict__ row_sumexp, const float* __restrict__ row_sumexp2,
+                        int64_t max_rows, __nv_bfloat16* __restrict__ xg, int64_t ldg, float* __restrict__ g_max,
+                        float* __restrict__ g_inv, int32_t* __restrict__ pk_len, int32_t* __restrict__ tail_src,
+                        float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
     const int lane = threadIdx.x & 31;
     const int n_out = row_off[B];
     const int warps = (gridDim.x * blockDim.x) >> 5;
+    const bool vec = (K % 8 == 0) && ((ldx % 8) == 0) && ((ldg % 8) == 0);
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_out; r += warps) {
         int lo = 0, hi = B;                                    // utterance of packed row r
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row_off[mid] <= r) lo = mid; else hi = mid; }
         const int b = lo, j = r - row_off[b];
         const int64_t pj = (int64_t)b * T + j;
         const int t0 = seg_start[pj], n = seg_len[pj];
-        const int dst0 = frame_off[b] + seg_foff[pj];
-        if (lane == 0) seg_src[r] = dst0;
+        // extra frames of earlier candidates: (kept frames before) - (kept candidates before)
+        const int tail0 = n_out + (frame_off[b] - row_off[b]) + (seg_foff[pj] - j);
+        if (lane == 0) { pk_len[r] = n; tail_src[r] = tail0; }
         for (int f = 0; f < n; ++f) {
-            if (dst0 + f >= max_rows) break;
+            const int64_t drow = f == 0 ? r : (int64_t)tail0 + f - 1;
+            if (drow >= max_rows) break;
             const __nv_bfloat16* src = x + ((int64_t)b * (T + n_prefix) + n_prefix + t0 + f) * ldx;
-            __nv_bfloat16* dst = xg + (int64_t)(dst0 + f) * ldg;
-            if ((K % 8 == 0) && ((ldx % 8) == 0) && ((ldg % 8) == 0)) {
+            __nv_bfloat16* dst = xg + drow * ldg;
+            if (vec) {
                 for (int c = lane; c < K / 8; c += 32)
                     reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
             } else {
@@ -129,9 +135,64 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
             }
             if (lane == 0) {
                 const int64_t fr = (int64_t)b * T + t0 + f;
-                g_max[dst0 + f] = row_max[fr];
-                g_inv[dst0 + f] = 1.f / row_sumexp[fr];
+                const float s = row_sumexp[fr];
+                g_max[drow] = row_max[fr];
+                g_inv[drow] = 1.f / s;
+                if (f == 0 && ln_mean != nullptr) {
+                    // single-frame row: mean p = 1/V, sum p^2 = s2/s^2 (multi-frame rows are overwritten by pool_tail)
+                    const float mean = 1.f / (float)V;
+                    const float q = row_sumexp2 ? row_sumexp2[fr] / (s * s) : 0.f;
+                    float var = q / (float)V - mean * mean;
+                    var = var < 0.f ? 0.f : var;
+                    ln_mean[r] = mean;
+                    ln_rstd[r] = rsqrtf(var + eps);
+                }
             }
+        }
+    }
+}
+
+// multi-frame candidates only: probs[r] = mean over its frames, in place; LayerNorm statistics of the result
+__global__ void __launch_bounds__(256)
+pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n_out, const int32_t* __restrict__ pk_len,
+                 const int32_t* __restrict__ tail_src, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
+    __shared__ float red[8];
+    for (int64_t r = blockIdx.x; r < n_out; r += gridDim.x) {
+        const int n = pk_len[r];
+        if (n <= 1) continue;                                  // CTA-uniform
+        __nv_bfloat16* row = probs + r * ld;
+        const __nv_bfloat16* tail = probs + (int64_t)tail_src[r] * ld;
+        const float inv = 1.f / (float)n;
+        float acc_q = 0.f;
+        const int nchunk = D / 8;
+        for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+            float v[8];
+            unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(row) + c), v, __nv_bfloat16());
+            for (int f = 1; f < n; ++f) {
+                float x[8];
+                unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(tail + (int64_t)(f - 1) * ld) + c), x, __nv_bfloat16());
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += x[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] *= inv; acc_q += v[e] * v[e]; }
+            reinterpret_cast<uint4*>(row)[c] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        for (int d = nchunk * 8 + threadIdx.x; d < D; d += blockDim.x) {
+            float v = __bfloat162float(row[d]);
+            for (int f = 1; f < n; ++f) v += __bfloat162float(tail[(int64_t)(f - 1) * ld + d]);
+            v *= inv;
+            acc_q += v * v;
+            row[d] = __float2bfloat16_rn(v);
+        }
+        acc_q = block_sum_f(acc_q, red);
+        if (threadIdx.x == 0 && ln_mean != nullptr) {
+            const float mean = 1.f / (float)D;
+            float var = acc_q / (float)D - mean * mean;
+            var = var < 0.f ? 0.f : var;
+            ln_mean[r] = mean;
+            ln_rstd[r] = rsqrtf(var + eps);
         }
     }
 }
@@ -199,20 +260,36 @@ extern "C" int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, con
     return TASU_OK;
 }
 
-extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K,
+extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K, int V,
                                      const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
                                      const int32_t* row_off, const int32_t* frame_off, const float* row_max,
-                                     const float* row_sumexp, int64_t max_rows, void* xg_bf16, int64_t ldg,
-                                     float* g_max, float* g_inv_sum, int32_t* seg_src, void* stream) {
-    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && ldx >= K && ldg >= K, "shape");
+                                     const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
+                                     void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
+                                     int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && V > 0 && ldx >= K && ldg >= K, "shape");
+    TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
     if (B == 0 || max_rows <= 0) return TASU_OK;
     TASU_CHECK_ARG(x_bf16 && seg_start && seg_len && seg_frame_off && row_off && frame_off && row_max && row_sumexp &&
-                   xg_bf16 && g_max && g_inv_sum && seg_src, "null pointer");
+                   xg_bf16 && g_max && g_inv_sum && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)x_bf16 % 16 == 0) && ((uintptr_t)xg_bf16 % 16 == 0), "16-byte alignment");
     const unsigned grid = (unsigned)(tasu::sm_count() * 8);
     gather_kept_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x_bf16, ldx, B, T, n_prefix, K, seg_start, seg_len, seg_frame_off, row_off, frame_off,
-        row_max, row_sumexp, max_rows, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, seg_src);
+        (const __nv_bfloat16*)x_bf16, ldx, B, T, n_prefix, K, V, seg_start, seg_len, seg_frame_off, row_off, frame_off,
+        row_max, row_sumexp, row_sumexp2, max_rows, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, pk_len, tail_src,
+        ln_mean, ln_rstd, ln_eps);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
+                              const int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
+    TASU_CHECK_ARG(D > 0 && ld >= D && n_out >= 0, "shape");
+    TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
+    if (n_out == 0) return TASU_OK;
+    TASU_CHECK_ARG(probs_bf16 && pk_len && tail_src, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)probs_bf16 % 16 == 0) && (ld % 8 == 0), "16-byte aligned rows");
+    pool_tail_kernel<<<row_grid(n_out), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
+                                                                         tail_src, ln_mean, ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -254,7 +254,7 @@ struct ScatterArgs {
     const void* text_src; int text_mode; int64_t text_stride;
     const void* audio; int audio_layout; int64_t audio_stride; int64_t audio_max_len; int n_audio;
     const int32_t* rowstat; const int32_t* new_pos; const int32_t* text_prefix; const int32_t* slot_ord;
-    const int32_t* slot_base; const int32_t* audio_off; const int64_t* header;
+    const int32_t* slot_base; const int32_t* audio_off; int left_padding;
     int64_t speech, pad_id, ignore_id;
     void* out_emb; void* out_mask; int64_t* out_labels; int64_t* out_pos; int64_t* out_ids;
 };
@@ -267,7 +267,7 @@ splice_scatter_kernel(ScatterArgs a) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (int64_t)a.B * a.Sp) return;
     const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
-    const bool left = a.header[TASU_SH_LEFT_PADDING] != 0;
+    const bool left = a.left_padding != 0;
     const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
                                 a.text_prefix, a.slot_ord, a.slot_base);
     const char* src = nullptr;
@@ -323,7 +323,7 @@ splice_audio_grad_kernel(ScatterArgs a, const void* grad_emb, void* grad_audio) 
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (int64_t)a.B * a.Sp) return;
     const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
-    const bool left = a.header[TASU_SH_LEFT_PADDING] != 0;
+    const bool left = a.left_padding != 0;
     const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
                                 a.text_prefix, a.slot_ord, a.slot_base);
     if (d.kind != 2) return;
@@ -395,7 +395,7 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
                                    int64_t audio_max_len, int n_audio, int emb_dtype,
                                    const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
                                    const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
-                                   const int64_t* header, int64_t pad_id, int64_t ignore_id,
+                                   int left_padding, int64_t pad_id, int64_t ignore_id,
                                    void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
                                    int64_t* out_ids, void* stream) {
     TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
@@ -405,7 +405,7 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
     TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
     if ((int64_t)B * spliced_len == 0) return TASU_OK;
     TASU_CHECK_ARG(input_ids && attention_mask && text_src && rowstat && new_pos && text_prefix && slot_ord &&
-                   slot_base && audio_off && header && out_emb && out_mask && out_pos, "null pointer");
+                   slot_base && audio_off && out_emb && out_mask && out_pos, "null pointer");
     ScatterArgs a{};
     a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype; a.labels = labels;
     a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
@@ -413,7 +413,7 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
     a.audio = audio_rows; a.audio_layout = audio_layout; a.audio_stride = audio_row_stride;
     a.audio_max_len = audio_max_len; a.n_audio = n_audio;
     a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
-    a.slot_base = slot_base; a.audio_off = audio_off; a.header = header;
+    a.slot_base = slot_base; a.audio_off = audio_off; a.left_padding = left_padding;
     a.speech = speech_id; a.pad_id = pad_id; a.ignore_id = ignore_id;
     a.out_emb = out_emb; a.out_mask = out_mask; a.out_labels = out_labels; a.out_pos = out_pos; a.out_ids = out_ids;
     unsigned grid;
@@ -429,20 +429,20 @@ extern "C" int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const
                                       const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
                                       int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
                                       const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
-                                      const int32_t* audio_off, const int64_t* header, int audio_layout,
+                                      const int32_t* audio_off, int left_padding, int audio_layout,
                                       int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
                                       void* grad_audio, void* stream) {
     TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
     TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
     if ((int64_t)B * spliced_len == 0) return TASU_OK;
     TASU_CHECK_ARG(grad_emb && input_ids && attention_mask && rowstat && new_pos && text_prefix && slot_ord &&
-                   slot_base && audio_off && header && grad_audio, "null pointer");
+                   slot_base && audio_off && grad_audio, "null pointer");
     ScatterArgs a{};
     a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype;
     a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
     a.audio_layout = audio_layout; a.audio_stride = audio_row_stride; a.audio_max_len = audio_max_len; a.n_audio = n_audio;
     a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
-    a.slot_base = slot_base; a.audio_off = audio_off; a.header = header; a.speech = speech_id;
+    a.slot_base = slot_base; a.audio_off = audio_off; a.left_padding = left_padding; a.speech = speech_id;
     unsigned grid;
     TASU_CHECK_ARG(launch_rows((int64_t)B * spliced_len, &grid) == 0, "too many rows");
     cudaStream_t st = (cudaStream_t)stream;

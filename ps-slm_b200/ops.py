@@ -54,7 +54,7 @@ def view3(x: torch.Tensor):
 
 
 class FrameStats:
-    __slots__ = ("argmax", "x_blank", "row_max", "row_sumexp", "gmax", "kind", "B", "T")
+    __slots__ = ("argmax", "x_blank", "row_max", "row_sumexp", "row_sumexp2", "gmax", "kind", "B", "T")
 
 
 def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[torch.Tensor] = None) -> FrameStats:
@@ -69,6 +69,7 @@ def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[
     st.x_blank = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.row_max = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.row_sumexp = torch.empty(B * T, dtype=torch.float32, device=dev) if input_kind == L.INPUT_LOGITS else None
+    st.row_sumexp2 = None
     st.gmax = torch.empty(1, dtype=torch.int32, device=dev)
     if lens is not None:
         lens = lens.to(torch.int64)
@@ -90,33 +91,48 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
     st.x_blank = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.row_max = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.row_sumexp = torch.empty(B * T, dtype=torch.float32, device=dev)
+    st.row_sumexp2 = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.gmax = torch.empty(1, dtype=torch.int32, device=dev)
     nbytes = L.lib().tasu_ctc_head_stats_workspace(B, T, n_prefix)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     L.check(L.lib().tasu_ctc_head_stats(x_bf16.data_ptr(), x_bf16.stride(0), w_bf16.data_ptr(), w_bf16.stride(0),
                                         _ptr(bias), B, T, n_prefix, V, K, blank_id, st.argmax.data_ptr(),
                                         st.x_blank.data_ptr(), st.row_max.data_ptr(), st.row_sumexp.data_ptr(),
-                                        ws.data_ptr(), nbytes, _stream()), "tasu_ctc_head_stats")
+                                        st.row_sumexp2.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+            "tasu_ctc_head_stats")
     _count(2)
     return st
 
 
-def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, plan: "CollapsePlan",
-                     st: FrameStats, n_frames: int, n_out: int):
-    """→ (xg bf16 [n_frames, pad64(K)], g_max, g_inv_sum [n_frames], seg_src int32 [n_out])."""
+def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, V: int, plan: "CollapsePlan",
+                     st: FrameStats, n_frames: int, n_out: int, ln_eps: float = 1e-5):
+    """→ (xg bf16 [n_frames, pad64(K)], g_max, g_inv_sum [n_frames], pk_len, tail_src int32 [n_out],
+    ln_mean, ln_rstd [n_out]).  Rows [0, n_out) are the first frames of the packed candidates."""
     dev = x_bf16.device
     ldg = pad_to(K)
     xg = torch.empty(max(n_frames, 1), ldg, dtype=torch.bfloat16, device=dev)
     g_max = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
     g_inv = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
-    seg_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
-    L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K,
+    pk_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+    tail_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+    mean = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
+    rstd = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
+    L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K, V,
                                           plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.seg_foff.data_ptr(),
                                           plan.row_off.data_ptr(), plan.frame_off.data_ptr(), st.row_max.data_ptr(),
-                                          st.row_sumexp.data_ptr(), n_frames, xg.data_ptr(), ldg, g_max.data_ptr(),
-                                          g_inv.data_ptr(), seg_src.data_ptr(), _stream()), "tasu_gather_kept_rows")
+                                          st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), n_frames, xg.data_ptr(), ldg,
+                                          g_max.data_ptr(), g_inv.data_ptr(), pk_len.data_ptr(), tail_src.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), float(ln_eps), _stream()),
+            "tasu_gather_kept_rows")
     _count(1)
-    return xg, g_max, g_inv, seg_src
+    return xg, g_max, g_inv, pk_len, tail_src, mean, rstd
+
+
+def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tail_src: torch.Tensor,
+              ln_mean: torch.Tensor, ln_rstd: torch.Tensor, ln_eps: float = 1e-5):
+    L.check(L.lib().tasu_pool_tail(probs.data_ptr(), probs.stride(0), D, n_out, pk_len.data_ptr(), tail_src.data_ptr(),
+                                   ln_mean.data_ptr(), ln_rstd.data_ptr(), float(ln_eps), _stream()), "tasu_pool_tail")
+    _count(1)
 
 
 class CollapsePlan:
@@ -141,6 +157,7 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     p.seg_foff = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
     p.frame_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    # ``header`` may be pinned host memory: under UVA its pointer is valid on the device
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
     lib = L.lib()
     L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
@@ -250,7 +267,7 @@ def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor,
 
 
 class SplicePlan:
-    __slots__ = ("rowstat", "new_pos", "text_prefix", "slot_ord", "slot_base", "audio_off", "header",
+    __slots__ = ("rowstat", "new_pos", "text_prefix", "slot_ord", "slot_base", "audio_off", "header", "left_padding",
                  "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask")
 
 
@@ -302,12 +319,16 @@ def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: 
 
 def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text_mode: int,
                    audio_rows: torch.Tensor, audio_layout: int, audio_max_len: int,
-                   labels: Optional[torch.Tensor], pad_id: int, ignore_id: int, want_ids: bool = True):
+                   labels: Optional[torch.Tensor], pad_id: int, ignore_id: int, want_ids: bool = True,
+                   left_padding: Optional[int] = None):
     """One gather/scatter pass → (emb [B,S',H], mask [B,S'], labels|None, position_ids, final_ids|None)."""
     _need_cuda(text_src, audio_rows, labels)
     B, S = p.B, p.S
     dev = p.input_ids.device
     H = text_src.shape[-1]
+    if left_padding is None:
+        left_padding = int(p.header.cpu()[L.SH_LEFT_PADDING])
+    p.left_padding = int(left_padding)
     if audio_rows.dtype != text_src.dtype:
         raise TypeError("audio rows (%s) and text embeddings (%s) must share a dtype" % (audio_rows.dtype, text_src.dtype))
     if text_src.stride(-1) != 1:
@@ -338,7 +359,7 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
         p.speech_id, text2.data_ptr(), text_mode, text_stride, audio_rows.data_ptr() if audio_rows.numel() else None,
         audio_layout, audio_stride, audio_max_len, p.n_audio, _dt(emb),
         p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(),
-        p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(), pad_id, ignore_id,
+        p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.left_padding, pad_id, ignore_id,
         emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), _stream()),
         "tasu_splice_scatter")
     _count(1)
@@ -358,7 +379,7 @@ def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, 
     L.check(L.lib().tasu_splice_audio_grad(
         grad_emb.data_ptr(), _dt(grad_emb), p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype,
         B, p.S, Sp, H, p.speech_id, p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(),
-        p.slot_ord.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.header.data_ptr(),
+        p.slot_ord.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.left_padding,
         audio_layout, H, audio_max_len, p.n_audio, ga.data_ptr(), _stream()), "tasu_splice_audio_grad")
     _count(1)
     return ga

@@ -68,8 +68,9 @@ def make_label_tracks(B: int, T: int, V: int, g: torch.Generator, rate: float = 
 
 
 def make_encoder_batch(B: int, T: int, w_ctc: torch.Tensor, seed: int = 2025, ragged: bool = False,
-                       noise: float = 0.3):
-    """raw_encoder_out [B, T+4, d] fp32, raw_lens [B] int64 (incl. the 4 prefix frames), labels [B,T]."""
+                       noise: float = 0.3, return_soft: bool = False):
+    """raw_encoder_out [B, T+4, d] fp32, raw_lens [B] int64 (incl. the 4 prefix frames), labels [B,T]
+    (+ the soft-blank mask [B,T] with ``return_soft``)."""
     V, d = w_ctc.shape
     g = torch.Generator().manual_seed(seed)
     lab = make_label_tracks(B, T, V, g)
@@ -88,7 +89,29 @@ def make_encoder_batch(B: int, T: int, w_ctc: torch.Tensor, seed: int = 2025, ra
         lens[0] = T
     else:
         lens = torch.full((B,), T, dtype=torch.long)
+    if return_soft:
+        return raw, (lens + N_PREFIX).to(torch.long), lab, soft
     return raw, (lens + N_PREFIX).to(torch.long), lab
+
+
+def expected_plan(lab: torch.Tensor, soft: torch.Tensor, lens: torch.Tensor):
+    """What PSD must produce for a planted batch, from first principles (ps-slm.py:268-297): token runs
+    merge and are always kept (their blank probability is ~0), blank frames stand alone and are kept
+    iff they are soft (p_blank < 0.9).  Returns per utterance the list of (start, length)."""
+    out = []
+    for b in range(lab.shape[0]):
+        L = int(lens[b])
+        row, sf = lab[b, :L].tolist(), soft[b, :L].tolist()
+        segs, s = [], 0
+        for e in range(1, L + 1):
+            if e == L or row[e] != row[s]:
+                if row[s] == 0:
+                    segs.extend((t, 1) for t in range(s, e) if sf[t])
+                else:
+                    segs.append((s, e - s))
+                s = e
+        out.append(segs)
+    return out
 
 
 def make_prompts(B: int, seed: int = 2025, tasks: Optional[List[str]] = None, left_pad: bool = True,

@@ -1,0 +1,101 @@
+"""GPU parity at BASELINE.json's full sizes (configs[1]: B=64 x 30 s) through size-independent
+properties, plus a mid-size run against the vectorised oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tasu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _bridge(dev, table_dtype=torch.bfloat16):
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    w, b = S.make_ctc_head()
+    torch.manual_seed(0)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=table_dtype, device=dev)
+    return w, b, proj, table, TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+
+
+@pytest.mark.parametrize("T,ragged", [(500, False), (1000, True), (83, True)])
+def test_full_batch_properties(dev, T, ragged):
+    """B=64: greedy ids == planted labels, kept candidates == first-principles plan, splice invariants,
+    fused and materialised paths agree on every integer and within 1e-2 on the embeddings."""
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.synth as S
+    import ps_slm_b200._lib as L
+    B = 64
+    w, b, proj, table, br = _bridge(dev)
+    raw, raw_lens, lab, soft = S.make_encoder_batch(B, T, w, seed=T, ragged=ragged, return_soft=True)
+    ids, mask, _ = S.make_prompts(B, seed=T, left_pad=True)
+    lens = raw_lens - 4
+    exp = S.expected_plan(lab, soft, lens)
+    exp_lens = torch.tensor([len(e) for e in exp])
+    outs = {}
+    for mode in (False, True):
+        br.materialize_logits = mode
+        e, m, _, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+        outs[mode] = (e, m, p, nl)
+        assert torch.equal(nl.cpu(), exp_lens), "compressed lengths differ from the planted plan"
+        # splice invariants: one row per prompt token + M_b - 1, left padded, positions count the mask
+        Sp = e.shape[1]
+        tok = mask.sum(1)
+        assert Sp == int((tok + exp_lens - 1).max())
+        assert torch.equal(m.sum(1).cpu(), tok + exp_lens - 1)
+        mm = m.cpu()
+        assert bool((mm[:, 1:] >= mm[:, :-1]).all()), "left padding: mask must be non-decreasing"
+        pos = p.cpu()
+        ref_pos = torch.cumsum(mm.long(), 1) - 1
+        ref_pos[~mm] = 1
+        assert torch.equal(pos, ref_pos)
+        assert bool((e.cpu()[~mm] == 0).all())
+    assert torch.equal(outs[False][1], outs[True][1]) and torch.equal(outs[False][2], outs[True][2])
+    a, c = outs[False][0].float(), outs[True][0].float()
+    assert ((a - c).norm() / c.norm()).item() < 1e-2
+    # the integer plan itself
+    x2, _, _ = ops.cast_rows(raw.to(dev).reshape(B * (T + 4), 512), torch.bfloat16)
+    wq, _, _ = ops.cast_rows(w.to(dev), torch.bfloat16)
+    st = ops.ctc_head_stats(x2, wq, b.to(dev), B, T, 4, S.V_CTC, 512, 0)
+    am = st.argmax.cpu().view(B, T).long()
+    valid = torch.arange(T)[None] < lens[:, None]
+    assert torch.equal(am[valid], lab[valid]), "greedy ids differ from the planted labels"
+    plan = ops.collapse_plan(st, lens.to(dev), 0, 0.9)
+    ss, sl = plan.seg_start.cpu().view(B, T), plan.seg_len.cpu().view(B, T)
+    for bb in range(B):
+        n = len(exp[bb])
+        assert list(zip(ss[bb, :n].tolist(), sl[bb, :n].tolist())) == exp[bb]
+    hdr = plan.header.cpu()
+    assert int(hdr[L.CH_N_OUT]) == int(exp_lens.sum()) and int(hdr[L.CH_MAX_LEN]) == int(exp_lens.max())
+    assert int(hdr[L.CH_KEPT_FRAMES]) == sum(n for e_ in exp for _, n in e_)
+
+
+def test_midsize_vs_oracle(dev):
+    """B=12 x 30 s through the whole bridge against the vectorised fp32 oracle."""
+    import ps_slm_b200.synth as S
+    B, T = 12, 500
+    w, b, proj, table, br = _bridge(dev, torch.float32)
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=99, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=99, left_pad=True)
+    sd = {k: v.detach().cpu() for k, v in proj.state_dict().items()}
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    (e_r, m_r, _, p_r, f_r), nl_r = O.bridge_inference(raw, raw_lens, w, b, pp, table.cpu(), ids, mask, None,
+                                                      S.SPEECH_ID, S.PAD_ID)
+    e, m, _, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    assert torch.equal(nl.cpu(), nl_r) and torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    audio = m_r & (f_r == S.PAD_ID)
+    e = e.cpu()
+    rows = (e[audio] - e_r[audio]).norm(dim=-1) / e_r[audio].norm(dim=-1)
+    assert rows.max().item() < 2e-2 and ((e[audio] - e_r[audio]).norm() / e_r[audio].norm()).item() < 1e-2
+    assert torch.equal(e[~audio], e_r[~audio])

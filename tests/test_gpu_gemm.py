@@ -117,6 +117,8 @@ def test_ctc_head_stats_fused(dev, B, T, P, V, K, blank):
     ref_sum = torch.exp(logits - ref_max[:, None]).sum(-1)
     np.testing.assert_allclose(st.row_sumexp.cpu().double().numpy(), ref_sum.numpy(), rtol=2e-3)
     np.testing.assert_allclose(st.x_blank.cpu().double().numpy(), logits[:, blank].numpy(), rtol=1e-4, atol=1e-4)
+    ref_sum2 = torch.exp(2 * (logits - ref_max[:, None])).sum(-1)
+    np.testing.assert_allclose(st.row_sumexp2.cpu().double().numpy(), ref_sum2.numpy(), rtol=2e-3)
 
 
 def _cfg(D, H, k=1):

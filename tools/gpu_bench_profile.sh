@@ -14,6 +14,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1; echo "ncu_list rc=$?" >> gpurun_out/rc_$TAG.txt
 # full capture of the hot kernels (one launch each, after warm-up launches)
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:'frame_stats_kernel|meanpool_kernel|gemm_bf16_tn_kernel|splice_scatter_kernel' -s 16 -c 5 \
+    -k regex:'frame_stats_kernel|meanpool_kernel|gemm_bf16_tn_kernel|splice_scatter_kernel|ctc_stats_kernel|pool_tail_kernel|gather_kept_rows_kernel' -s 21 -c 7 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu_full rc=$?" >> gpurun_out/rc_$TAG.txt
 cat gpurun_out/rc_$TAG.txt; tail -3 gpurun_out/smoke_$TAG.log; cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_ref_$TAG.json; tail -3 gpurun_out/bench_ref_$TAG.err
