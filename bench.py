@@ -240,7 +240,7 @@ def b200_arm(args):
 
     for i in range(max(args.warmup, 3)):
         step_dev(i)
-    run_e2e(max(args.warmup, 3))
+    run_e2e(max(args.warmup, 3, args.rotate + 1))      # every rotating batch once: allocator pools of the 3 streams warm
     # ---- device-resident timed region (value) with per-stage events
     barrier()
     sampler = ClockSampler(local)

@@ -89,6 +89,47 @@ def linear_silu_train(module, x):
     return y.view(B, T, -1)
 
 
+class LinearFunction(torch.autograd.Function):
+    """y = act(x·Wᵀ + b) on the tensor cores with a full backward (act ∈ {none, relu}); used by the
+    ``linear`` / ``simple_linear`` projectors (projector.py:39-50, :18-26) when they are trained."""
+
+    @staticmethod
+    def forward(ctx, x2, w, b, relu, out_dtype):
+        N, K = x2.shape
+        O = w.shape[0]
+        xb, _, _ = ops.cast_rows(x2.detach(), torch.bfloat16, ops.pad_to(K))
+        wb = cast_weight_bf16(w)
+        y = torch.empty(N, ops.pad_to(O, 8), dtype=out_dtype, device=x2.device)
+        ops.gemm_bf16_tn(xb, wb, N, O, K, y, L.EPI_BIAS_RELU if relu else L.EPI_BIAS, b.detach().float().contiguous())
+        y = y[:, :O]
+        ctx.save_for_backward(xb, w, y if relu else None)
+        ctx.relu, ctx.K, ctx.need_dx = relu, K, x2.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w, y = ctx.saved_tensors
+        N, K = xb.shape[0], ctx.K
+        O = w.shape[0]
+        dy = dy.float()
+        if ctx.relu:
+            dy = dy * (y > 0)                               # elementwise mask (plumbing), the contractions are ours
+        dy = dy.contiguous()
+        db = ops.colsum(dy)
+        dyT = ops.transpose_cast(dy, N, O)                  # [O, N]
+        xT = ops.transpose_cast(xb, N, K)                   # [K, N]
+        dw = torch.empty(O, ops.pad_to(K, 4), dtype=torch.float32, device=dy.device)
+        ops.gemm_bf16_tn(dyT, xT, O, K, N, dw)              # dW = dyᵀ·x
+        dx = None
+        if ctx.need_dx:
+            dyb, _, _ = ops.cast_rows(dy, torch.bfloat16, ops.pad_to(O, 8))
+            wT = ops.transpose_cast(w.detach(), O, K)       # [K, O]
+            dx = torch.empty(N, ops.pad_to(K, 4), dtype=torch.float32, device=dy.device)
+            ops.gemm_bf16_tn(dyb, wT, N, K, O, dx)          # dx = dy·W
+            dx = dx[:, :K]
+        return dx, dw[:, :K].to(w.dtype), db.to(w.dtype), None, None
+
+
 class SpliceFunction(torch.autograd.Function):
     """Differentiable splice: gradient flows to the audio rows only."""
 

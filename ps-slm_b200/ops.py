@@ -110,7 +110,8 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
     ln_mean, ln_rstd [n_out]).  Rows [0, n_out) are the first frames of the packed candidates."""
     dev = x_bf16.device
     ldg = pad_to(K)
-    xg = torch.empty(max(n_frames, 1), ldg, dtype=torch.bfloat16, device=dev)
+    cap = (max(n_frames, 1) + 2047) // 2048 * 2048          # few distinct sizes → allocator cache hits
+    xg = torch.empty(cap, ldg, dtype=torch.bfloat16, device=dev)[:max(n_frames, 1)]
     g_max = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
     g_inv = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
     pk_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)

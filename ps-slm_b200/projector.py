@@ -100,6 +100,12 @@ class EncoderProjectorConcat(nn.Module):
     def forward(self, x):
         x = _downsample(x, self.k)
         B, T, D = x.shape
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import LinearFunction
+            out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            h = LinearFunction.apply(x.reshape(B * T, D), self.linear1.weight, self.linear1.bias, True, torch.float32)
+            y = LinearFunction.apply(h, self.linear2.weight, self.linear2.bias, False, out_dtype)
+            return y.reshape(B, T, self.llm_dim)
         params = [self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias]
         w1, b1, w2, b2 = self._cache.get(params, lambda: (
             cast_weight_bf16(self.linear1.weight), self.linear1.bias.detach().float().contiguous(),
@@ -127,6 +133,11 @@ class EncoderProjectorLinear(nn.Module):
     def forward(self, x):
         x = _downsample(x, self.k)
         B, T, D = x.shape
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import LinearFunction
+            out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            y = LinearFunction.apply(x.reshape(B * T, D), self.map.weight, self.map.bias, False, out_dtype)
+            return y.reshape(B, T, self.llm_vocab)
         w, b = self._cache.get([self.map.weight, self.map.bias], lambda: (
             cast_weight_bf16(self.map.weight), self.map.bias.detach().float().contiguous()))
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32

@@ -52,7 +52,7 @@ def test_full_batch_properties(dev, T, ragged):
         # splice invariants: one row per prompt token + M_b - 1, left padded, positions count the mask
         Sp = e.shape[1]
         tok = mask.sum(1)
-        assert Sp == int((tok + exp_lens - 1).max())
+        assert Sp == ids.shape[1] + int(exp_lens.max()) - 1          # pad positions count one each (ps-slm.py:805-809)
         assert torch.equal(m.sum(1).cpu(), tok + exp_lens - 1)
         mm = m.cpu()
         assert bool((mm[:, 1:] >= mm[:, :-1]).all()), "left padding: mask must be non-decreasing"

@@ -71,6 +71,32 @@ def test_linear_silu_backward(dev, D, H, B, T):
     assert _rel(y2, l2(torch.nn.functional.silu(l1(norm(x)))).detach()) < 1e-2
 
 
+@pytest.mark.parametrize("kind", ["linear", "simple_linear"])
+def test_other_projectors_backward(dev, kind):
+    import ps_slm_b200.projector as P
+    torch.manual_seed(3)
+    D, H, k, B, T = 40, 72, 2, 3, 21
+    cls = P.EncoderProjectorConcat if kind == "linear" else P.EncoderProjectorLinear
+    m = cls(_cfg(D, H, k))
+    sd = {n: v.clone() for n, v in m.state_dict().items()}
+    x = torch.randn(B, T, D, requires_grad=True)
+    if kind == "linear":
+        y_ref = O.projector_concat(x, k, sd["linear1.weight"].requires_grad_(), sd["linear1.bias"].requires_grad_(),
+                                   sd["linear2.weight"].requires_grad_(), sd["linear2.bias"].requires_grad_())
+    else:
+        y_ref = O.projector_linear(x, k, sd["map.weight"].requires_grad_(), sd["map.bias"].requires_grad_())
+    gy = torch.randn_like(y_ref)
+    (y_ref * gy).sum().backward()
+    m = m.to(dev).train()
+    xd = x.detach().to(dev).requires_grad_(True)
+    y = m(xd)
+    assert y.shape == y_ref.shape and _rel(y.detach().cpu(), y_ref.detach()) < 1e-2
+    (y * gy.to(dev)).sum().backward()
+    for name, p in m.named_parameters():
+        assert _rel(p.grad.cpu(), sd[name].grad) < 2e-2, name
+    assert _rel(xd.grad.cpu(), x.grad) < 2e-2
+
+
 def test_splice_backward(dev):
     import ps_slm_b200.bridge as bridge
     torch.manual_seed(2)
