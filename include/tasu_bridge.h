@@ -107,18 +107,21 @@ int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, cons
  * only where PSD keeps them.  Layout: row r < N_out = FIRST frame of packed candidate r (so the GEMM writes
  * single-frame candidates — the majority — straight into their pooled row), rows >= N_out = the extra frames
  * of multi-frame runs in candidate order.  pk_len [N_out] = run length, tail_src [N_out] = compact row of a
- * candidate's second frame.  With row_sumexp2 given, LayerNorm statistics of the single-frame rows are
+ * candidate's second frame, multi_rows[0, *multi_count) = the packed rows with more than one frame (work list of
+ * tasu_pool_tail, unordered).  With row_sumexp2 given, LayerNorm statistics of the single-frame rows are
  * emitted (mean = 1/V, rstd from sum p^2); multi-frame rows get theirs from tasu_pool_tail. */
 int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K, int V,
                           const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
                           const int32_t* row_off, const int32_t* frame_off, const float* row_max,
                           const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
                           void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
-                          int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+                          int32_t* tail_src, int32_t* multi_rows /*[N_out] or NULL*/, int32_t* multi_count /*[1]*/,
+                          float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 /* In-place mean over the frames of every multi-frame candidate of the compact probability matrix
  * (ps-slm.py:286): probs[r] = (probs[r] + sum of its tail rows) / n, plus LayerNorm statistics. */
 int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
-                   const int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+                   const int32_t* tail_src, const int32_t* multi_rows, const int32_t* multi_count,
+                   float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,

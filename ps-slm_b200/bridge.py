@@ -276,13 +276,13 @@ class TasuBridge:
                 # compact matrix is the first frame of packed candidate r, so single-frame candidates (the majority)
                 # are final as the GEMM writes them; only multi-frame runs are averaged afterwards, in place.
                 with self._stage("gather_kept_rows"):
-                    xg, g_max, g_inv, pk_len, tail_src, mean, rstd = ops.gather_kept_rows(
+                    xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
                         x2, B, T, self.N_PREFIX, Denc, V, plan, st, n_frames, n_out, self.ln_eps)
                 pooled = torch.empty(_cap(n_frames), ldk, dtype=torch.bfloat16, device=dev)[:n_frames]
                 with self._stage("ctc_softmax_gemm"):
                     ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
                 with self._stage("pool_tail"):
-                    ops.pool_tail(pooled, V, n_out, pk_len, tail_src, mean, rstd, self.ln_eps)
+                    ops.pool_tail(pooled, V, n_out, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
             # (a5) projector
             audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                         stage=self._stage)

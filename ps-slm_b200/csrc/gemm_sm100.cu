@@ -374,8 +374,10 @@ struct StatsParams {
 };
 
 constexpr int kStatsSmemBytes = kStages * kStageBytes + 2 * BN * 4 + 128;
+constexpr int kStatsThreads = 384;                   // warps 0-3 control, warps 4-11 epilogue
+constexpr int kStatsEpiThreads = 256;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kStatsThreads, 1)
 ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const StatsParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -396,7 +398,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kStatsEpiThreads); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -456,25 +458,27 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;
-        const int et = threadIdx.x - (kThreads - kEpiThreads);
+        // 8 epilogue warps: warp pair (q, q+4) shares TMEM lane quadrant q and splits the 256 columns in halves,
+        // so the per-element softmax math keeps up with the tensor pipe (K is only 512 deep)
+        const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128;                          // 0..255
         constexpr float kL2e = 1.4426950408889634f;
         int acc = 0; uint32_t acc_phase = 0;
         int bbuf = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const int m_tile = item / p.splits, split = item % p.splits;
-            const int row = m_tile * BM + et;
+            const int row = m_tile * BM + ew * 32 + lane;
             const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
             float rm = -INFINITY, rs = 0.f, rs2 = 0.f, xb = 0.f;
             int best = 0x7fffffff;
             for (int nt = nb; nt < ne; ++nt) {
                 const int n0 = nt * BN;
                 float* sb = s_bias + bbuf * BN;
-                for (int c = et; c < BN; c += kEpiThreads) {
-                    const int col = n0 + c;                       // -inf masks the columns beyond the vocabulary
-                    sb[c] = col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
+                {
+                    const int col = n0 + et;                      // -inf masks the columns beyond the vocabulary
+                    sb[et] = col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
                 }
-                asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(kStatsEpiThreads) : "memory");
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
@@ -521,14 +525,15 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 };
 
                 uint32_t va[32], vb[32];
-                tmem_ld32(t_row, va);
+                const int sub0 = half * (BN / 64), sub1 = sub0 + BN / 64;      // this warp's 4 slabs
+                tmem_ld32(t_row + (uint32_t)(sub0 * 32), va);
 #pragma unroll 1
-                for (int sub = 0; sub < BN / 32; sub += 2) {
+                for (int sub = sub0; sub < sub1; sub += 2) {
                     tmem_ld_wait(va);
                     tmem_ld32(t_row + (uint32_t)((sub + 1) * 32), vb);
                     process(va, sub);
                     tmem_ld_wait(vb);
-                    if (sub + 2 < BN / 32) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
+                    if (sub + 2 < sub1) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
                     else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
                     process(vb, sub + 1);
                 }
@@ -536,12 +541,14 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 bbuf ^= 1;
             }
             if (row < p.M) {
-                const int64_t o = (int64_t)split * p.M + row;
+                const int64_t o = (int64_t)(split * 2 + half) * p.M + row;     // ascending column order of the partials
                 p.part_max[o] = rm;
                 p.part_sum[o] = rs;
                 p.part_sum2[o] = rs2;
                 p.part_arg[o] = best;
-                if (p.blank >= nb * BN && p.blank < ne * BN) p.xb_raw[row] = xb;
+                // the blank column lives in exactly one (tile, half): that thread publishes its logit
+                const int bt = p.blank / BN, bh = (p.blank % BN) / (BN / 2);
+                if (bt >= nb && bt < ne && bh == half) p.xb_raw[row] = xb;
             }
         }
     }
@@ -563,12 +570,13 @@ ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __r
     const int b = (int)(i / T), t = (int)(i % T);
     const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
     float m = -INFINITY; int a = 0x7fffffff;
-    for (int s = 0; s < p.splits; ++s) {
+    const int parts = 2 * p.splits;                                        // (split, column half), ascending columns
+    for (int s = 0; s < parts; ++s) {
         const float pm = p.part_max[(int64_t)s * p.M + r];
-        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower split = lower index
+        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
     }
     float sum = 0.f, sum2 = 0.f;
-    for (int s = 0; s < p.splits; ++s) {
+    for (int s = 0; s < parts; ++s) {
         const float f = exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
         sum += p.part_sum[(int64_t)s * p.M + r] * f;
         sum2 += p.part_sum2[(int64_t)s * p.M + r] * f * f;
@@ -745,7 +753,7 @@ extern "C" int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B,
 
 static void pick_splits(int m_tiles, int n_tiles, int grid, int* splits, int* nt_per) {
     double best_eff = -1.0; int best_s = 1, best_per = n_tiles;
-    for (int s = 1; s <= 16 && s <= n_tiles; ++s) {
+    for (int s = 1; s <= 8 && s <= n_tiles; ++s) {
         const int per = (n_tiles + s - 1) / s;
         const int eff_s = (n_tiles + per - 1) / per;          // splits actually used with this tile count
         const long items = (long)m_tiles * eff_s;
@@ -800,7 +808,7 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
         attr_err = cudaFuncSetAttribute(ctc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytes);
     });
     TASU_CHECK_CUDA(attr_err);
-    ctc_stats_kernel<<<grid, kThreads, kStatsSmemBytes, st>>>(ma, mb, p);
+    ctc_stats_kernel<<<grid, kStatsThreads, kStatsSmemBytes, st>>>(ma, mb, p);
     TASU_CHECK_LAUNCH();
     const int64_t frames = (int64_t)B * T;
     ctc_stats_combine_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max, row_sumexp, row_sumexp2);

@@ -108,6 +108,7 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
                         const float* __restrict__ row_sumexp, const float* __restrict__ row_sumexp2,
                         int64_t max_rows, __nv_bfloat16* __restrict__ xg, int64_t ldg, float* __restrict__ g_max,
                         float* __restrict__ g_inv, int32_t* __restrict__ pk_len, int32_t* __restrict__ tail_src,
+                        int32_t* __restrict__ multi_rows, int32_t* __restrict__ multi_count,
                         float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
     const int lane = threadIdx.x & 31;
     const int n_out = row_off[B];
@@ -121,7 +122,11 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
         const int t0 = seg_start[pj], n = seg_len[pj];
         // extra frames of earlier candidates: (kept frames before) - (kept candidates before)
         const int tail0 = n_out + (frame_off[b] - row_off[b]) + (seg_foff[pj] - j);
-        if (lane == 0) { pk_len[r] = n; tail_src[r] = tail0; }
+        if (lane == 0) {
+            pk_len[r] = n;
+            tail_src[r] = tail0;
+            if (n > 1 && multi_rows != nullptr) multi_rows[atomicAdd(multi_count, 1)] = r;   // work list of pool_tail
+        }
         for (int f = 0; f < n; ++f) {
             const int64_t drow = f == 0 ? r : (int64_t)tail0 + f - 1;
             if (drow >= max_rows) break;
@@ -152,12 +157,16 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
     }
 }
 
-// multi-frame candidates only: probs[r] = mean over its frames, in place; LayerNorm statistics of the result
+// multi-frame candidates only: probs[r] = mean over its frames, in place; LayerNorm statistics of the result.
+// Work list = multi_rows[0, *multi_count) (any order) or, without it, every row with pk_len > 1.
 __global__ void __launch_bounds__(256)
 pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n_out, const int32_t* __restrict__ pk_len,
-                 const int32_t* __restrict__ tail_src, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
+                 const int32_t* __restrict__ tail_src, const int32_t* __restrict__ multi_rows,
+                 const int32_t* __restrict__ multi_count, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
     __shared__ float red[8];
-    for (int64_t r = blockIdx.x; r < n_out; r += gridDim.x) {
+    const int64_t n_items = multi_rows != nullptr ? (int64_t)*multi_count : n_out;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int64_t r = multi_rows != nullptr ? (int64_t)multi_rows[it] : it;
         const int n = pk_len[r];
         if (n <= 1) continue;                                  // CTA-uniform
         __nv_bfloat16* row = probs + r * ld;
@@ -165,19 +174,52 @@ pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n
         const float inv = 1.f / (float)n;
         float acc_q = 0.f;
         const int nchunk = D / 8;
-        for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
-            float v[8];
-            unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(row) + c), v, __nv_bfloat16());
-            for (int f = 1; f < n; ++f) {
-                float x[8];
+        const int bd = blockDim.x;
+        for (int c = threadIdx.x; c < nchunk; c += 2 * bd) {
+            const bool two = c + bd < nchunk;
+            // issue every load of both chunks before the first add (runs are 2-3 frames almost always)
+            uint4 h0 = ld_stream_u4(reinterpret_cast<const uint4*>(row) + c), h1 = h0;
+            uint4 a0 = ld_stream_u4(reinterpret_cast<const uint4*>(tail) + c), a1 = a0, b0 = a0, b1 = a0;
+            if (two) { h1 = ld_stream_u4(reinterpret_cast<const uint4*>(row) + c + bd);
+                       a1 = ld_stream_u4(reinterpret_cast<const uint4*>(tail) + c + bd); }
+            if (n > 2) { b0 = ld_stream_u4(reinterpret_cast<const uint4*>(tail + ld) + c);
+                         if (two) b1 = ld_stream_u4(reinterpret_cast<const uint4*>(tail + ld) + c + bd); }
+            float v0[8], v1[8], x[8];
+            unpack16(h0, v0, __nv_bfloat16()); unpack16(h1, v1, __nv_bfloat16());
+            unpack16(a0, x, __nv_bfloat16());
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v0[e] += x[e];
+            unpack16(a1, x, __nv_bfloat16());
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v1[e] += x[e];
+            if (n > 2) {
+                unpack16(b0, x, __nv_bfloat16());
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v0[e] += x[e];
+                unpack16(b1, x, __nv_bfloat16());
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v1[e] += x[e];
+            }
+            for (int f = 3; f < n; ++f) {                      // long runs (rare)
                 unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(tail + (int64_t)(f - 1) * ld) + c), x, __nv_bfloat16());
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += x[e];
+                for (int e = 0; e < 8; ++e) v0[e] += x[e];
+                if (two) {
+                    unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(tail + (int64_t)(f - 1) * ld) + c + bd), x, __nv_bfloat16());
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v1[e] += x[e];
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { v[e] *= inv; acc_q += v[e] * v[e]; }
-            reinterpret_cast<uint4*>(row)[c] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            for (int e = 0; e < 8; ++e) { v0[e] *= inv; acc_q += v0[e] * v0[e]; }
+            reinterpret_cast<uint4*>(row)[c] = make_uint4(pack_bf16x2(v0[0], v0[1]), pack_bf16x2(v0[2], v0[3]),
+                                                         pack_bf16x2(v0[4], v0[5]), pack_bf16x2(v0[6], v0[7]));
+            if (two) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v1[e] *= inv; acc_q += v1[e] * v1[e]; }
+                reinterpret_cast<uint4*>(row)[c + bd] = make_uint4(pack_bf16x2(v1[0], v1[1]), pack_bf16x2(v1[2], v1[3]),
+                                                                  pack_bf16x2(v1[4], v1[5]), pack_bf16x2(v1[6], v1[7]));
+            }
         }
         for (int d = nchunk * 8 + threadIdx.x; d < D; d += blockDim.x) {
             float v = __bfloat162float(row[d]);
@@ -265,8 +307,11 @@ extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int
                                      const int32_t* row_off, const int32_t* frame_off, const float* row_max,
                                      const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
                                      void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
-                                     int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
+                                     int32_t* tail_src, int32_t* multi_rows, int32_t* multi_count, float* ln_mean,
+                                     float* ln_rstd, float ln_eps, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && V > 0 && ldx >= K && ldg >= K, "shape");
+    TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
+    if (multi_count) TASU_CHECK_CUDA(cudaMemsetAsync(multi_count, 0, sizeof(int32_t), (cudaStream_t)stream));
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
     if (B == 0 || max_rows <= 0) return TASU_OK;
     TASU_CHECK_ARG(x_bf16 && seg_start && seg_len && seg_frame_off && row_off && frame_off && row_max && row_sumexp &&
@@ -276,20 +321,23 @@ extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int
     gather_kept_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x_bf16, ldx, B, T, n_prefix, K, V, seg_start, seg_len, seg_frame_off, row_off, frame_off,
         row_max, row_sumexp, row_sumexp2, max_rows, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, pk_len, tail_src,
-        ln_mean, ln_rstd, ln_eps);
+        multi_rows, multi_count, ln_mean, ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
 
 extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
-                              const int32_t* tail_src, float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
+                              const int32_t* tail_src, const int32_t* multi_rows, const int32_t* multi_count,
+                              float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
     TASU_CHECK_ARG(D > 0 && ld >= D && n_out >= 0, "shape");
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
     if (n_out == 0) return TASU_OK;
     TASU_CHECK_ARG(probs_bf16 && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)probs_bf16 % 16 == 0) && (ld % 8 == 0), "16-byte aligned rows");
+    TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
     pool_tail_kernel<<<row_grid(n_out), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
-                                                                         tail_src, ln_mean, ln_rstd, ln_eps);
+                                                                         tail_src, multi_rows, multi_count, ln_mean,
+                                                                         ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

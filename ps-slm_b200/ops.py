@@ -116,6 +116,7 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
     g_inv = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
     pk_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
     tail_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+    multi = torch.empty(max(n_out, 1) + 1, dtype=torch.int32, device=dev)       # [0] = count, [1:] = row list
     mean = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
     rstd = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
     L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K, V,
@@ -123,15 +124,16 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
                                           plan.row_off.data_ptr(), plan.frame_off.data_ptr(), st.row_max.data_ptr(),
                                           st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), n_frames, xg.data_ptr(), ldg,
                                           g_max.data_ptr(), g_inv.data_ptr(), pk_len.data_ptr(), tail_src.data_ptr(),
-                                          mean.data_ptr(), rstd.data_ptr(), float(ln_eps), _stream()),
-            "tasu_gather_kept_rows")
+                                          multi[1:].data_ptr(), multi.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                          float(ln_eps), _stream()), "tasu_gather_kept_rows")
     _count(1)
-    return xg, g_max, g_inv, pk_len, tail_src, mean, rstd
+    return xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd
 
 
 def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tail_src: torch.Tensor,
-              ln_mean: torch.Tensor, ln_rstd: torch.Tensor, ln_eps: float = 1e-5):
+              multi: Optional[torch.Tensor], ln_mean: torch.Tensor, ln_rstd: torch.Tensor, ln_eps: float = 1e-5):
     L.check(L.lib().tasu_pool_tail(probs.data_ptr(), probs.stride(0), D, n_out, pk_len.data_ptr(), tail_src.data_ptr(),
+                                   multi[1:].data_ptr() if multi is not None else None, _ptr(multi),
                                    ln_mean.data_ptr(), ln_rstd.data_ptr(), float(ln_eps), _stream()), "tasu_pool_tail")
     _count(1)
 
