@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: text-only TASU training step on the bridge (no LLM).
+
+    python tools/bench_train.py --steps 10                                  # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 2 tools/bench_train.py  # utterance-sharded, grad all-reduce
+
+Per step and rank: draw the simulator's decisions on the host (reference RNG order,
+ps-slm.py:380-401) → device-built bf16 posterior rows + LayerNorm stats → trainable linear-silu
+projector forward → splice into right-padded prompt+target embeddings → synthetic upstream gradient
+dL/d(inputs_embeds) ~ N(0,1) → splice backward → projector backward (dW2, dh, G on the tensor cores)
+→ bucketed NCCL all-reduce of the 54.5 M projector gradients.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--global-batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    import ps_slm_b200.dist as D
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.sim as sim
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.autograd import SpliceFunction, linear_silu_train_rows
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    V, H = S.V_CTC, S.H_LLM
+    all_ids = S.make_transcripts(args.global_batch, V, seed=1234)
+    mine = D.shard_indices(args.global_batch, rank, world)
+    ids_list = [all_ids[i] for i in mine]
+    input_ids, mask, labels = S.make_prompts(len(mine), seed=rank, left_pad=False, target_lens=[len(i) for i in ids_list])
+    input_ids, mask, labels = input_ids.to(dev), mask.to(dev), labels.to(dev)
+    torch.manual_seed(0)
+    proj = P.EncoderProjectorLinearSiLU(types.SimpleNamespace(encoder_dim=V, llm_dim=H, encoder_projector_ds_rate=1)).to(dev).train()
+    table = S.make_embed_table(dtype=torch.float32, device=dev)
+    params = list(proj.parameters())
+    n_param = sum(p.numel() for p in params)
+
+    def step(i, timers):
+        torch.manual_seed(1000 + i)
+        t0 = time.perf_counter()
+        dec = sim.draw_noise_decisions(ids_list, 0)
+        timers["host_sim"] += time.perf_counter() - t0
+        rows, mean, rstd, lens = sim.build_packed_bf16(dec, V, dev)
+        y = linear_silu_train_rows(proj, rows, mean, rstd, rows.shape[0], torch.float32)
+        sp = ops.splice_rowstat(input_ids, mask, S.SPEECH_ID)
+        ops.splice_plan(sp, lens, 1)
+        hdr = sp.header.cpu()
+        sp.left_padding = int(hdr[1])
+        emb, _, _, _, _ = SpliceFunction.apply(y, sp, int(hdr[0]), table, 1, 0, int(lens.max()), labels, S.PAD_ID, S.IGNORE_ID)
+        g = torch.randn(emb.shape, device=dev, dtype=emb.dtype, generator=gen)
+        for p in params:
+            p.grad = None
+        emb.backward(g)
+        D.allreduce_gradients(params)
+        return rows.shape[0]
+
+    gen = torch.Generator(device=dev).manual_seed(7)
+    timers = {"host_sim": 0.0}
+    for i in range(args.warmup):
+        step(i, timers)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    timers = {"host_sim": 0.0}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_rows = 0
+    for i in range(args.steps):
+        n_rows = step(args.warmup + i, timers)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        nr = torch.tensor([n_rows], dtype=torch.int64, device=dev)
+        dist.all_reduce(nr)
+        n_rows_global = int(nr)
+    else:
+        n_rows_global = n_rows
+    if rank == 0:
+        per_step = ms / args.steps
+        flops = n_rows_global * (3 * 2.0 * V * 2048 + 3 * 2.0 * 2048 * H)     # fwd + dgrad-free wgrad (G) + dW2/dh
+        print(json.dumps({
+            "workload": "configs[2] text-only training step (simulated posteriors, projector fwd+bwd, grad all-reduce)",
+            "global_batch": args.global_batch, "n_gpus": world, "token_rows_per_step": n_rows_global,
+            "ms_per_step": per_step, "token_rows_per_s": n_rows_global / (per_step / 1e3),
+            "gemm_tflops": flops / (per_step / 1e3) / 1e12,
+            "host_sim_ms_per_step": 1e3 * timers["host_sim"] / args.steps,
+            "allreduce_bytes_per_rank": n_param * 4 if world > 1 else 0, "trainable_params": n_param}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
