@@ -36,7 +36,9 @@ constexpr int kBBytes = BN * BK * 2;                 // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
 constexpr int kStagingBytes = BM * 128;              // one 128-byte-wide column chunk of the C tile
 constexpr int kAuxBytes = 2 * BN * 4;                // per-tile bias / colsum slices
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + kAuxBytes + 128 /*barriers*/;
+constexpr int gemm_smem_bytes(int stages, int groups) {
+    return stages * kStageBytes + 2 * groups * kStagingBytes + groups * kAuxBytes + 128 /*barriers*/;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,16 +150,18 @@ struct Params {
 };
 
 // kOutBf16: C is bf16 (64 columns per 128-byte staging row) else fp32 (32 columns)
-template <bool kOutBf16, int kEpi>
-__global__ void __launch_bounds__(kThreads, 1)
+// kSt smem pipeline stages; kGroups epilogue warp-groups of 4 warps (2 groups interleave the 128-byte column
+// chunks of a tile, each with its own staging pair and TMA-store thread: for shallow-K, store-heavy shapes)
+template <bool kOutBf16, int kEpi, int kSt, int kGroups>
+__global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];          // 128B-swizzle atoms need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();               // no static shared memory in this kernel → offset 0
-    uint8_t* staging = smem + kStages * kStageBytes;
-    float* s_bias = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
-    float* s_colsum = s_bias + BN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes + kAuxBytes);
+    constexpr int kStages = kSt;
+    uint8_t* staging = smem + kStages * kStageBytes;                               // [kGroups][2] x 16 KB
+    float* s_aux = reinterpret_cast<float*>(staging + 2 * kGroups * kStagingBytes);  // [kGroups][bias, colsum][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kGroups * kStagingBytes + kGroups * kAuxBytes);
     uint64_t* full_bar = bars;                           // [kStages]
     uint64_t* empty_bar = bars + kStages;                // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;            // [kAccStages]
@@ -174,7 +178,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * kGroups); }
         fence_barrier_init();
     }
     if (warp == 2) {   // whole warp allocates all 512 TMEM columns (1 CTA per SM)
@@ -233,12 +237,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;                                   // TMEM lanes [32*ew, 32*ew+32)
-        const int et = threadIdx.x - (kThreads - kEpiThreads);     // 0..127 = row of the tile
+        const int grp = (warp - 4) >> 2;                           // epilogue group: chunks grp, grp+kGroups, ...
+        const int ew = (warp - 4) & 3;                             // TMEM lanes [32*ew, 32*ew+32)
+        const int et = ew * 32 + lane;                             // 0..127 = row of the tile
+        float* s_bias = s_aux + grp * (2 * BN);
+        float* s_colsum = s_bias + BN;
+        uint8_t* gstaging = staging + grp * 2 * kStagingBytes;
+        const int bar_id = 1 + grp;
         constexpr int kSubs = BN / 32;                             // 32-column TMEM loads per tile
         constexpr int kSubsPerChunk = kOutBf16 ? 2 : 1;            // one staging chunk = 128 bytes of C per row
         constexpr int kColsPerChunk = 32 * kSubsPerChunk;
-        const uint32_t stg_u32 = smem_u32(staging);
+        const uint32_t stg_u32 = smem_u32(gstaging);
         const int sw = et & 7;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
@@ -248,7 +257,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
             if (kEpi != TASU_EPI_NONE) {
-                for (int c = et; c < BN; c += kEpiThreads) {
+                for (int c = et; c < BN; c += kEpiThreads) {   // each group stages its own copy (own barrier)
                     const int col = n0 + c;
                     s_bias[c] = col < p.N ? __ldg(p.bias + col) : 0.f;
                     if (kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) s_colsum[c] = col < p.N ? __ldg(p.colsum + col) : 0.f;
@@ -266,12 +275,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // one 32-column slab: epilogue math in registers, swizzled st.shared, TMA store per chunk
             auto process = [&](uint32_t (&v)[32], int sub) {
                 const int ch = sub / kSubsPerChunk, h = sub % kSubsPerChunk;
-                if (ch >= n_chunks) return;                            // fully clipped (uniform over the 4 warps)
+                if (ch >= n_chunks) return;                            // fully clipped (uniform over the group's 4 warps)
                 const uint32_t srow = stg_u32 + (uint32_t)(sbuf * kStagingBytes + et * 128);
                 if (h == 0) {
                     // the TMA store that last read this staging buffer must have finished reading it
                     if (et == 0) tma_store_wait_read<1>();
-                    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(kEpiThreads) : "memory");
                 }
                 float f[32];
                 const float4* b4 = reinterpret_cast<const float4*>(s_bias + sub * 32);
@@ -321,30 +330,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 if (h == kSubsPerChunk - 1) {
                     fence_proxy_async_smem();
-                    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(kEpiThreads) : "memory");
                     if (et == 0) {
-                        tma_store_2d(&tmap_c, staging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
                         tma_store_commit();
                     }
                     sbuf ^= 1;
                 }
             };
 
+            // slabs of this group: chunks grp, grp + kGroups, ... (kSubsPerChunk slabs each), software-pipelined
+            constexpr int kGroupSubs = kSubs / kGroups;
+            auto sub_of = [&](int it) { return ((it / kSubsPerChunk) * kGroups + grp) * kSubsPerChunk + it % kSubsPerChunk; };
             uint32_t va[32], vb[32];
-            tmem_ld32(t_row, va);
+            tmem_ld32(t_row + (uint32_t)(sub_of(0) * 32), va);
 #pragma unroll 1
-            for (int sub = 0; sub < kSubs; sub += 2) {
+            for (int it = 0; it < kGroupSubs; it += 2) {
                 tmem_ld_wait(va);
-                tmem_ld32(t_row + (uint32_t)((sub + 1) * 32), vb);        // in flight while `va` is processed
-                process(va, sub);
+                tmem_ld32(t_row + (uint32_t)(sub_of(it + 1) * 32), vb);   // in flight while `va` is processed
+                process(va, sub_of(it));
                 tmem_ld_wait(vb);
-                if (sub + 2 < kSubs) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
+                if (it + 2 < kGroupSubs) tmem_ld32(t_row + (uint32_t)(sub_of(it + 2) * 32), va);
                 else {
-                    // every tcgen05.ld of this accumulator has completed → hand it back to the MMA warp early
+                    // every tcgen05.ld of this thread for this accumulator has completed → hand it back early
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[acc]);
                 }
-                process(vb, sub + 1);
+                process(vb, sub_of(it + 1));
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
@@ -670,36 +682,47 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
 }
 
 
-template <bool kOutBf16, int kEpi>
+template <bool kOutBf16, int kEpi, int kSt, int kGroups>
 static int launch_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
                       const Params& p) {
+    constexpr int smem = gemm_smem_bytes(kSt, kGroups);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kOutBf16, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kOutBf16, kEpi, kSt, kGroups>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
     TASU_CHECK_CUDA(attr_err);
-    gemm_bf16_tn_kernel<kOutBf16, kEpi><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, p);
+    gemm_bf16_tn_kernel<kOutBf16, kEpi, kSt, kGroups><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p);
     return TASU_OK;
 }
 
+// deep-K shapes: 4 smem stages, one epilogue group; shallow-K (store-heavy) shapes: 3 stages, two epilogue groups
+template <bool kOutBf16, int kEpi>
+static int launch_cfg(bool shallow_k, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+                      const CUtensorMap& mc, const Params& p) {
+    return shallow_k ? launch_one<kOutBf16, kEpi, 3, 2>(grid, st, ma, mb, mc, p)
+                     : launch_one<kOutBf16, kEpi, 4, 1>(grid, st, ma, mb, mc, p);
+}
+
 template <bool kOutBf16>
-static int launch_epi(int epilogue, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+static int launch_epi(int epilogue, bool sk, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                       const CUtensorMap& mc, const Params& p) {
     switch (epilogue) {
-        case TASU_EPI_NONE: return launch_one<kOutBf16, TASU_EPI_NONE>(grid, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS: return launch_one<kOutBf16, TASU_EPI_BIAS>(grid, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_SILU: return launch_one<kOutBf16, TASU_EPI_BIAS_SILU>(grid, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_RELU: return launch_one<kOutBf16, TASU_EPI_BIAS_RELU>(grid, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD_SILU: return launch_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD: return launch_one<kOutBf16, TASU_EPI_LNFOLD>(grid, st, ma, mb, mc, p);
-        default: return launch_one<kOutBf16, TASU_EPI_SOFTMAX>(grid, st, ma, mb, mc, p);
+        case TASU_EPI_NONE: return launch_cfg<kOutBf16, TASU_EPI_NONE>(sk, grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS: return launch_cfg<kOutBf16, TASU_EPI_BIAS>(sk, grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_SILU: return launch_cfg<kOutBf16, TASU_EPI_BIAS_SILU>(sk, grid, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_RELU: return launch_cfg<kOutBf16, TASU_EPI_BIAS_RELU>(sk, grid, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD_SILU: return launch_cfg<kOutBf16, TASU_EPI_LNFOLD_SILU>(sk, grid, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD: return launch_cfg<kOutBf16, TASU_EPI_LNFOLD>(sk, grid, st, ma, mb, mc, p);
+        default: return launch_cfg<kOutBf16, TASU_EPI_SOFTMAX>(sk, grid, st, ma, mb, mc, p);
     }
 }
 
-static int launch_dispatch(bool out_bf16, int epilogue, int grid, cudaStream_t st, const CUtensorMap& ma,
+static int launch_dispatch(bool out_bf16, int epilogue, bool shallow_k, int grid, cudaStream_t st, const CUtensorMap& ma,
                            const CUtensorMap& mb, const CUtensorMap& mc, const Params& p) {
-    return out_bf16 ? launch_epi<true>(epilogue, grid, st, ma, mb, mc, p) : launch_epi<false>(epilogue, grid, st, ma, mb, mc, p);
+    return out_bf16 ? launch_epi<true>(epilogue, shallow_k, grid, st, ma, mb, mc, p)
+                    : launch_epi<false>(epilogue, shallow_k, grid, st, ma, mb, mc, p);
 }
 
 }  // namespace gemm
@@ -729,7 +752,7 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     int grid = sm_count();
     if (grid > tiles) grid = tiles;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_dispatch(c_dtype == TASU_BF16, epilogue, grid, st, ma, mb, mc, p);
+    rc = launch_dispatch(c_dtype == TASU_BF16, epilogue, K <= 1024, grid, st, ma, mb, mc, p);
     if (rc) return rc;
     TASU_CHECK_LAUNCH();
     return TASU_OK;
