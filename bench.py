@@ -320,7 +320,12 @@ def b200_arm(args):
             kernels[name] = {"ms": avg[name]}
     dominant = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms"])
     roof = dict(kernels[dominant])
-    roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["source"] + " (MEASURED_PEAKS.json, sustained bf16 / copy HBM)"})
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dominant, {}).get("bytes_per_launch")
+    roof.update({"kernel": dominant, "traffic": traffic, "algorithmic_per_launch": algo[dominant][1], "peak_source": pk["source"] + " (MEASURED_PEAKS.json, sustained bf16 / copy HBM)"})
     roof.pop("ms", None)
 
     cpu = None

@@ -60,6 +60,24 @@ if os.path.isfile(rep):
                 f.write(f"| {w} | {r[i]} | {units[i]} |\n")
             f.write("\n")
 
+    # dram traffic per launch of every captured kernel → profiles/traffic.json (read by bench.py's roofline.traffic)
+    stage_of = [("ctc_stats_kernel", "ctc_head_stats"), ("gemm_bf16_tn_kernel<1, 6", "ctc_softmax_gemm"),
+                ("gemm_bf16_tn_kernel<1, 4", "projector_gemm1"), ("gemm_bf16_tn_kernel<1, 1", "projector_gemm2"),
+                ("gemm_bf16_tn_kernel<0, 1", "ctc_lo_gemm"), ("pool_tail_kernel", "pool_tail"),
+                ("splice_scatter_kernel", "splice_scatter"), ("frame_stats_kernel", "frame_stats"),
+                ("meanpool_kernel", "softmax_meanpool"), ("gather_kept_rows_kernel", "gather_kept_rows")]
+    tpath = os.path.join(out_dir, "traffic.json")
+    traffic = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    for r in rd[2:]:
+        for pat, stage in stage_of:
+            if pat in r[ik]:
+                traffic[stage] = {"bytes_per_launch": float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1),
+                                  "source": f"ncu --set full, {tag} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+    with open(tpath, "w") as f:
+        json.dump(traffic, f, indent=1)
+
 b = os.path.join(go, f"bench_{tag}.json")
 if os.path.isfile(b):
     for src, dst in ((b, f"{tag}_bench.json"), (os.path.join(go, f"bench_ref_{tag}.json"), f"{tag}_bench_reference.json")):
