@@ -297,6 +297,56 @@ class TasuBridge:
                             "kept_frames": int(hdr[L.CH_KEPT_FRAMES])}
         return emb, mask, out_labels, pos, plan.new_lens
 
+    # ------------------------------------------------------------------ two-phase API (cross-rank packing)
+    @torch.no_grad()
+    def compress_project(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor):
+        """Steps 1b-3 only: → (audio rows packed ``[sum M_b, H]``, ``new_lens [B]`` int64, ``max_b M_b``).
+        Used when compressed sequences are exchanged between ranks before the splice (dist.all_gather_packed)."""
+        B, T4, Denc = raw_encoder_out.shape
+        T = T4 - self.N_PREFIX
+        V = self.w_ctc.shape[0]
+        dev = raw_encoder_out.device
+        w_ctc, b_ctc = self._ctc_weights()
+        w1g, colsum, dbias, w2, b2 = self.projector.folded_weights()
+        out_dtype = self.embed_table.dtype
+        x2 = raw_encoder_out.reshape(B * T4, Denc)
+        if x2.dtype != torch.bfloat16:
+            x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+        lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
+        header = self._header_slot()
+        st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
+        plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+        n_out, max_len, n_frames = int(header[L.CH_N_OUT]), int(header[L.CH_MAX_LEN]), int(header[L.CH_KEPT_FRAMES])
+        if n_out == 0:
+            return torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev), plan.new_lens, 0
+        xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
+            x2, B, T, self.N_PREFIX, Denc, V, plan, st, n_frames, n_out, self.ln_eps)
+        ldk = ops.pad_to(V)
+        pooled = torch.empty(_cap(n_frames), ldk, dtype=torch.bfloat16, device=dev)[:n_frames]
+        ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
+        ops.pool_tail(pooled, V, n_out, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
+        audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype)
+        return audio, plan.new_lens, max_len
+
+    @torch.no_grad()
+    def splice(self, audio_rows: torch.Tensor, new_lens: torch.Tensor, input_ids: torch.Tensor,
+               attention_mask: torch.Tensor, labels: Optional[torch.Tensor] = None, want_ids: bool = False):
+        """Step 4 on packed audio rows (any origin: this rank's or gathered from all ranks)."""
+        sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
+        header = self._header_slot()
+        ops.splice_plan(sp, new_lens, self.projector.k, header=header[L.CH_WORDS:])
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+        shdr = header[L.CH_WORDS:].clone()
+        _raise_splice_errors(shdr, attention_mask, new_lens.numel())
+        return ops.splice_scatter(sp, int(shdr[L.SH_SPLICED_LEN]), self.embed_table, 1, audio_rows, 0, 0, labels,
+                                  self.pad_id, self.ignore_id, want_ids=want_ids,
+                                  left_padding=int(shdr[L.SH_LEFT_PADDING]))
+
 
 class HostPipeline:
     """End-to-end entry for HOST buffers (the call a serving loop makes): pinned host batches in,

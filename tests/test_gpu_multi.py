@@ -1,0 +1,68 @@
+"""Multi-GPU (NCCL) test of BASELINE configs[3]: a mixed multitask batch is utterance-sharded over the
+ranks, every rank compresses + projects its shard, lengths and packed rows are all-gathered, and the
+globally packed splice must equal the single-GPU result bit for bit.  Needs >= 2 GPUs (skipped otherwise;
+the host-side logic is covered on CPU by tests/test_dist_gloo.py)."""
+import os
+import socket
+import types
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import ps_slm_b200.dist as D
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    B, T = 10, 90
+    w, b = S.make_ctc_head()
+    torch.manual_seed(0)
+    proj = P.EncoderProjectorLinearSiLU(types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=5, ragged=True)
+    tasks = ["ASR", "EN2ZH", "EN2DE", "QA", "SLU_scenario"]
+    ids, mask, _ = S.make_prompts(B, seed=5, tasks=tasks, left_pad=True)
+    mine = D.shard_indices(B, rank, world)
+    audio, lens, _ = br.compress_project(raw[mine].to(dev), raw_lens[mine].to(dev))
+    rows_g, lens_g = D.all_gather_packed(audio, lens)
+    out = br.splice(rows_g, lens_g, ids.to(dev), mask.to(dev))
+    # single-GPU reference on the same device
+    ref = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    ok = (torch.equal(lens_g, ref[4]) and torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+          and torch.equal(out[3], ref[3]))
+    valid = int(out[1].sum())
+    q.put((rank, bool(ok), valid / out[1].numel()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_cross_rank_packing_matches_single_gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[:2] for r in res] == [(0, True), (1, True)], res
+    assert 0.3 < res[0][2] <= 1.0          # packing efficiency (valid / padded tokens) is reported
