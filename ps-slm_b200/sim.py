@@ -38,6 +38,39 @@ def draw_noise_decisions(ids_list: Sequence[Sequence[int]], blank_id: int = 0, d
     return out
 
 
+def draw_noise_descriptors(ids_list: Sequence[Sequence[int]], vocab_size: int, blank_id: int = 0,
+                           drop_prob: float = 0.05, insert_prob: float = 0.0, smooth_low: float = 0.0,
+                           smooth_high: float = 0.1):
+    """Same random stream as ``draw_noise_decisions`` but straight to flat numpy row descriptors
+    ``(tok int32, hot f32, base f32, lens)`` without per-token Python objects (the host side of a training step
+    must not dominate it).  Falls back to the list algorithm only for utterances that get inserts."""
+    toks, hots, bases, lens = [], [], [], []
+    for ids in ids_list:
+        alpha = torch.empty(()).uniform_(smooth_low, smooth_high).item()
+        keep = (torch.rand(len(ids)) > drop_prob).numpy()
+        tok = np.asarray(ids, dtype=np.int32)[keep]
+        h, c = soft_row_values(alpha, vocab_size)
+        n_insert = int(tok.shape[0] * insert_prob)
+        if n_insert == 0:
+            hot = np.full(tok.shape[0], h, dtype=np.float32)
+            base = np.full(tok.shape[0], c, dtype=np.float32)
+        else:
+            rows = [(int(v), False) for v in tok]
+            for _ in range(n_insert):
+                pos = torch.randint(0, len(rows) + 1, (1,)).item()
+                if torch.rand(1) < 0.5 and len(rows) > 0:
+                    rows.insert(pos, rows[pos - 1] if pos > 0 else rows[0])
+                else:
+                    rows.insert(pos, (blank_id, True))
+            tok = np.asarray([r[0] for r in rows], dtype=np.int32)
+            hard = np.asarray([r[1] for r in rows], dtype=bool)
+            hot = np.where(hard, np.float32(1.0), h).astype(np.float32)
+            base = np.where(hard, np.float32(0.0), c).astype(np.float32)
+        toks.append(tok); hots.append(hot); bases.append(base); lens.append(int(tok.shape[0]))
+    cat = (lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt))
+    return cat(toks, np.int32), cat(hots, np.float32), cat(bases, np.float32), lens
+
+
 def soft_row_values(alpha: float, vocab_size: int) -> Tuple[np.float32, np.float32]:
     """fp32 (hot, base) of ``(1 - alpha) * onehot + alpha / V`` as torch evaluates it (:385)."""
     a = np.float32(1.0 - alpha)
@@ -81,8 +114,12 @@ def build_dense(decisions, vocab_size: int, device, dtype=torch.float32):
 
 def build_packed_bf16(decisions, vocab_size: int, device, ln_eps: float = 1e-5):
     """Packed bf16 rows [sum L_b, pad64(V)] + LayerNorm stats + lens: the A operand of the folded
-    projector GEMM for the text-only training step (never materialises the fp32 posterior)."""
-    tok, hot, base, lens, _ = _descriptors(decisions, vocab_size, False)
+    projector GEMM for the text-only training step (never materialises the fp32 posterior).
+    ``decisions`` is either the list of ``draw_noise_decisions`` or the tuple of ``draw_noise_descriptors``."""
+    if isinstance(decisions, tuple):
+        tok, hot, base, lens = decisions
+    else:
+        tok, hot, base, lens, _ = _descriptors(decisions, vocab_size, False)
     n = int(tok.shape[0])
     ld = ops.pad_to(vocab_size)
     rows = torch.empty(n, ld, dtype=torch.bfloat16, device=device)

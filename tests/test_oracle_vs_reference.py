@@ -58,6 +58,15 @@ def test_sim_matches_reference_bitwise():
     d2 = sim.draw_noise_decisions(ids, 0, insert_prob=0.5)
     assert d1 == d2
     assert O.sim_row_values(0.0731, V) == sim.soft_row_values(0.0731, V)
+    # the flat-descriptor fast path consumes the identical stream and yields identical rows
+    import numpy as np
+    for ip in (0.0, 0.5):
+        torch.manual_seed(11)
+        dec = sim.draw_noise_decisions(ids, 0, insert_prob=ip)
+        tok, hot, base, lens, _ = sim._descriptors(dec, V, False)
+        torch.manual_seed(11)
+        tok2, hot2, base2, lens2 = sim.draw_noise_descriptors(ids, V, 0, insert_prob=ip)
+        assert lens == lens2 and np.array_equal(tok, tok2) and np.array_equal(hot, hot2) and np.array_equal(base, base2)
 
 
 @pytest.mark.parametrize("seed", range(60))

@@ -57,7 +57,7 @@ def main():
     def step(i, timers):
         torch.manual_seed(1000 + i)
         t0 = time.perf_counter()
-        dec = sim.draw_noise_decisions(ids_list, 0)
+        dec = sim.draw_noise_descriptors(ids_list, V, 0)
         timers["host_sim"] += time.perf_counter() - t0
         rows, mean, rstd, lens = sim.build_packed_bf16(dec, V, dev)
         y = linear_silu_train_rows(proj, rows, mean, rstd, rows.shape[0], torch.float32)
@@ -102,7 +102,7 @@ def main():
         n_rows_global = n_rows
     if rank == 0:
         per_step = ms / args.steps
-        flops = n_rows_global * (3 * 2.0 * V * 2048 + 3 * 2.0 * 2048 * H)     # fwd + dgrad-free wgrad (G) + dW2/dh
+        flops = n_rows_global * (2 * 2.0 * V * 2048 + 3 * 2.0 * 2048 * H)     # GEMM-1 fwd + G (no dLN GEMM) + GEMM-2 fwd, dW2, dh
         print(json.dumps({
             "workload": "configs[2] text-only training step (simulated posteriors, projector fwd+bwd, grad all-reduce)",
             "global_batch": args.global_batch, "n_gpus": world, "token_rows_per_step": n_rows_global,
