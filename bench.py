@@ -126,7 +126,7 @@ def reference_arm(args):
                          "sample": f"{sample_b} utterances x {T} frames per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,13 +356,31 @@ def b200_arm(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything any library prints (NCCL's version banner goes to fd 1) is routed to stderr; the ONE JSON
+    line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse()
+    protect_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:

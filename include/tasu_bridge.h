@@ -233,6 +233,15 @@ int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float*
                                   int Hb, int V,
                                   float* dw1, int64_t dw1_stride, float* dgamma, float* dbeta, void* stream);
 
+/* fp32-accurate mode on the bf16 tensor cores (the reference computes the projector in fp32,
+ * conf/ds_config.json:12-14): x = h1+h2+h3 (three bf16 terms); with A' = [h1|h1|h2|h1|h2|h3] (pattern 0) and
+ * B' = [h1|h2|h1|h3|h2|h1] (pattern 1), blocks of pad64(K), ONE tasu_gemm_bf16_tn over K' = 6*pad64(K) gives the
+ * fp32 product to ~1e-6.  col_scale (optional, [K]) multiplies columns first (LayerNorm gamma fold); optional
+ * LayerNorm statistics (activations) / row sums (folded weights: the colsum of TASU_EPI_LNFOLD*). */
+int tasu_split_bf16x3(const void* src, int src_dtype, int64_t rows, int K, int64_t src_stride,
+                      const float* col_scale, int pattern, void* dst_bf16, int64_t dst_stride,
+                      float* ln_mean, float* ln_rstd, float ln_eps, float* row_sum, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.
  *   input_ids [B,S] int64; attention_mask [B,S] uint8/bool (mask_dtype 0) or int64 (1);

@@ -211,3 +211,74 @@ extern "C" int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, c
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// fp32-accurate mode on the bf16 tensor cores: x = h1 + h2 + h3 (three bf16 terms, 24 mantissa bits);
+// A·B ≈ h1h1 + h1h2 + h2h1 + h1h3 + h2h2 + h3h1 is ONE GEMM over a 6x longer K when the operands are laid
+// out as  A' = [h1|h1|h2|h1|h2|h3]  and  B' = [h1|h2|h1|h3|h2|h1]  (blocks of pad64(K), zero padded).
+namespace tasu {
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+split3_kernel(const Ti* __restrict__ src, int64_t rows, int K, int64_t sstride, const float* __restrict__ col_scale,
+              int pattern, __nv_bfloat16* __restrict__ dst, int64_t dstride, int Kp, float* __restrict__ ln_mean,
+              float* __restrict__ ln_rstd, float eps, float* __restrict__ row_sum) {
+    __shared__ float red[8];
+    // block order of (h1,h2,h3) per pattern: A = 0,0,1,0,1,2   B = 0,1,0,2,1,0
+    const int pa[6] = {0, 0, 1, 0, 1, 2}, pb[6] = {0, 1, 0, 2, 1, 0};
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const Ti* s = src + r * sstride;
+        __nv_bfloat16* d = dst + r * dstride;
+        float acc_s = 0.f, acc_q = 0.f;
+        for (int c = threadIdx.x; c < Kp; c += blockDim.x) {
+            float x = 0.f;
+            if (c < K) { x = to_f32(s[c]); if (col_scale) x *= col_scale[c]; }
+            acc_s += x; acc_q += x * x;
+            __nv_bfloat16 h[3];
+            h[0] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(h[0]);
+            h[1] = __float2bfloat16_rn(r1);
+            h[2] = __float2bfloat16_rn(r1 - __bfloat162float(h[1]));
+#pragma unroll
+            for (int b = 0; b < 6; ++b) d[(int64_t)b * Kp + c] = h[pattern == 0 ? pa[b] : pb[b]];
+        }
+        if (ln_mean != nullptr || row_sum != nullptr) {
+            acc_s = block_sum_f(acc_s, red);
+            acc_q = block_sum_f(acc_q, red);
+            if (threadIdx.x == 0) {
+                if (row_sum) row_sum[r] = acc_s;
+                if (ln_mean) {
+                    const float mean = acc_s / (float)K;
+                    float var = acc_q / (float)K - mean * mean;
+                    var = var < 0.f ? 0.f : var;
+                    ln_mean[r] = mean;
+                    ln_rstd[r] = rsqrtf(var + eps);
+                }
+            }
+        }
+    }
+}
+}  // namespace tasu
+
+extern "C" int tasu_split_bf16x3(const void* src, int src_dtype, int64_t rows, int K, int64_t src_stride,
+                                 const float* col_scale, int pattern, void* dst_bf16, int64_t dst_stride,
+                                 float* ln_mean, float* ln_rstd, float ln_eps, float* row_sum, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && K > 0 && src_stride >= K, "shape");
+    TASU_CHECK_ARG(src_dtype == TASU_F32 || src_dtype == TASU_BF16, "src_dtype");
+    TASU_CHECK_ARG(pattern == 0 || pattern == 1, "pattern: 0 = A (activations), 1 = B (weights)");
+    TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
+    const int Kp = (K + 63) / 64 * 64;
+    TASU_CHECK_ARG(dst_stride >= 6 * (int64_t)Kp, "dst_stride must hold 6 blocks of pad64(K)");
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && dst_bf16, "null pointer");
+    int64_t g = (int64_t)tasu::sm_count() * 8;
+    if (g > rows) g = rows;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == TASU_F32)
+        tasu::split3_kernel<float><<<(unsigned)g, 256, 0, st>>>((const float*)src, rows, K, src_stride, col_scale, pattern,
+                                                               (__nv_bfloat16*)dst_bf16, dst_stride, Kp, ln_mean, ln_rstd, ln_eps, row_sum);
+    else
+        tasu::split3_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)src, rows, K, src_stride, col_scale, pattern,
+                                                                       (__nv_bfloat16*)dst_bf16, dst_stride, Kp, ln_mean, ln_rstd, ln_eps, row_sum);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

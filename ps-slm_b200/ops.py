@@ -446,3 +446,23 @@ def linear_silu_wgrad_finish(G: torch.Tensor, w1: torch.Tensor, gamma: torch.Ten
             "tasu_linear_silu_wgrad_finish")
     _count(1)
     return dw1, dgamma, dbeta
+
+
+def split_bf16x3(src: torch.Tensor, pattern: int, col_scale: Optional[torch.Tensor] = None, want_ln: bool = False,
+                 want_rowsum: bool = False, ln_eps: float = 1e-5):
+    """fp32 [rows, K] → bf16 [rows, 6*pad64(K)] three-term split laid out for the A (0) or B (1) side of one long-K GEMM.
+    Returns (dst, K', ln_mean, ln_rstd, row_sum)."""
+    _need_cuda(src, col_scale)
+    if src.shape[1] > 1 and src.stride(1) != 1:
+        src = src.contiguous()
+    rows, K = src.shape
+    Kp = pad_to(K)
+    dst = torch.empty(rows, 6 * Kp, dtype=torch.bfloat16, device=src.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=src.device) if want_ln else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=src.device) if want_ln else None
+    rsum = torch.empty(rows, dtype=torch.float32, device=src.device) if want_rowsum else None
+    L.check(L.lib().tasu_split_bf16x3(src.data_ptr(), _dt(src), rows, K, src.stride(0) if rows > 1 else K, _ptr(col_scale),
+                                      pattern, dst.data_ptr(), 6 * Kp, _ptr(mean), _ptr(rstd), float(ln_eps), _ptr(rsum),
+                                      _stream()), "tasu_split_bf16x3")
+    _count(1)
+    return dst, 6 * Kp, mean, rstd, rsum

@@ -57,6 +57,33 @@ class EncoderProjectorLinearSiLU(nn.Module):
         nn.init.zeros_(self.ffn[2].bias)
         self.k = 1
         self._cache = ProjectorCache()
+        # "bf16" (default): bf16 operands, fp32 accumulation (≤1e-2 of the fp32 reference);
+        # "fp32x3": three-term bf16 split on the same tensor cores, fp32-accurate (~1e-6), 6x the MMA work
+        self.precision = "bf16"
+        self._cache3 = ProjectorCache()
+
+    def _forward_fp32x3(self, x):
+        """fp32-accurate inference path (reference numerics: fp32 LayerNorm/Linear/SiLU/Linear)."""
+        B, T, D = x.shape
+        Hb, H = self.ffn[0].weight.shape[0], self.ffn[2].weight.shape[0]
+        params = [self.norm.weight, self.norm.bias, self.ffn[0].weight, self.ffn[0].bias, self.ffn[2].weight, self.ffn[2].bias]
+
+        def build():
+            with torch.no_grad():
+                w1s, k1, _, _, colsum = ops.split_bf16x3(self.ffn[0].weight.detach().float(), 1,
+                                                         col_scale=self.norm.weight.detach().float().contiguous(), want_rowsum=True)
+                dbias = (self.ffn[0].weight.detach().double() @ self.norm.bias.detach().double()
+                         + self.ffn[0].bias.detach().double()).float()       # tiny host-side GEMV, once per weight version
+                w2s, k2, _, _, _ = ops.split_bf16x3(self.ffn[2].weight.detach().float(), 1)
+                return w1s, k1, colsum, dbias, w2s, k2, self.ffn[2].bias.detach().float().contiguous()
+        w1s, k1, colsum, dbias, w2s, k2, b2 = self._cache3.get(params, build)
+        xs, kx, mean, rstd, _ = ops.split_bf16x3(x.reshape(B * T, D).float(), 0, want_ln=True, ln_eps=self.norm.eps)
+        h = torch.empty(B * T, Hb, dtype=torch.float32, device=x.device)
+        ops.gemm_bf16_tn(xs, w1s, B * T, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
+        hs, kh, _, _, _ = ops.split_bf16x3(h, 0)
+        y = torch.empty(B * T, H, dtype=torch.float32, device=x.device)
+        ops.gemm_bf16_tn(hs, w2s, B * T, H, kh, y, L.EPI_BIAS, b2)
+        return y.view(B, T, H).to(x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
 
     def folded_weights(self):
         """(W1·γ bf16 [2048, pad64(in)], colsum, W1β+b1, W2 bf16, b2 fp32), cached per parameter version."""
@@ -76,6 +103,8 @@ class EncoderProjectorLinearSiLU(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             from .autograd import linear_silu_train
             return linear_silu_train(self, x)
+        if self.precision == "fp32x3":
+            return self._forward_fp32x3(x)
         B, T, D = x.shape
         w1g, colsum, dbias, w2, b2 = self.folded_weights()
         xb, mean, rstd = _rows_bf16(x.reshape(B * T, D), True, self.norm.eps)

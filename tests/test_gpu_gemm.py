@@ -167,6 +167,31 @@ def test_projector_linear_silu_full_width(dev):
     assert rowerr < 2e-2, f"worst row relative error {rowerr}"
 
 
+def test_projector_fp32_accurate_mode(dev):
+    """precision="fp32x3": three-term bf16 split on the tensor cores reproduces the reference's fp32 projector
+    to ~1e-5 (north-star fp32 tolerance) at full width."""
+    import ps_slm_b200.projector as P
+    torch.manual_seed(0)
+    m = P.EncoderProjectorLinearSiLU(_cfg(25055, 1536))
+    with torch.no_grad():
+        m.norm.weight.uniform_(0.8, 1.2); m.norm.bias.uniform_(-0.05, 0.05); m.ffn[2].bias.uniform_(-0.1, 0.1)
+    x = torch.softmax(torch.randn(2, 24, 25055) * 6, -1)
+    x[1, 20:] = 0
+    sd = {k: v.double() for k, v in m.state_dict().items()}
+    ref = O.projector_linear_silu(x.double(), sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"],
+                                  sd["ffn.2.weight"], sd["ffn.2.bias"])           # fp64 ground truth
+    ref32 = O.projector_linear_silu(x, *[m.state_dict()[k] for k in ("norm.weight", "norm.bias", "ffn.0.weight",
+                                                                     "ffn.0.bias", "ffn.2.weight", "ffn.2.bias")])
+    m = m.to(dev).eval()
+    m.precision = "fp32x3"
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    err = ((y.double() - ref).norm() / ref.norm()).item()
+    err_ref32 = ((ref32.double() - ref).norm() / ref.norm()).item()     # what plain fp32 on the CPU achieves
+    assert err < 1e-5, f"fp32x3 relative error {err} (torch fp32 CPU: {err_ref32})"
+    assert ((y - ref32).norm() / ref32.norm()).item() < 1e-5
+
+
 @pytest.mark.parametrize("materialize", [False, True])
 @pytest.mark.parametrize("ragged,labels", [(False, False), (True, True)])
 def test_bridge_inference_vs_oracle(dev, ragged, labels, materialize):
