@@ -241,6 +241,11 @@ int tasu_linear_silu_wgrad_finish(const float* G, int64_t g_stride, const float*
 int tasu_split_bf16x3(const void* src, int src_dtype, int64_t rows, int K, int64_t src_stride,
                       const float* col_scale, int pattern, void* dst_bf16, int64_t dst_stride,
                       float* ln_mean, float* ln_rstd, float ln_eps, float* row_sum, void* stream);
+/* split-K combine of that mode: out = epilogue(sum_p parts[p]) with round-to-nearest fp32 adds; parts[p] is the
+ * TASU_EPI_NONE fp32 output of one K slice ([M, ldp], part_stride elements apart). */
+int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_stride, int M, int N, int64_t ldp,
+                      int epilogue, const float* bias, const float* row_rstd, const float* row_mean,
+                      const float* colsum, void* out, int out_dtype, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.

@@ -45,6 +45,7 @@ SIGNATURES = {
     "tasu_colsum": (_I, [_P, _I, _L, _I, _L, _P, _P]),
     "tasu_linear_silu_wgrad_finish": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "tasu_split_bf16x3": (_I, [_P, _I, _L, _I, _L, _P, _I, _P, _L, _P, _P, _F, _P, _P]),
+    "tasu_sum_epilogue": (_I, [_P, _I, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _P]),
     "tasu_splice_rowstat": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
     "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),

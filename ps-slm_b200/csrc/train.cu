@@ -282,3 +282,50 @@ extern "C" int tasu_split_bf16x3(const void* src, int src_dtype, int64_t rows, i
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
+
+// Split-K combine for the fp32-accurate mode: out = epilogue(sum_p parts[p]) with round-to-nearest fp32 adds
+// (the tensor core's own accumulation truncates; short K slices keep that bias below 1e-5).
+namespace tasu {
+template <typename To>
+__global__ void __launch_bounds__(256)
+sum_epilogue_kernel(const float* __restrict__ parts, int P, int64_t part_stride, int M, int N, int64_t ldp, int epi,
+                    const float* __restrict__ bias, const float* __restrict__ rstd, const float* __restrict__ mean,
+                    const float* __restrict__ colsum, To* __restrict__ out, int64_t ldo) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    const int m = (int)(idx / N), n = (int)(idx % N);
+    float x = 0.f;
+    for (int p = 0; p < P; ++p) x += parts[(int64_t)p * part_stride + (int64_t)m * ldp + n];
+    if (epi == TASU_EPI_LNFOLD_SILU || epi == TASU_EPI_LNFOLD) {
+        x = fmaf(rstd[m], x - mean[m] * colsum[n], bias[n]);
+        if (epi == TASU_EPI_LNFOLD_SILU) x = x / (1.f + expf(-x));
+    } else if (epi == TASU_EPI_SOFTMAX) {
+        x = expf(x + bias[n] - mean[m]) * rstd[m];
+    } else if (epi != TASU_EPI_NONE) {
+        x += bias[n];
+        if (epi == TASU_EPI_BIAS_SILU) x = x / (1.f + expf(-x));
+        else if (epi == TASU_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
+    }
+    out[(int64_t)m * ldo + n] = from_f32<To>(x);
+}
+}  // namespace tasu
+
+extern "C" int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_stride, int M, int N, int64_t ldp,
+                                 int epilogue, const float* bias, const float* row_rstd, const float* row_mean,
+                                 const float* colsum, void* out, int out_dtype, int64_t ldo, void* stream) {
+    TASU_CHECK_ARG(n_parts > 0 && M >= 0 && N > 0 && ldp >= N && ldo >= N, "shape");
+    TASU_CHECK_ARG(out_dtype == TASU_F32 || out_dtype == TASU_BF16, "out_dtype");
+    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_SOFTMAX, "epilogue");
+    if (M == 0) return TASU_OK;
+    TASU_CHECK_ARG(parts && out, "null pointer");
+    TASU_CHECK_ARG(epilogue == TASU_EPI_NONE || bias, "bias required");
+    const int64_t n = (int64_t)M * N;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == TASU_F32)
+        tasu::sum_epilogue_kernel<float><<<grid, 256, 0, st>>>(parts, n_parts, part_stride, M, N, ldp, epilogue, bias, row_rstd, row_mean, colsum, (float*)out, ldo);
+    else
+        tasu::sum_epilogue_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(parts, n_parts, part_stride, M, N, ldp, epilogue, bias, row_rstd, row_mean, colsum, (__nv_bfloat16*)out, ldo);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -466,3 +466,20 @@ def split_bf16x3(src: torch.Tensor, pattern: int, col_scale: Optional[torch.Tens
                                       _stream()), "tasu_split_bf16x3")
     _count(1)
     return dst, 6 * Kp, mean, rstd, rsum
+
+
+def gemm_fp32x3(a_split: torch.Tensor, b_split: torch.Tensor, M: int, N: int, Ksplit: int, out: torch.Tensor,
+                epilogue: int = L.EPI_NONE, bias=None, row_rstd=None, row_mean=None, colsum=None, slice_k: int = 6272):
+    """fp32-accurate GEMM on split operands (split_bf16x3): K' is cut into slices of ``slice_k`` so the tensor core's
+    truncating accumulation stays short; the slices are summed with round-to-nearest fp32 adds (tasu_sum_epilogue)."""
+    n_parts = (Ksplit + slice_k - 1) // slice_k
+    ldp = pad_to(N, 4)
+    parts = torch.empty(n_parts, M, ldp, dtype=torch.float32, device=out.device)
+    for p in range(n_parts):
+        k0, k1 = p * slice_k, min(Ksplit, (p + 1) * slice_k)
+        gemm_bf16_tn(a_split[:, k0:k1], b_split[:, k0:k1], M, N, k1 - k0, parts[p])
+    L.check(L.lib().tasu_sum_epilogue(parts.data_ptr(), n_parts, M * ldp, M, N, ldp, epilogue, _ptr(bias), _ptr(row_rstd),
+                                      _ptr(row_mean), _ptr(colsum), out.data_ptr(), _dt(out), out.stride(0), _stream()),
+            "tasu_sum_epilogue")
+    _count(1)
+    return out

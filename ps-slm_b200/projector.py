@@ -79,10 +79,10 @@ class EncoderProjectorLinearSiLU(nn.Module):
         w1s, k1, colsum, dbias, w2s, k2, b2 = self._cache3.get(params, build)
         xs, kx, mean, rstd, _ = ops.split_bf16x3(x.reshape(B * T, D).float(), 0, want_ln=True, ln_eps=self.norm.eps)
         h = torch.empty(B * T, Hb, dtype=torch.float32, device=x.device)
-        ops.gemm_bf16_tn(xs, w1s, B * T, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
+        ops.gemm_fp32x3(xs, w1s, B * T, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
         hs, kh, _, _, _ = ops.split_bf16x3(h, 0)
         y = torch.empty(B * T, H, dtype=torch.float32, device=x.device)
-        ops.gemm_bf16_tn(hs, w2s, B * T, H, kh, y, L.EPI_BIAS, b2)
+        ops.gemm_fp32x3(hs, w2s, B * T, H, kh, y, L.EPI_BIAS, b2)
         return y.view(B, T, H).to(x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
 
     def folded_weights(self):
