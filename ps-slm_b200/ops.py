@@ -469,7 +469,7 @@ def split_bf16x3(src: torch.Tensor, pattern: int, col_scale: Optional[torch.Tens
 
 
 def gemm_fp32x3(a_split: torch.Tensor, b_split: torch.Tensor, M: int, N: int, Ksplit: int, out: torch.Tensor,
-                epilogue: int = L.EPI_NONE, bias=None, row_rstd=None, row_mean=None, colsum=None, slice_k: int = 6272):
+                epilogue: int = L.EPI_NONE, bias=None, row_rstd=None, row_mean=None, colsum=None, slice_k: int = 1536):
     """fp32-accurate GEMM on split operands (split_bf16x3): K' is cut into slices of ``slice_k`` so the tensor core's
     truncating accumulation stays short; the slices are summed with round-to-nearest fp32 adds (tasu_sum_epilogue)."""
     n_parts = (Ksplit + slice_k - 1) // slice_k
