@@ -100,7 +100,9 @@ int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float*
 /* exclusive scans: new_lens → row_off [B+1] int32, kept_frames → frame_off [B+1] int32 (optional);
  * header [TASU_CH_WORDS] int64 */
 int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, const uint32_t* global_max_enc,
-                       int B, int32_t* row_off, int32_t* frame_off, int64_t* header, void* stream);
+                       int B, int32_t* row_off, int32_t* frame_off, int64_t* header,
+                       int32_t* counts_dev /*[4] {N_out, max_len, kept_frames, 0} in device memory, or NULL*/,
+                       void* stream);
 
 /* Gather the encoder rows of the kept frames into a compact [F_kept, K] bf16 matrix together with their
  * softmax scalars, so that a second, ~3x smaller CTC-head GEMM (TASU_EPI_SOFTMAX) recomputes probabilities
@@ -113,8 +115,8 @@ int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, cons
 int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K, int V,
                           const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
                           const int32_t* row_off, const int32_t* frame_off, const float* row_max,
-                          const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
-                          void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
+                          const float* row_sumexp, const float* row_sumexp2, int64_t max_rows /*compact rows*/,
+                          int64_t max_out /*packed rows*/, void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
                           int32_t* tail_src, int32_t* multi_rows /*[N_out] or NULL*/, int32_t* multi_count /*[1]*/,
                           float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 /* In-place mean over the frames of every multi-frame candidate of the compact probability matrix
@@ -181,11 +183,14 @@ int tasu_fold_layernorm(const float* w1, int64_t w1_stride, const float* gamma, 
  *   Stores are clipped at row M and at column N rounded up to the next 16-byte boundary of the
  *   row: pad columns inside the pitch may be written with zeros, nothing is written past it.
  *   bias [N] fp32 (EPI_BIAS*, LNFOLD), row_rstd/row_mean [M] and colsum [N] (LNFOLD only).
+ *   m_dev (optional): device int32 holding the live row count; M is then the capacity the buffers
+ *   were allocated for and the kernel works on min(*m_dev, M) rows — data-dependent sizes (compressed
+ *   rows, kept frames) need no host synchronisation between the plan and the GEMMs.
  */
 int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                       void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
                       const float* bias, const float* row_rstd, const float* row_mean,
-                      const float* colsum, void* stream);
+                      const float* colsum, const int32_t* m_dev, void* stream);
 /* ---------------------------------------------------------------------------------------
  * Steps 1b+2a fused — CTC head with the softmax statistics computed in the GEMM epilogue:
  * logits = X·W^T + b live only in TMEM; per frame the running max / sum-exp / argmax / blank logit

@@ -27,15 +27,15 @@ SIGNATURES = {
     "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
-    "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
-    "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P,
+    "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _F, _P]),
     "tasu_pool_tail": (_I, [_P, _L, _I, _L, _P, _P, _P, _P, _P, _P, _F, _P]),
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
-    "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "tasu_ctc_head_stats_workspace": (_L, [_I, _I, _I]),
     "tasu_ctc_head_stats": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_gemm_bf16_tn_simt": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -126,7 +126,8 @@ def _cap(n: int, q: int = 2048) -> int:
 
 def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Tensor, rstd: torch.Tensor,
                         w1g: torch.Tensor, colsum: torch.Tensor, dbias: torch.Tensor, w2: torch.Tensor,
-                        b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False, stage=None) -> torch.Tensor:
+                        b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False, stage=None,
+                        m_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm → Linear → SiLU → Linear of projector.py:149-151 as two tensor-core GEMMs:
     GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue."""
     Hb, H = w1g.shape[0], w2.shape[0]
@@ -135,10 +136,11 @@ def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Ten
     stage = stage or (lambda name: contextlib.nullcontext())
     h1 = torch.empty(_cap(rows), Hb, dtype=torch.bfloat16, device=dev)[:rows]
     with stage("projector_gemm1"):
-        ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt)
+        ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt,
+                         m_dev=m_dev)
     y = torch.empty(_cap(rows), H, dtype=out_dtype, device=dev)[:rows]
     with stage("projector_gemm2"):
-        ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt)
+        ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt, m_dev=m_dev)
     return y
 
 
@@ -183,6 +185,7 @@ class TasuBridge:
         self.speech_id, self.pad_id, self.ignore_id = int(speech_id), int(pad_id), int(ignore_id)
         self.blank_id, self.blank_threshold, self.ln_eps = int(blank_id), float(blank_threshold), float(ln_eps)
         self._ctc_cache = ProjectorCache()
+        self._capacity = {}           # (B, T) → (kept-frame rows, packed rows) the tail buffers are sized for
         self.last_counts = {}
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
@@ -190,6 +193,25 @@ class TasuBridge:
 
     def _stage(self, name):
         return _Stage(self, name)
+
+    def _tail(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2, out_dtype):
+        """Pass 2 + projector on capacity-sized buffers with device-side row counts (no host sync inside):
+        gather kept rows → softmax-epilogue CTC GEMM over the kept frames → in-place tail pooling → GEMM-1 → GEMM-2.
+        Row r of the compact matrix is the first frame of packed candidate r, so single-frame candidates (the
+        majority) are final as the GEMM writes them; only multi-frame runs are averaged afterwards."""
+        dev = x2.device
+        ldk = ops.pad_to(V)
+        with self._stage("gather_kept_rows"):
+            xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
+                x2, B, T, self.N_PREFIX, Denc, V, plan, st, cap_f, cap_o, self.ln_eps)
+        pooled = torch.empty(cap_f, ldk, dtype=torch.bfloat16, device=dev)
+        with self._stage("ctc_softmax_gemm"):
+            ops.gemm_bf16_tn(xg, w_ctc, cap_f, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max,
+                             m_dev=plan.counts[2:3])
+        with self._stage("pool_tail"):
+            ops.pool_tail(pooled, V, cap_o, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
+        return linear_silu_forward(pooled, cap_o, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
+                                   stage=self._stage, m_dev=plan.counts[0:1])
 
     def _header_slot(self):
         """Ring of pinned host header buffers (collapse + splice words), one per in-flight call."""
@@ -254,7 +276,17 @@ class TasuBridge:
         with self._stage("splice_plan"):
             ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record()                                                     # header is complete when this event fires
+        audio_cap = None
+        if not self.materialize_logits:
+            # The whole tail is enqueued BEFORE the host looks at the header: buffers are sized by capacity
+            # (high-water mark of earlier calls, worst case on the first) and every kernel takes its live row
+            # count from device memory, so the GPU never idles waiting for the host.
+            hw_f, hw_o = self._capacity.get((B, T), (0, 0))            # high-water marks of earlier batches of this shape
+            cap_f = _cap(int(1.25 * hw_f)) if hw_f else _cap(B * T)    # first call: worst case (every frame kept)
+            cap_o = _cap(int(1.25 * hw_o)) if hw_o else _cap(B * T)
+            audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2,
+                                   out_dtype)
         ev.synchronize()                                                # the single device→host hand-off
         hdr = header.clone()
         n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
@@ -263,31 +295,26 @@ class TasuBridge:
         _raise_splice_errors(shdr, attention_mask, B)
         spliced_len = int(shdr[L.SH_SPLICED_LEN])
 
-        if n_out > 0:
-            if self.materialize_logits:
+        if self.materialize_logits:
+            if n_out > 0:
                 pooled = torch.empty(_cap(n_out), ldk, dtype=torch.bfloat16, device=dev)[:n_out]
                 mean = torch.empty(n_out, dtype=torch.float32, device=dev)
                 rstd = torch.empty(n_out, dtype=torch.float32, device=dev)
                 with self._stage("softmax_meanpool"):
                     ops.segment_meanpool(post_view, plan, 0, max_len, n_out, pooled, ldk, softmax=st,
                                          ln_mean=mean, ln_rstd=rstd, ln_eps=self.ln_eps)
+                audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
+                                            stage=self._stage)
             else:
-                # second, ~3x smaller CTC-head pass over the kept frames only: probabilities in bf16.  Row r of the
-                # compact matrix is the first frame of packed candidate r, so single-frame candidates (the majority)
-                # are final as the GEMM writes them; only multi-frame runs are averaged afterwards, in place.
-                with self._stage("gather_kept_rows"):
-                    xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
-                        x2, B, T, self.N_PREFIX, Denc, V, plan, st, n_frames, n_out, self.ln_eps)
-                pooled = torch.empty(_cap(n_frames), ldk, dtype=torch.bfloat16, device=dev)[:n_frames]
-                with self._stage("ctc_softmax_gemm"):
-                    ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
-                with self._stage("pool_tail"):
-                    ops.pool_tail(pooled, V, n_out, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
-            # (a5) projector
-            audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
-                                        stage=self._stage)
+                audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
         else:
-            audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
+            if n_frames > cap_f or n_out > cap_o:                       # capacity exceeded (rare): redo the tail, exact
+                cap_f, cap_o = _cap(n_frames), _cap(n_out)
+                audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias,
+                                       w2, b2, out_dtype)
+            hw_f, hw_o = self._capacity.get((B, T), (0, 0))
+            self._capacity[(B, T)] = (max(hw_f, n_frames), max(hw_o, n_out))
+            audio = audio_cap[:n_out]
         # (a7+a8) splice with the embedding lookup fused
         with self._stage("splice_scatter"):
             emb, mask, out_labels, pos, fids = ops.splice_scatter(

@@ -141,7 +141,8 @@ __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
 
 struct Params {
-    int M, N, K;
+    int M, N, K;              // M = rows the tensor maps cover; the live row count may come from m_dev
+    const int32_t* m_dev;     // optional device-side row count (data-dependent M without a host sync)
     int epilogue;
     const float* bias;
     const float* row_rstd;
@@ -169,7 +170,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int M_live = p.m_dev != nullptr ? min(max(__ldg(p.m_dev), 0), p.M) : p.M;
+    const int m_tiles = (M_live + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (p.K + BK - 1) / BK;
 
@@ -264,7 +266,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             float rstd = 1.f, nmean = 0.f;
-            if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < p.M) {
+            if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < M_live) {
                 rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow);
             }
             const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
@@ -733,7 +735,8 @@ using namespace tasu::gemm;
 
 extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                                  int64_t ldc, int M, int N, int K, int epilogue, const float* bias,
-                                 const float* row_rstd, const float* row_mean, const float* colsum, void* stream) {
+                                 const float* row_rstd, const float* row_mean, const float* colsum,
+                                 const int32_t* m_dev, void* stream) {
     int rc = check_common(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, row_rstd, row_mean, colsum);
     if (rc != TASU_OK || M == 0) return rc;
     const int csz = c_dtype == TASU_F32 ? 4 : 2;
@@ -747,7 +750,7 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     rc = make_map(&mc, C, c_dtype == TASU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, csz,
                   M, N, ldc, BM, c_dtype == TASU_F32 ? 32 : 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
-    Params p{M, N, K, epilogue, bias, row_rstd, row_mean, colsum};
+    Params p{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = sm_count();
     if (grid > tiles) grid = tiles;
@@ -763,7 +766,7 @@ extern "C" int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B,
                                       const float* row_rstd, const float* row_mean, const float* colsum, void* stream) {
     int rc = check_common(A, lda, B, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, row_rstd, row_mean, colsum);
     if (rc != TASU_OK || M == 0) return rc;
-    Params p{M, N, K, epilogue, bias, row_rstd, row_mean, colsum};
+    Params p{M, N, K, nullptr, epilogue, bias, row_rstd, row_mean, colsum};
     dim3 grid((N + 15) / 16, (M + 15) / 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (c_dtype == TASU_F32)

@@ -106,15 +106,18 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
                         const int32_t* __restrict__ seg_foff, const int32_t* __restrict__ row_off,
                         const int32_t* __restrict__ frame_off, const float* __restrict__ row_max,
                         const float* __restrict__ row_sumexp, const float* __restrict__ row_sumexp2,
-                        int64_t max_rows, __nv_bfloat16* __restrict__ xg, int64_t ldg, float* __restrict__ g_max,
+                        int64_t max_rows, int64_t max_out, __nv_bfloat16* __restrict__ xg, int64_t ldg, float* __restrict__ g_max,
                         float* __restrict__ g_inv, int32_t* __restrict__ pk_len, int32_t* __restrict__ tail_src,
                         int32_t* __restrict__ multi_rows, int32_t* __restrict__ multi_count,
                         float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
     const int lane = threadIdx.x & 31;
     const int n_out = row_off[B];
+    // capacities (max_out packed rows, max_rows compact rows) bound every write: an overflowing batch produces
+    // an incomplete result that the host detects from the header and redoes with larger buffers
+    const int n_loop = n_out < max_out ? n_out : (int)max_out;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const bool vec = (K % 8 == 0) && ((ldx % 8) == 0) && ((ldg % 8) == 0);
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_out; r += warps) {
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_loop; r += warps) {
         int lo = 0, hi = B;                                    // utterance of packed row r
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row_off[mid] <= r) lo = mid; else hi = mid; }
         const int b = lo, j = r - row_off[b];
@@ -306,21 +309,21 @@ extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int
                                      const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
                                      const int32_t* row_off, const int32_t* frame_off, const float* row_max,
                                      const float* row_sumexp, const float* row_sumexp2, int64_t max_rows,
-                                     void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
+                                     int64_t max_out, void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
                                      int32_t* tail_src, int32_t* multi_rows, int32_t* multi_count, float* ln_mean,
                                      float* ln_rstd, float ln_eps, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && V > 0 && ldx >= K && ldg >= K, "shape");
     TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
     if (multi_count) TASU_CHECK_CUDA(cudaMemsetAsync(multi_count, 0, sizeof(int32_t), (cudaStream_t)stream));
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
-    if (B == 0 || max_rows <= 0) return TASU_OK;
+    if (B == 0 || max_rows <= 0 || max_out <= 0) return TASU_OK;
     TASU_CHECK_ARG(x_bf16 && seg_start && seg_len && seg_frame_off && row_off && frame_off && row_max && row_sumexp &&
                    xg_bf16 && g_max && g_inv_sum && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)x_bf16 % 16 == 0) && ((uintptr_t)xg_bf16 % 16 == 0), "16-byte alignment");
     const unsigned grid = (unsigned)(tasu::sm_count() * 8);
     gather_kept_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x_bf16, ldx, B, T, n_prefix, K, V, seg_start, seg_len, seg_frame_off, row_off, frame_off,
-        row_max, row_sumexp, row_sumexp2, max_rows, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, pk_len, tail_src,
+        row_max, row_sumexp, row_sumexp2, max_rows, max_out, (__nv_bfloat16*)xg_bf16, ldg, g_max, g_inv_sum, pk_len, tail_src,
         multi_rows, multi_count, ln_mean, ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
     return TASU_OK;

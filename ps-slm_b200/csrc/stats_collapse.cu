@@ -165,7 +165,7 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
 __global__ void __launch_bounds__(1024)
 collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __restrict__ kept_frames,
                      const uint32_t* __restrict__ gmax, int B, int32_t* __restrict__ row_off,
-                     int32_t* __restrict__ frame_off, int64_t* __restrict__ header) {
+                     int32_t* __restrict__ frame_off, int64_t* __restrict__ header, int32_t* __restrict__ counts_dev) {
     __shared__ int scratch[33];
     int carry = 0, mx = 0, frames = 0;
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
@@ -192,6 +192,7 @@ collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __rest
         header[TASU_CH_MAX_LEN] = mx;
         header[TASU_CH_IS_LOGPROB] = (gmax != nullptr && ordered_to_float(*gmax) <= 0.f) ? 1 : 0;
         header[TASU_CH_KEPT_FRAMES] = frames;
+        if (counts_dev != nullptr) { counts_dev[0] = carry; counts_dev[1] = mx; counts_dev[2] = frames; counts_dev[3] = 0; }
     }
 }
 
@@ -255,10 +256,10 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
 
 extern "C" int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames,
                                   const uint32_t* global_max_enc, int B, int32_t* row_off, int32_t* frame_off,
-                                  int64_t* header, void* stream) {
+                                  int64_t* header, int32_t* counts_dev, void* stream) {
     TASU_CHECK_ARG(B >= 0 && row_off && header, "B >= 0, non-null outputs");
     TASU_CHECK_ARG(B == 0 || new_lens, "null new_lens");
-    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, frame_off, header);
+    collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, frame_off, header, counts_dev);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -122,7 +122,7 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
     L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K, V,
                                           plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.seg_foff.data_ptr(),
                                           plan.row_off.data_ptr(), plan.frame_off.data_ptr(), st.row_max.data_ptr(),
-                                          st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), n_frames, xg.data_ptr(), ldg,
+                                          st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), n_frames, n_out, xg.data_ptr(), ldg,
                                           g_max.data_ptr(), g_inv.data_ptr(), pk_len.data_ptr(), tail_src.data_ptr(),
                                           multi[1:].data_ptr(), multi.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                           float(ln_eps), _stream()), "tasu_gather_kept_rows")
@@ -140,7 +140,7 @@ def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tai
 
 class CollapsePlan:
     __slots__ = ("seg_start", "seg_len", "seg_score", "seg_foff", "new_lens", "kept_frames", "row_off", "frame_off",
-                 "header", "B", "T")
+                 "header", "counts", "B", "T")
 
 
 def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: float,
@@ -159,6 +159,7 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     p.kept_frames = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
     p.seg_foff = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
     p.frame_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    p.counts = torch.empty(4, dtype=torch.int32, device=dev)       # {N_out, max_len, kept_frames, 0} for device-side M
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     # ``header`` may be pinned host memory: under UVA its pointer is valid on the device
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
@@ -170,8 +171,8 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
                                    p.seg_foff.data_ptr(), _stream()), "tasu_collapse_plan")
     L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
                                    st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
-                                   B, p.row_off.data_ptr(), p.frame_off.data_ptr(), p.header.data_ptr(), _stream()),
-            "tasu_collapse_scan")
+                                   B, p.row_off.data_ptr(), p.frame_off.data_ptr(), p.header.data_ptr(),
+                                   p.counts.data_ptr(), _stream()), "tasu_collapse_scan")
     _count(2)
     return p
 
@@ -240,8 +241,9 @@ def fold_layernorm(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1
 def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor,
                  epilogue: int = L.EPI_NONE, bias: Optional[torch.Tensor] = None,
                  row_rstd: Optional[torch.Tensor] = None, row_mean: Optional[torch.Tensor] = None,
-                 colsum: Optional[torch.Tensor] = None, simt: bool = False):
-    """out[M,N] = epilogue(A[M,K] · Bw[N,K]^T); A/Bw bf16 with pitch = stride(0); out bf16|fp32."""
+                 colsum: Optional[torch.Tensor] = None, simt: bool = False, m_dev: Optional[torch.Tensor] = None):
+    """out[M,N] = epilogue(A[M,K] · Bw[N,K]^T); A/Bw bf16 with pitch = stride(0); out bf16|fp32.
+    ``m_dev`` (int32 device scalar): live row count, M is then the allocated capacity."""
     _need_cuda(A, Bw, out)
     if A.dtype != torch.bfloat16 or Bw.dtype != torch.bfloat16:
         raise TypeError("GEMM operands must be bfloat16")
@@ -249,9 +251,12 @@ def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out:
     lda = A.stride(0) if A.dim() == 2 and A.shape[0] > 1 else max(K, A.shape[-1])
     ldb = Bw.stride(0) if Bw.shape[0] > 1 else max(K, Bw.shape[-1])
     ldc = out.stride(0) if out.shape[0] > 1 else max(N, out.shape[-1])
-    L.check(fn(A.data_ptr(), lda, Bw.data_ptr(), ldb, out.data_ptr(), _dt(out), ldc, M, N, K, epilogue,
-               _ptr(bias), _ptr(row_rstd), _ptr(row_mean), _ptr(colsum), _stream()),
-            "tasu_gemm_bf16_tn_simt" if simt else "tasu_gemm_bf16_tn")
+    args = (A.data_ptr(), lda, Bw.data_ptr(), ldb, out.data_ptr(), _dt(out), ldc, M, N, K, epilogue,
+            _ptr(bias), _ptr(row_rstd), _ptr(row_mean), _ptr(colsum))
+    if simt:
+        L.check(fn(*args, _stream()), "tasu_gemm_bf16_tn_simt")
+    else:
+        L.check(fn(*args, _ptr(m_dev), _stream()), "tasu_gemm_bf16_tn")
     _count(1)
     return out
 

@@ -49,10 +49,10 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.tasu_frame_stats(None, L.F32, L.INPUT_PROBS, 1, 1, 0, 0, 0, 0, None, None, None, None, None, None, None)
     assert rc == -1 and b"tasu_frame_stats" in lib.tasu_last_error()
     # unaligned GEMM pitch
-    rc = lib.tasu_gemm_bf16_tn(16, 3, 16, 8, 16, L.F32, 8, 4, 4, 8, 0, None, None, None, None, None)
+    rc = lib.tasu_gemm_bf16_tn(16, 3, 16, 8, 16, L.F32, 8, 4, 4, 8, 0, None, None, None, None, None, None)
     assert rc == -1
     # LN-fold epilogue without its vectors
-    rc = lib.tasu_gemm_bf16_tn(16, 8, 16, 8, 16, L.F32, 8, 4, 4, 8, L.EPI_LNFOLD_SILU, 16, None, None, None, None)
+    rc = lib.tasu_gemm_bf16_tn(16, 8, 16, 8, 16, L.F32, 8, 4, 4, 8, L.EPI_LNFOLD_SILU, 16, None, None, None, None, None)
     assert rc == -1 and b"LN-fold" in lib.tasu_last_error()
     rc = lib.tasu_segment_meanpool(None, 7, 1, 1, 1, 1, 1, None, None, None, None, None, None, 0, 1, 1, None, 0, 1, None, None, 1e-5, None)
     assert rc == -1
