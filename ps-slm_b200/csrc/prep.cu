@@ -44,6 +44,22 @@ cast_rows_kernel(const Ti* __restrict__ src, int64_t rows, int cols, int64_t sst
     }
 }
 
+// fast path: fp32 → bf16, rows of 8-element multiples, 16-byte aligned: 2 x 128-bit loads → 1 x 128-bit store
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_vec_kernel(const float* __restrict__ src, int64_t rows, int cols8, int64_t sstride, __nv_bfloat16* __restrict__ dst,
+                         int64_t dstride) {
+    const int64_t total = rows * cols8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols8;
+        const int c = (int)(i % cols8);
+        const uint4 a = ld_stream_u4(reinterpret_cast<const uint4*>(src + r * sstride) + 2 * c);
+        const uint4 b = ld_stream_u4(reinterpret_cast<const uint4*>(src + r * sstride) + 2 * c + 1);
+        const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(a.x), __uint_as_float(a.y)), pack_bf16x2(__uint_as_float(a.z), __uint_as_float(a.w)),
+                                   pack_bf16x2(__uint_as_float(b.x), __uint_as_float(b.y)), pack_bf16x2(__uint_as_float(b.z), __uint_as_float(b.w)));
+        reinterpret_cast<uint4*>(dst + r * dstride)[c] = o;
+    }
+}
+
 // one CTA per output feature n (row of W1)
 __global__ void __launch_bounds__(256)
 fold_layernorm_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
@@ -262,6 +278,15 @@ extern "C" int tasu_cast_rows(const void* src, int src_dtype, int64_t rows, int 
     if (rows == 0) return TASU_OK;
     TASU_CHECK_ARG(src && dst, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == TASU_F32 && dst_dtype == TASU_BF16 && ln_mean == nullptr && cols % 8 == 0 && src_stride % 4 == 0 &&
+        dst_stride % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+        const int64_t total = rows * (cols / 8);
+        int64_t g = (total + 255) / 256, gmax = (int64_t)tasu::sm_count() * 16;
+        if (g > gmax) g = gmax;
+        cast_f32_bf16_vec_kernel<<<(unsigned)g, 256, 0, st>>>((const float*)src, rows, cols / 8, src_stride, (__nv_bfloat16*)dst, dst_stride);
+        TASU_CHECK_LAUNCH();
+        return TASU_OK;
+    }
     const unsigned grid = row_grid(rows);
 #define LAUNCH(TI, TO) cast_rows_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, rows, cols, src_stride, (TO*)dst, dst_stride, ln_mean, ln_rstd, ln_eps)
     if (src_dtype == TASU_F32 && dst_dtype == TASU_BF16) LAUNCH(float, __nv_bfloat16);
