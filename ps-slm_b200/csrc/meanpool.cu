@@ -144,7 +144,31 @@ meanpool_kernel(PoolArgs a) {
                 orow[d] = from_f32<Tout>(v);
             }
         } else {
-            for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+            // rows with an odd pitch (reference tensors): coalesced 4-byte accesses, 4 columns in flight per thread
+            const int bd = blockDim.x;
+            int d = threadIdx.x;
+            for (; d + 3 * bd < a.D; d += 4 * bd) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int f = 0; f < n; ++f) {
+                    const Tin* sr = src + (int64_t)f * a.rstride;
+                    float x[4] = {to_f32(sr[d]), to_f32(sr[d + bd]), to_f32(sr[d + 2 * bd]), to_f32(sr[d + 3 * bd])};
+                    if (kSoftmax) {
+                        const int64_t fr = (int64_t)b * a.T + t0 + f;
+                        const float mx = a.smax[fr], is = 1.f / a.ssum[fr];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = __expf(x[e] - mx) * is;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] += x[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (n > 1) v[e] = v[e] / (float)n;
+                    acc_s += v[e]; acc_q += v[e] * v[e];
+                    orow[d + e * bd] = from_f32<Tout>(v[e]);
+                }
+            }
+            for (; d < a.D; d += bd) {
                 float v = 0.f;
                 for (int f = 0; f < n; ++f) {
                     float x = to_f32(src[(int64_t)f * a.rstride + d]);

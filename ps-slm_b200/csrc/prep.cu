@@ -18,7 +18,15 @@ cast_rows_kernel(const Ti* __restrict__ src, int64_t rows, int cols, int64_t sst
         const Ti* s = src + r * sstride;
         To* d = dst + r * dstride;
         float acc_s = 0.f, acc_q = 0.f;
-        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const int bd = blockDim.x;
+        int c = threadIdx.x;
+        for (; c + 3 * bd < cols; c += 4 * bd) {             // 4 independent coalesced loads in flight per thread
+            const float v0 = to_f32(s[c]), v1 = to_f32(s[c + bd]), v2 = to_f32(s[c + 2 * bd]), v3 = to_f32(s[c + 3 * bd]);
+            acc_s += (v0 + v1) + (v2 + v3);
+            acc_q += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+            d[c] = from_f32<To>(v0); d[c + bd] = from_f32<To>(v1); d[c + 2 * bd] = from_f32<To>(v2); d[c + 3 * bd] = from_f32<To>(v3);
+        }
+        for (; c < cols; c += bd) {
             const float v = to_f32(s[c]);
             acc_s += v;
             acc_q += v * v;
