@@ -99,3 +99,81 @@ def test_midsize_vs_oracle(dev):
     rows = (e[audio] - e_r[audio]).norm(dim=-1) / e_r[audio].norm(dim=-1)
     assert rows.max().item() < 2e-2 and ((e[audio] - e_r[audio]).norm() / e_r[audio].norm()).item() < 1e-2
     assert torch.equal(e[~audio], e_r[~audio])
+
+
+def _small_bridge(dev, V=61, D=32, H=48, table_rows=300):
+    import ps_slm_b200.projector as P
+    from ps_slm_b200.bridge import TasuBridge
+    import math
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(V, D, generator=g) / math.sqrt(D)
+    b = torch.randn(V, generator=g) * 0.05
+    torch.manual_seed(2)
+    proj = P.EncoderProjectorLinearSiLU(types.SimpleNamespace(encoder_dim=V, llm_dim=H, encoder_projector_ds_rate=1)).to(dev).eval()
+    table = torch.randn(table_rows, H, generator=g)
+    return w, b, proj, table, TasuBridge(w.to(dev), b.to(dev), proj, table.to(dev), 299, 0)
+
+
+def _oracle_small(raw, raw_lens, w, b, proj, table, ids, mask, labels=None):
+    sd = {k: v.detach().cpu() for k, v in proj.state_dict().items()}
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    return O.bridge_inference(raw, raw_lens, w, b, pp, table, ids, mask, labels, 299, 0)
+
+
+@pytest.mark.parametrize("case", ["all_dropped", "single_frame", "zero_length_rows", "one_utt", "everything_kept"])
+def test_bridge_edge_cases(dev, case):
+    """Empty / ragged / degenerate inputs through the fused path vs the oracle (ps-slm.py:261-264, :304-306)."""
+    import math
+    w, b, proj, table, br = _small_bridge(dev)
+    V, D = w.shape
+    what = w / w.norm(dim=1, keepdim=True)
+    g = torch.Generator().manual_seed(7)
+
+    def frames(labels, scale):
+        lab = torch.tensor(labels)
+        return (scale / w.norm(dim=1)[lab]).unsqueeze(-1) * what[lab] + 0.02 * torch.randn(len(labels), D, generator=g)
+
+    if case == "all_dropped":            # confident blanks only → every M_b = 0, the <speech> slot vanishes
+        B, T = 2, 6
+        body = torch.stack([frames([0] * T, 16.0) for _ in range(B)])
+        lens = torch.tensor([T, T])
+    elif case == "single_frame":
+        B, T = 1, 1
+        body = frames([5], 14.0).unsqueeze(0)
+        lens = torch.tensor([1])
+    elif case == "zero_length_rows":     # L = 0 for some utterances
+        B, T = 3, 9
+        body = torch.stack([frames([3, 3, 0, 7, 0, 0, 9, 9, 9], 14.0) for _ in range(B)])
+        lens = torch.tensor([9, 0, 4])
+    elif case == "one_utt":
+        B, T = 1, 12
+        body = frames([0, 4, 4, 0, 0, 8, 0, 2, 2, 2, 0, 1], 14.0).unsqueeze(0)
+        lens = torch.tensor([12])
+    else:                                # all different tokens, nothing merges or drops
+        B, T = 2, 10
+        body = torch.stack([frames(list(range(1 + i, 11 + i)), 14.0) for i in range(B)])
+        lens = torch.tensor([10, 7])
+    raw = torch.cat([torch.randn(B, 4, D, generator=g) * 0.1, body], 1).contiguous()
+    raw_lens = lens + 4
+    ids = torch.randint(1, 298, (B, 6), generator=g)
+    ids[:, 2] = 299
+    mask = torch.ones(B, 6, dtype=torch.bool)
+    if B > 1:
+        mask[1, :2] = False
+        ids[1, :2] = 0
+    (e_r, m_r, _, p_r, f_r), nl_r = _oracle_small(raw, raw_lens, w, b, proj, table, ids, mask)
+    e, m, _, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    assert torch.equal(nl.cpu(), nl_r), (nl.cpu(), nl_r)
+    assert e.shape == e_r.shape and torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    if case == "all_dropped":
+        assert int(nl_r.sum()) == 0 and e.shape[1] == 5
+    if e_r.numel():
+        assert ((e.cpu() - e_r).norm() / e_r.norm()).item() < 1e-2
+    # the stand-alone psd() on the same posterior agrees too
+    import ps_slm_b200.bridge as bridge
+    post, plens = O.ctc_head_posterior(raw, raw_lens, w, b)
+    f_ref, l_ref = O.psd_loop(post, plens, post)
+    f_gpu, l_gpu = bridge.psd(post.to(dev), plens.to(dev), post.to(dev))
+    assert torch.equal(l_gpu.cpu(), l_ref) and f_gpu.shape == f_ref.shape
+    if f_ref.numel():
+        np.testing.assert_allclose(f_gpu.cpu().numpy(), f_ref.numpy(), rtol=1e-5, atol=1e-7)
