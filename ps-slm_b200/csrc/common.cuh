@@ -37,6 +37,17 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 
+// grid of a persistent (grid-stride) kernel: SMs x CTAs that are actually resident for this kernel, capped by the
+// number of work items — a larger grid only adds a ragged second wave
+template <typename K>
+inline unsigned persistent_grid(K kernel, int block, int64_t items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+    int64_t g = (int64_t)sm_count() * per_sm;
+    if (g > items) g = items;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
 constexpr int kWarp = 32;
 
 // ---- order-preserving float <-> uint32 (so atomicMax on uint gives float max; 0 < every float)

@@ -233,24 +233,22 @@ extern "C" int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int
                seg_src, layout, max_len, max_rows, out, out_row_stride, ln_mean, ln_rstd, ln_eps};
     int64_t rows_cap = layout == 0 ? max_rows : (int64_t)B * max_len;
     if (rows_cap > max_rows) rows_cap = max_rows;
-    int64_t grid64 = (int64_t)sm_count() * 8;
-    if (grid64 > rows_cap) grid64 = rows_cap;
-    if (grid64 < 1) grid64 = 1;
-    const unsigned grid = (unsigned)grid64;
     cudaStream_t st = (cudaStream_t)stream;
     const bool sm = softmax_max != nullptr;
+#define LAUNCH1(K) K<<<persistent_grid(K, 256, rows_cap), 256, 0, st>>>(a)
 #define LAUNCH(TI, TO)                                                                              \
     do {                                                                                            \
-        if (sm) { if (vec) meanpool_kernel<TI, TO, true, true><<<grid, 256, 0, st>>>(a);            \
-                  else     meanpool_kernel<TI, TO, true, false><<<grid, 256, 0, st>>>(a); }         \
-        else    { if (vec) meanpool_kernel<TI, TO, false, true><<<grid, 256, 0, st>>>(a);           \
-                  else     meanpool_kernel<TI, TO, false, false><<<grid, 256, 0, st>>>(a); }        \
+        if (sm) { if (vec) LAUNCH1((meanpool_kernel<TI, TO, true, true>));                          \
+                  else     LAUNCH1((meanpool_kernel<TI, TO, true, false>)); }                       \
+        else    { if (vec) LAUNCH1((meanpool_kernel<TI, TO, false, true>));                         \
+                  else     LAUNCH1((meanpool_kernel<TI, TO, false, false>)); }                      \
     } while (0)
     if (in_dtype == TASU_F32 && out_dtype == TASU_F32) LAUNCH(float, float);
     else if (in_dtype == TASU_F32 && out_dtype == TASU_BF16) LAUNCH(float, __nv_bfloat16);
     else if (in_dtype == TASU_BF16 && out_dtype == TASU_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
     else LAUNCH(__nv_bfloat16, float);
 #undef LAUNCH
+#undef LAUNCH1
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

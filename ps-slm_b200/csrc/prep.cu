@@ -371,7 +371,7 @@ extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out
     TASU_CHECK_ARG(probs_bf16 && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)probs_bf16 % 16 == 0) && (ld % 8 == 0), "16-byte aligned rows");
     TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
-    pool_tail_kernel<<<row_grid(n_out), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
+    pool_tail_kernel<<<persistent_grid(pool_tail_kernel, 256, n_out), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
                                                                          tail_src, multi_rows, multi_count, ln_mean,
                                                                          ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
