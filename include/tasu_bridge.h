@@ -253,6 +253,40 @@ int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_stride, int 
                       const float* colsum, void* out, int out_dtype, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Token-row projector: steps 1a + 3 fused for TEXT-SIMULATED posteriors (ps-slm.py:337-358, :360-409 feeding
+ * projector.py:149-151).  Every simulated row is  base*1 + (hot-base)*onehot(tok)  (clean: hot=1, base=0;
+ * smoothed: hot=(1-alpha)+alpha/V, base=alpha/V; inserted blank: tok=blank, hot=1, base=0), so
+ *   W1*LN(x) + b1 = a*gamma[tok]*W1[:,tok] + e*S + D,  a = rstd*(hot-base), e = rstd*(base-mean),
+ *   S = W1*gamma, D = W1*beta + b1                      (closed-form mean/rstd of a two-valued row)
+ * — a column gather of the fp32 W1 instead of a 2*V*Hb-flop GEMM row, and a column scatter in the backward:
+ *   dW1[j,v] = gamma_v*(P[j,v] + E_j) + beta_v*db1_j,  P[j,v] = sum_{r: tok_r = v} a_r dz[r,j],  E_j = sum_r e_r dz[r,j]
+ *   dgamma_v = sum_j W1[j,v]*(P[j,v] + E_j),  dbeta_v = sum_j W1[j,v]*db1_j,  db1_j = sum_r dz[r,j].
+ * The [B, L, 25055] posterior (ps-slm.py:346, :403) is never built on this path.
+ *   tasu_host_group_tokens   HOST: stable counting sort of the rows by token → uniq[n_uniq], seg_off[n_uniq+1],
+ *                            perm[n_rows] (rows of token uniq[u] = perm[seg_off[u] .. seg_off[u+1]), ascending)
+ *   tasu_linear_rowdots      S[j], D[j] (fp32), one pass over W1
+ *   tasu_tokrow_fwd          z[r,:] (fp32, optional), h[r,:] = bf16(silu(z)), row_a[r], row_e[r]
+ *   tasu_tokrow_bwd_rows     dz = dh*silu'(z) on the fly; P [n_uniq, Hb] (compact), db1, E — all sums in a fixed order
+ *   tasu_tokrow_wgrad_finish dW1, dgamma, dbeta in one pass over W1; slot_ws = int32[V] scratch
+ */
+int tasu_host_group_tokens(const int32_t* tok_host, int64_t n_rows, int V, int32_t* uniq_host,
+                           int32_t* seg_off_host, int32_t* perm_host, int32_t* n_uniq_host);
+int tasu_linear_rowdots(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                        const float* b1, int N, int K, float* S, float* D, void* stream);
+int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* S, const float* D,
+                    const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, const float* hot,
+                    const float* base, int n_uniq, int64_t n_rows, int V, int Hb, float ln_eps, float* z,
+                    void* h_bf16, float* row_a, float* row_e, void* stream);
+int64_t tasu_tokrow_bwd_workspace(int Hb, int n_uniq);    /* bytes of per-CTA partial sums (deterministic db1 / E) */
+int tasu_tokrow_bwd_rows(const float* dh, const float* z, int64_t n_rows, int Hb, const int32_t* seg_off,
+                         const int32_t* perm, const float* row_a, const float* row_e, int n_uniq, float* P,
+                         float* db1, float* E, void* workspace, int64_t workspace_bytes, void* stream);
+int tasu_tokrow_wgrad_finish(const float* P, const int32_t* uniq, int n_uniq, int32_t* slot_ws, const float* w1,
+                             int64_t w1_stride, const float* gamma, const float* beta, const float* E,
+                             const float* db1, int Hb, int V, float* dw1, int64_t dw1_stride, float* dgamma,
+                             float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.
  *   input_ids [B,S] int64; attention_mask [B,S] uint8/bool (mask_dtype 0) or int64 (1);
  *   num_audio [n_audio] int64 (compressed lengths), divided by div_k on device

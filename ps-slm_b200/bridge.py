@@ -78,6 +78,29 @@ def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_
                               left_padding=int(hdr[L.SH_LEFT_PADDING]))
 
 
+def merge_packed_audio_rows(audio_rows: torch.Tensor, num_audio_tokens: torch.Tensor, max_audio_tokens: int,
+                            text_src: torch.Tensor, text_mode: int, input_ids: torch.Tensor,
+                            attention_mask: torch.Tensor, labels: Optional[torch.Tensor], speech_id: int, pad_id: int,
+                            ignore_id: int = -100):
+    """Step 4 on PACKED audio rows ``[sum M_b, H]`` (no [B, max M_b, H] padding in between); ``text_src`` is the
+    embedding table (``text_mode=1``: embed_tokens lookup fused, ps-slm.py:525,654) or ``inputs_embeds``
+    (``text_mode=0``).  Same 5-tuple and ValueErrors as ``_merge_input_ids_with_audio_features``
+    (ps-slm.py:679-873); differentiable w.r.t. ``audio_rows``."""
+    if audio_rows.dtype != text_src.dtype:
+        audio_rows = audio_rows.to(text_src.dtype)
+    p = ops.splice_rowstat(input_ids, attention_mask, speech_id)
+    ops.splice_plan(p, num_audio_tokens, 1)
+    hdr = p.header.cpu()
+    _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
+    p.left_padding = int(hdr[L.SH_LEFT_PADDING])
+    if torch.is_grad_enabled() and audio_rows.requires_grad:
+        from .autograd import SpliceFunction
+        return SpliceFunction.apply(audio_rows, p, int(hdr[L.SH_SPLICED_LEN]), text_src.detach(), text_mode, 0,
+                                    max_audio_tokens, labels, pad_id, ignore_id)
+    return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), text_src, text_mode, audio_rows, 0, max_audio_tokens,
+                              labels, pad_id, ignore_id, left_padding=p.left_padding)
+
+
 def _raise_splice_errors(hdr, attention_mask, num_audios):
     if int(hdr[L.SH_ERR_BOTH_SIDES]):
         raise ValueError(f"both side of attention_mask has zero, invalid. {attention_mask}")

@@ -1,0 +1,369 @@
+// Token-row projector: EncoderProjectorLinearSiLU (Multitask/model/projector.py:149-151) applied to
+// TEXT-SIMULATED posteriors (Multitask/model/ps-slm.py:337-358, :360-409) without ever building them.
+//
+// Every row the simulators emit is  x = base·1 + (hot − base)·e_t  (t = token id; clean rows: hot=1, base=0;
+// smoothed rows: hot = (1−α)+α/V, base = α/V; inserted hard blanks: t = blank, hot=1, base=0).  For such a row
+//   mean = (hot + (V−1)·base)/V,   var = (hot² + (V−1)·base²)/V − mean²,   rstd = 1/sqrt(var + eps)
+//   W1·LN(x) + b1 = a·γ_t·W1[:,t] + e·S + D,    a = rstd·(hot − base),  e = rstd·(base − mean),
+//   S = W1·γ (row dots),  D = W1·β + b1
+// so the 2·V·2048-flop GEMM row collapses to one column gather of W1 — fp32-exact, HBM-bound — and the backward
+// to a column scatter:  with dz = dL/dz,
+//   dW1[j,v] = γ_v·(P[j,v] + E_j) + β_v·db1_j,   P[j,v] = Σ_{r: t_r = v} a_r dz[r,j],  E_j = Σ_r e_r dz[r,j],
+//   dγ_v = Σ_j W1[j,v]·(P[j,v] + E_j),   dβ_v = Σ_j W1[j,v]·db1_j,   db1_j = Σ_r dz[r,j].
+// Rows are grouped by token on the host (tasu_host_group_tokens, a stable counting sort) so that every W1 column is
+// touched once per step and all sums are deterministic.
+#include "common.cuh"
+
+#include <vector>
+
+namespace tasu {
+
+// S[j] = Σ_v W1[j,v]·γ_v ;  D[j] = Σ_v W1[j,v]·β_v + b1[j]   (fp32; one CTA per output feature j)
+__global__ void __launch_bounds__(256)
+rowdots_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const float* __restrict__ b1, int K, float* __restrict__ S,
+               float* __restrict__ D) {
+    __shared__ float red[8];
+    const int j = blockIdx.x;
+    const float* w = w1 + (int64_t)j * wstride;
+    float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+    const int bd = blockDim.x;
+    int k = threadIdx.x;
+    for (; k + 3 * bd < K; k += 4 * bd) {                      // 4 independent coalesced loads in flight
+        const float a = w[k], b = w[k + bd], c = w[k + 2 * bd], d = w[k + 3 * bd];
+        s0 = fmaf(a, gamma[k], s0); s1 = fmaf(b, gamma[k + bd], s1);
+        s0 = fmaf(c, gamma[k + 2 * bd], s0); s1 = fmaf(d, gamma[k + 3 * bd], s1);
+        d0 = fmaf(a, beta[k], d0); d1 = fmaf(b, beta[k + bd], d1);
+        d0 = fmaf(c, beta[k + 2 * bd], d0); d1 = fmaf(d, beta[k + 3 * bd], d1);
+    }
+    for (; k < K; k += bd) { const float a = w[k]; s0 = fmaf(a, gamma[k], s0); d0 = fmaf(a, beta[k], d0); }
+    const float s = block_sum_f(s0 + s1, red);
+    const float d = block_sum_f(d0 + d1, red);
+    if (threadIdx.x == 0) { S[j] = s; D[j] = d + (b1 ? b1[j] : 0.f); }
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// one CTA per distinct token: column W1[:,t]·γ_t staged once in shared memory, then one pass per row of the group
+__global__ void __launch_bounds__(256)
+tokrow_fwd_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
+                  const float* __restrict__ S, const float* __restrict__ D, const int32_t* __restrict__ uniq,
+                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ perm, const float* __restrict__ hot,
+                  const float* __restrict__ base, int n_uniq, int V, int Hb, float eps, float* __restrict__ z,
+                  __nv_bfloat16* __restrict__ h, float* __restrict__ row_a, float* __restrict__ row_e) {
+    extern __shared__ float col[];                              // [Hb]
+    for (int u = blockIdx.x; u < n_uniq; u += gridDim.x) {
+        const int v = uniq[u];
+        const float g = gamma[v];
+        for (int j = threadIdx.x; j < Hb; j += blockDim.x) col[j] = w1[(int64_t)j * wstride + v] * g;
+        __syncthreads();
+        const int i0 = seg_off[u], i1 = seg_off[u + 1];
+        for (int i = i0; i < i1; ++i) {
+            const int r = perm[i];
+            // closed-form LayerNorm statistics of a two-valued row (double: no cancellation)
+            const double hv = (double)hot[r], bv = (double)base[r];
+            const double mean = (hv + (double)(V - 1) * bv) / V;
+            double var = (hv * hv + (double)(V - 1) * bv * bv) / V - mean * mean;
+            var = var < 0 ? 0 : var;
+            const double rstd = 1.0 / sqrt(var + (double)eps);
+            const float a = (float)(rstd * (hv - bv)), e = (float)(rstd * (bv - mean));
+            if (threadIdx.x == 0) { row_a[r] = a; row_e[r] = e; }
+            float* zr = z ? z + (int64_t)r * Hb : nullptr;
+            __nv_bfloat16* hr = h + (int64_t)r * Hb;
+            for (int j = threadIdx.x * 8; j < Hb; j += blockDim.x * 8) {
+                const float4 s0 = *reinterpret_cast<const float4*>(S + j), s1 = *reinterpret_cast<const float4*>(S + j + 4);
+                const float4 d0 = *reinterpret_cast<const float4*>(D + j), d1 = *reinterpret_cast<const float4*>(D + j + 4);
+                const float4 c0 = *reinterpret_cast<const float4*>(col + j), c1 = *reinterpret_cast<const float4*>(col + j + 4);
+                float4 z0, z1;
+                z0.x = fmaf(a, c0.x, fmaf(e, s0.x, d0.x)); z0.y = fmaf(a, c0.y, fmaf(e, s0.y, d0.y));
+                z0.z = fmaf(a, c0.z, fmaf(e, s0.z, d0.z)); z0.w = fmaf(a, c0.w, fmaf(e, s0.w, d0.w));
+                z1.x = fmaf(a, c1.x, fmaf(e, s1.x, d1.x)); z1.y = fmaf(a, c1.y, fmaf(e, s1.y, d1.y));
+                z1.z = fmaf(a, c1.z, fmaf(e, s1.z, d1.z)); z1.w = fmaf(a, c1.w, fmaf(e, s1.w, d1.w));
+                if (zr) { *reinterpret_cast<float4*>(zr + j) = z0; *reinterpret_cast<float4*>(zr + j + 4) = z1; }
+                *reinterpret_cast<uint4*>(hr + j) = make_uint4(pack_bf16x2(silu_f(z0.x), silu_f(z0.y)), pack_bf16x2(silu_f(z0.z), silu_f(z0.w)),
+                                                               pack_bf16x2(silu_f(z1.x), silu_f(z1.y)), pack_bf16x2(silu_f(z1.z), silu_f(z1.w)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ float silu_grad(float zz) {
+    const float s = 1.f / (1.f + __expf(-zz));
+    return s * (1.f + zz * (1.f - s));
+}
+
+// one CTA per distinct token (grid-stride): dz = dh·silu'(z) for the rows of the group, P[u,:] = Σ a_r dz[r,:];
+// db1 / E are accumulated per CTA in registers and written as per-CTA partials (part[cta][0|1][Hb]) that
+// reduce_partials_kernel sums in CTA order — no atomics, bit-reproducible.  blockDim.x·8·CHUNKS must cover Hb.
+template <int CHUNKS>
+__global__ void __launch_bounds__(256)
+tokrow_bwd_rows_kernel(const float* __restrict__ dh, const float* __restrict__ z, int Hb, const int32_t* __restrict__ seg_off,
+                       const int32_t* __restrict__ perm, const float* __restrict__ row_a, const float* __restrict__ row_e,
+                       int n_uniq, float* __restrict__ P, float* __restrict__ part) {
+    float adb[CHUNKS][8], ae[CHUNKS][8];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { adb[c][k] = 0.f; ae[c][k] = 0.f; }
+    for (int u = blockIdx.x; u < n_uniq; u += gridDim.x) {
+        const int i0 = seg_off[u], i1 = seg_off[u + 1];
+        float ap[CHUNKS][8];
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ap[c][k] = 0.f;
+        for (int i = i0; i < i1; ++i) {
+            const int r = perm[i];
+            const float a = row_a[r], e = row_e[r];
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int j = (c * blockDim.x + threadIdx.x) * 8;
+                if (j < Hb) {
+                    const float* dp = dh + (int64_t)r * Hb + j;
+                    const float* zp = z + (int64_t)r * Hb + j;
+                    const uint4 q0 = ld_stream_u4(dp), q1 = ld_stream_u4(dp + 4), y0 = ld_stream_u4(zp), y1 = ld_stream_u4(zp + 4);
+                    float d[8], zz[8];
+                    d[0] = __uint_as_float(q0.x); d[1] = __uint_as_float(q0.y); d[2] = __uint_as_float(q0.z); d[3] = __uint_as_float(q0.w);
+                    d[4] = __uint_as_float(q1.x); d[5] = __uint_as_float(q1.y); d[6] = __uint_as_float(q1.z); d[7] = __uint_as_float(q1.w);
+                    zz[0] = __uint_as_float(y0.x); zz[1] = __uint_as_float(y0.y); zz[2] = __uint_as_float(y0.z); zz[3] = __uint_as_float(y0.w);
+                    zz[4] = __uint_as_float(y1.x); zz[5] = __uint_as_float(y1.y); zz[6] = __uint_as_float(y1.z); zz[7] = __uint_as_float(y1.w);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dz = d[k] * silu_grad(zz[k]);
+                        adb[c][k] += dz;
+                        ae[c][k] = fmaf(e, dz, ae[c][k]);
+                        ap[c][k] = fmaf(a, dz, ap[c][k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int j = (c * blockDim.x + threadIdx.x) * 8;
+            if (j < Hb) {
+                float* pp = P + (int64_t)u * Hb + j;
+                *reinterpret_cast<float4*>(pp) = make_float4(ap[c][0], ap[c][1], ap[c][2], ap[c][3]);
+                *reinterpret_cast<float4*>(pp + 4) = make_float4(ap[c][4], ap[c][5], ap[c][6], ap[c][7]);
+            }
+        }
+    }
+    float* mine = part + (int64_t)blockIdx.x * 2 * Hb;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int j = (c * blockDim.x + threadIdx.x) * 8;
+        if (j < Hb) {
+            *reinterpret_cast<float4*>(mine + j) = make_float4(adb[c][0], adb[c][1], adb[c][2], adb[c][3]);
+            *reinterpret_cast<float4*>(mine + j + 4) = make_float4(adb[c][4], adb[c][5], adb[c][6], adb[c][7]);
+            *reinterpret_cast<float4*>(mine + Hb + j) = make_float4(ae[c][0], ae[c][1], ae[c][2], ae[c][3]);
+            *reinterpret_cast<float4*>(mine + Hb + j + 4) = make_float4(ae[c][4], ae[c][5], ae[c][6], ae[c][7]);
+        }
+    }
+}
+
+// out0[c] = Σ_p part[p][0][c], out1[c] = Σ_p part[p][1][c]  (p ascending: a fixed summation order)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out0, float* __restrict__ out1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2 * C) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int p = 0;
+    for (; p + 3 < n_parts; p += 4) {
+        a0 += part[(int64_t)p * 2 * C + c]; a1 += part[(int64_t)(p + 1) * 2 * C + c];
+        a2 += part[(int64_t)(p + 2) * 2 * C + c]; a3 += part[(int64_t)(p + 3) * 2 * C + c];
+    }
+    for (; p < n_parts; ++p) a0 += part[(int64_t)p * 2 * C + c];
+    const float r = (a0 + a1) + (a2 + a3);
+    if (c < C) out0[c] = r; else out1[c - C] = r;
+}
+
+__global__ void __launch_bounds__(256)
+slot_scatter_kernel(const int32_t* __restrict__ uniq, int n_uniq, int32_t* __restrict__ slot) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_uniq) slot[uniq[u]] = u;
+}
+
+// dW1 / dγ / dβ in one pass over W1: CTA = 32 vocabulary columns x ALL output features (so dγ/dβ need no atomics),
+// 64 features per iteration; the compact P rows ([n_uniq, Hb], j contiguous) are transposed through shared memory
+// into the [j, v] orientation of W1 / dW1.  8 independent loads per thread in flight in each phase.
+__global__ void __launch_bounds__(256)
+tokrow_wgrad_finish_kernel(const float* __restrict__ P, const int32_t* __restrict__ slot, const float* __restrict__ w1,
+                           int64_t wstride, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ E, const float* __restrict__ db1, int Hb, int V,
+                           float* __restrict__ dw1, int64_t dstride, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float tile[32][65];
+    __shared__ float s_ag[8][32], s_ab[8][32];
+    __shared__ int s_slot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v0 = blockIdx.x * 32;
+    if (threadIdx.x < 32) s_slot[threadIdx.x] = (v0 + threadIdx.x < V) ? slot[v0 + threadIdx.x] : -1;
+    const int v = v0 + lane;
+    const bool vok = v < V;
+    const float gm = vok ? gamma[v] : 0.f, bt = vok ? beta[v] : 0.f;
+    float ag = 0.f, ab = 0.f;
+    __syncthreads();
+    int sl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sl[q] = s_slot[warp * 4 + q];
+    for (int j0 = 0; j0 < Hb; j0 += 64) {
+        float pv[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                          // P rows → tile[v][j]
+            const float* pr = P + (int64_t)(sl[q] < 0 ? 0 : sl[q]) * Hb + j0;
+            pv[q][0] = (sl[q] >= 0 && j0 + lane < Hb) ? pr[lane] : 0.f;
+            pv[q][1] = (sl[q] >= 0 && j0 + 32 + lane < Hb) ? pr[32 + lane] : 0.f;
+        }
+        float wv[8], ev[8], dv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                          // W1 loads do not depend on the tile: issue them now
+            const int j = j0 + warp * 8 + q;
+            const bool ok = vok && j < Hb;
+            wv[q] = ok ? w1[(int64_t)j * wstride + v] : 0.f;
+            ev[q] = j < Hb ? E[j] : 0.f;
+            dv[q] = j < Hb ? db1[j] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { tile[warp * 4 + q][lane] = pv[q][0]; tile[warp * 4 + q][32 + lane] = pv[q][1]; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int jl = warp * 8 + q, j = j0 + jl;
+            if (j < Hb && vok) {
+                const float d = tile[lane][jl] + ev[q];
+                dw1[(int64_t)j * dstride + v] = fmaf(gm, d, bt * dv[q]);
+                ag = fmaf(wv[q], d, ag);
+                ab = fmaf(wv[q], dv[q], ab);
+            }
+        }
+        __syncthreads();
+    }
+    s_ag[warp][lane] = ag; s_ab[warp][lane] = ab;
+    __syncthreads();
+    if (warp == 0 && vok) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += s_ag[k][lane]; b += s_ab[k][lane]; }
+        dgamma[v] = a;
+        dbeta[v] = b;
+    }
+}
+
+}  // namespace tasu
+
+using namespace tasu;
+
+extern "C" int tasu_host_group_tokens(const int32_t* tok_host, int64_t n_rows, int V, int32_t* uniq_host,
+                                      int32_t* seg_off_host, int32_t* perm_host, int32_t* n_uniq_host) {
+    TASU_CHECK_ARG(n_rows >= 0 && V > 0, "n_rows >= 0, V > 0");
+    TASU_CHECK_ARG(n_uniq_host != nullptr, "null n_uniq_host");
+    *n_uniq_host = 0;
+    if (n_rows == 0) { if (seg_off_host) seg_off_host[0] = 0; return TASU_OK; }
+    TASU_CHECK_ARG(tok_host && uniq_host && seg_off_host && perm_host, "null pointer");
+    std::vector<int32_t> count((size_t)V + 1, 0);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int32_t t = tok_host[r];
+        TASU_CHECK_ARG(t >= 0 && t < V, "token id outside [0, V)");
+        ++count[(size_t)t + 1];
+    }
+    int32_t nu = 0;
+    for (int v = 0; v < V; ++v) {
+        if (count[(size_t)v + 1] > 0) { uniq_host[nu] = v; seg_off_host[nu] = count[v]; ++nu; }
+        count[(size_t)v + 1] += count[v];                      // exclusive start of token v = count[v]
+    }
+    seg_off_host[nu] = (int32_t)n_rows;
+    for (int64_t r = 0; r < n_rows; ++r) perm_host[count[tok_host[r]]++] = (int32_t)r;    // stable: ascending r per token
+    *n_uniq_host = nu;
+    return TASU_OK;
+}
+
+extern "C" int tasu_linear_rowdots(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                                   const float* b1, int N, int K, float* S, float* D, void* stream) {
+    TASU_CHECK_ARG(N > 0 && K > 0 && w1_stride >= K, "shape");
+    TASU_CHECK_ARG(w1 && gamma && beta && S && D, "null pointer");
+    rowdots_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(w1, w1_stride, gamma, beta, b1, K, S, D);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* S, const float* D,
+                               const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, const float* hot,
+                               const float* base, int n_uniq, int64_t n_rows, int V, int Hb, float ln_eps, float* z,
+                               void* h_bf16, float* row_a, float* row_e, void* stream) {
+    TASU_CHECK_ARG(n_uniq >= 0 && n_rows >= 0 && V > 0 && Hb > 0 && w1_stride >= V, "shape");
+    TASU_CHECK_ARG(Hb % 8 == 0, "Hb must be a multiple of 8");
+    if (n_uniq == 0 || n_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(w1 && gamma && S && D && uniq && seg_off && perm && hot && base && h_bf16 && row_a && row_e, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)S % 16 == 0) && ((uintptr_t)D % 16 == 0) && ((uintptr_t)h_bf16 % 16 == 0) &&
+                   (z == nullptr || (uintptr_t)z % 16 == 0), "16-byte alignment");
+    const size_t smem = sizeof(float) * (size_t)Hb;
+    TASU_CHECK_ARG(smem <= 200 * 1024, "Hb too large for the shared-memory column");
+    if (smem > 48 * 1024)
+        TASU_CHECK_CUDA(cudaFuncSetAttribute(tokrow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tokrow_fwd_kernel, 256, smem) != cudaSuccess || per_sm <= 0) per_sm = 4;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (grid > n_uniq) grid = n_uniq;
+    tokrow_fwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(w1, w1_stride, gamma, S, D, uniq, seg_off, perm, hot, base,
+                                                                          n_uniq, V, Hb, ln_eps, z, (__nv_bfloat16*)h_bf16, row_a, row_e);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+static unsigned bwd_rows_grid(int Hb, int n_uniq) {
+    const int chunks = (Hb + 2047) / 2048;
+    switch (chunks) {
+        case 1: return persistent_grid(tokrow_bwd_rows_kernel<1>, 256, n_uniq);
+        case 2: return persistent_grid(tokrow_bwd_rows_kernel<2>, 256, n_uniq);
+        case 3: return persistent_grid(tokrow_bwd_rows_kernel<3>, 256, n_uniq);
+        default: return persistent_grid(tokrow_bwd_rows_kernel<4>, 256, n_uniq);
+    }
+}
+
+extern "C" int64_t tasu_tokrow_bwd_workspace(int Hb, int n_uniq) {
+    if (Hb <= 0 || n_uniq <= 0) return 0;
+    return (int64_t)bwd_rows_grid(Hb, n_uniq) * 2 * Hb * (int64_t)sizeof(float);
+}
+
+extern "C" int tasu_tokrow_bwd_rows(const float* dh, const float* z, int64_t n_rows, int Hb, const int32_t* seg_off,
+                                    const int32_t* perm, const float* row_a, const float* row_e, int n_uniq, float* P,
+                                    float* db1, float* E, void* workspace, int64_t workspace_bytes, void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && n_uniq >= 0 && Hb > 0 && Hb % 8 == 0, "shape (Hb multiple of 8)");
+    TASU_CHECK_ARG(Hb <= 4 * 256 * 8, "Hb <= 8192");
+    TASU_CHECK_ARG(db1 && E, "null db1 / E");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0 || n_uniq == 0) {
+        TASU_CHECK_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * Hb, st));
+        TASU_CHECK_CUDA(cudaMemsetAsync(E, 0, sizeof(float) * Hb, st));
+        return TASU_OK;
+    }
+    TASU_CHECK_ARG(dh && z && seg_off && perm && row_a && row_e && P && workspace, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)dh % 16 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)P % 16 == 0) &&
+                   ((uintptr_t)workspace % 16 == 0), "16-byte alignment");
+    const unsigned grid = bwd_rows_grid(Hb, n_uniq);
+    TASU_CHECK_ARG(workspace_bytes >= (int64_t)grid * 2 * Hb * (int64_t)sizeof(float), "workspace too small (tasu_tokrow_bwd_workspace)");
+    const int chunks = (Hb + 2047) / 2048;
+    float* part = (float*)workspace;
+#define LAUNCH(C) tokrow_bwd_rows_kernel<C><<<grid, 256, 0, st>>>(dh, z, Hb, seg_off, perm, row_a, row_e, n_uniq, P, part)
+    if (chunks == 1) LAUNCH(1); else if (chunks == 2) LAUNCH(2); else if (chunks == 3) LAUNCH(3); else LAUNCH(4);
+#undef LAUNCH
+    TASU_CHECK_LAUNCH();
+    reduce_partials_kernel<<<(2 * Hb + 255) / 256, 256, 0, st>>>(part, (int)grid, Hb, db1, E);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_tokrow_wgrad_finish(const float* P, const int32_t* uniq, int n_uniq, int32_t* slot_ws, const float* w1,
+                                        int64_t w1_stride, const float* gamma, const float* beta, const float* E,
+                                        const float* db1, int Hb, int V, float* dw1, int64_t dw1_stride, float* dgamma,
+                                        float* dbeta, void* stream) {
+    TASU_CHECK_ARG(Hb > 0 && V > 0 && n_uniq >= 0 && w1_stride >= V && dw1_stride >= V, "shape");
+    TASU_CHECK_ARG(slot_ws && w1 && gamma && beta && E && db1 && dw1 && dgamma && dbeta, "null pointer");
+    TASU_CHECK_ARG(n_uniq == 0 || (P && uniq), "null P / uniq");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASU_CHECK_CUDA(cudaMemsetAsync(slot_ws, 0xFF, sizeof(int32_t) * V, st));
+    if (n_uniq > 0) slot_scatter_kernel<<<(n_uniq + 255) / 256, 256, 0, st>>>(uniq, n_uniq, slot_ws);
+    tokrow_wgrad_finish_kernel<<<(unsigned)((V + 31) / 32), 256, 0, st>>>(P, slot_ws, w1, w1_stride, gamma, beta, E, db1, Hb, V,
+                                                                         dw1, dw1_stride, dgamma, dbeta);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 try:  # imported as part of the package …
-    from . import bridge as _bridge, sim as _sim
+    from . import bridge as _bridge, ops as _ops, sim as _sim
     from .projector import PROJECTORS
 except ImportError:  # … or loaded by file path through the reference's plugin loader
     _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,6 +36,7 @@ except ImportError:  # … or loaded by file path through the reference's plugin
         sys.path.insert(0, _root)
     import ps_slm_b200.bridge as _bridge
     import ps_slm_b200.sim as _sim
+    import ps_slm_b200.ops as _ops
     from ps_slm_b200.projector import PROJECTORS
 
 
@@ -129,6 +130,8 @@ class slam_model_asr(nn.Module):
             self.encoder_tokenizer = SenseVoiceTokenizer(model_config.encoder_path)
             del ref
         self._bridge = None
+        # text-only batches go through the token-row projector (no [B, L, 25055] tensor); False = dense simulator path
+        self.token_row_path = True
 
     # ------------------------------------------------------------------ bridge methods
     def psd(self, encoder_out, encoder_out_lens, ctc_posterior, blank_id: int = 0, blank_threshold: float = 0.90):
@@ -187,6 +190,28 @@ class slam_model_asr(nn.Module):
                                                                  attention_mask, labels)
             return emb, mask, out_labels, pos
         blank = self.encoder.blank_id
+        rows_ok = (self.ctc_posterior and self.gt_emb and self.token_row_path
+                   and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
+                   and table.dtype in (torch.float32, torch.bfloat16))
+        if rows_ok:
+            # text-only branch (ps-slm.py:459-468 / :589-598): the simulated posterior is one-hot plus a constant per
+            # row, so it is handed to the projector as (token, hot, base) descriptors and never materialised
+            ids_list = [self.encoder_tokenizer.encode(t) for t in texts]
+            V = self.encoder_tokenizer.vocab_size
+            if noisy:
+                desc = _sim.draw_noise_descriptors(
+                    ids_list, V, blank, drop_prob=getattr(self, "drop_prob", 0.05),
+                    insert_prob=getattr(self, "insert_prob", 0.0), smooth_low=getattr(self, "smooth_low", 0.0),
+                    smooth_high=getattr(self, "smooth_high", 0.1))
+            else:
+                desc = _sim.clean_descriptors(ids_list)
+            rows = _ops.group_token_rows(*desc, V, input_ids.device)
+            audio = self.encoder_projector.forward_token_rows(rows, out_dtype=table.dtype)
+            emb, mask, out_labels, pos, _ = _bridge.merge_packed_audio_rows(
+                audio, rows.lens // self.encoder_projector.k, max(rows.lens_host, default=0), table, 1, input_ids,
+                attention_mask, labels, self.tokenizer.default_speech_token, self.tokenizer.pad_token_id,
+                self.tokenizer.default_ignore_token)
+            return emb, mask, out_labels, pos
         if raw_encoder_out is not None:                        # None on the text-only branch (encoder skipped)
             encoder_out = raw_encoder_out[:, 4:, :]
             encoder_out_lens = torch.clamp(raw_encoder_out_lens - 4, min=0)

@@ -488,3 +488,118 @@ def gemm_fp32x3(a_split: torch.Tensor, b_split: torch.Tensor, M: int, N: int, Ks
             "tasu_sum_epilogue")
     _count(1)
     return out
+
+
+# ----------------------------------------------------------------------------- token-row projector (text-simulated rows)
+class TokenRows:
+    """Row descriptors of a text-simulated posterior batch, grouped by token (tasu_host_group_tokens).
+    Row r is ``base[r]·1 + (hot[r] − base[r])·onehot(tok[r])``; rows are packed utterance after utterance."""
+    __slots__ = ("n_rows", "n_uniq", "V", "hot", "base", "uniq", "seg_off", "perm", "lens", "lens_host")
+
+
+def group_token_rows(tok, hot, base, lens, V: int, device) -> TokenRows:
+    """Host numpy descriptors (int32 tok, fp32 hot/base, per-utterance lens) → grouped device tensors with ONE
+    pinned staging buffer and ONE host→device copy."""
+    import ctypes
+
+    import numpy as np
+    n = int(tok.shape[0])
+    tok = np.ascontiguousarray(tok, dtype=np.int32)
+    B = len(lens)
+    # staging layout (int32 words): uniq[n] | seg_off[n+1] | perm[n] | hot[n] | base[n] | lens[B] (as int64 → 2B words)
+    o_uniq, o_seg, o_perm, o_hot, o_base = 0, n, 2 * n + 1, 3 * n + 1, 4 * n + 1
+    o_lens = 5 * n + 1 + ((5 * n + 1) & 1)                       # 8-byte aligned
+    words = o_lens + 2 * B
+    stage = torch.empty(max(words, 2), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    s = stage.numpy()
+    n_uniq = ctypes.c_int32(0)
+    i32p = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + 4 * off)   # noqa: E731
+    L.check(L.lib().tasu_host_group_tokens(i32p(tok), n, V, i32p(s, o_uniq), i32p(s, o_seg), i32p(s, o_perm),
+                                           ctypes.cast(ctypes.pointer(n_uniq), ctypes.c_void_p)),
+            "tasu_host_group_tokens")
+    s[o_hot:o_hot + n] = np.ascontiguousarray(hot, dtype=np.float32).view(np.int32)
+    s[o_base:o_base + n] = np.ascontiguousarray(base, dtype=np.float32).view(np.int32)
+    s[o_lens:o_lens + 2 * B] = np.asarray(lens, dtype=np.int64).view(np.int32)
+    d = stage.to(device, non_blocking=True)
+    t = TokenRows()
+    t.n_rows, t.n_uniq, t.V = n, int(n_uniq.value), V
+    t.uniq = d[o_uniq:o_uniq + t.n_uniq]
+    t.seg_off = d[o_seg:o_seg + t.n_uniq + 1]
+    t.perm = d[o_perm:o_perm + n]
+    t.hot = d[o_hot:o_hot + n].view(torch.float32)
+    t.base = d[o_base:o_base + n].view(torch.float32)
+    t.lens = d[o_lens:o_lens + 2 * B].view(torch.int64)
+    t.lens_host = [int(x) for x in lens]
+    return t
+
+
+def linear_rowdots(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1: Optional[torch.Tensor]):
+    """(S = W1·γ, D = W1·β + b1), fp32 [N] each."""
+    _need_cuda(w1, gamma, beta, b1)
+    N, K = w1.shape
+    w1 = w1.float().contiguous()
+    S = torch.empty(N, dtype=torch.float32, device=w1.device)
+    D = torch.empty(N, dtype=torch.float32, device=w1.device)
+    L.check(L.lib().tasu_linear_rowdots(w1.data_ptr(), w1.stride(0), gamma.float().contiguous().data_ptr(),
+                                        beta.float().contiguous().data_ptr(),
+                                        _ptr(b1.float().contiguous()) if b1 is not None else None, N, K,
+                                        S.data_ptr(), D.data_ptr(), _stream()), "tasu_linear_rowdots")
+    _count(1)
+    return S, D
+
+
+def tokrow_fwd(w1: torch.Tensor, gamma: torch.Tensor, S: torch.Tensor, D: torch.Tensor, rows: TokenRows,
+               ln_eps: float = 1e-5, want_z: bool = True):
+    """→ (z fp32 [n, Hb] | None, h bf16 [n, Hb], row_a, row_e)."""
+    _need_cuda(w1, gamma, S, D)
+    Hb, V = w1.shape
+    n = rows.n_rows
+    dev = w1.device
+    w1 = w1.float().contiguous()
+    z = torch.empty(max(n, 1), Hb, dtype=torch.float32, device=dev)[:n] if want_z else None
+    h = torch.empty(max(n, 1), Hb, dtype=torch.bfloat16, device=dev)[:n]
+    row_a = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    row_e = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    L.check(L.lib().tasu_tokrow_fwd(w1.data_ptr(), w1.stride(0), gamma.float().contiguous().data_ptr(), S.data_ptr(),
+                                    D.data_ptr(), rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(),
+                                    rows.hot.data_ptr(), rows.base.data_ptr(), rows.n_uniq, n, V, Hb, float(ln_eps),
+                                    _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(), _stream()),
+            "tasu_tokrow_fwd")
+    _count(1)
+    return z, h, row_a, row_e
+
+
+def tokrow_bwd_rows(dh: torch.Tensor, z: torch.Tensor, rows: TokenRows, row_a: torch.Tensor, row_e: torch.Tensor):
+    """→ (P fp32 [n_uniq, Hb], db1 [Hb], E [Hb])."""
+    _need_cuda(dh, z)
+    n, Hb = z.shape
+    dev = z.device
+    P = torch.empty(max(rows.n_uniq, 1), Hb, dtype=torch.float32, device=dev)
+    db1 = torch.empty(Hb, dtype=torch.float32, device=dev)
+    E = torch.empty(Hb, dtype=torch.float32, device=dev)
+    nbytes = L.lib().tasu_tokrow_bwd_workspace(Hb, rows.n_uniq)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    L.check(L.lib().tasu_tokrow_bwd_rows(dh.data_ptr(), z.data_ptr(), n, Hb, rows.seg_off.data_ptr(), rows.perm.data_ptr(),
+                                         row_a.data_ptr(), row_e.data_ptr(), rows.n_uniq, P.data_ptr(), db1.data_ptr(),
+                                         E.data_ptr(), ws.data_ptr(), nbytes, _stream()), "tasu_tokrow_bwd_rows")
+    _count(2)
+    return P, db1, E
+
+
+def tokrow_wgrad_finish(P: torch.Tensor, rows: TokenRows, w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                        E: torch.Tensor, db1: torch.Tensor):
+    """(dW1 [Hb, V], dgamma [V], dbeta [V]) in one pass over W1."""
+    Hb, V = w1.shape
+    dev = w1.device
+    w1 = w1.float().contiguous()
+    dw1 = torch.empty(Hb, V, dtype=torch.float32, device=dev)
+    dgamma = torch.empty(V, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(V, dtype=torch.float32, device=dev)
+    slot = torch.empty(V, dtype=torch.int32, device=dev)
+    L.check(L.lib().tasu_tokrow_wgrad_finish(P.data_ptr(), rows.uniq.data_ptr(), rows.n_uniq, slot.data_ptr(), w1.data_ptr(),
+                                             w1.stride(0), gamma.float().contiguous().data_ptr(),
+                                             beta.float().contiguous().data_ptr(), E.data_ptr(), db1.data_ptr(), Hb, V,
+                                             dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+            "tasu_tokrow_wgrad_finish")
+    _count(2)
+    return dw1, dgamma, dbeta

@@ -61,6 +61,7 @@ class EncoderProjectorLinearSiLU(nn.Module):
         # "fp32x3": three-term bf16 split on the same tensor cores, fp32-accurate (~1e-6), 6x the MMA work
         self.precision = "bf16"
         self._cache3 = ProjectorCache()
+        self._cache_rows = ProjectorCache()
 
     def _forward_fp32x3(self, x):
         """fp32-accurate inference path (reference numerics: fp32 LayerNorm/Linear/SiLU/Linear)."""
@@ -98,6 +99,30 @@ class EncoderProjectorLinearSiLU(nn.Module):
                 b2 = self.ffn[2].bias.detach().float().contiguous()
             return w1g, colsum, dbias, w2, b2
         return self._cache.get(params, build)
+
+    def forward_token_rows(self, rows, out_dtype=torch.float32):
+        """Projector output ``[n_rows, out_dim]`` (packed) for text-simulated rows given as descriptors
+        (``ops.TokenRows`` from ``sim``): same function as ``forward`` on the dense
+        ``ctc_pseudo_posterior[_noise]`` tensor (ps-slm.py:337-409 → projector.py:149-151), computed as a column
+        gather of W1 in fp32 instead of a GEMM over a [rows, 25055] matrix that is one-hot plus a constant."""
+        norm, l1, l2 = self.norm, self.ffn[0], self.ffn[2]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import TokenRowLinearSiLUFunction
+            return TokenRowLinearSiLUFunction.apply(rows, norm.weight, norm.bias, l1.weight, l1.bias, l2.weight,
+                                                    l2.bias, norm.eps, out_dtype)
+        params = [norm.weight, norm.bias, l1.weight, l1.bias, l2.weight, l2.bias]
+
+        def build():
+            with torch.no_grad():
+                S, D = ops.linear_rowdots(l1.weight.detach(), norm.weight.detach(), norm.bias.detach(), l1.bias.detach())
+                return S, D, cast_weight_bf16(l2.weight), l2.bias.detach().float().contiguous()
+        S, D, w2, b2 = self._cache_rows.get(params, build)
+        with torch.no_grad():
+            _, h, _, _ = ops.tokrow_fwd(l1.weight.detach(), norm.weight.detach(), S, D, rows, norm.eps, want_z=False)
+            n = rows.n_rows
+            y = torch.empty(max(n, 1), l2.weight.shape[0], dtype=out_dtype, device=h.device)[:n]
+            ops.gemm_bf16_tn(h, w2, n, l2.weight.shape[0], l1.weight.shape[0], y, L.EPI_BIAS, b2)
+        return y
 
     def forward(self, x):                  # (B, T, in_dim)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):

@@ -44,6 +44,8 @@ def draw_noise_descriptors(ids_list: Sequence[Sequence[int]], vocab_size: int, b
     """Same random stream as ``draw_noise_decisions`` but straight to flat numpy row descriptors
     ``(tok int32, hot f32, base f32, lens)`` without per-token Python objects (the host side of a training step
     must not dominate it).  Falls back to the list algorithm only for utterances that get inserts."""
+    if int(max((len(i) for i in ids_list), default=0) * insert_prob) == 0:
+        return _draw_noise_descriptors_batched(ids_list, vocab_size, drop_prob, smooth_low, smooth_high)
     toks, hots, bases, lens = [], [], [], []
     for ids in ids_list:
         alpha = torch.empty(()).uniform_(smooth_low, smooth_high).item()
@@ -69,6 +71,42 @@ def draw_noise_descriptors(ids_list: Sequence[Sequence[int]], vocab_size: int, b
         toks.append(tok); hots.append(hot); bases.append(base); lens.append(int(tok.shape[0]))
     cat = (lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt))
     return cat(toks, np.int32), cat(hots, np.float32), cat(bases, np.float32), lens
+
+
+def _draw_noise_descriptors_batched(ids_list, vocab_size: int, drop_prob: float, smooth_low: float, smooth_high: float):
+    """No-insert case (the shipped default, insert_prob=0): ONE ``torch.rand`` call for the whole batch.
+    torch's CPU generator hands out one 24-bit draw per fp32 uniform in call order, so ``rand(sum(L_b + 1))`` is
+    the same stream as the reference's per-utterance ``uniform_()`` (:384) + ``rand(L_b)`` (:387) sequence
+    (checked bit for bit in tests/test_oracle_vs_reference.py); ``uniform_(lo, hi)`` is ``u·(hi − lo) + lo`` in fp32."""
+    lens_in = np.fromiter((len(i) for i in ids_list), dtype=np.int64, count=len(ids_list))
+    B = lens_in.shape[0]
+    total = int(lens_in.sum()) + B
+    u = torch.rand(total).numpy()
+    starts = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens_in + 1, out=starts[1:])
+    lo, hi = np.float32(smooth_low), np.float32(smooth_high)
+    alpha = (u[starts[:-1]] * (hi - lo) + lo).astype(np.float32).astype(np.float64)      # .item() → python float
+    is_alpha = np.zeros(total, dtype=bool)
+    is_alpha[starts[:-1]] = True
+    keep = u[~is_alpha] > np.float32(drop_prob)
+    tok_all = (np.concatenate([np.asarray(i, dtype=np.int32) for i in ids_list]) if total > B
+               else np.zeros(0, dtype=np.int32))
+    utt = np.repeat(np.arange(B), lens_in)
+    tok = tok_all[keep]
+    utt_k = utt[keep]
+    lens = np.bincount(utt_k, minlength=B).astype(np.int64) if B else np.zeros(0, dtype=np.int64)
+    a32 = (1.0 - alpha).astype(np.float32)                      # python double → fp32 scalar, as torch does (:385)
+    c32 = (alpha / vocab_size).astype(np.float32)
+    h32 = (a32 + c32).astype(np.float32)
+    return tok, h32[utt_k], c32[utt_k], [int(x) for x in lens]
+
+
+def clean_descriptors(ids_list: Sequence[Sequence[int]]):
+    """Descriptors of the clean one-hot simulator (ps-slm.py:337-358): hot = 1, base = 0."""
+    lens = [len(i) for i in ids_list]
+    n = sum(lens)
+    tok = (np.concatenate([np.asarray(i, dtype=np.int32) for i in ids_list]) if n else np.zeros(0, dtype=np.int32))
+    return tok, np.ones(n, dtype=np.float32), np.zeros(n, dtype=np.float32), lens
 
 
 def soft_row_values(alpha: float, vocab_size: int) -> Tuple[np.float32, np.float32]:
