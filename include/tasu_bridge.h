@@ -286,6 +286,27 @@ int tasu_tokrow_wgrad_finish(const float* P, const int32_t* uniq, int n_uniq, in
                              const float* db1, int Hb, int V, float* dw1, int64_t dw1_stride, float* dgamma,
                              float* dbeta, void* stream);
 
+/* Composite calls (one per direction of a text-only training step; the launches go out back to back):
+ *   fwd: tasu_linear_rowdots → tasu_tokrow_fwd → bf16 cast of W2 → tasu_gemm_bf16_tn(EPI_BIAS)   → y [n_rows, H]
+ *   bwd: db2, dW2 = dy^T·h, dh = dy·W2 (tensor cores) → tasu_tokrow_bwd_rows → tasu_tokrow_wgrad_finish
+ * z / h_bf16 / row_a / row_e are the activations saved between the two calls; `workspace` (256-byte aligned,
+ * tasu_tokrow_train_workspace bytes) is scratch and may be shared by both calls. */
+int64_t tasu_tokrow_train_workspace(int64_t n_rows, int n_uniq, int V, int Hb, int H);
+int tasu_tokrow_linear_silu_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                                const float* b1, const float* w2, int64_t w2_stride, const float* b2,
+                                const int32_t* uniq, const int32_t* seg_off, const int32_t* perm,
+                                const float* hot, const float* base, int n_uniq, int64_t n_rows, int V, int Hb,
+                                int H, float ln_eps, float* z, void* h_bf16, float* row_a, float* row_e,
+                                void* y, int y_dtype, int64_t ldy, void* workspace, int64_t workspace_bytes,
+                                void* stream);
+int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t ldy, const float* z, const void* h_bf16,
+                                const float* row_a, const float* row_e, const float* w1, int64_t w1_stride,
+                                const float* gamma, const float* beta, const float* w2, int64_t w2_stride,
+                                const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, int n_uniq,
+                                int64_t n_rows, int V, int Hb, int H, float* dw1, int64_t dw1_stride,
+                                float* dgamma, float* dbeta, float* db1, float* dw2, int64_t dw2_stride,
+                                float* db2, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.
  *   input_ids [B,S] int64; attention_mask [B,S] uint8/bool (mask_dtype 0) or int64 (1);

@@ -78,40 +78,21 @@ class TokenRowLinearSiLUFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rows, gamma, beta, w1, b1, w2, b2, eps, out_dtype):
-        Hb, H = w1.shape[0], w2.shape[0]
-        n = rows.n_rows
-        dev = w1.device
-        S, D = ops.linear_rowdots(w1.detach(), gamma.detach(), beta.detach(), b1.detach())
-        z, h, row_a, row_e = ops.tokrow_fwd(w1.detach(), gamma.detach(), S, D, rows, eps, want_z=True)
-        w2b = cast_weight_bf16(w2)
-        y = torch.empty(max(n, 1), H, dtype=out_dtype, device=dev)[:n]
-        ops.gemm_bf16_tn(h, w2b, n, H, Hb, y, L.EPI_BIAS, b2.detach().float().contiguous())
+        ws = ops.tokrow_train_workspace(rows, w1.shape[0], w2.shape[0], w1.device)
+        y, z, h, row_a, row_e = ops.tokrow_linear_silu_fwd(rows, gamma, beta, w1, b1, w2, b2, eps, out_dtype, ws)
         ctx.save_for_backward(z, h, row_a, row_e, gamma, beta, w1, w2)
-        ctx.rows = rows
+        ctx.rows, ctx.ws = rows, ws
         return y
 
     @staticmethod
     def backward(ctx, dy):
         z, h, row_a, row_e, gamma, beta, w1, w2 = ctx.saved_tensors
-        rows = ctx.rows
-        N = rows.n_rows
-        Hb, V = w1.shape
-        H = w2.shape[0]
-        dev = dy.device
         dy = dy.contiguous()
         if dy.dtype not in (torch.float32, torch.bfloat16):
             dy = dy.float()
-        db2 = ops.colsum(dy)
-        dyb, _, _ = ops.cast_rows(dy, torch.bfloat16) if dy.dtype != torch.bfloat16 else (dy, None, None)
-        dyT = ops.transpose_cast(dy, N, H)                        # [H, N]
-        hT = ops.transpose_cast(h, N, Hb)                         # [Hb, N]
-        dw2 = torch.empty(H, Hb, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_tn(dyT, hT, H, Hb, N, dw2)                  # dW2 = dyᵀ·h
-        w2T = ops.transpose_cast(w2.detach(), H, Hb)              # [Hb, H]
-        dh = torch.empty(max(N, 1), Hb, dtype=torch.float32, device=dev)[:N]
-        ops.gemm_bf16_tn(dyb, w2T, N, Hb, H, dh)                  # dh = dy·W2
-        P, db1, E = ops.tokrow_bwd_rows(dh, z, rows, row_a, row_e)
-        dw1, dgamma, dbeta = ops.tokrow_wgrad_finish(P, rows, w1.detach(), gamma.detach(), beta.detach(), E, db1)
+        dgamma, dbeta, dw1, db1, dw2, db2 = ops.tokrow_linear_silu_bwd(dy, ctx.rows, z, h, row_a, row_e, gamma, beta,
+                                                                       w1, w2, ctx.ws)
+        ctx.ws = None
         return (None, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), dw1.to(w1.dtype), db1.to(w1.dtype),
                 dw2.to(w2.dtype), db2.to(w2.dtype), None, None)
 

@@ -78,26 +78,63 @@ def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_
                               left_padding=int(hdr[L.SH_LEFT_PADDING]))
 
 
+_PINNED_HDR = []
+
+
+def _pinned_header():
+    """Small ring of pinned host header buffers (UVA-mapped: the plan kernels write them directly)."""
+    if not _PINNED_HDR:
+        _PINNED_HDR.extend([[torch.zeros(L.SH_WORDS, dtype=torch.int64).pin_memory() for _ in range(8)], 0])
+    ring = _PINNED_HDR[0]
+    _PINNED_HDR[1] = (_PINNED_HDR[1] + 1) % len(ring)
+    return ring[_PINNED_HDR[1]]
+
+
+class PendingSplicePlan:
+    """Splice plan whose header lands in pinned host memory; ``finish()`` waits for the plan kernels only, so work
+    enqueued after ``begin_splice_plan`` (e.g. the projector) keeps the GPU busy while the host reads S'."""
+    __slots__ = ("plan", "header", "event", "attention_mask", "n_audio")
+
+    def finish(self):
+        self.event.synchronize()
+        hdr = self.header.clone()
+        _raise_splice_errors(hdr, self.attention_mask, self.n_audio)
+        self.plan.left_padding = int(hdr[L.SH_LEFT_PADDING])
+        return self.plan, int(hdr[L.SH_SPLICED_LEN])
+
+
+def begin_splice_plan(input_ids: torch.Tensor, attention_mask: torch.Tensor, num_audio_tokens: torch.Tensor,
+                      speech_id: int, div_k: int = 1) -> PendingSplicePlan:
+    """Integer part of step 4 (ps-slm.py:765-812, :842-865), enqueued early."""
+    pend = PendingSplicePlan()
+    pend.header = _pinned_header()
+    pend.plan = ops.splice_rowstat(input_ids, attention_mask, speech_id)
+    ops.splice_plan(pend.plan, num_audio_tokens, div_k, header=pend.header)
+    pend.event = torch.cuda.Event()
+    pend.event.record()
+    pend.attention_mask, pend.n_audio = attention_mask, num_audio_tokens.numel()
+    return pend
+
+
 def merge_packed_audio_rows(audio_rows: torch.Tensor, num_audio_tokens: torch.Tensor, max_audio_tokens: int,
                             text_src: torch.Tensor, text_mode: int, input_ids: torch.Tensor,
                             attention_mask: torch.Tensor, labels: Optional[torch.Tensor], speech_id: int, pad_id: int,
-                            ignore_id: int = -100):
+                            ignore_id: int = -100, pending: Optional[PendingSplicePlan] = None):
     """Step 4 on PACKED audio rows ``[sum M_b, H]`` (no [B, max M_b, H] padding in between); ``text_src`` is the
     embedding table (``text_mode=1``: embed_tokens lookup fused, ps-slm.py:525,654) or ``inputs_embeds``
     (``text_mode=0``).  Same 5-tuple and ValueErrors as ``_merge_input_ids_with_audio_features``
-    (ps-slm.py:679-873); differentiable w.r.t. ``audio_rows``."""
+    (ps-slm.py:679-873); differentiable w.r.t. ``audio_rows``.  ``pending``: a plan begun before the audio rows
+    were computed (``begin_splice_plan``)."""
     if audio_rows.dtype != text_src.dtype:
         audio_rows = audio_rows.to(text_src.dtype)
-    p = ops.splice_rowstat(input_ids, attention_mask, speech_id)
-    ops.splice_plan(p, num_audio_tokens, 1)
-    hdr = p.header.cpu()
-    _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
-    p.left_padding = int(hdr[L.SH_LEFT_PADDING])
+    if pending is None:
+        pending = begin_splice_plan(input_ids, attention_mask, num_audio_tokens, speech_id)
+    p, spliced_len = pending.finish()
     if torch.is_grad_enabled() and audio_rows.requires_grad:
         from .autograd import SpliceFunction
-        return SpliceFunction.apply(audio_rows, p, int(hdr[L.SH_SPLICED_LEN]), text_src.detach(), text_mode, 0,
+        return SpliceFunction.apply(audio_rows, p, spliced_len, text_src.detach(), text_mode, 0,
                                     max_audio_tokens, labels, pad_id, ignore_id)
-    return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), text_src, text_mode, audio_rows, 0, max_audio_tokens,
+    return ops.splice_scatter(p, spliced_len, text_src, text_mode, audio_rows, 0, max_audio_tokens,
                               labels, pad_id, ignore_id, left_padding=p.left_padding)
 
 

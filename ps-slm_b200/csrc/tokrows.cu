@@ -161,20 +161,27 @@ tokrow_bwd_rows_kernel(const float* __restrict__ dh, const float* __restrict__ z
     }
 }
 
-// out0[c] = Σ_p part[p][0][c], out1[c] = Σ_p part[p][1][c]  (p ascending: a fixed summation order)
-__global__ void __launch_bounds__(256)
+// out0[c] = Σ_p part[p][0][c], out1[c] = Σ_p part[p][1][c] in a fixed order: CTA = 32 columns x 32 warps, warp w sums
+// p = w, w+32, ... (all loads independent), then the 32 warp sums are combined in warp order.
+__global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out0, float* __restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * C) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int p = 0;
-    for (; p + 3 < n_parts; p += 4) {
-        a0 += part[(int64_t)p * 2 * C + c]; a1 += part[(int64_t)(p + 1) * 2 * C + c];
-        a2 += part[(int64_t)(p + 2) * 2 * C + c]; a3 += part[(int64_t)(p + 3) * 2 * C + c];
+    __shared__ float s[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < 2 * C) {
+        int p = warp;
+        for (; p + 32 < n_parts; p += 64) { a0 += part[(int64_t)p * 2 * C + c]; a1 += part[(int64_t)(p + 32) * 2 * C + c]; }
+        if (p < n_parts) a0 += part[(int64_t)p * 2 * C + c];
     }
-    for (; p < n_parts; ++p) a0 += part[(int64_t)p * 2 * C + c];
-    const float r = (a0 + a1) + (a2 + a3);
-    if (c < C) out0[c] = r; else out1[c - C] = r;
+    s[warp][lane] = a0 + a1;
+    __syncthreads();
+    if (warp == 0 && c < 2 * C) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) r += s[w][lane];
+        if (c < C) out0[c] = r; else out1[c - C] = r;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -347,7 +354,7 @@ extern "C" int tasu_tokrow_bwd_rows(const float* dh, const float* z, int64_t n_r
     if (chunks == 1) LAUNCH(1); else if (chunks == 2) LAUNCH(2); else if (chunks == 3) LAUNCH(3); else LAUNCH(4);
 #undef LAUNCH
     TASU_CHECK_LAUNCH();
-    reduce_partials_kernel<<<(2 * Hb + 255) / 256, 256, 0, st>>>(part, (int)grid, Hb, db1, E);
+    reduce_partials_kernel<<<(2 * Hb + 31) / 32, 1024, 0, st>>>(part, (int)grid, Hb, db1, E);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
@@ -365,5 +372,120 @@ extern "C" int tasu_tokrow_wgrad_finish(const float* P, const int32_t* uniq, int
     tokrow_wgrad_finish_kernel<<<(unsigned)((V + 31) / 32), 256, 0, st>>>(P, slot_ws, w1, w1_stride, gamma, beta, E, db1, Hb, V,
                                                                          dw1, dw1_stride, dgamma, dbeta);
     TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Composite entry points: the whole projector forward / backward of a text-only step behind ONE call each, so the
+// host (Python) issues two calls instead of ~25 and the launches go out back to back.
+static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
+static inline int64_t pad_to(int64_t n, int64_t a) { return (n + a - 1) / a * a; }
+
+struct TrainWs {
+    int64_t S, D, w2b, dyb, dyT, hT, w2T, dh, P, part, E, slot, total;
+};
+static TrainWs train_ws(int64_t n, int n_uniq, int V, int Hb, int H) {
+    TrainWs w;
+    int64_t o = 0;
+    w.S = o; o += al256(4LL * Hb);
+    w.D = o; o += al256(4LL * Hb);
+    w.w2b = o; o += al256(2LL * H * pad_to(Hb, 64));
+    w.dyb = o; o += al256(2LL * (n > 0 ? n : 1) * pad_to(H, 8));
+    w.dyT = o; o += al256(2LL * H * pad_to(n > 0 ? n : 1, 8));
+    w.hT = o; o += al256(2LL * Hb * pad_to(n > 0 ? n : 1, 8));
+    w.w2T = o; o += al256(2LL * Hb * pad_to(H, 8));
+    w.dh = o; o += al256(4LL * (n > 0 ? n : 1) * Hb);
+    w.P = o; o += al256(4LL * (n_uniq > 0 ? n_uniq : 1) * Hb);
+    w.part = o; o += al256(tasu_tokrow_bwd_workspace(Hb, n_uniq) + 16);
+    w.E = o; o += al256(4LL * Hb);
+    w.slot = o; o += al256(4LL * V);
+    w.total = o;
+    return w;
+}
+
+extern "C" int64_t tasu_tokrow_train_workspace(int64_t n_rows, int n_uniq, int V, int Hb, int H) {
+    if (n_rows < 0 || n_uniq < 0 || V <= 0 || Hb <= 0 || H <= 0) return 0;
+    return train_ws(n_rows, n_uniq, V, Hb, H).total;
+}
+
+#define TASU_TRY(expr) do { int rc__ = (expr); if (rc__ != TASU_OK) return rc__; } while (0)
+
+extern "C" int tasu_tokrow_linear_silu_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
+                                           const float* b1, const float* w2, int64_t w2_stride, const float* b2,
+                                           const int32_t* uniq, const int32_t* seg_off, const int32_t* perm,
+                                           const float* hot, const float* base, int n_uniq, int64_t n_rows, int V, int Hb,
+                                           int H, float ln_eps, float* z, void* h_bf16, float* row_a, float* row_e,
+                                           void* y, int y_dtype, int64_t ldy, void* workspace, int64_t workspace_bytes,
+                                           void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && n_uniq >= 0 && V > 0 && Hb > 0 && H > 0, "shape");
+    if (n_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(workspace && ((uintptr_t)workspace % 256 == 0), "workspace must be 256-byte aligned");
+    const TrainWs ws = train_ws(n_rows, n_uniq, V, Hb, H);
+    TASU_CHECK_ARG(workspace_bytes >= ws.total, "workspace too small (tasu_tokrow_train_workspace)");
+    TASU_CHECK_ARG(w2 && b2 && y, "null pointer");
+    char* wsb = (char*)workspace;
+    float* S = (float*)(wsb + ws.S);
+    float* D = (float*)(wsb + ws.D);
+    void* w2b = wsb + ws.w2b;
+    const int64_t ldw2 = pad_to(Hb, 64);
+    TASU_TRY(tasu_linear_rowdots(w1, w1_stride, gamma, beta, b1, Hb, V, S, D, stream));
+    TASU_TRY(tasu_tokrow_fwd(w1, w1_stride, gamma, S, D, uniq, seg_off, perm, hot, base, n_uniq, n_rows, V, Hb, ln_eps, z, h_bf16,
+                             row_a, row_e, stream));
+    TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
+    TASU_TRY(tasu_gemm_bf16_tn(h_bf16, Hb, w2b, ldw2, y, y_dtype, ldy, (int)n_rows, H, Hb, TASU_EPI_BIAS, b2, nullptr, nullptr,
+                               nullptr, nullptr, stream));
+    return TASU_OK;
+}
+
+extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t ldy, const float* z, const void* h_bf16,
+                                           const float* row_a, const float* row_e, const float* w1, int64_t w1_stride,
+                                           const float* gamma, const float* beta, const float* w2, int64_t w2_stride,
+                                           const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, int n_uniq,
+                                           int64_t n_rows, int V, int Hb, int H, float* dw1, int64_t dw1_stride,
+                                           float* dgamma, float* dbeta, float* db1, float* dw2, int64_t dw2_stride,
+                                           float* db2, void* workspace, int64_t workspace_bytes, void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && n_uniq >= 0 && V > 0 && Hb > 0 && H > 0, "shape");
+    TASU_CHECK_ARG(dw1 && dgamma && dbeta && db1 && dw2 && db2, "null gradient pointer");
+    TASU_CHECK_ARG(dy_dtype == TASU_F32 || dy_dtype == TASU_BF16, "dy_dtype");
+    TASU_CHECK_ARG(workspace && ((uintptr_t)workspace % 256 == 0), "workspace must be 256-byte aligned");
+    const TrainWs ws = train_ws(n_rows, n_uniq, V, Hb, H);
+    TASU_CHECK_ARG(workspace_bytes >= ws.total, "workspace too small (tasu_tokrow_train_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wsb = (char*)workspace;
+    if (n_rows == 0) {                                      // no rows: every gradient is zero
+        TASU_CHECK_CUDA(cudaMemsetAsync(db1, 0, 4LL * Hb, st));
+        TASU_CHECK_CUDA(cudaMemsetAsync(db2, 0, 4LL * H, st));
+        TASU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, 4LL * V, st));
+        TASU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, 4LL * V, st));
+        TASU_CHECK_CUDA(cudaMemset2DAsync(dw1, 4 * dw1_stride, 0, 4LL * V, Hb, st));
+        TASU_CHECK_CUDA(cudaMemset2DAsync(dw2, 4 * dw2_stride, 0, 4LL * Hb, H, st));
+        return TASU_OK;
+    }
+    const int64_t ldn = pad_to(n_rows, 8), ldh8 = pad_to(H, 8);
+    void* dyb = wsb + ws.dyb;
+    void* dyT = wsb + ws.dyT;
+    void* hT = wsb + ws.hT;
+    void* w2T = wsb + ws.w2T;
+    float* dh = (float*)(wsb + ws.dh);
+    float* P = (float*)(wsb + ws.P);
+    float* E = (float*)(wsb + ws.E);
+    TASU_TRY(tasu_colsum(dy, dy_dtype, n_rows, H, ldy, db2, stream));
+    const void* dy_bf16 = dy;
+    int64_t ld_dyb = ldy;
+    if (dy_dtype != TASU_BF16 || (ldy * 2) % 16 != 0 || (uintptr_t)dy % 16 != 0) {
+        TASU_TRY(tasu_cast_rows(dy, dy_dtype, n_rows, H, ldy, dyb, TASU_BF16, ldh8, nullptr, nullptr, 0.f, stream));
+        dy_bf16 = dyb; ld_dyb = ldh8;
+    }
+    TASU_TRY(tasu_transpose_cast(dy, dy_dtype, n_rows, H, ldy, nullptr, dyT, ldn, stream));          // [H, N]
+    TASU_TRY(tasu_transpose_cast(h_bf16, TASU_BF16, n_rows, Hb, Hb, nullptr, hT, ldn, stream));       // [Hb, N]
+    TASU_TRY(tasu_gemm_bf16_tn(dyT, ldn, hT, ldn, dw2, TASU_F32, dw2_stride, H, Hb, (int)n_rows, TASU_EPI_NONE, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, stream));                                    // dW2 = dy^T · h
+    TASU_TRY(tasu_transpose_cast(w2, TASU_F32, H, Hb, w2_stride, nullptr, w2T, ldh8, stream));         // [Hb, H]
+    TASU_TRY(tasu_gemm_bf16_tn(dy_bf16, ld_dyb, w2T, ldh8, dh, TASU_F32, Hb, (int)n_rows, Hb, H, TASU_EPI_NONE, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, stream));                                    // dh = dy · W2
+    TASU_TRY(tasu_tokrow_bwd_rows(dh, z, n_rows, Hb, seg_off, perm, row_a, row_e, n_uniq, P, db1, E, wsb + ws.part,
+                                  ws.E - ws.part, stream));
+    TASU_TRY(tasu_tokrow_wgrad_finish(P, uniq, n_uniq, (int32_t*)(wsb + ws.slot), w1, w1_stride, gamma, beta, E, db1, Hb, V, dw1,
+                                      dw1_stride, dgamma, dbeta, stream));
     return TASU_OK;
 }

@@ -206,11 +206,13 @@ class slam_model_asr(nn.Module):
             else:
                 desc = _sim.clean_descriptors(ids_list)
             rows = _ops.group_token_rows(*desc, V, input_ids.device)
+            feat_len = rows.lens // self.encoder_projector.k
+            pending = _bridge.begin_splice_plan(input_ids, attention_mask, feat_len, self.tokenizer.default_speech_token)
             audio = self.encoder_projector.forward_token_rows(rows, out_dtype=table.dtype)
             emb, mask, out_labels, pos, _ = _bridge.merge_packed_audio_rows(
-                audio, rows.lens // self.encoder_projector.k, max(rows.lens_host, default=0), table, 1, input_ids,
+                audio, feat_len, max(rows.lens_host, default=0), table, 1, input_ids,
                 attention_mask, labels, self.tokenizer.default_speech_token, self.tokenizer.pad_token_id,
-                self.tokenizer.default_ignore_token)
+                self.tokenizer.default_ignore_token, pending=pending)
             return emb, mask, out_labels, pos
         if raw_encoder_out is not None:                        # None on the text-only branch (encoder skipped)
             encoder_out = raw_encoder_out[:, 4:, :]

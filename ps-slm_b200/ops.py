@@ -603,3 +603,71 @@ def tokrow_wgrad_finish(P: torch.Tensor, rows: TokenRows, w1: torch.Tensor, gamm
             "tasu_tokrow_wgrad_finish")
     _count(2)
     return dw1, dgamma, dbeta
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+_TOKROW_WS = {}     # device → grow-only scratch buffer (stream-ordered reuse; holds no state between calls)
+
+
+def _cap_rows(n: int, q: int = 2048) -> int:
+    """Data-dependent row counts are rounded up for allocation so the caching allocator sees a few distinct sizes."""
+    return max(q, (n + q - 1) // q * q)
+
+
+def tokrow_train_workspace(rows: TokenRows, Hb: int, H: int, device) -> torch.Tensor:
+    nbytes = L.lib().tasu_tokrow_train_workspace(_cap_rows(rows.n_rows), _cap_rows(rows.n_uniq), rows.V, Hb, H)
+    key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    ws = _TOKROW_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _TOKROW_WS[key] = None
+        ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=device)
+        _TOKROW_WS[key] = ws
+    return ws
+
+
+def tokrow_linear_silu_fwd(rows: TokenRows, gamma, beta, w1, b1, w2, b2, eps: float, out_dtype, ws: torch.Tensor,
+                           want_z: bool = True):
+    """Composite forward (tasu_tokrow_linear_silu_fwd) → (y [n, H], z fp32 [n, Hb] | None, h bf16, row_a, row_e)."""
+    _need_cuda(w1, w2)
+    Hb, V = w1.shape
+    H = w2.shape[0]
+    n, dev = rows.n_rows, w1.device
+    w1, w2, gamma, beta, b1, b2 = _f32c(w1), _f32c(w2), _f32c(gamma), _f32c(beta), _f32c(b1), _f32c(b2)
+    cap = _cap_rows(n)
+    z = torch.empty(cap, Hb, dtype=torch.float32, device=dev)[:n] if want_z else None
+    h = torch.empty(cap, Hb, dtype=torch.bfloat16, device=dev)[:n]
+    ab = torch.empty(2, cap, dtype=torch.float32, device=dev)
+    y = torch.empty(cap, H, dtype=out_dtype, device=dev)[:n]
+    L.check(L.lib().tasu_tokrow_linear_silu_fwd(
+        w1.data_ptr(), w1.stride(0), gamma.data_ptr(), beta.data_ptr(), b1.data_ptr(), w2.data_ptr(), w2.stride(0),
+        b2.data_ptr(), rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(), rows.hot.data_ptr(),
+        rows.base.data_ptr(), rows.n_uniq, n, V, Hb, H, float(eps), _ptr(z), h.data_ptr(), ab[0].data_ptr(),
+        ab[1].data_ptr(), y.data_ptr(), _dt(y), H, ws.data_ptr(), ws.numel(), _stream()), "tasu_tokrow_linear_silu_fwd")
+    _count(4)
+    return y, z, h, ab[0], ab[1]
+
+
+def tokrow_linear_silu_bwd(dy: torch.Tensor, rows: TokenRows, z, h, row_a, row_e, gamma, beta, w1, w2, ws: torch.Tensor):
+    """Composite backward (tasu_tokrow_linear_silu_bwd) → (dgamma, dbeta, dW1, db1, dW2, db2), all fp32."""
+    Hb, V = w1.shape
+    H = w2.shape[0]
+    n, dev = rows.n_rows, w1.device
+    w1, w2, gamma, beta = _f32c(w1), _f32c(w2), _f32c(gamma), _f32c(beta)
+    dw1 = torch.empty(Hb, V, dtype=torch.float32, device=dev)
+    dw2 = torch.empty(H, Hb, dtype=torch.float32, device=dev)
+    Vp, Hbp = pad_to(V), pad_to(Hb)                                  # one allocation, 256-byte aligned slices
+    vecs = torch.empty(2 * Vp + Hbp + H, dtype=torch.float32, device=dev)
+    dgamma, dbeta, db1, db2 = vecs[:V], vecs[Vp:Vp + V], vecs[2 * Vp:2 * Vp + Hb], vecs[2 * Vp + Hbp:]
+    L.check(L.lib().tasu_tokrow_linear_silu_bwd(
+        dy.data_ptr(), _dt(dy), dy.stride(0) if n > 1 else H, _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(),
+        w1.data_ptr(), w1.stride(0), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), w2.stride(0),
+        rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(), rows.n_uniq, n, V, Hb, H,
+        dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), db1.data_ptr(), dw2.data_ptr(), Hb, db2.data_ptr(),
+        ws.data_ptr(), ws.numel(), _stream()), "tasu_tokrow_linear_silu_bwd")
+    _count(12)
+    return dgamma, dbeta, dw1, db1, dw2, db2

@@ -32,6 +32,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import ps_slm_b200.bridge as bridge
     import ps_slm_b200.dist as D
     import ps_slm_b200.ops as ops
     import ps_slm_b200.projector as P
@@ -64,19 +65,18 @@ def main():
         timers["host_sim"] += time.perf_counter() - t0
         if args.dense:
             rows, mean, rstd, lens = sim.build_packed_bf16(dec, V, dev)
+            pend = bridge.begin_splice_plan(input_ids, mask, lens, S.SPEECH_ID)
             y = linear_silu_train_rows(proj, rows, mean, rstd, rows.shape[0], torch.float32)
-            lmax = int(lens.max())
+            lmax = max(dec[3])
         else:
             t1 = time.perf_counter()
             tr = ops.group_token_rows(*dec, V, dev)
             timers["host_sim"] += time.perf_counter() - t1
+            pend = bridge.begin_splice_plan(input_ids, mask, tr.lens, S.SPEECH_ID)
             y = proj.forward_token_rows(tr, torch.float32)
             lens, lmax = tr.lens, max(tr.lens_host)
-        sp = ops.splice_rowstat(input_ids, mask, S.SPEECH_ID)
-        ops.splice_plan(sp, lens, 1)
-        hdr = sp.header.cpu()
-        sp.left_padding = int(hdr[1])
-        emb, _, _, _, _ = SpliceFunction.apply(y, sp, int(hdr[0]), table, 1, 0, lmax, labels, S.PAD_ID, S.IGNORE_ID)
+        emb, _, _, _, _ = bridge.merge_packed_audio_rows(y, lens, lmax, table, 1, input_ids, mask, labels, S.SPEECH_ID,
+                                                         S.PAD_ID, S.IGNORE_ID, pending=pend)
         # synthetic upstream gradient dL/d(inputs_embeds) ~ N(0,1): a window of a pre-generated pool (the LLM that
         # would produce it is outside the bridge; generating 0.3 GB of normals per step is not part of the path)
         off = (i * 4099) % 65536
