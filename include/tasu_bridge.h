@@ -271,12 +271,27 @@ int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_stride, int 
  */
 int tasu_host_group_tokens(const int32_t* tok_host, int64_t n_rows, int V, int32_t* uniq_host,
                            int32_t* seg_off_host, int32_t* perm_host, int32_t* n_uniq_host);
+/* HOST: all of ctc_pseudo_posterior_noise's decisions (ps-slm.py:380-401, insert_prob = 0) from ONE uniform draw
+ * u = torch.rand(sum(L_b) + B) — bit-identical to the reference's per-utterance uniform_()/rand(L_b) stream — written
+ * as grouped row descriptors into a (pinned) staging buffer; layout in int32 words with cap = sum(L_b):
+ * uniq[cap] | seg_off[cap+1] | perm[cap] | hot[cap] (f32) | base[cap] (f32) | pad to 8 B | lens[B] (int64). */
+int tasu_host_sim_token_rows(const float* u_host, const int32_t* tok_in_host, const int64_t* len_in_host, int B,
+                             int V, float drop_prob, float smooth_low, float smooth_high, int32_t* stage_host,
+                             int64_t stage_words, int64_t* n_rows_host, int32_t* n_uniq_host);
 int tasu_linear_rowdots(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
                         const float* b1, int N, int K, float* S, float* D, void* stream);
 int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* S, const float* D,
                     const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, const float* hot,
                     const float* base, int n_uniq, int64_t n_rows, int V, int Hb, float ln_eps, float* z,
-                    void* h_bf16, float* row_a, float* row_e, void* stream);
+                    void* h_bf16, float* row_a, float* row_e,
+                    const float* colT /*optional [n_uniq, Hb] from tasu_tokrow_cols; NULL: gather W1 columns*/,
+                    void* stream);
+/* training forward (W1 changes every step): ONE dense pass over W1 gives S, D and the compact gamma-scaled
+ * columns colT[u,:] = gamma[uniq[u]]*W1[:,uniq[u]] (every sector of W1 read once instead of one sector per element) */
+int64_t tasu_tokrow_cols_workspace(int V, int Hb);
+int tasu_tokrow_cols(const float* w1, int64_t w1_stride, const float* gamma, const float* beta, const float* b1,
+                     const int32_t* uniq, int n_uniq, int V, int Hb, float* colT, float* S, float* D,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 int64_t tasu_tokrow_bwd_workspace(int Hb, int n_uniq);    /* bytes of per-CTA partial sums (deterministic db1 / E) */
 int tasu_tokrow_bwd_rows(const float* dh, const float* z, int64_t n_rows, int Hb, const int32_t* seg_off,
                          const int32_t* perm, const float* row_a, const float* row_e, int n_uniq, float* P,
@@ -316,7 +331,8 @@ int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t ldy, const
  * tasu_splice_plan    : placeholders, cumsum, per-token slot ordinals    (:805-812, :842-859)
  * tasu_splice_header  : S', padding side, error words, per-row bases     (:809, :861)
  * (the caller reads the header — S', padding side, error words — and passes them back by value)
- * tasu_splice_scatter : writes inputs_embeds / mask / labels / position_ids / final ids
+ * tasu_splice_scatter : row-map pass (integer outputs + source of every output row) and one pure copy pass:
+ *                       writes inputs_embeds / mask / labels / position_ids / final ids
  *                       (:821-840, :867-871); text rows come from `text_src`:
  *                       text_mode 0 = inputs_embeds [B,S,H]; 1 = embedding table indexed by
  *                       token id (fuses embed_tokens, ps-slm.py:525,654).
@@ -340,15 +356,13 @@ int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, in
                         const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
                         int left_padding, int64_t pad_id, int64_t ignore_id,
                         void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
-                        int64_t* out_ids, void* stream);
-/* backward of the audio part of the splice: grad_audio[a,:] = grad_emb[slot(a),:] (training) */
-int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const int64_t* input_ids,
-                           const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
-                           int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
-                           const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
-                           const int32_t* audio_off, int left_padding, int audio_layout,
-                           int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
-                           void* grad_audio, void* stream);
+                        int64_t* out_ids, int64_t* row_src_ws /*[B*S'] scratch: source of every output row*/,
+                        int32_t* audio_dest /*optional: output row of every audio row; caller pre-fills -1*/,
+                        void* stream);
+/* dst[r,:] = idx[r] >= 0 ? src[idx[r],:] : 0.  With idx = audio_dest of tasu_splice_scatter and src = the gradient of
+ * inputs_embeds this is the backward of the audio part of the splice (index_put of ps-slm.py:867-869; training). */
+int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stride, const int32_t* idx, int64_t n_rows, int H,
+                     void* dst, int64_t dst_row_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,8 +47,11 @@ SIGNATURES = {
     "tasu_split_bf16x3": (_I, [_P, _I, _L, _I, _L, _P, _I, _P, _L, _P, _P, _F, _P, _P]),
     "tasu_sum_epilogue": (_I, [_P, _I, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _P]),
     "tasu_host_group_tokens": (_I, [_P, _L, _I, _P, _P, _P, _P]),
+    "tasu_host_sim_token_rows": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _L, _P, _P]),
     "tasu_linear_rowdots": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _P, _P]),
-    "tasu_tokrow_fwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "tasu_tokrow_fwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "tasu_tokrow_cols_workspace": (_L, [_I, _I]),
+    "tasu_tokrow_cols": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
     "tasu_tokrow_bwd_workspace": (_L, [_I, _I]),
     "tasu_tokrow_bwd_rows": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P]),
     "tasu_tokrow_wgrad_finish": (_I, [_P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
@@ -61,9 +64,8 @@ SIGNATURES = {
     "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),
     "tasu_splice_scatter": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _L, _L, _I, _I,
-                                 _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P]),
-    "tasu_splice_audio_grad": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _I,
-                                    _I, _L, _L, _I, _P, _P]),
+                                 _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_gather_rows": (_I, [_P, _I, _L, _P, _L, _I, _P, _L, _P]),
 }
 
 _lib = None

@@ -10,7 +10,7 @@ The reference trains the projector with plain autograd through nn.LayerNorm / nn
   dW1/dγ/dβ from G by the LayerNorm-fold algebra (no third big GEMM), db1, db2.  The input (a
   posterior) never needs a gradient.
 * ``SpliceFunction``      — forward: tasu_splice_scatter; backward: gather of the upstream gradient at
-  the audio slots (tasu_splice_audio_grad).  Text embeddings are treated as constants (frozen LLM,
+  the audio slots (tasu_gather_rows through the scatter's audio_dest map).  Text embeddings are treated as constants (frozen LLM,
   scripts/finetune_deespeed_sensevoice.sh:84).
 """
 import torch
@@ -166,7 +166,8 @@ class SpliceFunction(torch.autograd.Function):
         emb, mask, out_labels, pos, fids = ops.splice_scatter(plan, spliced_len, text_src, text_mode,
                                                               audio_rows.detach(), audio_layout, audio_max_len,
                                                               labels, pad_id, ignore_id,
-                                                              left_padding=getattr(plan, "left_padding", None))
+                                                              left_padding=getattr(plan, "left_padding", None),
+                                                              want_audio_dest=True)
         ctx.plan, ctx.layout, ctx.max_len = plan, audio_layout, audio_max_len
         ctx.shape = tuple(audio_rows.shape)
         ctx.mark_non_differentiable(mask, pos, fids)

@@ -259,40 +259,51 @@ struct ScatterArgs {
     void* out_emb; void* out_mask; int64_t* out_labels; int64_t* out_pos; int64_t* out_ids;
 };
 
-// one warp per destination row; ESZ = bytes per embedding element
-template <int ESZ>
+// Row map: one THREAD per destination row resolves where the row comes from (text token / audio row / nothing) and
+// writes the integer outputs; the dependent-load chain of the resolve (binary search over new_pos, …) stays out of
+// the copy kernel, whose only dependent load is row_src[row].
+//   row_src[row] = -1 (zero row) | text source row | kAudioFlag + audio row
+constexpr int64_t kAudioFlag = 1LL << 62;
 __global__ void __launch_bounds__(256)
-splice_scatter_kernel(ScatterArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+splice_rowmap_kernel(ScatterArgs a, int64_t* __restrict__ row_src, int32_t* __restrict__ audio_dest) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (int64_t)a.B * a.Sp) return;
     const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
     const bool left = a.left_padding != 0;
     const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
                                 a.text_prefix, a.slot_ord, a.slot_base);
-    const char* src = nullptr;
-    int64_t lab = a.ignore_id, fid = a.pad_id;
+    int64_t src = -1, lab = a.ignore_id, fid = a.pad_id;
     int mval = 0;
     if (d.kind == 1) {
         const int64_t i = (int64_t)b * a.S + d.j;
-        const int64_t srow = a.text_mode == 1 ? a.ids[i] : i;
-        src = reinterpret_cast<const char*>(a.text_src) + srow * a.text_stride * ESZ;
+        src = a.text_mode == 1 ? a.ids[i] : i;
         if (a.labels) lab = a.labels[i];
         fid = a.ids[i];
         mval = 1;
     } else if (d.kind == 2) {
         const int64_t ar = audio_row_of(d.a, a.audio_layout, a.audio_max_len, a.n_audio, a.audio_off);
-        if (ar >= 0) src = reinterpret_cast<const char*>(a.audio) + ar * a.audio_stride * ESZ;
+        if (ar >= 0) {
+            src = kAudioFlag + ar;
+            if (audio_dest) audio_dest[ar] = (int32_t)row;
+        }
         mval = 1;
     }
-    char* dst = reinterpret_cast<char*>(a.out_emb) + row * (int64_t)a.H * ESZ;
-    const int64_t nbytes = (int64_t)a.H * ESZ;
+    row_src[row] = src;
+    if (a.mdt == 0) reinterpret_cast<uint8_t*>(a.out_mask)[row] = (uint8_t)mval;
+    else reinterpret_cast<int64_t*>(a.out_mask)[row] = mval;
+    if (a.out_labels) a.out_labels[row] = lab;
+    a.out_pos[row] = mval ? d.pos : 1;
+    if (a.out_ids) a.out_ids[row] = fid;
+}
+
+// 16-byte-chunk row copy with 4 independent loads in flight per lane (src == nullptr: zero fill)
+__device__ __forceinline__ void copy_row_warp(const char* __restrict__ src, char* __restrict__ dst, int64_t nbytes, int lane) {
     const bool vec = (nbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
                      (src == nullptr || (reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (vec) {
         const int nv = (int)(nbytes / 16);
         if (src) {
-            for (int c = lane; c < nv; c += 128) {        // 4 independent 16-byte loads in flight per lane
+            for (int c = lane; c < nv; c += 128) {
                 uint4 q[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -304,39 +315,52 @@ splice_scatter_kernel(ScatterArgs a) {
         } else {
             for (int c = lane; c < nv; c += 32) st_stream_u4(reinterpret_cast<uint4*>(dst) + c, make_uint4(0, 0, 0, 0));
         }
+    } else if ((nbytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) &&
+               (src == nullptr || (reinterpret_cast<uintptr_t>(src) & 3) == 0)) {     // odd pitches: 4-byte words
+        const int nw = (int)(nbytes / 4);
+        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+        for (int c = lane; c < nw; c += 128) {
+            uint32_t q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = (src && c + 32 * u < nw) ? s4[c + 32 * u] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c + 32 * u < nw) d4[c + 32 * u] = q[u];
+        }
     } else {
         for (int64_t c = lane; c < nbytes; c += 32) dst[c] = src ? src[c] : 0;
     }
-    if (lane == 0) {
-        if (a.mdt == 0) reinterpret_cast<uint8_t*>(a.out_mask)[row] = (uint8_t)mval;
-        else reinterpret_cast<int64_t*>(a.out_mask)[row] = mval;
-        if (a.out_labels) a.out_labels[row] = lab;
-        a.out_pos[row] = mval ? d.pos : 1;
-        if (a.out_ids) a.out_ids[row] = fid;
+}
+
+// one warp per destination row (grid-stride); ESZ = bytes per embedding element
+template <int ESZ>
+__global__ void __launch_bounds__(256)
+splice_copy_kernel(const int64_t* __restrict__ row_src, int64_t n_rows, int H, const void* __restrict__ text_src,
+                   int64_t text_stride, const void* __restrict__ audio, int64_t audio_stride, void* __restrict__ out_emb) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t nbytes = (int64_t)H * ESZ;
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += nwarp) {
+        const int64_t sr = row_src[row];
+        const char* src = nullptr;
+        if (sr >= kAudioFlag) src = reinterpret_cast<const char*>(audio) + (sr - kAudioFlag) * audio_stride * ESZ;
+        else if (sr >= 0) src = reinterpret_cast<const char*>(text_src) + sr * text_stride * ESZ;
+        copy_row_warp(src, reinterpret_cast<char*>(out_emb) + row * nbytes, nbytes, lane);
     }
 }
 
+// dst[r,:] = idx[r] >= 0 ? src[idx[r],:] : 0   (backward of the audio part of the splice)
 template <int ESZ>
 __global__ void __launch_bounds__(256)
-splice_audio_grad_kernel(ScatterArgs a, const void* grad_emb, void* grad_audio) {
+gather_rows_kernel(const void* __restrict__ src, int64_t src_stride, const int32_t* __restrict__ idx, int64_t n_rows, int H,
+                   void* __restrict__ dst, int64_t dst_stride) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= (int64_t)a.B * a.Sp) return;
-    const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
-    const bool left = a.left_padding != 0;
-    const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
-                                a.text_prefix, a.slot_ord, a.slot_base);
-    if (d.kind != 2) return;
-    const int64_t ar = audio_row_of(d.a, a.audio_layout, a.audio_max_len, a.n_audio, a.audio_off);
-    if (ar < 0) return;
-    const char* src = reinterpret_cast<const char*>(grad_emb) + row * (int64_t)a.H * ESZ;
-    char* dst = reinterpret_cast<char*>(grad_audio) + ar * a.audio_stride * ESZ;
-    const int64_t nbytes = (int64_t)a.H * ESZ;
-    if ((nbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-        for (int c = lane; c < nbytes / 16; c += 32)
-            reinterpret_cast<uint4*>(dst)[c] = ld_stream_u4(reinterpret_cast<const uint4*>(src) + c);
-    } else {
-        for (int64_t c = lane; c < nbytes; c += 32) dst[c] = src[c];
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += nwarp) {
+        const int i = idx[r];
+        const char* s = i >= 0 ? reinterpret_cast<const char*>(src) + (int64_t)i * src_stride * ESZ : nullptr;
+        copy_row_warp(s, reinterpret_cast<char*>(dst) + r * dst_stride * ESZ, (int64_t)H * ESZ, lane);
     }
 }
 
@@ -381,11 +405,10 @@ extern "C" int tasu_splice_header(const int32_t* rowstat, const int64_t* num_aud
     return TASU_OK;
 }
 
-static int launch_rows(int64_t rows, unsigned* grid) {
-    const int64_t g = (rows + 7) / 8;
-    if (g > 0x7fffffffLL) return -1;
-    *grid = (unsigned)g;
-    return 0;
+static unsigned warp_row_grid(int64_t rows) {          // 8 warps per CTA, enough CTAs to fill the machine, grid-stride beyond
+    int64_t g = (rows + 7) / 8, gmax = (int64_t)tasu::sm_count() * 16;
+    if (g > gmax) g = gmax;
+    return (unsigned)(g < 1 ? 1 : g);
 }
 
 extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
@@ -397,15 +420,17 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
                                    const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
                                    int left_padding, int64_t pad_id, int64_t ignore_id,
                                    void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
-                                   int64_t* out_ids, void* stream) {
+                                   int64_t* out_ids, int64_t* row_src_ws, int32_t* audio_dest, void* stream) {
     TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
     TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
     TASU_CHECK_ARG(text_mode == 0 || text_mode == 1, "text_mode");
     TASU_CHECK_ARG(audio_layout == 0 || audio_layout == 1, "audio_layout");
     TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
-    if ((int64_t)B * spliced_len == 0) return TASU_OK;
+    const int64_t rows = (int64_t)B * spliced_len;
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(rows < (1LL << 31), "too many rows");
     TASU_CHECK_ARG(input_ids && attention_mask && text_src && rowstat && new_pos && text_prefix && slot_ord &&
-                   slot_base && audio_off && out_emb && out_mask && out_pos, "null pointer");
+                   slot_base && audio_off && out_emb && out_mask && out_pos && row_src_ws, "null pointer");
     ScatterArgs a{};
     a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype; a.labels = labels;
     a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
@@ -416,38 +441,28 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
     a.slot_base = slot_base; a.audio_off = audio_off; a.left_padding = left_padding;
     a.speech = speech_id; a.pad_id = pad_id; a.ignore_id = ignore_id;
     a.out_emb = out_emb; a.out_mask = out_mask; a.out_labels = out_labels; a.out_pos = out_pos; a.out_ids = out_ids;
-    unsigned grid;
-    TASU_CHECK_ARG(launch_rows((int64_t)B * spliced_len, &grid) == 0, "too many rows");
     cudaStream_t st = (cudaStream_t)stream;
-    if (emb_dtype == TASU_F32) splice_scatter_kernel<4><<<grid, 256, 0, st>>>(a);
-    else splice_scatter_kernel<2><<<grid, 256, 0, st>>>(a);
+    splice_rowmap_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(a, row_src_ws, audio_dest);
+    TASU_CHECK_LAUNCH();
+    const unsigned grid = warp_row_grid(rows);
+    if (emb_dtype == TASU_F32)
+        splice_copy_kernel<4><<<grid, 256, 0, st>>>(row_src_ws, rows, H, text_src, text_row_stride, audio_rows, audio_row_stride, out_emb);
+    else
+        splice_copy_kernel<2><<<grid, 256, 0, st>>>(row_src_ws, rows, H, text_src, text_row_stride, audio_rows, audio_row_stride, out_emb);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
 
-extern "C" int tasu_splice_audio_grad(const void* grad_emb, int emb_dtype, const int64_t* input_ids,
-                                      const void* attention_mask, int mask_dtype, int B, int S, int spliced_len,
-                                      int H, int64_t speech_id, const int32_t* rowstat, const int32_t* new_pos,
-                                      const int32_t* text_prefix, const int32_t* slot_ord, const int32_t* slot_base,
-                                      const int32_t* audio_off, int left_padding, int audio_layout,
-                                      int64_t audio_row_stride, int64_t audio_max_len, int n_audio,
-                                      void* grad_audio, void* stream) {
-    TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
-    TASU_CHECK_ARG(emb_dtype == TASU_F32 || emb_dtype == TASU_BF16, "emb_dtype");
-    if ((int64_t)B * spliced_len == 0) return TASU_OK;
-    TASU_CHECK_ARG(grad_emb && input_ids && attention_mask && rowstat && new_pos && text_prefix && slot_ord &&
-                   slot_base && audio_off && grad_audio, "null pointer");
-    ScatterArgs a{};
-    a.ids = input_ids; a.mask = attention_mask; a.mdt = mask_dtype;
-    a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
-    a.audio_layout = audio_layout; a.audio_stride = audio_row_stride; a.audio_max_len = audio_max_len; a.n_audio = n_audio;
-    a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
-    a.slot_base = slot_base; a.audio_off = audio_off; a.left_padding = left_padding; a.speech = speech_id;
-    unsigned grid;
-    TASU_CHECK_ARG(launch_rows((int64_t)B * spliced_len, &grid) == 0, "too many rows");
+extern "C" int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stride, const int32_t* idx, int64_t n_rows, int H,
+                                void* dst, int64_t dst_row_stride, void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && H > 0 && src_row_stride >= H && dst_row_stride >= H, "shape");
+    TASU_CHECK_ARG(dtype == TASU_F32 || dtype == TASU_BF16, "dtype");
+    if (n_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && idx && dst, "null pointer");
+    const unsigned grid = warp_row_grid(n_rows);
     cudaStream_t st = (cudaStream_t)stream;
-    if (emb_dtype == TASU_F32) splice_audio_grad_kernel<4><<<grid, 256, 0, st>>>(a, grad_emb, grad_audio);
-    else splice_audio_grad_kernel<2><<<grid, 256, 0, st>>>(a, grad_emb, grad_audio);
+    if (dtype == TASU_F32) gather_rows_kernel<4><<<grid, 256, 0, st>>>(src, src_row_stride, idx, n_rows, H, dst, dst_row_stride);
+    else gather_rows_kernel<2><<<grid, 256, 0, st>>>(src, src_row_stride, idx, n_rows, H, dst, dst_row_stride);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -50,12 +50,19 @@ tokrow_fwd_kernel(const float* __restrict__ w1, int64_t wstride, const float* __
                   const float* __restrict__ S, const float* __restrict__ D, const int32_t* __restrict__ uniq,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ perm, const float* __restrict__ hot,
                   const float* __restrict__ base, int n_uniq, int V, int Hb, float eps, float* __restrict__ z,
-                  __nv_bfloat16* __restrict__ h, float* __restrict__ row_a, float* __restrict__ row_e) {
+                  __nv_bfloat16* __restrict__ h, float* __restrict__ row_a, float* __restrict__ row_e,
+                  const float* __restrict__ colT) {
     extern __shared__ float col[];                              // [Hb]
     for (int u = blockIdx.x; u < n_uniq; u += gridDim.x) {
-        const int v = uniq[u];
-        const float g = gamma[v];
-        for (int j = threadIdx.x; j < Hb; j += blockDim.x) col[j] = w1[(int64_t)j * wstride + v] * g;
+        if (colT != nullptr) {                                  // columns already gathered by tokrow_cols_kernel
+            const float* c = colT + (int64_t)u * Hb;
+            for (int j = threadIdx.x * 4; j < Hb; j += blockDim.x * 4)
+                *reinterpret_cast<float4*>(col + j) = *reinterpret_cast<const float4*>(c + j);
+        } else {
+            const int v = uniq[u];
+            const float g = gamma[v];
+            for (int j = threadIdx.x; j < Hb; j += blockDim.x) col[j] = w1[(int64_t)j * wstride + v] * g;
+        }
         __syncthreads();
         const int i0 = seg_off[u], i1 = seg_off[u + 1];
         for (int i = i0; i < i1; ++i) {
@@ -164,7 +171,8 @@ tokrow_bwd_rows_kernel(const float* __restrict__ dh, const float* __restrict__ z
 // out0[c] = Σ_p part[p][0][c], out1[c] = Σ_p part[p][1][c] in a fixed order: CTA = 32 columns x 32 warps, warp w sums
 // p = w, w+32, ... (all loads independent), then the 32 warp sums are combined in warp order.
 __global__ void __launch_bounds__(1024)
-reduce_partials_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out0, float* __restrict__ out1) {
+reduce_partials_kernel(const float* __restrict__ part, int n_parts, int C, float* __restrict__ out0, float* __restrict__ out1,
+                       const float* __restrict__ add1) {
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -180,7 +188,55 @@ reduce_partials_kernel(const float* __restrict__ part, int n_parts, int C, float
         float r = 0.f;
 #pragma unroll
         for (int w = 0; w < 32; ++w) r += s[w][lane];
-        if (c < C) out0[c] = r; else out1[c - C] = r;
+        if (c < C) out0[c] = r; else out1[c - C] = r + (add1 ? add1[c - C] : 0.f);
+    }
+}
+
+// Training forward, dense pass over W1 (every sector used once): CTA = 32 vocabulary columns x all output features.
+//   colT[slot(v), j] = W1[j,v]·γ_v  for the tokens present in the batch (compact, j contiguous),
+//   part[cta][0][j]  = Σ_{v in CTA} W1[j,v]·γ_v,   part[cta][1][j] = Σ_{v in CTA} W1[j,v]·β_v   (→ S, D by reduce_partials)
+__global__ void __launch_bounds__(256)
+tokrow_cols_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const int32_t* __restrict__ slot, int Hb, int V,
+                   float* __restrict__ colT, float* __restrict__ part) {
+    __shared__ float tile[2][64][33];                          // [0] = W1·γ, [1] = W1·β for 64 features x 32 columns
+    __shared__ int s_slot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v0 = blockIdx.x * 32;
+    if (threadIdx.x < 32) s_slot[threadIdx.x] = (v0 + threadIdx.x < V) ? slot[v0 + threadIdx.x] : -1;
+    const int v = v0 + lane;
+    const bool vok = v < V;
+    const float gm = vok ? gamma[v] : 0.f, bt = vok ? beta[v] : 0.f;
+    __syncthreads();
+    int sl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sl[q] = s_slot[warp * 4 + q];
+    float* mine = part + (int64_t)blockIdx.x * 2 * Hb;
+    const float* wp = w1 + (int64_t)(warp * 8) * wstride + v;
+    for (int j0 = 0; j0 < Hb; j0 += 64) {
+        float wv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) wv[q] = (vok && j0 + warp * 8 + q < Hb) ? wp[(int64_t)(j0 + q) * wstride] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { tile[0][warp * 8 + q][lane] = wv[q] * gm; tile[1][warp * 8 + q][lane] = wv[q] * bt; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (sl[q] >= 0) {
+                float* dst = colT + (int64_t)sl[q] * Hb + j0;
+                if (j0 + lane < Hb) dst[lane] = tile[0][lane][warp * 4 + q];
+                if (j0 + 32 + lane < Hb) dst[32 + lane] = tile[0][32 + lane][warp * 4 + q];
+            }
+        }
+        if (threadIdx.x < 128) {                               // row sums over the CTA's 32 columns (fixed order)
+            const int which = threadIdx.x >> 6, jl = threadIdx.x & 63;
+            const float* row = tile[which][jl];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) { a0 += row[k]; a1 += row[k + 1]; a2 += row[k + 2]; a3 += row[k + 3]; }
+            if (j0 + jl < Hb) mine[(int64_t)which * Hb + j0 + jl] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
     }
 }
 
@@ -198,37 +254,40 @@ tokrow_wgrad_finish_kernel(const float* __restrict__ P, const int32_t* __restric
                            int64_t wstride, const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ E, const float* __restrict__ db1, int Hb, int V,
                            float* __restrict__ dw1, int64_t dstride, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float s_vec[];                            // E[Hb] | db1[Hb]
     __shared__ float tile[32][65];
     __shared__ float s_ag[8][32], s_ab[8][32];
     __shared__ int s_slot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int v0 = blockIdx.x * 32;
     if (threadIdx.x < 32) s_slot[threadIdx.x] = (v0 + threadIdx.x < V) ? slot[v0 + threadIdx.x] : -1;
+    for (int j = threadIdx.x; j < Hb; j += blockDim.x) { s_vec[j] = E[j]; s_vec[Hb + j] = db1[j]; }
     const int v = v0 + lane;
     const bool vok = v < V;
     const float gm = vok ? gamma[v] : 0.f, bt = vok ? beta[v] : 0.f;
     float ag = 0.f, ab = 0.f;
     __syncthreads();
-    int sl[4];
+    const float* pr[4];
+    bool has[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sl[q] = s_slot[warp * 4 + q];
+    for (int q = 0; q < 4; ++q) {
+        const int sl = s_slot[warp * 4 + q];
+        has[q] = sl >= 0;
+        pr[q] = P + (int64_t)(sl < 0 ? 0 : sl) * Hb + lane;
+    }
+    const float* wp = w1 + (int64_t)(warp * 8) * wstride + v;
+    float* dp = dw1 + (int64_t)(warp * 8) * dstride + v;
     for (int j0 = 0; j0 < Hb; j0 += 64) {
         float pv[4][2];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                          // P rows → tile[v][j]
-            const float* pr = P + (int64_t)(sl[q] < 0 ? 0 : sl[q]) * Hb + j0;
-            pv[q][0] = (sl[q] >= 0 && j0 + lane < Hb) ? pr[lane] : 0.f;
-            pv[q][1] = (sl[q] >= 0 && j0 + 32 + lane < Hb) ? pr[32 + lane] : 0.f;
+            pv[q][0] = (has[q] && j0 + lane < Hb) ? pr[q][j0] : 0.f;
+            pv[q][1] = (has[q] && j0 + 32 + lane < Hb) ? pr[q][j0 + 32] : 0.f;
         }
-        float wv[8], ev[8], dv[8];
+        float wv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {                          // W1 loads do not depend on the tile: issue them now
-            const int j = j0 + warp * 8 + q;
-            const bool ok = vok && j < Hb;
-            wv[q] = ok ? w1[(int64_t)j * wstride + v] : 0.f;
-            ev[q] = j < Hb ? E[j] : 0.f;
-            dv[q] = j < Hb ? db1[j] : 0.f;
-        }
+        for (int q = 0; q < 8; ++q)                            // W1 loads do not depend on the tile: issue them now
+            wv[q] = (vok && j0 + warp * 8 + q < Hb) ? wp[(int64_t)(j0 + q) * wstride] : 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { tile[warp * 4 + q][lane] = pv[q][0]; tile[warp * 4 + q][32 + lane] = pv[q][1]; }
         __syncthreads();
@@ -236,10 +295,11 @@ tokrow_wgrad_finish_kernel(const float* __restrict__ P, const int32_t* __restric
         for (int q = 0; q < 8; ++q) {
             const int jl = warp * 8 + q, j = j0 + jl;
             if (j < Hb && vok) {
-                const float d = tile[lane][jl] + ev[q];
-                dw1[(int64_t)j * dstride + v] = fmaf(gm, d, bt * dv[q]);
+                const float d = tile[lane][jl] + s_vec[j];
+                const float db = s_vec[Hb + j];
+                dp[(int64_t)(j0 + q) * dstride] = fmaf(gm, d, bt * db);
                 ag = fmaf(wv[q], d, ag);
-                ab = fmaf(wv[q], dv[q], ab);
+                ab = fmaf(wv[q], db, ab);
             }
         }
         __syncthreads();
@@ -266,21 +326,73 @@ extern "C" int tasu_host_group_tokens(const int32_t* tok_host, int64_t n_rows, i
     *n_uniq_host = 0;
     if (n_rows == 0) { if (seg_off_host) seg_off_host[0] = 0; return TASU_OK; }
     TASU_CHECK_ARG(tok_host && uniq_host && seg_off_host && perm_host, "null pointer");
-    std::vector<int32_t> count((size_t)V + 1, 0);
+    thread_local std::vector<int32_t> count_tls;               // reused across calls (one per host thread)
+    count_tls.assign((size_t)V, 0);
+    int32_t* __restrict__ count = count_tls.data();            // hoisted: no TLS lookup inside the loops
+    bool bad = false;
     for (int64_t r = 0; r < n_rows; ++r) {
-        const int32_t t = tok_host[r];
-        TASU_CHECK_ARG(t >= 0 && t < V, "token id outside [0, V)");
-        ++count[(size_t)t + 1];
+        const uint32_t t = (uint32_t)tok_host[r];
+        if (t >= (uint32_t)V) { bad = true; break; }
+        ++count[t];
     }
-    int32_t nu = 0;
-    for (int v = 0; v < V; ++v) {
-        if (count[(size_t)v + 1] > 0) { uniq_host[nu] = v; seg_off_host[nu] = count[v]; ++nu; }
-        count[(size_t)v + 1] += count[v];                      // exclusive start of token v = count[v]
+    TASU_CHECK_ARG(!bad, "token id outside [0, V)");
+    int32_t nu = 0, run = 0, sink_u = 0, sink_s = 0;
+    for (int v = 0; v < V; ++v) {                               // branch-free: ~half of the bins are empty
+        const int32_t c = count[v];
+        int32_t* pu = c ? uniq_host + nu : &sink_u;
+        int32_t* ps = c ? seg_off_host + nu : &sink_s;
+        *pu = v; *ps = run;
+        count[v] = run;                                        // exclusive start of token v
+        nu += (c != 0); run += c;
     }
     seg_off_host[nu] = (int32_t)n_rows;
     for (int64_t r = 0; r < n_rows; ++r) perm_host[count[tok_host[r]]++] = (int32_t)r;    // stable: ascending r per token
     *n_uniq_host = nu;
     return TASU_OK;
+}
+
+// The whole host side of ctc_pseudo_posterior_noise (ps-slm.py:380-401, insert_prob = 0) in one call: u is ONE
+// torch.rand(sum(L_b) + B) draw (the reference's stream: per utterance one uniform_ for alpha, then rand(L_b) for
+// the keep mask); the descriptors go straight into the caller's (pinned) staging buffer, already grouped by token.
+// Staging layout in int32 words, cap = sum(L_b):  uniq[cap] | seg_off[cap+1] | perm[cap] | hot[cap] | base[cap] |
+// pad to 8 bytes | lens[B] (int64).
+extern "C" int tasu_host_sim_token_rows(const float* u_host, const int32_t* tok_in_host, const int64_t* len_in_host, int B,
+                                        int V, float drop_prob, float smooth_low, float smooth_high, int32_t* stage_host,
+                                        int64_t stage_words, int64_t* n_rows_host, int32_t* n_uniq_host) {
+    TASU_CHECK_ARG(B >= 0 && V > 0, "B >= 0, V > 0");
+    TASU_CHECK_ARG(n_rows_host && n_uniq_host, "null output");
+    *n_rows_host = 0; *n_uniq_host = 0;
+    int64_t cap = 0;
+    for (int b = 0; b < B; ++b) { TASU_CHECK_ARG(len_in_host[b] >= 0, "negative length"); cap += len_in_host[b]; }
+    const int64_t o_uniq = 0, o_seg = cap, o_perm = 2 * cap + 1, o_hot = 3 * cap + 1, o_base = 4 * cap + 1;
+    const int64_t o_lens = 5 * cap + 1 + ((5 * cap + 1) & 1);
+    TASU_CHECK_ARG(stage_host && stage_words >= o_lens + 2 * (int64_t)B, "staging buffer too small");
+    TASU_CHECK_ARG(B == 0 || (u_host && len_in_host && (cap == 0 || tok_in_host)), "null pointer");
+    float* hot = reinterpret_cast<float*>(stage_host + o_hot);
+    float* base = reinterpret_cast<float*>(stage_host + o_base);
+    int64_t* lens = reinterpret_cast<int64_t*>(stage_host + o_lens);
+    std::vector<int32_t> tok((size_t)cap);
+    const volatile float span = smooth_high - smooth_low;       // fp32, like at::uniform_real_distribution<float>
+    int64_t n = 0, iu = 0, it = 0;
+    for (int b = 0; b < B; ++b) {
+        const volatile float prod = u_host[iu++] * span;        // volatile: no fused multiply-add contraction
+        const float alpha32 = prod + smooth_low;
+        const double alpha = (double)alpha32;                   // .item() → python float
+        const float a32 = (float)(1.0 - alpha), c32 = (float)(alpha / (double)V);
+        const volatile float h32 = a32 + c32;
+        int64_t kept = 0;
+        for (int64_t i = 0; i < len_in_host[b]; ++i, ++iu, ++it) {
+            if (u_host[iu] > drop_prob) {
+                const int32_t t = tok_in_host[it];
+                TASU_CHECK_ARG(t >= 0 && t < V, "token id outside [0, V)");
+                tok[(size_t)n] = t; hot[n] = h32; base[n] = c32;
+                ++n; ++kept;
+            }
+        }
+        lens[b] = kept;
+    }
+    *n_rows_host = n;
+    return tasu_host_group_tokens(tok.data(), n, V, stage_host + o_uniq, stage_host + o_seg, stage_host + o_perm, n_uniq_host);
 }
 
 extern "C" int tasu_linear_rowdots(const float* w1, int64_t w1_stride, const float* gamma, const float* beta,
@@ -295,13 +407,13 @@ extern "C" int tasu_linear_rowdots(const float* w1, int64_t w1_stride, const flo
 extern "C" int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* gamma, const float* S, const float* D,
                                const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, const float* hot,
                                const float* base, int n_uniq, int64_t n_rows, int V, int Hb, float ln_eps, float* z,
-                               void* h_bf16, float* row_a, float* row_e, void* stream) {
+                               void* h_bf16, float* row_a, float* row_e, const float* colT, void* stream) {
     TASU_CHECK_ARG(n_uniq >= 0 && n_rows >= 0 && V > 0 && Hb > 0 && w1_stride >= V, "shape");
     TASU_CHECK_ARG(Hb % 8 == 0, "Hb must be a multiple of 8");
     if (n_uniq == 0 || n_rows == 0) return TASU_OK;
     TASU_CHECK_ARG(w1 && gamma && S && D && uniq && seg_off && perm && hot && base && h_bf16 && row_a && row_e, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)S % 16 == 0) && ((uintptr_t)D % 16 == 0) && ((uintptr_t)h_bf16 % 16 == 0) &&
-                   (z == nullptr || (uintptr_t)z % 16 == 0), "16-byte alignment");
+                   (z == nullptr || (uintptr_t)z % 16 == 0) && (colT == nullptr || (uintptr_t)colT % 16 == 0), "16-byte alignment");
     const size_t smem = sizeof(float) * (size_t)Hb;
     TASU_CHECK_ARG(smem <= 200 * 1024, "Hb too large for the shared-memory column");
     if (smem > 48 * 1024)
@@ -311,7 +423,33 @@ extern "C" int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* 
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (grid > n_uniq) grid = n_uniq;
     tokrow_fwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(w1, w1_stride, gamma, S, D, uniq, seg_off, perm, hot, base,
-                                                                          n_uniq, V, Hb, ln_eps, z, (__nv_bfloat16*)h_bf16, row_a, row_e);
+                                                                          n_uniq, V, Hb, ln_eps, z, (__nv_bfloat16*)h_bf16, row_a, row_e, colT);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int64_t tasu_tokrow_cols_workspace(int V, int Hb) {
+    if (V <= 0 || Hb <= 0) return 0;
+    return (int64_t)((V + 31) / 32) * 2 * Hb * (int64_t)sizeof(float) + 4LL * ((V + 63) / 64 * 64);
+}
+
+extern "C" int tasu_tokrow_cols(const float* w1, int64_t w1_stride, const float* gamma, const float* beta, const float* b1,
+                                const int32_t* uniq, int n_uniq, int V, int Hb, float* colT, float* S, float* D,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    TASU_CHECK_ARG(V > 0 && Hb > 0 && n_uniq >= 0 && w1_stride >= V, "shape");
+    TASU_CHECK_ARG(w1 && gamma && beta && S && D && workspace, "null pointer");
+    TASU_CHECK_ARG(n_uniq == 0 || (uniq && colT), "null uniq / colT");
+    TASU_CHECK_ARG(workspace_bytes >= tasu_tokrow_cols_workspace(V, Hb), "workspace too small (tasu_tokrow_cols_workspace)");
+    TASU_CHECK_ARG((uintptr_t)workspace % 16 == 0, "workspace alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_cta = (V + 31) / 32;
+    float* part = (float*)workspace;
+    int32_t* slot = (int32_t*)((char*)workspace + (int64_t)n_cta * 2 * Hb * sizeof(float));
+    TASU_CHECK_CUDA(cudaMemsetAsync(slot, 0xFF, sizeof(int32_t) * V, st));
+    if (n_uniq > 0) slot_scatter_kernel<<<(n_uniq + 255) / 256, 256, 0, st>>>(uniq, n_uniq, slot);
+    tokrow_cols_kernel<<<n_cta, 256, 0, st>>>(w1, w1_stride, gamma, beta, slot, Hb, V, colT, part);
+    TASU_CHECK_LAUNCH();
+    reduce_partials_kernel<<<(2 * Hb + 31) / 32, 1024, 0, st>>>(part, n_cta, Hb, S, D, b1);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
@@ -354,7 +492,7 @@ extern "C" int tasu_tokrow_bwd_rows(const float* dh, const float* z, int64_t n_r
     if (chunks == 1) LAUNCH(1); else if (chunks == 2) LAUNCH(2); else if (chunks == 3) LAUNCH(3); else LAUNCH(4);
 #undef LAUNCH
     TASU_CHECK_LAUNCH();
-    reduce_partials_kernel<<<(2 * Hb + 31) / 32, 1024, 0, st>>>(part, (int)grid, Hb, db1, E);
+    reduce_partials_kernel<<<(2 * Hb + 31) / 32, 1024, 0, st>>>(part, (int)grid, Hb, db1, E, nullptr);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
@@ -369,8 +507,12 @@ extern "C" int tasu_tokrow_wgrad_finish(const float* P, const int32_t* uniq, int
     cudaStream_t st = (cudaStream_t)stream;
     TASU_CHECK_CUDA(cudaMemsetAsync(slot_ws, 0xFF, sizeof(int32_t) * V, st));
     if (n_uniq > 0) slot_scatter_kernel<<<(n_uniq + 255) / 256, 256, 0, st>>>(uniq, n_uniq, slot_ws);
-    tokrow_wgrad_finish_kernel<<<(unsigned)((V + 31) / 32), 256, 0, st>>>(P, slot_ws, w1, w1_stride, gamma, beta, E, db1, Hb, V,
-                                                                         dw1, dw1_stride, dgamma, dbeta);
+    const size_t smem = 2 * sizeof(float) * (size_t)Hb;
+    TASU_CHECK_ARG(smem <= 96 * 1024, "Hb too large");
+    if (smem > 32 * 1024)
+        TASU_CHECK_CUDA(cudaFuncSetAttribute(tokrow_wgrad_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tokrow_wgrad_finish_kernel<<<(unsigned)((V + 31) / 32), 256, smem, st>>>(P, slot_ws, w1, w1_stride, gamma, beta, E, db1, Hb, V,
+                                                                            dw1, dw1_stride, dgamma, dbeta);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
@@ -396,7 +538,10 @@ static TrainWs train_ws(int64_t n, int n_uniq, int V, int Hb, int H) {
     w.w2T = o; o += al256(2LL * Hb * pad_to(H, 8));
     w.dh = o; o += al256(4LL * (n > 0 ? n : 1) * Hb);
     w.P = o; o += al256(4LL * (n_uniq > 0 ? n_uniq : 1) * Hb);
-    w.part = o; o += al256(tasu_tokrow_bwd_workspace(Hb, n_uniq) + 16);
+    {
+        const int64_t a = tasu_tokrow_bwd_workspace(Hb, n_uniq) + 16, b = tasu_tokrow_cols_workspace(V, Hb) + 16;
+        w.part = o; o += al256(a > b ? a : b);
+    }
     w.E = o; o += al256(4LL * Hb);
     w.slot = o; o += al256(4LL * V);
     w.total = o;
@@ -428,9 +573,10 @@ extern "C" int tasu_tokrow_linear_silu_fwd(const float* w1, int64_t w1_stride, c
     float* D = (float*)(wsb + ws.D);
     void* w2b = wsb + ws.w2b;
     const int64_t ldw2 = pad_to(Hb, 64);
-    TASU_TRY(tasu_linear_rowdots(w1, w1_stride, gamma, beta, b1, Hb, V, S, D, stream));
+    float* colT = (float*)(wsb + ws.P);                      // the forward's compact columns share the backward's P area
+    TASU_TRY(tasu_tokrow_cols(w1, w1_stride, gamma, beta, b1, uniq, n_uniq, V, Hb, colT, S, D, wsb + ws.part, ws.E - ws.part, stream));
     TASU_TRY(tasu_tokrow_fwd(w1, w1_stride, gamma, S, D, uniq, seg_off, perm, hot, base, n_uniq, n_rows, V, Hb, ln_eps, z, h_bf16,
-                             row_a, row_e, stream));
+                             row_a, row_e, colT, stream));
     TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
     TASU_TRY(tasu_gemm_bf16_tn(h_bf16, Hb, w2b, ldw2, y, y_dtype, ldy, (int)n_rows, H, Hb, TASU_EPI_BIAS, b2, nullptr, nullptr,
                                nullptr, nullptr, stream));

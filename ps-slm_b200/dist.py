@@ -46,32 +46,71 @@ def all_gather_lengths(lens: torch.Tensor, group=None) -> List[torch.Tensor]:
     return [b[:int(c)] for b, c in zip(bufs, counts)]
 
 
-def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None):
+def _gather_rows(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """rows[i] = flat[idx[i]] — tasu_gather_rows on the GPU; plain indexing only for the CPU (gloo) tests."""
+    if flat.is_cuda:
+        from . import _lib as L
+        from . import ops
+        H = flat.shape[1]
+        out = torch.empty(max(idx.numel(), 1), H, dtype=flat.dtype, device=flat.device)[:idx.numel()]
+        L.check(L.lib().tasu_gather_rows(flat.data_ptr(), ops._dt(flat), flat.stride(0), idx.data_ptr(), idx.numel(), H,
+                                         out.data_ptr(), H, ops._stream()), "tasu_gather_rows")
+        ops._count(1)
+        return out
+    return flat.index_select(0, idx.long())
+
+
+def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing=None):
     """Gather every rank's packed compressed rows ``[sum M_b, H]`` and lengths.
 
     Returns ``(rows_global [sum over all utterances, H], lens_global [n_utts])`` in GLOBAL utterance
-    order (utterance i lives on rank i % W).  Lengths go first, then one padded-to-max all-gather of
-    the payload: on NVSwitch a flat all-gather is bandwidth-optimal, no topology-aware ring needed."""
+    order (utterance i lives on rank i % W).  Two small collectives for the lengths, ONE host read of them,
+    ONE padded-to-max all-gather of the payload (on NVSwitch a flat all-gather is bandwidth-optimal, no
+    topology-aware ring needed) and one row-gather kernel that puts the rows in global order."""
     rank, W = world()
     if W == 1:
         return rows, lens
     all_lens = all_gather_lengths(lens, group)
-    totals = [int(l.sum()) for l in all_lens]
+    lens_host = [l.cpu() for l in all_lens]                      # the single device→host hand-off
+    totals = [int(l.sum()) for l in lens_host]
     m = max(totals + [1])
     H = rows.shape[1]
-    pad = torch.zeros(m, H, dtype=rows.dtype, device=rows.device)
+    pad = torch.empty(m, H, dtype=rows.dtype, device=rows.device)
     pad[:rows.shape[0]] = rows
-    bufs = [torch.empty_like(pad) for _ in range(W)]
-    dist.all_gather(bufs, pad, group=group)
-    n = sum(l.numel() for l in all_lens)
-    offs = [torch.cat([torch.zeros(1, dtype=torch.int64, device=l.device), torch.cumsum(l, 0)]) for l in all_lens]
-    pieces, glens = [], []
+    flat = torch.empty(W * m, H, dtype=rows.dtype, device=rows.device)
+    if timing is not None and rows.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    dist.all_gather_into_tensor(flat, pad, group=group)
+    if timing is not None and rows.is_cuda:
+        e1.record()
+        timing.append((e0, e1, W * m * H * rows.element_size()))
+    n = sum(l.numel() for l in lens_host)
+    offs = [torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(l, 0)]) for l in lens_host]
+    idx, glens = [], []
     for r, j in global_order(n, W):
         s, e = int(offs[r][j]), int(offs[r][j + 1])
-        pieces.append(bufs[r][s:e])
-        glens.append(all_lens[r][j])
-    rows_g = torch.cat(pieces, 0) if pieces else rows[:0]
-    return rows_g, torch.stack(glens) if glens else lens[:0]
+        idx.append(torch.arange(r * m + s, r * m + e, dtype=torch.int32))
+        glens.append(int(lens_host[r][j]))
+    idx = torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int32)
+    if rows.is_cuda:
+        idx = idx.pin_memory().to(rows.device, non_blocking=True)
+    rows_g = _gather_rows(flat, idx)
+    return rows_g, torch.tensor(glens, dtype=lens.dtype).to(lens.device)
+
+
+def _shared_flat(grads):
+    """The whole storage as one 1-D tensor if every gradient is a view of the same fp32 storage (the token-row
+    backward hands out views of one flat buffer), else None."""
+    if not grads:
+        return None
+    st = grads[0].untyped_storage()
+    if any(g.dtype != torch.float32 or g.untyped_storage().data_ptr() != st.data_ptr() for g in grads):
+        return None
+    covered = sum(g.numel() for g in grads) * 4
+    if covered < 0.9 * st.nbytes():                              # views of something much larger: not ours
+        return None
+    return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st)
 
 
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20, average: bool = True,
@@ -83,6 +122,14 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
     if W == 1:
         return []
     grads = [p.grad for p in params if p.grad is not None]
+    flat = _shared_flat(grads)
+    if flat is not None:                                         # one in-place message, no flatten / copy-back
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        handles = [(work, flat, [])]
+        if async_op:
+            return handles
+        finish_allreduce(handles, W if average else 1)
+        return []
     handles, bucket, size = [], [], 0
 
     def flush():

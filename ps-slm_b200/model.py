@@ -198,14 +198,15 @@ class slam_model_asr(nn.Module):
             # row, so it is handed to the projector as (token, hot, base) descriptors and never materialised
             ids_list = [self.encoder_tokenizer.encode(t) for t in texts]
             V = self.encoder_tokenizer.vocab_size
-            if noisy:
-                desc = _sim.draw_noise_descriptors(
-                    ids_list, V, blank, drop_prob=getattr(self, "drop_prob", 0.05),
-                    insert_prob=getattr(self, "insert_prob", 0.0), smooth_low=getattr(self, "smooth_low", 0.0),
-                    smooth_high=getattr(self, "smooth_high", 0.1))
+            hp = dict(drop_prob=getattr(self, "drop_prob", 0.05), smooth_low=getattr(self, "smooth_low", 0.0),
+                      smooth_high=getattr(self, "smooth_high", 0.1))
+            insert_prob = getattr(self, "insert_prob", 0.0)
+            if noisy and int(max((len(i) for i in ids_list), default=0) * insert_prob) == 0:
+                rows = _ops.sim_token_rows(_ops.TokenBatch(ids_list), V, input_ids.device, **hp)   # one native host call
             else:
-                desc = _sim.clean_descriptors(ids_list)
-            rows = _ops.group_token_rows(*desc, V, input_ids.device)
+                desc = (_sim.draw_noise_descriptors(ids_list, V, blank, insert_prob=insert_prob, **hp) if noisy
+                        else _sim.clean_descriptors(ids_list))
+                rows = _ops.group_token_rows(*desc, V, input_ids.device)
             feat_len = rows.lens // self.encoder_projector.k
             pending = _bridge.begin_splice_plan(input_ids, attention_mask, feat_len, self.tokenizer.default_speech_token)
             audio = self.encoder_projector.forward_token_rows(rows, out_dtype=table.dtype)

@@ -276,7 +276,7 @@ def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor,
 
 class SplicePlan:
     __slots__ = ("rowstat", "new_pos", "text_prefix", "slot_ord", "slot_base", "audio_off", "header", "left_padding",
-                 "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask")
+                 "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask", "audio_dest")
 
 
 def _mask_arg(attention_mask: torch.Tensor):
@@ -328,8 +328,9 @@ def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: 
 def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text_mode: int,
                    audio_rows: torch.Tensor, audio_layout: int, audio_max_len: int,
                    labels: Optional[torch.Tensor], pad_id: int, ignore_id: int, want_ids: bool = True,
-                   left_padding: Optional[int] = None):
-    """One gather/scatter pass → (emb [B,S',H], mask [B,S'], labels|None, position_ids, final_ids|None)."""
+                   left_padding: Optional[int] = None, want_audio_dest: bool = False):
+    """Row map + one copy pass → (emb [B,S',H], mask [B,S'], labels|None, position_ids, final_ids|None).
+    ``want_audio_dest``: also keep ``p.audio_dest`` (output row of every audio row) for the backward."""
     _need_cuda(text_src, audio_rows, labels)
     B, S = p.B, p.S
     dev = p.input_ids.device
@@ -352,8 +353,10 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
     if audio_layout == 1:
         audio_rows = audio_rows.contiguous()
         audio_stride = H
+        n_audio_rows = p.n_audio * audio_max_len
     else:
         audio_stride = audio_rows.stride(0) if audio_rows.dim() == 2 and audio_rows.shape[0] > 1 else H
+        n_audio_rows = audio_rows.shape[0] if audio_rows.dim() == 2 else 0
     emb = torch.empty(B, spliced_len, H, dtype=text_src.dtype, device=dev)
     mask = torch.empty(B, spliced_len, dtype=torch.bool if p.mask_dtype == 0 else torch.int64, device=dev)
     out_labels = None
@@ -362,35 +365,35 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
         out_labels = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
     pos = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
     fids = torch.empty(B, spliced_len, dtype=torch.int64, device=dev) if want_ids else None
+    row_src = torch.empty(max(B * spliced_len, 1), dtype=torch.int64, device=dev)
+    audio_dest = torch.full((max(n_audio_rows, 1),), -1, dtype=torch.int32, device=dev) if want_audio_dest else None
     L.check(L.lib().tasu_splice_scatter(
         p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, _ptr(labels), B, S, spliced_len, H,
         p.speech_id, text2.data_ptr(), text_mode, text_stride, audio_rows.data_ptr() if audio_rows.numel() else None,
         audio_layout, audio_stride, audio_max_len, p.n_audio, _dt(emb),
         p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(),
         p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.left_padding, pad_id, ignore_id,
-        emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), _stream()),
-        "tasu_splice_scatter")
-    _count(1)
+        emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), row_src.data_ptr(),
+        _ptr(audio_dest), _stream()), "tasu_splice_scatter")
+    p.audio_dest = audio_dest
+    _count(2)
     return emb, mask, out_labels, pos, fids
 
 
 def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, audio_max_len: int,
                       n_rows: int):
-    """grad wrt the audio rows = gather of grad_emb at the audio slots (backward of splice_scatter)."""
+    """grad wrt the audio rows = gather of grad_emb at the audio slots (``p.audio_dest`` of the forward scatter)."""
     _need_cuda(grad_emb)
     grad_emb = grad_emb.contiguous()
     B, Sp, H = grad_emb.shape
-    if audio_layout == 1:
-        ga = torch.zeros(p.n_audio, audio_max_len, H, dtype=grad_emb.dtype, device=grad_emb.device)
-    else:
-        ga = torch.zeros(n_rows, H, dtype=grad_emb.dtype, device=grad_emb.device)
-    L.check(L.lib().tasu_splice_audio_grad(
-        grad_emb.data_ptr(), _dt(grad_emb), p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype,
-        B, p.S, Sp, H, p.speech_id, p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(),
-        p.slot_ord.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.left_padding,
-        audio_layout, H, audio_max_len, p.n_audio, ga.data_ptr(), _stream()), "tasu_splice_audio_grad")
+    if p.audio_dest is None:
+        raise L.TasuError("splice_audio_grad needs the forward scatter to have run with want_audio_dest=True")
+    rows = p.n_audio * audio_max_len if audio_layout == 1 else n_rows
+    ga = torch.empty(max(rows, 1), H, dtype=grad_emb.dtype, device=grad_emb.device)[:rows]
+    L.check(L.lib().tasu_gather_rows(grad_emb.data_ptr(), _dt(grad_emb), H, p.audio_dest.data_ptr(), rows, H,
+                                     ga.data_ptr(), H, _stream()), "tasu_gather_rows")
     _count(1)
-    return ga
+    return ga.view(p.n_audio, audio_max_len, H) if audio_layout == 1 else ga
 
 
 # ----------------------------------------------------------------------------- training helpers
@@ -533,6 +536,49 @@ def group_token_rows(tok, hot, base, lens, V: int, device) -> TokenRows:
     return t
 
 
+class TokenBatch:
+    """Tokenised transcripts of one batch, flattened once (the data loader's output): int32 ids + int64 lengths."""
+    __slots__ = ("tok", "lens", "B", "total")
+
+    def __init__(self, ids_list):
+        import numpy as np
+        self.B = len(ids_list)
+        self.lens = np.fromiter((len(i) for i in ids_list), dtype=np.int64, count=self.B)
+        self.total = int(self.lens.sum())
+        self.tok = (np.concatenate([np.asarray(i, dtype=np.int32) for i in ids_list]) if self.total
+                    else np.zeros(0, dtype=np.int32))
+
+
+def sim_token_rows(batch: TokenBatch, V: int, device, drop_prob: float = 0.05, smooth_low: float = 0.0,
+                   smooth_high: float = 0.1) -> TokenRows:
+    """Noisy simulator (ps-slm.py:360-409, insert_prob = 0) → grouped descriptors on the device: one ``torch.rand``
+    call (the reference's RNG stream), one native host call, one host→device copy."""
+    import ctypes
+    cap, B = batch.total, batch.B
+    u = torch.rand(cap + B)
+    o_uniq, o_seg, o_perm, o_hot, o_base = 0, cap, 2 * cap + 1, 3 * cap + 1, 4 * cap + 1
+    o_lens = 5 * cap + 1 + ((5 * cap + 1) & 1)
+    words = o_lens + 2 * B
+    stage = torch.empty(max(words, 2), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    n_rows, n_uniq = ctypes.c_int64(0), ctypes.c_int32(0)
+    L.check(L.lib().tasu_host_sim_token_rows(u.data_ptr(), batch.tok.ctypes.data, batch.lens.ctypes.data, B, V,
+                                             float(drop_prob), float(smooth_low), float(smooth_high), stage.data_ptr(),
+                                             words, ctypes.addressof(n_rows), ctypes.addressof(n_uniq)),
+            "tasu_host_sim_token_rows")
+    n = int(n_rows.value)
+    d = stage.to(device, non_blocking=True)
+    t = TokenRows()
+    t.n_rows, t.n_uniq, t.V = n, int(n_uniq.value), V
+    t.uniq = d[o_uniq:o_uniq + t.n_uniq]
+    t.seg_off = d[o_seg:o_seg + t.n_uniq + 1]
+    t.perm = d[o_perm:o_perm + n]
+    t.hot = d[o_hot:o_hot + n].view(torch.float32)
+    t.base = d[o_base:o_base + n].view(torch.float32)
+    t.lens = d[o_lens:o_lens + 2 * B].view(torch.int64)
+    t.lens_host = stage[o_lens:o_lens + 2 * B].view(torch.int64).tolist()
+    return t
+
+
 def linear_rowdots(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1: Optional[torch.Tensor]):
     """(S = W1·γ, D = W1·β + b1), fp32 [N] each."""
     _need_cuda(w1, gamma, beta, b1)
@@ -548,8 +594,28 @@ def linear_rowdots(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1
     return S, D
 
 
+def tokrow_cols(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b1: Optional[torch.Tensor], rows: TokenRows):
+    """One dense pass over W1 → (colT fp32 [n_uniq, Hb], S, D)."""
+    _need_cuda(w1, gamma, beta, b1)
+    Hb, V = w1.shape
+    dev = w1.device
+    w1 = w1.float().contiguous()
+    colT = torch.empty(max(rows.n_uniq, 1), Hb, dtype=torch.float32, device=dev)
+    S = torch.empty(Hb, dtype=torch.float32, device=dev)
+    D = torch.empty(Hb, dtype=torch.float32, device=dev)
+    nbytes = L.lib().tasu_tokrow_cols_workspace(V, Hb)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(L.lib().tasu_tokrow_cols(w1.data_ptr(), w1.stride(0), gamma.float().contiguous().data_ptr(),
+                                     beta.float().contiguous().data_ptr(),
+                                     _ptr(b1.float().contiguous()) if b1 is not None else None, rows.uniq.data_ptr(),
+                                     rows.n_uniq, V, Hb, colT.data_ptr(), S.data_ptr(), D.data_ptr(), ws.data_ptr(),
+                                     nbytes, _stream()), "tasu_tokrow_cols")
+    _count(3)
+    return colT, S, D
+
+
 def tokrow_fwd(w1: torch.Tensor, gamma: torch.Tensor, S: torch.Tensor, D: torch.Tensor, rows: TokenRows,
-               ln_eps: float = 1e-5, want_z: bool = True):
+               ln_eps: float = 1e-5, want_z: bool = True, colT: Optional[torch.Tensor] = None):
     """→ (z fp32 [n, Hb] | None, h bf16 [n, Hb], row_a, row_e)."""
     _need_cuda(w1, gamma, S, D)
     Hb, V = w1.shape
@@ -563,7 +629,7 @@ def tokrow_fwd(w1: torch.Tensor, gamma: torch.Tensor, S: torch.Tensor, D: torch.
     L.check(L.lib().tasu_tokrow_fwd(w1.data_ptr(), w1.stride(0), gamma.float().contiguous().data_ptr(), S.data_ptr(),
                                     D.data_ptr(), rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(),
                                     rows.hot.data_ptr(), rows.base.data_ptr(), rows.n_uniq, n, V, Hb, float(ln_eps),
-                                    _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(), _stream()),
+                                    _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(), _ptr(colT), _stream()),
             "tasu_tokrow_fwd")
     _count(1)
     return z, h, row_a, row_e
@@ -658,11 +724,20 @@ def tokrow_linear_silu_bwd(dy: torch.Tensor, rows: TokenRows, z, h, row_a, row_e
     H = w2.shape[0]
     n, dev = rows.n_rows, w1.device
     w1, w2, gamma, beta = _f32c(w1), _f32c(w2), _f32c(gamma), _f32c(beta)
-    dw1 = torch.empty(Hb, V, dtype=torch.float32, device=dev)
-    dw2 = torch.empty(H, Hb, dtype=torch.float32, device=dev)
-    Vp, Hbp = pad_to(V), pad_to(Hb)                                  # one allocation, 256-byte aligned slices
-    vecs = torch.empty(2 * Vp + Hbp + H, dtype=torch.float32, device=dev)
-    dgamma, dbeta, db1, db2 = vecs[:V], vecs[Vp:Vp + V], vecs[2 * Vp:2 * Vp + Hb], vecs[2 * Vp + Hbp:]
+    # ONE flat gradient buffer in parameter order (norm.weight, norm.bias, ffn.0.weight, ffn.0.bias, ffn.2.weight,
+    # ffn.2.bias), every slice 256-byte aligned: the gradients autograd hands to the parameters are views of it, so
+    # the data-parallel all-reduce (dist.allreduce_gradients) runs in place on one message without a flatten/copy
+    sizes = (V, V, Hb * V, Hb, H * Hb, H)
+    offs, o = [], 0
+    for n_el in sizes:
+        offs.append(o)
+        o += pad_to(n_el)
+    flat = torch.empty(o, dtype=torch.float32, device=dev)
+    dgamma, dbeta = flat[offs[0]:offs[0] + V], flat[offs[1]:offs[1] + V]
+    dw1 = flat[offs[2]:offs[2] + Hb * V].view(Hb, V)
+    db1 = flat[offs[3]:offs[3] + Hb]
+    dw2 = flat[offs[4]:offs[4] + H * Hb].view(H, Hb)
+    db2 = flat[offs[5]:offs[5] + H]
     L.check(L.lib().tasu_tokrow_linear_silu_bwd(
         dy.data_ptr(), _dt(dy), dy.stride(0) if n > 1 else H, _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(),
         w1.data_ptr(), w1.stride(0), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), w2.stride(0),

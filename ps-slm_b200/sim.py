@@ -183,3 +183,59 @@ def ctc_pseudo_posterior_noise(ids_list: List[List[int]], vocab_size: int, devic
     """Smoothed / dropped / inserted pseudo-posterior and lens on ``device`` (ps-slm.py:360-409)."""
     dec = draw_noise_decisions(ids_list, blank_id, drop_prob, insert_prob, smooth_low, smooth_high)
     return build_dense(dec, vocab_size, device)
+
+
+class TokenRowPrefetcher:
+    """Runs the noisy simulator (ps-slm.py:360-409) one batch AHEAD of the training step on a host thread:
+    ``torch.rand`` + the native descriptor call + the pinned host→device copy (on a side stream) of batch i+1
+    overlap the kernels and launches of batch i.  Draw order — hence the RNG stream — is the iteration order.
+
+        for rows in TokenRowPrefetcher(batches, V, device):      # batches: iterable of ops.TokenBatch
+            y = projector.forward_token_rows(rows)
+    ``seeds`` (optional iterable) re-seeds torch's CPU generator before each draw (reproducible benchmarks)."""
+
+    def __init__(self, batches, vocab_size: int, device, depth: int = 2, seeds=None, drop_prob: float = 0.05,
+                 smooth_low: float = 0.0, smooth_high: float = 0.1):
+        import queue
+        import threading
+        self.V, self.device = vocab_size, torch.device(device)
+        self.kw = dict(drop_prob=drop_prob, smooth_low=smooth_low, smooth_high=smooth_high)
+        self.q = queue.Queue(maxsize=depth)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.err = None
+        self.t = threading.Thread(target=self._run, args=(iter(batches), iter(seeds) if seeds is not None else None),
+                                  daemon=True)
+        self.t.start()
+
+    def _run(self, it, seeds):
+        try:
+            if self.stream is not None:
+                torch.cuda.set_device(self.device)
+            for batch in it:
+                if seeds is not None:
+                    torch.manual_seed(next(seeds))
+                if self.stream is None:
+                    self.q.put((ops.sim_token_rows(batch, self.V, self.device, **self.kw), None))
+                    continue
+                with torch.cuda.stream(self.stream):
+                    rows = ops.sim_token_rows(batch, self.V, self.device, **self.kw)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                self.q.put((rows, ev))
+        except BaseException as e:  # noqa: BLE001 — re-raised in the consumer
+            self.err = e
+        self.q.put(None)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                if self.err is not None:
+                    raise self.err
+                return
+            rows, ev = item
+            if ev is not None:
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(ev)
+                rows.hot.record_stream(cur)              # all descriptor tensors are views of one staging copy
+            yield rows

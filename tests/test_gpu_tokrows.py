@@ -73,6 +73,12 @@ def test_preactivation_is_fp32_exact(dev, V, insert_prob):
     assert z.shape == z_ref.shape
     assert _rel(z.cpu(), z_ref) < 1e-5
     assert _rel(h.float().cpu(), torch.nn.functional.silu(z_ref)) < 4e-3           # bf16 rounding of h only
+    # training forward: one dense pass over W1 (compact columns + S, D), then the same row kernel
+    colT, S2, D2 = ops.tokrow_cols(md.ffn[0].weight.detach(), md.norm.weight.detach(), md.norm.bias.detach(),
+                                   md.ffn[0].bias.detach(), rows)
+    assert _rel(S2.cpu(), S.cpu()) < 1e-5 and _rel(D2.cpu(), D.cpu()) < 1e-5
+    z2, _, _, _ = ops.tokrow_fwd(md.ffn[0].weight.detach(), md.norm.weight.detach(), S2, D2, rows, md.norm.eps, colT=colT)
+    assert _rel(z2.cpu(), z_ref) < 1e-5
 
 
 def test_clean_rows_inference(dev):

@@ -87,3 +87,34 @@ def test_host_group_tokens_rejects_out_of_range():
     import ps_slm_b200.ops as ops
     with pytest.raises(L.TasuError):
         ops.group_token_rows(np.asarray([1, V], dtype=np.int32), np.ones(2, np.float32), np.zeros(2, np.float32), [2], V, "cpu")
+
+
+def test_native_sim_call_matches_python_descriptors():
+    """tasu_host_sim_token_rows (one native call) == draw_noise_descriptors + group_token_rows, same RNG stream."""
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.sim as sim
+    for seed in range(3):
+        ids = _transcripts(20 + seed, 11)
+        torch.manual_seed(seed)
+        a = ops.group_token_rows(*sim.draw_noise_descriptors(ids, V, 0, drop_prob=0.1, smooth_low=0.02, smooth_high=0.3),
+                                 V, "cpu")
+        after_a = torch.rand(1)
+        torch.manual_seed(seed)
+        b = ops.sim_token_rows(ops.TokenBatch(ids), V, "cpu", drop_prob=0.1, smooth_low=0.02, smooth_high=0.3)
+        after_b = torch.rand(1)
+        assert torch.equal(after_a, after_b) and a.n_rows == b.n_rows and a.n_uniq == b.n_uniq and a.lens_host == b.lens_host
+        for k in ("uniq", "seg_off", "perm", "hot", "base", "lens"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_prefetcher_preserves_draw_order():
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.sim as sim
+    batches = [ops.TokenBatch(_transcripts(40 + i, 5)) for i in range(4)]
+    torch.manual_seed(9)
+    want = [ops.sim_token_rows(b, V, "cpu") for b in batches]
+    torch.manual_seed(9)
+    got = list(sim.TokenRowPrefetcher(batches, V, "cpu"))
+    assert len(got) == 4
+    for w, g in zip(want, got):
+        assert torch.equal(w.perm, g.perm) and torch.equal(w.hot, g.hot) and w.lens_host == g.lens_host

@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--global-batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--kernel-table", action="store_true",
+                    help="after the timed run, print in-situ per-kernel device times (CUPTI via torch.profiler) of 5 steps")
+    ap.add_argument("--no-prefetch", action="store_true", help="run the simulator inside the step instead of one batch ahead")
     ap.add_argument("--dense", action="store_true",
                     help="dense path: bf16 posterior rows built in HBM + tensor-core GEMM-1/G (default: token-row projector)")
     args = ap.parse_args()
@@ -58,20 +61,24 @@ def main():
     params = list(proj.parameters())
     n_param = sum(p.numel() for p in params)
 
-    def step(i, timers):
-        torch.manual_seed(1000 + i)
-        t0 = time.perf_counter()
-        dec = sim.draw_noise_descriptors(ids_list, V, 0)
-        timers["host_sim"] += time.perf_counter() - t0
+    tbatch = ops.TokenBatch(ids_list)
+
+    def step(i, timers, tr=None):
         if args.dense:
+            torch.manual_seed(1000 + i)
+            t0 = time.perf_counter()
+            dec = sim.draw_noise_descriptors(ids_list, V, 0)
+            timers["host_sim"] += time.perf_counter() - t0
             rows, mean, rstd, lens = sim.build_packed_bf16(dec, V, dev)
             pend = bridge.begin_splice_plan(input_ids, mask, lens, S.SPEECH_ID)
             y = linear_silu_train_rows(proj, rows, mean, rstd, rows.shape[0], torch.float32)
             lmax = max(dec[3])
         else:
-            t1 = time.perf_counter()
-            tr = ops.group_token_rows(*dec, V, dev)
-            timers["host_sim"] += time.perf_counter() - t1
+            if tr is None:                                   # no prefetch: simulator on the critical path
+                torch.manual_seed(1000 + i)
+                t0 = time.perf_counter()
+                tr = ops.sim_token_rows(tbatch, V, dev)
+                timers["host_sim"] += time.perf_counter() - t0
             pend = bridge.begin_splice_plan(input_ids, mask, tr.lens, S.SPEECH_ID)
             y = proj.forward_token_rows(tr, torch.float32)
             lens, lmax = tr.lens, max(tr.lens_host)
@@ -79,7 +86,7 @@ def main():
                                                          S.PAD_ID, S.IGNORE_ID, pending=pend)
         # synthetic upstream gradient dL/d(inputs_embeds) ~ N(0,1): a window of a pre-generated pool (the LLM that
         # would produce it is outside the bridge; generating 0.3 GB of normals per step is not part of the path)
-        off = (i * 4099) % 65536
+        off = (i * 4096) % 65536                         # 16-byte aligned like any autograd-produced gradient
         g = gpool[off:off + emb.numel()].view(emb.shape)
         for p in params:
             p.grad = None
@@ -91,8 +98,12 @@ def main():
     s_max = input_ids.shape[1] + max(len(i) for i in ids_list)
     gpool = torch.randn(len(mine) * s_max * H + 65536, device=dev, dtype=torch.float32, generator=gen)
     timers = {"host_sim": 0.0}
+    prefetch = not (args.dense or args.no_prefetch)
+    n_total = args.warmup + args.steps
+    feed = iter(sim.TokenRowPrefetcher((tbatch for _ in range(n_total)), V, dev, seeds=(1000 + i for i in range(n_total)))) \
+        if prefetch else None
     for i in range(args.warmup):
-        step(i, timers)
+        step(i, timers, next(feed) if prefetch else None)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -101,7 +112,7 @@ def main():
     e0.record()
     n_rows = 0
     for i in range(args.steps):
-        n_rows = step(args.warmup + i, timers)
+        n_rows = step(args.warmup + i, timers, next(feed) if prefetch else None)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -126,8 +137,20 @@ def main():
             "global_batch": args.global_batch, "n_gpus": world, "token_rows_per_step": n_rows_global,
             "ms_per_step": per_step, "token_rows_per_s": n_rows_global / (per_step / 1e3),
             "gemm_tflops": flops / (per_step / 1e3) / 1e12,
-            "host_sim_ms_per_step": 1e3 * timers["host_sim"] / args.steps,
+            "host_sim_ms_per_step": 1e3 * timers["host_sim"] / args.steps, "simulator_prefetch": prefetch,
             "allreduce_bytes_per_rank": n_param * 4 if world > 1 else 0, "trainable_params": n_param}), flush=True)
+    if args.kernel_table and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(5):
+                step(1000 + i, timers)
+            torch.cuda.synchronize()
+        rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+        tot = sum(r[2] for r in rows)
+        print("| kernel | launches/step | us/step | share |\n|---|---:|---:|---:|", file=sys.stderr)
+        for k, c, t in sorted(rows, key=lambda r: -r[2]):
+            print(f"| `{k[:100]}` | {c / 5:.1f} | {t / 5:.1f} | {100 * t / tot:.1f}% |", file=sys.stderr)
+        print(f"device-busy total {tot / 5:.1f} us/step", file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 
