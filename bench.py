@@ -195,6 +195,8 @@ def b200_arm(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    import ps_slm_b200.dist as D
+    numa_cpus = D.bind_to_local_numa(local)          # before any pinned allocation: staging buffers land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, int(round(args.seconds / 0.06))
@@ -351,6 +353,7 @@ def b200_arm(args):
                             (B * (T + 4) * 25056 * 4 if args.materialize_logits else (f_kept + n_out) * 25088 * 2) / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "pcie": pcie,
+                "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
                 "api": "ps_slm_b200.bridge.HostPipeline.run (pinned host batches in/out, copies overlapped with kernels)"},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -142,3 +142,27 @@ def ref_projector(kind, encoder_dim, llm_dim, ds_rate=1):
            "linear": pmod.EncoderProjectorConcat,
            "simple_linear": pmod.EncoderProjectorLinear}[kind]
     return cls(cfg)
+
+
+def load_dataset_module():
+    """The reference's dataset/speech_dataset_large.py with its unused heavy imports (whisper, kaldiio, torchaudio)
+    stubbed — only ``MultiTaskDataset.collator`` / ``.pad``, ``MultiTaskDynamicBatchDataset`` and ``window_class``
+    (Multitask/dataset/speech_dataset_large.py:190-338) are exercised."""
+    if "dataset" in _cache:
+        return _cache["dataset"]
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    for name in ("whisper", "kaldiio", "torchaudio", "torchaudio.compliance", "torchaudio.compliance.kaldi"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []                                   # lets "import a.b.c" resolve through sys.modules
+            sys.modules[name] = m
+    sys.modules["torchaudio"].compliance = sys.modules["torchaudio.compliance"]
+    sys.modules["torchaudio.compliance"].kaldi = sys.modules["torchaudio.compliance.kaldi"]
+    loader = importlib.machinery.SourceFileLoader(
+        "tasu_reference_dataset", os.path.join(REF_ROOT, "dataset", "speech_dataset_large.py"))
+    spec = importlib.util.spec_from_loader(loader.name, loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    _cache["dataset"] = mod
+    return mod

@@ -8,7 +8,7 @@ all-reduce the projector gradients in training.
 * the gradient all-reduce replaces DeepSpeed ZeRO-2's reduce-scatter of the 54.5 M trainable
   projector parameters (Multitask/conf/ds_config.json:15-21, finetune_deepspeed.py:147-149).
 """
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -20,6 +20,30 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def bind_to_local_numa(device_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that pinned
+    staging buffers allocated afterwards are first-touched on the memory next to the GPU's PCIe root.  With one
+    process per GPU this keeps 8 ranks from pulling all their host↔device traffic through one socket.  Returns the
+    CPU list, or None when NVML / affinity is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 — affinity is an optimisation, never a requirement
+        return None
+
+
 def shard_indices(n: int, rank: int, world_size: int) -> List[int]:
     """Global utterance indices owned by ``rank`` (utterance i → rank i % W)."""
     return list(range(rank, n, world_size))
@@ -28,6 +52,36 @@ def shard_indices(n: int, rank: int, world_size: int) -> List[int]:
 def global_order(n: int, world_size: int) -> List[Tuple[int, int]]:
     """For every global utterance i: (owner rank, local index)."""
     return [(i % world_size, i // world_size) for i in range(n)]
+
+
+def length_grouped_partition(total_lens: Sequence[int], world_size: int) -> List[List[int]]:
+    """Re-deal a global batch to ``world_size`` ranks for padded batching: utterances are sorted by spliced length and
+    cut into contiguous groups (so every rank pads to a length close to its own sequences) whose PADDED areas
+    ``count x max_len`` are balanced — the smallest area cap for which a greedy cut needs at most ``world_size``
+    groups (binary search).  Returns the utterance indices per rank (ranks may hold different counts)."""
+    n = len(total_lens)
+    order = sorted(range(n), key=lambda u: (-int(total_lens[u]), u))
+    if n == 0:
+        return [[] for _ in range(world_size)]
+
+    def cut(cap):
+        groups, i = [], 0
+        while i < n:
+            mx = max(int(total_lens[order[i]]), 1)
+            k = max(1, cap // mx)
+            groups.append(order[i:i + k])
+            i += k
+        return groups
+
+    lo, hi = max(int(total_lens[order[0]]), 1), max(int(total_lens[order[0]]), 1) * n
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if len(cut(mid)) <= world_size:
+            hi = mid
+        else:
+            lo = mid + 1
+    groups = cut(lo)
+    return groups + [[] for _ in range(world_size - len(groups))]
 
 
 def all_gather_lengths(lens: torch.Tensor, group=None) -> List[torch.Tensor]:
@@ -60,7 +114,7 @@ def _gather_rows(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return flat.index_select(0, idx.long())
 
 
-def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing=None):
+def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing=None, return_host: bool = False):
     """Gather every rank's packed compressed rows ``[sum M_b, H]`` and lengths.
 
     Returns ``(rows_global [sum over all utterances, H], lens_global [n_utts])`` in GLOBAL utterance
@@ -69,7 +123,7 @@ def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing
     topology-aware ring needed) and one row-gather kernel that puts the rows in global order."""
     rank, W = world()
     if W == 1:
-        return rows, lens
+        return (rows, lens, lens.tolist()) if return_host else (rows, lens)
     all_lens = all_gather_lengths(lens, group)
     lens_host = [l.cpu() for l in all_lens]                      # the single device→host hand-off
     totals = [int(l.sum()) for l in lens_host]
@@ -96,7 +150,8 @@ def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing
     if rows.is_cuda:
         idx = idx.pin_memory().to(rows.device, non_blocking=True)
     rows_g = _gather_rows(flat, idx)
-    return rows_g, torch.tensor(glens, dtype=lens.dtype).to(lens.device)
+    lens_g = torch.tensor(glens, dtype=lens.dtype).to(lens.device)
+    return (rows_g, lens_g, glens) if return_host else (rows_g, lens_g)
 
 
 def _shared_flat(grads):

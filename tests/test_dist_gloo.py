@@ -63,3 +63,21 @@ def test_gather_and_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_length_grouped_partition():
+    import random
+
+    import ps_slm_b200.dist as D
+    rnd = random.Random(0)
+    for w in (1, 2, 8):
+        for n in (0, 1, 5, 64, 513):
+            tot = [rnd.choice([25, 40, 110, 160, 230]) + rnd.randint(0, 20) for _ in range(n)]
+            parts = D.length_grouped_partition(tot, w)
+            assert len(parts) == w and sorted(sum(parts, [])) == list(range(n))
+            if n >= 8 * w and w > 1:
+                area = [len(p) * max(tot[u] for u in p) for p in parts if p]
+                eff = sum(tot) / sum(area)
+                naive = [list(range(r, n, w)) for r in range(w)]
+                eff_naive = sum(tot) / sum(len(p) * max(tot[u] for u in p) for p in naive)
+                assert eff > eff_naive and max(area) <= 1.5 * (sum(area) / len(area)) + 260

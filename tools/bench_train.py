@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--global-batch", type=int, default=256)
+    ap.add_argument("--weak", action="store_true", help="--global-batch utterances PER GPU (weak scaling) instead of sharded")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--kernel-table", action="store_true",
@@ -49,8 +50,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     V, H = S.V_CTC, S.H_LLM
-    all_ids = S.make_transcripts(args.global_batch, V, seed=1234)
-    mine = D.shard_indices(args.global_batch, rank, world)
+    n_global = args.global_batch * (world if args.weak else 1)
+    all_ids = S.make_transcripts(n_global, V, seed=1234)
+    mine = D.shard_indices(n_global, rank, world)
     import numpy as np
     ids_list = [np.asarray(all_ids[i], dtype=np.int32) for i in mine]      # tokenisation is the data loader's job
     input_ids, mask, labels = S.make_prompts(len(mine), seed=rank, left_pad=False, target_lens=[len(i) for i in ids_list])
@@ -134,7 +136,7 @@ def main():
         print(json.dumps({
             "workload": "configs[2] text-only training step (simulated posteriors, projector fwd+bwd, grad all-reduce)",
             "path": "dense bf16 rows + tensor-core GEMM-1/G" if args.dense else "token-row projector (column gather/scatter of W1, GEMM-2/dW2/dh on tensor cores)",
-            "global_batch": args.global_batch, "n_gpus": world, "token_rows_per_step": n_rows_global,
+            "global_batch": n_global, "scaling": "weak" if args.weak else "strong", "n_gpus": world, "token_rows_per_step": n_rows_global,
             "ms_per_step": per_step, "token_rows_per_s": n_rows_global / (per_step / 1e3),
             "gemm_tflops": flops / (per_step / 1e3) / 1e12,
             "host_sim_ms_per_step": 1e3 * timers["host_sim"] / args.steps, "simulator_prefetch": prefetch,
