@@ -371,7 +371,11 @@ extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out
     TASU_CHECK_ARG(probs_bf16 && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)probs_bf16 % 16 == 0) && (ld % 8 == 0), "16-byte aligned rows");
     TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
-    pool_tail_kernel<<<persistent_grid(pool_tail_kernel, 256, n_out), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
+    // One CTA per potential work item (the live count is on the device; surplus CTAs exit at once): the hardware CTA
+    // scheduler then balances the ~2 k multi-frame rows dynamically — a persistent grid of SMs x occupancy CTAs leaves
+    // half the machine idle while the CTAs that drew 3 rows instead of 2 finish.
+    const int64_t grid = n_out < 0x7fffffffLL ? n_out : 0x7fffffffLL;
+    pool_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
                                                                          tail_src, multi_rows, multi_count, ln_mean,
                                                                          ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
