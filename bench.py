@@ -329,6 +329,8 @@ def b200_arm(args):
         else:
             ach, peak, unit = work / t / 1e12, pk["bf16_tflops"], "TFLOP/s"
         kernels[name] = {"bound": bound, "ms": avg[name], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+        if bound == "tensor":                       # for the record: against cuBLAS's best single-GEMM (burst) rate too
+            kernels[name]["frac_of_burst_peak"] = ach / pk["bf16_tflops_burst"]
     for name in avg:
         if name not in kernels:
             kernels[name] = {"ms": avg[name]}

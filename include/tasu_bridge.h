@@ -207,6 +207,15 @@ int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int
                         float* x_blank, float* row_max, float* row_sumexp, float* row_sumexp2,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* C[M,N] (fp32) = A · B with either operand in either storage order, no epilogue — the backward contractions of the
+ * projector without materialised transposes:  a_mn_major = 0: A is [M, K] (K contiguous), 1: A is [K, M] (M contiguous);
+ * b_mn_major = 0: B is [N, K] (K contiguous, nn.Linear layout), 1: B is [K, N] (N contiguous).  MN-major operands are
+ * fetched as [64 K-rows][64 MN] TMA boxes and consumed through MN-major UMMA shared-memory descriptors.
+ *   dW2 = dy^T · h : A = dy [rows, H] (a_mn_major = 1), B = h [rows, Hb] (b_mn_major = 1), K = rows
+ *   dh  = dy · W2  : A = dy [rows, H] (0),              B = W2 [H, Hb]  (b_mn_major = 1), K = H            */
+int tasu_gemm_bf16_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                       float* C, int64_t ldc, int M, int N, int K, void* stream);
+
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
                            void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,

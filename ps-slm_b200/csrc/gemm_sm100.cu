@@ -98,7 +98,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
+// MN-major (the operand is stored [K, MN] with MN contiguous), 128-byte swizzle: the canonical layout in 16-byte units is
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) — an atom is 8 K-rows x 128 B (64 MN elements); one TMA box [64 K-rows][64 MN] stacks
+// 8 atoms along K (SBO = 1024 B) and consecutive boxes (the next 64 MN elements) are 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(8192u >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major (bit 15 / 16 = A / B MN-major),
 // N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -153,7 +165,8 @@ struct Params {
 // kOutBf16: C is bf16 (64 columns per 128-byte staging row) else fp32 (32 columns)
 // kSt smem pipeline stages; kGroups epilogue warp-groups of 4 warps (2 groups interleave the 128-byte column
 // chunks of a tile, each with its own staging pair and TMA-store thread: for shallow-K, store-heavy shapes)
-template <bool kOutBf16, int kEpi, int kSt, int kGroups>
+// kMajor: bit 0 = A is MN-major ([K, M] in memory), bit 1 = B is MN-major ([K, N] in memory); 0 = both K-major ("TN")
+template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0>
 __global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -203,8 +216,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kStageBytes;
                     mbar_expect_tx(&full_bar[stage], kStageBytes);
-                    tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
-                    tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    if (kMajor & 1) {                               // [64 K-rows][64 M] boxes, 8 KB apart
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i) tma_load_2d(&tmap_a, &full_bar[stage], sa + i * 8192, m0 + 64 * i, kb * BK);
+                    } else {
+                        tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                    }
+                    if (kMajor & 2) {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes + i * 8192, n0 + 64 * i, kb * BK);
+                    } else {
+                        tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -214,6 +238,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            constexpr uint32_t idesc = kInstrDesc | ((uint32_t)(kMajor & 1) << 15) | ((uint32_t)((kMajor >> 1) & 1) << 16);
+            // per UMMA_K step: K-major advances 32 B inside the swizzle row (+2 in the >>4 address field); MN-major
+            // advances two 8-row K groups = 2048 B (+128)
+            constexpr uint64_t a_step = (kMajor & 1) ? 128 : 2, b_step = (kMajor & 2) ? 128 : 2;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
@@ -222,12 +250,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t adesc = make_smem_desc(sa);
-                    const uint64_t bdesc = make_smem_desc(sa + kABytes);
+                    const uint64_t adesc = (kMajor & 1) ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+                    const uint64_t bdesc = (kMajor & 2) ? make_smem_desc_mn(sa + kABytes) : make_smem_desc(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                        umma_bf16(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc,
                                   (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
@@ -750,11 +777,62 @@ static int launch_dispatch(bool out_bf16, int epilogue, bool shallow_k, int grid
                     : launch_epi<false>(epilogue, shallow_k, grid, st, ma, mb, mc, p);
 }
 
+template <int kSt, int kGroups, int kMajor>
+static int launch_major(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                        const Params& p) {
+    constexpr int smem = gemm_smem_bytes(kSt, kGroups);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, TASU_EPI_NONE, kSt, kGroups, kMajor>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
+    TASU_CHECK_CUDA(attr_err);
+    gemm_bf16_tn_kernel<false, TASU_EPI_NONE, kSt, kGroups, kMajor><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p);
+    return TASU_OK;
+}
+
 }  // namespace gemm
 }  // namespace tasu
 
 using namespace tasu;
 using namespace tasu::gemm;
+
+extern "C" int tasu_gemm_bf16_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                                  float* C, int64_t ldc, int M, int N, int K, void* stream) {
+    TASU_CHECK_ARG(M >= 0 && N > 0 && K > 0, "M >= 0, N,K > 0");
+    TASU_CHECK_ARG((a_mn_major == 0 || a_mn_major == 1) && (b_mn_major == 0 || b_mn_major == 1), "major flags are 0 or 1");
+    TASU_CHECK_ARG(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldc >= N, "leading dimension too small");
+    if (M == 0) return TASU_OK;
+    if (!a_mn_major && !b_mn_major)
+        return tasu_gemm_bf16_tn(A, lda, B, ldb, C, TASU_F32, ldc, M, N, K, TASU_EPI_NONE, nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, stream);
+    TASU_CHECK_ARG(A && B && C, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
+    TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * 4) % 16 == 0, "row pitches must be multiples of 16 bytes");
+    CUtensorMap ma, mb, mc;
+    int rc = a_mn_major ? make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda, BK, 64, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
+                        : make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+    rc = b_mn_major ? make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb, BK, 64, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
+                    : make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    rc = make_map(&mc, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldc, BM, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    Params p{M, N, K, nullptr, TASU_EPI_NONE, nullptr, nullptr, nullptr, nullptr};
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool sk = K <= 1024;
+    const int major = a_mn_major | (b_mn_major << 1);
+    if (major == 1) rc = sk ? launch_major<3, 2, 1>(grid, st, ma, mb, mc, p) : launch_major<4, 1, 1>(grid, st, ma, mb, mc, p);
+    else if (major == 2) rc = sk ? launch_major<3, 2, 2>(grid, st, ma, mb, mc, p) : launch_major<4, 1, 2>(grid, st, ma, mb, mc, p);
+    else rc = sk ? launch_major<3, 2, 3>(grid, st, ma, mb, mc, p) : launch_major<4, 1, 3>(grid, st, ma, mb, mc, p);
+    if (rc) return rc;
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
 
 extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                                  int64_t ldc, int M, int N, int K, int epilogue, const float* bias,

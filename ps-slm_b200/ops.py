@@ -261,6 +261,20 @@ def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out:
     return out
 
 
+def gemm_bf16_f32(A: torch.Tensor, a_mn_major: bool, Bw: torch.Tensor, b_mn_major: bool, M: int, N: int, K: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] fp32 = A · B with either operand K-major ([M|N, K]) or MN-major ([K, M|N]) in memory (tasu_gemm_bf16_f32)."""
+    _need_cuda(A, Bw, out)
+    if A.dtype != torch.bfloat16 or Bw.dtype != torch.bfloat16:
+        raise TypeError("GEMM operands must be bfloat16")
+    if out is None:
+        out = torch.empty(M, pad_to(N, 4), dtype=torch.float32, device=A.device)[:, :N]
+    L.check(L.lib().tasu_gemm_bf16_f32(A.data_ptr(), A.stride(0), int(a_mn_major), Bw.data_ptr(), Bw.stride(0), int(b_mn_major),
+                                       out.data_ptr(), out.stride(0), M, N, K, _stream()), "tasu_gemm_bf16_f32")
+    _count(1)
+    return out
+
+
 def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor, V: int, out: torch.Tensor,
                        out_row_stride: int, dst_row: Optional[torch.Tensor] = None,
                        ln_mean: Optional[torch.Tensor] = None, ln_rstd: Optional[torch.Tensor] = None,

@@ -235,3 +235,35 @@ def test_bridge_inference_vs_oracle(dev, ragged, labels, materialize):
     aerr = (e[audio] - e_r[audio]).norm() / e_r[audio].norm()
     assert aerr < 1e-2, f"audio embedding relative error {aerr}"
     assert torch.equal(e[~audio], e_r[~audio])
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 300, 520), (1536, 2048, 1737), (777, 2048, 1536), (64, 72, 3000)])
+def test_gemm_mn_major_operands(dev, a_mn, b_mn, M, N, K):
+    """tasu_gemm_bf16_f32: either operand stored [K, MN] (MN contiguous) — the projector's backward contractions
+    (dW2 = dy^T·h, dh = dy·W2) without materialised transposes — against the fp32 product of the same bf16 values."""
+    import ps_slm_b200.ops as ops
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)          # logical A [M, K], B [N, K]
+    Bm = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    ref = A.float() @ Bm.float().t()
+    p8 = lambda n: (n + 7) // 8 * 8                                # noqa: E731
+    if a_mn:                                                       # stored [K, M], padded pitch
+        a_store = torch.zeros(K, p8(M), dtype=torch.bfloat16)
+        a_store[:, :M] = A.t()
+        a_dev = a_store.to(dev)[:, :M]
+    else:
+        a_store = torch.zeros(M, p8(K), dtype=torch.bfloat16)
+        a_store[:, :K] = A
+        a_dev = a_store.to(dev)[:, :K]
+    if b_mn:
+        b_store = torch.zeros(K, p8(N), dtype=torch.bfloat16)
+        b_store[:, :N] = Bm.t()
+        b_dev = b_store.to(dev)[:, :N]
+    else:
+        b_store = torch.zeros(N, p8(K), dtype=torch.bfloat16)
+        b_store[:, :K] = Bm
+        b_dev = b_store.to(dev)[:, :K]
+    out = ops.gemm_bf16_f32(a_dev, a_mn, b_dev, b_mn, M, N, K)
+    err = ((out.cpu() - ref).norm() / ref.norm()).item()
+    assert err < 1e-3, f"relative error {err}"                    # exact bf16 products, (truncating) fp32 accumulation

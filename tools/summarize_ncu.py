@@ -64,7 +64,7 @@ if os.path.isfile(rep):
     stage_of = [("ctc_stats_kernel", "ctc_head_stats"), ("gemm_bf16_tn_kernel<1, 6", "ctc_softmax_gemm"),
                 ("gemm_bf16_tn_kernel<1, 4", "projector_gemm1"), ("gemm_bf16_tn_kernel<1, 1", "projector_gemm2"),
                 ("gemm_bf16_tn_kernel<0, 1", "ctc_lo_gemm"), ("pool_tail_kernel", "pool_tail"),
-                ("splice_scatter_kernel", "splice_scatter"), ("frame_stats_kernel", "frame_stats"),
+                ("splice_copy_kernel", "splice_scatter"), ("frame_stats_kernel", "frame_stats"),
                 ("meanpool_kernel", "softmax_meanpool"), ("gather_kept_rows_kernel", "gather_kept_rows")]
     tpath = os.path.join(out_dir, "traffic.json")
     traffic = json.load(open(tpath)) if os.path.isfile(tpath) else {}
@@ -96,4 +96,52 @@ if os.path.isfile(c):
     with open(os.path.join(out_dir, f"{tag}_clocks.txt"), "w") as f:
         f.write(f"samples={len(sm)} sm_mhz median={sm[len(sm) // 2] if sm else None} min={sm[0] if sm else None} max={sm[-1] if sm else None} "
                 f"reasons_active={active}\n")
+
+# ---- configs[2] training step / configs[3] mixed batch evidence (tools/gpu_bench_profile.sh)
+def _copy_json(src_name, dst_name):
+    src = os.path.join(go, src_name)
+    if os.path.isfile(src):
+        txt = open(src).read().strip()
+        if txt:
+            with open(os.path.join(out_dir, dst_name), "w") as f:
+                json.dump(json.loads(txt.splitlines()[-1]), f, indent=1)
+
+
+for a, b_ in ((f"train_{tag}.json", f"{tag}_train_bench.json"), (f"train_dense_{tag}.json", f"{tag}_train_dense_bench.json"),
+              (f"mixed_{tag}.json", f"{tag}_mixed_bench.json")):
+    _copy_json(a, b_)
+for n in (2, 4, 8):
+    for a, b_ in ((f"bench_n{n}_{tag}.json", f"{tag}_bench_n{n}.json"), (f"train_strong_n{n}_{tag}.json", f"{tag}_train_strong_n{n}.json"),
+                  (f"train_weak_n{n}_{tag}.json", f"{tag}_train_weak_n{n}.json"), (f"mixed_n{n}_{tag}.json", f"{tag}_mixed_n{n}.json")):
+        _copy_json(a, b_)
+tt = os.path.join(go, f"train_table_{tag}.md")
+if os.path.isfile(tt):
+    lines = [l for l in open(tt).read().splitlines() if l.startswith("|") or l.startswith("device-busy")]
+    with open(os.path.join(out_dir, f"{tag}_train_kernels.md"), "w") as f:
+        f.write(f"# text-only training step, in-situ kernel times — {tag}\n\n`python tools/bench_train.py --steps 50 --kernel-table` "
+                "(CUPTI via torch.profiler over 5 steps, kernels running back to back as in the timed loop)\n\n")
+        f.write("\n".join(lines) + "\n")
+tl = os.path.join(go, f"launches_train_{tag}.csv")
+if os.path.isfile(tl):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), tl, "3"], capture_output=True, text=True).stdout
+    with open(os.path.join(out_dir, f"{tag}_train_launches.md"), "w") as f:
+        f.write(f"# ncu launch list, text-only training step — {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none "
+                "python tools/bench_train.py --steps 2 --warmup 1 --no-prefetch` (cold-cache, serialised: compare shares)\n\n" + out)
+rep2 = os.path.join(go, f"prof_train_{tag}.ncu-rep")
+if os.path.isfile(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(raw.splitlines()))
+    hdr, units = rd[0], rd[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "launch__registers_per_thread",
+            "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct"]
+    idx = [(w, hdr.index(w)) for w in want if w in hdr]
+    with open(os.path.join(out_dir, f"{tag}_train_ncu_full.md"), "w") as f:
+        f.write(f"# ncu --set full, text-only training step kernels — {tag}\n\n")
+        for r in rd[2:]:
+            f.write("## " + r[hdr.index("Kernel Name")][:110] + "\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for w, i in idx:
+                f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+            f.write("\n")
 print("wrote", sorted(n for n in os.listdir(out_dir) if n.startswith(tag)))
