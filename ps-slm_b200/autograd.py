@@ -51,18 +51,15 @@ class LinearSiLUFunction(torch.autograd.Function):
             dy = dy.float()
         db2 = ops.colsum(dy)
         dyb, _, _ = ops.cast_rows(dy, torch.bfloat16) if dy.dtype != torch.bfloat16 else (dy, None, None)
-        dyT = ops.transpose_cast(dy, N, H)                        # [H, N]
-        hT = ops.transpose_cast(h, N, Hb)                         # [Hb, N]
+        # the three backward contractions read dy, h, W2 and x where they lie (MN-major GEMM operands): no transposes
         dw2 = torch.empty(H, Hb, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_tn(dyT, hT, H, Hb, N, dw2)                  # dW2 = dyᵀ·h
-        w2T = ops.transpose_cast(w2.detach(), H, Hb)              # [Hb, H]
+        ops.gemm_bf16_f32(dyb, True, h, True, H, Hb, N, dw2)      # dW2 = dyᵀ·h
         dh = torch.empty(N, Hb, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_tn(dyb, w2T, N, Hb, H, dh)                  # dh = dy·W2
+        ops.gemm_bf16_f32(dyb, False, cast_weight_bf16(w2), True, N, Hb, H, dh)   # dh = dy·W2
         dzsT, db1, g0 = ops.silu_bwd(dh, z, rstd, mean)           # [Hb, N] = (rstd·dz)ᵀ
-        xT = ops.transpose_cast(xb, N, V)                         # [V, N]
         ldv = ops.pad_to(V, 4)
         G = torch.empty(Hb, ldv, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_tn(dzsT, xT, Hb, V, N, G)                   # G = (rstd·dz)ᵀ·x
+        ops.gemm_bf16_f32(dzsT, False, xb, True, Hb, V, N, G)     # G = (rstd·dz)ᵀ·x
         dw1, dgamma, dbeta = ops.linear_silu_wgrad_finish(G, w1.detach().float().contiguous(),
                                                           gamma.detach().float().contiguous(),
                                                           beta.detach().float().contiguous(), g0, db1)

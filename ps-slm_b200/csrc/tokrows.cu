@@ -524,7 +524,7 @@ static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 static inline int64_t pad_to(int64_t n, int64_t a) { return (n + a - 1) / a * a; }
 
 struct TrainWs {
-    int64_t S, D, w2b, dyb, dyT, hT, w2T, dh, P, part, E, slot, total;
+    int64_t S, D, w2b, dyb, dh, P, part, E, slot, total;
 };
 static TrainWs train_ws(int64_t n, int n_uniq, int V, int Hb, int H) {
     TrainWs w;
@@ -533,9 +533,6 @@ static TrainWs train_ws(int64_t n, int n_uniq, int V, int Hb, int H) {
     w.D = o; o += al256(4LL * Hb);
     w.w2b = o; o += al256(2LL * H * pad_to(Hb, 64));
     w.dyb = o; o += al256(2LL * (n > 0 ? n : 1) * pad_to(H, 8));
-    w.dyT = o; o += al256(2LL * H * pad_to(n > 0 ? n : 1, 8));
-    w.hT = o; o += al256(2LL * Hb * pad_to(n > 0 ? n : 1, 8));
-    w.w2T = o; o += al256(2LL * Hb * pad_to(H, 8));
     w.dh = o; o += al256(4LL * (n > 0 ? n : 1) * Hb);
     w.P = o; o += al256(4LL * (n_uniq > 0 ? n_uniq : 1) * Hb);
     {
@@ -607,11 +604,9 @@ extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t
         TASU_CHECK_CUDA(cudaMemset2DAsync(dw2, 4 * dw2_stride, 0, 4LL * Hb, H, st));
         return TASU_OK;
     }
-    const int64_t ldn = pad_to(n_rows, 8), ldh8 = pad_to(H, 8);
+    const int64_t ldh8 = pad_to(H, 8), ldw2 = pad_to(Hb, 64);
     void* dyb = wsb + ws.dyb;
-    void* dyT = wsb + ws.dyT;
-    void* hT = wsb + ws.hT;
-    void* w2T = wsb + ws.w2T;
+    void* w2b = wsb + ws.w2b;
     float* dh = (float*)(wsb + ws.dh);
     float* P = (float*)(wsb + ws.P);
     float* E = (float*)(wsb + ws.E);
@@ -622,13 +617,10 @@ extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t
         TASU_TRY(tasu_cast_rows(dy, dy_dtype, n_rows, H, ldy, dyb, TASU_BF16, ldh8, nullptr, nullptr, 0.f, stream));
         dy_bf16 = dyb; ld_dyb = ldh8;
     }
-    TASU_TRY(tasu_transpose_cast(dy, dy_dtype, n_rows, H, ldy, nullptr, dyT, ldn, stream));          // [H, N]
-    TASU_TRY(tasu_transpose_cast(h_bf16, TASU_BF16, n_rows, Hb, Hb, nullptr, hT, ldn, stream));       // [Hb, N]
-    TASU_TRY(tasu_gemm_bf16_tn(dyT, ldn, hT, ldn, dw2, TASU_F32, dw2_stride, H, Hb, (int)n_rows, TASU_EPI_NONE, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, stream));                                    // dW2 = dy^T · h
-    TASU_TRY(tasu_transpose_cast(w2, TASU_F32, H, Hb, w2_stride, nullptr, w2T, ldh8, stream));         // [Hb, H]
-    TASU_TRY(tasu_gemm_bf16_tn(dy_bf16, ld_dyb, w2T, ldh8, dh, TASU_F32, Hb, (int)n_rows, Hb, H, TASU_EPI_NONE, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, stream));                                    // dh = dy · W2
+    TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
+    // both contractions read dy, h and W2 where they lie (MN-major operands): no transposed copies
+    TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 1, h_bf16, Hb, 1, dw2, dw2_stride, H, Hb, (int)n_rows, stream));   // dW2 = dy^T · h
+    TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 0, w2b, ldw2, 1, dh, Hb, (int)n_rows, Hb, H, stream));              // dh = dy · W2
     TASU_TRY(tasu_tokrow_bwd_rows(dh, z, n_rows, Hb, seg_off, perm, row_a, row_e, n_uniq, P, db1, E, wsb + ws.part,
                                   ws.E - ws.part, stream));
     TASU_TRY(tasu_tokrow_wgrad_finish(P, uniq, n_uniq, (int32_t*)(wsb + ws.slot), w1, w1_stride, gamma, beta, E, db1, Hb, V, dw1,
