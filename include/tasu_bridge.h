@@ -298,6 +298,11 @@ int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* gamma, cons
 /* training forward (W1 changes every step): ONE dense pass over W1 gives S, D and the compact gamma-scaled
  * columns colT[u,:] = gamma[uniq[u]]*W1[:,uniq[u]] (every sector of W1 read once instead of one sector per element) */
 int64_t tasu_tokrow_cols_workspace(int V, int Hb);
+/* row pass on the compact columns: one warp per row, z / h / row_a / row_e as tasu_tokrow_fwd; row_slot_ws = int32[n_rows] */
+int tasu_tokrow_rows_fwd(const float* colT, const float* S, const float* D, const int32_t* seg_off,
+                         const int32_t* perm, const float* hot, const float* base, int n_uniq, int64_t n_rows,
+                         int V, int Hb, float ln_eps, float* z, void* h_bf16, float* row_a, float* row_e,
+                         int32_t* row_slot_ws, void* stream);
 int tasu_tokrow_cols(const float* w1, int64_t w1_stride, const float* gamma, const float* beta, const float* b1,
                      const int32_t* uniq, int n_uniq, int V, int Hb, float* colT, float* S, float* D,
                      void* workspace, int64_t workspace_bytes, void* stream);

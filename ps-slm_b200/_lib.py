@@ -52,6 +52,7 @@ SIGNATURES = {
     "tasu_linear_rowdots": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _P, _P]),
     "tasu_tokrow_fwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "tasu_tokrow_cols_workspace": (_L, [_I, _I]),
+    "tasu_tokrow_rows_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "tasu_tokrow_cols": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
     "tasu_tokrow_bwd_workspace": (_L, [_I, _I]),
     "tasu_tokrow_bwd_rows": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P]),

@@ -95,6 +95,53 @@ tokrow_fwd_kernel(const float* __restrict__ w1, int64_t wstride, const float* __
     }
 }
 
+// row_slot[perm[i]] = u for seg_off[u] <= i < seg_off[u+1]  (one thread per sorted position, binary search)
+__global__ void __launch_bounds__(256)
+row_slot_kernel(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ perm, int n_uniq, int64_t n_rows,
+                int32_t* __restrict__ row_slot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    int lo = 0, hi = n_uniq;                                   // largest u with seg_off[u] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= (int)i) lo = mid; else hi = mid; }
+    row_slot[perm[i]] = lo;
+}
+
+// Training forward, row pass: one WARP per row, no shared memory, no barriers.  z[r,:] = a·colT[slot(r),:] + e·S + D,
+// h = bf16(silu(z)); the compact column colT[u] (8 KB) is streamed from L2 (rows of the same token re-read it there).
+__global__ void __launch_bounds__(256)
+tokrow_rows_kernel(const float* __restrict__ colT, const int32_t* __restrict__ row_slot, const float* __restrict__ S,
+                   const float* __restrict__ D, const float* __restrict__ hot, const float* __restrict__ base, int64_t n_rows,
+                   int V, int Hb, float eps, float* __restrict__ z, __nv_bfloat16* __restrict__ h, float* __restrict__ row_a,
+                   float* __restrict__ row_e) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += nwarp) {
+        const float* c = colT + (int64_t)row_slot[r] * Hb;
+        const double hv = (double)hot[r], bv = (double)base[r];
+        const double mean = (hv + (double)(V - 1) * bv) / V;
+        double var = (hv * hv + (double)(V - 1) * bv * bv) / V - mean * mean;
+        var = var < 0 ? 0 : var;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const float a = (float)(rstd * (hv - bv)), e = (float)(rstd * (bv - mean));
+        if (lane == 0) { row_a[r] = a; row_e[r] = e; }
+        float* zr = z ? z + r * Hb : nullptr;
+        __nv_bfloat16* hr = h + r * Hb;
+        for (int j = lane * 8; j < Hb; j += 256) {
+            const float4 c0 = *reinterpret_cast<const float4*>(c + j), c1 = *reinterpret_cast<const float4*>(c + j + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(S + j), s1 = *reinterpret_cast<const float4*>(S + j + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(D + j), d1 = *reinterpret_cast<const float4*>(D + j + 4);
+            float4 z0, z1;
+            z0.x = fmaf(a, c0.x, fmaf(e, s0.x, d0.x)); z0.y = fmaf(a, c0.y, fmaf(e, s0.y, d0.y));
+            z0.z = fmaf(a, c0.z, fmaf(e, s0.z, d0.z)); z0.w = fmaf(a, c0.w, fmaf(e, s0.w, d0.w));
+            z1.x = fmaf(a, c1.x, fmaf(e, s1.x, d1.x)); z1.y = fmaf(a, c1.y, fmaf(e, s1.y, d1.y));
+            z1.z = fmaf(a, c1.z, fmaf(e, s1.z, d1.z)); z1.w = fmaf(a, c1.w, fmaf(e, s1.w, d1.w));
+            if (zr) { *reinterpret_cast<float4*>(zr + j) = z0; *reinterpret_cast<float4*>(zr + j + 4) = z1; }
+            *reinterpret_cast<uint4*>(hr + j) = make_uint4(pack_bf16x2(silu_f(z0.x), silu_f(z0.y)), pack_bf16x2(silu_f(z0.z), silu_f(z0.w)),
+                                                           pack_bf16x2(silu_f(z1.x), silu_f(z1.y)), pack_bf16x2(silu_f(z1.z), silu_f(z1.w)));
+        }
+    }
+}
+
 __device__ __forceinline__ float silu_grad(float zz) {
     const float s = 1.f / (1.f + __expf(-zz));
     return s * (1.f + zz * (1.f - s));
@@ -249,13 +296,14 @@ slot_scatter_kernel(const int32_t* __restrict__ uniq, int n_uniq, int32_t* __res
 // dW1 / dγ / dβ in one pass over W1: CTA = 32 vocabulary columns x ALL output features (so dγ/dβ need no atomics),
 // 64 features per iteration; the compact P rows ([n_uniq, Hb], j contiguous) are transposed through shared memory
 // into the [j, v] orientation of W1 / dW1.  8 independent loads per thread in flight in each phase.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 tokrow_wgrad_finish_kernel(const float* __restrict__ P, const int32_t* __restrict__ slot, const float* __restrict__ w1,
                            int64_t wstride, const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ E, const float* __restrict__ db1, int Hb, int V,
                            float* __restrict__ dw1, int64_t dstride, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    // 6 CTAs per SM (<= 40 registers): the ceil(V/32) = 783 CTAs of the real shape are resident in ONE wave
     extern __shared__ float s_vec[];                            // E[Hb] | db1[Hb]
-    __shared__ float tile[32][65];
+    __shared__ float tile[32][33];
     __shared__ float s_ag[8][32], s_ab[8][32];
     __shared__ int s_slot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,33 +315,24 @@ tokrow_wgrad_finish_kernel(const float* __restrict__ P, const int32_t* __restric
     const float gm = vok ? gamma[v] : 0.f, bt = vok ? beta[v] : 0.f;
     float ag = 0.f, ab = 0.f;
     __syncthreads();
-    const float* pr[4];
-    bool has[4];
+    const float* wp = w1 + (int64_t)(warp * 4) * wstride + v;
+    float* dp = dw1 + (int64_t)(warp * 4) * dstride + v;
+    for (int j0 = 0; j0 < Hb; j0 += 32) {
+        float pv[4], wv[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int sl = s_slot[warp * 4 + q];
-        has[q] = sl >= 0;
-        pr[q] = P + (int64_t)(sl < 0 ? 0 : sl) * Hb + lane;
-    }
-    const float* wp = w1 + (int64_t)(warp * 8) * wstride + v;
-    float* dp = dw1 + (int64_t)(warp * 8) * dstride + v;
-    for (int j0 = 0; j0 < Hb; j0 += 64) {
-        float pv[4][2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                          // P rows → tile[v][j]
-            pv[q][0] = (has[q] && j0 + lane < Hb) ? pr[q][j0] : 0.f;
-            pv[q][1] = (has[q] && j0 + 32 + lane < Hb) ? pr[q][j0 + 32] : 0.f;
+        for (int q = 0; q < 4; ++q) {                          // P rows of this warp's 4 columns → tile[v][j]
+            const int sl = s_slot[warp * 4 + q];
+            pv[q] = (sl >= 0 && j0 + lane < Hb) ? P[(int64_t)sl * Hb + j0 + lane] : 0.f;
         }
-        float wv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)                            // W1 loads do not depend on the tile: issue them now
-            wv[q] = (vok && j0 + warp * 8 + q < Hb) ? wp[(int64_t)(j0 + q) * wstride] : 0.f;
+        for (int q = 0; q < 4; ++q)                            // W1 loads do not depend on the tile: issue them now
+            wv[q] = (vok && j0 + warp * 4 + q < Hb) ? wp[(int64_t)(j0 + q) * wstride] : 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { tile[warp * 4 + q][lane] = pv[q][0]; tile[warp * 4 + q][32 + lane] = pv[q][1]; }
+        for (int q = 0; q < 4; ++q) tile[warp * 4 + q][lane] = pv[q];
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int jl = warp * 8 + q, j = j0 + jl;
+        for (int q = 0; q < 4; ++q) {
+            const int jl = warp * 4 + q, j = j0 + jl;
             if (j < Hb && vok) {
                 const float d = tile[lane][jl] + s_vec[j];
                 const float db = s_vec[Hb + j];
@@ -428,6 +467,25 @@ extern "C" int tasu_tokrow_fwd(const float* w1, int64_t w1_stride, const float* 
     return TASU_OK;
 }
 
+extern "C" int tasu_tokrow_rows_fwd(const float* colT, const float* S, const float* D, const int32_t* seg_off,
+                                    const int32_t* perm, const float* hot, const float* base, int n_uniq, int64_t n_rows,
+                                    int V, int Hb, float ln_eps, float* z, void* h_bf16, float* row_a, float* row_e,
+                                    int32_t* row_slot_ws, void* stream) {
+    TASU_CHECK_ARG(n_uniq >= 0 && n_rows >= 0 && V > 0 && Hb > 0 && Hb % 8 == 0, "shape (Hb multiple of 8)");
+    if (n_uniq == 0 || n_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(colT && S && D && seg_off && perm && hot && base && h_bf16 && row_a && row_e && row_slot_ws, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)colT % 16 == 0) && ((uintptr_t)S % 16 == 0) && ((uintptr_t)D % 16 == 0) &&
+                   ((uintptr_t)h_bf16 % 16 == 0) && (z == nullptr || (uintptr_t)z % 16 == 0), "16-byte alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    row_slot_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(seg_off, perm, n_uniq, n_rows, row_slot_ws);
+    int64_t grid = (n_rows + 7) / 8, gmax = (int64_t)sm_count() * 8;
+    if (grid > gmax) grid = gmax;
+    tokrow_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(colT, row_slot_ws, S, D, hot, base, n_rows, V, Hb, ln_eps, z,
+                                                      (__nv_bfloat16*)h_bf16, row_a, row_e);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
 extern "C" int64_t tasu_tokrow_cols_workspace(int V, int Hb) {
     if (V <= 0 || Hb <= 0) return 0;
     return (int64_t)((V + 31) / 32) * 2 * Hb * (int64_t)sizeof(float) + 4LL * ((V + 63) / 64 * 64);
@@ -540,7 +598,7 @@ static TrainWs train_ws(int64_t n, int n_uniq, int V, int Hb, int H) {
         w.part = o; o += al256(a > b ? a : b);
     }
     w.E = o; o += al256(4LL * Hb);
-    w.slot = o; o += al256(4LL * V);
+    w.slot = o; o += al256(4LL * (V > n ? V : n));      // finish: slot[V]; forward rows: row_slot[n_rows]
     w.total = o;
     return w;
 }
@@ -572,8 +630,8 @@ extern "C" int tasu_tokrow_linear_silu_fwd(const float* w1, int64_t w1_stride, c
     const int64_t ldw2 = pad_to(Hb, 64);
     float* colT = (float*)(wsb + ws.P);                      // the forward's compact columns share the backward's P area
     TASU_TRY(tasu_tokrow_cols(w1, w1_stride, gamma, beta, b1, uniq, n_uniq, V, Hb, colT, S, D, wsb + ws.part, ws.E - ws.part, stream));
-    TASU_TRY(tasu_tokrow_fwd(w1, w1_stride, gamma, S, D, uniq, seg_off, perm, hot, base, n_uniq, n_rows, V, Hb, ln_eps, z, h_bf16,
-                             row_a, row_e, colT, stream));
+    TASU_TRY(tasu_tokrow_rows_fwd(colT, S, D, seg_off, perm, hot, base, n_uniq, n_rows, V, Hb, ln_eps, z, h_bf16, row_a, row_e,
+                                  (int32_t*)(wsb + ws.slot), stream));
     TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
     TASU_TRY(tasu_gemm_bf16_tn(h_bf16, Hb, w2b, ldw2, y, y_dtype, ldy, (int)n_rows, H, Hb, TASU_EPI_BIAS, b2, nullptr, nullptr,
                                nullptr, nullptr, stream));

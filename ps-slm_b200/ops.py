@@ -640,6 +640,14 @@ def tokrow_fwd(w1: torch.Tensor, gamma: torch.Tensor, S: torch.Tensor, D: torch.
     h = torch.empty(max(n, 1), Hb, dtype=torch.bfloat16, device=dev)[:n]
     row_a = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
     row_e = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    if colT is not None:                                       # training forward: warp-per-row pass on compact columns
+        slot_ws = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        L.check(L.lib().tasu_tokrow_rows_fwd(colT.data_ptr(), S.data_ptr(), D.data_ptr(), rows.seg_off.data_ptr(),
+                                             rows.perm.data_ptr(), rows.hot.data_ptr(), rows.base.data_ptr(), rows.n_uniq, n,
+                                             V, Hb, float(ln_eps), _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(),
+                                             slot_ws.data_ptr(), _stream()), "tasu_tokrow_rows_fwd")
+        _count(2)
+        return z, h, row_a, row_e
     L.check(L.lib().tasu_tokrow_fwd(w1.data_ptr(), w1.stride(0), gamma.float().contiguous().data_ptr(), S.data_ptr(),
                                     D.data_ptr(), rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(),
                                     rows.hot.data_ptr(), rows.base.data_ptr(), rows.n_uniq, n, V, Hb, float(ln_eps),
