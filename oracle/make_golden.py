@@ -204,7 +204,8 @@ def golden_model():
     out = {}
     for name in F.CASES:
         inp = F.build_inputs(name)
-        cls = {"linear-silu": pmod.EncoderProjectorLinearSiLU, "linear": pmod.EncoderProjectorConcat}[inp["proj"]]
+        cls = {"linear-silu": pmod.EncoderProjectorLinearSiLU, "linear": pmod.EncoderProjectorConcat,
+               "cross-attention": pmod.EncoderProjectorCTCCA}[inp["proj"]]
         encoder, llm, projector, tok, train_config, model_config = F.build_parts(inp, cls)
         m = mod.slam_model_asr.__new__(mod.slam_model_asr)
         torch.nn.Module.__init__(m)
@@ -213,7 +214,7 @@ def golden_model():
         m.train_config, m.model_config = train_config, model_config
         for k, v in inp["flags"].items():
             setattr(m, k, v)
-        m.cross_attn = False
+        m.cross_attn = inp["proj"] == "cross-attention"       # ps-slm.py:229
         m.encoder_tokenizer = F.FakeCTCTokenizer()
         torch.manual_seed(4321)                         # RNG stream of the noisy simulator
         with contextlib.redirect_stdout(io.StringIO()):

@@ -140,7 +140,8 @@ def ref_projector(kind, encoder_dim, llm_dim, ds_rate=1):
                                 encoder_projector_ds_rate=ds_rate)
     cls = {"linear-silu": pmod.EncoderProjectorLinearSiLU,
            "linear": pmod.EncoderProjectorConcat,
-           "simple_linear": pmod.EncoderProjectorLinear}[kind]
+           "simple_linear": pmod.EncoderProjectorLinear,
+           "cross-attention": pmod.EncoderProjectorCTCCA}[kind]
     return cls(cfg)
 
 

@@ -261,6 +261,21 @@ def projector_linear(x, k, w, b):
     return F.linear(_downsample(x, k), w, b)
 
 
+def projector_ctcca(post, llm_embed, wq, n_heads: int = 8):
+    """Cross-attention projector ``EncoderProjectorCTCCA.forward`` — projector.py:104-126: Q = W_q·post, multi-head
+    softmax attention of Q over the LLM embedding table (keys = values = table), heads concatenated."""
+    B, T, _ = post.shape
+    Q = F.linear(post, wq)                                         # :113
+    h = n_heads
+    d = Q.size(-1) // h
+    q = Q.view(B, T, h, d)
+    k = llm_embed.view(-1, h, d)
+    scores = torch.einsum("bthd,vhd->bthv", q, k) / d ** 0.5        # :121
+    attn = scores.softmax(dim=-1)                                  # :122
+    z = torch.einsum("bthv,vhd->bthd", attn, k)                    # :123
+    return z.contiguous().view(B, T, -1)                           # :124
+
+
 # --------------------------------------------------------------------------
 # (a8) splice — Multitask/model/ps-slm.py:679-873
 # --------------------------------------------------------------------------

@@ -121,8 +121,10 @@ class slam_model_asr(nn.Module):
         self.gt_emb_noise = _cfg_get(train_config, "gt_emb_noise", False)
         self.top1_emb = _cfg_get(train_config, "top1_emb", False)
         self.cross_attn = model_config.encoder_projector == "cross-attention"
-        if self.voca_trans or self.cross_attn:
-            raise NotImplementedError("voca_trans / cross-attention are 'next' rows of the scope table (SURVEY §8f)")
+        if self.voca_trans:
+            # the reference's own voca_trans branch reads `encoder_outs` before assigning it (ps-slm.py:488, :618)
+            raise NotImplementedError("voca_trans has no runnable reference behaviour (UnboundLocalError at ps-slm.py:488); "
+                                      "it is a 'next' row of the scope table (SURVEY §8f)")
         self.encoder_tokenizer = kwargs.get("encoder_tokenizer", None)
         if self.encoder_tokenizer is None and (self.gt_emb or kwargs.get("need_encoder_tokenizer", False)):
             ref = _load_reference_module()           # SentencePiece wrapper of the reference (host-side, out of scope)
@@ -236,8 +238,11 @@ class slam_model_asr(nn.Module):
                 encoder_outs, feat_len = self.psd(encoder_out, encoder_out_lens, post, blank)
             else:
                 encoder_outs, feat_len = encoder_out, encoder_out_lens
-        projector_outs = self.encoder_projector(encoder_outs)
-        feat_len = feat_len // self.encoder_projector.k
+        if self.cross_attn and self.ctc_posterior:                 # ps-slm.py:475-480 / :605-610
+            projector_outs = self.encoder_projector(encoder_outs, table.detach())
+        else:
+            projector_outs = self.encoder_projector(encoder_outs)
+            feat_len = feat_len // self.encoder_projector.k
         inputs_embeds = self.llm.get_input_embeddings()(input_ids)
         emb, mask, out_labels, pos, _ = self._merge_input_ids_with_audio_features(
             projector_outs, feat_len, inputs_embeds, input_ids, attention_mask, labels)

@@ -9,6 +9,7 @@ DeepSpeed/AdamW own ordinary ``nn.Parameter``s:
 * ``EncoderProjectorLinearSiLU`` ("linear-silu", default) ← projector.py:129-151
 * ``EncoderProjectorConcat``     ("linear")              ← projector.py:29-50
 * ``EncoderProjectorLinear``     ("simple_linear")       ← projector.py:10-26
+* ``EncoderProjectorCTCCA``      ("cross-attention")     ← projector.py:104-126 (inference)
 
 The Linear layers run as bf16 tcgen05 GEMMs with fp32 accumulation (libtasu_bridge.so); the
 LayerNorm of the default projector is folded into GEMM-1's epilogue.  There is no PyTorch
@@ -202,8 +203,79 @@ class EncoderProjectorLinear(nn.Module):
         return y.view(B, T, ld)[:, :, :self.llm_vocab]
 
 
+class EncoderProjectorCTCCA(nn.Module):
+    """Cross-attention projector — projector.py:104-126 ("cross-attention", called as
+    ``encoder_projector(posterior, llm_embedding)``, ps-slm.py:475-480): ``Q = W_q·post``; 8-head softmax attention of Q
+    over the LLM embedding table (keys = values = the table), heads concatenated.
+
+    Composed from the bridge's tensor-core kernels, one head at a time, without ever holding the reference's
+    ``[B, T, 8, 151936]`` fp32 score tensor (40 GB at config-2 size):
+      1. ``Q`` (bf16, pre-scaled by 1/sqrt(d) through the cached weight copy)  — ``tasu_gemm_bf16_tn``
+      2. per head: row max / sum-exp of ``Q_h·K_hᵀ`` from the stats epilogue    — ``tasu_ctc_head_stats`` (no scores in HBM)
+      3. per head: probabilities ``P_h`` (bf16, ``[rows, V2]``, one reused buffer) — ``tasu_gemm_bf16_tn(EPI_SOFTMAX)``
+      4. per head: ``Z_h = P_h·V_h`` with the table slice read in place (MN-major B operand) — ``tasu_gemm_bf16_f32``
+    Inference only: the attention backward is not implemented (a training call raises)."""
+
+    def __init__(self, config, n_heads=8):
+        super().__init__()
+        self.W_q = nn.Linear(config.encoder_dim, config.llm_dim, bias=False)
+        self.n_heads = n_heads
+        self._cache = ProjectorCache()
+        self._tcache = ProjectorCache()
+
+    def forward(self, post, llm_embed):
+        if torch.is_grad_enabled() and (post.requires_grad or self.W_q.weight.requires_grad):
+            raise NotImplementedError("the cross-attention projector of the B200 bridge is inference-only "
+                                      "(call under torch.no_grad(); its backward is a 'next' row, DESIGN.md §6)")
+        B, T, V1 = post.shape
+        N, D, h = B * T, self.W_q.weight.shape[0], self.n_heads
+        d = D // h
+        V2 = llm_embed.shape[0]
+        dev = post.device
+        out_dtype = post.dtype if post.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        if N == 0:
+            return torch.zeros(B, T, D, dtype=out_dtype, device=dev)
+
+        def build_w():
+            with torch.no_grad():                                  # scores / sqrt(d): folded into the cached weight
+                return cast_weight_bf16(self.W_q.weight.detach().float() * (d ** -0.5))
+        wq = self._cache.get([self.W_q.weight], build_w)
+
+        def build_t():
+            t = llm_embed.detach()
+            return t.contiguous() if t.dtype == torch.bfloat16 else ops.cast_rows(t.contiguous(), torch.bfloat16)[0]
+        table = self._tcache.get([llm_embed], build_t)
+        xb, _, _ = _rows_bf16(post.reshape(N, V1), False)
+        Q = torch.empty(N, ops.pad_to(D, 8), dtype=torch.bfloat16, device=dev)
+        ops.gemm_bf16_tn(xb, wq, N, D, V1, Q)
+        Q = Q[:, :D]
+        dp = d
+        if d % 8 != 0:
+            # head slices must start on 16-byte boundaries for TMA: zero-pad every head to a multiple of 8 columns
+            # (zero columns change neither the scores nor the outputs); Qwen2.5-1.5B (d = 192) never takes this branch
+            dp = ops.pad_to(d, 8)
+            Qp = torch.zeros(N, h, dp, dtype=torch.bfloat16, device=dev)
+            Qp[:, :, :d] = Q.reshape(N, h, d)
+            Tp = torch.zeros(V2, h, dp, dtype=torch.bfloat16, device=dev)
+            Tp[:, :, :d] = table.reshape(V2, h, d)
+            Q, table = Qp.view(N, h * dp), Tp.view(V2, h * dp)
+        Z = torch.empty(N, h * dp, dtype=torch.float32, device=dev)
+        P = torch.empty(N, ops.pad_to(V2), dtype=torch.bfloat16, device=dev)      # one head's probabilities at a time
+        zero_bias = torch.zeros(V2, dtype=torch.float32, device=dev)
+        for i in range(h):
+            qh, kh = Q[:, i * dp:(i + 1) * dp], table[:, i * dp:(i + 1) * dp]
+            st = ops.ctc_head_stats(qh, kh, None, 1, N, 0, V2, dp, 0)
+            inv = torch.reciprocal(st.row_sumexp)
+            ops.gemm_bf16_tn(qh, kh, N, V2, dp, P, L.EPI_SOFTMAX, zero_bias, inv, st.row_max)
+            ops.gemm_bf16_f32(P, False, kh, True, N, dp, V2, Z[:, i * dp:(i + 1) * dp])
+        if dp != d:
+            Z = Z.view(N, h, dp)[:, :, :d].reshape(N, D)
+        return Z.view(B, T, D).to(out_dtype)
+
+
 PROJECTORS = {
     "linear": EncoderProjectorConcat,
     "linear-silu": EncoderProjectorLinearSiLU,
     "simple_linear": EncoderProjectorLinear,
+    "cross-attention": EncoderProjectorCTCCA,
 }

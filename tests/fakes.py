@@ -147,6 +147,8 @@ CASES = {
                         "linear", D, 2, True, False, "generate"),
     "posterior_nopsd": (dict(ctc_posterior=True, do_psd=False, voca_trans=False, gt_emb=False, gt_emb_noise=False, top1_emb=False),
                         "linear-silu", V, 1, True, False, "generate"),
+    "infer_cross_attn": (dict(ctc_posterior=True, do_psd=True, voca_trans=False, gt_emb=False, gt_emb_noise=False, top1_emb=False),
+                         "cross-attention", V, 1, True, False, "generate"),
 }
 
 

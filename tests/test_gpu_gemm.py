@@ -267,3 +267,26 @@ def test_gemm_mn_major_operands(dev, a_mn, b_mn, M, N, K):
     out = ops.gemm_bf16_f32(a_dev, a_mn, b_dev, b_mn, M, N, K)
     err = ((out.cpu() - ref).norm() / ref.norm()).item()
     assert err < 1e-3, f"relative error {err}"                    # exact bf16 products, (truncating) fp32 accumulation
+
+
+@pytest.mark.parametrize("V1,D,V2,B,T", [(300, 64, 1000, 2, 37), (61, 48, 200, 3, 20), (25055, 1536, 4099, 1, 150)])
+def test_cross_attention_projector(dev, V1, D, V2, B, T):
+    """EncoderProjectorCTCCA (projector.py:104-126) composed from the stats / softmax / MN-major GEMM kernels vs the
+    fp32 oracle; d = D/8 = 6 exercises the head-padding branch, d = 192 is the Qwen2.5-1.5B shape."""
+    import ps_slm_b200.projector as P
+    torch.manual_seed(V1 + D)
+    m = P.EncoderProjectorCTCCA(types.SimpleNamespace(encoder_dim=V1, llm_dim=D, encoder_projector_ds_rate=1))
+    post = torch.softmax(torch.randn(B, T, V1) * 4, -1)
+    post[0, T - 3:] = 0                                              # zero-padded rows as psd() emits them
+    table = torch.randn(V2, D) * 0.5
+    with torch.no_grad():
+        ref = O.projector_ctcca(post, table, m.W_q.weight, m.n_heads)
+        md = m.to(dev).eval()
+        out = md(post.to(dev), table.to(dev))
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        err = ((out.cpu() - ref).norm() / ref.norm()).item()
+        assert err < 1e-2, f"relative error {err}"
+        out_bf = md(post.to(dev), table.to(dev).bfloat16())         # bf16 LLM embedding table
+        assert ((out_bf.cpu() - ref).norm() / ref.norm()).item() < 2e-2
+    with pytest.raises(NotImplementedError):                        # training call: backward not implemented
+        md.train()(post.to(dev), table.to(dev))

@@ -104,3 +104,16 @@ def test_merge_matches_reference(seed):
     if r is not None:
         for x, y in zip(r, o):
             assert (x is None and y is None) or (x.dtype == y.dtype and torch.equal(x, y))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_cross_attention_projector_matches_reference(seed):
+    g = torch.Generator().manual_seed(seed)
+    V1, D, V2, B, T = 23, 48, 77, 2, 5
+    ref = R.ref_projector("cross-attention", V1, D)
+    post = torch.softmax(torch.randn(B, T, V1, generator=g) * 3, -1)
+    table = torch.randn(V2, D, generator=g)
+    with torch.no_grad():
+        a = ref(post, table)
+        b = O.projector_ctcca(post, table, ref.W_q.weight, ref.n_heads)
+    assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-6, atol=1e-7)
