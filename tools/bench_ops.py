@@ -61,6 +61,15 @@ ms = timeit(lambda: bridge.merge_input_ids_with_audio_features(af, nl, emb, ids,
 e = bridge.merge_input_ids_with_audio_features(af, nl, emb, ids, mask, None, S.SPEECH_ID, S.PAD_ID)[0]
 byt = (n_out + int(mask.sum()) + e.shape[0] * e.shape[1]) * S.H_LLM * 4
 rows.append(("_merge_input_ids_with_audio_features API (fp32)", ms, byt / ms / 1e6, "GB/s", byt / ms / 1e6 / HBM))
+# cross-attention projector (projector.py:104-126) on the same compressed batch against the full 151 936-row table
+ca = P.EncoderProjectorCTCCA(cfg).to(dev).eval()
+table_bf = table.bfloat16()
+with torch.no_grad():
+    ms = timeit(lambda: ca(out, table_bf), n=3, warm=1)
+rows_ca = out.shape[0] * out.shape[1]
+fl = rows_ca * (2.0 * V * S.H_LLM + 3 * 2.0 * S.V_LLM * S.H_LLM)          # W_q GEMM + stats pass, softmax pass, P·V
+rows.append((f"EncoderProjectorCTCCA (cross-attention over the 151936-row table) on padded [{out.shape[0]},{out.shape[1]},V]", ms,
+             fl / ms / 1e9, "TFLOP/s", fl / ms / 1e9 / 1357.9))
 print("| op (B=64, T=500) | ms | achieved | unit | frac of measured peak |\n|---|---:|---:|---|---:|")
 for r in rows:
     print(f"| {r[0]} | {r[1]:.3f} | {r[2]:.0f} | {r[3]} | {r[4]:.2f} |")

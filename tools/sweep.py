@@ -24,7 +24,12 @@ def main():
     import ps_slm_b200.projector as P
     import ps_slm_b200.synth as S
     from ps_slm_b200.bridge import TasuBridge
-    dev = torch.device("cuda:0")
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                       # weak scaling: every rank runs the same per-GPU batch size
+        dist.init_process_group("nccl", device_id=dev)
     w, b = S.make_ctc_head()
     torch.manual_seed(0)
     proj = P.EncoderProjectorLinearSiLU(types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)).to(dev).eval()
@@ -35,33 +40,50 @@ def main():
         for B in args.batches:
             # build the batch from a 64-utterance seed batch tiled to B (generation on the host is the slow part)
             base_b = min(B, 64)
-            raw, raw_lens, _ = S.make_encoder_batch(base_b, T, w, seed=T)
+            raw, raw_lens, _ = S.make_encoder_batch(base_b, T, w, seed=T + 7919 * rank)
             ids, mask, _ = S.make_prompts(base_b, seed=T, left_pad=True)
             rep = B // base_b
             raw, raw_lens, ids, mask = (t.to(dev).repeat(rep, *([1] * (t.dim() - 1))) for t in (raw, raw_lens, ids, mask))
             for _ in range(3):
                 out = bridge(raw, raw_lens, ids, mask)
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.steps):
                 out = bridge(raw, raw_lens, ids, mask)
             e1.record()
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
             c = bridge.last_counts
-            res.append({"seconds": round(T * 0.06, 1), "T": T, "B": B, "ms_per_step": ms, "frames_in_per_s": B * T / (ms / 1e3),
-                        "frames_out_per_s": c["n_out"] / (ms / 1e3), "compression": B * T / max(c["n_out"], 1),
-                        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9})
+            n_out = c["n_out"]
+            if world > 1:                               # device time = max over ranks; rows summed over ranks
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
+                t = torch.tensor([n_out], dtype=torch.int64, device=dev)
+                dist.all_reduce(t)
+                n_out = int(t)
+            res.append({"seconds": round(T * 0.06, 1), "T": T, "B": B, "n_gpus": world, "ms_per_step": ms,
+                        "frames_in_per_s": world * B * T / (ms / 1e3), "frames_out_per_s": n_out / (ms / 1e3),
+                        "compression": world * B * T / max(n_out, 1), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9})
             del out, raw
             torch.cuda.empty_cache()
             torch.cuda.reset_peak_memory_stats()
-            print(res[-1], flush=True)
+            if rank == 0:
+                print(res[-1], flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "sweep%s.json" % ("" if world == 1 else "_n%d" % world)), "w") as f:
         json.dump(res, f, indent=1)
-    with open(os.path.join(ROOT, "gpurun_out", "sweep.md"), "w") as f:
-        f.write("| utt length | batch | ms/step | frames in /s | rows out /s | compression | peak mem GB |"
+    with open(os.path.join(ROOT, "gpurun_out", "sweep%s.md" % ("" if world == 1 else "_n%d" % world)), "w") as f:
+        f.write("| utt length | batch per GPU | ms/step | frames in /s | rows out /s | compression | peak mem GB |"
                 + (" vs CPU ref |" if args.cpu_frames_per_s else "") + "\n|---|---:|---:|---:|---:|---:|---:|"
                 + ("---:|" if args.cpu_frames_per_s else "") + "\n")
         for r in res:
