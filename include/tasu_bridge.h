@@ -334,7 +334,9 @@ int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t ldy, const
                                 const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, int n_uniq,
                                 int64_t n_rows, int V, int Hb, int H, float* dw1, int64_t dw1_stride,
                                 float* dgamma, float* dbeta, float* db1, float* dw2, int64_t dw2_stride,
-                                float* db2, void* workspace, int64_t workspace_bytes, void* stream);
+                                float* db2, int phase /* 0 = all; 1 = W1 half (dW1, dgamma, dbeta, db1) then 2 = W2 half
+                                (dW2, db2): lets a data-parallel caller all-reduce dW1 under the W2 half */,
+                                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 4 — splice (ps-slm.py:765-871).  Integer plan, then one gather/scatter pass.

@@ -61,7 +61,7 @@ SIGNATURES = {
     "tasu_tokrow_linear_silu_fwd": (_I, [_P, _L, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _F,
                                          _P, _P, _P, _P, _P, _I, _L, _P, _L, _P]),
     "tasu_tokrow_linear_silu_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _P, _I, _L, _I, _I,
-                                         _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _P]),
+                                         _I, _P, _L, _P, _P, _P, _P, _L, _P, _I, _P, _L, _P]),
     "tasu_splice_rowstat": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
     "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),

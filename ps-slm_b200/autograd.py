@@ -87,8 +87,9 @@ class TokenRowLinearSiLUFunction(torch.autograd.Function):
         dy = dy.contiguous()
         if dy.dtype not in (torch.float32, torch.bfloat16):
             dy = dy.float()
+        from . import dist as D
         dgamma, dbeta, dw1, db1, dw2, db2 = ops.tokrow_linear_silu_bwd(dy, ctx.rows, z, h, row_a, row_e, gamma, beta,
-                                                                       w1, w2, ctx.ws)
+                                                                       w1, w2, ctx.ws, between=D.overlap_hook())
         ctx.ws = None
         return (None, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), dw1.to(w1.dtype), db1.to(w1.dtype),
                 dw2.to(w2.dtype), db2.to(w2.dtype), None, None)

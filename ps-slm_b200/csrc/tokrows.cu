@@ -644,9 +644,11 @@ extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t
                                            const int32_t* uniq, const int32_t* seg_off, const int32_t* perm, int n_uniq,
                                            int64_t n_rows, int V, int Hb, int H, float* dw1, int64_t dw1_stride,
                                            float* dgamma, float* dbeta, float* db1, float* dw2, int64_t dw2_stride,
-                                           float* db2, void* workspace, int64_t workspace_bytes, void* stream) {
+                                           float* db2, int phase, void* workspace, int64_t workspace_bytes, void* stream) {
     TASU_CHECK_ARG(n_rows >= 0 && n_uniq >= 0 && V > 0 && Hb > 0 && H > 0, "shape");
+    TASU_CHECK_ARG(phase >= 0 && phase <= 2, "phase: 0 = all, 1 = W1 half (dW1, dgamma, dbeta, db1), 2 = W2 half (dW2, db2)");
     TASU_CHECK_ARG(dw1 && dgamma && dbeta && db1 && dw2 && db2, "null gradient pointer");
+    const bool do_w1 = phase != 2, do_w2 = phase != 1;
     TASU_CHECK_ARG(dy_dtype == TASU_F32 || dy_dtype == TASU_BF16, "dy_dtype");
     TASU_CHECK_ARG(workspace && ((uintptr_t)workspace % 256 == 0), "workspace must be 256-byte aligned");
     const TrainWs ws = train_ws(n_rows, n_uniq, V, Hb, H);
@@ -654,12 +656,16 @@ extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     char* wsb = (char*)workspace;
     if (n_rows == 0) {                                      // no rows: every gradient is zero
-        TASU_CHECK_CUDA(cudaMemsetAsync(db1, 0, 4LL * Hb, st));
-        TASU_CHECK_CUDA(cudaMemsetAsync(db2, 0, 4LL * H, st));
-        TASU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, 4LL * V, st));
-        TASU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, 4LL * V, st));
-        TASU_CHECK_CUDA(cudaMemset2DAsync(dw1, 4 * dw1_stride, 0, 4LL * V, Hb, st));
-        TASU_CHECK_CUDA(cudaMemset2DAsync(dw2, 4 * dw2_stride, 0, 4LL * Hb, H, st));
+        if (do_w1) {
+            TASU_CHECK_CUDA(cudaMemsetAsync(db1, 0, 4LL * Hb, st));
+            TASU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, 4LL * V, st));
+            TASU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, 4LL * V, st));
+            TASU_CHECK_CUDA(cudaMemset2DAsync(dw1, 4 * dw1_stride, 0, 4LL * V, Hb, st));
+        }
+        if (do_w2) {
+            TASU_CHECK_CUDA(cudaMemsetAsync(db2, 0, 4LL * H, st));
+            TASU_CHECK_CUDA(cudaMemset2DAsync(dw2, 4 * dw2_stride, 0, 4LL * Hb, H, st));
+        }
         return TASU_OK;
     }
     const int64_t ldh8 = pad_to(H, 8), ldw2 = pad_to(Hb, 64);
@@ -668,20 +674,27 @@ extern "C" int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t
     float* dh = (float*)(wsb + ws.dh);
     float* P = (float*)(wsb + ws.P);
     float* E = (float*)(wsb + ws.E);
-    TASU_TRY(tasu_colsum(dy, dy_dtype, n_rows, H, ldy, db2, stream));
+    // The W1 half goes first: dW1 is 94 % of the gradient bytes, so a data-parallel caller can start its all-reduce
+    // (phase 1 → all-reduce → phase 2) while the W2 half still computes.  The bf16 copy of dy made in phase 1 stays in
+    // the workspace for phase 2 (nothing else may use the workspace in between).
     const void* dy_bf16 = dy;
     int64_t ld_dyb = ldy;
     if (dy_dtype != TASU_BF16 || (ldy * 2) % 16 != 0 || (uintptr_t)dy % 16 != 0) {
-        TASU_TRY(tasu_cast_rows(dy, dy_dtype, n_rows, H, ldy, dyb, TASU_BF16, ldh8, nullptr, nullptr, 0.f, stream));
+        if (do_w1) TASU_TRY(tasu_cast_rows(dy, dy_dtype, n_rows, H, ldy, dyb, TASU_BF16, ldh8, nullptr, nullptr, 0.f, stream));
         dy_bf16 = dyb; ld_dyb = ldh8;
     }
-    TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
     // both contractions read dy, h and W2 where they lie (MN-major operands): no transposed copies
-    TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 1, h_bf16, Hb, 1, dw2, dw2_stride, H, Hb, (int)n_rows, stream));   // dW2 = dy^T · h
-    TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 0, w2b, ldw2, 1, dh, Hb, (int)n_rows, Hb, H, stream));              // dh = dy · W2
-    TASU_TRY(tasu_tokrow_bwd_rows(dh, z, n_rows, Hb, seg_off, perm, row_a, row_e, n_uniq, P, db1, E, wsb + ws.part,
-                                  ws.E - ws.part, stream));
-    TASU_TRY(tasu_tokrow_wgrad_finish(P, uniq, n_uniq, (int32_t*)(wsb + ws.slot), w1, w1_stride, gamma, beta, E, db1, Hb, V, dw1,
-                                      dw1_stride, dgamma, dbeta, stream));
+    if (do_w1) {
+        TASU_TRY(tasu_cast_rows(w2, TASU_F32, H, Hb, w2_stride, w2b, TASU_BF16, ldw2, nullptr, nullptr, 0.f, stream));
+        TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 0, w2b, ldw2, 1, dh, Hb, (int)n_rows, Hb, H, stream));          // dh = dy · W2
+        TASU_TRY(tasu_tokrow_bwd_rows(dh, z, n_rows, Hb, seg_off, perm, row_a, row_e, n_uniq, P, db1, E, wsb + ws.part,
+                                      ws.E - ws.part, stream));
+        TASU_TRY(tasu_tokrow_wgrad_finish(P, uniq, n_uniq, (int32_t*)(wsb + ws.slot), w1, w1_stride, gamma, beta, E, db1, Hb, V,
+                                          dw1, dw1_stride, dgamma, dbeta, stream));
+    }
+    if (do_w2) {
+        TASU_TRY(tasu_colsum(dy, dy_dtype, n_rows, H, ldy, db2, stream));
+        TASU_TRY(tasu_gemm_bf16_f32(dy_bf16, ld_dyb, 1, h_bf16, Hb, 1, dw2, dw2_stride, H, Hb, (int)n_rows, stream));   // dW2 = dy^T · h
+    }
     return TASU_OK;
 }

@@ -100,6 +100,18 @@ def all_gather_lengths(lens: torch.Tensor, group=None) -> List[torch.Tensor]:
     return [b[:int(c)] for b, c in zip(bufs, counts)]
 
 
+def concat_ranges(starts, lens):
+    """int32 index vector of the concatenated ranges [starts[i], starts[i] + lens[i]) — vectorised (no Python loop)."""
+    import numpy as np
+    starts = np.asarray(starts, dtype=np.int64)
+    lens = np.asarray(lens, dtype=np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.int32)
+    before = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    return (np.repeat(starts - before, lens) + np.arange(total)).astype(np.int32)
+
+
 def _gather_rows(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """rows[i] = flat[idx[i]] — tasu_gather_rows on the GPU; plain indexing only for the CPU (gloo) tests."""
     if flat.is_cuda:
@@ -139,19 +151,50 @@ def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing
     if timing is not None and rows.is_cuda:
         e1.record()
         timing.append((e0, e1, W * m * H * rows.element_size()))
+    import numpy as np
     n = sum(l.numel() for l in lens_host)
-    offs = [torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(l, 0)]) for l in lens_host]
-    idx, glens = [], []
-    for r, j in global_order(n, W):
-        s, e = int(offs[r][j]), int(offs[r][j + 1])
-        idx.append(torch.arange(r * m + s, r * m + e, dtype=torch.int32))
-        glens.append(int(lens_host[r][j]))
-    idx = torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int32)
+    # global utterance i lives on rank i % W at local index i // W: its rows are flat[r*m + off_r[j] : ... + len]
+    lens_np = [l.numpy().astype(np.int64) for l in lens_host]
+    offs_np = [np.concatenate([[0], np.cumsum(l)]) for l in lens_np]
+    gi = np.arange(n)
+    r_of, j_of = gi % W, gi // W
+    glens_np = np.zeros(n, dtype=np.int64)
+    starts = np.zeros(n, dtype=np.int64)
+    for r in range(W):
+        sel = r_of == r
+        glens_np[sel] = lens_np[r][j_of[sel]]
+        starts[sel] = r * m + offs_np[r][j_of[sel]]
+    idx = torch.from_numpy(concat_ranges(starts, glens_np))
+    glens = glens_np.tolist()
     if rows.is_cuda:
         idx = idx.pin_memory().to(rows.device, non_blocking=True)
     rows_g = _gather_rows(flat, idx)
     lens_g = torch.tensor(glens, dtype=lens.dtype).to(lens.device)
     return (rows_g, lens_g, glens) if return_host else (rows_g, lens_g)
+
+
+# ---- gradient all-reduce overlapped with the backward (token-row projector) -------------------------------------------
+_OVERLAP = {"on": False, "group": None, "pending": {}}
+
+
+def enable_overlapped_allreduce(on: bool = True, group=None):
+    """Data-parallel training without DeepSpeed: when on, the token-row backward starts the all-reduce of its W1 half
+    (dgamma | dbeta | dW1 | db1 = 94 % of the bytes) as soon as it is enqueued, so NCCL runs under the W2 half of the
+    backward; ``allreduce_gradients`` then only sends the remainder and waits.  Off (default): nothing is communicated
+    inside backward (what DeepSpeed / an external reducer expects)."""
+    _OVERLAP["on"], _OVERLAP["group"] = bool(on), group
+
+
+def overlap_hook():
+    """Callback for ``ops.tokrow_linear_silu_bwd(between=...)`` or None when overlap is off / single process."""
+    rank, W = world()
+    if not _OVERLAP["on"] or W == 1:
+        return None
+
+    def between(flat, n_first):
+        work = dist.all_reduce(flat[:n_first], op=dist.ReduceOp.SUM, group=_OVERLAP["group"], async_op=True)
+        _OVERLAP["pending"][flat.untyped_storage().data_ptr()] = (work, n_first)
+    return between
 
 
 def _shared_flat(grads):
@@ -179,7 +222,13 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
     grads = [p.grad for p in params if p.grad is not None]
     flat = _shared_flat(grads)
     if flat is not None:                                         # one in-place message, no flatten / copy-back
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        early = _OVERLAP["pending"].pop(flat.untyped_storage().data_ptr(), None)
+        if early is not None:                                    # the W1 half is already in flight (overlap_hook)
+            work0, n_first = early
+            work = dist.all_reduce(flat[n_first:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            work0.wait()
+        else:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
         handles = [(work, flat, [])]
         if async_op:
             return handles

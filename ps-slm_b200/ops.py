@@ -740,8 +740,12 @@ def tokrow_linear_silu_fwd(rows: TokenRows, gamma, beta, w1, b1, w2, b2, eps: fl
     return y, z, h, ab[0], ab[1]
 
 
-def tokrow_linear_silu_bwd(dy: torch.Tensor, rows: TokenRows, z, h, row_a, row_e, gamma, beta, w1, w2, ws: torch.Tensor):
-    """Composite backward (tasu_tokrow_linear_silu_bwd) → (dgamma, dbeta, dW1, db1, dW2, db2), all fp32."""
+def tokrow_linear_silu_bwd(dy: torch.Tensor, rows: TokenRows, z, h, row_a, row_e, gamma, beta, w1, w2, ws: torch.Tensor,
+                           between=None):
+    """Composite backward (tasu_tokrow_linear_silu_bwd) → (dgamma, dbeta, dW1, db1, dW2, db2), all fp32 views of ONE
+    flat buffer in parameter order.  ``between(flat, n_first)``: optional callback invoked after the W1 half
+    (flat[:n_first] = dgamma | dbeta | dW1 | db1 is enqueued) and before the W2 half — the hook for overlapping a
+    gradient all-reduce with the rest of the backward."""
     Hb, V = w1.shape
     H = w2.shape[0]
     n, dev = rows.n_rows, w1.device
@@ -760,11 +764,19 @@ def tokrow_linear_silu_bwd(dy: torch.Tensor, rows: TokenRows, z, h, row_a, row_e
     db1 = flat[offs[3]:offs[3] + Hb]
     dw2 = flat[offs[4]:offs[4] + H * Hb].view(H, Hb)
     db2 = flat[offs[5]:offs[5] + H]
-    L.check(L.lib().tasu_tokrow_linear_silu_bwd(
-        dy.data_ptr(), _dt(dy), dy.stride(0) if n > 1 else H, _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(),
-        w1.data_ptr(), w1.stride(0), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), w2.stride(0),
-        rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(), rows.n_uniq, n, V, Hb, H,
-        dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), db1.data_ptr(), dw2.data_ptr(), Hb, db2.data_ptr(),
-        ws.data_ptr(), ws.numel(), _stream()), "tasu_tokrow_linear_silu_bwd")
-    _count(12)
+
+    def call(phase):
+        L.check(L.lib().tasu_tokrow_linear_silu_bwd(
+            dy.data_ptr(), _dt(dy), dy.stride(0) if n > 1 else H, _ptr(z), h.data_ptr(), row_a.data_ptr(), row_e.data_ptr(),
+            w1.data_ptr(), w1.stride(0), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), w2.stride(0),
+            rows.uniq.data_ptr(), rows.seg_off.data_ptr(), rows.perm.data_ptr(), rows.n_uniq, n, V, Hb, H,
+            dw1.data_ptr(), V, dgamma.data_ptr(), dbeta.data_ptr(), db1.data_ptr(), dw2.data_ptr(), Hb, db2.data_ptr(),
+            phase, ws.data_ptr(), ws.numel(), _stream()), "tasu_tokrow_linear_silu_bwd")
+    if between is None:
+        call(0)
+    else:
+        call(1)
+        between(flat, offs[4])
+        call(2)
+    _count(10)
     return dgamma, dbeta, dw1, db1, dw2, db2

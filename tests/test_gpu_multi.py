@@ -66,3 +66,62 @@ def test_cross_rank_packing_matches_single_gpu():
         p.join(timeout=60)
     assert [r[:2] for r in res] == [(0, True), (1, True)], res
     assert 0.3 < res[0][2] <= 1.0          # packing efficiency (valid / padded tokens) is reported
+
+
+def _worker_overlap(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import ps_slm_b200.dist as D
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    V, H = S.V_CTC, S.H_LLM
+    torch.manual_seed(0)
+    proj = P.EncoderProjectorLinearSiLU(types.SimpleNamespace(encoder_dim=V, llm_dim=H, encoder_projector_ds_rate=1)).to(dev).train()
+    ids = S.make_transcripts(12, V, seed=3, lo=5, hi=30)
+    mine = D.shard_indices(12, rank, world)
+    torch.manual_seed(100 + rank)
+    rows = ops.sim_token_rows(ops.TokenBatch([ids[i] for i in mine]), V, dev)
+    gy = torch.randn(rows.n_rows, H, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+    params = list(proj.parameters())
+
+    def grads(overlap):
+        D.enable_overlapped_allreduce(overlap)
+        for p in params:
+            p.grad = None
+        y = proj.forward_token_rows(rows)
+        (y * gy).sum().backward()
+        if overlap:
+            D.allreduce_gradients(params)                       # W1 half already in flight from inside backward
+            return [p.grad.clone() for p in params]
+        out = []
+        for p in params:                                        # reference: plain per-tensor all-reduce, then average
+            g = p.grad.clone()
+            dist.all_reduce(g)
+            out.append(g / world)
+        return out
+    ref = grads(False)
+    got = grads(True)
+    D.enable_overlapped_allreduce(False)
+    ok = all(torch.allclose(a, b, rtol=1e-6, atol=1e-9) for a, b in zip(ref, got))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_overlapped_gradient_allreduce_matches_plain():
+    """The all-reduce started inside the token-row backward (W1 half under the W2 half) gives the same averaged
+    gradients as reducing every tensor after the backward."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res

@@ -76,6 +76,7 @@ def main():
     ids_g, mask_g = ids_g.to(dev), mask_g.to(dev)
     perm_local = torch.tensor(a_loc + t_loc)                                             # rows come out audio-first
     inv_local = torch.argsort(perm_local).to(dev)
+    src_of_local = np.argsort(np.asarray(a_loc + t_loc))                                 # position of local utterance j in that order
     timing = []
     stats = {}
 
@@ -89,20 +90,19 @@ def main():
         # local utterance order: lengths permuted back to shard order, rows re-ordered by one row gather
         lens_cat = torch.cat([lens_a, tr.lens])
         lens_loc = lens_cat[inv_local]
-        lens_host = lens_cat.cpu()
-        offs = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens_host, 0)])
-        order = (a_loc + t_loc)
-        src_of_local = {j: k for k, j in enumerate(order)}
-        idx = torch.cat([torch.arange(int(offs[src_of_local[j]]), int(offs[src_of_local[j] + 1]), dtype=torch.int32)
-                         for j in range(len(order))]) if len(order) else torch.zeros(0, dtype=torch.int32)
+        lens_host = lens_cat.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(lens_host)])
+        idx = torch.from_numpy(D.concat_ranges(offs[:-1][src_of_local], lens_host[src_of_local]))
         rows_loc = D._gather_rows(torch.cat([rows_a, rows_t]), idx.pin_memory().to(dev, non_blocking=True))
         rows_g, lens_gd, lens_gh = D.all_gather_packed(rows_loc, lens_loc, timing=timing, return_host=True)
         # length-grouped re-deal: contiguous groups of the length-sorted batch with balanced padded areas
         tot = [prompt_len[u] + int(lens_gh[u]) - 1 for u in range(Bg)]
         share = D.length_grouped_partition(tot, world)
         sel = sorted(share[rank])
-        goff = np.concatenate([[0], np.cumsum(np.asarray(lens_gh, dtype=np.int64))])
-        idx2 = np.concatenate([np.arange(goff[u], goff[u + 1], dtype=np.int32) for u in sel]) if sel else np.zeros(0, np.int32)
+        lens_gn = np.asarray(lens_gh, dtype=np.int64)
+        goff = np.concatenate([[0], np.cumsum(lens_gn)])
+        sel_n = np.asarray(sel, dtype=np.int64)
+        idx2 = D.concat_ranges(goff[:-1][sel_n], lens_gn[sel_n])
         rows_sel = D._gather_rows(rows_g, torch.from_numpy(idx2).pin_memory().to(dev, non_blocking=True))
         sel_t = torch.tensor(sel, device=dev)
         ids_s, mask_s = ids_g[sel_t], mask_g[sel_t]

@@ -49,7 +49,7 @@ pipe.bridge = Wrap(bridge)
 t0 = torch.cuda.Event(enable_timing=True); t0.record(); torch.cuda.synchronize()
 import time
 w0 = time.perf_counter()
-for _ in pipe.run(host[i % 4] for i in range(6)):
+for _ in pipe.run(host[i % 4] for i in range(8)):
     pass
 torch.cuda.synchronize()
 print("wall ms", (time.perf_counter() - w0) * 1e3)
