@@ -52,6 +52,30 @@ def psd(encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, ctc_posterior
     return out, plan.new_lens
 
 
+def psd_from_encoder(raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor, w_ctc_bf16: torch.Tensor,
+                     b_ctc: torch.Tensor, blank_id: int = 0, blank_threshold: float = BLANK_THRESHOLD, n_prefix: int = 4):
+    """Raw-feature branch (``ctc_posterior=False, do_psd=True``; ps-slm.py:450-454 + :515-518 / :581-585 + :645-648):
+    ``psd(encoder_out, lens, softmax(ctc_lo(raw))[:, 4:])`` WITHOUT materialising the ``[B, T, 25055]`` posterior —
+    the segmentation comes from the fused CTC-head statistics (argmax / blank probability out of the tcgen05 GEMM
+    epilogue), the 512-d encoder frames themselves are mean-pooled.  Same return contract as ``psd``."""
+    B, T4, Denc = raw_encoder_out.shape
+    T = T4 - n_prefix
+    V = w_ctc_bf16.shape[0]
+    dev = raw_encoder_out.device
+    feats = _as_compute(raw_encoder_out)
+    x2 = feats.reshape(B * T4, Denc)
+    xb = x2 if x2.dtype == torch.bfloat16 and Denc % 64 == 0 else ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))[0]
+    lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - n_prefix, min=0)
+    st = ops.ctc_head_stats(xb, w_ctc_bf16, b_ctc, B, T, n_prefix, V, Denc, blank_id)
+    plan = ops.collapse_plan(st, lens, blank_id, blank_threshold)
+    max_len = int(plan.header.cpu()[L.CH_MAX_LEN])
+    if max_len == 0:
+        return feats.new_zeros(B, 0, Denc), torch.zeros(B, dtype=torch.long, device=dev)
+    out = torch.empty(B, max_len, Denc, dtype=feats.dtype, device=dev)
+    ops.segment_meanpool(feats[:, n_prefix:, :], plan, 1, max_len, B * max_len, out, Denc)
+    return out, plan.new_lens
+
+
 def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_tokens: torch.Tensor,
                                         inputs_embeds: torch.Tensor, input_ids: torch.Tensor,
                                         attention_mask: torch.Tensor, labels: Optional[torch.Tensor],

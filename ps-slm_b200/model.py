@@ -132,6 +132,7 @@ class slam_model_asr(nn.Module):
             self.encoder_tokenizer = SenseVoiceTokenizer(model_config.encoder_path)
             del ref
         self._bridge = None
+        self._ctc_cache = _bridge.ProjectorCache()
         # text-only batches go through the token-row projector (no [B, L, 25055] tensor); False = dense simulator path
         self.token_row_path = True
 
@@ -233,9 +234,13 @@ class slam_model_asr(nn.Module):
                     encoder_outs, feat_len = post, encoder_out_lens
         else:
             if self.do_psd:
-                logits = self.encoder.ctc.ctc_lo(raw_encoder_out)
-                post = torch.softmax(logits, dim=-1)[:, 4:, :]
-                encoder_outs, feat_len = self.psd(encoder_out, encoder_out_lens, post, blank)
+                # raw-feature branch: segmentation from the fused CTC-head statistics, no [B, T, V] posterior
+                ctc_lo = self.encoder.ctc.ctc_lo
+                w_bf16, b_f32 = self._ctc_cache.get([ctc_lo.weight, ctc_lo.bias], lambda: (
+                    _bridge.cast_weight_bf16(ctc_lo.weight),
+                    ctc_lo.bias.detach().float().contiguous() if ctc_lo.bias is not None
+                    else torch.zeros(ctc_lo.weight.shape[0], dtype=torch.float32, device=ctc_lo.weight.device)))
+                encoder_outs, feat_len = _bridge.psd_from_encoder(raw_encoder_out, raw_encoder_out_lens, w_bf16, b_f32, blank)
             else:
                 encoder_outs, feat_len = encoder_out, encoder_out_lens
         if self.cross_attn and self.ctc_posterior:                 # ps-slm.py:475-480 / :605-610

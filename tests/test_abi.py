@@ -98,5 +98,8 @@ def test_projector_state_dict_names():
     c = P.EncoderProjectorConcat(types.SimpleNamespace(encoder_dim=512, llm_dim=1536, encoder_projector_ds_rate=2))
     assert set(c.state_dict()) == {"linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"} and c.k == 2
     assert tuple(c.linear1.weight.shape) == (2048, 1024)
+    ca = P.EncoderProjectorCTCCA(types.SimpleNamespace(encoder_dim=25055, llm_dim=1536, encoder_projector_ds_rate=1))
+    assert {k: tuple(v.shape) for k, v in ca.state_dict().items()} == {"W_q.weight": (1536, 25055)} and ca.n_heads == 8
+    assert not hasattr(ca, "k")                       # like the reference: the cross-attention branch never reads .k
     s = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=512, llm_dim=151644, encoder_projector_ds_rate=1))
     assert set(s.state_dict()) == {"map.weight", "map.bias"} and tuple(s.map.weight.shape) == (151644, 512)

@@ -48,3 +48,20 @@ def test_model_dispatch_matches_reference(dev, golden, name):
     assert e.shape == r.shape
     err = ((e - r).norm() / r.norm()).item()
     assert err < 1e-2, f"{name}: inputs_embeds relative error {err}"
+
+
+def test_raw_feature_psd_from_encoder(dev):
+    """bridge.psd_from_encoder (raw-feature branch, no [B,T,V] posterior) vs the oracle's psd on the fp32 posterior of
+    the same planted batch: compressed lengths bit-exact, pooled 512-d features to 1e-5."""
+    import ps_slm_b200.bridge as bridge
+    import ps_slm_b200.synth as S
+    from oracle import tasu_oracle as O
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(5, 120, w, seed=77, ragged=True)
+    raw_lens[3] = 4                                             # an utterance with zero valid frames
+    post = torch.softmax(torch.nn.functional.linear(raw, w, b), -1)[:, 4:]
+    lens = torch.clamp(raw_lens - 4, min=0)
+    ref, ref_lens, _ = O.psd_vec(raw[:, 4:], lens, post, 0, 0.9)
+    out, new_lens = bridge.psd_from_encoder(raw.to(dev), raw_lens.to(dev), bridge.cast_weight_bf16(w.to(dev)), b.to(dev))
+    assert torch.equal(new_lens.cpu(), ref_lens) and out.shape == ref.shape
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-6)

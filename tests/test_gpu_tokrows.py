@@ -169,3 +169,17 @@ def test_model_text_branch_uses_token_rows(dev, golden, name, monkeypatch):
     assert np.array_equal(seen["labels"].cpu().numpy(), g[f"{name}_ref_labels"])
     e, r = seen["inputs_embeds"].detach().float().cpu(), torch.from_numpy(g[f"{name}_ref_embeds"])
     assert e.shape == r.shape and _rel(e, r) < 1e-2
+
+
+def test_zero_rows_training_step(dev):
+    """Every transcript dropped / empty: forward gives [0, H], backward gives all-zero parameter gradients."""
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.sim as sim
+    V, H = 300, 96
+    m = _module(V, H).to(dev).train()
+    rows = ops.group_token_rows(*sim.clean_descriptors([[], [], []]), V, dev)
+    y = m.forward_token_rows(rows)
+    assert y.shape == (0, H) and y.requires_grad
+    y.sum().backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and float(p.grad.abs().sum()) == 0.0, n
