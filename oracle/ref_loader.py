@@ -153,17 +153,25 @@ def load_dataset_module():
         return _cache["dataset"]
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    added = []
     for name in ("whisper", "kaldiio", "torchaudio", "torchaudio.compliance", "torchaudio.compliance.kaldi"):
         if name not in sys.modules:
             m = types.ModuleType(name)
             m.__path__ = []                                   # lets "import a.b.c" resolve through sys.modules
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
             sys.modules[name] = m
-    sys.modules["torchaudio"].compliance = sys.modules["torchaudio.compliance"]
-    sys.modules["torchaudio.compliance"].kaldi = sys.modules["torchaudio.compliance.kaldi"]
+            added.append(name)
+    if "torchaudio" in added:
+        sys.modules["torchaudio"].compliance = sys.modules["torchaudio.compliance"]
+        sys.modules["torchaudio.compliance"].kaldi = sys.modules["torchaudio.compliance.kaldi"]
     loader = importlib.machinery.SourceFileLoader(
         "tasu_reference_dataset", os.path.join(REF_ROOT, "dataset", "speech_dataset_large.py"))
     spec = importlib.util.spec_from_loader(loader.name, loader)
     mod = importlib.util.module_from_spec(spec)
-    loader.exec_module(mod)
+    try:
+        loader.exec_module(mod)
+    finally:
+        for name in added:                                    # the stubs must not leak: transformers probes
+            sys.modules.pop(name, None)                       # importlib.util.find_spec("torchaudio") later on
     _cache["dataset"] = mod
     return mod
