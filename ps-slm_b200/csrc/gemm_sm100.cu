@@ -151,6 +151,12 @@ __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t
 }
 
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {          // MUFU.EX2, 2 ulp, flushes denormal results to zero
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct Params {
     int M, N, K;              // M = rows the tensor maps cover; the live row count may come from m_dev
@@ -288,7 +294,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (kEpi != TASU_EPI_NONE) {
                 for (int c = et; c < BN; c += kEpiThreads) {   // each group stages its own copy (own barrier)
                     const int col = n0 + c;
-                    s_bias[c] = col < p.N ? __ldg(p.bias + col) : 0.f;
+                    // softmax epilogue works in the log2 domain: bias pre-scaled once per tile, not once per element
+                    s_bias[c] = col < p.N ? __ldg(p.bias + col) * (kEpi == TASU_EPI_SOFTMAX ? kLog2e : 1.f) : 0.f;
                     if (kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD) s_colsum[c] = col < p.N ? __ldg(p.colsum + col) : 0.f;
                 }
             }
@@ -296,6 +303,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < M_live) {
                 rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow);
             }
+            // softmax: p = exp(acc + bias - max) / sum = 2^(acc*log2e + bias*log2e + rowc), rowc = -max*log2e + log2(1/sum):
+            // one FADD + one FFMA + one MUFU.EX2 per element
+            const float rowc = kEpi == TASU_EPI_SOFTMAX ? fmaf(nmean, kLog2e, __log2f(fmaxf(rstd, 1e-37f))) : 0.f;
             const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -332,7 +342,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         } else if (kEpi == TASU_EPI_SOFTMAX) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)      // softmax with known row max (-nmean) and 1/sum (rstd)
-                                x[e] = exp2f((x[e] + b[e] + nmean) * 1.4426950408889634f) * rstd;
+                                x[e] = ex2_approx(fmaf(x[e], kLog2e, b[e] + rowc));
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -563,7 +573,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         cm = fmaxf(cm, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
                     }
                     if (cm > rm) {                                 // rare after the first slabs
-                        const float f = exp2f((rm - cm) * kL2e);
+                        const float f = ex2_approx((rm - cm) * kL2e);      // rm = -inf on the first slab: 2^-inf = 0
                         rs *= f;
                         rs2 *= f * f;
                         rm = cm;
@@ -576,7 +586,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     float acc_s = 0.f, acc_s2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float e = exp2f(fmaf(x[j], kL2e, -mb));
+                        const float e = ex2_approx(fmaf(x[j], kL2e, -mb));   // one FFMA + one MUFU.EX2 per logit
                         acc_s += e;
                         acc_s2 = fmaf(e, e, acc_s2);           // Σ exp(2(x-m)): gives Σ p² = s2/s² for the LayerNorm fold
                     }
