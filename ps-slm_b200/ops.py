@@ -371,16 +371,29 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
     else:
         audio_stride = audio_rows.stride(0) if audio_rows.dim() == 2 and audio_rows.shape[0] > 1 else H
         n_audio_rows = audio_rows.shape[0] if audio_rows.dim() == 2 else 0
-    emb = torch.empty(B, spliced_len, H, dtype=text_src.dtype, device=dev)
-    mask = torch.empty(B, spliced_len, dtype=torch.bool if p.mask_dtype == 0 else torch.int64, device=dev)
+    # S' changes from batch to batch: allocate for S' rounded up to 32 positions so the caching allocator keeps hitting
+    # the same few block sizes (a fresh size per step means cudaMalloc / cudaFree churn on a 0.3 GB tensor)
+    n_pos = B * spliced_len
+    cap_pos = B * ((spliced_len + 31) // 32 * 32)
+
+    def alloc(shape_tail, dtype):
+        per = 1
+        for d in shape_tail:
+            per *= d
+        return torch.empty(max(cap_pos, 1) * per, dtype=dtype, device=dev)[:n_pos * per].view(B, spliced_len, *shape_tail)
+    emb = alloc((H,), text_src.dtype)
+    mask = alloc((), torch.bool if p.mask_dtype == 0 else torch.int64)
     out_labels = None
     if labels is not None:
         labels = labels.to(torch.int64).contiguous()
-        out_labels = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
-    pos = torch.empty(B, spliced_len, dtype=torch.int64, device=dev)
-    fids = torch.empty(B, spliced_len, dtype=torch.int64, device=dev) if want_ids else None
-    row_src = torch.empty(max(B * spliced_len, 1), dtype=torch.int64, device=dev)
-    audio_dest = torch.full((max(n_audio_rows, 1),), -1, dtype=torch.int32, device=dev) if want_audio_dest else None
+        out_labels = alloc((), torch.int64)
+    pos = alloc((), torch.int64)
+    fids = alloc((), torch.int64) if want_ids else None
+    row_src = torch.empty(max(cap_pos, 1), dtype=torch.int64, device=dev)
+    audio_dest = None
+    if want_audio_dest:
+        audio_dest = torch.empty(_cap_rows(max(n_audio_rows, 1)), dtype=torch.int32, device=dev)[:max(n_audio_rows, 1)]
+        audio_dest.fill_(-1)
     L.check(L.lib().tasu_splice_scatter(
         p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, _ptr(labels), B, S, spliced_len, H,
         p.speech_id, text2.data_ptr(), text_mode, text_stride, audio_rows.data_ptr() if audio_rows.numel() else None,
@@ -403,7 +416,7 @@ def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, 
     if p.audio_dest is None:
         raise L.TasuError("splice_audio_grad needs the forward scatter to have run with want_audio_dest=True")
     rows = p.n_audio * audio_max_len if audio_layout == 1 else n_rows
-    ga = torch.empty(max(rows, 1), H, dtype=grad_emb.dtype, device=grad_emb.device)[:rows]
+    ga = torch.empty(_cap_rows(max(rows, 1)), H, dtype=grad_emb.dtype, device=grad_emb.device)[:rows]
     L.check(L.lib().tasu_gather_rows(grad_emb.data_ptr(), _dt(grad_emb), H, p.audio_dest.data_ptr(), rows, H,
                                      ga.data_ptr(), H, _stream()), "tasu_gather_rows")
     _count(1)
