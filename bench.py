@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (defeats L2 reuse)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-decisions", action="store_true",
+                    help="refine the frames whose greedy decisions lie inside the bf16 noise of the fused head with the "
+                         "fp32-accurate GEMM (TasuBridge.exact_decisions)")
     ap.add_argument("--materialize-logits", action="store_true",
                     help="round-1a path: ctc_lo writes fp32 logits to HBM and a streaming kernel computes the stats")
     return ap.parse_args()
@@ -214,6 +217,7 @@ def b200_arm(args):
     table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
     bridge = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
     bridge.materialize_logits = args.materialize_logits
+    bridge.exact_decisions = args.exact_decisions
     host, devb = [], []
     for r in range(args.rotate):
         raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=1000 * rank + r)
@@ -357,7 +361,7 @@ def b200_arm(args):
                                "-> splice with Qwen2.5-1.5B-shaped embed table" % (B, args.seconds, T),
                    "batch_per_gpu": B, "frames_per_utt": T, "V": V, "compressed_rows_per_step": n_out,
                    "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
-                   "kept_frames_per_step": f_kept,
+                   "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
                    "path": "materialized fp32 logits" if args.materialize_logits else "fused ctc_lo+stats, recompute kept frames",
                    "l2": "rotating %d distinct input batches (%.0f MB > 126 MB L2); per-step intermediates (%.2f GB) exceed L2"
                          % (args.rotate, args.rotate * in_bytes / 1e6,

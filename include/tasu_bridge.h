@@ -97,6 +97,21 @@ int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float*
                        int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
                        int32_t* kept_frames, int32_t* seg_frame_off, void* stream);
 
+/* Exact-decision mode of the fused CTC head (tasu_ctc_head_stats computes logits from bf16 operands): list the frames
+ * whose greedy decisions lie inside the bf16 noise — argmax probability < p_max_min (possible near-tie) or a blank frame
+ * with |p_blank - threshold| < band — as (frame index, raw encoder row) pairs (count zeroed, unused slots = -1); the
+ * caller recomputes their logits with the fp32-accurate GEMM (tasu_split_bf16x3 + tasu_gemm_bf16_tn + tasu_sum_epilogue),
+ * takes tasu_frame_stats of them and writes the statistics back with tasu_scatter_frame_stats before
+ * tasu_collapse_plan, so run boundaries and keep/drop decisions equal the fp32 reference (ps-slm.py:265, :295-297). */
+int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_blank, const float* row_max,
+                               const float* row_sumexp, const int64_t* lens, int B, int T, int n_prefix,
+                               int blank_id, float threshold, float p_max_min, float band, int cap,
+                               int32_t* frame_idx, int32_t* raw_row, int32_t* count, void* stream);
+int tasu_scatter_frame_stats(const int32_t* frame_idx, const int32_t* count, int cap, const int32_t* argmax_src,
+                             const float* x_blank_src, const float* row_max_src, const float* row_sumexp_src,
+                             int32_t* argmax, float* x_blank, float* row_max, float* row_sumexp,
+                             float* row_sumexp2, void* stream);
+
 /* exclusive scans: new_lens → row_off [B+1] int32, kept_frames → frame_off [B+1] int32 (optional);
  * header [TASU_CH_WORDS] int64 */
 int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, const uint32_t* global_max_enc,

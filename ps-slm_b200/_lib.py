@@ -27,6 +27,8 @@ SIGNATURES = {
     "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "tasu_scatter_frame_stats": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _F, _P]),

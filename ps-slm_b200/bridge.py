@@ -271,6 +271,12 @@ class TasuBridge:
         self._ctc_cache = ProjectorCache()
         self._capacity = {}           # (B, T) → (kept-frame rows, packed rows) the tail buffers are sized for
         self.last_counts = {}
+        # True: frames whose greedy decisions lie inside the bf16 noise of the fused head (near-tie argmax, blank
+        # probability within 0.02 of the drop threshold) are recomputed with the fp32-accurate GEMM before the collapse
+        # plan, so indices / run boundaries equal the fp32 reference even on adversarial inputs (+6 small launches)
+        self.exact_decisions = False
+        self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
+        self._ctc_split_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
         self.events = []              # [(stage name, start event, end event)] of the profiled calls
@@ -353,6 +359,13 @@ class TasuBridge:
             # (a1+a2) fused: logits live only in TMEM, softmax statistics come out of the GEMM epilogue
             with self._stage("ctc_head_stats"):
                 st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
+            if self.exact_decisions and raw_encoder_out.dtype == torch.float32:
+                with self._stage("refine_ambiguous"):
+                    w_split, k_split = self._ctc_split_cache.get(
+                        [self.w_ctc], lambda: ops.split_bf16x3(self.w_ctc.detach().float(), 1)[:2])
+                    self.last_ambiguous = ops.refine_ambiguous_frames(
+                        st, lens, raw_encoder_out.reshape(B * T4, Denc), w_split, k_split, b_ctc, T, self.N_PREFIX, V,
+                        self.blank_id, self.blank_threshold)
 
         # (a2) collapse plan, (a8) splice plan; one header for both
         with self._stage("collapse_plan"):

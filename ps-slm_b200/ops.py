@@ -104,6 +104,42 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
     return st
 
 
+def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, raw_f32: torch.Tensor, w_split: torch.Tensor, k_split: int,
+                            bias: Optional[torch.Tensor], T: int, n_prefix: int, V: int, blank_id: int, threshold: float,
+                            p_max_min: float = 0.6, band: float = 0.02, cap: int = 1024) -> torch.Tensor:
+    """Exact-decision mode: recompute the statistics of the frames tasu_flag_ambiguous_frames lists with the
+    fp32-accurate GEMM and write them back into ``st``.  ``raw_f32`` = [B*(T+P), K] fp32 encoder rows, ``w_split`` =
+    split_bf16x3(W_ctc, pattern 1).  Returns the device counter of flagged frames (int32[1]); no host sync."""
+    dev = st.argmax.device
+    frame_idx = torch.empty(cap, dtype=torch.int32, device=dev)
+    raw_row = torch.empty(cap, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = L.lib()
+    L.check(lib.tasu_flag_ambiguous_frames(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
+                                           st.row_sumexp.data_ptr(), lens.data_ptr(), st.B, T, n_prefix, blank_id,
+                                           float(threshold), float(p_max_min), float(band), cap, frame_idx.data_ptr(),
+                                           raw_row.data_ptr(), count.data_ptr(), _stream()), "tasu_flag_ambiguous_frames")
+    K = raw_f32.shape[1]
+    xg = torch.empty(cap, K, dtype=torch.float32, device=dev)                       # unused slots (-1) gather zero rows
+    L.check(lib.tasu_gather_rows(raw_f32.data_ptr(), L.F32, raw_f32.stride(0), raw_row.data_ptr(), cap, K, xg.data_ptr(), K,
+                                 _stream()), "tasu_gather_rows")
+    _count(2)
+    xs, kx, _, _, _ = split_bf16x3(xg, 0)
+    assert kx == k_split
+    ldv = pad_to(V, 4)
+    logits = torch.empty(cap, ldv, dtype=torch.float32, device=dev)
+    # only the live rows (device-side count) go through the tensor cores; rows beyond it hold stale values that the
+    # scatter never reads
+    gemm_fp32x3(xs, w_split, cap, V, kx, logits, L.EPI_BIAS if bias is not None else L.EPI_NONE, bias, m_dev=count)
+    st2 = frame_stats(logits.view(1, cap, ldv)[:, :, :V], L.INPUT_LOGITS, blank_id)
+    L.check(lib.tasu_scatter_frame_stats(frame_idx.data_ptr(), count.data_ptr(), cap, st2.argmax.data_ptr(),
+                                         st2.x_blank.data_ptr(), st2.row_max.data_ptr(), st2.row_sumexp.data_ptr(),
+                                         st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
+                                         st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), _stream()), "tasu_scatter_frame_stats")
+    _count(1)
+    return count
+
+
 def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, V: int, plan: "CollapsePlan",
                      st: FrameStats, n_frames: int, n_out: int, ln_eps: float = 1e-5):
     """→ (xg bf16 [n_frames, pad64(K)], g_max, g_inv_sum [n_frames], pk_len, tail_src int32 [n_out],
@@ -504,7 +540,8 @@ def split_bf16x3(src: torch.Tensor, pattern: int, col_scale: Optional[torch.Tens
 
 
 def gemm_fp32x3(a_split: torch.Tensor, b_split: torch.Tensor, M: int, N: int, Ksplit: int, out: torch.Tensor,
-                epilogue: int = L.EPI_NONE, bias=None, row_rstd=None, row_mean=None, colsum=None, slice_k: int = 1536):
+                epilogue: int = L.EPI_NONE, bias=None, row_rstd=None, row_mean=None, colsum=None, slice_k: int = 1536,
+                m_dev: Optional[torch.Tensor] = None):
     """fp32-accurate GEMM on split operands (split_bf16x3): K' is cut into slices of ``slice_k`` so the tensor core's
     truncating accumulation stays short; the slices are summed with round-to-nearest fp32 adds (tasu_sum_epilogue)."""
     n_parts = (Ksplit + slice_k - 1) // slice_k
@@ -512,7 +549,7 @@ def gemm_fp32x3(a_split: torch.Tensor, b_split: torch.Tensor, M: int, N: int, Ks
     parts = torch.empty(n_parts, M, ldp, dtype=torch.float32, device=out.device)
     for p in range(n_parts):
         k0, k1 = p * slice_k, min(Ksplit, (p + 1) * slice_k)
-        gemm_bf16_tn(a_split[:, k0:k1], b_split[:, k0:k1], M, N, k1 - k0, parts[p])
+        gemm_bf16_tn(a_split[:, k0:k1], b_split[:, k0:k1], M, N, k1 - k0, parts[p], m_dev=m_dev)
     L.check(L.lib().tasu_sum_epilogue(parts.data_ptr(), n_parts, M * ldp, M, N, ldp, epilogue, _ptr(bias), _ptr(row_rstd),
                                       _ptr(row_mean), _ptr(colsum), out.data_ptr(), _dt(out), out.stride(0), _stream()),
             "tasu_sum_epilogue")

@@ -298,3 +298,68 @@ def test_merge_random_vs_oracle(dev, seed):
             assert o is None
             continue
         assert r.dtype == o.dtype and torch.equal(r, o.cpu())
+
+
+def test_exact_decisions_on_adversarial_frames(dev):
+    """Frames planted INSIDE the bf16 noise of the fused head — blank probability 0.9 ± 1e-4..1e-3 (keep/drop threshold,
+    ps-slm.py:295-297) and two labels whose logits differ by 1e-3 (argmax, :265) — must give the fp32 reference's
+    compressed lengths, masks and positions when TasuBridge.exact_decisions is on."""
+    import types
+
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 2, 96
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=31)
+    g = torch.Generator().manual_seed(5)
+    u = w / (w.norm(dim=1, keepdim=True) ** 2)                        # u_v · w_v = 1
+
+    def p_blank(x):
+        return torch.softmax(torch.nn.functional.linear(x, w, b), -1)[0]
+
+    planted = 0
+    for k, t in enumerate(range(3, T, 4)):                            # every 4th frame: blank near the threshold
+        noise = 0.02 * torch.randn(S.D_ENC, generator=g)
+        target = 0.9 + (1 if k % 2 else -1) * (1e-4, 3e-4, 1e-3)[k % 3]
+        lo, hi = 5.0, 40.0
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if float(p_blank(mid * u[0] + noise)) < target:
+                lo = mid
+            else:
+                hi = mid
+        raw[k % B, 4 + t] = 0.5 * (lo + hi) * u[0] + noise
+        planted += 1
+    for k, t in enumerate(range(1, T, 16)):                           # near-tie argmax between two labels
+        a_, b_ = 100 + k, 2000 + k
+        lo, hi = 0.0, 1.0
+        for _ in range(60):
+            lam = 0.5 * (lo + hi)
+            x = 18.0 * (lam * u[a_] + (1 - lam) * u[b_])
+            z = torch.nn.functional.linear(x, w, b)
+            if float(z[a_] - z[b_]) < 1e-3:
+                lo = lam
+            else:
+                hi = lam
+        raw[(k + 1) % B, 4 + t] = 18.0 * (hi * u[a_] + (1 - hi) * u[b_])
+    ids, mask, _ = S.make_prompts(B, seed=2, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg)
+    table = S.make_embed_table(dtype=torch.float32)
+    sd = proj.state_dict()
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    (e_r, m_r, _, p_r, _), nl_r = O.bridge_inference(raw, raw_lens, w, b, pp, table, ids, mask, None, S.SPEECH_ID, S.PAD_ID)
+    br = TasuBridge(w.to(dev), b.to(dev), proj.to(dev).eval(), table.to(dev), S.SPEECH_ID, S.PAD_ID)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    br.exact_decisions = True
+    e, m, _, p, nl = br(*args)
+    n_amb = int(br.last_ambiguous.item())
+    assert n_amb >= planted, (n_amb, planted)                         # every planted frame was caught and refined
+    assert torch.equal(nl.cpu(), nl_r), (nl.cpu().tolist(), nl_r.tolist())
+    assert torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    assert ((e.cpu().float() - e_r).norm() / e_r.norm()).item() < 1e-2
+    br.exact_decisions = False                                        # for the record: the plain bf16 head on the same batch
+    nl0 = br(*args)[4]
+    print("bf16-head compressed lengths", nl0.cpu().tolist(), "fp32 reference", nl_r.tolist(), "refined frames", n_amb)
