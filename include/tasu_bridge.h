@@ -276,6 +276,12 @@ int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_stride, int 
                       int epilogue, const float* bias, const float* row_rstd, const float* row_mean,
                       const float* colsum, void* out, int out_dtype, int64_t ldo, void* stream);
 
+/* Row softmax with known statistics (tasu_frame_stats, TASU_INPUT_LOGITS): out[r, v] = bf16(exp(x[r,v] - row_max[r]) /
+ * row_sumexp[r]), columns V..out_row_stride-1 zeroed — the K-major A operand of the vocabulary-transfer contraction
+ * softmax(logits_no_blank) · embed_matrix (ps-slm.py:494-497, :509-511). */
+int tasu_softmax_rows(const void* x, int x_dtype, int64_t x_row_stride, int64_t rows, int V, const float* row_max,
+                      const float* row_sumexp, void* out_bf16, int64_t out_row_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Token-row projector: steps 1a + 3 fused for TEXT-SIMULATED posteriors (ps-slm.py:337-358, :360-409 feeding
  * projector.py:149-151).  Every simulated row is  base*1 + (hot-base)*onehot(tok)  (clean: hot=1, base=0;

@@ -205,9 +205,11 @@ def golden_model():
     for name in F.CASES:
         inp = F.build_inputs(name)
         cls = {"linear-silu": pmod.EncoderProjectorLinearSiLU, "linear": pmod.EncoderProjectorConcat,
-               "cross-attention": pmod.EncoderProjectorCTCCA}[inp["proj"]]
+               "cross-attention": pmod.EncoderProjectorCTCCA, "simple_linear": pmod.EncoderProjectorLinear}[inp["proj"]]
         encoder, llm, projector, tok, train_config, model_config = F.build_parts(inp, cls)
-        m = mod.slam_model_asr.__new__(mod.slam_model_asr)
+        # the shipped voca_trans branch raises UnboundLocalError: that one case runs the source with the one-line fix
+        mod_c = R.load_voca_fixed() if inp["flags"].get("voca_trans") else mod
+        m = mod_c.slam_model_asr.__new__(mod_c.slam_model_asr)
         torch.nn.Module.__init__(m)
         m.encoder, m.llm, m.encoder_projector, m.tokenizer = encoder, llm, projector, tok
         m.metric = "acc"

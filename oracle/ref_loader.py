@@ -175,3 +175,23 @@ def load_dataset_module():
             sys.modules.pop(name, None)                       # importlib.util.find_spec("torchaudio") later on
     _cache["dataset"] = mod
     return mod
+
+
+def load_voca_fixed():
+    """The reference's model/ps-slm.py with ONE line added in memory: its ``voca_trans`` branch reads ``encoder_outs`` /
+    ``encoder_feature_length`` before assigning them (ps-slm.py:488, :618 — UnboundLocalError as shipped); the fix binds
+    them to ``encoder_out`` / ``encoder_out_lens`` right after the branch's print statement.  Nothing else differs from
+    the file on disk, which is never modified."""
+    if "voca" in _cache:
+        return _cache["voca"]
+    load()                                                     # stubs + sys.path
+    path = os.path.join(REF_ROOT, "model", "ps-slm.py")
+    src = open(path).read()
+    marker = 'print("Vocabulary Transform is ready ...")'
+    assert src.count(marker) == 2, "reference layout changed"
+    src = src.replace(marker, marker + "; encoder_outs, encoder_feature_length = encoder_out, encoder_out_lens")
+    mod = types.ModuleType("tasu_reference_ps_slm_voca_fixed")
+    mod.__file__ = path
+    exec(compile(src, path, "exec"), mod.__dict__)
+    _cache["voca"] = mod
+    return mod

@@ -276,6 +276,28 @@ def projector_ctcca(post, llm_embed, wq, n_heads: int = 8):
     return z.contiguous().view(B, T, -1)                           # :124
 
 
+def voca_trans(encoder_out, encoder_out_lens, w_map, b_map, k, embed_matrix, do_psd, top1_emb, blank_id=151643):
+    """Vocabulary-transfer branch — Multitask/model/ps-slm.py:485-516 (forward) / :615-646 (generate).  The shipped
+    reference reads ``encoder_outs`` / ``encoder_feature_length`` there before assigning them (UnboundLocalError); this
+    restates the branch with ``encoder_out`` / ``encoder_out_lens``, the only candidates in scope, and is pinned against
+    the reference source with exactly that one-line fix applied in memory (oracle/make_golden.py, golden case
+    ``infer_voca_trans``)."""
+    logits = projector_linear(encoder_out, k, w_map, b_map)             # :488  simple_linear as a CTC head
+    lens = encoder_out_lens // k                                        # :489
+    if do_psd:
+        post = torch.softmax(logits, dim=-1)                            # :490
+        outs, lens, _ = psd_vec(logits, lens, post, blank_id, 0.9)      # :491  features = the logits themselves
+        v_real = outs.size(-1) - 1                                      # :494
+        ctc = torch.softmax(outs[..., :v_real], dim=-1)                 # :495-496
+        res = torch.einsum("btv,vh->bth", ctc, embed_matrix[:v_real])   # :497
+    else:
+        ctc = torch.softmax(logits, dim=-1)                             # :510
+        res = torch.einsum("btv,vh->bth", ctc, embed_matrix[:logits.size(-1)])   # :511
+    if top1_emb:
+        res = embed_matrix[ctc.argmax(dim=-1)]                          # :500-502, :514-516
+    return res, lens
+
+
 # --------------------------------------------------------------------------
 # (a8) splice — Multitask/model/ps-slm.py:679-873
 # --------------------------------------------------------------------------

@@ -36,6 +36,7 @@ SIGNATURES = {
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_softmax_rows": (_I, [_P, _I, _L, _L, _I, _P, _P, _P, _L, _P]),
     "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "tasu_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "tasu_gemm_bf16_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P]),

@@ -76,6 +76,53 @@ def psd_from_encoder(raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.
     return out, plan.new_lens
 
 
+LLM_BLANK_ID = 151643     # blank index of the LLM-vocabulary CTC head, hard-coded in the reference (ps-slm.py:491, :621)
+
+
+def voca_trans_project(projector, encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, embed_table_bf16: torch.Tensor,
+                       do_psd: bool, top1_emb: bool, blank_id: int = LLM_BLANK_ID, blank_threshold: float = BLANK_THRESHOLD):
+    """Vocabulary-transfer branch (``voca_trans=True``; ps-slm.py:485-513 / :615-643) with the input the branch evidently
+    means — the reference reads ``encoder_outs`` there before assigning it (UnboundLocalError as shipped); the only
+    tensor of the right shape in scope is ``encoder_out``:
+
+      logits = simple_linear projector (a CTC head over the LLM vocabulary, projector.py:10-26)
+      do_psd: psd(features = logits, posterior = softmax(logits), blank = 151643)  → pooled logits, blank column dropped
+      softmax over the remaining columns · embed_matrix[:V_real]   (or the embedding row of the top-1 id, ``top1_emb``)
+
+    No ``[B, T, V]`` softmax tensor is materialised: greedy statistics come from ``tasu_frame_stats`` on the logits,
+    the contraction reads the embedding table in place (MN-major B operand of ``tasu_gemm_bf16_f32``).
+    Returns ``(projector_outs [B, T_new, H] fp32 | table dtype for top1, lengths [B] int64)``."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in projector.parameters()):
+        raise NotImplementedError("the voca_trans branch of the B200 bridge is inference-only")
+    logits = projector(encoder_out)                                        # [B, T', Vp] (a view of a 16-byte-pitched buffer)
+    B, Tp, Vp = logits.shape
+    dev = logits.device
+    H = embed_table_bf16.shape[1]
+    feat_len = encoder_out_lens.to(device=dev, dtype=torch.int64) // projector.k
+    if do_psd:
+        st = ops.frame_stats(logits, L.INPUT_LOGITS, blank_id, feat_len)
+        plan = ops.collapse_plan(st, feat_len, blank_id, blank_threshold)
+        max_len = int(plan.header.cpu()[L.CH_MAX_LEN])
+        if max_len == 0:
+            return torch.zeros(B, 0, H, dtype=torch.float32, device=dev), torch.zeros(B, dtype=torch.long, device=dev)
+        pitch = ops.pad_to(Vp, 4)
+        pooled = torch.empty(B * max_len, pitch, dtype=logits.dtype, device=dev)
+        ops.segment_meanpool(logits, plan, 1, max_len, B * max_len, pooled, pitch)       # mean of the LOGITS (ps-slm.py:286)
+        rows, new_lens, V_real = pooled, plan.new_lens, Vp - 1                            # :493 drops the blank column
+    else:
+        rows = logits.reshape(B * Tp, Vp) if logits.is_contiguous() else logits.contiguous().view(B * Tp, Vp)
+        new_lens, max_len, V_real = feat_len, Tp, Vp                                      # :509-511 keeps every column
+    N = rows.shape[0]
+    st2 = ops.frame_stats(rows.unsqueeze(0)[:, :, :V_real], L.INPUT_LOGITS, 0)
+    if top1_emb:                                                                          # :498-502, :512-516
+        out = ops.gather_rows(embed_table_bf16, st2.argmax)
+    else:
+        probs = ops.softmax_rows(rows, V_real, st2)
+        out = torch.empty(N, H, dtype=torch.float32, device=dev)
+        ops.gemm_bf16_f32(probs, False, embed_table_bf16[:V_real], True, N, H, V_real, out)
+    return out.view(B, max_len, H), new_lens
+
+
 def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_tokens: torch.Tensor,
                                         inputs_embeds: torch.Tensor, input_ids: torch.Tensor,
                                         attention_mask: torch.Tensor, labels: Optional[torch.Tensor],

@@ -122,6 +122,31 @@ sim_rows_kernel(const int32_t* __restrict__ tok, const float* __restrict__ hot, 
     }
 }
 
+// out[r, v] = bf16(exp(x[r, v] - row_max[r]) / row_sumexp[r]) for v < V, 0 for V <= v < ldo: the softmax of rows whose
+// statistics are known (tasu_frame_stats), written as the K-major bf16 A operand of a following contraction
+// (voca_trans: softmax(logits_no_blank) · embed_matrix, ps-slm.py:494-497).  One CTA per row, grid-stride.
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const Ti* __restrict__ x, int64_t xstride, int64_t rows, int V, const float* __restrict__ row_max,
+                    const float* __restrict__ row_sumexp, __nv_bfloat16* __restrict__ out, int64_t ostride) {
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const Ti* s = x + r * xstride;
+        __nv_bfloat16* d = out + r * ostride;
+        const float m = row_max[r] * 1.4426950408889634f, inv = 1.f / row_sumexp[r];
+        const int bd = blockDim.x;
+        int c = threadIdx.x;
+        for (; c + 3 * bd < V; c += 4 * bd) {                   // 4 independent coalesced loads in flight per thread
+            const float v0 = to_f32(s[c]), v1 = to_f32(s[c + bd]), v2 = to_f32(s[c + 2 * bd]), v3 = to_f32(s[c + 3 * bd]);
+            d[c] = __float2bfloat16_rn(exp2f(fmaf(v0, 1.4426950408889634f, -m)) * inv);
+            d[c + bd] = __float2bfloat16_rn(exp2f(fmaf(v1, 1.4426950408889634f, -m)) * inv);
+            d[c + 2 * bd] = __float2bfloat16_rn(exp2f(fmaf(v2, 1.4426950408889634f, -m)) * inv);
+            d[c + 3 * bd] = __float2bfloat16_rn(exp2f(fmaf(v3, 1.4426950408889634f, -m)) * inv);
+        }
+        for (; c < V; c += bd) d[c] = __float2bfloat16_rn(exp2f(fmaf(to_f32(s[c]), 1.4426950408889634f, -m)) * inv);
+        for (int64_t k = V + threadIdx.x; k < ostride; k += bd) d[k] = __float2bfloat16_rn(0.f);
+    }
+}
+
 // one warp per kept candidate: copy its frames' encoder rows (K bf16 each) into the compact matrix.
 // Row r < n_out holds the candidate's first frame, extra frames of multi-frame runs go to the tail.
 __global__ void __launch_bounds__(256)
@@ -378,6 +403,24 @@ extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out
     pool_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
                                                                          tail_src, multi_rows, multi_count, ln_mean,
                                                                          ln_rstd, ln_eps);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_softmax_rows(const void* x, int x_dtype, int64_t x_row_stride, int64_t rows, int V, const float* row_max,
+                                 const float* row_sumexp, void* out_bf16, int64_t out_row_stride, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && V > 0 && x_row_stride >= V && out_row_stride >= V, "shape");
+    TASU_CHECK_ARG(x_dtype == TASU_F32 || x_dtype == TASU_BF16, "x_dtype");
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(x && row_max && row_sumexp && out_bf16, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = row_grid(rows);
+    if (x_dtype == TASU_F32)
+        softmax_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_row_stride, rows, V, row_max, row_sumexp,
+                                                         (__nv_bfloat16*)out_bf16, out_row_stride);
+    else
+        softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, x_row_stride, rows, V, row_max, row_sumexp,
+                                                                 (__nv_bfloat16*)out_bf16, out_row_stride);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -121,10 +121,8 @@ class slam_model_asr(nn.Module):
         self.gt_emb_noise = _cfg_get(train_config, "gt_emb_noise", False)
         self.top1_emb = _cfg_get(train_config, "top1_emb", False)
         self.cross_attn = model_config.encoder_projector == "cross-attention"
-        if self.voca_trans:
-            # the reference's own voca_trans branch reads `encoder_outs` before assigning it (ps-slm.py:488, :618)
-            raise NotImplementedError("voca_trans has no runnable reference behaviour (UnboundLocalError at ps-slm.py:488); "
-                                      "it is a 'next' row of the scope table (SURVEY §8f)")
+        # voca_trans: the reference's own branch reads `encoder_outs` before assigning it (ps-slm.py:488, :618 —
+        # UnboundLocalError as shipped); bridge.voca_trans_project implements it on `encoder_out`, the evident intent
         self.encoder_tokenizer = kwargs.get("encoder_tokenizer", None)
         if self.encoder_tokenizer is None and (self.gt_emb or kwargs.get("need_encoder_tokenizer", False)):
             ref = _load_reference_module()           # SentencePiece wrapper of the reference (host-side, out of scope)
@@ -133,6 +131,7 @@ class slam_model_asr(nn.Module):
             del ref
         self._bridge = None
         self._ctc_cache = _bridge.ProjectorCache()
+        self._table_cache = _bridge.ProjectorCache()
         # text-only batches go through the token-row projector (no [B, L, 25055] tensor); False = dense simulator path
         self.token_row_path = True
 
@@ -221,6 +220,16 @@ class slam_model_asr(nn.Module):
         if raw_encoder_out is not None:                        # None on the text-only branch (encoder skipped)
             encoder_out = raw_encoder_out[:, 4:, :]
             encoder_out_lens = torch.clamp(raw_encoder_out_lens - 4, min=0)
+        if self.ctc_posterior and self.voca_trans:                 # ps-slm.py:485-513 / :615-643
+            tb = self._table_cache.get([table], lambda: (
+                table.detach().contiguous() if table.dtype == torch.bfloat16
+                else _ops.cast_rows(table.detach().contiguous(), torch.bfloat16)[0]))
+            projector_outs, feat_len = _bridge.voca_trans_project(self.encoder_projector, encoder_out, encoder_out_lens, tb,
+                                                                  self.do_psd, self.top1_emb)
+            inputs_embeds = self.llm.get_input_embeddings()(input_ids)
+            emb, mask, out_labels, pos, _ = self._merge_input_ids_with_audio_features(
+                projector_outs, feat_len, inputs_embeds, input_ids, attention_mask, labels)
+            return emb, mask, out_labels, pos
         if self.ctc_posterior:
             if self.gt_emb:
                 post, lens = (self.ctc_pseudo_posterior_noise(texts) if noisy else self.ctc_pseudo_posterior(texts))

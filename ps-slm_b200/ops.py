@@ -311,6 +311,31 @@ def gemm_bf16_f32(A: torch.Tensor, a_mn_major: bool, Bw: torch.Tensor, b_mn_majo
     return out
 
 
+def softmax_rows(x2: torch.Tensor, V: int, st: FrameStats) -> torch.Tensor:
+    """bf16 [rows, pad64(V)] = softmax(x2[:, :V]) with the row max / sum-exp of ``st`` (tasu_softmax_rows)."""
+    _need_cuda(x2)
+    rows = x2.shape[0]
+    ld = pad_to(V)
+    out = torch.empty(max(rows, 1), ld, dtype=torch.bfloat16, device=x2.device)[:rows]
+    L.check(L.lib().tasu_softmax_rows(x2.data_ptr(), _dt(x2), x2.stride(0) if rows > 1 else max(V, x2.shape[-1]), rows, V,
+                                      st.row_max.data_ptr(), st.row_sumexp.data_ptr(), out.data_ptr(), ld, _stream()),
+            "tasu_softmax_rows")
+    _count(1)
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[idx[i]] (idx int32; -1 → zero row) — tasu_gather_rows."""
+    _need_cuda(src, idx)
+    H = src.shape[1]
+    n = idx.numel()
+    out = torch.empty(max(n, 1), H, dtype=src.dtype, device=src.device)[:n]
+    L.check(L.lib().tasu_gather_rows(src.data_ptr(), _dt(src), src.stride(0), idx.data_ptr(), n, H, out.data_ptr(), H, _stream()),
+            "tasu_gather_rows")
+    _count(1)
+    return out
+
+
 def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor, V: int, out: torch.Tensor,
                        out_row_stride: int, dst_row: Optional[torch.Tensor] = None,
                        ln_mean: Optional[torch.Tensor] = None, ln_rstd: Optional[torch.Tensor] = None,

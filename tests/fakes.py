@@ -9,6 +9,7 @@ import torch.nn as nn
 
 V, D, H, LLM_VOCAB = 61, 32, 48, 200
 SPEECH_ID, PAD_ID, BOS_ID, EOS_ID = 199, 0, 1, 2
+VOCA_HEAD, VOCA_LLM_ROWS = 151644, 151650          # CTC head over the LLM vocabulary: 151643 labels + blank (ps-slm.py:491)
 
 
 class FakeEncoderCore(nn.Module):
@@ -42,9 +43,9 @@ class FakeSenseVoice(nn.Module):
 class FakeLLM(nn.Module):
     """Records what the bridge hands to the LLM; returns logits from a linear head."""
 
-    def __init__(self):
+    def __init__(self, vocab=LLM_VOCAB):
         super().__init__()
-        self.emb = nn.Embedding(LLM_VOCAB, H)
+        self.emb = nn.Embedding(vocab, H)
         self.head = nn.Linear(H, LLM_VOCAB)
         self.seen = None
 
@@ -147,6 +148,9 @@ CASES = {
                         "linear", D, 2, True, False, "generate"),
     "posterior_nopsd": (dict(ctc_posterior=True, do_psd=False, voca_trans=False, gt_emb=False, gt_emb_noise=False, top1_emb=False),
                         "linear-silu", V, 1, True, False, "generate"),
+    # vocabulary transfer: simple_linear projector = CTC head over the LLM vocabulary, blank id 151643 (ps-slm.py:491)
+    "infer_voca_trans": (dict(ctc_posterior=True, do_psd=True, voca_trans=True, gt_emb=False, gt_emb_noise=False, top1_emb=False),
+                         "simple_linear", D, 2, True, False, "generate"),
     "infer_cross_attn": (dict(ctc_posterior=True, do_psd=True, voca_trans=False, gt_emb=False, gt_emb_noise=False, top1_emb=False),
                          "cross-attention", V, 1, True, False, "generate"),
 }
@@ -175,10 +179,16 @@ def build_parts(inp, projector_cls, seed=0):
     """(encoder, llm, projector, tokenizer, train_config, model_config) with seeded weights."""
     torch.manual_seed(400 + seed)
     encoder = FakeSenseVoice(inp["canned"], inp["lens"], inp["w"], inp["b"])
-    llm = FakeLLM()
-    model_config = Cfg(encoder_projector=inp["proj"], encoder_dim=inp["enc_dim"], llm_dim=H,
+    voca = bool(inp["flags"].get("voca_trans"))
+    llm = FakeLLM(VOCA_LLM_ROWS) if voca else FakeLLM()
+    model_config = Cfg(encoder_projector=inp["proj"], encoder_dim=inp["enc_dim"], llm_dim=VOCA_HEAD if voca else H,
                        encoder_projector_ds_rate=inp["k"], encoder_path="unused")
     projector = projector_cls(model_config)
+    if voca:
+        with torch.no_grad():                          # a peaky head: frames decide for a label or for the blank (151643)
+            projector.map.weight.mul_(12.0)
+            projector.map.bias.zero_()
+            projector.map.bias[VOCA_HEAD - 1] = 3.0
     if inp["proj"] == "linear-silu":
         with torch.no_grad():
             projector.norm.weight.uniform_(0.8, 1.2)

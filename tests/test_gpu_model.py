@@ -65,3 +65,35 @@ def test_raw_feature_psd_from_encoder(dev):
     out, new_lens = bridge.psd_from_encoder(raw.to(dev), raw_lens.to(dev), bridge.cast_weight_bf16(w.to(dev)), b.to(dev))
     assert torch.equal(new_lens.cpu(), ref_lens) and out.shape == ref.shape
     assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("do_psd,top1", [(True, False), (False, False), (True, True), (False, True)])
+def test_voca_trans_project(dev, do_psd, top1):
+    """bridge.voca_trans_project (ps-slm.py:485-516 with the evident input) vs the oracle restatement: CTC head over a
+    small "LLM vocabulary" (blank = last class), PSD on the logits, softmax(no-blank) · embedding table / top-1 rows."""
+    import types
+
+    import ps_slm_b200.bridge as bridge
+    import ps_slm_b200.projector as P
+    from oracle import tasu_oracle as O
+    torch.manual_seed(3)
+    Denc, k, Vh, H, B, T = 24, 2, 301, 64, 3, 41                     # head: 300 labels + blank (id 300)
+    proj = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=Denc, llm_dim=Vh, encoder_projector_ds_rate=k))
+    with torch.no_grad():
+        proj.map.weight.mul_(14.0)
+        proj.map.bias.zero_()
+        proj.map.bias[Vh - 1] = 2.5
+    table = torch.randn(Vh + 7, H) * 0.3
+    x = torch.randn(B, T, Denc)
+    x[:, 1::3] = x[:, 0:-1:3][:, :x[:, 1::3].shape[1]]                # repeated frames → multi-frame runs after the k-concat
+    lens = torch.tensor([T, 17, 30])
+    with torch.no_grad():
+        ref, ref_lens = O.voca_trans(x, lens, proj.map.weight, proj.map.bias, k, table, do_psd, top1, blank_id=Vh - 1)
+        out, new_lens = bridge.voca_trans_project(proj.to(dev).eval(), x.to(dev), lens.to(dev), table.to(dev).bfloat16(),
+                                                  do_psd, top1, blank_id=Vh - 1)
+    assert torch.equal(new_lens.cpu(), ref_lens) and out.shape == ref.shape
+    for b in range(B):                                                # rows beyond the compressed length are padding
+        n = int(ref_lens[b])
+        if n:
+            err = ((out[b, :n].float().cpu() - ref[b, :n]).norm() / ref[b, :n].norm()).item()
+            assert err < (2e-2 if not top1 else 1e-2), (b, err)
