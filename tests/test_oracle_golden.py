@@ -123,3 +123,37 @@ def test_merge_golden_errors(golden, name):
     ids, att, M = _t(g[name + "_ids"]), _t(g[name + "_att"]).bool(), _t(g[name + "_M"])
     with pytest.raises(ValueError):
         O.merge(torch.zeros(ids.shape[0], int(M.max()), 8), M, torch.zeros(*ids.shape, 8), ids, att, None, SP, PAD)
+
+
+@pytest.mark.parametrize("name", ["infer_cross_attn", "infer_voca_trans"])
+def test_oracle_reproduces_model_golden(golden, name):
+    """CPU: the oracle restatements of the cross-attention projector (projector.py:104-126) and of the voca_trans branch
+    (ps-slm.py:485-516) reproduce what the reference handed to the LLM (tests/golden/model.npz; the voca_trans case comes
+    from the reference source with its one-line UnboundLocalError fix, oracle/ref_loader.py:load_voca_fixed)."""
+    import fakes as F
+    import torch
+    from oracle import tasu_oracle as O
+    import ps_slm_b200.projector as P                       # only as a parameter container with the reference's names/init
+    g = golden["model"]
+    inp = F.build_inputs(name)
+    encoder, llm, projector, tok, train_config, model_config = F.build_parts(inp, P.PROJECTORS[inp["proj"]])
+    wsum = sum(float(p.detach().double().sum()) for m in (encoder, llm, projector) for p in m.parameters())
+    assert abs(wsum - float(g[f"{name}_wsum"])) < 1e-6 * max(1.0, abs(wsum))
+    batch = inp["batch"]
+    with torch.no_grad():
+        raw, raw_lens = encoder.encoder(torch.zeros(batch["input_features"].shape[0], batch["input_features"].shape[1] + 4, 1),
+                                        batch["input_feature_length"] + 4)
+        lens = torch.clamp(raw_lens.long() - 4, min=0)
+        table = llm.emb.weight
+        if name == "infer_cross_attn":
+            post = torch.softmax(encoder.ctc.ctc_lo(raw), -1)[:, 4:]
+            outs, feat_len, _ = O.psd_vec(post, lens, post, 0, 0.9)
+            proj = O.projector_ctcca(outs, table, projector.W_q.weight, projector.n_heads)
+        else:
+            proj, feat_len = O.voca_trans(raw[:, 4:], lens, projector.map.weight, projector.map.bias, projector.k, table,
+                                          True, False)
+        emb, mask, _, _, _ = O.merge(proj, feat_len, table[batch["input_ids"]], batch["input_ids"], batch["attention_mask"],
+                                     None, F.SPEECH_ID, F.PAD_ID)
+    assert np.array_equal(mask.numpy(), g[f"{name}_ref_mask"])
+    ref = torch.from_numpy(g[f"{name}_ref_embeds"])
+    assert emb.shape == ref.shape and torch.allclose(emb, ref, rtol=1e-4, atol=1e-5)
