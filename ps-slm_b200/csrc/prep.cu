@@ -211,7 +211,7 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
 
 // multi-frame candidates only: probs[r] = mean over its frames, in place; LayerNorm statistics of the result.
 // Work list = multi_rows[0, *multi_count) (any order) or, without it, every row with pk_len > 1.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n_out, const int32_t* __restrict__ pk_len,
                  const int32_t* __restrict__ tail_src, const int32_t* __restrict__ multi_rows,
                  const int32_t* __restrict__ multi_count, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
