@@ -106,9 +106,11 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
 
 def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, raw_f32: torch.Tensor, w_split: torch.Tensor, k_split: int,
                             bias: Optional[torch.Tensor], T: int, n_prefix: int, V: int, blank_id: int, threshold: float,
-                            p_max_min: float = 0.6, band: float = 0.02, cap: int = 1024) -> torch.Tensor:
+                            p_max_min: float = 0.53, band: float = 0.02, cap: int = 512) -> torch.Tensor:
     """Exact-decision mode: recompute the statistics of the frames tasu_flag_ambiguous_frames lists with the
-    fp32-accurate GEMM and write them back into ``st``.  ``raw_f32`` = [B*(T+P), K] fp32 encoder rows, ``w_split`` =
+    fp32-accurate GEMM and write them back into ``st``.  Defaults: bf16 rounding of the 512-term dot products moves a
+    logit by a few 1e-2, so an argmax can only flip when the runner-up is within ~0.1 of it, i.e. p_max <= 1/(1+e^-0.1)
+    = 0.525; a blank probability near 0.9 moves by p(1-p)*0.1 < 0.01.  ``raw_f32`` = [B*(T+P), K] fp32 encoder rows, ``w_split`` =
     split_bf16x3(W_ctc, pattern 1).  Returns the device counter of flagged frames (int32[1]); no host sync."""
     dev = st.argmax.device
     frame_idx = torch.empty(cap, dtype=torch.int32, device=dev)
