@@ -249,6 +249,13 @@ int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ld
  *   tasu_linear_silu_wgrad_finish   with G = dzsT · x  ([Hb, V], from tasu_gemm_bf16_tn):
  *                        dW1 = gamma*(G - g0) + beta*db1, dgamma = sum_j W1*(G - g0), dbeta = sum_j W1*db1
  */
+/* Backward of the cross-attention projector (projector.py:104-126; trained by autograd in the reference): per head,
+ * dS = P ∘ (dP − δ), δ_r = dZ[r,:]·Z[r,:] (= Σ_v P·dP), written as the bf16 K-major A operand of dQ_h = dS · K_h.
+ * P = the head's probabilities (tasu_gemm_bf16_tn, EPI_SOFTMAX), dP = dZ_h · K_hᵀ (tasu_gemm_bf16_tn), dZ / Z = the
+ * head's d-wide slices of the output gradient / output (row stride z_stride). */
+int tasu_attn_score_grad(const void* P_bf16, int64_t p_stride, const float* dP, int64_t dp_stride,
+                         const float* dZ, const float* Z, int64_t z_stride, int d, int64_t rows, int V,
+                         void* dS_bf16, int64_t ds_stride, void* stream);
 int tasu_transpose_cast(const void* src, int src_dtype, int64_t rows, int64_t cols, int64_t src_stride,
                         const float* row_scale, void* dst_bf16, int64_t dst_stride, void* stream);
 int tasu_silu_fwd(const float* z, int64_t n, void* h_bf16, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "tasu_ctc_head_stats_workspace": (_L, [_I, _I, _I]),
     "tasu_ctc_head_stats": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_gemm_bf16_tn_simt": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "tasu_attn_score_grad": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _L, _I, _P, _L, _P]),
     "tasu_transpose_cast": (_I, [_P, _I, _L, _L, _L, _P, _P, _L, _P]),
     "tasu_silu_fwd": (_I, [_P, _L, _P, _P]),
     "tasu_silu_bwd": (_I, [_P, _P, _L, _I, _P, _P, _P, _L, _P, _P, _P]),

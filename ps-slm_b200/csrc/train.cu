@@ -127,9 +127,52 @@ wgrad_finish_kernel(const float* __restrict__ G, int64_t gstride, const float* _
     atomicAdd(dbeta + v, ab);
 }
 
+// Softmax-attention backward, score gradient: dS[r,v] = P[r,v]·(dP[r,v] − δ_r) with δ_r = Σ_v P[r,v]·dP[r,v] = dZ[r,:]·Z[r,:]
+// (Z = P·V, dP = dZ·Vᵀ), so δ needs only the d-wide output rows.  One CTA per row; bf16 K-major operand of dQ = dS·K.
+__global__ void __launch_bounds__(256)
+attn_ds_kernel(const __nv_bfloat16* __restrict__ P, int64_t pstride, const float* __restrict__ dP, int64_t dstride,
+               const float* __restrict__ dZ, const float* __restrict__ Z, int64_t zstride, int d, int64_t rows, int V,
+               __nv_bfloat16* __restrict__ dS, int64_t sstride) {
+    __shared__ float red[8];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        float part = 0.f;
+        for (int c = threadIdx.x; c < d; c += blockDim.x) part = fmaf(dZ[r * zstride + c], Z[r * zstride + c], part);
+        const float delta = block_sum_f(part, red);
+        const __nv_bfloat16* p = P + r * pstride;
+        const float* g = dP + r * dstride;
+        __nv_bfloat16* o = dS + r * sstride;
+        const int bd = blockDim.x;
+        int c = threadIdx.x;
+        for (; c + 3 * bd < V; c += 4 * bd) {
+            const float p0 = __bfloat162float(p[c]), p1 = __bfloat162float(p[c + bd]), p2 = __bfloat162float(p[c + 2 * bd]),
+                        p3 = __bfloat162float(p[c + 3 * bd]);
+            const float g0 = g[c], g1 = g[c + bd], g2 = g[c + 2 * bd], g3 = g[c + 3 * bd];
+            o[c] = __float2bfloat16_rn(p0 * (g0 - delta)); o[c + bd] = __float2bfloat16_rn(p1 * (g1 - delta));
+            o[c + 2 * bd] = __float2bfloat16_rn(p2 * (g2 - delta)); o[c + 3 * bd] = __float2bfloat16_rn(p3 * (g3 - delta));
+        }
+        for (; c < V; c += bd) o[c] = __float2bfloat16_rn(__bfloat162float(p[c]) * (g[c] - delta));
+        for (int64_t k = V + threadIdx.x; k < sstride; k += bd) o[k] = __float2bfloat16_rn(0.f);
+        __syncthreads();                                       // `red` is reused by the next row
+    }
+}
+
 }  // namespace tasu
 
 using namespace tasu;
+
+extern "C" int tasu_attn_score_grad(const void* P_bf16, int64_t p_stride, const float* dP, int64_t dp_stride,
+                                    const float* dZ, const float* Z, int64_t z_stride, int d, int64_t rows, int V,
+                                    void* dS_bf16, int64_t ds_stride, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && V > 0 && d > 0 && p_stride >= V && dp_stride >= V && ds_stride >= V && z_stride >= d, "shape");
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(P_bf16 && dP && dZ && Z && dS_bf16, "null pointer");
+    int64_t g = (int64_t)tasu::sm_count() * 8;
+    if (g > rows) g = rows;
+    attn_ds_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)P_bf16, p_stride, dP, dp_stride, dZ, Z,
+                                                                  z_stride, d, rows, V, (__nv_bfloat16*)dS_bf16, ds_stride);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
 
 extern "C" int tasu_transpose_cast(const void* src, int src_dtype, int64_t rows, int64_t cols, int64_t src_stride,
                                    const float* row_scale, void* dst_bf16, int64_t dst_stride, void* stream) {

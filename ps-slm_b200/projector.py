@@ -9,7 +9,7 @@ DeepSpeed/AdamW own ordinary ``nn.Parameter``s:
 * ``EncoderProjectorLinearSiLU`` ("linear-silu", default) ← projector.py:129-151
 * ``EncoderProjectorConcat``     ("linear")              ← projector.py:29-50
 * ``EncoderProjectorLinear``     ("simple_linear")       ← projector.py:10-26
-* ``EncoderProjectorCTCCA``      ("cross-attention")     ← projector.py:104-126 (inference)
+* ``EncoderProjectorCTCCA``      ("cross-attention")     ← projector.py:104-126
 
 The Linear layers run as bf16 tcgen05 GEMMs with fp32 accumulation (libtasu_bridge.so); the
 LayerNorm of the default projector is folded into GEMM-1's epilogue.  There is no PyTorch
@@ -203,6 +203,75 @@ class EncoderProjectorLinear(nn.Module):
         return y.view(B, T, ld)[:, :, :self.llm_vocab]
 
 
+def _attention_heads(Q, table, N, V2, h, dp, P):
+    """Per-head softmax attention of Q over the table (keys = values): yields (head, q_h, k_h, stats) after writing the
+    head's probabilities into ``P``."""
+    zero_bias = torch.zeros(V2, dtype=torch.float32, device=Q.device)
+    for i in range(h):
+        qh, kh = Q[:, i * dp:(i + 1) * dp], table[:, i * dp:(i + 1) * dp]
+        st = ops.ctc_head_stats(qh, kh, None, 1, N, 0, V2, dp, 0)
+        inv = torch.reciprocal(st.row_sumexp)
+        ops.gemm_bf16_tn(qh, kh, N, V2, dp, P, L.EPI_SOFTMAX, zero_bias, inv, st.row_max)
+        yield i, qh, kh
+
+
+class _CrossAttnFunction(torch.autograd.Function):
+    """Z = concat_h softmax(Q_h·K_hᵀ)·K_h with Q = x·(W_q/√d)ᵀ; gradient to W_q only (the posterior input and the
+    detached LLM table — ps-slm.py:476-478 — need none).  Backward per head: recompute P, dP = dZ_h·K_hᵀ,
+    dS = P∘(dP − dZ_h·Z_h) (tasu_attn_score_grad), dQ_h = dS·K_h; then dW_q = d^-½ · dQᵀ·x (operands read in place)."""
+
+    @staticmethod
+    def forward(ctx, wq_param, xb, wq_bf16, table, N, V1, V2, h, d, dp):
+        D = h * d
+        dev = xb.device
+        Qr = torch.empty(N, ops.pad_to(D, 8), dtype=torch.bfloat16, device=dev)
+        ops.gemm_bf16_tn(xb, wq_bf16, N, D, V1, Qr)
+        Q = Qr[:, :D]
+        if dp != d:                                    # zero-pad every head to 16-byte aligned slices (see forward())
+            Qp = torch.zeros(N, h, dp, dtype=torch.bfloat16, device=dev)
+            Qp[:, :, :d] = Q.reshape(N, h, d)
+            Q = Qp.view(N, h * dp)
+        Z = torch.empty(N, h * dp, dtype=torch.float32, device=dev)
+        P = torch.empty(N, ops.pad_to(V2), dtype=torch.bfloat16, device=dev)      # one head's probabilities at a time
+        for i, qh, kh in _attention_heads(Q, table, N, V2, h, dp, P):
+            ops.gemm_bf16_f32(P, False, kh, True, N, dp, V2, Z[:, i * dp:(i + 1) * dp])
+        ctx.save_for_backward(xb, Q, Z, table)
+        ctx.dims = (N, V1, V2, h, d, dp)
+        return Z if dp == d else Z.view(N, h, dp)[:, :, :d].reshape(N, D)
+
+    @staticmethod
+    def backward(ctx, dZ):
+        xb, Q, Z, table = ctx.saved_tensors
+        N, V1, V2, h, d, dp = ctx.dims
+        D = h * d
+        dev = dZ.device
+        dZ = dZ.float().contiguous()
+        if dp != d:
+            dZp = torch.zeros(N, h, dp, dtype=torch.float32, device=dev)
+            dZp[:, :, :d] = dZ.view(N, h, d)
+            dZ = dZp.view(N, h * dp)
+        dZb, _, _ = ops.cast_rows(dZ, torch.bfloat16)
+        ldv = ops.pad_to(V2)
+        P = torch.empty(N, ldv, dtype=torch.bfloat16, device=dev)
+        dS = torch.empty(N, ldv, dtype=torch.bfloat16, device=dev)
+        dP = torch.empty(N, ops.pad_to(V2, 4), dtype=torch.float32, device=dev)
+        dQ = torch.empty(N, h * dp, dtype=torch.float32, device=dev)
+        for i, qh, kh in _attention_heads(Q, table, N, V2, h, dp, P):
+            sl = slice(i * dp, (i + 1) * dp)
+            ops.gemm_bf16_tn(dZb[:, sl], kh, N, V2, dp, dP)                      # dP = dZ_h · K_hᵀ
+            L.check(L.lib().tasu_attn_score_grad(P.data_ptr(), ldv, dP.data_ptr(), dP.stride(0), dZ[:, sl].data_ptr(),
+                                                 Z[:, sl].data_ptr(), h * dp, dp, N, V2, dS.data_ptr(), ldv,
+                                                 ops._stream()), "tasu_attn_score_grad")
+            ops._count(1)
+            ops.gemm_bf16_f32(dS, False, kh, True, N, dp, V2, dQ[:, sl])         # dQ_h = dS · K_h
+        if dp != d:
+            dQ = dQ.view(N, h, dp)[:, :, :d].reshape(N, D).contiguous()
+        dQb, _, _ = ops.cast_rows(dQ, torch.bfloat16, ops.pad_to(D, 8))
+        dwq = torch.empty(D, ops.pad_to(V1, 4), dtype=torch.float32, device=dev)
+        ops.gemm_bf16_f32(dQb[:, :D], True, xb[:, :V1], True, D, V1, N, dwq[:, :V1])   # dQᵀ · x, both operands MN-major
+        return (dwq[:, :V1] * (d ** -0.5), None, None, None, None, None, None, None, None, None)
+
+
 class EncoderProjectorCTCCA(nn.Module):
     """Cross-attention projector — projector.py:104-126 ("cross-attention", called as
     ``encoder_projector(posterior, llm_embedding)``, ps-slm.py:475-480): ``Q = W_q·post``; 8-head softmax attention of Q
@@ -214,7 +283,7 @@ class EncoderProjectorCTCCA(nn.Module):
       2. per head: row max / sum-exp of ``Q_h·K_hᵀ`` from the stats epilogue    — ``tasu_ctc_head_stats`` (no scores in HBM)
       3. per head: probabilities ``P_h`` (bf16, ``[rows, V2]``, one reused buffer) — ``tasu_gemm_bf16_tn(EPI_SOFTMAX)``
       4. per head: ``Z_h = P_h·V_h`` with the table slice read in place (MN-major B operand) — ``tasu_gemm_bf16_f32``
-    Inference only: the attention backward is not implemented (a training call raises)."""
+    Trainable: ``W_q`` receives its gradient through ``_CrossAttnFunction`` (probabilities recomputed per head)."""
 
     def __init__(self, config, n_heads=8):
         super().__init__()
@@ -224,12 +293,12 @@ class EncoderProjectorCTCCA(nn.Module):
         self._tcache = ProjectorCache()
 
     def forward(self, post, llm_embed):
-        if torch.is_grad_enabled() and (post.requires_grad or self.W_q.weight.requires_grad):
-            raise NotImplementedError("the cross-attention projector of the B200 bridge is inference-only "
-                                      "(call under torch.no_grad(); its backward is a 'next' row, DESIGN.md §6)")
+        if post.requires_grad:
+            raise NotImplementedError("the bridge projector does not propagate a gradient to its (posterior) input")
         B, T, V1 = post.shape
         N, D, h = B * T, self.W_q.weight.shape[0], self.n_heads
         d = D // h
+        dp = ops.pad_to(d, 8)
         V2 = llm_embed.shape[0]
         dev = post.device
         out_dtype = post.dtype if post.dtype in (torch.float32, torch.bfloat16) else torch.float32
@@ -242,35 +311,32 @@ class EncoderProjectorCTCCA(nn.Module):
         wq = self._cache.get([self.W_q.weight], build_w)
 
         def build_t():
-            t = llm_embed.detach()
-            return t.contiguous() if t.dtype == torch.bfloat16 else ops.cast_rows(t.contiguous(), torch.bfloat16)[0]
+            with torch.no_grad():
+                t = llm_embed.detach()
+                t = t.contiguous() if t.dtype == torch.bfloat16 else ops.cast_rows(t.contiguous(), torch.bfloat16)[0]
+                if dp != d:
+                    # head slices must start on 16-byte boundaries for TMA: zero-pad every head to a multiple of 8
+                    # columns (zero columns change neither scores nor outputs); Qwen2.5-1.5B (d = 192) never pads
+                    tp = torch.zeros(V2, h, dp, dtype=torch.bfloat16, device=dev)
+                    tp[:, :, :d] = t.reshape(V2, h, d)
+                    t = tp.view(V2, h * dp)
+                return t
         table = self._tcache.get([llm_embed], build_t)
-        xb, _, _ = _rows_bf16(post.reshape(N, V1), False)
-        Q = torch.empty(N, ops.pad_to(D, 8), dtype=torch.bfloat16, device=dev)
-        ops.gemm_bf16_tn(xb, wq, N, D, V1, Q)
-        Q = Q[:, :D]
-        dp = d
-        if d % 8 != 0:
-            # head slices must start on 16-byte boundaries for TMA: zero-pad every head to a multiple of 8 columns
-            # (zero columns change neither the scores nor the outputs); Qwen2.5-1.5B (d = 192) never takes this branch
-            dp = ops.pad_to(d, 8)
-            Qp = torch.zeros(N, h, dp, dtype=torch.bfloat16, device=dev)
-            Qp[:, :, :d] = Q.reshape(N, h, d)
-            Tp = torch.zeros(V2, h, dp, dtype=torch.bfloat16, device=dev)
-            Tp[:, :, :d] = table.reshape(V2, h, d)
-            Q, table = Qp.view(N, h * dp), Tp.view(V2, h * dp)
-        Z = torch.empty(N, h * dp, dtype=torch.float32, device=dev)
-        P = torch.empty(N, ops.pad_to(V2), dtype=torch.bfloat16, device=dev)      # one head's probabilities at a time
-        zero_bias = torch.zeros(V2, dtype=torch.float32, device=dev)
-        for i in range(h):
-            qh, kh = Q[:, i * dp:(i + 1) * dp], table[:, i * dp:(i + 1) * dp]
-            st = ops.ctc_head_stats(qh, kh, None, 1, N, 0, V2, dp, 0)
-            inv = torch.reciprocal(st.row_sumexp)
-            ops.gemm_bf16_tn(qh, kh, N, V2, dp, P, L.EPI_SOFTMAX, zero_bias, inv, st.row_max)
-            ops.gemm_bf16_f32(P, False, kh, True, N, dp, V2, Z[:, i * dp:(i + 1) * dp])
-        if dp != d:
-            Z = Z.view(N, h, dp)[:, :, :d].reshape(N, D)
+        xb, _, _ = _rows_bf16(post.detach().reshape(N, V1), False)
+        train = torch.is_grad_enabled() and self.W_q.weight.requires_grad
+        if train:
+            Z = _CrossAttnFunction.apply(self.W_q.weight, xb, wq, table, N, V1, V2, h, d, dp)
+        else:
+            with torch.no_grad():
+                Z = _CrossAttnFunction.forward(_NoCtx(), None, xb, wq, table, N, V1, V2, h, d, dp)
         return Z.view(B, T, D).to(out_dtype)
+
+
+class _NoCtx:
+    """Stand-in for the autograd context on the inference path (nothing is saved)."""
+
+    def save_for_backward(self, *a):
+        pass
 
 
 PROJECTORS = {

@@ -288,5 +288,27 @@ def test_cross_attention_projector(dev, V1, D, V2, B, T):
         assert err < 1e-2, f"relative error {err}"
         out_bf = md(post.to(dev), table.to(dev).bfloat16())         # bf16 LLM embedding table
         assert ((out_bf.cpu() - ref).norm() / ref.norm()).item() < 2e-2
-    with pytest.raises(NotImplementedError):                        # training call: backward not implemented
-        md.train()(post.to(dev), table.to(dev))
+
+
+@pytest.mark.parametrize("V1,D,V2,B,T", [(300, 64, 1000, 2, 37), (61, 48, 200, 3, 20)])
+def test_cross_attention_projector_backward(dev, V1, D, V2, B, T):
+    """W_q gradient of the cross-attention projector (probabilities recomputed per head, dS = P∘(dP − dZ·Z)) vs torch
+    autograd through the fp32 oracle."""
+    import ps_slm_b200.projector as P
+    torch.manual_seed(V1 + D + 1)
+    m = P.EncoderProjectorCTCCA(types.SimpleNamespace(encoder_dim=V1, llm_dim=D, encoder_projector_ds_rate=1))
+    post = torch.softmax(torch.randn(B, T, V1) * 4, -1)
+    table = torch.randn(V2, D) * 0.5
+    gz = torch.randn(B, T, D)
+    wq = m.W_q.weight.detach().clone().requires_grad_(True)
+    ref = O.projector_ctcca(post, table, wq, m.n_heads)
+    (ref * gz).sum().backward()
+    md = m.to(dev).train()
+    out = md(post.to(dev), table.to(dev))
+    assert out.requires_grad
+    assert ((out.detach().cpu() - ref.detach()).norm() / ref.detach().norm()).item() < 1e-2
+    (out * gz.to(dev)).sum().backward()
+    g = md.W_q.weight.grad
+    assert g is not None and g.shape == wq.grad.shape
+    err = ((g.cpu() - wq.grad).norm() / wq.grad.norm()).item()
+    assert err < 3e-2, f"relative gradient error {err}"
