@@ -79,6 +79,87 @@ def psd_from_encoder(raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.
 LLM_BLANK_ID = 151643     # blank index of the LLM-vocabulary CTC head, hard-coded in the reference (ps-slm.py:491, :621)
 
 
+class _VocaTransFunction(torch.autograd.Function):
+    """out = softmax(pooled logits without the blank column) · E[:V_real], logits = CTC head over the LLM vocabulary
+    (``map``) applied to the k-concatenated encoder frames, PSD mean-pooling of the LOGITS in between.  Gradient to the
+    head only:  dProbs = dOut·Eᵀ,  dS = P∘(dProbs − dOut·Out) (tasu_attn_score_grad),  and — mean-pooling being linear —
+    dW = dSᵀ·x̄ with x̄ the SAME segmented mean of the input frames, db = Σ_rows dS; no un-pooling is needed."""
+
+    @staticmethod
+    def forward(ctx, w_map, b_map, projector, encoder_out, lens, table, do_psd, top1_emb, blank_id, threshold):
+        with torch.no_grad():
+            logits = projector(encoder_out)                                    # [B, T', Vp] (view of a padded buffer)
+        B, Tp, Vp = logits.shape
+        dev = logits.device
+        H = table.shape[1]
+        k = projector.k
+        feat_len = lens.to(device=dev, dtype=torch.int64) // k
+        x = encoder_out
+        if x.shape[1] % k:
+            x = x[:, :x.shape[1] - x.shape[1] % k]
+        xk = x.contiguous().view(B, Tp, -1)                                    # the k-concat the head saw (projector.py:19-24)
+        xk = xk if xk.dtype in (torch.float32, torch.bfloat16) else xk.float()
+        if do_psd:
+            st = ops.frame_stats(logits, L.INPUT_LOGITS, blank_id, feat_len)
+            plan = ops.collapse_plan(st, feat_len, blank_id, threshold)
+            max_len = int(plan.header.cpu()[L.CH_MAX_LEN])
+            if max_len == 0:
+                ctx.empty = True
+                ctx.shapes = (w_map.shape, b_map.shape)
+                return torch.zeros(B, 0, H, dtype=torch.float32, device=dev), torch.zeros(B, dtype=torch.long, device=dev)
+            pitch = ops.pad_to(Vp, 4)
+            rows = torch.empty(B * max_len, pitch, dtype=logits.dtype, device=dev)
+            ops.segment_meanpool(logits, plan, 1, max_len, B * max_len, rows, pitch)      # mean of the LOGITS (ps-slm.py:286)
+            xbar = torch.empty(B * max_len, xk.shape[2], dtype=xk.dtype, device=dev)
+            ops.segment_meanpool(xk, plan, 1, max_len, B * max_len, xbar, xk.shape[2])    # same segments, input side
+            new_lens, V_real = plan.new_lens, Vp - 1                                      # :493 drops the blank column
+        else:
+            rows = logits.reshape(B * Tp, Vp) if logits.is_contiguous() else logits.contiguous().view(B * Tp, Vp)
+            xbar = xk.reshape(B * Tp, -1)
+            new_lens, max_len, V_real = feat_len, Tp, Vp                                  # :509-511 keeps every column
+        N = rows.shape[0]
+        st2 = ops.frame_stats(rows.unsqueeze(0)[:, :, :V_real], L.INPUT_LOGITS, 0)
+        ctx.empty = False
+        if top1_emb:                                                                      # :498-502, :512-516 (no gradient)
+            out = ops.gather_rows(table, st2.argmax)
+            ctx.top1 = True
+            ctx.shapes = (w_map.shape, b_map.shape)
+        else:
+            probs = ops.softmax_rows(rows, V_real, st2)
+            out = torch.empty(N, H, dtype=torch.float32, device=dev)
+            ops.gemm_bf16_f32(probs, False, table[:V_real], True, N, H, V_real, out)
+            ctx.top1 = False
+            ctx.save_for_backward(probs, out, xbar, table)
+            ctx.dims = (N, H, V_real, Vp, xbar.shape[1])
+        ctx.mark_non_differentiable(new_lens)
+        return out.view(B, max_len, H), new_lens
+
+    @staticmethod
+    def backward(ctx, dout, _):
+        if ctx.empty or ctx.top1:
+            ws, bs = ctx.shapes
+            return (torch.zeros(ws, device=dout.device), torch.zeros(bs, device=dout.device)) + (None,) * 8
+        probs, out, xbar, table = ctx.saved_tensors
+        N, H, V_real, Vp, Dk = ctx.dims
+        dev = dout.device
+        do = dout.reshape(N, H).float().contiguous()
+        dob, _, _ = ops.cast_rows(do, torch.bfloat16, ops.pad_to(H, 8))
+        dP = torch.empty(N, ops.pad_to(V_real, 4), dtype=torch.float32, device=dev)
+        ops.gemm_bf16_tn(dob, table, N, V_real, H, dP)                                    # dProbs = dOut · Eᵀ
+        ldv = probs.stride(0)
+        dS = torch.empty(N, ldv, dtype=torch.bfloat16, device=dev)
+        L.check(L.lib().tasu_attn_score_grad(probs.data_ptr(), ldv, dP.data_ptr(), dP.stride(0), do.data_ptr(),
+                                             out.data_ptr(), H, H, N, V_real, dS.data_ptr(), ldv, ops._stream()),
+                "tasu_attn_score_grad")
+        ops._count(1)
+        xb, _, _ = ops.cast_rows(xbar if xbar.dim() == 2 else xbar.reshape(N, Dk), torch.bfloat16, ops.pad_to(Dk, 8))
+        dw = torch.zeros(Vp, ops.pad_to(Dk, 4), dtype=torch.float32, device=dev)          # blank row (do_psd) stays zero
+        ops.gemm_bf16_f32(dS[:, :V_real], True, xb[:, :Dk], True, V_real, Dk, N, dw[:V_real, :Dk])   # dW = dSᵀ · x̄
+        db = torch.zeros(Vp, dtype=torch.float32, device=dev)
+        db[:V_real] = ops.colsum(dS[:, :V_real])
+        return (dw[:, :Dk], db) + (None,) * 8
+
+
 def voca_trans_project(projector, encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, embed_table_bf16: torch.Tensor,
                        do_psd: bool, top1_emb: bool, blank_id: int = LLM_BLANK_ID, blank_threshold: float = BLANK_THRESHOLD):
     """Vocabulary-transfer branch (``voca_trans=True``; ps-slm.py:485-513 / :615-643) with the input the branch evidently
@@ -90,37 +171,13 @@ def voca_trans_project(projector, encoder_out: torch.Tensor, encoder_out_lens: t
       softmax over the remaining columns · embed_matrix[:V_real]   (or the embedding row of the top-1 id, ``top1_emb``)
 
     No ``[B, T, V]`` softmax tensor is materialised: greedy statistics come from ``tasu_frame_stats`` on the logits,
-    the contraction reads the embedding table in place (MN-major B operand of ``tasu_gemm_bf16_f32``).
+    the contraction reads the embedding table in place (MN-major B operand of ``tasu_gemm_bf16_f32``).  Trainable: the
+    head (``map.weight`` / ``map.bias``) receives its gradient through ``_VocaTransFunction``.
     Returns ``(projector_outs [B, T_new, H] fp32 | table dtype for top1, lengths [B] int64)``."""
-    if torch.is_grad_enabled() and any(p.requires_grad for p in projector.parameters()):
-        raise NotImplementedError("the voca_trans branch of the B200 bridge is inference-only")
-    logits = projector(encoder_out)                                        # [B, T', Vp] (a view of a 16-byte-pitched buffer)
-    B, Tp, Vp = logits.shape
-    dev = logits.device
-    H = embed_table_bf16.shape[1]
-    feat_len = encoder_out_lens.to(device=dev, dtype=torch.int64) // projector.k
-    if do_psd:
-        st = ops.frame_stats(logits, L.INPUT_LOGITS, blank_id, feat_len)
-        plan = ops.collapse_plan(st, feat_len, blank_id, blank_threshold)
-        max_len = int(plan.header.cpu()[L.CH_MAX_LEN])
-        if max_len == 0:
-            return torch.zeros(B, 0, H, dtype=torch.float32, device=dev), torch.zeros(B, dtype=torch.long, device=dev)
-        pitch = ops.pad_to(Vp, 4)
-        pooled = torch.empty(B * max_len, pitch, dtype=logits.dtype, device=dev)
-        ops.segment_meanpool(logits, plan, 1, max_len, B * max_len, pooled, pitch)       # mean of the LOGITS (ps-slm.py:286)
-        rows, new_lens, V_real = pooled, plan.new_lens, Vp - 1                            # :493 drops the blank column
-    else:
-        rows = logits.reshape(B * Tp, Vp) if logits.is_contiguous() else logits.contiguous().view(B * Tp, Vp)
-        new_lens, max_len, V_real = feat_len, Tp, Vp                                      # :509-511 keeps every column
-    N = rows.shape[0]
-    st2 = ops.frame_stats(rows.unsqueeze(0)[:, :, :V_real], L.INPUT_LOGITS, 0)
-    if top1_emb:                                                                          # :498-502, :512-516
-        out = ops.gather_rows(embed_table_bf16, st2.argmax)
-    else:
-        probs = ops.softmax_rows(rows, V_real, st2)
-        out = torch.empty(N, H, dtype=torch.float32, device=dev)
-        ops.gemm_bf16_f32(probs, False, embed_table_bf16[:V_real], True, N, H, V_real, out)
-    return out.view(B, max_len, H), new_lens
+    if encoder_out.requires_grad:
+        raise NotImplementedError("the bridge does not propagate a gradient to the encoder output")
+    return _VocaTransFunction.apply(projector.map.weight, projector.map.bias, projector, encoder_out, encoder_out_lens,
+                                    embed_table_bf16, bool(do_psd), bool(top1_emb), int(blank_id), float(blank_threshold))
 
 
 def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_tokens: torch.Tensor,

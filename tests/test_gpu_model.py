@@ -97,3 +97,40 @@ def test_voca_trans_project(dev, do_psd, top1):
         if n:
             err = ((out[b, :n].float().cpu() - ref[b, :n]).norm() / ref[b, :n].norm()).item()
             assert err < (2e-2 if not top1 else 1e-2), (b, err)
+
+
+@pytest.mark.parametrize("do_psd", [True, False])
+def test_voca_trans_backward(dev, do_psd):
+    """Gradient of the voca_trans branch to the CTC head (map.weight / map.bias) vs torch autograd through the oracle:
+    dProbs = dOut·Eᵀ, dS = P∘(dProbs − dOut·Out), dW = dSᵀ·x̄ with x̄ the same segmented mean of the input frames."""
+    import types
+
+    import ps_slm_b200.bridge as bridge
+    import ps_slm_b200.projector as P
+    from oracle import tasu_oracle as O
+    torch.manual_seed(11)
+    Denc, k, Vh, H, B, T = 24, 2, 301, 64, 3, 41
+    proj = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=Denc, llm_dim=Vh, encoder_projector_ds_rate=k))
+    with torch.no_grad():
+        proj.map.weight.mul_(14.0)
+        proj.map.bias.zero_()
+        proj.map.bias[Vh - 1] = 2.5
+    table = torch.randn(Vh + 7, H) * 0.3
+    x = torch.randn(B, T, Denc)
+    x[:, 1::3] = x[:, 0:-1:3][:, :x[:, 1::3].shape[1]]
+    lens = torch.tensor([T, 17, 30])
+    w = proj.map.weight.detach().clone().requires_grad_(True)
+    b = proj.map.bias.detach().clone().requires_grad_(True)
+    ref, ref_lens = O.voca_trans(x, lens, w, b, k, table, do_psd, False, blank_id=Vh - 1)
+    valid = (torch.arange(ref.shape[1])[None, :] < ref_lens[:, None]).float().unsqueeze(-1)   # padding rows carry no loss
+    gz = torch.randn_like(ref) * valid
+    (ref * gz).sum().backward()
+    md = proj.to(dev).train()
+    out, new_lens = bridge.voca_trans_project(md, x.to(dev), lens.to(dev), table.to(dev).bfloat16(), do_psd, False,
+                                              blank_id=Vh - 1)
+    assert out.requires_grad and torch.equal(new_lens.cpu(), ref_lens)
+    (out * gz.to(dev)).sum().backward()
+    for name, g, r in (("map.weight", md.map.weight.grad, w.grad), ("map.bias", md.map.bias.grad, b.grad)):
+        assert g is not None and g.shape == r.shape, name
+        err = ((g.cpu() - r).norm() / r.norm()).item()
+        assert err < 3e-2, f"{name}: relative gradient error {err}"
