@@ -70,6 +70,23 @@ rows_ca = out.shape[0] * out.shape[1]
 fl = rows_ca * (2.0 * V * S.H_LLM + 3 * 2.0 * S.V_LLM * S.H_LLM)          # W_q GEMM + stats pass, softmax pass, P·V
 rows.append((f"EncoderProjectorCTCCA (cross-attention over the 151936-row table) on padded [{out.shape[0]},{out.shape[1]},V]", ms,
              fl / ms / 1e9, "TFLOP/s", fl / ms / 1e9 / 1357.9))
+# voca_trans branch (ps-slm.py:485-516): simple_linear CTC head over the LLM vocabulary (k = 2), PSD on its logits,
+# softmax(no-blank) · embed_matrix — on the raw 512-d encoder frames of the same batch
+del ca
+torch.cuda.empty_cache()
+vcfg = types.SimpleNamespace(encoder_dim=S.D_ENC, llm_dim=151644, encoder_projector_ds_rate=2)
+head = P.EncoderProjectorLinear(vcfg).to(dev).eval()
+with torch.no_grad():
+    head.map.weight.mul_(8.0)
+    head.map.bias[151643] = 4.0
+enc = raw[:, 4:].to(dev)
+with torch.no_grad():
+    ms = timeit(lambda: bridge.voca_trans_project(head, enc, lens, table_bf, True, False), n=3, warm=1)
+    vo, vl = bridge.voca_trans_project(head, enc, lens, table_bf, True, False)
+n_v = B * (T // 2)
+fl = n_v * 2.0 * 1024 * 151644 + int(vl.sum()) * 2.0 * 151643 * S.H_LLM
+rows.append((f"voca_trans branch: CTC head over 151644 classes on {n_v} concat frames + PSD + softmax·E ({int(vl.sum())} rows kept)", ms,
+             fl / ms / 1e9, "TFLOP/s", fl / ms / 1e9 / 1357.9))
 print("| op (B=64, T=500) | ms | achieved | unit | frac of measured peak |\n|---|---:|---:|---|---:|")
 for r in rows:
     print(f"| {r[0]} | {r[1]:.3f} | {r[2]:.0f} | {r[3]} | {r[4]:.2f} |")
