@@ -59,6 +59,14 @@ enum { TASU_CH_N_OUT = 0,         /* total compressed rows  sum_b M_b */
 
 int tasu_abi_version(void);
 const char* tasu_last_error(void);
+/* Run-time options.  Every option defaults to 0 (= the validated path) unless the environment variable of the same
+ * purpose is set when the library is first used.
+ *   TASU_OPT_GEMM_PAIR (env TASU_GEMM_PAIR): EXPERIMENTAL — tasu_gemm_bf16_tn runs deep-K shapes (K > 1024, M > 128) as
+ *   CTA pairs: clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of
+ *   the B tile.  Same contract and results as the default kernel (the accumulation order inside a tile is unchanged). */
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
+int tasu_set_option(int option, int value);
+int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */
 int tasu_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 

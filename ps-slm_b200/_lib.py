@@ -18,6 +18,7 @@ INPUT_PROBS, INPUT_LOGITS = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, EPI_SOFTMAX = 0, 1, 2, 3, 4, 5, 6
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
+OPT_GEMM_PAIR, OPT_COUNT = 0, 1          # run-time options (tasu_set_option); 0 = the validated default path
 
 # name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
@@ -25,6 +26,8 @@ SIGNATURES = {
     "tasu_abi_version": (_I, []),
     "tasu_last_error": (c_char_p, []),
     "tasu_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "tasu_set_option": (_I, [_I, _I]),
+    "tasu_get_option": (_I, [_I]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),

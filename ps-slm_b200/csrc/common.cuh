@@ -36,6 +36,7 @@ void set_error(const char* fmt, ...);
 #define TASU_CHECK_LAUNCH() TASU_CHECK_CUDA(cudaGetLastError())
 
 int sm_count();
+int option(int id);          // tasu_set_option / tasu_get_option values (core.cu)
 
 // grid of a persistent (grid-stride) kernel: SMs x CTAs that are actually resident for this kernel, capped by the
 // number of work items — a larger grid only adds a ragged second wave

@@ -1,7 +1,10 @@
 // Error reporting and device queries of libtasu_bridge.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 
 namespace tasu {
 
@@ -26,7 +29,39 @@ int sm_count() {
     return cached[dev];
 }
 
+// run-time options (tasu_set_option); the initial value of option X comes from the environment variable named below
+static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR"};
+static std::atomic<int> g_options[TASU_OPT_COUNT];
+static std::once_flag g_options_once;
+
+static void init_options() {
+    std::call_once(g_options_once, [] {
+        for (int i = 0; i < TASU_OPT_COUNT; ++i) {
+            const char* e = getenv(kOptionEnv[i]);
+            g_options[i].store(e != nullptr ? atoi(e) : 0);
+        }
+    });
+}
+
+int option(int id) {
+    if (id < 0 || id >= TASU_OPT_COUNT) return 0;
+    init_options();
+    return g_options[id].load(std::memory_order_relaxed);
+}
+
 }  // namespace tasu
+
+extern "C" int tasu_set_option(int option, int value) {
+    TASU_CHECK_ARG(option >= 0 && option < TASU_OPT_COUNT, "unknown option");
+    tasu::init_options();
+    tasu::g_options[option].store(value);
+    return TASU_OK;
+}
+
+extern "C" int tasu_get_option(int option) {
+    TASU_CHECK_ARG(option >= 0 && option < TASU_OPT_COUNT, "unknown option");
+    return tasu::option(option);
+}
 
 extern "C" int tasu_abi_version(void) { return TASU_ABI_VERSION; }
 

@@ -17,169 +17,31 @@
 //   * warps 4-7 = epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / SiLU / ReLU /
 //     LayerNorm-fold math in registers, swizzled st.shared into a 128-byte-wide staging tile,
 //     TMA store (clips the ragged edges) double-buffered against the next chunk.
-#include "common.cuh"
-#include <cuda.h>
-#include <mutex>
+#include "gemm_common.cuh"
 
 namespace tasu {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64;          // bf16: BK*2 = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
-constexpr int kAccStages = 2;
-constexpr int kTmemCols = 512;
-constexpr int kThreads = 256;                        // warps 0-3 control, warps 4-7 epilogue
-constexpr int kEpiThreads = 128;
-constexpr int kABytes = BM * BK * 2;                 // 16 KB
-constexpr int kBBytes = BN * BK * 2;                 // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
-constexpr int kStagingBytes = BM * 128;              // one 128-byte-wide column chunk of the C tile
-constexpr int kAuxBytes = 2 * BN * 4;                // per-tile bias / colsum slices
-constexpr int gemm_smem_bytes(int stages, int groups) {
-    return stages * kStageBytes + 2 * groups * kStagingBytes + groups * kAuxBytes + 128 /*barriers*/;
-}
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
-}
-template <int N> __device__ __forceinline__ void tma_store_wait_all() {
-    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 UMMA format):
-// bits [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024 B
-// between 8-row groups, [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// MN-major (the operand is stored [K, MN] with MN contiguous), 128-byte swizzle: the canonical layout in 16-byte units is
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) — an atom is 8 K-rows x 128 B (64 MN elements); one TMA box [64 K-rows][64 MN] stacks
-// 8 atoms along K (SBO = 1024 B) and consecutive boxes (the next 64 MN elements) are 8192 B apart (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
-    d |= (uint64_t)(8192u >> 4) << 16;
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major (bit 15 / 16 = A / B MN-major),
-// N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-// the registers are passed as in/out operands so the compiler cannot schedule their consumers above the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :: "memory");
-}
-__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
-constexpr float kLog2e = 1.4426950408889634f;
-__device__ __forceinline__ float ex2_approx(float x) {          // MUFU.EX2, 2 ulp, flushes denormal results to zero
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-struct Params {
-    int M, N, K;              // M = rows the tensor maps cover; the live row count may come from m_dev
-    const int32_t* m_dev;     // optional device-side row count (data-dependent M without a host sync)
-    int epilogue;
-    const float* bias;
-    const float* row_rstd;
-    const float* row_mean;
-    const float* colsum;
-};
 
 // kOutBf16: C is bf16 (64 columns per 128-byte staging row) else fp32 (32 columns)
 // kSt smem pipeline stages; kGroups epilogue warp-groups of 4 warps (2 groups interleave the 128-byte column
 // chunks of a tile, each with its own staging pair and TMA-store thread: for shallow-K, store-heavy shapes)
 // kMajor: bit 0 = A is MN-major ([K, M] in memory), bit 1 = B is MN-major ([K, N] in memory); 0 = both K-major ("TN")
-template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0>
+// kPair: CTA-pair mode (launched as clusters of 2): one tcgen05.mma.cta_group::2 of M = 256 per 256x256 pair tile;
+//        each CTA stages its own 128 rows of A and 128 of the 256 B rows (32 KB per stage instead of 48 KB, a third
+//        less L2->smem traffic per flop), the rank-0 CTA issues the MMAs and multicasts its commits to both CTAs,
+//        every CTA runs the epilogue of its own 128 accumulator rows.  EXPERIMENTAL: see tasu_set_option.
+template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false>
 __global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];          // 128B-swizzle atoms need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();               // no static shared memory in this kernel → offset 0
+    static_assert(!kPair || (kMajor == 0 && kGroups == 1), "pair mode: K-major operands, one epilogue group");
     constexpr int kStages = kSt;
-    uint8_t* staging = smem + kStages * kStageBytes;                               // [kGroups][2] x 16 KB
+    constexpr int kStgBytes = kPair ? kPairStageBytes : kStageBytes;               // A 16 KB + B 32 KB (pair: 16 KB)
+    constexpr int kTileM = kPair ? 2 * BM : BM;                                    // rows of C per work item
+    uint8_t* staging = smem + kStages * kStgBytes;                                 // [kGroups][2] x 16 KB
     float* s_aux = reinterpret_cast<float*>(staging + 2 * kGroups * kStagingBytes);  // [kGroups][bias, colsum][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kGroups * kStagingBytes + kGroups * kAuxBytes);
     uint64_t* full_bar = bars;                           // [kStages]
@@ -190,25 +52,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M_live = p.m_dev != nullptr ? min(max(__ldg(p.m_dev), 0), p.M) : p.M;
-    const int m_tiles = (M_live + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (M_live + kTileM - 1) / kTileM, n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (p.K + BK - 1) / BK;
+    // work distribution: one CTA (pair mode: one cluster of two CTAs) per tile, static round-robin
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+#define TASU_TILE_LOOP for (int tile = kPair ? (blockIdx.x >> 1) : blockIdx.x; tile < num_tiles; tile += kPair ? (gridDim.x >> 1) : gridDim.x)
+#define TASU_TILE_M0 ((tile / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0))
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_c);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * kGroups); }
+        // pair mode: the epilogue threads of BOTH CTAs release an accumulator on the MMA-issuing CTA's barrier
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * kGroups * (kPair ? 2 : 1)); }
         fence_barrier_init();
     }
     if (warp == 2) {   // whole warp allocates all 512 TMEM columns (1 CTA per SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {   // one warp of each CTA of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();     // the peer's barriers are initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -216,11 +90,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            TASU_TILE_LOOP {
+                const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sa = smem + stage * kStgBytes;
+                    if (kPair) {
+                        // both CTAs' halves of the stage complete on the rank-0 barrier the MMA thread waits on; the
+                        // peer's bytes may land before rank 0 posts its expect_tx (the pending arrival keeps the phase open)
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        tma_load_2d_pair(&tmap_a, fb, sa, kb * BK, m0);
+                        tma_load_2d_pair(&tmap_b, fb, sa + kABytes, kb * BK, n0 + (int)rank * (BN / 2));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], kStageBytes);
                     if (kMajor & 1) {                               // [64 K-rows][64 M] boxes, 8 KB apart
 #pragma unroll
@@ -241,30 +125,38 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && (!kPair || rank == 0)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            constexpr uint32_t idesc = kInstrDesc | ((uint32_t)(kMajor & 1) << 15) | ((uint32_t)((kMajor >> 1) & 1) << 16);
+            constexpr uint32_t idesc = (kPair ? kInstrDescPair : kInstrDesc) | ((uint32_t)(kMajor & 1) << 15) | ((uint32_t)((kMajor >> 1) & 1) << 16);
             // per UMMA_K step: K-major advances 32 B inside the swizzle row (+2 in the >>4 address field); MN-major
             // advances two 8-row K groups = 2048 B (+128)
             constexpr uint64_t a_step = (kMajor & 1) ? 128 : 2, b_step = (kMajor & 2) ? 128 : 2;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+            TASU_TILE_LOOP {
+                if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);   // drained by both CTAs' epilogues
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * kStgBytes);
                     const uint64_t adesc = (kMajor & 1) ? make_smem_desc_mn(sa) : make_smem_desc(sa);
                     const uint64_t bdesc = (kMajor & 2) ? make_smem_desc_mn(sa + kABytes) : make_smem_desc(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc,
-                                  (kb > 0 || k > 0) ? 1u : 0u);
+                        if (kPair) umma_bf16_pair(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc,
+                                                  (kb > 0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (kPair) {                                    // the same barriers of both CTAs
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);             // smem stage reusable once these MMAs retire
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -286,8 +178,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int sw = et & 7;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        TASU_TILE_LOOP {
+            const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
             const int grow = m0 + et;
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
@@ -371,7 +263,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     fence_proxy_async_smem();
                     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(kEpiThreads) : "memory");
                     if (et == 0) {
-                        tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        // pair mode: the upper CTA's 128 rows may lie entirely beyond the last row
+                        if (!kPair || m0 < p.M) tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
                         tma_store_commit();
                     }
                     sbuf ^= 1;
@@ -393,7 +286,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 else {
                     // every tcgen05.ld of this thread for this accumulator has completed → hand it back early
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty[acc]);
+                    if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                    else mbar_arrive(&tmem_empty[acc]);
                 }
                 process(vb, sub_of(it + 1));
             }
@@ -404,10 +298,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();     // no CTA leaves (or frees TMEM) while its peer can still signal or read it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
     }
+#undef TASU_TILE_LOOP
+#undef TASU_TILE_M0
 }
 
 // ------------------------------------------------------------------ fused CTC head + softmax statistics
@@ -694,54 +592,6 @@ gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bf
     }
 }
 
-// ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    });
-    return fn;
-}
-
-// 2-D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols], 128B swizzle
-static int make_map(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esz, int64_t rows, int64_t cols,
-                    int64_t ld, int box_rows, int box_cols, CUtensorMapL2promotion promo) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TASU_ERR_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TASU_ERR_CUDA; }
-    return TASU_OK;
-}
-
-static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype, int64_t ldc,
-                        int M, int N, int K, int epilogue, const float* bias, const float* row_rstd,
-                        const float* row_mean, const float* colsum) {
-    TASU_CHECK_ARG(M >= 0 && N > 0 && K > 0, "M >= 0, N,K > 0");
-    TASU_CHECK_ARG(c_dtype == TASU_F32 || c_dtype == TASU_BF16, "c_dtype");
-    TASU_CHECK_ARG(epilogue >= TASU_EPI_NONE && epilogue <= TASU_EPI_SOFTMAX, "epilogue");
-    TASU_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
-    if (M == 0) return TASU_OK;
-    TASU_CHECK_ARG(A && B && C, "null pointer");
-    TASU_CHECK_ARG(epilogue == TASU_EPI_NONE || bias, "bias required");
-    TASU_CHECK_ARG((epilogue != TASU_EPI_LNFOLD_SILU && epilogue != TASU_EPI_LNFOLD) || (row_rstd && row_mean && colsum),
-                   "LN-fold vectors required");
-    TASU_CHECK_ARG(epilogue != TASU_EPI_SOFTMAX || (row_rstd && row_mean), "softmax row vectors required");
-    return TASU_OK;
-}
 
 
 template <bool kOutBf16, int kEpi, int kSt, int kGroups>
@@ -785,6 +635,45 @@ static int launch_dispatch(bool out_bf16, int epilogue, bool shallow_k, int grid
                            const CUtensorMap& mb, const CUtensorMap& mc, const Params& p) {
     return out_bf16 ? launch_epi<true>(epilogue, shallow_k, grid, st, ma, mb, mc, p)
                     : launch_epi<false>(epilogue, shallow_k, grid, st, ma, mb, mc, p);
+}
+
+// CTA-pair mode (EXPERIMENTAL, TASU_OPT_GEMM_PAIR): clusters of two CTAs, one 256x256 tile per cluster
+template <bool kOutBf16, int kEpi>
+static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+                           const CUtensorMap& mc, const Params& p) {
+    constexpr int smem = gemm_smem_bytes_pair(kPairStages);
+    static_assert(smem <= 227 * 1024, "pair-mode shared memory exceeds the 227 KB a CTA can opt into");
+    auto kern = gemm_bf16_tn_kernel<kOutBf16, kEpi, kPairStages, 1, 0, true>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    TASU_CHECK_CUDA(attr_err);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)clusters);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    return TASU_OK;
+}
+
+template <bool kOutBf16>
+static int launch_pair_epi(int epilogue, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+                           const CUtensorMap& mc, const Params& p) {
+    switch (epilogue) {
+        case TASU_EPI_NONE: return launch_pair_one<kOutBf16, TASU_EPI_NONE>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS: return launch_pair_one<kOutBf16, TASU_EPI_BIAS>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_SILU: return launch_pair_one<kOutBf16, TASU_EPI_BIAS_SILU>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_RELU: return launch_pair_one<kOutBf16, TASU_EPI_BIAS_RELU>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD_SILU: return launch_pair_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD: return launch_pair_one<kOutBf16, TASU_EPI_LNFOLD>(clusters, st, ma, mb, mc, p);
+        default: return launch_pair_one<kOutBf16, TASU_EPI_SOFTMAX>(clusters, st, ma, mb, mc, p);
+    }
 }
 
 template <int kSt, int kGroups, int kMajor>
@@ -853,15 +742,28 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     const int csz = c_dtype == TASU_F32 ? 4 : 2;
     TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
     TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
+    // EXPERIMENTAL CTA-pair mode (off unless TASU_OPT_GEMM_PAIR is set): deep-K shapes with at least one 256-row tile
+    const bool pair = option(TASU_OPT_GEMM_PAIR) != 0 && K > 1024 && M > BM && sm_count() >= 2;
     CUtensorMap ma, mb, mc;
     rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
-    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, pair ? BN / 2 : BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
     rc = make_map(&mc, C, c_dtype == TASU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, csz,
                   M, N, ldc, BM, c_dtype == TASU_F32 ? 32 : 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
     Params p{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
+    if (pair) {
+        const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+        int clusters = sm_count() / 2;
+        if (clusters > pair_tiles) clusters = pair_tiles;
+        cudaStream_t pst = (cudaStream_t)stream;
+        rc = c_dtype == TASU_BF16 ? launch_pair_epi<true>(epilogue, clusters, pst, ma, mb, mc, p)
+                                  : launch_pair_epi<false>(epilogue, clusters, pst, ma, mb, mc, p);
+        if (rc) return rc;
+        TASU_CHECK_LAUNCH();
+        return TASU_OK;
+    }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = sm_count();
     if (grid > tiles) grid = tiles;

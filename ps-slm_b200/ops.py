@@ -40,6 +40,18 @@ def _need_cuda(*ts):
             raise L.TasuError("tasu bridge ops need CUDA tensors (no CPU fallback exists)")
 
 
+def set_option(option: int, value: int) -> None:
+    """tasu_set_option: run-time switches of the library (``_lib.OPT_*``); 0 = the validated default path."""
+    L.check(L.lib().tasu_set_option(int(option), int(value)), "tasu_set_option")
+
+
+def get_option(option: int) -> int:
+    v = L.lib().tasu_get_option(int(option))
+    if v == -1 and not 0 <= int(option) < L.OPT_COUNT:
+        L.check(v, "tasu_get_option")
+    return v
+
+
 def pad_to(n: int, a: int = V_ALIGN) -> int:
     return (n + a - 1) // a * a
 

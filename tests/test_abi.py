@@ -103,3 +103,19 @@ def test_projector_state_dict_names():
     assert not hasattr(ca, "k")                       # like the reference: the cross-attention branch never reads .k
     s = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=512, llm_dim=151644, encoder_projector_ds_rate=1))
     assert set(s.state_dict()) == {"map.weight", "map.bias"} and tuple(s.map.weight.shape) == (151644, 512)
+
+
+def test_options_default_off_and_validated(lib):
+    """Run-time options: every experimental switch defaults to 0 (the validated path) and unknown ids are rejected."""
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    assert "TASU_GEMM_PAIR" not in os.environ
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 0
+    ops.set_option(L.OPT_GEMM_PAIR, 1)
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 1
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 0
+    assert lib.tasu_set_option(L.OPT_COUNT, 1) == -1 and b"unknown option" in lib.tasu_last_error()
+    assert lib.tasu_get_option(-3) == -1
+    with pytest.raises(L.TasuError):
+        ops.set_option(99, 1)

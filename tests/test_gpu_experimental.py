@@ -1,0 +1,152 @@
+"""GPU tests of code paths that are written but NOT yet validated on a B200 (the round's GPU budget ran out before
+they could be run).  They are skipped unless TASU_EXPERIMENTAL=1, so the default `pytest -m gpu` run only exercises the
+validated path; `tools/gpu_experimental.sh` runs them under a timeout.
+
+  * CTA-pair GEMM (tasu_set_option(TASU_OPT_GEMM_PAIR, 1)): tcgen05.mma.cta_group::2, M = 256 per pair of CTAs.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TASU_EXPERIMENTAL") != "1", reason="experimental paths: set TASU_EXPERIMENTAL=1")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture()
+def pair_mode():
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    ops.set_option(L.OPT_GEMM_PAIR, 1)
+    yield
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+
+
+def _ref(A, B, epi, bias, rstd, mean, colsum):
+    acc = A.float().double() @ B.float().double().T
+    if epi in (4, 5):
+        z = rstd.double()[:, None] * (acc - mean.double()[:, None] * colsum.double()[None, :]) + bias.double()[None, :]
+        return torch.nn.functional.silu(z) if epi == 4 else z
+    if epi == 6:
+        return torch.exp(acc + bias.double()[None, :] - mean.double()[:, None]) * rstd.double()[:, None]
+    if epi >= 1:
+        acc = acc + bias.double()[None, :]
+    if epi == 2:
+        acc = torch.nn.functional.silu(acc)
+    if epi == 3:
+        acc = torch.relu(acc)
+    return acc
+
+
+# deep-K shapes only (K > 1024, M > 128 select the pair kernel): ragged M / N / K, M below / above one pair tile, a tile
+# whose upper CTA is entirely out of range (M = 300: rows 256..299 live in the lower CTA of the second pair tile)
+PAIR_SHAPES = [(256, 256, 1088), (129, 8, 1032), (300, 260, 1100), (257, 1536, 2048), (1000, 2048, 25055), (8341, 2048, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (3, torch.bfloat16),
+                                           (4, torch.bfloat16), (5, torch.float32), (6, torch.bfloat16)])
+def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtype):
+    """The CTA-pair kernel accumulates every output element in the same order as the default kernel (one TMEM
+    accumulator, K blocks in ascending order), so the two must agree BIT FOR BIT; both are checked against fp64."""
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    if K > 20000 and epi not in (1, 4):
+        pytest.skip("large K: a subset of epilogues is enough")
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
+    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 0.6 * (K ** 0.5))     # softmax: a plausible row max
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    C = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 1
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C, epi, *vec)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+    C0 = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C0, epi, *vec)
+    torch.cuda.synchronize()
+    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    got = C.cpu()
+    pad = got[:, N:].float()
+    assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
+    scale = ref.abs().max().item() + 1e-6
+    tol = 1e-4 if out_dtype == torch.float32 else 6e-3
+    err = (got[:, :N].double() - ref).abs().max().item() / scale
+    assert err < tol, f"pair GEMM max error {err} (scaled) for {(M, N, K, epi)}"
+    assert torch.equal(C[:, :N], C0[:, :N]), "pair kernel and default kernel must agree bit for bit"
+
+
+def test_pair_gemm_device_side_row_count(dev, pair_mode):
+    """m_dev: live rows below the capacity M, including a live count that leaves whole pair tiles (and the upper CTA
+    of the last live one) without work."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(3)
+    M, N, K = 1024, 512, 2048
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    ref = A.float() @ B.float().T
+    for live in (0, 1, 128, 129, 300, 1024):
+        C = torch.full((M, N), -5.0, dtype=torch.float32, device=dev)
+        m_dev = torch.tensor([live], dtype=torch.int32, device=dev)
+        ops.gemm_bf16_tn(A, B, M, N, K, C, m_dev=m_dev)
+        torch.cuda.synchronize()
+        if live:
+            assert (C[:live] - ref[:live]).abs().max().item() / ref.abs().max().item() < 1e-4
+        tiles = (live + 255) // 256
+        assert bool((C[min(M, tiles * 256):] == -5.0).all()), "rows of pair tiles without live rows must stay untouched"
+
+
+def test_pair_gemm_back_to_back(dev, pair_mode):
+    """Pipeline state (mbarrier phases, TMEM accumulator ring) survives many tiles per CTA pair and repeated launches."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(5)
+    M, N, K = 8341, 2048, 2048           # 33 x 8 = 264 pair tiles on 74 pairs: 3.6 tiles per pair
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    C1 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    C2 = torch.empty_like(C1)
+    for _ in range(3):
+        ops.gemm_bf16_tn(A, B, M, N, K, C1)
+    ops.gemm_bf16_tn(A, B, M, N, K, C2)
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    ref = A.float() @ B.float().T
+    assert (C1 - ref).abs().max().item() / ref.abs().max().item() < 1e-4
+
+
+def test_bridge_with_pair_gemm_matches_default(dev, pair_mode):
+    """Whole inference bridge with the projector GEMMs in pair mode: integers and embeddings equal the default path."""
+    import types
+
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 8, 500
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=11, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=5, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    out_pair = [t.clone() for t in br(*args)]
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+    out_def = br(*args)
+    torch.cuda.synchronize()
+    for a, d in zip(out_pair, out_def):
+        assert torch.equal(a, d)

@@ -1,0 +1,14 @@
+#!/bin/bash
+# One GPU call for the paths that are written but not yet validated on a B200 (tests/test_gpu_experimental.py):
+# every test runs under its own timeout so that a hang in a new tcgen05 kernel cannot hold the box, and the pair-mode
+# GEMM is timed against the default kernel on the projector shapes.
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TASU_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 > gpurun_out/t_experimental.log 2>&1
+echo "experimental rc=$?" > gpurun_out/rc_experimental.txt
+tail -25 gpurun_out/t_experimental.log
+if grep -q "rc=0" gpurun_out/rc_experimental.txt; then
+    timeout 300 python tools/bench_pair_gemm.py > gpurun_out/pair_gemm.md 2>&1
+    cat gpurun_out/pair_gemm.md
+fi
+cat gpurun_out/rc_experimental.txt
