@@ -239,6 +239,24 @@ int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int
 int tasu_gemm_bf16_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                        float* C, int64_t ldc, int M, int N, int K, void* stream);
 
+/* EXPERIMENTAL (not yet validated on a GPU, not called by the bridge unless asked to): tasu_gemm_bf16_tn with a
+ * stream-K tail.  The full waves of 128x256 tiles run one tile per CTA as usual; the tiles of the ragged last wave are
+ * cut along K into contiguous pieces dealt out evenly to the CTAs, partial accumulators go through `workspace`
+ * (tasu_gemm_streamk_workspace() bytes, 256-byte aligned, ZERO-FILLED ONCE by the caller, then owned by the library; it
+ * must not be shared by launches that can run concurrently) and are added in a fixed order by the CTA that holds the
+ * tile's last K-block, which then runs the epilogue.  Same contract as tasu_gemm_bf16_tn otherwise; results are
+ * deterministic, but split tiles may differ from the unsplit kernel in the last fp32 bits.  Launched cooperatively.
+ * tasu_gemm_streamk_schedule_host: HOST — the pieces {tile, kb0, kb1, kind (0 full, 1 contributed, 2 finishing),
+ * n_contrib} CTA `cta` computes after its tiles of the full waves, in processing order; returns their number (0..2). */
+int64_t tasu_gemm_streamk_workspace(void);
+int tasu_gemm_bf16_tn_streamk(const void* A, int64_t lda, const void* B, int64_t ldb,
+                              void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
+                              const float* bias, const float* row_rstd, const float* row_mean,
+                              const float* colsum, const int32_t* m_dev, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+int tasu_gemm_streamk_schedule_host(int num_tiles, int k_blocks, int grid, int cta, int32_t* pieces_host,
+                                    int32_t* dp_tiles_host);
+
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
                            void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,

@@ -311,6 +311,54 @@ def gemm_bf16_tn(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out:
     return out
 
 
+_STREAMK_WS = {}
+
+
+def streamk_workspace(device) -> torch.Tensor:
+    """Per-device workspace of the EXPERIMENTAL stream-K GEMM (flags + one fp32 partial tile per SM), zero-filled once.
+    One workspace per device: launches that use it must be stream-ordered (the bridge has one compute stream)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _STREAMK_WS:
+        _STREAMK_WS[key] = torch.zeros(int(L.lib().tasu_gemm_streamk_workspace()), dtype=torch.uint8,
+                                       device=torch.device("cuda", key))
+    return _STREAMK_WS[key]
+
+
+def gemm_bf16_tn_streamk(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor,
+                         epilogue: int = L.EPI_NONE, bias: Optional[torch.Tensor] = None,
+                         row_rstd: Optional[torch.Tensor] = None, row_mean: Optional[torch.Tensor] = None,
+                         colsum: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None):
+    """EXPERIMENTAL (tasu_gemm_bf16_tn_streamk): ``gemm_bf16_tn`` with the ragged last wave of tiles cut along K."""
+    _need_cuda(A, Bw, out)
+    if A.dtype != torch.bfloat16 or Bw.dtype != torch.bfloat16:
+        raise TypeError("GEMM operands must be bfloat16")
+    ws = streamk_workspace(A.device)
+    lda = A.stride(0) if A.dim() == 2 and A.shape[0] > 1 else max(K, A.shape[-1])
+    ldb = Bw.stride(0) if Bw.shape[0] > 1 else max(K, Bw.shape[-1])
+    ldc = out.stride(0) if out.shape[0] > 1 else max(N, out.shape[-1])
+    L.check(L.lib().tasu_gemm_bf16_tn_streamk(A.data_ptr(), lda, Bw.data_ptr(), ldb, out.data_ptr(), _dt(out), ldc, M, N, K,
+                                              epilogue, _ptr(bias), _ptr(row_rstd), _ptr(row_mean), _ptr(colsum),
+                                              _ptr(m_dev), ws.data_ptr(), ws.numel(), _stream()),
+            "tasu_gemm_bf16_tn_streamk")
+    _count(1)
+    return out
+
+
+def streamk_schedule(num_tiles: int, k_blocks: int, grid: int):
+    """HOST: the stream-K schedule the kernel runs — ``(dp_tiles, [pieces of CTA 0, pieces of CTA 1, ...])`` with pieces
+    ``(tile, kb0, kb1, kind, n_contrib)`` in processing order (tasu_gemm_streamk_schedule_host)."""
+    import ctypes
+    buf = (ctypes.c_int32 * 10)()
+    dp = ctypes.c_int32(0)
+    out = []
+    for cta in range(grid):
+        n = L.lib().tasu_gemm_streamk_schedule_host(num_tiles, k_blocks, grid, cta, ctypes.addressof(buf), ctypes.addressof(dp))
+        if n < 0:
+            L.check(n, "tasu_gemm_streamk_schedule_host")
+        out.append([tuple(buf[5 * i:5 * i + 5]) for i in range(n)])
+    return dp.value, out
+
+
 def gemm_bf16_f32(A: torch.Tensor, a_mn_major: bool, Bw: torch.Tensor, b_mn_major: bool, M: int, N: int, K: int,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] fp32 = A · B with either operand K-major ([M|N, K]) or MN-major ([K, M|N]) in memory (tasu_gemm_bf16_f32)."""

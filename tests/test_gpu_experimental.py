@@ -3,6 +3,7 @@ they could be run).  They are skipped unless TASU_EXPERIMENTAL=1, so the default
 validated path; `tools/gpu_experimental.sh` runs them under a timeout.
 
   * CTA-pair GEMM (tasu_set_option(TASU_OPT_GEMM_PAIR, 1)): tcgen05.mma.cta_group::2, M = 256 per pair of CTAs.
+  * stream-K GEMM (tasu_gemm_bf16_tn_streamk): the ragged last wave of tiles cut along K, fix-up through a workspace.
 """
 import os
 
@@ -150,3 +151,80 @@ def test_bridge_with_pair_gemm_matches_default(dev, pair_mode):
     torch.cuda.synchronize()
     for a, d in zip(out_pair, out_def):
         assert torch.equal(a, d)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stream-K tail (tasu_gemm_bf16_tn_streamk)
+# ---------------------------------------------------------------------------------------------------------------
+# (M, N, K): 528 tiles = 3 waves + 84 cut tiles (the headline GEMM-1 shape with a shorter K); fewer tiles than CTAs
+# (every tile cut 4 ways); exact multiple of 148 tiles (no cut); one leftover tile; ragged M / N / K; tiny K (1 K-block)
+SK_SHAPES = [(8341, 2048, 4096), (300, 512, 2048), (128 * 37, 1024, 1088), (128 * 37 + 1, 1024, 1088), (1000, 2048, 25055),
+             (130, 260, 72), (257, 1536, 2048), (5, 40, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", SK_SHAPES)
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
+                                           (6, torch.bfloat16)])
+def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
+    import ps_slm_b200.ops as ops
+    if K > 20000 and epi not in (1, 4):
+        pytest.skip("large K: a subset of epilogues is enough")
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
+    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 0.6 * (K ** 0.5))
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    outs = []
+    for _ in range(3):                                   # the workspace flags must be handed back after every launch
+        C = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+        ops.gemm_bf16_tn_streamk(Ad, Bd, M, N, K, C, epi, *vec)
+        torch.cuda.synchronize()
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), "fixed summation order: deterministic"
+    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    got = outs[0].cpu()
+    pad = got[:, N:].float()
+    assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
+    scale = ref.abs().max().item() + 1e-6
+    tol = 1e-4 if out_dtype == torch.float32 else 6e-3
+    err = (got[:, :N].double() - ref).abs().max().item() / scale
+    assert err < tol, f"stream-K GEMM max error {err} (scaled) for {(M, N, K, epi)}"
+    assert int(ops.streamk_workspace(dev)[:4 * 148].view(torch.int32).abs().sum()) == 0, "flags are zero between launches"
+
+
+def test_streamk_gemm_device_side_row_count(dev):
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(3)
+    M, N, K = 4096, 2048, 2048
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    ref = A.float() @ B.float().T
+    for live in (0, 1, 128, 129, 2500, 4096):            # the schedule is computed in the kernel from the live row count
+        C = torch.full((M, N), -5.0, dtype=torch.float32, device=dev)
+        m_dev = torch.tensor([live], dtype=torch.int32, device=dev)
+        ops.gemm_bf16_tn_streamk(A, B, M, N, K, C, m_dev=m_dev)
+        torch.cuda.synchronize()
+        if live:
+            assert (C[:live] - ref[:live]).abs().max().item() / ref.abs().max().item() < 1e-4
+        tiles = (live + 127) // 128
+        assert bool((C[min(M, tiles * 128):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
+
+
+def test_streamk_matches_default_on_uncut_tiles(dev):
+    """The tiles of the full waves take exactly the default path: bit-equal to tasu_gemm_bf16_tn there."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(9)
+    M, N, K = 8341, 2048, 2048                           # 528 tiles: tiles 0..443 are whole, 444..527 are cut
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    C0 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    C1 = torch.empty_like(C0)
+    ops.gemm_bf16_tn(A, B, M, N, K, C0)
+    ops.gemm_bf16_tn_streamk(A, B, M, N, K, C1)
+    torch.cuda.synchronize()
+    whole_rows = (444 // 8) * 128                        # n fastest: tile = m_tile * 8 + n_tile
+    assert torch.equal(C0[:whole_rows], C1[:whole_rows])
+    assert (C0 - C1).abs().max().item() / C0.abs().max().item() < 1e-5

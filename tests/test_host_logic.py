@@ -79,3 +79,47 @@ def test_model_rejects_nothing_silently_on_cpu():
     with pytest.raises(L.TasuError):
         m._merge_input_ids_with_audio_features(torch.zeros(1, 2, 4), torch.tensor([2]), torch.zeros(1, 3, 4),
                                                torch.tensor([[1, 9, 2]]), torch.ones(1, 3, dtype=torch.bool), None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# EXPERIMENTAL stream-K GEMM: the schedule is plain integer logic shared by host and kernel — provable on the CPU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num_tiles,k_blocks,grid", [
+    (528, 392, 148),      # projector GEMM-1 of the headline batch: 3 full waves + 84 tiles cut along K
+    (444, 392, 148),      # exact multiple of the grid: no stream-K pieces at all
+    (445, 392, 148),      # one leftover tile: cut 4 ways
+    (591, 32, 148),       # 147 leftover tiles: every CTA gets almost a whole tile
+    (7, 17, 148), (1, 1, 148), (3, 2, 148), (149, 1, 148), (37, 5, 8), (0, 9, 148), (1000, 33, 7),
+])
+def test_streamk_schedule_covers_every_k_block_once(num_tiles, k_blocks, grid):
+    import ps_slm_b200.ops as ops
+    FULL, CONTRIB, FINISH = 0, 1, 2
+    dp_tiles, per_cta = ops.streamk_schedule(num_tiles, k_blocks, grid)
+    assert dp_tiles == (num_tiles // grid) * grid
+    cover = {}                       # tile -> list of (kb0, kb1, cta, kind, n_contrib)
+    for cta, pieces in enumerate(per_cta):
+        assert len(pieces) <= 2
+        kinds = [p[3] for p in pieces]
+        assert kinds.count(CONTRIB) <= 1, "one partial-accumulator slot per CTA"
+        if CONTRIB in kinds:
+            assert kinds[0] == CONTRIB, "a CTA contributes BEFORE it finishes (no wait chains)"
+        for tile, kb0, kb1, kind, n_contrib in pieces:
+            assert dp_tiles <= tile < num_tiles and 0 <= kb0 < kb1 <= k_blocks
+            assert kind == (FULL if (kb0 == 0 and kb1 == k_blocks) else FINISH if kb1 == k_blocks else CONTRIB)
+            cover.setdefault(tile, []).append((kb0, kb1, cta, kind, n_contrib))
+    assert sorted(cover) == list(range(dp_tiles, num_tiles)), "every tile of the ragged wave is scheduled"
+    for tile, ps in cover.items():
+        ps.sort()
+        assert ps[0][0] == 0 and ps[-1][1] == k_blocks
+        for a, b in zip(ps, ps[1:]):
+            assert a[1] == b[0], "pieces of a tile are contiguous and disjoint"
+        ctas = [p[2] for p in ps]
+        assert ctas == list(range(ctas[0], ctas[0] + len(ps))), "consecutive CTAs, ascending with K"
+        assert len(ps) <= 6
+        # exactly the last piece finishes (or the tile is whole) and it names the CTAs below it as its contributors
+        assert [p[3] for p in ps[:-1]] == [CONTRIB] * (len(ps) - 1)
+        assert ps[-1][3] == (FULL if len(ps) == 1 else FINISH)
+        assert ps[-1][4] == len(ps) - 1
+    # balance: no CTA gets more than one tile's worth of K-blocks in the tail
+    for pieces in per_cta:
+        assert sum(p[2] - p[1] for p in pieces) <= k_blocks

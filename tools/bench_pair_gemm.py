@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Default (one CTA per 128x256 tile) vs EXPERIMENTAL CTA-pair (cta_group::2, 256x256 per pair) tcgen05 GEMM on the
+"""Default (one CTA per 128x256 tile) vs EXPERIMENTAL CTA-pair (cta_group::2, 256x256 per pair) and stream-K tcgen05 GEMM on the
 deep-K shapes of the bridge: projector GEMM-1 (M = compressed rows, N = 2048, K = 25055, LN-fold + SiLU epilogue) and
 GEMM-2 (N = 1536, K = 2048, bias).  CUDA events, L2 flushed between launches by a 256 MB memset.  Markdown table."""
 import os
@@ -30,8 +30,8 @@ def time_ms(fn, n=20, warm=3):
     return ts[len(ts) // 2]
 
 
-print("| shape (M, N, K) | epilogue | default ms | TFLOP/s | pair ms | TFLOP/s | pair / default |")
-print("|---|---|---:|---:|---:|---:|---:|")
+print("| shape (M, N, K) | epilogue | default ms | TFLOP/s | pair ms | TFLOP/s | pair / default | stream-K ms | TFLOP/s | stream-K / default |")
+print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|")
 for (M, N, K, epi, name) in [(8341, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + SiLU"), (8341, 1536, 2048, L.EPI_BIAS, "bias"),
                              (16384, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + SiLU"), (8192, 8192, 8192, L.EPI_NONE, "none")]:
     torch.manual_seed(0)
@@ -44,5 +44,7 @@ for (M, N, K, epi, name) in [(8341, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + S
         ops.set_option(L.OPT_GEMM_PAIR, pair)
         res[pair] = time_ms(lambda: ops.gemm_bf16_tn(A, B, M, N, K, C, epi, bias, rstd, mean, colsum))
     ops.set_option(L.OPT_GEMM_PAIR, 0)
+    sk = time_ms(lambda: ops.gemm_bf16_tn_streamk(A, B, M, N, K, C, epi, bias, rstd, mean, colsum))
     fl = 2.0 * M * N * K
-    print(f"| {M}, {N}, {K} | {name} | {res[0]:.3f} | {fl / res[0] / 1e9:.0f} | {res[1]:.3f} | {fl / res[1] / 1e9:.0f} | {res[1] / res[0]:.3f} |")
+    print(f"| {M}, {N}, {K} | {name} | {res[0]:.3f} | {fl / res[0] / 1e9:.0f} | {res[1]:.3f} | {fl / res[1] / 1e9:.0f} | {res[1] / res[0]:.3f} "
+          f"| {sk:.3f} | {fl / sk / 1e9:.0f} | {sk / res[0]:.3f} |")
