@@ -12,6 +12,7 @@ Function names, argument meaning, return tuples and error behaviour mirror
 
 Everything here is tensor plumbing; the arithmetic lives in libtasu_bridge.so.
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -315,17 +316,21 @@ def _cap(n: int, q: int = 2048) -> int:
 def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Tensor, rstd: torch.Tensor,
                         w1g: torch.Tensor, colsum: torch.Tensor, dbias: torch.Tensor, w2: torch.Tensor,
                         b2: torch.Tensor, out_dtype: torch.dtype, simt: bool = False, stage=None,
-                        m_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        m_dev: Optional[torch.Tensor] = None, streamk: bool = False) -> torch.Tensor:
     """LayerNorm → Linear → SiLU → Linear of projector.py:149-151 as two tensor-core GEMMs:
-    GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue."""
+    GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue.
+    ``streamk``: EXPERIMENTAL — GEMM-1 through ``tasu_gemm_bf16_tn_streamk``."""
     Hb, H = w1g.shape[0], w2.shape[0]
     dev = x_bf16.device
     import contextlib
     stage = stage or (lambda name: contextlib.nullcontext())
     h1 = torch.empty(_cap(rows), Hb, dtype=torch.bfloat16, device=dev)[:rows]
     with stage("projector_gemm1"):
-        ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt,
-                         m_dev=m_dev)
+        if streamk and not simt:
+            ops.gemm_bf16_tn_streamk(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, m_dev=m_dev)
+        else:
+            ops.gemm_bf16_tn(x_bf16, w1g, rows, Hb, K, h1, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum, simt=simt,
+                             m_dev=m_dev)
     y = torch.empty(_cap(rows), H, dtype=out_dtype, device=dev)[:rows]
     with stage("projector_gemm2"):
         ops.gemm_bf16_tn(h1, w2, rows, H, Hb, y, L.EPI_BIAS, b2, simt=simt, m_dev=m_dev)
@@ -382,6 +387,8 @@ class TasuBridge:
         self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
         self._ctc_split_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
+        # EXPERIMENTAL (not yet validated on a GPU): projector GEMM-1 with the stream-K tail
+        self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK") == "1"
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
         self.events = []              # [(stage name, start event, end event)] of the profiled calls
 
@@ -405,7 +412,7 @@ class TasuBridge:
         with self._stage("pool_tail"):
             ops.pool_tail(pooled, V, cap_o, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
         return linear_silu_forward(pooled, cap_o, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
-                                   stage=self._stage, m_dev=plan.counts[0:1])
+                                   stage=self._stage, m_dev=plan.counts[0:1], streamk=self.streamk_gemm1)
 
     def _header_slot(self):
         """Ring of pinned host header buffers (collapse + splice words), one per in-flight call."""

@@ -12,3 +12,14 @@ if grep -q "rc=0" gpurun_out/rc_experimental.txt; then
     cat gpurun_out/pair_gemm.md
 fi
 cat gpurun_out/rc_experimental.txt
+# A/B of the headline bench with the experimental GEMM paths (only after their tests passed)
+if grep -q "rc=0" gpurun_out/rc_experimental.txt; then
+    for flag in "" "--streamk" "--pair-gemm" "--streamk --pair-gemm"; do
+        timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline $flag > "gpurun_out/bench_exp${flag// /_}.json" 2> /dev/null
+        python - "gpurun_out/bench_exp${flag// /_}.json" "$flag" <<'PY'
+import json, sys
+d = json.load(open(sys.argv[1]))
+print("bench %-22s %.3f ms/step  gemm1 %.3f ms  e2e %.3f ms" % (sys.argv[2] or "(default)", d["ms_per_step"], d["kernels"]["projector_gemm1"]["ms"], d["e2e"]["ms_per_step"]))
+PY
+    done
+fi
