@@ -61,9 +61,11 @@ int tasu_abi_version(void);
 const char* tasu_last_error(void);
 /* Run-time options.  Every option defaults to 0 (= the validated path) unless the environment variable of the same
  * purpose is set when the library is first used.
- *   TASU_OPT_GEMM_PAIR (env TASU_GEMM_PAIR): EXPERIMENTAL — tasu_gemm_bf16_tn runs deep-K shapes (K > 1024, M > 128) as
- *   CTA pairs: clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of
- *   the B tile.  Same contract and results as the default kernel (the accumulation order inside a tile is unchanged). */
+ *   TASU_OPT_GEMM_PAIR (env TASU_GEMM_PAIR): EXPERIMENTAL — tasu_gemm_bf16_tn runs problems with M > 128 as CTA pairs:
+ *   clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of the B
+ *   tile.  Bit 0 (value 1): deep-K shapes (K > 1024: 6 stages, one epilogue group); bit 1 (value 2): K <= 1024
+ *   (4 stages, two epilogue groups); 3 = both.  Same contract and results as the default kernel (the accumulation
+ *   order inside a tile is unchanged). */
 enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */

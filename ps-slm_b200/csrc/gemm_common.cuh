@@ -198,11 +198,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 // instruction descriptor of the pair MMA: M = 256 (128 rows per CTA), N = 256
 constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-constexpr int kPairStages = 6;
+constexpr int kPairStages = 6;                              // deep K: 6 x 32 KB stages, one epilogue group
+constexpr int kPairStagesShallow = 4;                       // K <= 1024 (store-heavy): 4 stages, two epilogue groups
 constexpr int kPairBBytes = (BN / 2) * BK * 2;              // each CTA loads half of the B tile: 16 KB
 constexpr int kPairStageBytes = kABytes + kPairBBytes;      // 32 KB
-constexpr int gemm_smem_bytes_pair(int stages) {
-    return stages * kPairStageBytes + 2 * kStagingBytes + kAuxBytes + 256 /*barriers*/;
+constexpr int gemm_smem_bytes_pair(int stages, int groups) {
+    return stages * kPairStageBytes + 2 * groups * kStagingBytes + groups * kAuxBytes + 256 /*barriers*/;
 }
 
 struct Params {

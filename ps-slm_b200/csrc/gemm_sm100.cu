@@ -37,7 +37,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];          // 128B-swizzle atoms need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();               // no static shared memory in this kernel → offset 0
-    static_assert(!kPair || (kMajor == 0 && kGroups == 1), "pair mode: K-major operands, one epilogue group");
+    static_assert(!kPair || kMajor == 0, "pair mode: K-major operands only");
     constexpr int kStages = kSt;
     constexpr int kStgBytes = kPair ? kPairStageBytes : kStageBytes;               // A 16 KB + B 32 KB (pair: 16 KB)
     constexpr int kTileM = kPair ? 2 * BM : BM;                                    // rows of C per work item
@@ -638,19 +638,20 @@ static int launch_dispatch(bool out_bf16, int epilogue, bool shallow_k, int grid
 }
 
 // CTA-pair mode (EXPERIMENTAL, TASU_OPT_GEMM_PAIR): clusters of two CTAs, one 256x256 tile per cluster
-template <bool kOutBf16, int kEpi>
+template <bool kOutBf16, int kEpi, int kSt, int kGroups>
 static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                            const CUtensorMap& mc, const Params& p) {
-    constexpr int smem = gemm_smem_bytes_pair(kPairStages);
+    constexpr int smem = gemm_smem_bytes_pair(kSt, kGroups);
     static_assert(smem <= 227 * 1024, "pair-mode shared memory exceeds the 227 KB a CTA can opt into");
-    auto kern = gemm_bf16_tn_kernel<kOutBf16, kEpi, kPairStages, 1, 0, true>;
+    static_assert((2 * kSt + 2 * kAccStages) * 8 + 4 <= 256, "barrier area");
+    auto kern = gemm_bf16_tn_kernel<kOutBf16, kEpi, kSt, kGroups, 0, true>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     TASU_CHECK_CUDA(attr_err);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * (unsigned)clusters);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(128 + 128 * kGroups);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -662,17 +663,24 @@ static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma,
     return TASU_OK;
 }
 
+template <bool kOutBf16, int kEpi>
+static int launch_pair_cfg(bool shallow_k, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+                           const CUtensorMap& mc, const Params& p) {
+    return shallow_k ? launch_pair_one<kOutBf16, kEpi, kPairStagesShallow, 2>(clusters, st, ma, mb, mc, p)
+                     : launch_pair_one<kOutBf16, kEpi, kPairStages, 1>(clusters, st, ma, mb, mc, p);
+}
+
 template <bool kOutBf16>
-static int launch_pair_epi(int epilogue, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+static int launch_pair_epi(int epilogue, bool sk, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                            const CUtensorMap& mc, const Params& p) {
     switch (epilogue) {
-        case TASU_EPI_NONE: return launch_pair_one<kOutBf16, TASU_EPI_NONE>(clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS: return launch_pair_one<kOutBf16, TASU_EPI_BIAS>(clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_SILU: return launch_pair_one<kOutBf16, TASU_EPI_BIAS_SILU>(clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_RELU: return launch_pair_one<kOutBf16, TASU_EPI_BIAS_RELU>(clusters, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD_SILU: return launch_pair_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(clusters, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD: return launch_pair_one<kOutBf16, TASU_EPI_LNFOLD>(clusters, st, ma, mb, mc, p);
-        default: return launch_pair_one<kOutBf16, TASU_EPI_SOFTMAX>(clusters, st, ma, mb, mc, p);
+        case TASU_EPI_NONE: return launch_pair_cfg<kOutBf16, TASU_EPI_NONE>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_SILU: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS_SILU>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_BIAS_RELU: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS_RELU>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD_SILU: return launch_pair_cfg<kOutBf16, TASU_EPI_LNFOLD_SILU>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_LNFOLD: return launch_pair_cfg<kOutBf16, TASU_EPI_LNFOLD>(sk, clusters, st, ma, mb, mc, p);
+        default: return launch_pair_cfg<kOutBf16, TASU_EPI_SOFTMAX>(sk, clusters, st, ma, mb, mc, p);
     }
 }
 
@@ -742,8 +750,10 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     const int csz = c_dtype == TASU_F32 ? 4 : 2;
     TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
     TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
-    // EXPERIMENTAL CTA-pair mode (off unless TASU_OPT_GEMM_PAIR is set): deep-K shapes with at least one 256-row tile
-    const bool pair = option(TASU_OPT_GEMM_PAIR) != 0 && K > 1024 && M > BM && sm_count() >= 2;
+    // EXPERIMENTAL CTA-pair mode (off unless TASU_OPT_GEMM_PAIR is set; bit 0: deep-K shapes, bit 1: K <= 1024),
+    // for problems with more than one 128-row tile
+    const int pair_opt = option(TASU_OPT_GEMM_PAIR);
+    const bool pair = (pair_opt & (K > 1024 ? 1 : 2)) != 0 && M > BM && sm_count() >= 2;
     CUtensorMap ma, mb, mc;
     rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
@@ -758,8 +768,8 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
         int clusters = sm_count() / 2;
         if (clusters > pair_tiles) clusters = pair_tiles;
         cudaStream_t pst = (cudaStream_t)stream;
-        rc = c_dtype == TASU_BF16 ? launch_pair_epi<true>(epilogue, clusters, pst, ma, mb, mc, p)
-                                  : launch_pair_epi<false>(epilogue, clusters, pst, ma, mb, mc, p);
+        rc = c_dtype == TASU_BF16 ? launch_pair_epi<true>(epilogue, K <= 1024, clusters, pst, ma, mb, mc, p)
+                                  : launch_pair_epi<false>(epilogue, K <= 1024, clusters, pst, ma, mb, mc, p);
         if (rc) return rc;
         TASU_CHECK_LAUNCH();
         return TASU_OK;

@@ -24,7 +24,7 @@ def dev():
 def pair_mode():
     import ps_slm_b200._lib as L
     import ps_slm_b200.ops as ops
-    ops.set_option(L.OPT_GEMM_PAIR, 1)
+    ops.set_option(L.OPT_GEMM_PAIR, 3)          # bit 0: deep-K shapes, bit 1: K <= 1024
     yield
     ops.set_option(L.OPT_GEMM_PAIR, 0)
 
@@ -45,9 +45,11 @@ def _ref(A, B, epi, bias, rstd, mean, colsum):
     return acc
 
 
-# deep-K shapes only (K > 1024, M > 128 select the pair kernel): ragged M / N / K, M below / above one pair tile, a tile
-# whose upper CTA is entirely out of range (M = 300: rows 256..299 live in the lower CTA of the second pair tile)
-PAIR_SHAPES = [(256, 256, 1088), (129, 8, 1032), (300, 260, 1100), (257, 1536, 2048), (1000, 2048, 25055), (8341, 2048, 4096)]
+# M > 128 selects the pair kernel (K > 1024: 6-stage / one epilogue group; K <= 1024: 4-stage / two groups): ragged
+# M / N / K, M below / above one pair tile, a tile whose upper CTA is entirely out of range (M = 300: rows 256..299 live
+# in the lower CTA of the second pair tile), the kept-frame softmax GEMM shape (K = 512, N = 25055)
+PAIR_SHAPES = [(256, 256, 1088), (129, 8, 1032), (300, 260, 1100), (257, 1536, 2048), (1000, 2048, 25055), (8341, 2048, 4096),
+               (256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512)]
 
 
 @pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
@@ -58,8 +60,8 @@ def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtyp
     accumulator, K blocks in ascending order), so the two must agree BIT FOR BIT; both are checked against fp64."""
     import ps_slm_b200._lib as L
     import ps_slm_b200.ops as ops
-    if K > 20000 and epi not in (1, 4):
-        pytest.skip("large K: a subset of epilogues is enough")
+    if (K > 20000 or N > 20000) and epi not in (1, 4, 6):
+        pytest.skip("large shapes: a subset of epilogues is enough")
     torch.manual_seed(M + 3 * N + 7 * K + epi)
     lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
     A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
@@ -69,7 +71,7 @@ def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtyp
     Ad, Bd = A.to(dev), B.to(dev)
     vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
     C = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
-    assert ops.get_option(L.OPT_GEMM_PAIR) == 1
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 3
     ops.gemm_bf16_tn(Ad, Bd, M, N, K, C, epi, *vec)
     torch.cuda.synchronize()
     ops.set_option(L.OPT_GEMM_PAIR, 0)

@@ -33,15 +33,16 @@ def time_ms(fn, n=20, warm=3):
 print("| shape (M, N, K) | epilogue | default ms | TFLOP/s | pair ms | TFLOP/s | pair / default | stream-K ms | TFLOP/s | stream-K / default |")
 print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|")
 for (M, N, K, epi, name) in [(8341, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + SiLU"), (8341, 1536, 2048, L.EPI_BIAS, "bias"),
-                             (16384, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + SiLU"), (8192, 8192, 8192, L.EPI_NONE, "none")]:
+                             (16384, 2048, 25055, L.EPI_LNFOLD_SILU, "LN-fold + SiLU"), (8192, 8192, 8192, L.EPI_NONE, "none"),
+                             (11330, 25055, 512, L.EPI_SOFTMAX, "softmax (kept frames)")]:
     torch.manual_seed(0)
     A = (torch.randn(M, ops.pad_to(K), device=dev) * 0.3).bfloat16()
     B = (torch.randn(N, ops.pad_to(K), device=dev) * 0.3).bfloat16()
-    C = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    C = torch.empty(M, ops.pad_to(N), dtype=torch.bfloat16, device=dev)[:, :N]      # 16-byte aligned row pitch
     bias, rstd, mean, colsum = (torch.randn(n, device=dev) for n in (N, M, M, N))
     res = {}
     for pair in (0, 1):
-        ops.set_option(L.OPT_GEMM_PAIR, pair)
+        ops.set_option(L.OPT_GEMM_PAIR, 3 * pair)
         res[pair] = time_ms(lambda: ops.gemm_bf16_tn(A, B, M, N, K, C, epi, bias, rstd, mean, colsum))
     ops.set_option(L.OPT_GEMM_PAIR, 0)
     sk = time_ms(lambda: ops.gemm_bf16_tn_streamk(A, B, M, N, K, C, epi, bias, rstd, mean, colsum))
