@@ -45,7 +45,7 @@ def parse():
                     help="EXPERIMENTAL (DESIGN.md §9): projector GEMM-1 with the stream-K tail (tasu_gemm_bf16_tn_streamk)")
     ap.add_argument("--pair-gemm", type=int, default=0, metavar="MASK",
                     help="EXPERIMENTAL (DESIGN.md §9): GEMMs as CTA pairs, tasu_set_option(TASU_OPT_GEMM_PAIR, MASK): "
-                         "1 = deep-K shapes (projector), 2 = K <= 1024 (kept-frame softmax GEMM), 3 = both")
+                         "1 = deep-K shapes (projector), 2 = K <= 1024 (kept-frame softmax GEMM), 4 = fused CTC head + stats, 7 = all")
     ap.add_argument("--materialize-logits", action="store_true",
                     help="round-1a path: ctc_lo writes fp32 logits to HBM and a streaming kernel computes the stats")
     return ap.parse_args()

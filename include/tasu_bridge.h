@@ -65,7 +65,9 @@ const char* tasu_last_error(void);
  *   clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of the B
  *   tile.  Bit 0 (value 1): deep-K shapes (K > 1024: 6 stages, one epilogue group); bit 1 (value 2): K <= 1024
  *   (4 stages, two epilogue groups); 3 = both.  Same contract and results as the default kernel (the accumulation
- *   order inside a tile is unchanged). */
+ *   order inside a tile is unchanged).  Bit 2 (value 4): tasu_ctc_head_stats with K <= 512 as CTA pairs (256 frames
+ *   per work item, each CTA keeps its 128 frames resident and streams half of every weight tile through 6 stages);
+ *   the vocabulary may be split differently, so sums agree with the default kernel to fp32 rounding, not bit for bit. */
 enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */

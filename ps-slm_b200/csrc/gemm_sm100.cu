@@ -327,17 +327,25 @@ constexpr int kStatsSmemBytesARes = 8 * kABytes + 3 * kBBytes + 2 * BN * 4 + 128
 constexpr int kStatsThreads = 384;                   // warps 0-3 control, warps 4-11 epilogue
 constexpr int kStatsEpiThreads = 256;
 
+constexpr int kStatsPairStages = 6;                  // pair mode: 6 x 16 KB half-B stages next to the resident A tile
+constexpr int kStatsSmemBytesPair = 8 * kABytes + kStatsPairStages * kPairBBytes + 2 * BN * 4 + 256;
+
 // kARes (K <= 512): the 128-frame A tile stays resident in shared memory for the whole vocabulary sweep of an item
 // and only the weight tiles stream through a 3-stage ring — a third less L2→SM traffic per MMA.
-template <bool kARes>
+// kPair (EXPERIMENTAL, with kARes; launched as clusters of 2, see gemm_bf16_tn_kernel): a work item covers 256 frames,
+// each CTA keeps its own 128 frames resident and streams HALF of every 256-column weight tile (16 KB per stage, 6
+// stages), the rank-0 CTA issues tcgen05.mma.cta_group::2, every CTA reduces the statistics of its own 128 frames.
+template <bool kARes, bool kPair = false>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const StatsParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    constexpr int kSt = kARes ? 3 : kStages;                                   // ring stages
-    constexpr int kRingStage = kARes ? kBBytes : kStageBytes;                  // bytes per ring stage
+    static_assert(!kPair || kARes, "pair mode keeps the A tile resident");
+    constexpr int kSt = kPair ? kStatsPairStages : kARes ? 3 : kStages;        // ring stages
+    constexpr int kRingStage = kPair ? kPairBBytes : kARes ? kBBytes : kStageBytes;   // bytes per ring stage
     constexpr int kRingOff = kARes ? 8 * kABytes : 0;                          // resident A: 8 k-blocks x 16 KB
+    constexpr int kTileM = kPair ? 2 * BM : BM;                                // frames per work item
     uint8_t* ring = smem + kRingOff;
     float* s_bias = reinterpret_cast<float*>(ring + kSt * kRingStage);         // [2][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSt * kRingStage + 2 * BN * 4);
@@ -350,33 +358,61 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + kTileM - 1) / kTileM, n_tiles = (p.N + BN - 1) / BN;
     const int num_items = m_tiles * p.splits;
     const int k_blocks = (p.K + BK - 1) / BK;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+#define TASU_ITEM_LOOP for (int item = kPair ? (blockIdx.x >> 1) : blockIdx.x; item < num_items; item += kPair ? (gridDim.x >> 1) : gridDim.x)
+#define TASU_ITEM_M0 ((item / p.splits) * kTileM + (kPair ? (int)rank * BM : 0))
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kSt; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kStatsEpiThreads); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kStatsEpiThreads * (kPair ? 2 : 1)); }
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, a_phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int m0 = (item / p.splits) * BM;
+            TASU_ITEM_LOOP {
+                const int m0 = TASU_ITEM_M0;
                 const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+                if (kPair) {
+                    // both CTAs' frames / weight halves complete on the rank-0 barriers the MMA thread waits on
+                    mbar_wait(a_empty, a_phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(2 * k_blocks * kABytes));
+                    const uint32_t af = mapa_u32(smem_u32(a_full), 0);
+                    for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d_pair(&tmap_a, af, smem + kb * kABytes, kb * BK, m0);
+                    a_phase ^= 1;
+                    for (int nt = nb; nt < ne; ++nt) {
+                        for (int kb = 0; kb < k_blocks; ++kb) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * kRingStage));
+                            tma_load_2d_pair(&tmap_b, mapa_u32(smem_u32(&full_bar[stage]), 0), ring + stage * kRingStage,
+                                             kb * BK, nt * BN + (int)rank * (BN / 2));
+                            if (++stage == kSt) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 if (kARes) {
                     mbar_wait(a_empty, a_phase ^ 1);               // MMAs of the previous item are done with A
                     mbar_expect_tx(a_full, (uint32_t)(k_blocks * kABytes));
@@ -400,14 +436,15 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && (!kPair || rank == 0)) {
             int stage = 0; uint32_t phase = 0, a_phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            TASU_ITEM_LOOP {
                 const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
                 if (kARes) { mbar_wait(a_full, a_phase); tc_fence_after(); a_phase ^= 1; }
                 for (int nt = nb; nt < ne; ++nt) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+                    else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                     for (int kb = 0; kb < k_blocks; ++kb) {
@@ -417,16 +454,25 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint64_t adesc = make_smem_desc(kARes ? smem_u32(smem + kb * kABytes) : sr);
                         const uint64_t bdesc = make_smem_desc(kARes ? sr : sr + kABytes);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                      (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (kPair) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDescPair,
+                                                      (kb > 0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                           (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if (kPair) {
+                            umma_commit_pair(&empty_bar[stage]);
+                            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        }
                         if (++stage == kSt) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
                 }
-                if (kARes) umma_commit(a_empty);                   // every MMA of this item has retired → A may be replaced
+                if (kPair) umma_commit_pair(a_empty);              // both CTAs may replace their resident frames
+                else if (kARes) umma_commit(a_empty);              // every MMA of this item has retired → A may be replaced
             }
         }
     } else if (warp >= 4) {
@@ -437,9 +483,9 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr float kL2e = 1.4426950408889634f;
         int acc = 0; uint32_t acc_phase = 0;
         int bbuf = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const int m_tile = item / p.splits, split = item % p.splits;
-            const int row = m_tile * BM + ew * 32 + lane;
+        TASU_ITEM_LOOP {
+            const int split = item % p.splits;
+            const int row = TASU_ITEM_M0 + ew * 32 + lane;
             const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
             float rm = -INFINITY, rs = 0.f, rs2 = 0.f, xb = 0.f;
             int best = 0x7fffffff;
@@ -506,7 +552,11 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     process(va, sub);
                     tmem_ld_wait(vb);
                     if (sub + 2 < sub1) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
-                    else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+                    else {
+                        tc_fence_before();
+                        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
                     process(vb, sub + 1);
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -526,10 +576,14 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
     }
+#undef TASU_ITEM_LOOP
+#undef TASU_ITEM_M0
 }
 
 // merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
@@ -838,8 +892,14 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     if (rc) return rc;
     rc = make_map(&mb, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V, K, ldw, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
-    const int m_tiles = (M + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
-    int grid = sm_count();
+    // EXPERIMENTAL CTA-pair mode (TASU_OPT_GEMM_PAIR bit 2): 256 frames per work item, clusters of two CTAs
+    const bool pair = (option(TASU_OPT_GEMM_PAIR) & 4) != 0 && K <= 8 * BK && M > BM && sm_count() >= 2;
+    if (pair) {
+        rc = make_map(&mb, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V, K, ldw, BN / 2, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    const int m_tiles = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
+    int grid = pair ? sm_count() / 2 : sm_count();           // pair mode: clusters
     StatsParams p{};
     p.M = M; p.N = V; p.K = K; p.blank = blank_id; p.bias = bias;
     pick_splits(m_tiles, n_tiles, grid, &p.splits, &p.nt_per);
@@ -859,7 +919,27 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
             attr_err = cudaFuncSetAttribute(ctc_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytes);
     });
     TASU_CHECK_CUDA(attr_err);
-    if (K <= 8 * BK) ctc_stats_kernel<true><<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
+    if (pair) {
+        static_assert(kStatsSmemBytesPair <= 227 * 1024, "pair-mode shared memory exceeds the 227 KB a CTA can opt into");
+        auto kern = ctc_stats_kernel<true, true>;
+        static std::once_flag once_pair;
+        static cudaError_t attr_err_pair = cudaSuccess;
+        std::call_once(once_pair, [&] {
+            attr_err_pair = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesPair);
+        });
+        TASU_CHECK_CUDA(attr_err_pair);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)grid);
+        cfg.blockDim = dim3(kStatsThreads);
+        cfg.dynamicSmemBytes = kStatsSmemBytesPair;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+    } else if (K <= 8 * BK) ctc_stats_kernel<true><<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
     else ctc_stats_kernel<false><<<grid, kStatsThreads, kStatsSmemBytes, st>>>(ma, mb, p);
     TASU_CHECK_LAUNCH();
     const int64_t frames = (int64_t)B * T;

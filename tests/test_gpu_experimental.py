@@ -230,3 +230,41 @@ def test_streamk_matches_default_on_uncut_tiles(dev):
     whole_rows = (444 // 8) * 128                        # n fastest: tile = m_tile * 8 + n_tile
     assert torch.equal(C0[:whole_rows], C1[:whole_rows])
     assert (C0 - C1).abs().max().item() / C0.abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CTA-pair mode of the fused CTC head + statistics kernel (TASU_OPT_GEMM_PAIR bit 2)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,P,V,K,blank", [(3, 37, 4, 25055, 512, 0), (2, 130, 4, 300, 64, 7), (5, 300, 4, 4099, 512, 0),
+                                             (64, 500, 4, 25055, 512, 0), (1, 200, 0, 1000, 448, 999)])
+def test_pair_ctc_head_stats(dev, B, T, P, V, K, blank):
+    import numpy as np
+
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(V + T)
+    rows = B * (T + P)
+    x = (torch.randn(rows, K) * 0.7).bfloat16()
+    w = (torch.randn(V, K) * 0.6).bfloat16()
+    lab = torch.randint(0, V, (rows,))
+    x += (4.0 * w[lab].float() / w[lab].float().norm(dim=1, keepdim=True)).bfloat16()     # a clear winner per frame
+    bias = torch.randn(V) * 0.1
+    xd = torch.zeros(rows, ops.pad_to(K), dtype=torch.bfloat16); xd[:, :K] = x
+    wd = torch.zeros(V, ops.pad_to(K), dtype=torch.bfloat16); wd[:, :K] = w
+    xd, wd, bd = xd.to(dev), wd.to(dev), bias.to(dev)
+    st0 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_PAIR, 4)
+    try:
+        st1 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+        st2 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(L.OPT_GEMM_PAIR, 0)
+    # logits are accumulated in the same order (one TMEM accumulator, ascending K): max / argmax / blank logit are
+    # bit-equal to the default kernel; the exp-sums may be split differently over the vocabulary → fp32 rounding
+    assert torch.equal(st1.argmax, st0.argmax) and torch.equal(st1.row_max, st0.row_max) and torch.equal(st1.x_blank, st0.x_blank)
+    np.testing.assert_allclose(st1.row_sumexp.cpu().numpy(), st0.row_sumexp.cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(st1.row_sumexp2.cpu().numpy(), st0.row_sumexp2.cpu().numpy(), rtol=1e-5)
+    for a, b in ((st1.argmax, st2.argmax), (st1.row_sumexp, st2.row_sumexp), (st1.row_sumexp2, st2.row_sumexp2)):
+        assert torch.equal(a, b), "back-to-back launches must agree bit for bit"
