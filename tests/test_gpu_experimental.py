@@ -67,7 +67,7 @@ def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtyp
     A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
     B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
-    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 0.6 * (K ** 0.5))     # softmax: a plausible row max
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))     # softmax: a plausible row max
     Ad, Bd = A.to(dev), B.to(dev)
     vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
     C = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
@@ -176,7 +176,7 @@ def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
     A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
     B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
-    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 0.6 * (K ** 0.5))
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
     Ad, Bd = A.to(dev), B.to(dev)
     vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
     outs = []
