@@ -67,8 +67,11 @@ const char* tasu_last_error(void);
  *   (4 stages, two epilogue groups); 3 = both.  Same contract and results as the default kernel (the accumulation
  *   order inside a tile is unchanged).  Bit 2 (value 4): tasu_ctc_head_stats with K <= 512 as CTA pairs (256 frames
  *   per work item, each CTA keeps its 128 frames resident and streams half of every weight tile through 6 stages);
- *   the vocabulary may be split differently, so sums agree with the default kernel to fp32 rounding, not bit for bit. */
-enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
+ *   the vocabulary may be split differently, so sums agree with the default kernel to fp32 rounding, not bit for bit.
+ *   TASU_OPT_EPI_PREFETCH (env TASU_EPI_PREFETCH): EXPERIMENTAL — epilogue vectors (bias, colsum, row statistics) of the
+ *   NEXT tile are fetched while the current tile is processed.  Bit 0: tasu_gemm_bf16_tn for K <= 1024; bit 1:
+ *   tasu_ctc_head_stats.  Same values and arithmetic: results are bit-identical to the default kernels. */
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_COUNT = 2 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */

@@ -31,7 +31,12 @@ namespace gemm {
 //        each CTA stages its own 128 rows of A and 128 of the 256 B rows (32 KB per stage instead of 48 KB, a third
 //        less L2->smem traffic per flop), the rank-0 CTA issues the MMAs and multicasts its commits to both CTAs,
 //        every CTA runs the epilogue of its own 128 accumulator rows.  EXPERIMENTAL: see tasu_set_option.
-template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false>
+// kPrefetch (EXPERIMENTAL, TASU_OPT_EPI_PREFETCH): the epilogue fetches the bias / colsum / row-statistics values of
+//        its NEXT tile into registers while it processes the current one, instead of loading them at the top of every
+//        tile.  For K = 512 a tile lasts ~2 us and the exposed L2 latency of those loads is the largest single stall
+//        of the kept-frame softmax GEMM (profiles/r01h_ncu_detail.md).  Same values, same arithmetic: results are
+//        bit-identical to the default kernel.
+template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false, bool kPrefetch = false>
 __global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -178,11 +183,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int sw = et & 7;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
+        // kPrefetch: values of the NEXT tile, fetched one tile ahead (column c = et + i * kEpiThreads of the tile)
+        constexpr bool kLnFold = kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD;
+        constexpr bool kRowVec = kLnFold || kEpi == TASU_EPI_SOFTMAX;
+        float pf_bias[BN / kEpiThreads], pf_colsum[BN / kEpiThreads], pf_rstd = 1.f, pf_mean = 0.f;
+        auto prefetch_tile = [&](int t) {
+            const int pm0 = (t / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0), pn0 = (t % n_tiles) * BN;
+#pragma unroll
+            for (int i = 0; i < BN / kEpiThreads; ++i) {
+                const int col = pn0 + et + i * kEpiThreads;
+                pf_bias[i] = (kEpi != TASU_EPI_NONE && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                pf_colsum[i] = (kLnFold && col < p.N) ? __ldg(p.colsum + col) : 0.f;
+            }
+            pf_rstd = 1.f; pf_mean = 0.f;
+            if (kRowVec && pm0 + et < M_live) { pf_rstd = __ldg(p.row_rstd + pm0 + et); pf_mean = __ldg(p.row_mean + pm0 + et); }
+        };
+        if (kPrefetch) {
+            const int t0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+            if (t0 < num_tiles) prefetch_tile(t0);
+        }
         TASU_TILE_LOOP {
             const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
             const int grow = m0 + et;
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
+            if (kPrefetch) {
+                if (kEpi != TASU_EPI_NONE) {
+#pragma unroll
+                    for (int i = 0; i < BN / kEpiThreads; ++i) {
+                        s_bias[et + i * kEpiThreads] = pf_bias[i] * (kEpi == TASU_EPI_SOFTMAX ? kLog2e : 1.f);
+                        if (kLnFold) s_colsum[et + i * kEpiThreads] = pf_colsum[i];
+                    }
+                }
+            } else
             if (kEpi != TASU_EPI_NONE) {
                 for (int c = et; c < BN; c += kEpiThreads) {   // each group stages its own copy (own barrier)
                     const int col = n0 + c;
@@ -192,6 +225,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             float rstd = 1.f, nmean = 0.f;
+            if (kPrefetch) {
+                rstd = pf_rstd; nmean = -pf_mean;
+                // the next tile's values are in flight while this tile is processed
+                const int nxt = tile + (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+                if (nxt < num_tiles) prefetch_tile(nxt);
+            } else
             if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < M_live) {
                 rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow);
             }
@@ -335,7 +374,9 @@ constexpr int kStatsSmemBytesPair = 8 * kABytes + kStatsPairStages * kPairBBytes
 // kPair (EXPERIMENTAL, with kARes; launched as clusters of 2, see gemm_bf16_tn_kernel): a work item covers 256 frames,
 // each CTA keeps its own 128 frames resident and streams HALF of every 256-column weight tile (16 KB per stage, 6
 // stages), the rank-0 CTA issues tcgen05.mma.cta_group::2, every CTA reduces the statistics of its own 128 frames.
-template <bool kARes, bool kPair = false>
+// kPrefetch (EXPERIMENTAL, TASU_OPT_EPI_PREFETCH bit 1): every epilogue thread fetches its bias value of the NEXT
+// vocabulary tile while the current one is reduced (the load at the top of each tile is exposed L2 latency otherwise).
+template <bool kARes, bool kPair = false, bool kPrefetch = false>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const StatsParams p) {
@@ -483,6 +524,13 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr float kL2e = 1.4426950408889634f;
         int acc = 0; uint32_t acc_phase = 0;
         int bbuf = 0;
+        // kPrefetch: this thread's bias value (column et) of the tile after the current one, in program order
+#define TASU_BIAS_OF(n0_) (((n0_) + et) < p.N ? (p.bias ? __ldg(p.bias + (n0_) + et) : 0.f) : -INFINITY)
+        [[maybe_unused]] float pf_bias = 0.f;
+        if constexpr (kPrefetch) {
+            const int it0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+            if (it0 < num_items) pf_bias = TASU_BIAS_OF((it0 % p.splits) * p.nt_per * BN);
+        }
         TASU_ITEM_LOOP {
             const int split = item % p.splits;
             const int row = TASU_ITEM_M0 + ew * 32 + lane;
@@ -492,6 +540,13 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int nt = nb; nt < ne; ++nt) {
                 const int n0 = nt * BN;
                 float* sb = s_bias + bbuf * BN;
+                if constexpr (kPrefetch) {
+                    sb[et] = pf_bias;
+                    // next tile of this item, else the first tile of this CTA's next item
+                    const int nxt_item = item + (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+                    if (nt + 1 < ne) pf_bias = TASU_BIAS_OF((nt + 1) * BN);
+                    else if (nxt_item < num_items) pf_bias = TASU_BIAS_OF((nxt_item % p.splits) * p.nt_per * BN);
+                } else
                 {
                     const int col = n0 + et;                      // -inf masks the columns beyond the vocabulary
                     sb[et] = col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
@@ -584,6 +639,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 #undef TASU_ITEM_LOOP
 #undef TASU_ITEM_M0
+#undef TASU_BIAS_OF
 }
 
 // merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
@@ -663,10 +719,25 @@ static int launch_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CU
     return TASU_OK;
 }
 
+// EXPERIMENTAL (TASU_OPT_EPI_PREFETCH bit 0): shallow-K configuration with the epilogue vectors fetched one tile ahead
+template <bool kOutBf16, int kEpi>
+static int launch_one_prefetch(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                               const Params& p) {
+    constexpr int smem = gemm_smem_bytes(3, 2);
+    auto kern = gemm_bf16_tn_kernel<kOutBf16, kEpi, 3, 2, 0, false, true>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    TASU_CHECK_CUDA(attr_err);
+    kern<<<grid, 128 + 128 * 2, smem, st>>>(ma, mb, mc, p);
+    return TASU_OK;
+}
+
 // deep-K shapes: 4 smem stages, one epilogue group; shallow-K (store-heavy) shapes: 3 stages, two epilogue groups
 template <bool kOutBf16, int kEpi>
 static int launch_cfg(bool shallow_k, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                       const CUtensorMap& mc, const Params& p) {
+    if (shallow_k && (option(TASU_OPT_EPI_PREFETCH) & 1) != 0) return launch_one_prefetch<kOutBf16, kEpi>(grid, st, ma, mb, mc, p);
     return shallow_k ? launch_one<kOutBf16, kEpi, 3, 2>(grid, st, ma, mb, mc, p)
                      : launch_one<kOutBf16, kEpi, 4, 1>(grid, st, ma, mb, mc, p);
 }
@@ -919,7 +990,17 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
             attr_err = cudaFuncSetAttribute(ctc_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytes);
     });
     TASU_CHECK_CUDA(attr_err);
-    if (pair) {
+    const bool prefetch = (option(TASU_OPT_EPI_PREFETCH) & 2) != 0;
+    if (prefetch && !pair && K <= 8 * BK) {
+        auto kern = ctc_stats_kernel<true, false, true>;
+        static std::once_flag once_pf;
+        static cudaError_t attr_err_pf = cudaSuccess;
+        std::call_once(once_pf, [&] {
+            attr_err_pf = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesARes);
+        });
+        TASU_CHECK_CUDA(attr_err_pf);
+        kern<<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
+    } else if (pair) {
         static_assert(kStatsSmemBytesPair <= 227 * 1024, "pair-mode shared memory exceeds the 227 KB a CTA can opt into");
         auto kern = ctc_stats_kernel<true, true>;
         static std::once_flag once_pair;

@@ -4,6 +4,7 @@ validated path; `tools/gpu_experimental.sh` runs them under a timeout.
 
   * CTA-pair GEMM (tasu_set_option(TASU_OPT_GEMM_PAIR, 1)): tcgen05.mma.cta_group::2, M = 256 per pair of CTAs.
   * stream-K GEMM (tasu_gemm_bf16_tn_streamk): the ragged last wave of tiles cut along K, fix-up through a workspace.
+  * epilogue prefetch (tasu_set_option(TASU_OPT_EPI_PREFETCH, mask)): bias / row vectors of the next tile fetched early.
 """
 import os
 
@@ -268,3 +269,57 @@ def test_pair_ctc_head_stats(dev, B, T, P, V, K, blank):
     np.testing.assert_allclose(st1.row_sumexp2.cpu().numpy(), st0.row_sumexp2.cpu().numpy(), rtol=1e-5)
     for a, b in ((st1.argmax, st2.argmax), (st1.row_sumexp, st2.row_sumexp), (st1.row_sumexp2, st2.row_sumexp2)):
         assert torch.equal(a, b), "back-to-back launches must agree bit for bit"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# epilogue vectors fetched one tile ahead (TASU_OPT_EPI_PREFETCH): same values, same arithmetic → bit-identical
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512), (11330, 4099, 512), (5, 40, 136)])
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
+                                           (5, torch.float32), (6, torch.bfloat16)])
+def test_epilogue_prefetch_gemm_is_bit_identical(dev, M, N, K, epi, out_dtype):
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
+    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    C0 = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C0, epi, *vec)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_EPI_PREFETCH, 1)
+    try:
+        C1 = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
+        ops.gemm_bf16_tn(Ad, Bd, M, N, K, C1, epi, *vec)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(L.OPT_EPI_PREFETCH, 0)
+    assert torch.equal(C0, C1)
+    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    scale = ref.abs().max().item() + 1e-6
+    assert (C1.cpu()[:, :N].double() - ref).abs().max().item() / scale < (1e-4 if out_dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("B,T,P,V,K,blank", [(3, 37, 4, 25055, 512, 0), (2, 130, 4, 300, 64, 7), (64, 500, 4, 25055, 512, 0)])
+def test_epilogue_prefetch_ctc_head_stats_is_bit_identical(dev, B, T, P, V, K, blank):
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(V + T)
+    rows = B * (T + P)
+    xd = torch.zeros(rows, ops.pad_to(K), dtype=torch.bfloat16); xd[:, :K] = (torch.randn(rows, K) * 0.7).bfloat16()
+    wd = torch.zeros(V, ops.pad_to(K), dtype=torch.bfloat16); wd[:, :K] = (torch.randn(V, K) * 0.6).bfloat16()
+    xd, wd, bd = xd.to(dev), wd.to(dev), (torch.randn(V) * 0.1).to(dev)
+    st0 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_EPI_PREFETCH, 2)
+    try:
+        st1 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(L.OPT_EPI_PREFETCH, 0)
+    for name in ("argmax", "x_blank", "row_max", "row_sumexp", "row_sumexp2"):
+        assert torch.equal(getattr(st0, name), getattr(st1, name)), name

@@ -14,7 +14,7 @@ fi
 cat gpurun_out/rc_experimental.txt
 # A/B of the headline bench with the experimental GEMM paths (only after their tests passed)
 if grep -q "rc=0" gpurun_out/rc_experimental.txt; then
-    for flag in "" "--streamk" "--pair-gemm 1" "--pair-gemm 2" "--pair-gemm 3" "--pair-gemm 4" "--pair-gemm 7" "--streamk --pair-gemm 6"; do
+    for flag in "" "--epi-prefetch 3" "--streamk" "--streamk --epi-prefetch 3" "--pair-gemm 1" "--pair-gemm 2" "--pair-gemm 3" "--pair-gemm 4" "--pair-gemm 7" "--streamk --pair-gemm 6"; do
         timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline $flag > "gpurun_out/bench_exp${flag// /_}.json" 2> /dev/null
         python - "gpurun_out/bench_exp${flag// /_}.json" "$flag" <<'PY'
 import json, sys
