@@ -70,8 +70,11 @@ const char* tasu_last_error(void);
  *   the vocabulary may be split differently, so sums agree with the default kernel to fp32 rounding, not bit for bit.
  *   TASU_OPT_EPI_PREFETCH (env TASU_EPI_PREFETCH): EXPERIMENTAL — epilogue vectors (bias, colsum, row statistics) of the
  *   NEXT tile are fetched while the current tile is processed.  Bit 0: tasu_gemm_bf16_tn for K <= 1024; bit 1:
- *   tasu_ctc_head_stats.  Same values and arithmetic: results are bit-identical to the default kernels. */
-enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_COUNT = 2 };
+ *   tasu_ctc_head_stats.  Same values and arithmetic: results are bit-identical to the default kernels.
+ *   TASU_OPT_STATS_WIDE (env TASU_STATS_WIDE): EXPERIMENTAL — tasu_ctc_head_stats (K <= 512) with 16 epilogue warps
+ *   (four per scheduler, each a 64-column quarter of the tile read as 16-column TMEM slabs) instead of 8; sums are
+ *   associated differently (quarters instead of halves): equal to the default kernel to fp32 rounding. */
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_STATS_WIDE = 2, TASU_OPT_COUNT = 3 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */

@@ -642,6 +642,213 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #undef TASU_BIAS_OF
 }
 
+// ------------------------------------------------------------------ EXPERIMENTAL: 16 epilogue warps
+// TASU_OPT_STATS_WIDE.  profiles/r01h_ncu_detail.md: ctc_stats_kernel is epilogue-bound (the MMA thread spins ~4 M times
+// on tmem_empty) although MUFU (42 %) and the issue slots (46 %) are half idle — with two epilogue warps per scheduler the
+// fixed-latency dependency waits are exposed.  This variant runs FOUR epilogue warps per scheduler: 16 warps, each owning
+// one TMEM lane quadrant and a 64-column quarter of the 256-column tile, read as 16-column tcgen05.ld slabs so that
+// 640 threads fit the register file; the bias value of the next tile is prefetched.  Producer / MMA roles, the resident
+// A tile and the 3-stage weight ring are those of ctc_stats_kernel<true>; partials are written per (split, quarter).
+constexpr int kWideThreads = 640;                    // warps 0-3 control, warps 4-19 epilogue
+constexpr int kWideEpiThreads = 512;
+
+__global__ void __launch_bounds__(kWideThreads, 1)
+ctc_stats_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const StatsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    constexpr int kSt = 3;
+    uint8_t* ring = smem + 8 * kABytes;                                        // resident A: 8 k-blocks x 16 KB
+    float* s_bias = reinterpret_cast<float*>(ring + kSt * kBBytes);            // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSt * kBBytes + 2 * BN * 4);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kSt;
+    uint64_t* tmem_full = bars + 2 * kSt;
+    uint64_t* tmem_empty = bars + 2 * kSt + kAccStages;
+    uint64_t* a_full = bars + 2 * kSt + 2 * kAccStages;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int num_items = m_tiles * p.splits;
+    const int k_blocks = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kSt; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kWideEpiThreads); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int m0 = (item / p.splits) * BM;
+                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+                mbar_wait(a_empty, a_phase ^ 1);                   // MMAs of the previous item are done with A
+                mbar_expect_tx(a_full, (uint32_t)(k_blocks * kABytes));
+                for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(&tmap_a, a_full, smem + kb * kABytes, kb * BK, m0);
+                a_phase ^= 1;
+                for (int nt = nb; nt < ne; ++nt) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes);
+                        tma_load_2d(&tmap_b, &full_bar[stage], ring + stage * kBBytes, kb * BK, nt * BN);
+                        if (++stage == kSt) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+                mbar_wait(a_full, a_phase); tc_fence_after(); a_phase ^= 1;
+                for (int nt = nb; nt < ne; ++nt) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc(smem_u32(smem + kb * kABytes));
+                        const uint64_t bdesc = make_smem_desc(smem_u32(ring + stage * kBBytes));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        if (++stage == kSt) { stage = 0; phase ^= 1; }
+                    }
+                    if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // 16 epilogue warps: warps (q, q+4, q+8, q+12) share TMEM lane quadrant q; `quarter` selects 64 of the 256 columns
+        const int ew = (warp - 4) & 3, quarter = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128;                          // 0..511; threads 0..255 stage the bias
+        constexpr float kL2e = 1.4426950408889634f;
+        int acc = 0; uint32_t acc_phase = 0;
+        int bbuf = 0;
+        auto bias_of = [&](int n0) {                               // -inf masks the columns beyond the vocabulary
+            const int col = n0 + et;
+            return col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
+        };
+        float pf_bias = 0.f;                                       // bias of the NEXT tile (column et), fetched one tile ahead
+        if (et < BN && (int)blockIdx.x < num_items) pf_bias = bias_of(((int)blockIdx.x % p.splits) * p.nt_per * BN);
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int m_tile = item / p.splits, split = item % p.splits;
+            const int row = m_tile * BM + ew * 32 + lane;
+            const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
+            float rm = -INFINITY, rs = 0.f, rs2 = 0.f, xb = 0.f;
+            int best = 0x7fffffff;
+            for (int nt = nb; nt < ne; ++nt) {
+                const int n0 = nt * BN;
+                float* sb = s_bias + bbuf * BN;
+                if (et < BN) {
+                    sb[et] = pf_bias;
+                    const int nxt_item = item + (int)gridDim.x;
+                    if (nt + 1 < ne) pf_bias = bias_of((nt + 1) * BN);
+                    else if (nxt_item < num_items) pf_bias = bias_of((nxt_item % p.splits) * p.nt_per * BN);
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(kWideEpiThreads) : "memory");
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+
+                auto process = [&](uint32_t (&v)[16], int sub) {   // sub = index of the 16-column slab in the tile
+                    const int base = n0 + sub * 16;
+                    if (base >= p.N) return;
+                    const float4* b4 = reinterpret_cast<const float4*>(sb + sub * 16);
+                    float x[16];
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = b4[q];
+                        x[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
+                        x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+                        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+                        x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+                        cm = fmaxf(cm, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
+                    }
+                    if (cm > rm) {
+                        const float f = ex2_approx((rm - cm) * kL2e);      // rm = -inf on the first slab: 2^-inf = 0
+                        rs *= f;
+                        rs2 *= f * f;
+                        rm = cm;
+                        int j0 = 15;
+#pragma unroll
+                        for (int j = 14; j >= 0; --j) j0 = (x[j] == cm) ? j : j0;
+                        best = base + j0;                          // first index of the maximum (torch tie rule)
+                    }
+                    const float mb = rm * kL2e;
+                    float acc_s = 0.f, acc_s2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float e = ex2_approx(fmaf(x[j], kL2e, -mb));
+                        acc_s += e;
+                        acc_s2 = fmaf(e, e, acc_s2);
+                    }
+                    rs += acc_s;
+                    rs2 += acc_s2;
+                    if (p.blank >= base && p.blank < base + 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xb = (base + j == p.blank) ? x[j] : xb;
+                    }
+                };
+
+                uint32_t va[16], vb[16];
+                const int sub0 = quarter * 4, sub1 = sub0 + 4;             // this warp's four 16-column slabs
+                tmem_ld16(t_row + (uint32_t)(sub0 * 16), va);
+#pragma unroll 1
+                for (int sub = sub0; sub < sub1; sub += 2) {
+                    tmem_ld_wait16(va);
+                    tmem_ld16(t_row + (uint32_t)((sub + 1) * 16), vb);
+                    process(va, sub);
+                    tmem_ld_wait16(vb);
+                    if (sub + 2 < sub1) tmem_ld16(t_row + (uint32_t)((sub + 2) * 16), va);
+                    else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+                    process(vb, sub + 1);
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                bbuf ^= 1;
+            }
+            if (row < p.M) {
+                const int64_t o = (int64_t)(split * 4 + quarter) * p.M + row;  // ascending column order of the partials
+                p.part_max[o] = rm;
+                p.part_sum[o] = rs;
+                p.part_sum2[o] = rs2;
+                p.part_arg[o] = best;
+                const int bt = p.blank / BN, bq = (p.blank % BN) / (BN / 4);
+                if (bt >= nb && bt < ne && bq == quarter) p.xb_raw[row] = xb;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
 // merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
 __global__ void __launch_bounds__(256)
 ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __restrict__ argmax,
@@ -653,6 +860,34 @@ ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __r
     const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
     float m = -INFINITY; int a = 0x7fffffff;
     const int parts = 2 * p.splits;                                        // (split, column half), ascending columns
+    for (int s = 0; s < parts; ++s) {
+        const float pm = p.part_max[(int64_t)s * p.M + r];
+        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
+    }
+    float sum = 0.f, sum2 = 0.f;
+    for (int s = 0; s < parts; ++s) {
+        const float f = exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
+        sum += p.part_sum[(int64_t)s * p.M + r] * f;
+        sum2 += p.part_sum2[(int64_t)s * p.M + r] * f * f;
+    }
+    if (row_sumexp2) row_sumexp2[i] = sum2;
+    argmax[i] = a;
+    x_blank[i] = p.xb_raw[r];
+    row_max[i] = m;
+    row_sumexp[i] = sum;
+}
+
+// the same merge for ctc_stats_wide_kernel: four column quarters per split
+__global__ void __launch_bounds__(256)
+ctc_stats_combine_wide_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __restrict__ argmax,
+                              float* __restrict__ x_blank, float* __restrict__ row_max, float* __restrict__ row_sumexp,
+                              float* __restrict__ row_sumexp2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * T) return;
+    const int b = (int)(i / T), t = (int)(i % T);
+    const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
+    float m = -INFINITY; int a = 0x7fffffff;
+    const int parts = 4 * p.splits;                                        // (split, column quarter), ascending columns
     for (int s = 0; s < parts; ++s) {
         const float pm = p.part_max[(int64_t)s * p.M + r];
         if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
@@ -940,7 +1175,9 @@ static void pick_splits(int m_tiles, int n_tiles, int grid, int* splits, int* nt
 
 extern "C" int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix) {
     const int64_t rows = (int64_t)B * (T + n_prefix);
-    return rows * 16 * 16 + rows * 4 + 256;       // up to 16 splits x (max, sum, sum2, arg) + blank logits
+    // up to 32 partials per frame (8 vocabulary splits x 4 column quarters of the wide kernel; the default kernel uses
+    // 16 = 8 splits x 2 halves) x (max, sum, sum2, arg) + blank logits
+    return rows * 32 * 16 + rows * 4 + 256;
 }
 
 extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
@@ -975,12 +1212,15 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     p.M = M; p.N = V; p.K = K; p.blank = blank_id; p.bias = bias;
     pick_splits(m_tiles, n_tiles, grid, &p.splits, &p.nt_per);
     if (grid > m_tiles * p.splits) grid = m_tiles * p.splits;
+    // EXPERIMENTAL 16-epilogue-warp kernel (TASU_OPT_STATS_WIDE): four partials per split instead of two
+    const bool wide = option(TASU_OPT_STATS_WIDE) != 0 && !pair && K <= 8 * BK;
+    const int64_t cap = wide ? 32 : 16;                      // partial slots per frame in the workspace layout
     float* ws = reinterpret_cast<float*>(workspace);
     p.part_max = ws;
-    p.part_sum = ws + (int64_t)16 * M;
-    p.part_sum2 = ws + (int64_t)32 * M;
-    p.part_arg = reinterpret_cast<int32_t*>(ws + (int64_t)48 * M);
-    p.xb_raw = ws + (int64_t)64 * M;
+    p.part_sum = ws + cap * M;
+    p.part_sum2 = ws + 2 * cap * M;
+    p.part_arg = reinterpret_cast<int32_t*>(ws + 3 * cap * M);
+    p.xb_raw = ws + 4 * cap * M;
     cudaStream_t st = (cudaStream_t)stream;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -991,6 +1231,21 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     });
     TASU_CHECK_CUDA(attr_err);
     const bool prefetch = (option(TASU_OPT_EPI_PREFETCH) & 2) != 0;
+    if (wide) {
+        static std::once_flag once_wide;
+        static cudaError_t attr_err_wide = cudaSuccess;
+        std::call_once(once_wide, [&] {
+            attr_err_wide = cudaFuncSetAttribute(ctc_stats_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesARes);
+        });
+        TASU_CHECK_CUDA(attr_err_wide);
+        ctc_stats_wide_kernel<<<grid, kWideThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
+        TASU_CHECK_LAUNCH();
+        const int64_t frames_w = (int64_t)B * T;
+        ctc_stats_combine_wide_kernel<<<(unsigned)((frames_w + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max,
+                                                                                      row_sumexp, row_sumexp2);
+        TASU_CHECK_LAUNCH();
+        return TASU_OK;
+    }
     if (prefetch && !pair && K <= 8 * BK) {
         auto kern = ctc_stats_kernel<true, false, true>;
         static std::once_flag once_pf;

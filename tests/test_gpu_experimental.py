@@ -5,6 +5,7 @@ validated path; `tools/gpu_experimental.sh` runs them under a timeout.
   * CTA-pair GEMM (tasu_set_option(TASU_OPT_GEMM_PAIR, 1)): tcgen05.mma.cta_group::2, M = 256 per pair of CTAs.
   * stream-K GEMM (tasu_gemm_bf16_tn_streamk): the ragged last wave of tiles cut along K, fix-up through a workspace.
   * epilogue prefetch (tasu_set_option(TASU_OPT_EPI_PREFETCH, mask)): bias / row vectors of the next tile fetched early.
+  * 16-epilogue-warp fused CTC head (tasu_set_option(TASU_OPT_STATS_WIDE, 1)).
 """
 import os
 
@@ -323,3 +324,75 @@ def test_epilogue_prefetch_ctc_head_stats_is_bit_identical(dev, B, T, P, V, K, b
         ops.set_option(L.OPT_EPI_PREFETCH, 0)
     for name in ("argmax", "x_blank", "row_max", "row_sumexp", "row_sumexp2"):
         assert torch.equal(getattr(st0, name), getattr(st1, name)), name
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused CTC head + statistics with 16 epilogue warps (TASU_OPT_STATS_WIDE)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,P,V,K,blank", [(3, 37, 4, 25055, 512, 0), (2, 130, 4, 300, 64, 7), (1, 9, 0, 61, 32, 60),
+                                             (5, 300, 4, 4099, 512, 0), (64, 500, 4, 25055, 512, 0), (2, 100, 4, 25055, 512, 25054),
+                                             (2, 100, 4, 1000, 512, 200)])
+def test_wide_ctc_head_stats(dev, B, T, P, V, K, blank):
+    import numpy as np
+
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(V + T)
+    rows = B * (T + P)
+    x = (torch.randn(rows, K) * 0.7).bfloat16()
+    w = (torch.randn(V, K) * 0.6).bfloat16()
+    lab = torch.randint(0, V, (rows,))
+    x += (4.0 * w[lab].float() / w[lab].float().norm(dim=1, keepdim=True)).bfloat16()     # a clear winner per frame
+    xd = torch.zeros(rows, ops.pad_to(K), dtype=torch.bfloat16); xd[:, :K] = x
+    wd = torch.zeros(V, ops.pad_to(K), dtype=torch.bfloat16); wd[:, :K] = w
+    xd, wd, bd = xd.to(dev), wd.to(dev), (torch.randn(V) * 0.1).to(dev)
+    st0 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_STATS_WIDE, 1)
+    try:
+        st1 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+        st2 = ops.ctc_head_stats(xd, wd, bd, B, T, P, V, K, blank)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(L.OPT_STATS_WIDE, 0)
+    # same logits (one accumulator, ascending K): max / argmax / blank logit bit-equal; exp-sums associated by quarters
+    assert torch.equal(st1.argmax, st0.argmax) and torch.equal(st1.row_max, st0.row_max) and torch.equal(st1.x_blank, st0.x_blank)
+    np.testing.assert_allclose(st1.row_sumexp.cpu().numpy(), st0.row_sumexp.cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(st1.row_sumexp2.cpu().numpy(), st0.row_sumexp2.cpu().numpy(), rtol=1e-5)
+    for a, b in ((st1.argmax, st2.argmax), (st1.row_sumexp, st2.row_sumexp), (st1.row_sumexp2, st2.row_sumexp2)):
+        assert torch.equal(a, b), "back-to-back launches must agree bit for bit"
+
+
+def test_bridge_with_wide_stats_and_prefetch_matches_default_integers(dev):
+    """Whole inference bridge with the experimental epilogues: every integer output equals the default path."""
+    import types
+
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 8, 500
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=11, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=5, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    ref = [t.clone() if t is not None else None for t in br(*args)]
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_STATS_WIDE, 1)
+    ops.set_option(L.OPT_EPI_PREFETCH, 3)
+    try:
+        out = br(*args)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(L.OPT_STATS_WIDE, 0)
+        ops.set_option(L.OPT_EPI_PREFETCH, 0)
+    emb, mask_o, _, pos, new_lens = out
+    assert torch.equal(new_lens, ref[4]) and torch.equal(mask_o, ref[1]) and torch.equal(pos, ref[3])
+    err = ((emb.float() - ref[0].float()).norm() / ref[0].float().norm()).item()
+    assert err < 1e-3, err
