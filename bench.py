@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--epi-prefetch", type=int, default=0, metavar="MASK",
                     help="EXPERIMENTAL (DESIGN.md §9): epilogue vectors of the next tile fetched early, "
                          "tasu_set_option(TASU_OPT_EPI_PREFETCH, MASK): 1 = kept-frame softmax GEMM, 2 = fused CTC head, 3 = both")
+    ap.add_argument("--wide-epi", action="store_true",
+                    help="EXPERIMENTAL (DESIGN.md §9): kept-frame softmax GEMM with 16 independent epilogue warps "
+                         "(TASU_OPT_GEMM_WIDE_EPI)")
     ap.add_argument("--stats-wide", action="store_true",
                     help="EXPERIMENTAL (DESIGN.md §9): fused CTC head with 16 epilogue warps (TASU_OPT_STATS_WIDE)")
     ap.add_argument("--materialize-logits", action="store_true",
@@ -239,6 +242,9 @@ def b200_arm(args):
     if args.stats_wide:
         import ps_slm_b200._lib as L
         ops.set_option(L.OPT_STATS_WIDE, 1)
+    if args.wide_epi:
+        import ps_slm_b200._lib as L
+        ops.set_option(L.OPT_GEMM_WIDE_EPI, 1)
     host, devb = [], []
     for r in range(args.rotate):
         raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=1000 * rank + r)
@@ -385,7 +391,7 @@ def b200_arm(args):
                    "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
                    "experimental": [n for n, on in (("streamk_gemm1", bridge.streamk_gemm1), ("pair_gemm=%d" % args.pair_gemm, args.pair_gemm),
                                                              ("epi_prefetch=%d" % args.epi_prefetch, args.epi_prefetch),
-                                                             ("stats_wide", args.stats_wide)) if on],
+                                                             ("stats_wide", args.stats_wide), ("wide_epi", args.wide_epi)) if on],
                    "path": "materialized fp32 logits" if args.materialize_logits else "fused ctc_lo+stats, recompute kept frames",
                    "l2": "rotating %d distinct input batches (%.0f MB > 126 MB L2); per-step intermediates (%.2f GB) exceed L2"
                          % (args.rotate, args.rotate * in_bytes / 1e6,

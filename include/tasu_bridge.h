@@ -73,8 +73,11 @@ const char* tasu_last_error(void);
  *   tasu_ctc_head_stats.  Same values and arithmetic: results are bit-identical to the default kernels.
  *   TASU_OPT_STATS_WIDE (env TASU_STATS_WIDE): EXPERIMENTAL — tasu_ctc_head_stats (K <= 512) with 16 epilogue warps
  *   (four per scheduler, each a 64-column quarter of the tile read as 16-column TMEM slabs) instead of 8; sums are
- *   associated differently (quarters instead of halves): equal to the default kernel to fp32 rounding. */
-enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_STATS_WIDE = 2, TASU_OPT_COUNT = 3 };
+ *   associated differently (quarters instead of halves): equal to the default kernel to fp32 rounding.
+ *   TASU_OPT_GEMM_WIDE_EPI (env TASU_GEMM_WIDE_EPI): EXPERIMENTAL — tasu_gemm_bf16_tn with K <= 1024 and bf16 output
+ *   runs with 16 independent epilogue warps (each stages and TMA-stores its own 32 x 64 sub-tile, no barriers between
+ *   them, next tile's vectors prefetched).  Same arithmetic: results are bit-identical to the default kernel. */
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_STATS_WIDE = 2, TASU_OPT_GEMM_WIDE_EPI = 3, TASU_OPT_COUNT = 4 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */

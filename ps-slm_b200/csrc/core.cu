@@ -30,7 +30,7 @@ int sm_count() {
 }
 
 // run-time options (tasu_set_option); the initial value of option X comes from the environment variable named below
-static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR", "TASU_EPI_PREFETCH", "TASU_STATS_WIDE"};
+static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR", "TASU_EPI_PREFETCH", "TASU_STATS_WIDE", "TASU_GEMM_WIDE_EPI"};
 static std::atomic<int> g_options[TASU_OPT_COUNT];
 static std::once_flag g_options_once;
 

@@ -279,5 +279,9 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
     return TASU_OK;
 }
 
+// EXPERIMENTAL 16-epilogue-warp shallow-K GEMM (gemm_wide_sm100.cu), bf16 output
+int launch_wide_epi(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N, int K,
+                    const Params& p, cudaStream_t st);
+
 }  // namespace gemm
 }  // namespace tasu

@@ -1110,6 +1110,11 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     const int csz = c_dtype == TASU_F32 ? 4 : 2;
     TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
     TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
+    // EXPERIMENTAL 16-epilogue-warp kernel for the store-heavy shallow-K shapes with bf16 output (TASU_OPT_GEMM_WIDE_EPI)
+    if (option(TASU_OPT_GEMM_WIDE_EPI) != 0 && K <= 1024 && c_dtype == TASU_BF16) {
+        Params pw{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
+        return launch_wide_epi(A, lda, B, ldb, C, ldc, M, N, K, pw, (cudaStream_t)stream);
+    }
     // EXPERIMENTAL CTA-pair mode (off unless TASU_OPT_GEMM_PAIR is set; bit 0: deep-K shapes, bit 1: K <= 1024),
     // for problems with more than one 128-row tile
     const int pair_opt = option(TASU_OPT_GEMM_PAIR);

@@ -117,6 +117,7 @@ def test_options_default_off_and_validated(lib):
     assert ops.get_option(L.OPT_GEMM_PAIR) == 0
     assert "TASU_EPI_PREFETCH" not in os.environ and ops.get_option(L.OPT_EPI_PREFETCH) == 0
     assert "TASU_STATS_WIDE" not in os.environ and ops.get_option(L.OPT_STATS_WIDE) == 0
+    assert "TASU_GEMM_WIDE_EPI" not in os.environ and ops.get_option(L.OPT_GEMM_WIDE_EPI) == 0
     assert lib.tasu_set_option(L.OPT_COUNT, 1) == -1 and b"unknown option" in lib.tasu_last_error()
     assert lib.tasu_get_option(-3) == -1
     with pytest.raises(L.TasuError):

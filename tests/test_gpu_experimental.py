@@ -6,6 +6,7 @@ validated path; `tools/gpu_experimental.sh` runs them under a timeout.
   * stream-K GEMM (tasu_gemm_bf16_tn_streamk): the ragged last wave of tiles cut along K, fix-up through a workspace.
   * epilogue prefetch (tasu_set_option(TASU_OPT_EPI_PREFETCH, mask)): bias / row vectors of the next tile fetched early.
   * 16-epilogue-warp fused CTC head (tasu_set_option(TASU_OPT_STATS_WIDE, 1)).
+  * 16-independent-epilogue-warp shallow-K GEMM (tasu_set_option(TASU_OPT_GEMM_WIDE_EPI, 1)).
 """
 import os
 
@@ -363,7 +364,7 @@ def test_wide_ctc_head_stats(dev, B, T, P, V, K, blank):
         assert torch.equal(a, b), "back-to-back launches must agree bit for bit"
 
 
-def test_bridge_with_wide_stats_and_prefetch_matches_default_integers(dev):
+def test_bridge_with_wide_ctc_head_and_vectors_ahead_matches_default_integers(dev):
     """Whole inference bridge with the experimental epilogues: every integer output equals the default path."""
     import types
 
@@ -396,3 +397,65 @@ def test_bridge_with_wide_stats_and_prefetch_matches_default_integers(dev):
     assert torch.equal(new_lens, ref[4]) and torch.equal(mask_o, ref[1]) and torch.equal(pos, ref[3])
     err = ((emb.float() - ref[0].float()).norm() / ref[0].float().norm()).item()
     assert err < 1e-3, err
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# shallow-K GEMM with 16 independent epilogue warps (TASU_OPT_GEMM_WIDE_EPI): bf16 output, bit-identical
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512),
+                                   (11330, 4099, 512), (5, 40, 136), (1, 8, 8), (3000, 70, 512)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4, 5, 6])
+def test_widegemm_epilogue_is_bit_identical(dev, M, N, K, epi):
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8) + 8
+    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    C0 = torch.full((M, ldc), -777.0, dtype=torch.bfloat16, device=dev)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C0, epi, *vec)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_WIDE_EPI, 1)
+    try:
+        outs = []
+        for _ in range(2):
+            C1 = torch.full((M, ldc), -777.0, dtype=torch.bfloat16, device=dev)
+            ops.gemm_bf16_tn(Ad, Bd, M, N, K, C1, epi, *vec)
+            torch.cuda.synchronize()
+            outs.append(C1)
+    finally:
+        ops.set_option(L.OPT_GEMM_WIDE_EPI, 0)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(C0[:, :N], outs[0][:, :N]), "same arithmetic per element: bit-identical to the default kernel"
+    pad = outs[0][:, N:].float().cpu()
+    assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
+    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    scale = ref.abs().max().item() + 1e-6
+    assert (outs[0].cpu()[:, :N].double() - ref).abs().max().item() / scale < 6e-3
+
+
+def test_widegemm_device_side_row_count(dev):
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(3)
+    M, N, K = 2048, 1000, 512
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    ref = A.float() @ B.float().T
+    ops.set_option(L.OPT_GEMM_WIDE_EPI, 1)
+    try:
+        for live in (0, 1, 128, 129, 700, 2048):
+            C = torch.full((M, ops.pad_to(N, 8)), -5.0, dtype=torch.bfloat16, device=dev)
+            m_dev = torch.tensor([live], dtype=torch.int32, device=dev)
+            ops.gemm_bf16_tn(A, B, M, N, K, C, m_dev=m_dev)
+            torch.cuda.synchronize()
+            if live:
+                assert (C[:live, :N].float() - ref[:live]).abs().max().item() / ref.abs().max().item() < 6e-3
+            tiles = (live + 127) // 128
+            assert bool((C[min(M, tiles * 128):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
+    finally:
+        ops.set_option(L.OPT_GEMM_WIDE_EPI, 0)

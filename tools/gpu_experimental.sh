@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 export TASU_EXPERIMENTAL=1
 : > gpurun_out/rc_experimental.txt
 declare -A OK
-for group in prefetch wide streamk pair; do
+for group in prefetch wide_ctc widegemm streamk pair; do
     timeout 420 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 -k "$group" \
         > gpurun_out/t_experimental_$group.log 2>&1
     rc=$?
@@ -33,7 +33,8 @@ fi
 FLAGS=("")
 ALL=""
 [ "${OK[prefetch]}" = 0 ] && FLAGS+=("--epi-prefetch 1" "--epi-prefetch 2" "--epi-prefetch 3") && ALL="$ALL --epi-prefetch 3"
-[ "${OK[wide]}" = 0 ] && FLAGS+=("--stats-wide") && ALL="${ALL/--epi-prefetch 3/--epi-prefetch 1} --stats-wide"
+[ "${OK[wide_ctc]}" = 0 ] && FLAGS+=("--stats-wide") && ALL="${ALL/--epi-prefetch 3/--epi-prefetch 1} --stats-wide"
+[ "${OK[widegemm]}" = 0 ] && FLAGS+=("--wide-epi") && ALL="${ALL/--epi-prefetch 1/} --wide-epi"
 [ "${OK[streamk]}" = 0 ] && FLAGS+=("--streamk") && ALL="$ALL --streamk"
 [ "${OK[pair]}" = 0 ] && FLAGS+=("--pair-gemm 1" "--pair-gemm 2" "--pair-gemm 4" "--pair-gemm 7")
 [ -n "$ALL" ] && FLAGS+=("$ALL")
