@@ -32,8 +32,25 @@ def pair_mode():
     ops.set_option(L.OPT_GEMM_PAIR, 0)
 
 
-def _ref(A, B, epi, bias, rstd, mean, colsum):
-    acc = A.float().double() @ B.float().double().T
+_PROBLEM = {}
+
+
+def _problem(M, N, K):
+    """bf16 operands (padded pitches, garbage beyond K) and their fp64 product; the last shape is kept so that the
+    epilogue variants of one shape (the fastest-varying test parameter) share the expensive reference product."""
+    import ps_slm_b200.ops as ops
+    key = (M, N, K)
+    if key not in _PROBLEM:
+        _PROBLEM.clear()
+        torch.manual_seed(M + 3 * N + 7 * K)
+        lda, ldb = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8)
+        A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+        B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+        _PROBLEM[key] = (A, B, A[:, :K].float().double() @ B[:, :K].float().double().T)
+    return _PROBLEM[key]
+
+
+def _ref(acc, epi, bias, rstd, mean, colsum):
     if epi in (4, 5):
         z = rstd.double()[:, None] * (acc - mean.double()[:, None] * colsum.double()[None, :]) + bias.double()[None, :]
         return torch.nn.functional.silu(z) if epi == 4 else z
@@ -55,9 +72,9 @@ PAIR_SHAPES = [(256, 256, 1088), (129, 8, 1032), (300, 260, 1100), (257, 1536, 2
                (256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512)]
 
 
-@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
 @pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (3, torch.bfloat16),
                                            (4, torch.bfloat16), (5, torch.float32), (6, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
 def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtype):
     """The CTA-pair kernel accumulates every output element in the same order as the default kernel (one TMEM
     accumulator, K blocks in ascending order), so the two must agree BIT FOR BIT; both are checked against fp64."""
@@ -65,10 +82,9 @@ def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtyp
     import ps_slm_b200.ops as ops
     if (K > 20000 or N > 20000) and epi not in (1, 4, 6):
         pytest.skip("large shapes: a subset of epilogues is enough")
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8)
     torch.manual_seed(M + 3 * N + 7 * K + epi)
-    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
-    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
-    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
     mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))     # softmax: a plausible row max
     Ad, Bd = A.to(dev), B.to(dev)
@@ -81,7 +97,7 @@ def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtyp
     C0 = torch.full((M, ldc), -777.0, dtype=out_dtype, device=dev)
     ops.gemm_bf16_tn(Ad, Bd, M, N, K, C0, epi, *vec)
     torch.cuda.synchronize()
-    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
     got = C.cpu()
     pad = got[:, N:].float()
     assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
@@ -167,17 +183,16 @@ SK_SHAPES = [(8341, 2048, 4096), (300, 512, 2048), (128 * 37, 1024, 1088), (128 
              (130, 260, 72), (257, 1536, 2048), (5, 40, 64)]
 
 
-@pytest.mark.parametrize("M,N,K", SK_SHAPES)
 @pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
                                            (6, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", SK_SHAPES)
 def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
     import ps_slm_b200.ops as ops
     if K > 20000 and epi not in (1, 4):
         pytest.skip("large K: a subset of epilogues is enough")
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8)
     torch.manual_seed(M + 3 * N + 7 * K + epi)
-    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
-    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
-    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
     mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
     Ad, Bd = A.to(dev), B.to(dev)
@@ -189,7 +204,7 @@ def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
         torch.cuda.synchronize()
         outs.append(C)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), "fixed summation order: deterministic"
-    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
     got = outs[0].cpu()
     pad = got[:, N:].float()
     assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
@@ -276,16 +291,15 @@ def test_pair_ctc_head_stats(dev, B, T, P, V, K, blank):
 # ---------------------------------------------------------------------------------------------------------------
 # epilogue vectors fetched one tile ahead (TASU_OPT_EPI_PREFETCH): same values, same arithmetic → bit-identical
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512), (11330, 4099, 512), (5, 40, 136)])
 @pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
                                            (5, torch.float32), (6, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512), (11330, 4099, 512), (5, 40, 136)])
 def test_epilogue_prefetch_gemm_is_bit_identical(dev, M, N, K, epi, out_dtype):
     import ps_slm_b200._lib as L
     import ps_slm_b200.ops as ops
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8)
     torch.manual_seed(M + 3 * N + 7 * K + epi)
-    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8)
-    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
-    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
     mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
     Ad, Bd = A.to(dev), B.to(dev)
@@ -301,7 +315,7 @@ def test_epilogue_prefetch_gemm_is_bit_identical(dev, M, N, K, epi, out_dtype):
     finally:
         ops.set_option(L.OPT_EPI_PREFETCH, 0)
     assert torch.equal(C0, C1)
-    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
     scale = ref.abs().max().item() + 1e-6
     assert (C1.cpu()[:, :N].double() - ref).abs().max().item() / scale < (1e-4 if out_dtype == torch.float32 else 6e-3)
 
@@ -402,16 +416,15 @@ def test_bridge_with_wide_ctc_head_and_vectors_ahead_matches_default_integers(de
 # ---------------------------------------------------------------------------------------------------------------
 # shallow-K GEMM with 16 independent epilogue warps (TASU_OPT_GEMM_WIDE_EPI): bf16 output, bit-identical
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 64), (130, 260, 72), (200, 300, 1000), (900, 25055, 512),
                                    (11330, 4099, 512), (5, 40, 136), (1, 8, 8), (3000, 70, 512)])
-@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4, 5, 6])
 def test_widegemm_epilogue_is_bit_identical(dev, M, N, K, epi):
     import ps_slm_b200._lib as L
     import ps_slm_b200.ops as ops
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8) + 8
     torch.manual_seed(M + 3 * N + 7 * K + epi)
-    lda, ldb, ldc = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8), ops.pad_to(N, 8) + 8
-    A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
-    B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
     bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
     mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
     Ad, Bd = A.to(dev), B.to(dev)
@@ -433,7 +446,7 @@ def test_widegemm_epilogue_is_bit_identical(dev, M, N, K, epi):
     assert torch.equal(C0[:, :N], outs[0][:, :N]), "same arithmetic per element: bit-identical to the default kernel"
     pad = outs[0][:, N:].float().cpu()
     assert bool(((pad == -777.0) | (pad == 0.0)).all()), "pad columns must be untouched or zero"
-    ref = _ref(A[:, :K], B[:, :K], epi, bias, rstd, mean, colsum)
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
     scale = ref.abs().max().item() + 1e-6
     assert (outs[0].cpu()[:, :N].double() - ref).abs().max().item() / scale < 6e-3
 

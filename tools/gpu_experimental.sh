@@ -2,14 +2,14 @@
 # One GPU call for the paths that are written but not yet validated on a B200 (tests/test_gpu_experimental.py,
 # DESIGN.md §9).  Every feature is tested on its own (a hang or failure in one new kernel must not hide the others),
 # every pytest run has a per-test timeout, and the headline bench is A/B'd only with the features whose tests passed.
-#   bash tools/gpu_experimental.sh            (under gpurun: give the call ~25 minutes)
+#   bash tools/gpu_experimental.sh            (under gpurun: give the call ~40 minutes; each group is capped at 15)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export TASU_EXPERIMENTAL=1
 : > gpurun_out/rc_experimental.txt
 declare -A OK
 for group in prefetch wide_ctc widegemm streamk pair; do
-    timeout 420 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 -k "$group" \
+    timeout 900 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 -k "$group" \
         > gpurun_out/t_experimental_$group.log 2>&1
     rc=$?
     echo "$group rc=$rc" >> gpurun_out/rc_experimental.txt
