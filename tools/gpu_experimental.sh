@@ -29,6 +29,22 @@ if [ "${OK[pair]}" = 0 ] && [ "${OK[streamk]}" = 0 ]; then
     cat gpurun_out/pair_gemm.md
 fi
 
+# optional (SANITIZE=1): compute-sanitizer memcheck + racecheck over one small case of every group that passed
+if [ "${SANITIZE:-0}" = 1 ]; then
+    declare -A SMALL=( [prefetch]="prefetch_gemm and 130-260-72" [wide_ctc]="wide_ctc_head_stats and 2-130-4-300-64-7"
+                       [widegemm]="widegemm_epilogue and 130-260-72" [streamk]="streamk_gemm and 300-512-2048 and not device"
+                       [pair]="pair_gemm_matches and 300-260-1100" )
+    for group in prefetch wide_ctc widegemm streamk pair; do
+        [ "${OK[$group]}" = 0 ] || continue
+        for tool in memcheck racecheck; do
+            timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_experimental.py -q -m gpu \
+                -k "${SMALL[$group]}" > gpurun_out/sanitize_${group}_$tool.log 2>&1
+            echo "$group $tool rc=$?" >> gpurun_out/rc_experimental.txt
+            grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/sanitize_${group}_$tool.log | tail -2
+        done
+    done
+fi
+
 # A/B of the headline bench: default, then every validated feature alone, then all validated features together
 FLAGS=("")
 ALL=""
