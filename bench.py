@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--exact-decisions", action="store_true",
                     help="refine the frames whose greedy decisions lie inside the bf16 noise of the fused head with the "
                          "fp32-accurate GEMM (TasuBridge.exact_decisions)")
+    ap.add_argument("--host-bf16", action="store_true",
+                    help="encoder output handed over as bf16 instead of fp32 (halves the H2D bytes of e2e and skips the cast "
+                         "kernel; the kernels compute on the same bf16 values either way). Off by default: the reference's "
+                         "encoder output is fp32")
     ap.add_argument("--streamk", action="store_true",
                     help="EXPERIMENTAL (DESIGN.md §9): projector GEMM-1 with the stream-K tail (tasu_gemm_bf16_tn_streamk)")
     ap.add_argument("--pair-gemm", type=int, default=0, metavar="MASK",
@@ -248,6 +252,8 @@ def b200_arm(args):
     host, devb = [], []
     for r in range(args.rotate):
         raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=1000 * rank + r)
+        if args.host_bf16:
+            raw = raw.bfloat16()
         ids, mask, _ = S.make_prompts(B, seed=1000 * rank + r, left_pad=True)
         hb = tuple(t.pin_memory() for t in (raw, raw_lens, ids, mask))
         host.append(hb)
@@ -389,6 +395,7 @@ def b200_arm(args):
                    "batch_per_gpu": B, "frames_per_utt": T, "V": V, "compressed_rows_per_step": n_out,
                    "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
                    "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
+                   "encoder_out_dtype": "bf16" if args.host_bf16 else "f32",
                    "experimental": [n for n, on in (("streamk_gemm1", bridge.streamk_gemm1), ("pair_gemm=%d" % args.pair_gemm, args.pair_gemm),
                                                              ("epi_prefetch=%d" % args.epi_prefetch, args.epi_prefetch),
                                                              ("stats_wide", args.stats_wide), ("wide_epi", args.wide_epi)) if on],

@@ -472,3 +472,28 @@ def test_widegemm_device_side_row_count(dev):
             assert bool((C[min(M, tiles * 128):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
     finally:
         ops.set_option(L.OPT_GEMM_WIDE_EPI, 0)
+
+
+def test_bridge_bf16_encoder_output_equals_fp32_input(dev):
+    """bench.py --host-bf16: handing the encoder output over as bf16 skips the cast kernel; the kernels see the same
+    bf16 values, so every output is bit-identical to the fp32-input call."""
+    import types
+
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 6, 300
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=21, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=7, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    tail = (raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    out32 = [t.clone() if t is not None else None for t in br(raw.to(dev), *tail)]
+    out16 = br(raw.bfloat16().to(dev), *tail)
+    torch.cuda.synchronize()
+    for a, c in zip(out32, out16):
+        assert (a is None and c is None) or torch.equal(a, c)

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 export TASU_EXPERIMENTAL=1
 : > gpurun_out/rc_experimental.txt
 declare -A OK
-for group in prefetch wide_ctc widegemm streamk pair; do
+for group in bf16_encoder prefetch wide_ctc widegemm streamk pair; do
     timeout 900 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 -k "$group" \
         > gpurun_out/t_experimental_$group.log 2>&1
     rc=$?
@@ -48,6 +48,7 @@ fi
 # A/B of the headline bench: default, then every validated feature alone, then all validated features together
 FLAGS=("")
 ALL=""
+[ "${OK[bf16_encoder]}" = 0 ] && FLAGS+=("--host-bf16")
 [ "${OK[prefetch]}" = 0 ] && FLAGS+=("--epi-prefetch 1" "--epi-prefetch 2" "--epi-prefetch 3") && ALL="$ALL --epi-prefetch 3"
 [ "${OK[wide_ctc]}" = 0 ] && FLAGS+=("--stats-wide") && ALL="${ALL/--epi-prefetch 3/--epi-prefetch 1} --stats-wide"
 [ "${OK[widegemm]}" = 0 ] && FLAGS+=("--wide-epi") && ALL="${ALL/--epi-prefetch 1/} --wide-epi"
