@@ -92,6 +92,17 @@ def test_model_rejects_nothing_silently_on_cpu():
     (7, 17, 148), (1, 1, 148), (3, 2, 148), (149, 1, 148), (37, 5, 8), (0, 9, 148), (1000, 33, 7),
 ])
 def test_streamk_schedule_covers_every_k_block_once(num_tiles, k_blocks, grid):
+    _check_streamk_schedule(num_tiles, k_blocks, grid)
+
+
+def test_streamk_schedule_random_problems():
+    rng = np.random.default_rng(7)
+    for _ in range(150):
+        grid = int(rng.choice([1, 2, 7, 16, 74, 132, 148]))
+        _check_streamk_schedule(int(rng.integers(0, 6 * grid + 3)), int(rng.integers(1, 400)), grid)
+
+
+def _check_streamk_schedule(num_tiles, k_blocks, grid):
     import ps_slm_b200.ops as ops
     FULL, CONTRIB, FINISH = 0, 1, 2
     dp_tiles, per_cta = ops.streamk_schedule(num_tiles, k_blocks, grid)
