@@ -235,20 +235,14 @@ def b200_arm(args):
     bridge = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
     bridge.materialize_logits = args.materialize_logits
     bridge.exact_decisions = args.exact_decisions
+    # experimental switches: all off unless asked for
+    import ps_slm_b200._lib as L
     if args.streamk:
         bridge.streamk_gemm1 = True
-    if args.pair_gemm:
-        import ps_slm_b200._lib as L
-        ops.set_option(L.OPT_GEMM_PAIR, args.pair_gemm)
-    if args.epi_prefetch:
-        import ps_slm_b200._lib as L
-        ops.set_option(L.OPT_EPI_PREFETCH, args.epi_prefetch)
-    if args.stats_wide:
-        import ps_slm_b200._lib as L
-        ops.set_option(L.OPT_STATS_WIDE, 1)
-    if args.wide_epi:
-        import ps_slm_b200._lib as L
-        ops.set_option(L.OPT_GEMM_WIDE_EPI, 1)
+    for opt, val in ((L.OPT_GEMM_PAIR, args.pair_gemm), (L.OPT_EPI_PREFETCH, args.epi_prefetch),
+                     (L.OPT_STATS_WIDE, int(args.stats_wide)), (L.OPT_GEMM_WIDE_EPI, int(args.wide_epi))):
+        if val:
+            ops.set_option(opt, val)
     host, devb = [], []
     for r in range(args.rotate):
         raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=1000 * rank + r)
