@@ -220,7 +220,7 @@ gemm_wide_epi_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             fence_proxy_async_smem();                              // this lane's st.shared before the TMA store reads them
             __syncwarp();
             if (lane == 0) {
-                if (live) tma_store_2d(&tmap_c, wstage, c0, m0 + ew * 32);
+                if (live && m0 + ew * 32 < p.M) tma_store_2d(&tmap_c, wstage, c0, m0 + ew * 32);   // box inside the matrix
                 tma_store_commit();
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
