@@ -38,9 +38,11 @@ def parse():
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (defeats L2 reuse)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exact-decisions", action="store_true",
-                    help="refine the frames whose greedy decisions lie inside the bf16 noise of the fused head with the "
-                         "fp32-accurate GEMM (TasuBridge.exact_decisions)")
+    ap.add_argument("--no-exact-decisions", dest="exact_decisions", action="store_false",
+                    help="take the greedy decisions straight from the bf16 head (default: frames whose decisions lie inside "
+                         "the rounding-error bound of the bf16 head are recomputed in fp32, TasuBridge.exact_decisions)")
+    ap.add_argument("--exact-decisions", dest="exact_decisions", action="store_true", help="(default)")
+    ap.set_defaults(exact_decisions=True)
     ap.add_argument("--host-bf16", action="store_true",
                     help="encoder output handed over as bf16 instead of fp32 (halves the H2D bytes of e2e and skips the cast "
                          "kernel; the kernels compute on the same bf16 values either way). Off by default: the reference's "

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TASU_ABI_VERSION 1
+#define TASU_ABI_VERSION 2
 
 enum { TASU_OK = 0, TASU_ERR_INVALID_ARG = -1, TASU_ERR_CUDA = -2, TASU_ERR_UNSUPPORTED = -3 };
 enum { TASU_F32 = 0, TASU_BF16 = 1 };
@@ -118,20 +118,32 @@ int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float*
                        int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
                        int32_t* kept_frames, int32_t* seg_frame_off, void* stream);
 
-/* Exact-decision mode of the fused CTC head (tasu_ctc_head_stats computes logits from bf16 operands): list the frames
- * whose greedy decisions lie inside the bf16 noise — argmax probability < p_max_min (possible near-tie) or a blank frame
- * with |p_blank - threshold| < band — as (frame index, raw encoder row) pairs (count zeroed, unused slots = -1); the
- * caller recomputes their logits with the fp32-accurate GEMM (tasu_split_bf16x3 + tasu_gemm_bf16_tn + tasu_sum_epilogue),
- * takes tasu_frame_stats of them and writes the statistics back with tasu_scatter_frame_stats before
- * tasu_collapse_plan, so run boundaries and keep/drop decisions equal the fp32 reference (ps-slm.py:265, :295-297). */
+/* Exact-decision mode of the fused CTC head.  tasu_ctc_head_stats computes its logits from bf16 operands, so a logit
+ * differs from the fp32 one (ctc_lo of ps-slm.py:450, :581) by at most delta_f = ||x_f|| * max_v ||w_v|| * err_scale
+ * (err_scale = 2^-8: both operands rounded to 8 significant bits; 2^-9 when the encoder rows were GIVEN in bf16).  The
+ * greedy decisions of a frame — argmax (ps-slm.py:265) and the strict fp32 `score < threshold` test (:295-297) — can only
+ * differ from the fp32 reference when their margin is below 2*delta_f.  tasu_flag_ambiguous_frames lists those frames:
+ * top-2 logit gap (bounded from p1 = 1/row_sumexp and p2 <= min(1 - p1, sqrt(sum p^2 - p1^2))) below the margin, a blank
+ * frame with |logit(p_blank) - logit(threshold)| below it, a non-blank frame whose blank probability could reach the
+ * threshold.  The list has one slot per frame (no cap, nothing can be dropped): frame_idx / raw_row [B*T] int32,
+ * count [1] int32 (zeroed by the call).  dec_max / dec_sum [B*T] receive a copy of row_max / row_sumexp: the normalisers
+ * the collapse plan uses (tasu_collapse_plan), kept apart from the bf16-consistent ones pass 2 needs.
+ *   x [B*(T+n_prefix), ldx] the encoder rows (fp32 or bf16), w_norm_max_enc [1] from tasu_row_norm_max.
+ * tasu_ctc_head_refine recomputes the listed frames with fp32 FMAs from the fp32 weights (every dot product in ascending
+ * k), for all `*count` frames, in-kernel, and writes argmax / x_blank / dec_max / dec_sum of those frames. */
+int tasu_row_norm_max(const void* w, int dtype, int rows, int cols, int64_t ld,
+                      uint32_t* out_enc /*[1] order-preserving encoding of max_r ||w_r||_2; zeroed by the call*/, void* stream);
 int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_blank, const float* row_max,
-                               const float* row_sumexp, const int64_t* lens, int B, int T, int n_prefix,
-                               int blank_id, float threshold, float p_max_min, float band, int cap,
-                               int32_t* frame_idx, int32_t* raw_row, int32_t* count, void* stream);
-int tasu_scatter_frame_stats(const int32_t* frame_idx, const int32_t* count, int cap, const int32_t* argmax_src,
-                             const float* x_blank_src, const float* row_max_src, const float* row_sumexp_src,
-                             int32_t* argmax, float* x_blank, float* row_max, float* row_sumexp,
-                             float* row_sumexp2, void* stream);
+                               const float* row_sumexp, const float* row_sumexp2 /*or NULL*/, const int64_t* lens,
+                               const void* x, int x_dtype, int64_t ldx, int K, const uint32_t* w_norm_max_enc,
+                               float err_scale, int B, int T, int n_prefix, int blank_id, float threshold,
+                               float* dec_max, float* dec_sum, int32_t* frame_idx, int32_t* raw_row, int32_t* count,
+                               void* stream);
+int64_t tasu_ctc_head_refine_workspace(int64_t max_frames);
+int tasu_ctc_head_refine(const void* x, int x_dtype, int64_t ldx, const float* w_f32, int64_t ldw, const float* bias,
+                         int V, int K, int blank_id, const int32_t* frame_idx, const int32_t* raw_row,
+                         const int32_t* count, int64_t max_frames /*list capacity = B*T*/, int32_t* argmax, float* x_blank,
+                         float* dec_max, float* dec_sum, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* exclusive scans: new_lens → row_off [B+1] int32, kept_frames → frame_off [B+1] int32 (optional);
  * header [TASU_CH_WORDS] int64 */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtasu_bridge.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 TASU_OK = 0
+ABI_VERSION = 2
 F32, BF16 = 0, 1
 INPUT_PROBS, INPUT_LOGITS = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, EPI_SOFTMAX = 0, 1, 2, 3, 4, 5, 6
@@ -30,8 +31,10 @@ SIGNATURES = {
     "tasu_get_option": (_I, [_I]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
-    "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
-    "tasu_scatter_frame_stats": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_row_norm_max": (_I, [_P, _I, _I, _I, _L, _P, _P]),
+    "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _F, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "tasu_ctc_head_refine_workspace": (_L, [_L]),
+    "tasu_ctc_head_refine": (_I, [_P, _I, _L, _P, _L, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _F, _P]),
@@ -112,7 +115,7 @@ def lib():
         fn = getattr(handle, name)          # AttributeError here = header and library out of sync
         fn.restype = res
         fn.argtypes = args
-    if handle.tasu_abi_version() != 1:
+    if handle.tasu_abi_version() != ABI_VERSION:
         raise TasuError("libtasu_bridge.so ABI version mismatch")
     _lib = handle
     return _lib

@@ -380,12 +380,13 @@ class TasuBridge:
         self._ctc_cache = ProjectorCache()
         self._capacity = {}           # (B, T) → (kept-frame rows, packed rows) the tail buffers are sized for
         self.last_counts = {}
-        # True: frames whose greedy decisions lie inside the bf16 noise of the fused head (near-tie argmax, blank
-        # probability within 0.02 of the drop threshold) are recomputed with the fp32-accurate GEMM before the collapse
-        # plan, so indices / run boundaries equal the fp32 reference even on adversarial inputs (+6 small launches)
-        self.exact_decisions = False
+        # Exact decisions (default): the frames whose greedy decisions — argmax (ps-slm.py:265), strict fp32 blank
+        # threshold (:295-297) — lie inside the rounding-error bound of the bf16 head are recomputed with fp32 FMAs from the
+        # fp32 weights before the collapse plan (csrc/refine.cu), so every index / run boundary / kept row equals the fp32
+        # reference.  Per-frame bound, uncapped list, cost proportional to the number of such frames (3 small launches when
+        # there are none).  False: decisions straight from the bf16 head.
+        self.exact_decisions = True
         self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
-        self._ctc_split_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         # EXPERIMENTAL (not yet validated on a GPU): projector GEMM-1 with the stream-K tail
         self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK") == "1"
@@ -430,6 +431,28 @@ class TasuBridge:
             return w, b
         return self._ctc_cache.get([self.w_ctc, self.b_ctc], build)
 
+    def _ctc_exact_weights(self):
+        """fp32 weights of the CTC head + max_v ||w_v|| (device scalar) for the exact-decision refinement."""
+        def build():
+            w = self.w_ctc.detach()
+            w = w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+            return w, ops.row_norm_max(w)
+        return self._ctc_exact_cache.get([self.w_ctc], build)
+
+    def _head_stats(self, raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V):
+        """(a1 + the decisions of a2) fused CTC head statistics, refined to fp32-exact decisions when asked for."""
+        with self._stage("ctc_head_stats"):
+            st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
+        if self.exact_decisions:
+            with self._stage("refine_ambiguous"):
+                w32, wnorm = self._ctc_exact_weights()
+                rows = raw_encoder_out.reshape(B * (T + self.N_PREFIX), Denc)
+                if rows.dtype not in (torch.float32, torch.bfloat16):
+                    rows = rows.float()
+                self.last_ambiguous = ops.refine_ambiguous_frames(st, lens, rows, w32, b_ctc, wnorm, T, self.N_PREFIX, V,
+                                                                  self.blank_id, self.blank_threshold)
+        return st
+
     @torch.no_grad()
     def __call__(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor,
                  input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: Optional[torch.Tensor] = None,
@@ -468,15 +491,7 @@ class TasuBridge:
                 st = ops.frame_stats(post_view, L.INPUT_LOGITS, self.blank_id, lens)
         else:
             # (a1+a2) fused: logits live only in TMEM, softmax statistics come out of the GEMM epilogue
-            with self._stage("ctc_head_stats"):
-                st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
-            if self.exact_decisions and raw_encoder_out.dtype == torch.float32:
-                with self._stage("refine_ambiguous"):
-                    w_split, k_split = self._ctc_split_cache.get(
-                        [self.w_ctc], lambda: ops.split_bf16x3(self.w_ctc.detach().float(), 1)[:2])
-                    self.last_ambiguous = ops.refine_ambiguous_frames(
-                        st, lens, raw_encoder_out.reshape(B * T4, Denc), w_split, k_split, b_ctc, T, self.N_PREFIX, V,
-                        self.blank_id, self.blank_threshold)
+            st = self._head_stats(raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V)
 
         # (a2) collapse plan, (a8) splice plan; one header for both
         with self._stage("collapse_plan"):
@@ -549,7 +564,7 @@ class TasuBridge:
             x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
         header = self._header_slot()
-        st = ops.ctc_head_stats(x2, w_ctc, b_ctc, B, T, self.N_PREFIX, V, Denc, self.blank_id)
+        st = self._head_stats(raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V)
         plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
         ev = torch.cuda.Event()
         ev.record()

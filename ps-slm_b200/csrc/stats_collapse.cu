@@ -196,50 +196,6 @@ collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __rest
     }
 }
 
-// ---- exact-decision mode of the fused CTC head -----------------------------------------------------------------------
-// The fused head computes logits from bf16 operands; a frame whose greedy decisions sit inside the bf16 noise (argmax
-// probability below p_max_min — a possible near-tie — or a blank frame whose blank probability is within `band` of the
-// drop threshold) is listed here, recomputed by the caller with the fp32-accurate GEMM (bf16x3 split) and written back
-// with scatter_frame_stats_kernel, so that run boundaries and keep/drop decisions match the fp32 reference.
-__global__ void __launch_bounds__(256)
-flag_ambiguous_kernel(const int32_t* __restrict__ argmax, const float* __restrict__ x_blank, const float* __restrict__ row_max,
-                      const float* __restrict__ row_sumexp, const int64_t* __restrict__ lens, int B, int T, int n_prefix,
-                      int blank, float threshold, float p_max_min, float band, int cap, int32_t* __restrict__ frame_idx,
-                      int32_t* __restrict__ raw_row, int32_t* __restrict__ count) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= (int64_t)B * T) return;
-    const int b = (int)(f / T), t = (int)(f % T);
-    if (t >= lens[b]) return;
-    const float inv = 1.f / row_sumexp[f];
-    const float p_max = inv;                                   // exp(max - max) / sum
-    const float p_blank = __expf(x_blank[f] - row_max[f]) * inv;
-    const bool amb = (p_max < p_max_min) || (argmax[f] == blank && fabsf(p_blank - threshold) < band);
-    if (!amb) return;
-    const int k = atomicAdd(count, 1);
-    if (k < cap) { frame_idx[k] = (int32_t)f; raw_row[k] = b * (T + n_prefix) + n_prefix + t; }
-}
-
-__global__ void __launch_bounds__(256)
-scatter_frame_stats_kernel(const int32_t* __restrict__ frame_idx, const int32_t* __restrict__ count, int cap,
-                           const int32_t* __restrict__ argmax_s, const float* __restrict__ x_blank_s,
-                           const float* __restrict__ row_max_s, const float* __restrict__ row_sumexp_s,
-                           int32_t* __restrict__ argmax, float* __restrict__ x_blank, float* __restrict__ row_max,
-                           float* __restrict__ row_sumexp, float* __restrict__ row_sumexp2) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = min(*count, cap);
-    if (k >= n) return;
-    const int f = frame_idx[k];
-    // Σexp² is kept consistent with the new (max, Σexp): rescale the bf16-path value to the new reference point
-    if (row_sumexp2) {
-        const float r = __expf(2.f * (row_max[f] - row_max_s[k]));
-        row_sumexp2[f] *= r;
-    }
-    argmax[f] = argmax_s[k];
-    x_blank[f] = x_blank_s[k];
-    row_max[f] = row_max_s[k];
-    row_sumexp[f] = row_sumexp_s[k];
-}
-
 }  // namespace tasu
 
 using namespace tasu;
@@ -304,42 +260,6 @@ extern "C" int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_f
     TASU_CHECK_ARG(B >= 0 && row_off && header, "B >= 0, non-null outputs");
     TASU_CHECK_ARG(B == 0 || new_lens, "null new_lens");
     collapse_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(new_lens, kept_frames, global_max_enc, B, row_off, frame_off, header, counts_dev);
-    TASU_CHECK_LAUNCH();
-    return TASU_OK;
-}
-
-extern "C" int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_blank, const float* row_max,
-                                          const float* row_sumexp, const int64_t* lens, int B, int T, int n_prefix,
-                                          int blank_id, float threshold, float p_max_min, float band, int cap,
-                                          int32_t* frame_idx, int32_t* raw_row, int32_t* count, void* stream) {
-    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && cap >= 0, "shape");
-    TASU_CHECK_ARG(frame_idx && raw_row && count, "null output");
-    cudaStream_t st = (cudaStream_t)stream;
-    TASU_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
-    if (cap > 0) {
-        TASU_CHECK_CUDA(cudaMemsetAsync(frame_idx, 0xFF, sizeof(int32_t) * cap, st));       // -1 = unused slot
-        TASU_CHECK_CUDA(cudaMemsetAsync(raw_row, 0xFF, sizeof(int32_t) * cap, st));
-    }
-    if ((int64_t)B * T == 0) return TASU_OK;
-    TASU_CHECK_ARG(argmax && x_blank && row_max && row_sumexp && lens, "null pointer");
-    const int64_t n = (int64_t)B * T;
-    flag_ambiguous_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, lens, B, T, n_prefix,
-                                                                      blank_id, threshold, p_max_min, band, cap, frame_idx, raw_row, count);
-    TASU_CHECK_LAUNCH();
-    return TASU_OK;
-}
-
-extern "C" int tasu_scatter_frame_stats(const int32_t* frame_idx, const int32_t* count, int cap, const int32_t* argmax_src,
-                                        const float* x_blank_src, const float* row_max_src, const float* row_sumexp_src,
-                                        int32_t* argmax, float* x_blank, float* row_max, float* row_sumexp,
-                                        float* row_sumexp2, void* stream) {
-    TASU_CHECK_ARG(cap >= 0, "cap >= 0");
-    if (cap == 0) return TASU_OK;
-    TASU_CHECK_ARG(frame_idx && count && argmax_src && x_blank_src && row_max_src && row_sumexp_src && argmax && x_blank &&
-                   row_max && row_sumexp, "null pointer");
-    scatter_frame_stats_kernel<<<(cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        frame_idx, count, cap, argmax_src, x_blank_src, row_max_src, row_sumexp_src, argmax, x_blank, row_max, row_sumexp,
-        row_sumexp2);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

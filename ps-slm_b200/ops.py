@@ -66,7 +66,12 @@ def view3(x: torch.Tensor):
 
 
 class FrameStats:
-    __slots__ = ("argmax", "x_blank", "row_max", "row_sumexp", "row_sumexp2", "gmax", "kind", "B", "T")
+    """``dec_max`` / ``dec_sum`` (exact-decision mode): the softmax normalisers the collapse plan uses instead of
+    ``row_max`` / ``row_sumexp`` (fp32-recomputed for the refined frames)."""
+    __slots__ = ("argmax", "x_blank", "row_max", "row_sumexp", "row_sumexp2", "gmax", "kind", "B", "T", "dec_max", "dec_sum")
+
+    def __init__(self):
+        self.dec_max = self.dec_sum = None
 
 
 def frame_stats(x: torch.Tensor, input_kind: int, blank_id: int, lens: Optional[torch.Tensor] = None) -> FrameStats:
@@ -116,41 +121,56 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
     return st
 
 
-def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, raw_f32: torch.Tensor, w_split: torch.Tensor, k_split: int,
-                            bias: Optional[torch.Tensor], T: int, n_prefix: int, V: int, blank_id: int, threshold: float,
-                            p_max_min: float = 0.53, band: float = 0.02, cap: int = 512) -> torch.Tensor:
-    """Exact-decision mode: recompute the statistics of the frames tasu_flag_ambiguous_frames lists with the
-    fp32-accurate GEMM and write them back into ``st``.  Defaults: bf16 rounding of the 512-term dot products moves a
-    logit by a few 1e-2, so an argmax can only flip when the runner-up is within ~0.1 of it, i.e. p_max <= 1/(1+e^-0.1)
-    = 0.525; a blank probability near 0.9 moves by p(1-p)*0.1 < 0.01.  ``raw_f32`` = [B*(T+P), K] fp32 encoder rows, ``w_split`` =
-    split_bf16x3(W_ctc, pattern 1).  Returns the device counter of flagged frames (int32[1]); no host sync."""
-    dev = st.argmax.device
-    frame_idx = torch.empty(cap, dtype=torch.int32, device=dev)
-    raw_row = torch.empty(cap, dtype=torch.int32, device=dev)
-    count = torch.empty(1, dtype=torch.int32, device=dev)
-    lib = L.lib()
-    L.check(lib.tasu_flag_ambiguous_frames(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
-                                           st.row_sumexp.data_ptr(), lens.data_ptr(), st.B, T, n_prefix, blank_id,
-                                           float(threshold), float(p_max_min), float(band), cap, frame_idx.data_ptr(),
-                                           raw_row.data_ptr(), count.data_ptr(), _stream()), "tasu_flag_ambiguous_frames")
-    K = raw_f32.shape[1]
-    xg = torch.empty(cap, K, dtype=torch.float32, device=dev)                       # unused slots (-1) gather zero rows
-    L.check(lib.tasu_gather_rows(raw_f32.data_ptr(), L.F32, raw_f32.stride(0), raw_row.data_ptr(), cap, K, xg.data_ptr(), K,
-                                 _stream()), "tasu_gather_rows")
-    _count(2)
-    xs, kx, _, _, _ = split_bf16x3(xg, 0)
-    assert kx == k_split
-    ldv = pad_to(V, 4)
-    logits = torch.empty(cap, ldv, dtype=torch.float32, device=dev)
-    # only the live rows (device-side count) go through the tensor cores; rows beyond it hold stale values that the
-    # scatter never reads
-    gemm_fp32x3(xs, w_split, cap, V, kx, logits, L.EPI_BIAS if bias is not None else L.EPI_NONE, bias, m_dev=count)
-    st2 = frame_stats(logits.view(1, cap, ldv)[:, :, :V], L.INPUT_LOGITS, blank_id)
-    L.check(lib.tasu_scatter_frame_stats(frame_idx.data_ptr(), count.data_ptr(), cap, st2.argmax.data_ptr(),
-                                         st2.x_blank.data_ptr(), st2.row_max.data_ptr(), st2.row_sumexp.data_ptr(),
-                                         st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
-                                         st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), _stream()), "tasu_scatter_frame_stats")
+def row_norm_max(w: torch.Tensor) -> torch.Tensor:
+    """max_r ||w_r||_2 as a device uint32[1] in the order-preserving encoding (tasu_row_norm_max)."""
+    _need_cuda(w)
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    out = torch.empty(1, dtype=torch.int32, device=w.device)
+    L.check(L.lib().tasu_row_norm_max(w.data_ptr(), _dt(w), w.shape[0], w.shape[1], w.stride(0), out.data_ptr(), _stream()),
+            "tasu_row_norm_max")
     _count(1)
+    return out
+
+
+ERR_SCALE_F32_INPUT = 1.05 * 2.0 ** -8     # x and W both rounded to bf16 by the fused head (+5 % for the fp32 accumulation)
+ERR_SCALE_BF16_INPUT = 1.05 * 2.0 ** -9    # x was GIVEN in bf16: only W is rounded
+
+
+def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, x_rows: torch.Tensor, w_f32: torch.Tensor,
+                            bias: Optional[torch.Tensor], w_norm_max: torch.Tensor, T: int, n_prefix: int, V: int,
+                            blank_id: int, threshold: float) -> torch.Tensor:
+    """Exact-decision mode (csrc/refine.cu): list the frames whose greedy decisions (argmax, ps-slm.py:265; strict fp32
+    blank threshold, :295-297) lie inside the rounding error bound of the bf16 head, recompute exactly those with fp32
+    FMAs from the fp32 weights, and publish the decision statistics in ``st`` (``argmax`` / ``x_blank`` in place,
+    ``dec_max`` / ``dec_sum`` new) for ``collapse_plan``.  ``x_rows`` = [B*(T+P), K] encoder rows as GIVEN (fp32 or bf16).
+    The list holds one slot per frame: nothing is capped or dropped.  Returns the device counter (int32[1]); no sync."""
+    _need_cuda(x_rows, w_f32, bias)
+    dev = st.argmax.device
+    n = st.B * T
+    if x_rows.stride(-1) != 1:
+        x_rows = x_rows.contiguous()
+    K = x_rows.shape[1]
+    lists = torch.empty(2, max(n, 1), dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    dec = torch.empty(2, max(n, 1), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    lens = lens.to(device=dev, dtype=torch.int64)
+    err = ERR_SCALE_BF16_INPUT if x_rows.dtype == torch.bfloat16 else ERR_SCALE_F32_INPUT
+    L.check(lib.tasu_flag_ambiguous_frames(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
+                                           st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), lens.data_ptr(),
+                                           x_rows.data_ptr(), _dt(x_rows), x_rows.stride(0), K, w_norm_max.data_ptr(),
+                                           float(err), st.B, T, n_prefix, blank_id, float(threshold), dec[0].data_ptr(),
+                                           dec[1].data_ptr(), lists[0].data_ptr(), lists[1].data_ptr(), count.data_ptr(),
+                                           _stream()), "tasu_flag_ambiguous_frames")
+    nbytes = lib.tasu_ctc_head_refine_workspace(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(lib.tasu_ctc_head_refine(x_rows.data_ptr(), _dt(x_rows), x_rows.stride(0), w_f32.data_ptr(), w_f32.stride(0),
+                                     _ptr(bias), V, K, blank_id, lists[0].data_ptr(), lists[1].data_ptr(), count.data_ptr(),
+                                     n, st.argmax.data_ptr(), st.x_blank.data_ptr(), dec[0].data_ptr(), dec[1].data_ptr(),
+                                     ws.data_ptr(), nbytes, _stream()), "tasu_ctc_head_refine")
+    st.dec_max, st.dec_sum = dec[0], dec[1]
+    _count(3)
     return count
 
 
@@ -214,8 +234,10 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     # ``header`` may be pinned host memory: under UVA its pointer is valid on the device
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
     lib = L.lib()
-    L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
-                                   _ptr(st.row_sumexp), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
+    d_max = st.dec_max if st.dec_max is not None else st.row_max
+    d_sum = st.dec_sum if st.dec_sum is not None else st.row_sumexp
+    L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), d_max.data_ptr(),
+                                   _ptr(d_sum), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
                                    blank_id, float(threshold), p.seg_start.data_ptr(), p.seg_len.data_ptr(),
                                    _ptr(p.seg_score), p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
                                    p.seg_foff.data_ptr(), _stream()), "tasu_collapse_plan")

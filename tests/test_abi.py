@@ -40,7 +40,7 @@ def test_header_symbols_exported(lib):
         assert name in L.SIGNATURES, f"{name} has no ctypes signature"
         assert len(L.SIGNATURES[name][1]) == nargs, f"{name}: header has {nargs} args, binding {len(L.SIGNATURES[name][1])}"
     assert set(L.SIGNATURES) == set(funcs)
-    assert lib.tasu_abi_version() == 1
+    assert lib.tasu_abi_version() == 2
 
 
 def test_argument_validation_without_gpu(lib):

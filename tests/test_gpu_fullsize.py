@@ -101,6 +101,55 @@ def test_midsize_vs_oracle(dev):
     assert torch.equal(e[~audio], e_r[~audio])
 
 
+def test_fullsize_vs_oracle(dev):
+    """BASELINE.json configs[1] at its full size (B = 64 x 30 s, ragged lengths) through the whole bridge — the
+    benchmarked configuration, exact decisions on — against the ORACLE (oracle/tasu_oracle.py: fp32 softmax(ctc_lo) of the
+    full [64, 504, 25055] posterior on the host, psd_vec, fp32 projector, merge): compressed lengths, masks, position
+    ids and the text rows bit-exact; projected audio rows within 1e-2 (bf16 tensor-core path)."""
+    import ps_slm_b200.synth as S
+    B, T = 64, 500
+    w, b, proj, table, br = _bridge(dev, torch.float32)
+    assert br.exact_decisions
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=2025, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=2025, left_pad=True)
+    sd = {k: v.detach().cpu() for k, v in proj.state_dict().items()}
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    with torch.no_grad():
+        post, lens = O.ctc_head_posterior(raw, raw_lens, w, b)
+        feats, nl_r, plan = O.psd_vec(post, lens, post, 0)
+        del post
+        proj_r = O.projector_linear_silu(feats, *pp)
+        del feats
+        e_r, m_r, _, p_r, f_r = O.merge(proj_r, nl_r, torch.nn.functional.embedding(ids, table.cpu()), ids, mask, None,
+                                        S.SPEECH_ID, S.PAD_ID)
+    e, m, _, p, nl = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    assert torch.equal(nl.cpu(), nl_r), "compressed lengths differ from the oracle"
+    assert torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    audio = m_r & (f_r == S.PAD_ID)
+    e = e.cpu()
+    assert torch.equal(e[~audio], e_r[~audio])
+    assert ((e[audio] - e_r[audio]).norm() / e_r[audio].norm()).item() < 1e-2
+    rows = (e[audio] - e_r[audio]).norm(dim=-1) / e_r[audio].norm(dim=-1)
+    assert rows.max().item() < 3e-2
+    # the integer plan of the device (greedy ids of every valid frame, kept candidates) against the oracle's
+    st_ids = plan["ids"]
+    import ps_slm_b200.ops as ops
+    x2, _, _ = ops.cast_rows(raw.to(dev).reshape(B * (T + 4), 512), torch.bfloat16)
+    wq, _, _ = ops.cast_rows(w.to(dev), torch.bfloat16)
+    st = ops.ctc_head_stats(x2, wq, b.to(dev), B, T, 4, S.V_CTC, 512, 0)
+    ops.refine_ambiguous_frames(st, lens.to(dev), raw.to(dev).reshape(B * (T + 4), 512), w.to(dev), b.to(dev),
+                                ops.row_norm_max(w.to(dev)), T, 4, S.V_CTC, 0, 0.9)
+    valid = torch.arange(T)[None] < lens[:, None]
+    assert torch.equal(st.argmax.cpu().view(B, T).long()[valid], st_ids[valid])
+    dplan = ops.collapse_plan(st, lens.to(dev), 0, 0.9)
+    ss, sl = dplan.seg_start.cpu().view(B, T), dplan.seg_len.cpu().view(B, T)
+    kb, kt, kl = plan["kept_b"], plan["kept_t"], plan["kept_len"]
+    for bb in range(B):
+        sel = kb == bb
+        n = int(sel.sum())
+        assert ss[bb, :n].tolist() == kt[sel].tolist() and sl[bb, :n].tolist() == kl[sel].tolist()
+
+
 def _small_bridge(dev, V=61, D=32, H=48, table_rows=300):
     import ps_slm_b200.projector as P
     from ps_slm_b200.bridge import TasuBridge

@@ -353,7 +353,7 @@ def test_exact_decisions_on_adversarial_frames(dev):
     (e_r, m_r, _, p_r, _), nl_r = O.bridge_inference(raw, raw_lens, w, b, pp, table, ids, mask, None, S.SPEECH_ID, S.PAD_ID)
     br = TasuBridge(w.to(dev), b.to(dev), proj.to(dev).eval(), table.to(dev), S.SPEECH_ID, S.PAD_ID)
     args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
-    br.exact_decisions = True
+    assert br.exact_decisions, "exact decisions are the default"
     e, m, _, p, nl = br(*args)
     n_amb = int(br.last_ambiguous.item())
     assert n_amb >= planted, (n_amb, planted)                         # every planted frame was caught and refined
@@ -363,3 +363,107 @@ def test_exact_decisions_on_adversarial_frames(dev):
     br.exact_decisions = False                                        # for the record: the plain bf16 head on the same batch
     nl0 = br(*args)[4]
     print("bf16-head compressed lengths", nl0.cpu().tolist(), "fp32 reference", nl_r.tolist(), "refined frames", n_amb)
+
+
+def _plant_blank_frames(w, b, targets, g, noise=0.02, iters=44):
+    """Encoder rows whose fp32 blank probability equals ``targets`` (batched bisection on the logit scale)."""
+    n = targets.numel()
+    u0 = w[0] / (w[0].norm() ** 2)
+    nz = noise * torch.randn(n, w.shape[1], generator=g)
+    lo, hi = torch.full((n,), 5.0), torch.full((n,), 40.0)
+    for _ in range(iters):
+        mid = 0.5 * (lo + hi)
+        pb = torch.softmax(torch.nn.functional.linear(mid[:, None] * u0[None] + nz, w, b), -1)[:, 0]
+        below = pb < targets
+        lo = torch.where(below, mid, lo)
+        hi = torch.where(below, hi, mid)
+    return 0.5 * (lo + hi)[:, None] * u0[None] + nz
+
+
+def test_exact_decisions_with_more_than_512_ambiguous_frames(dev):
+    """800 frames of a 4 x 256 batch sit within 1e-4 .. 2e-3 of the keep/drop threshold (ps-slm.py:295-297) — more than the
+    512 slots the round-1 refinement had.  The list is uncapped: every one of them must come out as the fp32 reference
+    decides, and the device counter must report them all."""
+    import types
+
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 4, 256
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=77, ragged=True)
+    g = torch.Generator().manual_seed(9)
+    slots = [(bb, t) for bb in range(B) for t in range(T) if t % 32 >= 7][:800]
+    k = torch.arange(len(slots))
+    offs = torch.tensor([1e-4, 3e-4, 1e-3, 2e-3])[k % 4] * torch.where(k % 2 == 0, 1.0, -1.0)
+    rows = _plant_blank_frames(w, b, 0.9 + offs, g)
+    pb = torch.softmax(torch.nn.functional.linear(rows, w, b), -1)[:, 0]
+    solid = (pb - 0.9).abs() > 3e-5                                   # the fp32 decision itself must not be a coin toss
+    assert int(solid.sum()) > 700
+    for i, (bb, t) in enumerate(slots):
+        if solid[i]:
+            raw[bb, 4 + t] = rows[i]
+    ids, mask, _ = S.make_prompts(B, seed=4, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg)
+    table = S.make_embed_table(dtype=torch.float32)
+    sd = proj.state_dict()
+    pp = (sd["norm.weight"], sd["norm.bias"], sd["ffn.0.weight"], sd["ffn.0.bias"], sd["ffn.2.weight"], sd["ffn.2.bias"])
+    (e_r, m_r, _, p_r, _), nl_r = O.bridge_inference(raw, raw_lens, w, b, pp, table, ids, mask, None, S.SPEECH_ID, S.PAD_ID)
+    br = TasuBridge(w.to(dev), b.to(dev), proj.to(dev).eval(), table.to(dev), S.SPEECH_ID, S.PAD_ID)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    e, m, _, p, nl = br(*args)
+    valid = torch.tensor([t < int(raw_lens[bb]) - 4 for bb, t in slots]) & solid
+    n_amb = int(br.last_ambiguous.item())
+    assert n_amb >= int(valid.sum()) > 512, (n_amb, int(valid.sum()))
+    assert torch.equal(nl.cpu(), nl_r), (nl.cpu().tolist(), nl_r.tolist())
+    assert torch.equal(m.cpu(), m_r) and torch.equal(p.cpu(), p_r)
+    assert ((e.cpu().float() - e_r).norm() / e_r.norm()).item() < 1e-2
+    # bf16 encoder rows handed over: the refinement works from exactly those values (reference = fp32 math on them)
+    raw16 = raw.bfloat16()
+    (_, m_r2, _, p_r2, _), nl_r2 = O.bridge_inference(raw16.float(), raw_lens, w, b, pp, table, ids, mask, None,
+                                                      S.SPEECH_ID, S.PAD_ID)
+    _, m2, _, p2, nl2 = br(raw16.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    assert torch.equal(nl2.cpu(), nl_r2) and torch.equal(m2.cpu(), m_r2) and torch.equal(p2.cpu(), p_r2)
+
+
+def test_refined_statistics_match_fp32(dev):
+    """tasu_ctc_head_refine on EVERY frame of a small batch (margin forced by err_scale) reproduces the fp32 logits'
+    argmax (first index), max, sum-exp and blank logit; ragged vocabulary / K tails included."""
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200._lib as L
+    for (B, T, P_, V, K, blank) in [(2, 37, 4, 25055, 512, 0), (3, 50, 0, 301, 72, 300), (1, 700, 4, 1000, 40, 5)]:
+        g = torch.Generator().manual_seed(V + K)
+        w = torch.randn(V, K, generator=g) / K ** 0.5
+        bias = torch.randn(V, generator=g) * 0.1
+        x = torch.randn(B, T + P_, K, generator=g) * 3.0
+        x[0, P_ + 1] = 0                                              # all logits = bias
+        bias[7], bias[3] = bias.max() + 1, bias.max() + 1             # exact tie → lowest index wins (torch rule)
+        bias[3] = bias[7]
+        lens = torch.full((B,), T, dtype=torch.long)
+        lens[-1] = T - 3
+        logits = torch.nn.functional.linear(x[:, P_:], w, bias)
+        xd = x.to(dev).reshape(B * (T + P_), K)
+        ldk = ops.pad_to(K)
+        xb = torch.zeros(B * (T + P_), ldk, dtype=torch.bfloat16, device=dev); xb[:, :K] = xd.bfloat16()
+        wb = torch.zeros(V, ldk, dtype=torch.bfloat16, device=dev); wb[:, :K] = w.to(dev).bfloat16()
+        st = ops.ctc_head_stats(xb, wb, bias.to(dev), B, T, P_, V, K, blank)
+        import ps_slm_b200.ops as ops_mod
+        old = ops_mod.ERR_SCALE_F32_INPUT
+        ops_mod.ERR_SCALE_F32_INPUT = 1e6                             # every valid frame is "ambiguous"
+        try:
+            cnt = ops.refine_ambiguous_frames(st, lens.to(dev), xd, w.to(dev), bias.to(dev), ops.row_norm_max(w.to(dev)),
+                                              T, P_, V, blank, 0.9)
+        finally:
+            ops_mod.ERR_SCALE_F32_INPUT = old
+        assert int(cnt.item()) == int(lens.sum())
+        am = st.argmax.cpu().view(B, T).long()
+        valid = torch.arange(T)[None] < lens[:, None]
+        assert torch.equal(am[valid], logits.argmax(-1)[valid])
+        mx, sm = st.dec_max.cpu().view(B, T), st.dec_sum.cpu().view(B, T)
+        ref_m = logits.max(-1).values
+        ref_s = torch.exp(logits - ref_m[..., None]).sum(-1)
+        assert torch.allclose(mx[valid], ref_m[valid], rtol=0, atol=5e-5)
+        assert torch.allclose(sm[valid], ref_s[valid], rtol=5e-5)
+        assert torch.allclose(st.x_blank.cpu().view(B, T)[valid], logits[..., blank][valid], rtol=0, atol=5e-5)

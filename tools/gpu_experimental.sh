@@ -9,7 +9,7 @@ export TASU_EXPERIMENTAL=1
 : > gpurun_out/rc_experimental.txt
 declare -A OK
 for group in bf16_encoder prefetch wide_ctc widegemm streamk pair; do
-    timeout 900 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 --timeout-method=thread -k "$group" \
+    timeout 420 python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 120 --timeout-method=thread -k "$group" \
         > gpurun_out/t_experimental_$group.log 2>&1
     rc=$?
     echo "$group rc=$rc" >> gpurun_out/rc_experimental.txt
