@@ -59,25 +59,13 @@ enum { TASU_CH_N_OUT = 0,         /* total compressed rows  sum_b M_b */
 
 int tasu_abi_version(void);
 const char* tasu_last_error(void);
-/* Run-time options.  Every option defaults to 0 (= the validated path) unless the environment variable of the same
- * purpose is set when the library is first used.
- *   TASU_OPT_GEMM_PAIR (env TASU_GEMM_PAIR): EXPERIMENTAL — tasu_gemm_bf16_tn runs problems with M > 128 as CTA pairs:
- *   clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of the B
- *   tile.  Bit 0 (value 1): deep-K shapes (K > 1024: 6 stages, one epilogue group); bit 1 (value 2): K <= 1024
- *   (4 stages, two epilogue groups); 3 = both.  Same contract and results as the default kernel (the accumulation
- *   order inside a tile is unchanged).  Bit 2 (value 4): tasu_ctc_head_stats with K <= 512 as CTA pairs (256 frames
- *   per work item, each CTA keeps its 128 frames resident and streams half of every weight tile through 6 stages);
- *   the vocabulary may be split differently, so sums agree with the default kernel to fp32 rounding, not bit for bit.
- *   TASU_OPT_EPI_PREFETCH (env TASU_EPI_PREFETCH): EXPERIMENTAL — epilogue vectors (bias, colsum, row statistics) of the
- *   NEXT tile are fetched while the current tile is processed.  Bit 0: tasu_gemm_bf16_tn for K <= 1024; bit 1:
- *   tasu_ctc_head_stats.  Same values and arithmetic: results are bit-identical to the default kernels.
- *   TASU_OPT_STATS_WIDE (env TASU_STATS_WIDE): EXPERIMENTAL — tasu_ctc_head_stats (K <= 512) with 16 epilogue warps
- *   (four per scheduler, each a 64-column quarter of the tile read as 16-column TMEM slabs) instead of 8; sums are
- *   associated differently (quarters instead of halves): equal to the default kernel to fp32 rounding.
- *   TASU_OPT_GEMM_WIDE_EPI (env TASU_GEMM_WIDE_EPI): EXPERIMENTAL — tasu_gemm_bf16_tn with K <= 1024 and bf16 output
- *   runs with 16 independent epilogue warps (each stages and TMA-stores its own 32 x 64 sub-tile, no barriers between
- *   them, next tile's vectors prefetched).  Same arithmetic: results are bit-identical to the default kernel. */
-enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_EPI_PREFETCH = 1, TASU_OPT_STATS_WIDE = 2, TASU_OPT_GEMM_WIDE_EPI = 3, TASU_OPT_COUNT = 4 };
+/* Run-time options; the initial value comes from the environment variable of the same purpose when the library is first
+ * used, else the default.
+ *   TASU_OPT_GEMM_PAIR (env TASU_GEMM_PAIR, default 1): tasu_gemm_bf16_tn runs deep-K problems (K > 1024, M > 128) as CTA
+ *   pairs — clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of
+ *   the B tile (a third less shared-memory fill per flop).  Same contract and bit-identical results as the one-CTA
+ *   kernel (the accumulation order inside a tile is unchanged); 0 selects the one-CTA kernel. */
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */
@@ -168,8 +156,9 @@ int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_p
                           int32_t* tail_src, int32_t* multi_rows /*[N_out] or NULL*/, int32_t* multi_count /*[1]*/,
                           float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 /* In-place mean over the frames of every multi-frame candidate of the compact probability matrix
- * (ps-slm.py:286): probs[r] = (probs[r] + sum of its tail rows) / n, plus LayerNorm statistics. */
-int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
+ * (ps-slm.py:286): probs[r] = (probs[r] + sum of its tail rows) / n, plus LayerNorm statistics.  max_rows = rows the
+ * compact matrix holds: a candidate whose frames do not all lie below it is skipped (no access beyond the buffer). */
+int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, int64_t max_rows, const int32_t* pk_len,
                    const int32_t* tail_src, const int32_t* multi_rows, const int32_t* multi_count,
                    float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 
@@ -206,6 +195,12 @@ int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, const float* b
                             const int64_t* dst_row, int64_t n_rows, int V,
                             void* out, int out_dtype, int64_t out_row_stride,
                             float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+
+/* Content fingerprint of up to 8 device buffers (4096 evenly spaced 32-bit words of each, position-dependent hash):
+ * the host mirror validates its cached bf16 / folded weight copies with it, because optimizers that update parameters
+ * through flat buffers (DeepSpeed ZeRO, finetune_deepspeed.py:147-149) change neither a tensor's address nor torch's
+ * version counter.  `out` [1] may be device or pinned host memory (plain store by one thread). */
+int tasu_fingerprint(const void* const* ptrs_host, const int64_t* nbytes_host, int n, uint64_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Step 3 helpers — operand preparation for the tensor-core GEMMs.
@@ -458,6 +453,22 @@ int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, in
  * inputs_embeds this is the backward of the audio part of the splice (index_put of ps-slm.py:867-869; training). */
 int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stride, const int32_t* idx, int64_t n_rows, int H,
                      void* dst, int64_t dst_row_stride, void* stream);
+
+/* dst[i] = cast(scale * src[i]), i < n: gradient wire format of the data-parallel all-reduce (fp32 -> bf16 before it,
+ * bf16 -> fp32 with the 1/world factor after it; reference: fp32 ZeRO-2 reduce-scatter, conf/ds_config.json:15-21). */
+int tasu_flat_scale_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Cross-rank packing (north star: "NCCL ... only to all-gather per-rank compressed lengths and outputs for packing").
+ * After all-gathering the per-rank lengths (all_lens [W, b_max] int64, utterance i = rank i % W, local index i / W —
+ * the reference's sample sharding, speech_dataset_large.py:80-91) and the packed rows (flat: rank r's rows start at row
+ * r * slab_rows), copy the rows of the selected utterances sel[0..n_sel) (global ids, any order; NULL = 0..n_sel-1) into
+ * `out`, contiguously in selection order, and emit their lengths.  `total` [1] = rows written (never more than max_rows).
+ * workspace: (W * b_max + 2 * n_sel) int32.  Two launches, nothing is built on or shipped from the host. */
+int tasu_packed_select(const void* flat, int dtype, int64_t flat_row_stride, int64_t slab_rows, int H,
+                       const int64_t* all_lens, int W, int b_max, int64_t n_global, const int32_t* sel, int n_sel,
+                       void* out, int64_t out_row_stride, int64_t max_rows, int64_t* out_lens, int32_t* total,
+                       int32_t* workspace, void* stream);
 
 #ifdef __cplusplus
 }

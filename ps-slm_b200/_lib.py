@@ -19,7 +19,7 @@ INPUT_PROBS, INPUT_LOGITS = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, EPI_SOFTMAX = 0, 1, 2, 3, 4, 5, 6
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
-OPT_GEMM_PAIR, OPT_EPI_PREFETCH, OPT_STATS_WIDE, OPT_GEMM_WIDE_EPI, OPT_COUNT = 0, 1, 2, 3, 4     # run-time options (tasu_set_option); 0 = the validated default path
+OPT_GEMM_PAIR, OPT_COUNT = 0, 1     # run-time options (tasu_set_option)
 
 # name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
@@ -38,9 +38,10 @@ SIGNATURES = {
     "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _F, _P]),
-    "tasu_pool_tail": (_I, [_P, _L, _I, _L, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "tasu_pool_tail": (_I, [_P, _L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P]),
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
+    "tasu_fingerprint": (_I, [_P, _P, _I, _P, _P]),
     "tasu_cast_rows": (_I, [_P, _I, _L, _I, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_softmax_rows": (_I, [_P, _I, _L, _L, _I, _P, _P, _P, _L, _P]),
     "tasu_fold_layernorm": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _P]),
@@ -80,6 +81,8 @@ SIGNATURES = {
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),
     "tasu_splice_scatter": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _L, _L, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_flat_scale_cast": (_I, [_P, _I, _P, _I, _L, _F, _P]),
+    "tasu_packed_select": (_I, [_P, _I, _L, _L, _I, _P, _I, _I, _L, _P, _I, _P, _L, _L, _P, _P, _P, _P]),
     "tasu_gather_rows": (_I, [_P, _I, _L, _P, _L, _I, _P, _L, _P]),
 }
 

@@ -278,19 +278,48 @@ def _raise_splice_errors(hdr, attention_mask, num_audios):
             f" the number of audio given to the model is {num_audios}. This prevents correct indexing and breaks batch generation.")
 
 
+CACHE_GENERATION = [0]
+VERIFY_CACHES = True      # validate cached weight copies against a content fingerprint of the live parameters
+
+
+def invalidate_caches():
+    """Drop every cached bf16 / folded weight copy (all ``ProjectorCache`` objects).  Called by ``Module.train()`` /
+    ``.eval()`` of the bridge's modules; call it yourself after changing parameters through raw storage."""
+    CACHE_GENERATION[0] += 1
+
+
 class ProjectorCache:
-    """bf16 / folded copies of the projector weights, rebuilt only when a parameter changes
-    (tracked through torch's per-tensor version counter, so optimizer steps are seen)."""
+    """bf16 / folded copies of (frozen or evaluation-time) weights.
+
+    A copy is rebuilt when (a) a parameter's address, shape or torch version counter changes, (b) ``invalidate_caches()``
+    ran since it was built — every ``train()`` / ``eval()`` of the bridge's modules does that — or (c) ``verify=True`` and
+    the content fingerprint of the live parameters (tasu_fingerprint, one tiny kernel + one scalar read-back) differs
+    from the one taken when the copy was built.  (c) is what catches optimizers that update parameters through flat
+    buffers and ``.data.copy_`` (DeepSpeed ZeRO-1/2, finetune_deepspeed.py:147-149): neither address nor version
+    counter moves there.  ``fresh=True`` (training forwards) never caches."""
 
     def __init__(self):
         self._key = None
         self.data = None
+        self.fp = None
+        self.builds = 0
 
-    def get(self, params, builder):
-        key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params if p is not None)
-        if key != self._key:
+    def get(self, params, builder, fresh=False, verify=False):
+        if fresh:
+            self._key, self.data, self.fp = None, None, None
+            self.builds += 1
+            return builder()
+        live = [p for p in params if p is not None]
+        key = (CACHE_GENERATION[0],) + tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in live)
+        fp = None
+        if verify and VERIFY_CACHES and live and live[0].is_cuda:
+            fp = int(ops.fingerprint(live[:8]).item())
+        if key != self._key or (fp is not None and self.fp is not None and fp != self.fp):
             self.data = builder()
             self._key = key
+            self.builds += 1
+        if fp is not None:
+            self.fp = fp
         return self.data
 
 
@@ -378,6 +407,7 @@ class TasuBridge:
         self.speech_id, self.pad_id, self.ignore_id = int(speech_id), int(pad_id), int(ignore_id)
         self.blank_id, self.blank_threshold, self.ln_eps = int(blank_id), float(blank_threshold), float(ln_eps)
         self._ctc_cache = ProjectorCache()
+        self._fp = None               # content fingerprint of the parameters the cached weight copies were made from
         self._capacity = {}           # (B, T) → (kept-frame rows, packed rows) the tail buffers are sized for
         self.last_counts = {}
         # Exact decisions (default): the frames whose greedy decisions — argmax (ps-slm.py:265), strict fp32 blank
@@ -387,6 +417,7 @@ class TasuBridge:
         # there are none).  False: decisions straight from the bf16 head.
         self.exact_decisions = True
         self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
+        self._ctc_exact_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         # EXPERIMENTAL (not yet validated on a GPU): projector GEMM-1 with the stream-K tail
         self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK") == "1"
@@ -418,7 +449,7 @@ class TasuBridge:
     def _header_slot(self):
         """Ring of pinned host header buffers (collapse + splice words), one per in-flight call."""
         if not hasattr(self, "_hdr_ring"):
-            self._hdr_ring = [torch.zeros(L.CH_WORDS + L.SH_WORDS, dtype=torch.int64).pin_memory() for _ in range(4)]
+            self._hdr_ring = [torch.zeros(L.CH_WORDS + L.SH_WORDS + 1, dtype=torch.int64).pin_memory() for _ in range(4)]
             self._hdr_i = 0
         self._hdr_i = (self._hdr_i + 1) % len(self._hdr_ring)
         return self._hdr_ring[self._hdr_i]
@@ -453,14 +484,45 @@ class TasuBridge:
                                                                   self.blank_id, self.blank_threshold)
         return st
 
+    def _weight_params(self):
+        return [self.w_ctc, self.b_ctc] + [p for p in self.projector.parameters()][:6]
+
+    def _cache_builds(self):
+        return self._ctc_cache.builds + self._ctc_exact_cache.builds + self.projector._cache.builds
+
+    def _check_fingerprint(self, fp: int, builds_before: int) -> bool:
+        """True when the cached weight copies this call used are current.  The fingerprint of the live parameters was
+        taken by the first kernel of the call and arrives with the plan header (no extra synchronisation)."""
+        if not VERIFY_CACHES:
+            return True
+        rebuilt = self._cache_builds() != builds_before
+        if self._fp is None or fp == self._fp or rebuilt:
+            self._fp = fp
+            return True
+        # parameters changed behind torch's version counter (flat-buffer optimizer): drop the copies, redo the call
+        self._fp = None
+        invalidate_caches()
+        return False
+
     @torch.no_grad()
     def __call__(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor,
                  input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: Optional[torch.Tensor] = None,
                  want_ids: bool = False):
+        for _ in range(2):
+            out = self._run(raw_encoder_out, raw_encoder_out_lens, input_ids, attention_mask, labels, want_ids)
+            if out is not None:
+                return out
+        raise L.TasuError("projector / CTC-head parameters keep changing while the bridge runs")
+
+    def _run(self, raw_encoder_out, raw_encoder_out_lens, input_ids, attention_mask, labels, want_ids):
         B, T4, Denc = raw_encoder_out.shape
         T = T4 - self.N_PREFIX
         V = self.w_ctc.shape[0]
         dev = raw_encoder_out.device
+        builds_before = self._cache_builds()
+        header = self._header_slot()
+        if VERIFY_CACHES:
+            ops.fingerprint(self._weight_params(), out=header[L.CH_WORDS + L.SH_WORDS:])
         w_ctc, b_ctc = self._ctc_weights()
         w1g, colsum, dbias, w2, b2 = self.projector.folded_weights()
         out_dtype = self.embed_table.dtype
@@ -477,7 +539,6 @@ class TasuBridge:
         # The plan headers are written by the kernels straight into pinned (UVA-mapped) host memory: the one
         # device→host hand-off of the step needs no copy-engine transfer, so it cannot queue behind the bulk
         # D2H of the previous batch when calls are pipelined (HostPipeline).
-        header = self._header_slot()
         ldk = ops.pad_to(V)
 
         if self.materialize_logits:
@@ -512,9 +573,11 @@ class TasuBridge:
                                    out_dtype)
         ev.synchronize()                                                # the single device→host hand-off
         hdr = header.clone()
+        if not self._check_fingerprint(int(hdr[L.CH_WORDS + L.SH_WORDS]), builds_before):
+            return None                                                 # stale weight copies: the caller redoes the call
         n_out, max_len = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN])
         n_frames = int(hdr[L.CH_KEPT_FRAMES])
-        shdr = hdr[L.CH_WORDS:]
+        shdr = hdr[L.CH_WORDS:L.CH_WORDS + L.SH_WORDS]
         _raise_splice_errors(shdr, attention_mask, B)
         spliced_len = int(shdr[L.SH_SPLICED_LEN])
 
@@ -549,37 +612,43 @@ class TasuBridge:
 
     # ------------------------------------------------------------------ two-phase API (cross-rank packing)
     @torch.no_grad()
-    def compress_project(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor):
-        """Steps 1b-3 only: → (audio rows packed ``[sum M_b, H]``, ``new_lens [B]`` int64, ``max_b M_b``).
-        Used when compressed sequences are exchanged between ranks before the splice (dist.all_gather_packed)."""
+    def compress_project_async(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor) -> "PendingCompress":
+        """Steps 1b-3, enqueued without a host synchronisation: head statistics → (exact decisions) → collapse plan →
+        speculative tail on capacity-sized buffers (as in ``__call__``).  ``finish()`` waits for the header only."""
         B, T4, Denc = raw_encoder_out.shape
         T = T4 - self.N_PREFIX
         V = self.w_ctc.shape[0]
         dev = raw_encoder_out.device
+        pend = PendingCompress()
+        pend.bridge, pend.inputs = self, (raw_encoder_out, raw_encoder_out_lens)
+        pend.builds_before = self._cache_builds()
+        header = self._header_slot()
+        if VERIFY_CACHES:
+            ops.fingerprint(self._weight_params(), out=header[L.CH_WORDS + L.SH_WORDS:])
         w_ctc, b_ctc = self._ctc_weights()
-        w1g, colsum, dbias, w2, b2 = self.projector.folded_weights()
+        proj_w = self.projector.folded_weights()
         out_dtype = self.embed_table.dtype
         x2 = raw_encoder_out.reshape(B * T4, Denc)
         if x2.dtype != torch.bfloat16:
             x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
-        header = self._header_slot()
         st = self._head_stats(raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V)
         plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
         ev = torch.cuda.Event()
         ev.record()
-        ev.synchronize()
-        n_out, max_len, n_frames = int(header[L.CH_N_OUT]), int(header[L.CH_MAX_LEN]), int(header[L.CH_KEPT_FRAMES])
-        if n_out == 0:
-            return torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev), plan.new_lens, 0
-        xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
-            x2, B, T, self.N_PREFIX, Denc, V, plan, st, n_frames, n_out, self.ln_eps)
-        ldk = ops.pad_to(V)
-        pooled = torch.empty(_cap(n_frames), ldk, dtype=torch.bfloat16, device=dev)[:n_frames]
-        ops.gemm_bf16_tn(xg, w_ctc, n_frames, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max)
-        ops.pool_tail(pooled, V, n_out, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
-        audio = linear_silu_forward(pooled, n_out, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype)
-        return audio, plan.new_lens, max_len
+        hw_f, hw_o = self._capacity.get((B, T), (0, 0))
+        cap_f = _cap(int(1.25 * hw_f)) if hw_f else _cap(B * T)
+        cap_o = _cap(int(1.25 * hw_o)) if hw_o else _cap(B * T)
+        pend.tail_args = (x2, st, plan, B, T, Denc, V)
+        pend.weights = (w_ctc, b_ctc) + tuple(proj_w) + (out_dtype,)
+        pend.audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, *proj_w, out_dtype)
+        pend.cap_f, pend.cap_o, pend.header, pend.event, pend.plan = cap_f, cap_o, header, ev, plan
+        return pend
+
+    def compress_project(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor):
+        """Steps 1b-3 only: → (audio rows packed ``[sum M_b, H]``, ``new_lens [B]`` int64, ``max_b M_b``).
+        Used when compressed sequences are exchanged between ranks before the splice (dist.gather_packed)."""
+        return self.compress_project_async(raw_encoder_out, raw_encoder_out_lens).finish()
 
     @torch.no_grad()
     def splice(self, audio_rows: torch.Tensor, new_lens: torch.Tensor, input_ids: torch.Tensor,
@@ -596,6 +665,29 @@ class TasuBridge:
         return ops.splice_scatter(sp, int(shdr[L.SH_SPLICED_LEN]), self.embed_table, 1, audio_rows, 0, 0, labels,
                                   self.pad_id, self.ignore_id, want_ids=want_ids,
                                   left_padding=int(shdr[L.SH_LEFT_PADDING]))
+
+
+class PendingCompress:
+    """Handle of ``TasuBridge.compress_project_async``: the kernels are enqueued, ``finish()`` waits for the 96-byte plan
+    header, validates the cached weight copies, redoes the tail if a capacity was exceeded and returns
+    ``(audio rows [sum M_b, H] — a view of a capacity-sized buffer —, new_lens [B] int64, max_b M_b)``."""
+    __slots__ = ("bridge", "inputs", "builds_before", "tail_args", "weights", "audio_cap", "cap_f", "cap_o", "header",
+                 "event", "plan")
+
+    def finish(self):
+        br = self.bridge
+        self.event.synchronize()
+        hdr = self.header.clone()
+        if not br._check_fingerprint(int(hdr[L.CH_WORDS + L.SH_WORDS]), self.builds_before):
+            return br.compress_project(*self.inputs)                    # stale weight copies: redo with fresh ones
+        n_out, max_len, n_frames = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN]), int(hdr[L.CH_KEPT_FRAMES])
+        x2, st, plan, B, T, Denc, V = self.tail_args
+        if n_frames > self.cap_f or n_out > self.cap_o:                 # capacity exceeded (rare): redo the tail, exact
+            self.audio_cap = br._tail(x2, st, plan, B, T, Denc, V, _cap(n_frames), _cap(n_out), *self.weights)
+        hw_f, hw_o = br._capacity.get((B, T), (0, 0))
+        br._capacity[(B, T)] = (max(hw_f, n_frames), max(hw_o, n_out))
+        br.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "kept_frames": n_frames}
+        return self.audio_cap[:n_out], self.plan.new_lens, max_len
 
 
 class HostPipeline:

@@ -30,7 +30,8 @@ int sm_count() {
 }
 
 // run-time options (tasu_set_option); the initial value of option X comes from the environment variable named below
-static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR", "TASU_EPI_PREFETCH", "TASU_STATS_WIDE", "TASU_GEMM_WIDE_EPI"};
+static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR"};
+static const int kOptionDefault[TASU_OPT_COUNT] = {1};
 static std::atomic<int> g_options[TASU_OPT_COUNT];
 static std::once_flag g_options_once;
 
@@ -38,7 +39,7 @@ static void init_options() {
     std::call_once(g_options_once, [] {
         for (int i = 0; i < TASU_OPT_COUNT; ++i) {
             const char* e = getenv(kOptionEnv[i]);
-            g_options[i].store(e != nullptr ? atoi(e) : 0);
+            g_options[i].store(e != nullptr ? atoi(e) : kOptionDefault[i]);
         }
     });
 }

@@ -26,27 +26,22 @@ constexpr int kStatsSmemBytesARes = 8 * kABytes + 3 * kBBytes + 2 * BN * 4 + 128
 constexpr int kStatsThreads = 384;                   // warps 0-3 control, warps 4-11 epilogue
 constexpr int kStatsEpiThreads = 256;
 
-constexpr int kStatsPairStages = 6;                  // pair mode: 6 x 16 KB half-B stages next to the resident A tile
-constexpr int kStatsSmemBytesPair = 8 * kABytes + kStatsPairStages * kPairBBytes + 2 * BN * 4 + 256;
-
 // kARes (K <= 512): the 128-frame A tile stays resident in shared memory for the whole vocabulary sweep of an item
 // and only the weight tiles stream through a 3-stage ring — a third less L2→SM traffic per MMA.
-// kPair (EXPERIMENTAL, with kARes; launched as clusters of 2, see gemm_bf16_tn_kernel): a work item covers 256 frames,
-// each CTA keeps its own 128 frames resident and streams HALF of every 256-column weight tile (16 KB per stage, 6
-// stages), the rank-0 CTA issues tcgen05.mma.cta_group::2, every CTA reduces the statistics of its own 128 frames.
-// kPrefetch (EXPERIMENTAL, TASU_OPT_EPI_PREFETCH bit 1): every epilogue thread fetches its bias value of the NEXT
-// vocabulary tile while the current one is reduced (the load at the top of each tile is exposed L2 latency otherwise).
-template <bool kARes, bool kPair = false, bool kPrefetch = false>
+// Every epilogue thread fetches its bias value of the NEXT vocabulary tile while the current one is reduced (the load
+// at the top of each tile is exposed L2 latency otherwise; measured −2 % on the headline batch, profiles/r02a_ab.md).
+// Variants measured and removed in round 2 (profiles/r02a_ab.md): CTA pairs (cta_group::2, 256 frames per item) +10 %
+// time, 16 epilogue warps on 16-column TMEM slabs +1 %.
+template <bool kARes>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const StatsParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    static_assert(!kPair || kARes, "pair mode keeps the A tile resident");
-    constexpr int kSt = kPair ? kStatsPairStages : kARes ? 3 : kStages;        // ring stages
-    constexpr int kRingStage = kPair ? kPairBBytes : kARes ? kBBytes : kStageBytes;   // bytes per ring stage
+    constexpr int kSt = kARes ? 3 : kStages;                                   // ring stages
+    constexpr int kRingStage = kARes ? kBBytes : kStageBytes;                  // bytes per ring stage
     constexpr int kRingOff = kARes ? 8 * kABytes : 0;                          // resident A: 8 k-blocks x 16 KB
-    constexpr int kTileM = kPair ? 2 * BM : BM;                                // frames per work item
+    constexpr int kTileM = BM;                                                 // frames per work item
     uint8_t* ring = smem + kRingOff;
     float* s_bias = reinterpret_cast<float*>(ring + kSt * kRingStage);         // [2][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSt * kRingStage + 2 * BN * 4);
@@ -62,31 +57,23 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int m_tiles = (p.M + kTileM - 1) / kTileM, n_tiles = (p.N + BN - 1) / BN;
     const int num_items = m_tiles * p.splits;
     const int k_blocks = (p.K + BK - 1) / BK;
-    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-#define TASU_ITEM_LOOP for (int item = kPair ? (blockIdx.x >> 1) : blockIdx.x; item < num_items; item += kPair ? (gridDim.x >> 1) : gridDim.x)
-#define TASU_ITEM_M0 ((item / p.splits) * kTileM + (kPair ? (int)rank * BM : 0))
+#define TASU_ITEM_LOOP for (int item = blockIdx.x; item < num_items; item += gridDim.x)
+#define TASU_ITEM_M0 ((item / p.splits) * kTileM)
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kSt; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kStatsEpiThreads * (kPair ? 2 : 1)); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kStatsEpiThreads); }
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        if (kPair) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (kPair) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -96,24 +83,6 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             TASU_ITEM_LOOP {
                 const int m0 = TASU_ITEM_M0;
                 const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
-                if (kPair) {
-                    // both CTAs' frames / weight halves complete on the rank-0 barriers the MMA thread waits on
-                    mbar_wait(a_empty, a_phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(2 * k_blocks * kABytes));
-                    const uint32_t af = mapa_u32(smem_u32(a_full), 0);
-                    for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d_pair(&tmap_a, af, smem + kb * kABytes, kb * BK, m0);
-                    a_phase ^= 1;
-                    for (int nt = nb; nt < ne; ++nt) {
-                        for (int kb = 0; kb < k_blocks; ++kb) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * kRingStage));
-                            tma_load_2d_pair(&tmap_b, mapa_u32(smem_u32(&full_bar[stage]), 0), ring + stage * kRingStage,
-                                             kb * BK, nt * BN + (int)rank * (BN / 2));
-                            if (++stage == kSt) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                    continue;
-                }
                 if (kARes) {
                     mbar_wait(a_empty, a_phase ^ 1);               // MMAs of the previous item are done with A
                     mbar_expect_tx(a_full, (uint32_t)(k_blocks * kABytes));
@@ -137,15 +106,14 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && (!kPair || rank == 0)) {
+        if (lane == 0) {
             int stage = 0; uint32_t phase = 0, a_phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             TASU_ITEM_LOOP {
                 const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
                 if (kARes) { mbar_wait(a_full, a_phase); tc_fence_after(); a_phase ^= 1; }
                 for (int nt = nb; nt < ne; ++nt) {
-                    if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
-                    else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                     for (int kb = 0; kb < k_blocks; ++kb) {
@@ -156,24 +124,16 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint64_t bdesc = make_smem_desc(kARes ? sr : sr + kABytes);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
-                            if (kPair) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDescPair,
-                                                      (kb > 0 || k > 0) ? 1u : 0u);
-                            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                           (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
                         }
-                        if (kPair) {
-                            umma_commit_pair(&empty_bar[stage]);
-                            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
-                        } else {
-                            umma_commit(&empty_bar[stage]);
-                            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
-                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                         if (++stage == kSt) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
                 }
-                if (kPair) umma_commit_pair(a_empty);              // both CTAs may replace their resident frames
-                else if (kARes) umma_commit(a_empty);              // every MMA of this item has retired → A may be replaced
+                if (kARes) umma_commit(a_empty);                   // every MMA of this item has retired → A may be replaced
             }
         }
     } else if (warp >= 4) {
@@ -184,13 +144,10 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr float kL2e = 1.4426950408889634f;
         int acc = 0; uint32_t acc_phase = 0;
         int bbuf = 0;
-        // kPrefetch: this thread's bias value (column et) of the tile after the current one, in program order
+        // this thread's bias value (column et) of the tile after the current one, in program order
 #define TASU_BIAS_OF(n0_) (((n0_) + et) < p.N ? (p.bias ? __ldg(p.bias + (n0_) + et) : 0.f) : -INFINITY)
-        [[maybe_unused]] float pf_bias = 0.f;
-        if constexpr (kPrefetch) {
-            const int it0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-            if (it0 < num_items) pf_bias = TASU_BIAS_OF((it0 % p.splits) * p.nt_per * BN);
-        }
+        float pf_bias = 0.f;
+        if ((int)blockIdx.x < num_items) pf_bias = TASU_BIAS_OF(((int)blockIdx.x % p.splits) * p.nt_per * BN);
         TASU_ITEM_LOOP {
             const int split = item % p.splits;
             const int row = TASU_ITEM_M0 + ew * 32 + lane;
@@ -200,17 +157,11 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int nt = nb; nt < ne; ++nt) {
                 const int n0 = nt * BN;
                 float* sb = s_bias + bbuf * BN;
-                if constexpr (kPrefetch) {
-                    sb[et] = pf_bias;
-                    // next tile of this item, else the first tile of this CTA's next item
-                    const int nxt_item = item + (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
-                    if (nt + 1 < ne) pf_bias = TASU_BIAS_OF((nt + 1) * BN);
-                    else if (nxt_item < num_items) pf_bias = TASU_BIAS_OF((nxt_item % p.splits) * p.nt_per * BN);
-                } else
-                {
-                    const int col = n0 + et;                      // -inf masks the columns beyond the vocabulary
-                    sb[et] = col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
-                }
+                sb[et] = pf_bias;                                  // -inf masks the columns beyond the vocabulary
+                // next tile of this item, else the first tile of this CTA's next item
+                const int nxt_item = item + (int)gridDim.x;
+                if (nt + 1 < ne) pf_bias = TASU_BIAS_OF((nt + 1) * BN);
+                else if (nxt_item < num_items) pf_bias = TASU_BIAS_OF((nxt_item % p.splits) * p.nt_per * BN);
                 asm volatile("bar.sync 1, %0;" :: "n"(kStatsEpiThreads) : "memory");
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -269,8 +220,7 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (sub + 2 < sub1) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
                     else {
                         tc_fence_before();
-                        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
-                        else mbar_arrive(&tmem_empty[acc]);
+                        mbar_arrive(&tmem_empty[acc]);
                     }
                     process(vb, sub + 1);
                 }
@@ -291,222 +241,13 @@ ctc_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (kPair) cluster_sync_all();
-    if (warp == 2) {
-        tc_fence_after();
-        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
-    }
-#undef TASU_ITEM_LOOP
-#undef TASU_ITEM_M0
-#undef TASU_BIAS_OF
-}
-
-// ------------------------------------------------------------------ EXPERIMENTAL: 16 epilogue warps
-// TASU_OPT_STATS_WIDE.  profiles/r01h_ncu_detail.md: ctc_stats_kernel is epilogue-bound (the MMA thread spins ~4 M times
-// on tmem_empty) although MUFU (42 %) and the issue slots (46 %) are half idle — with two epilogue warps per scheduler the
-// fixed-latency dependency waits are exposed.  This variant runs FOUR epilogue warps per scheduler: 16 warps, each owning
-// one TMEM lane quadrant and a 64-column quarter of the 256-column tile, read as 16-column tcgen05.ld slabs so that
-// 640 threads fit the register file; the bias value of the next tile is prefetched.  Producer / MMA roles, the resident
-// A tile and the 3-stage weight ring are those of ctc_stats_kernel<true>; partials are written per (split, quarter).
-constexpr int kWideThreads = 640;                    // warps 0-3 control, warps 4-19 epilogue
-constexpr int kWideEpiThreads = 512;
-
-__global__ void __launch_bounds__(kWideThreads, 1)
-ctc_stats_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const StatsParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    constexpr int kSt = 3;
-    uint8_t* ring = smem + 8 * kABytes;                                        // resident A: 8 k-blocks x 16 KB
-    float* s_bias = reinterpret_cast<float*>(ring + kSt * kBBytes);            // [2][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSt * kBBytes + 2 * BN * 4);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kSt;
-    uint64_t* tmem_full = bars + 2 * kSt;
-    uint64_t* tmem_empty = bars + 2 * kSt + kAccStages;
-    uint64_t* a_full = bars + 2 * kSt + 2 * kAccStages;
-    uint64_t* a_empty = a_full + 1;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_full + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-    const int num_items = m_tiles * p.splits;
-    const int k_blocks = (p.K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kSt; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kWideEpiThreads); }
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
-        fence_barrier_init();
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, a_phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int m0 = (item / p.splits) * BM;
-                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
-                mbar_wait(a_empty, a_phase ^ 1);                   // MMAs of the previous item are done with A
-                mbar_expect_tx(a_full, (uint32_t)(k_blocks * kABytes));
-                for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(&tmap_a, a_full, smem + kb * kABytes, kb * BK, m0);
-                a_phase ^= 1;
-                for (int nt = nb; nt < ne; ++nt) {
-                    for (int kb = 0; kb < k_blocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes);
-                        tma_load_2d(&tmap_b, &full_bar[stage], ring + stage * kBBytes, kb * BK, nt * BN);
-                        if (++stage == kSt) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, a_phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int nb = (item % p.splits) * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
-                mbar_wait(a_full, a_phase); tc_fence_after(); a_phase ^= 1;
-                for (int nt = nb; nt < ne; ++nt) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < k_blocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint64_t adesc = make_smem_desc(smem_u32(smem + kb * kABytes));
-                        const uint64_t bdesc = make_smem_desc(smem_u32(ring + stage * kBBytes));
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                      (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
-                        if (++stage == kSt) { stage = 0; phase ^= 1; }
-                    }
-                    if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-                }
-                umma_commit(a_empty);
-            }
-        }
-    } else if (warp >= 4) {
-        // 16 epilogue warps: warps (q, q+4, q+8, q+12) share TMEM lane quadrant q; `quarter` selects 64 of the 256 columns
-        const int ew = (warp - 4) & 3, quarter = (warp - 4) >> 2;
-        const int et = threadIdx.x - 128;                          // 0..511; threads 0..255 stage the bias
-        constexpr float kL2e = 1.4426950408889634f;
-        int acc = 0; uint32_t acc_phase = 0;
-        int bbuf = 0;
-        auto bias_of = [&](int n0) {                               // -inf masks the columns beyond the vocabulary
-            const int col = n0 + et;
-            return col < p.N ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
-        };
-        float pf_bias = 0.f;                                       // bias of the NEXT tile (column et), fetched one tile ahead
-        if (et < BN && (int)blockIdx.x < num_items) pf_bias = bias_of(((int)blockIdx.x % p.splits) * p.nt_per * BN);
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const int m_tile = item / p.splits, split = item % p.splits;
-            const int row = m_tile * BM + ew * 32 + lane;
-            const int nb = split * p.nt_per, ne = min(nb + p.nt_per, n_tiles);
-            float rm = -INFINITY, rs = 0.f, rs2 = 0.f, xb = 0.f;
-            int best = 0x7fffffff;
-            for (int nt = nb; nt < ne; ++nt) {
-                const int n0 = nt * BN;
-                float* sb = s_bias + bbuf * BN;
-                if (et < BN) {
-                    sb[et] = pf_bias;
-                    const int nxt_item = item + (int)gridDim.x;
-                    if (nt + 1 < ne) pf_bias = bias_of((nt + 1) * BN);
-                    else if (nxt_item < num_items) pf_bias = bias_of((nxt_item % p.splits) * p.nt_per * BN);
-                }
-                asm volatile("bar.sync 1, %0;" :: "n"(kWideEpiThreads) : "memory");
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-
-                auto process = [&](uint32_t (&v)[16], int sub) {   // sub = index of the 16-column slab in the tile
-                    const int base = n0 + sub * 16;
-                    if (base >= p.N) return;
-                    const float4* b4 = reinterpret_cast<const float4*>(sb + sub * 16);
-                    float x[16];
-                    float cm = -INFINITY;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bb = b4[q];
-                        x[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
-                        x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-                        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-                        x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
-                        cm = fmaxf(cm, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
-                    }
-                    if (cm > rm) {
-                        const float f = ex2_approx((rm - cm) * kL2e);      // rm = -inf on the first slab: 2^-inf = 0
-                        rs *= f;
-                        rs2 *= f * f;
-                        rm = cm;
-                        int j0 = 15;
-#pragma unroll
-                        for (int j = 14; j >= 0; --j) j0 = (x[j] == cm) ? j : j0;
-                        best = base + j0;                          // first index of the maximum (torch tie rule)
-                    }
-                    const float mb = rm * kL2e;
-                    float acc_s = 0.f, acc_s2 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float e = ex2_approx(fmaf(x[j], kL2e, -mb));
-                        acc_s += e;
-                        acc_s2 = fmaf(e, e, acc_s2);
-                    }
-                    rs += acc_s;
-                    rs2 += acc_s2;
-                    if (p.blank >= base && p.blank < base + 16) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) xb = (base + j == p.blank) ? x[j] : xb;
-                    }
-                };
-
-                uint32_t va[16], vb[16];
-                const int sub0 = quarter * 4, sub1 = sub0 + 4;             // this warp's four 16-column slabs
-                tmem_ld16(t_row + (uint32_t)(sub0 * 16), va);
-#pragma unroll 1
-                for (int sub = sub0; sub < sub1; sub += 2) {
-                    tmem_ld_wait16(va);
-                    tmem_ld16(t_row + (uint32_t)((sub + 1) * 16), vb);
-                    process(va, sub);
-                    tmem_ld_wait16(vb);
-                    if (sub + 2 < sub1) tmem_ld16(t_row + (uint32_t)((sub + 2) * 16), va);
-                    else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
-                    process(vb, sub + 1);
-                }
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-                bbuf ^= 1;
-            }
-            if (row < p.M) {
-                const int64_t o = (int64_t)(split * 4 + quarter) * p.M + row;  // ascending column order of the partials
-                p.part_max[o] = rm;
-                p.part_sum[o] = rs;
-                p.part_sum2[o] = rs2;
-                p.part_arg[o] = best;
-                const int bt = p.blank / BN, bq = (p.blank % BN) / (BN / 4);
-                if (bt >= nb && bt < ne && bq == quarter) p.xb_raw[row] = xb;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
     }
+#undef TASU_ITEM_LOOP
+#undef TASU_ITEM_M0
+#undef TASU_BIAS_OF
 }
 
 // merge the per-split partial statistics and drop the prefix frames: frame (b,t) ↔ raw row b*(T+P)+P+t
@@ -520,34 +261,6 @@ ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __r
     const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
     float m = -INFINITY; int a = 0x7fffffff;
     const int parts = 2 * p.splits;                                        // (split, column half), ascending columns
-    for (int s = 0; s < parts; ++s) {
-        const float pm = p.part_max[(int64_t)s * p.M + r];
-        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
-    }
-    float sum = 0.f, sum2 = 0.f;
-    for (int s = 0; s < parts; ++s) {
-        const float f = exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
-        sum += p.part_sum[(int64_t)s * p.M + r] * f;
-        sum2 += p.part_sum2[(int64_t)s * p.M + r] * f * f;
-    }
-    if (row_sumexp2) row_sumexp2[i] = sum2;
-    argmax[i] = a;
-    x_blank[i] = p.xb_raw[r];
-    row_max[i] = m;
-    row_sumexp[i] = sum;
-}
-
-// the same merge for ctc_stats_wide_kernel: four column quarters per split
-__global__ void __launch_bounds__(256)
-ctc_stats_combine_wide_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __restrict__ argmax,
-                              float* __restrict__ x_blank, float* __restrict__ row_max, float* __restrict__ row_sumexp,
-                              float* __restrict__ row_sumexp2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * T) return;
-    const int b = (int)(i / T), t = (int)(i % T);
-    const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
-    float m = -INFINITY; int a = 0x7fffffff;
-    const int parts = 4 * p.splits;                                        // (split, column quarter), ascending columns
     for (int s = 0; s < parts; ++s) {
         const float pm = p.part_max[(int64_t)s * p.M + r];
         if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
@@ -586,9 +299,8 @@ static void pick_splits(int m_tiles, int n_tiles, int grid, int* splits, int* nt
 
 extern "C" int64_t tasu_ctc_head_stats_workspace(int B, int T, int n_prefix) {
     const int64_t rows = (int64_t)B * (T + n_prefix);
-    // up to 32 partials per frame (8 vocabulary splits x 4 column quarters of the wide kernel; the default kernel uses
-    // 16 = 8 splits x 2 halves) x (max, sum, sum2, arg) + blank logits
-    return rows * 32 * 16 + rows * 4 + 256;
+    // 16 partials per frame (8 vocabulary splits x 2 column halves) x (max, sum, sum2, arg) + blank logits
+    return rows * 16 * 16 + rows * 4 + 256;
 }
 
 extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* w_bf16, int64_t ldw, const float* bias,
@@ -611,21 +323,13 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
     if (rc) return rc;
     rc = make_map(&mb, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V, K, ldw, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
-    // EXPERIMENTAL CTA-pair mode (TASU_OPT_GEMM_PAIR bit 2): 256 frames per work item, clusters of two CTAs
-    const bool pair = (option(TASU_OPT_GEMM_PAIR) & 4) != 0 && K <= 8 * BK && M > BM && sm_count() >= 2;
-    if (pair) {
-        rc = make_map(&mb, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V, K, ldw, BN / 2, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-        if (rc) return rc;
-    }
-    const int m_tiles = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
-    int grid = pair ? sm_count() / 2 : sm_count();           // pair mode: clusters
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
+    int grid = sm_count();
     StatsParams p{};
     p.M = M; p.N = V; p.K = K; p.blank = blank_id; p.bias = bias;
     pick_splits(m_tiles, n_tiles, grid, &p.splits, &p.nt_per);
     if (grid > m_tiles * p.splits) grid = m_tiles * p.splits;
-    // EXPERIMENTAL 16-epilogue-warp kernel (TASU_OPT_STATS_WIDE): four partials per split instead of two
-    const bool wide = option(TASU_OPT_STATS_WIDE) != 0 && !pair && K <= 8 * BK;
-    const int64_t cap = wide ? 32 : 16;                      // partial slots per frame in the workspace layout
+    const int64_t cap = 16;                                  // partial slots per frame in the workspace layout
     float* ws = reinterpret_cast<float*>(workspace);
     p.part_max = ws;
     p.part_sum = ws + cap * M;
@@ -641,52 +345,7 @@ extern "C" int tasu_ctc_head_stats(const void* x_bf16, int64_t ldx, const void* 
             attr_err = cudaFuncSetAttribute(ctc_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytes);
     });
     TASU_CHECK_CUDA(attr_err);
-    const bool prefetch = (option(TASU_OPT_EPI_PREFETCH) & 2) != 0;
-    if (wide) {
-        static std::once_flag once_wide;
-        static cudaError_t attr_err_wide = cudaSuccess;
-        std::call_once(once_wide, [&] {
-            attr_err_wide = cudaFuncSetAttribute(ctc_stats_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesARes);
-        });
-        TASU_CHECK_CUDA(attr_err_wide);
-        ctc_stats_wide_kernel<<<grid, kWideThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
-        TASU_CHECK_LAUNCH();
-        const int64_t frames_w = (int64_t)B * T;
-        ctc_stats_combine_wide_kernel<<<(unsigned)((frames_w + 255) / 256), 256, 0, st>>>(p, B, T, n_prefix, argmax, x_blank, row_max,
-                                                                                      row_sumexp, row_sumexp2);
-        TASU_CHECK_LAUNCH();
-        return TASU_OK;
-    }
-    if (prefetch && !pair && K <= 8 * BK) {
-        auto kern = ctc_stats_kernel<true, false, true>;
-        static std::once_flag once_pf;
-        static cudaError_t attr_err_pf = cudaSuccess;
-        std::call_once(once_pf, [&] {
-            attr_err_pf = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesARes);
-        });
-        TASU_CHECK_CUDA(attr_err_pf);
-        kern<<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
-    } else if (pair) {
-        static_assert(kStatsSmemBytesPair <= 227 * 1024, "pair-mode shared memory exceeds the 227 KB a CTA can opt into");
-        auto kern = ctc_stats_kernel<true, true>;
-        static std::once_flag once_pair;
-        static cudaError_t attr_err_pair = cudaSuccess;
-        std::call_once(once_pair, [&] {
-            attr_err_pair = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmemBytesPair);
-        });
-        TASU_CHECK_CUDA(attr_err_pair);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2u * (unsigned)grid);
-        cfg.blockDim = dim3(kStatsThreads);
-        cfg.dynamicSmemBytes = kStatsSmemBytesPair;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
-    } else if (K <= 8 * BK) ctc_stats_kernel<true><<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
+    if (K <= 8 * BK) ctc_stats_kernel<true><<<grid, kStatsThreads, kStatsSmemBytesARes, st>>>(ma, mb, p);
     else ctc_stats_kernel<false><<<grid, kStatsThreads, kStatsSmemBytes, st>>>(ma, mb, p);
     TASU_CHECK_LAUNCH();
     const int64_t frames = (int64_t)B * T;

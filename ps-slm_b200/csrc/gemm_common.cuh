@@ -131,20 +131,6 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-}
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -213,7 +199,6 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 // instruction descriptor of the pair MMA: M = 256 (128 rows per CTA), N = 256
 constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 constexpr int kPairStages = 6;                              // deep K: 6 x 32 KB stages, one epilogue group
-constexpr int kPairStagesShallow = 4;                       // K <= 1024 (store-heavy): 4 stages, two epilogue groups
 constexpr int kPairBBytes = (BN / 2) * BK * 2;              // each CTA loads half of the B tile: 16 KB
 constexpr int kPairStageBytes = kABytes + kPairBBytes;      // 32 KB
 constexpr int gemm_smem_bytes_pair(int stages, int groups) {
@@ -278,10 +263,6 @@ static int check_common(const void* A, int64_t lda, const void* B, int64_t ldb, 
     TASU_CHECK_ARG(epilogue != TASU_EPI_SOFTMAX || (row_rstd && row_mean), "softmax row vectors required");
     return TASU_OK;
 }
-
-// EXPERIMENTAL 16-epilogue-warp shallow-K GEMM (gemm_wide_sm100.cu), bf16 output
-int launch_wide_epi(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N, int K,
-                    const Params& p, cudaStream_t st);
 
 }  // namespace gemm
 }  // namespace tasu

@@ -30,13 +30,12 @@ namespace gemm {
 // kPair: CTA-pair mode (launched as clusters of 2): one tcgen05.mma.cta_group::2 of M = 256 per 256x256 pair tile;
 //        each CTA stages its own 128 rows of A and 128 of the 256 B rows (32 KB per stage instead of 48 KB, a third
 //        less L2->smem traffic per flop), the rank-0 CTA issues the MMAs and multicasts its commits to both CTAs,
-//        every CTA runs the epilogue of its own 128 accumulator rows.  EXPERIMENTAL: see tasu_set_option.
-// kPrefetch (EXPERIMENTAL, TASU_OPT_EPI_PREFETCH): the epilogue fetches the bias / colsum / row-statistics values of
-//        its NEXT tile into registers while it processes the current one, instead of loading them at the top of every
-//        tile.  For K = 512 a tile lasts ~2 us and the exposed L2 latency of those loads is the largest single stall
-//        of the kept-frame softmax GEMM (profiles/r01h_ncu_detail.md).  Same values, same arithmetic: results are
-//        bit-identical to the default kernel.
-template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false, bool kPrefetch = false>
+//        every CTA runs the epilogue of its own 128 accumulator rows.
+//        Default for deep-K problems (K > 1024, M > 128): projector GEMM-1 runs 7 % faster than with one CTA per tile
+//        (profiles/r02a_ab.md); for K <= 1024 the pair kernel measured 11 % SLOWER and is not instantiated.
+// Variants measured and removed in round 2 (profiles/r02a_ab.md): epilogue vectors of the next tile prefetched (no
+// change for the kept-frame softmax GEMM), 16 independent epilogue warps with warp-private TMA stores (+6 % time).
+template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false>
 __global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -183,39 +182,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int sw = et & 7;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
-        // kPrefetch: values of the NEXT tile, fetched one tile ahead (column c = et + i * kEpiThreads of the tile)
-        constexpr bool kLnFold = kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD;
-        constexpr bool kRowVec = kLnFold || kEpi == TASU_EPI_SOFTMAX;
-        float pf_bias[BN / kEpiThreads], pf_colsum[BN / kEpiThreads], pf_rstd = 1.f, pf_mean = 0.f;
-        auto prefetch_tile = [&](int t) {
-            const int pm0 = (t / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0), pn0 = (t % n_tiles) * BN;
-#pragma unroll
-            for (int i = 0; i < BN / kEpiThreads; ++i) {
-                const int col = pn0 + et + i * kEpiThreads;
-                pf_bias[i] = (kEpi != TASU_EPI_NONE && col < p.N) ? __ldg(p.bias + col) : 0.f;
-                pf_colsum[i] = (kLnFold && col < p.N) ? __ldg(p.colsum + col) : 0.f;
-            }
-            pf_rstd = 1.f; pf_mean = 0.f;
-            if (kRowVec && pm0 + et < M_live) { pf_rstd = __ldg(p.row_rstd + pm0 + et); pf_mean = __ldg(p.row_mean + pm0 + et); }
-        };
-        if (kPrefetch) {
-            const int t0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-            if (t0 < num_tiles) prefetch_tile(t0);
-        }
         TASU_TILE_LOOP {
             const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
             const int grow = m0 + et;
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
-            if (kPrefetch) {
-                if (kEpi != TASU_EPI_NONE) {
-#pragma unroll
-                    for (int i = 0; i < BN / kEpiThreads; ++i) {
-                        s_bias[et + i * kEpiThreads] = pf_bias[i] * (kEpi == TASU_EPI_SOFTMAX ? kLog2e : 1.f);
-                        if (kLnFold) s_colsum[et + i * kEpiThreads] = pf_colsum[i];
-                    }
-                }
-            } else
             if (kEpi != TASU_EPI_NONE) {
                 for (int c = et; c < BN; c += kEpiThreads) {   // each group stages its own copy (own barrier)
                     const int col = n0 + c;
@@ -225,12 +196,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             float rstd = 1.f, nmean = 0.f;
-            if (kPrefetch) {
-                rstd = pf_rstd; nmean = -pf_mean;
-                // the next tile's values are in flight while this tile is processed
-                const int nxt = tile + (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
-                if (nxt < num_tiles) prefetch_tile(nxt);
-            } else
             if ((kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD || kEpi == TASU_EPI_SOFTMAX) && grow < M_live) {
                 rstd = __ldg(p.row_rstd + grow); nmean = -__ldg(p.row_mean + grow);
             }
@@ -396,25 +361,10 @@ static int launch_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CU
     return TASU_OK;
 }
 
-// EXPERIMENTAL (TASU_OPT_EPI_PREFETCH bit 0): shallow-K configuration with the epilogue vectors fetched one tile ahead
-template <bool kOutBf16, int kEpi>
-static int launch_one_prefetch(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
-                               const Params& p) {
-    constexpr int smem = gemm_smem_bytes(3, 2);
-    auto kern = gemm_bf16_tn_kernel<kOutBf16, kEpi, 3, 2, 0, false, true>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-    TASU_CHECK_CUDA(attr_err);
-    kern<<<grid, 128 + 128 * 2, smem, st>>>(ma, mb, mc, p);
-    return TASU_OK;
-}
-
 // deep-K shapes: 4 smem stages, one epilogue group; shallow-K (store-heavy) shapes: 3 stages, two epilogue groups
 template <bool kOutBf16, int kEpi>
 static int launch_cfg(bool shallow_k, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                       const CUtensorMap& mc, const Params& p) {
-    if (shallow_k && (option(TASU_OPT_EPI_PREFETCH) & 1) != 0) return launch_one_prefetch<kOutBf16, kEpi>(grid, st, ma, mb, mc, p);
     return shallow_k ? launch_one<kOutBf16, kEpi, 3, 2>(grid, st, ma, mb, mc, p)
                      : launch_one<kOutBf16, kEpi, 4, 1>(grid, st, ma, mb, mc, p);
 }
@@ -439,7 +389,7 @@ static int launch_dispatch(bool out_bf16, int epilogue, bool shallow_k, int grid
                     : launch_epi<false>(epilogue, shallow_k, grid, st, ma, mb, mc, p);
 }
 
-// CTA-pair mode (EXPERIMENTAL, TASU_OPT_GEMM_PAIR): clusters of two CTAs, one 256x256 tile per cluster
+// CTA-pair mode (deep-K shapes; TASU_OPT_GEMM_PAIR = 0 turns it off): clusters of two CTAs, one 256x256 tile per cluster
 template <bool kOutBf16, int kEpi, int kSt, int kGroups>
 static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                            const CUtensorMap& mc, const Params& p) {
@@ -465,25 +415,20 @@ static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma,
     return TASU_OK;
 }
 
-template <bool kOutBf16, int kEpi>
-static int launch_pair_cfg(bool shallow_k, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
-                           const CUtensorMap& mc, const Params& p) {
-    return shallow_k ? launch_pair_one<kOutBf16, kEpi, kPairStagesShallow, 2>(clusters, st, ma, mb, mc, p)
-                     : launch_pair_one<kOutBf16, kEpi, kPairStages, 1>(clusters, st, ma, mb, mc, p);
-}
-
 template <bool kOutBf16>
-static int launch_pair_epi(int epilogue, bool sk, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
+static int launch_pair_epi(int epilogue, int clusters, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                            const CUtensorMap& mc, const Params& p) {
+#define TASU_PAIR(E) launch_pair_one<kOutBf16, E, kPairStages, 1>(clusters, st, ma, mb, mc, p)
     switch (epilogue) {
-        case TASU_EPI_NONE: return launch_pair_cfg<kOutBf16, TASU_EPI_NONE>(sk, clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS>(sk, clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_SILU: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS_SILU>(sk, clusters, st, ma, mb, mc, p);
-        case TASU_EPI_BIAS_RELU: return launch_pair_cfg<kOutBf16, TASU_EPI_BIAS_RELU>(sk, clusters, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD_SILU: return launch_pair_cfg<kOutBf16, TASU_EPI_LNFOLD_SILU>(sk, clusters, st, ma, mb, mc, p);
-        case TASU_EPI_LNFOLD: return launch_pair_cfg<kOutBf16, TASU_EPI_LNFOLD>(sk, clusters, st, ma, mb, mc, p);
-        default: return launch_pair_cfg<kOutBf16, TASU_EPI_SOFTMAX>(sk, clusters, st, ma, mb, mc, p);
+        case TASU_EPI_NONE: return TASU_PAIR(TASU_EPI_NONE);
+        case TASU_EPI_BIAS: return TASU_PAIR(TASU_EPI_BIAS);
+        case TASU_EPI_BIAS_SILU: return TASU_PAIR(TASU_EPI_BIAS_SILU);
+        case TASU_EPI_BIAS_RELU: return TASU_PAIR(TASU_EPI_BIAS_RELU);
+        case TASU_EPI_LNFOLD_SILU: return TASU_PAIR(TASU_EPI_LNFOLD_SILU);
+        case TASU_EPI_LNFOLD: return TASU_PAIR(TASU_EPI_LNFOLD);
+        default: return TASU_PAIR(TASU_EPI_SOFTMAX);
     }
+#undef TASU_PAIR
 }
 
 template <int kSt, int kGroups, int kMajor>
@@ -552,15 +497,8 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     const int csz = c_dtype == TASU_F32 ? 4 : 2;
     TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
     TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
-    // EXPERIMENTAL 16-epilogue-warp kernel for the store-heavy shallow-K shapes with bf16 output (TASU_OPT_GEMM_WIDE_EPI)
-    if (option(TASU_OPT_GEMM_WIDE_EPI) != 0 && K <= 1024 && c_dtype == TASU_BF16) {
-        Params pw{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
-        return launch_wide_epi(A, lda, B, ldb, C, ldc, M, N, K, pw, (cudaStream_t)stream);
-    }
-    // EXPERIMENTAL CTA-pair mode (off unless TASU_OPT_GEMM_PAIR is set; bit 0: deep-K shapes, bit 1: K <= 1024),
-    // for problems with more than one 128-row tile
-    const int pair_opt = option(TASU_OPT_GEMM_PAIR);
-    const bool pair = (pair_opt & (K > 1024 ? 1 : 2)) != 0 && M > BM && sm_count() >= 2;
+    // CTA-pair mode for deep-K problems with more than one 128-row tile (TASU_OPT_GEMM_PAIR, default 1)
+    const bool pair = option(TASU_OPT_GEMM_PAIR) != 0 && K > 1024 && M > BM && sm_count() >= 2;
     CUtensorMap ma, mb, mc;
     rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
@@ -575,8 +513,8 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
         int clusters = sm_count() / 2;
         if (clusters > pair_tiles) clusters = pair_tiles;
         cudaStream_t pst = (cudaStream_t)stream;
-        rc = c_dtype == TASU_BF16 ? launch_pair_epi<true>(epilogue, K <= 1024, clusters, pst, ma, mb, mc, p)
-                                  : launch_pair_epi<false>(epilogue, K <= 1024, clusters, pst, ma, mb, mc, p);
+        rc = c_dtype == TASU_BF16 ? launch_pair_epi<true>(epilogue, clusters, pst, ma, mb, mc, p)
+                                  : launch_pair_epi<false>(epilogue, clusters, pst, ma, mb, mc, p);
         if (rc) return rc;
         TASU_CHECK_LAUNCH();
         return TASU_OK;

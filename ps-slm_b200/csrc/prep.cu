@@ -212,7 +212,8 @@ gather_kept_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B,
 // multi-frame candidates only: probs[r] = mean over its frames, in place; LayerNorm statistics of the result.
 // Work list = multi_rows[0, *multi_count) (any order) or, without it, every row with pk_len > 1.
 __global__ void __launch_bounds__(256, 5)
-pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n_out, const int32_t* __restrict__ pk_len,
+pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n_out, int64_t max_rows,
+                 const int32_t* __restrict__ pk_len,
                  const int32_t* __restrict__ tail_src, const int32_t* __restrict__ multi_rows,
                  const int32_t* __restrict__ multi_count, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
     __shared__ float red[8];
@@ -221,6 +222,9 @@ pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n
         const int64_t r = multi_rows != nullptr ? (int64_t)multi_rows[it] : it;
         const int n = pk_len[r];
         if (n <= 1) continue;                                  // CTA-uniform
+        // a row whose frames do not all fit the compact matrix (capacity exceeded: the host redoes the batch with
+        // larger buffers) is left alone — nothing is read or written beyond max_rows
+        if (r >= max_rows || (int64_t)tail_src[r] + (n - 1) > max_rows) continue;
         __nv_bfloat16* row = probs + r * ld;
         const __nv_bfloat16* tail = probs + (int64_t)tail_src[r] * ld;
         const float inv = 1.f / (float)n;
@@ -288,6 +292,35 @@ pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n
             ln_mean[r] = mean;
             ln_rstd[r] = rsqrtf(var + eps);
         }
+    }
+}
+
+// Content fingerprint of up to 8 buffers (weight-cache validation): 4096 evenly spaced 32-bit words of every buffer,
+// each multiplied by an odd constant that depends on its sample index, summed modulo 2^64.  One CTA; thread 0 stores
+// the result with a plain store, so `out` may live in pinned host memory.
+struct FingerprintArgs { const uint32_t* ptr[8]; int64_t words[8]; int n; };
+constexpr int kFpSamples = 4096;
+
+__global__ void __launch_bounds__(1024)
+fingerprint_kernel(const FingerprintArgs a, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long red[32];
+    unsigned long long h = 0;
+    for (int i = threadIdx.x; i < a.n * kFpSamples; i += blockDim.x) {
+        const int t = i / kFpSamples, k = i % kFpSamples;
+        const int64_t w = a.words[t];
+        if (w <= 0 || (w < kFpSamples && k >= w)) continue;
+        const int64_t idx = w <= kFpSamples ? k : ((int64_t)k * (w - 1)) / (kFpSamples - 1);
+        const unsigned long long v = a.ptr[t][idx];
+        h += (v + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ull + 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        *out = s;
     }
 }
 
@@ -387,12 +420,12 @@ extern "C" int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int
     return TASU_OK;
 }
 
-extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, const int32_t* pk_len,
+extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, int64_t max_rows, const int32_t* pk_len,
                               const int32_t* tail_src, const int32_t* multi_rows, const int32_t* multi_count,
                               float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
-    TASU_CHECK_ARG(D > 0 && ld >= D && n_out >= 0, "shape");
+    TASU_CHECK_ARG(D > 0 && ld >= D && n_out >= 0 && max_rows >= 0, "shape");
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
-    if (n_out == 0) return TASU_OK;
+    if (n_out == 0 || max_rows == 0) return TASU_OK;
     TASU_CHECK_ARG(probs_bf16 && pk_len && tail_src, "null pointer");
     TASU_CHECK_ARG(((uintptr_t)probs_bf16 % 16 == 0) && (ld % 8 == 0), "16-byte aligned rows");
     TASU_CHECK_ARG((multi_rows == nullptr) == (multi_count == nullptr), "multi_rows / multi_count come in pairs");
@@ -400,7 +433,7 @@ extern "C" int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out
     // scheduler then balances the ~2 k multi-frame rows dynamically — a persistent grid of SMs x occupancy CTAs leaves
     // half the machine idle while the CTAs that drew 3 rows instead of 2 finish.
     const int64_t grid = n_out < 0x7fffffffLL ? n_out : 0x7fffffffLL;
-    pool_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, pk_len,
+    pool_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)probs_bf16, ld, D, n_out, max_rows, pk_len,
                                                                          tail_src, multi_rows, multi_count, ln_mean,
                                                                          ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();
@@ -421,6 +454,22 @@ extern "C" int tasu_softmax_rows(const void* x, int x_dtype, int64_t x_row_strid
     else
         softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, x_row_stride, rows, V, row_max, row_sumexp,
                                                                  (__nv_bfloat16*)out_bf16, out_row_stride);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_fingerprint(const void* const* ptrs_host, const int64_t* nbytes_host, int n, uint64_t* out, void* stream) {
+    TASU_CHECK_ARG(n >= 0 && n <= 8, "at most 8 buffers per call");
+    TASU_CHECK_ARG(out != nullptr && (n == 0 || (ptrs_host && nbytes_host)), "null pointer");
+    FingerprintArgs a{};
+    a.n = n;
+    for (int i = 0; i < n; ++i) {
+        TASU_CHECK_ARG(nbytes_host[i] >= 0 && (nbytes_host[i] == 0 || ptrs_host[i] != nullptr), "buffer");
+        TASU_CHECK_ARG((uintptr_t)ptrs_host[i] % 4 == 0, "4-byte aligned buffers");
+        a.ptr[i] = (const uint32_t*)ptrs_host[i];
+        a.words[i] = nbytes_host[i] / 4;
+    }
+    fingerprint_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, (unsigned long long*)out);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -156,6 +156,35 @@ attn_ds_kernel(const __nv_bfloat16* __restrict__ P, int64_t pstride, const float
     }
 }
 
+
+// dst[i] = cast(scale * src[i]) over a flat buffer (gradient wire format: fp32 -> bf16 before the all-reduce, bf16 -> fp32
+// with the 1/world averaging factor after it).  8 elements per thread, 128-bit accesses on the aligned body.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+flat_scale_cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int64_t n, float scale) {
+    const int64_t n8 = n / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        if constexpr (sizeof(TI) == 4) {
+            const uint4 a = ld_stream_u4(reinterpret_cast<const uint4*>(src) + 2 * i), b = ld_stream_u4(reinterpret_cast<const uint4*>(src) + 2 * i + 1);
+            v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+            v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+        } else {
+            unpack16(ld_stream_u4(reinterpret_cast<const uint4*>(src) + i), v, __nv_bfloat16());
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= scale;
+        if constexpr (sizeof(TO) == 4) {
+            reinterpret_cast<uint4*>(dst)[2 * i] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+            reinterpret_cast<uint4*>(dst)[2 * i + 1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+        } else {
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+    }
+    for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = from_f32<TO>(to_f32(src[i]) * scale);
+}
+
 }  // namespace tasu
 
 using namespace tasu;
@@ -369,6 +398,24 @@ extern "C" int tasu_sum_epilogue(const float* parts, int n_parts, int64_t part_s
         tasu::sum_epilogue_kernel<float><<<grid, 256, 0, st>>>(parts, n_parts, part_stride, M, N, ldp, epilogue, bias, row_rstd, row_mean, colsum, (float*)out, ldo);
     else
         tasu::sum_epilogue_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(parts, n_parts, part_stride, M, N, ldp, epilogue, bias, row_rstd, row_mean, colsum, (__nv_bfloat16*)out, ldo);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_flat_scale_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, float scale, void* stream) {
+    TASU_CHECK_ARG(n >= 0, "n >= 0");
+    TASU_CHECK_ARG((src_dtype == TASU_F32 || src_dtype == TASU_BF16) && (dst_dtype == TASU_F32 || dst_dtype == TASU_BF16), "dtype");
+    if (n == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && dst, "null pointer");
+    TASU_CHECK_ARG((uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "16-byte aligned buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = (n / 8 + 255) / 256, gmax = (int64_t)tasu::sm_count() * 16;
+    if (g > gmax) g = gmax;
+    if (g < 1) g = 1;
+    if (src_dtype == TASU_F32 && dst_dtype == TASU_BF16) flat_scale_cast_kernel<float, __nv_bfloat16><<<(unsigned)g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n, scale);
+    else if (src_dtype == TASU_BF16 && dst_dtype == TASU_F32) flat_scale_cast_kernel<__nv_bfloat16, float><<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n, scale);
+    else if (src_dtype == TASU_F32) flat_scale_cast_kernel<float, float><<<(unsigned)g, 256, 0, st>>>((const float*)src, (float*)dst, n, scale);
+    else flat_scale_cast_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n, scale);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -126,24 +126,126 @@ def _gather_rows(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return flat.index_select(0, idx.long())
 
 
-def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing=None, return_host: bool = False):
-    """Gather every rank's packed compressed rows ``[sum M_b, H]`` and lengths.
+_PINNED = {}
 
-    Returns ``(rows_global [sum over all utterances, H], lens_global [n_utts])`` in GLOBAL utterance
-    order (utterance i lives on rank i % W).  Two small collectives for the lengths, ONE host read of them,
-    ONE padded-to-max all-gather of the payload (on NVSwitch a flat all-gather is bandwidth-optimal, no
-    topology-aware ring needed) and one row-gather kernel that puts the rows in global order."""
+
+def _pinned_i64(n: int, slot: int = 0) -> torch.Tensor:
+    """Small ring of reusable pinned int64 host buffers (pinning memory per call costs more than the exchange itself)."""
+    key = (slot, max(64, 1 << (max(n, 1) - 1).bit_length()))
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.empty(key[1], dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        _PINNED[key] = buf
+    return buf[:n]
+
+
+class PackedGather:
+    """Result of ``gather_packed``: the flat all-gather buffer of every rank's packed rows (rank r's rows start at row
+    ``r * slab_rows``), the gathered lengths on the device (``all_lens [W, b_max]`` int64) and on the host
+    (``lens_host``: numpy [n_global] in GLOBAL utterance order, utterance i = rank i % W, local index i // W)."""
+    __slots__ = ("flat", "all_lens", "lens_host", "slab_rows", "W", "b_max", "n_global")
+
+    def select(self, sel: Optional[Sequence[int]] = None):
+        """Rows and lengths of the utterances ``sel`` (global ids, in that order; None = all, global order):
+        ``(rows [sum len, H], lens int64 [n_sel])`` — ``tasu_packed_select`` copies them straight out of the
+        all-gather buffer (2 launches; only the ≤ n_sel utterance ids travel to the device)."""
+        import numpy as np
+        n_sel = self.n_global if sel is None else len(sel)
+        H = self.flat.shape[1]
+        dev = self.flat.device
+        sel_np = np.arange(self.n_global, dtype=np.int64) if sel is None else np.asarray(sel, dtype=np.int64)
+        lens_sel = self.lens_host[sel_np] if n_sel else np.zeros(0, dtype=np.int64)
+        total = int(lens_sel.sum())
+        if not self.flat.is_cuda:                                # CPU (gloo) tests: plain indexing
+            r_of, j_of = sel_np % self.W, sel_np // self.W
+            local_off = np.zeros((self.W, self.b_max + 1), dtype=np.int64)
+            lens2 = np.zeros((self.W, self.b_max), dtype=np.int64)
+            gi = np.arange(self.n_global)
+            lens2[gi % self.W, gi // self.W] = self.lens_host
+            local_off[:, 1:] = np.cumsum(lens2, axis=1)
+            starts = r_of * self.slab_rows + local_off[r_of, j_of]
+            idx = torch.from_numpy(concat_ranges(starts, lens_sel))
+            return _gather_rows(self.flat, idx), torch.from_numpy(lens_sel.copy())
+        from . import _lib as L
+        from . import ops
+        out = torch.empty(max(total, 1), H, dtype=self.flat.dtype, device=dev)[:total]
+        out_lens = torch.empty(max(n_sel, 1), dtype=torch.int64, device=dev)[:n_sel]
+        ws = torch.empty(self.W * self.b_max + 2 * n_sel + 1, dtype=torch.int32, device=dev)
+        sel_dev = None
+        if sel is not None and n_sel:
+            host = _pinned_i64(n_sel, slot=1)
+            host.copy_(torch.from_numpy(sel_np))
+            sel_dev = host.to(dev, non_blocking=True).to(torch.int32)
+        L.check(L.lib().tasu_packed_select(self.flat.data_ptr(), ops._dt(self.flat), self.flat.stride(0), self.slab_rows, H,
+                                           self.all_lens.data_ptr(), self.W, self.b_max, self.n_global,
+                                           sel_dev.data_ptr() if sel_dev is not None else None, n_sel, out.data_ptr(), H,
+                                           total, out_lens.data_ptr(), ws[-1:].data_ptr(), ws.data_ptr(), ops._stream()),
+                "tasu_packed_select")
+        ops._count(2)
+        return out, out_lens
+
+
+def gather_packed(rows: torch.Tensor, lens: torch.Tensor, n_global: Optional[int] = None, group=None,
+                  timing=None) -> PackedGather:
+    """All-gather every rank's packed compressed rows ``[sum M_b, H]`` and lengths (north star: the only data-path
+    collectives of inference).  One fixed-shape all-gather of the lengths, ONE device→host read of them (pinned,
+    reused buffer), one all-gather of the payload padded to the largest rank's row count (on NVSwitch a flat all-gather
+    is bandwidth-optimal).  ``n_global``: number of utterances of the global batch when known (utterance i lives on
+    rank i % W); without it the per-rank counts are exchanged first.  ``timing``: list that receives
+    ``(start event, end event, bytes received per rank)`` of the payload all-gather."""
+    import numpy as np
     rank, W = world()
-    if W == 1:
-        return (rows, lens, lens.tolist()) if return_host else (rows, lens)
-    all_lens = all_gather_lengths(lens, group)
-    lens_host = [l.cpu() for l in all_lens]                      # the single device→host hand-off
-    totals = [int(l.sum()) for l in lens_host]
-    m = max(totals + [1])
+    n_local = lens.numel()
+    if n_global is None:
+        if W == 1:
+            n_global = n_local
+        else:
+            cnt = torch.tensor([n_local], dtype=torch.int64, device=lens.device)
+            counts = [torch.zeros_like(cnt) for _ in range(W)]
+            dist.all_gather(counts, cnt, group=group)
+            n_global = int(sum(int(c) for c in counts))
+    b_max = (n_global + W - 1) // W
+    if n_local != len(shard_indices(n_global, rank, W)):
+        raise ValueError("rank %d holds %d utterances, the i %% W sharding of %d gives %d"
+                         % (rank, n_local, n_global, len(shard_indices(n_global, rank, W))))
+    dev = rows.device
     H = rows.shape[1]
-    pad = torch.empty(m, H, dtype=rows.dtype, device=rows.device)
-    pad[:rows.shape[0]] = rows
-    flat = torch.empty(W * m, H, dtype=rows.dtype, device=rows.device)
+    pad_lens = torch.zeros(max(b_max, 1), dtype=torch.int64, device=dev)
+    pad_lens[:n_local] = lens.to(torch.int64)
+    all_lens = torch.empty(W, max(b_max, 1), dtype=torch.int64, device=dev)
+    if W > 1:
+        dist.all_gather_into_tensor(all_lens.view(-1), pad_lens, group=group)
+    else:
+        all_lens[0] = pad_lens
+    # the single device→host hand-off of the exchange
+    if dev.type == "cuda":
+        host = _pinned_i64(all_lens.numel(), slot=0)
+        host.copy_(all_lens.view(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        lens2 = host.numpy().reshape(W, max(b_max, 1)).copy()
+    else:
+        lens2 = all_lens.numpy().copy()
+    gi = np.arange(n_global)
+    g = PackedGather()
+    g.W, g.b_max, g.n_global = W, max(b_max, 1), n_global
+    g.lens_host = lens2[gi % W, gi // W] if n_global else np.zeros(0, dtype=np.int64)
+    totals = lens2.sum(axis=1)
+    if int(totals[rank]) != rows.shape[0]:
+        raise ValueError("rank %d: %d packed rows but the lengths sum to %d" % (rank, rows.shape[0], int(totals[rank])))
+    m = int(max(int(totals.max()), 1))
+    g.slab_rows, g.all_lens = m, all_lens
+    if W == 1:
+        g.flat = rows
+        return g
+    # payload, padded to the largest rank: a view when the caller's buffer is large enough, else one copy
+    base = rows._base if rows._base is not None else rows
+    if (rows.is_contiguous() and base.dim() == 2 and base.shape[1] == H and base.is_contiguous()
+            and base.data_ptr() == rows.data_ptr() and base.shape[0] >= m):
+        pad = base[:m]
+    else:
+        pad = torch.empty(m, H, dtype=rows.dtype, device=dev)
+        pad[:rows.shape[0]] = rows
+    flat = torch.empty(W * m, H, dtype=rows.dtype, device=dev)
     if timing is not None and rows.is_cuda:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -151,44 +253,93 @@ def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing
     if timing is not None and rows.is_cuda:
         e1.record()
         timing.append((e0, e1, W * m * H * rows.element_size()))
+    g.flat = flat
+    return g
+
+
+def all_gather_packed(rows: torch.Tensor, lens: torch.Tensor, group=None, timing=None, return_host: bool = False,
+                      n_global: Optional[int] = None):
+    """``gather_packed`` + ``select(None)``: ``(rows_global [sum over all utterances, H], lens_global [n_utts])`` in
+    GLOBAL utterance order (utterance i lives on rank i % W)."""
+    g = gather_packed(rows, lens, n_global=n_global, group=group, timing=timing)
+    if g.W == 1:
+        return (rows, lens, g.lens_host.tolist()) if return_host else (rows, lens)
+    rows_g, lens_g = g.select(None)
+    lens_g = lens_g.to(dtype=lens.dtype, device=lens.device)
+    return (rows_g, lens_g, g.lens_host.tolist()) if return_host else (rows_g, lens_g)
+
+
+def packed_inference_step(bridge, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor,
+                          input_ids_global: torch.Tensor, attention_mask_global: torch.Tensor,
+                          prompt_lens: Sequence[int], group=None, timing=None):
+    """One inference step of BASELINE.json configs[3] on this rank: compress + project the rank's utterance shard
+    (``TasuBridge.compress_project_async``), all-gather compressed lengths and packed rows (``gather_packed``), re-deal
+    the global batch into length-homogeneous per-rank batches (``length_grouped_partition``), pick this rank's
+    utterances straight out of the all-gather buffer (``PackedGather.select``) and splice them (``TasuBridge.splice``).
+
+    ``input_ids_global`` / ``attention_mask_global`` ``[n_global, S]`` (left-padded prompts, identical on every rank,
+    on the device), ``prompt_lens`` their token counts on the host.  Returns ``(splice outputs, info)`` with
+    ``info = {sel, lens_host, valid_tokens, padded_tokens, rows_global}``.
+    Host synchronisations: the plan header (overlapped with the tail kernels), the gathered lengths, the splice header."""
     import numpy as np
-    n = sum(l.numel() for l in lens_host)
-    # global utterance i lives on rank i % W at local index i // W: its rows are flat[r*m + off_r[j] : ... + len]
-    lens_np = [l.numpy().astype(np.int64) for l in lens_host]
-    offs_np = [np.concatenate([[0], np.cumsum(l)]) for l in lens_np]
-    gi = np.arange(n)
-    r_of, j_of = gi % W, gi // W
-    glens_np = np.zeros(n, dtype=np.int64)
-    starts = np.zeros(n, dtype=np.int64)
-    for r in range(W):
-        sel = r_of == r
-        glens_np[sel] = lens_np[r][j_of[sel]]
-        starts[sel] = r * m + offs_np[r][j_of[sel]]
-    idx = torch.from_numpy(concat_ranges(starts, glens_np))
-    glens = glens_np.tolist()
-    if rows.is_cuda:
-        idx = idx.pin_memory().to(rows.device, non_blocking=True)
-    rows_g = _gather_rows(flat, idx)
-    lens_g = torch.tensor(glens, dtype=lens.dtype).to(lens.device)
-    return (rows_g, lens_g, glens) if return_host else (rows_g, lens_g)
+    rank, W = world()
+    n_global = input_ids_global.shape[0]
+    dev = raw_encoder_out.device
+    pend = bridge.compress_project_async(raw_encoder_out, raw_encoder_out_lens)
+    rows, lens, _ = pend.finish()
+    g = gather_packed(rows, lens, n_global=n_global, group=group, timing=timing)
+    plen = np.asarray(prompt_lens, dtype=np.int64)
+    tot = plen + g.lens_host - 1                                   # spliced length of every utterance (one <speech> each)
+    share = length_grouped_partition(tot.tolist(), W)
+    sel = sorted(share[rank])
+    info = {"sel": sel, "lens_host": g.lens_host, "rows_global": int(g.lens_host.sum()),
+            "valid_tokens": int(tot[sel].sum()) if sel else 0, "padded_tokens": 0}
+    if not sel:
+        return None, info
+    rows_sel, lens_sel = g.select(sel)
+    sel_t = torch.as_tensor(sel, dtype=torch.int64).to(dev, non_blocking=True)
+    cut = int(input_ids_global.shape[1] - int(plen[sel].max()))    # drop the columns that are padding for this group
+    ids_s = input_ids_global.index_select(0, sel_t)[:, cut:].contiguous()
+    mask_s = attention_mask_global.index_select(0, sel_t)[:, cut:].contiguous()
+    out = bridge.splice(rows_sel, lens_sel, ids_s, mask_s)
+    info["padded_tokens"] = int(out[0].shape[0] * out[0].shape[1])
+    return out, info
 
 
 # ---- gradient all-reduce overlapped with the backward (token-row projector) -------------------------------------------
-_OVERLAP = {"on": False, "group": None, "pending": {}}
+_OVERLAP = {"on": False, "group": None, "pending": {}, "params": None}
 
 
-def enable_overlapped_allreduce(on: bool = True, group=None):
+def enable_overlapped_allreduce(on: bool = True, group=None, params: Optional[Sequence[torch.nn.Parameter]] = None):
     """Data-parallel training without DeepSpeed: when on, the token-row backward starts the all-reduce of its W1 half
     (dgamma | dbeta | dW1 | db1 = 94 % of the bytes) as soon as it is enqueued, so NCCL runs under the W2 half of the
-    backward; ``allreduce_gradients`` then only sends the remainder and waits.  Off (default): nothing is communicated
-    inside backward (what DeepSpeed / an external reducer expects)."""
+    backward; ``allreduce_gradients`` then only sends the remainder and waits.  ``params`` (required when on): the
+    parameters whose gradients that backward produces — the early all-reduce is only started when none of them already
+    holds a gradient (with gradient accumulation autograd adds the new gradient INTO the old storage, and a half that
+    was already summed over the ranks must not be reduced again).  Off (default): nothing is communicated inside
+    backward (what DeepSpeed / an external reducer expects)."""
+    if on and params is None:
+        raise ValueError("enable_overlapped_allreduce(True) needs the parameters of the overlapped backward")
+    _drain_pending()
     _OVERLAP["on"], _OVERLAP["group"] = bool(on), group
+    _OVERLAP["params"] = list(params) if params is not None else None
+
+
+def _drain_pending():
+    """Wait for and forget every early all-reduce that no ``allreduce_gradients`` call picked up."""
+    for work, _ in _OVERLAP["pending"].values():
+        work.wait()
+    _OVERLAP["pending"].clear()
 
 
 def overlap_hook():
-    """Callback for ``ops.tokrow_linear_silu_bwd(between=...)`` or None when overlap is off / single process."""
+    """Callback for ``ops.tokrow_linear_silu_bwd(between=...)`` or None when overlap is off / single process / the
+    parameters already hold gradients (accumulation: the whole gradient is reduced once, after the backward)."""
     rank, W = world()
     if not _OVERLAP["on"] or W == 1:
+        return None
+    _drain_pending()                                             # a backward whose reduction was never finished
+    if any(p.grad is not None for p in _OVERLAP["params"]):
         return None
 
     def between(flat, n_first):
@@ -212,10 +363,14 @@ def _shared_flat(grads):
 
 
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20, average: bool = True,
-                        group=None, async_op: bool = False):
-    """Bucketed gradient all-reduce of the projector parameters (54 512 062 params = 218 MB fp32 for
-    linear-silu).  Buckets are sized for launch latency/overlap, not link count: NVSwitch gives every
-    GPU full bandwidth to every peer.  Returns the list of (work, flat, grads) handles when async."""
+                        group=None, async_op: bool = False, wire_dtype: Optional[torch.dtype] = None):
+    """Gradient all-reduce of the projector parameters (54 512 062 params = 218 MB fp32 for linear-silu; replaces the
+    ZeRO-2 reduce-scatter of conf/ds_config.json:15-21).  The token-row backward writes every gradient into ONE flat
+    buffer, which is reduced in place as a single message; other gradients go in buckets sized for launch latency
+    (NVSwitch gives every GPU full bandwidth to every peer, so not for link count).
+    ``wire_dtype=torch.bfloat16`` (flat-buffer case, CUDA): the message is sent as bf16 — half the bytes; the sum over
+    ranks is formed by NCCL in bf16, the result is widened and averaged back into the fp32 buffer.  Default (None): fp32
+    on the wire, as the reference.  Returns the list of (work, flat, grads) handles when async."""
     rank, W = world()
     if W == 1:
         return []
@@ -223,6 +378,13 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
     flat = _shared_flat(grads)
     if flat is not None:                                         # one in-place message, no flatten / copy-back
         early = _OVERLAP["pending"].pop(flat.untyped_storage().data_ptr(), None)
+        if early is None and wire_dtype == torch.bfloat16 and flat.is_cuda and not async_op:
+            from . import ops
+            wire = torch.empty(flat.numel(), dtype=torch.bfloat16, device=flat.device)
+            ops.flat_scale_cast(flat, wire, 1.0)
+            dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=group)
+            ops.flat_scale_cast(wire, flat, 1.0 / W if average else 1.0)
+            return []
         if early is not None:                                    # the W1 half is already in flight (overlap_hook)
             work0, n_first = early
             work = dist.all_reduce(flat[n_first:], op=dist.ReduceOp.SUM, group=group, async_op=True)
@@ -234,6 +396,7 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
             return handles
         finish_allreduce(handles, W if average else 1)
         return []
+    _drain_pending()                                             # gradients were accumulated: nothing early applies
     handles, bucket, size = [], [], 0
 
     def flush():

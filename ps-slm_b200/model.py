@@ -135,6 +135,13 @@ class slam_model_asr(nn.Module):
         # text-only batches go through the token-row projector (no [B, L, 25055] tensor); False = dense simulator path
         self.token_row_path = True
 
+    def train(self, mode: bool = True):
+        """Every switch between training and evaluation drops the cached bf16 / folded weight copies
+        (deepspeed_utils.py:249-256 evaluates inside the training loop; ZeRO updates parameters through flat buffers
+        that move neither a tensor's address nor its version counter)."""
+        _bridge.invalidate_caches()
+        return super().train(mode)
+
     # ------------------------------------------------------------------ bridge methods
     def psd(self, encoder_out, encoder_out_lens, ctc_posterior, blank_id: int = 0, blank_threshold: float = 0.90):
         return _bridge.psd(encoder_out, encoder_out_lens, ctc_posterior, blank_id, blank_threshold)
@@ -223,7 +230,8 @@ class slam_model_asr(nn.Module):
         if self.ctc_posterior and self.voca_trans:                 # ps-slm.py:485-513 / :615-643
             tb = self._table_cache.get([table], lambda: (
                 table.detach().contiguous() if table.dtype == torch.bfloat16
-                else _ops.cast_rows(table.detach().contiguous(), torch.bfloat16)[0]))
+                else _ops.cast_rows(table.detach().contiguous(), torch.bfloat16)[0]),
+                fresh=torch.is_grad_enabled() and table.requires_grad, verify=True)
             projector_outs, feat_len = _bridge.voca_trans_project(self.encoder_projector, encoder_out, encoder_out_lens, tb,
                                                                   self.do_psd, self.top1_emb)
             inputs_embeds = self.llm.get_input_embeddings()(input_ids)
@@ -248,7 +256,7 @@ class slam_model_asr(nn.Module):
                 w_bf16, b_f32 = self._ctc_cache.get([ctc_lo.weight, ctc_lo.bias], lambda: (
                     _bridge.cast_weight_bf16(ctc_lo.weight),
                     ctc_lo.bias.detach().float().contiguous() if ctc_lo.bias is not None
-                    else torch.zeros(ctc_lo.weight.shape[0], dtype=torch.float32, device=ctc_lo.weight.device)))
+                    else torch.zeros(ctc_lo.weight.shape[0], dtype=torch.float32, device=ctc_lo.weight.device)), verify=True)
                 encoder_outs, feat_len = _bridge.psd_from_encoder(raw_encoder_out, raw_encoder_out_lens, w_bf16, b_f32, blank)
             else:
                 encoder_outs, feat_len = encoder_out, encoder_out_lens

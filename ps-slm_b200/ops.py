@@ -121,6 +121,25 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
     return st
 
 
+def fingerprint(tensors, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tasu_fingerprint of up to 8 device tensors → int64[1] (``out`` may be a pinned host slot; no sync here)."""
+    import ctypes
+    ts = [t.detach() for t in tensors if t is not None]
+    _need_cuda(*ts)
+    if len(ts) > 8:
+        raise ValueError("fingerprint takes at most 8 tensors per call")
+    ts = [t if t.is_contiguous() else t.contiguous() for t in ts]
+    n = len(ts)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in ts])
+    sizes = (ctypes.c_int64 * max(n, 1))(*[t.numel() * t.element_size() for t in ts])
+    if out is None:
+        out = torch.empty(1, dtype=torch.int64, device=ts[0].device)
+    L.check(L.lib().tasu_fingerprint(ctypes.addressof(ptrs), ctypes.addressof(sizes), n, out.data_ptr(), _stream()),
+            "tasu_fingerprint")
+    _count(1)
+    return out
+
+
 def row_norm_max(w: torch.Tensor) -> torch.Tensor:
     """max_r ||w_r||_2 as a device uint32[1] in the order-preserving encoding (tasu_row_norm_max)."""
     _need_cuda(w)
@@ -202,7 +221,8 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
 
 def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tail_src: torch.Tensor,
               multi: Optional[torch.Tensor], ln_mean: torch.Tensor, ln_rstd: torch.Tensor, ln_eps: float = 1e-5):
-    L.check(L.lib().tasu_pool_tail(probs.data_ptr(), probs.stride(0), D, n_out, pk_len.data_ptr(), tail_src.data_ptr(),
+    """``probs``: the compact [rows, ld] matrix; its row count is the capacity no access may exceed."""
+    L.check(L.lib().tasu_pool_tail(probs.data_ptr(), probs.stride(0), D, n_out, probs.shape[0], pk_len.data_ptr(), tail_src.data_ptr(),
                                    multi[1:].data_ptr() if multi is not None else None, _ptr(multi),
                                    ln_mean.data_ptr(), ln_rstd.data_ptr(), float(ln_eps), _stream()), "tasu_pool_tail")
     _count(1)
@@ -601,6 +621,17 @@ def silu_bwd(dh: torch.Tensor, z: torch.Tensor, rstd: Optional[torch.Tensor], me
                                   db1.data_ptr(), g0.data_ptr(), _stream()), "tasu_silu_bwd")
     _count(1)
     return dzsT, db1, g0
+
+
+def flat_scale_cast(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """dst = cast(scale * src) over flat contiguous buffers of equal length (tasu_flat_scale_cast)."""
+    _need_cuda(src, dst)
+    if src.numel() != dst.numel() or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("flat_scale_cast needs contiguous buffers of equal length")
+    L.check(L.lib().tasu_flat_scale_cast(src.data_ptr(), _dt(src), dst.data_ptr(), _dt(dst), src.numel(), float(scale), _stream()),
+            "tasu_flat_scale_cast")
+    _count(1)
+    return dst
 
 
 def colsum(src: torch.Tensor):

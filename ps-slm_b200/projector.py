@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .bridge import ProjectorCache, cast_weight_bf16, linear_silu_forward
+from .bridge import ProjectorCache, cast_weight_bf16, invalidate_caches, linear_silu_forward
 
 
 def _rows_bf16(x2: torch.Tensor, want_ln: bool, eps: float = 1e-5):
@@ -41,7 +41,16 @@ def _downsample(x: torch.Tensor, k: int) -> torch.Tensor:
     return x.contiguous().view(B, T // k, D * k)
 
 
-class EncoderProjectorLinearSiLU(nn.Module):
+class _CachedWeightsModule(nn.Module):
+    """Switching between training and evaluation drops every cached weight copy: the copies made during one evaluation
+    phase must not survive the optimizer steps that follow (ProjectorCache)."""
+
+    def train(self, mode: bool = True):
+        invalidate_caches()
+        return super().train(mode)
+
+
+class EncoderProjectorLinearSiLU(_CachedWeightsModule):
     """LayerNorm(in) → Linear(in, 2048) → SiLU → Linear(2048, out) — projector.py:129-151."""
 
     def __init__(self, config, bottleneck=2048):
@@ -78,7 +87,7 @@ class EncoderProjectorLinearSiLU(nn.Module):
                          + self.ffn[0].bias.detach().double()).float()       # tiny host-side GEMV, once per weight version
                 w2s, k2, _, _, _ = ops.split_bf16x3(self.ffn[2].weight.detach().float(), 1)
                 return w1s, k1, colsum, dbias, w2s, k2, self.ffn[2].bias.detach().float().contiguous()
-        w1s, k1, colsum, dbias, w2s, k2, b2 = self._cache3.get(params, build)
+        w1s, k1, colsum, dbias, w2s, k2, b2 = self._cache3.get(params, build, verify=True)
         xs, kx, mean, rstd, _ = ops.split_bf16x3(x.reshape(B * T, D).float(), 0, want_ln=True, ln_eps=self.norm.eps)
         h = torch.empty(B * T, Hb, dtype=torch.float32, device=x.device)
         ops.gemm_fp32x3(xs, w1s, B * T, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
@@ -87,8 +96,10 @@ class EncoderProjectorLinearSiLU(nn.Module):
         ops.gemm_fp32x3(hs, w2s, B * T, H, kh, y, L.EPI_BIAS, b2)
         return y.view(B, T, H).to(x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
 
-    def folded_weights(self):
-        """(W1·γ bf16 [2048, pad64(in)], colsum, W1β+b1, W2 bf16, b2 fp32), cached per parameter version."""
+    def folded_weights(self, verify: bool = False):
+        """(W1·γ bf16 [2048, pad64(in)], colsum, W1β+b1, W2 bf16, b2 fp32), cached (see ProjectorCache).
+        ``verify``: check the copy against the live parameters' fingerprint (TasuBridge does that itself, piggybacked
+        on its header read)."""
         params = [self.norm.weight, self.norm.bias, self.ffn[0].weight, self.ffn[0].bias,
                   self.ffn[2].weight, self.ffn[2].bias]
 
@@ -99,7 +110,7 @@ class EncoderProjectorLinearSiLU(nn.Module):
                 w2 = cast_weight_bf16(self.ffn[2].weight)
                 b2 = self.ffn[2].bias.detach().float().contiguous()
             return w1g, colsum, dbias, w2, b2
-        return self._cache.get(params, build)
+        return self._cache.get(params, build, verify=verify)
 
     def forward_token_rows(self, rows, out_dtype=torch.float32):
         """Projector output ``[n_rows, out_dim]`` (packed) for text-simulated rows given as descriptors
@@ -117,7 +128,7 @@ class EncoderProjectorLinearSiLU(nn.Module):
             with torch.no_grad():
                 S, D = ops.linear_rowdots(l1.weight.detach(), norm.weight.detach(), norm.bias.detach(), l1.bias.detach())
                 return S, D, cast_weight_bf16(l2.weight), l2.bias.detach().float().contiguous()
-        S, D, w2, b2 = self._cache_rows.get(params, build)
+        S, D, w2, b2 = self._cache_rows.get(params, build, verify=True)
         with torch.no_grad():
             _, h, _, _ = ops.tokrow_fwd(l1.weight.detach(), norm.weight.detach(), S, D, rows, norm.eps, want_z=False)
             n = rows.n_rows
@@ -132,14 +143,14 @@ class EncoderProjectorLinearSiLU(nn.Module):
         if self.precision == "fp32x3":
             return self._forward_fp32x3(x)
         B, T, D = x.shape
-        w1g, colsum, dbias, w2, b2 = self.folded_weights()
+        w1g, colsum, dbias, w2, b2 = self.folded_weights(verify=True)
         xb, mean, rstd = _rows_bf16(x.reshape(B * T, D), True, self.norm.eps)
         y = linear_silu_forward(xb, B * T, D, mean, rstd, w1g, colsum, dbias, w2, b2, x.dtype
                                 if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
         return y.view(B, T, -1)
 
 
-class EncoderProjectorConcat(nn.Module):
+class EncoderProjectorConcat(_CachedWeightsModule):
     """k-frame concat → Linear(D·k, 2048) → ReLU → Linear(2048, llm_dim) — projector.py:29-50."""
 
     def __init__(self, config):
@@ -164,7 +175,7 @@ class EncoderProjectorConcat(nn.Module):
         params = [self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias]
         w1, b1, w2, b2 = self._cache.get(params, lambda: (
             cast_weight_bf16(self.linear1.weight), self.linear1.bias.detach().float().contiguous(),
-            cast_weight_bf16(self.linear2.weight), self.linear2.bias.detach().float().contiguous()))
+            cast_weight_bf16(self.linear2.weight), self.linear2.bias.detach().float().contiguous()), verify=True)
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
         xb, _, _ = _rows_bf16(x.reshape(B * T, D), False)
         h = torch.empty(B * T, 2048, dtype=torch.bfloat16, device=x.device)
@@ -174,7 +185,7 @@ class EncoderProjectorConcat(nn.Module):
         return y.view(B, T, self.llm_dim)
 
 
-class EncoderProjectorLinear(nn.Module):
+class EncoderProjectorLinear(_CachedWeightsModule):
     """k-frame concat → Linear(D·k, llm_dim) — projector.py:10-26 (CTC head over the LLM vocab)."""
 
     def __init__(self, config):
@@ -194,7 +205,7 @@ class EncoderProjectorLinear(nn.Module):
             y = LinearFunction.apply(x.reshape(B * T, D), self.map.weight, self.map.bias, False, out_dtype)
             return y.reshape(B, T, self.llm_vocab)
         w, b = self._cache.get([self.map.weight, self.map.bias], lambda: (
-            cast_weight_bf16(self.map.weight), self.map.bias.detach().float().contiguous()))
+            cast_weight_bf16(self.map.weight), self.map.bias.detach().float().contiguous()), verify=True)
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
         xb, _, _ = _rows_bf16(x.reshape(B * T, D), False)
         ld = ops.pad_to(self.llm_vocab, 8)
@@ -272,7 +283,7 @@ class _CrossAttnFunction(torch.autograd.Function):
         return (dwq[:, :V1] * (d ** -0.5), None, None, None, None, None, None, None, None, None)
 
 
-class EncoderProjectorCTCCA(nn.Module):
+class EncoderProjectorCTCCA(_CachedWeightsModule):
     """Cross-attention projector — projector.py:104-126 ("cross-attention", called as
     ``encoder_projector(posterior, llm_embedding)``, ps-slm.py:475-480): ``Q = W_q·post``; 8-head softmax attention of Q
     over the LLM embedding table (keys = values = the table), heads concatenated.
@@ -308,7 +319,8 @@ class EncoderProjectorCTCCA(nn.Module):
         def build_w():
             with torch.no_grad():                                  # scores / sqrt(d): folded into the cached weight
                 return cast_weight_bf16(self.W_q.weight.detach().float() * (d ** -0.5))
-        wq = self._cache.get([self.W_q.weight], build_w)
+        train = torch.is_grad_enabled() and self.W_q.weight.requires_grad
+        wq = self._cache.get([self.W_q.weight], build_w, fresh=train, verify=True)    # a training forward never caches
 
         def build_t():
             with torch.no_grad():
@@ -321,9 +333,8 @@ class EncoderProjectorCTCCA(nn.Module):
                     tp[:, :, :d] = t.reshape(V2, h, d)
                     t = tp.view(V2, h * dp)
                 return t
-        table = self._tcache.get([llm_embed], build_t)
+        table = self._tcache.get([llm_embed], build_t, fresh=torch.is_grad_enabled() and llm_embed.requires_grad, verify=True)
         xb, _, _ = _rows_bf16(post.detach().reshape(N, V1), False)
-        train = torch.is_grad_enabled() and self.W_q.weight.requires_grad
         if train:
             Z = _CrossAttnFunction.apply(self.W_q.weight, xb, wq, table, N, V1, V2, h, d, dp)
         else:

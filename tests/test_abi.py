@@ -105,19 +105,16 @@ def test_projector_state_dict_names():
     assert set(s.state_dict()) == {"map.weight", "map.bias"} and tuple(s.map.weight.shape) == (151644, 512)
 
 
-def test_options_default_off_and_validated(lib):
-    """Run-time options: every experimental switch defaults to 0 (the validated path) and unknown ids are rejected."""
+def test_options_defaults_and_validation(lib):
+    """Run-time options: the CTA-pair GEMM is on by default (0 selects the one-CTA kernel); unknown ids are rejected."""
     import ps_slm_b200._lib as L
     import ps_slm_b200.ops as ops
     assert "TASU_GEMM_PAIR" not in os.environ
-    assert ops.get_option(L.OPT_GEMM_PAIR) == 0
-    ops.set_option(L.OPT_GEMM_PAIR, 1)
     assert ops.get_option(L.OPT_GEMM_PAIR) == 1
     ops.set_option(L.OPT_GEMM_PAIR, 0)
     assert ops.get_option(L.OPT_GEMM_PAIR) == 0
-    assert "TASU_EPI_PREFETCH" not in os.environ and ops.get_option(L.OPT_EPI_PREFETCH) == 0
-    assert "TASU_STATS_WIDE" not in os.environ and ops.get_option(L.OPT_STATS_WIDE) == 0
-    assert "TASU_GEMM_WIDE_EPI" not in os.environ and ops.get_option(L.OPT_GEMM_WIDE_EPI) == 0
+    ops.set_option(L.OPT_GEMM_PAIR, 1)
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 1
     assert lib.tasu_set_option(L.OPT_COUNT, 1) == -1 and b"unknown option" in lib.tasu_last_error()
     assert lib.tasu_get_option(-3) == -1
     with pytest.raises(L.TasuError):

@@ -38,6 +38,26 @@ def _worker(rank, world, port, n_utts, out_q):
     D.allreduce_gradients(params, bucket_bytes=4096)
     exp = [(1 + 2) / 2 * (i + 1) for i in range(4)]
     ok = ok and all(torch.allclose(p.grad, torch.full_like(p, e)) for p, e in zip(params, exp))
+    # selection straight out of the all-gather buffer (what a rank splices after the length-grouped re-deal)
+    g = D.gather_packed(rows, lens, n_global=n_utts)
+    sel = [5, 0, 3]
+    rows_s, lens_s = g.select(sel)
+    ok = ok and torch.equal(lens_s, lens_all[sel]) and torch.equal(rows_s, torch.cat([rows_all[i] for i in sel], 0))
+    ok = ok and g.lens_host.tolist() == lens_all.tolist()
+    # overlapped all-reduce: first part of one flat gradient buffer reduced early, the rest afterwards
+    flat = torch.arange(10.) * (rank + 1)
+    ps = [torch.nn.Parameter(torch.zeros(6)), torch.nn.Parameter(torch.zeros(4))]
+    D.enable_overlapped_allreduce(True, params=ps)
+    hook = D.overlap_hook()
+    ok = ok and hook is not None
+    hook(flat, 6)
+    ps[0].grad, ps[1].grad = flat[:6], flat[6:]
+    D.allreduce_gradients(ps)
+    ok = ok and torch.allclose(flat, torch.arange(10.) * 1.5)
+    # gradient accumulation: the parameters already hold gradients → nothing may be reduced early (a half that is
+    # already summed over the ranks would be reduced twice)
+    ok = ok and D.overlap_hook() is None
+    D.enable_overlapped_allreduce(False)
     out_q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -150,6 +150,28 @@ def test_fullsize_vs_oracle(dev):
         assert ss[bb, :n].tolist() == kt[sel].tolist() and sl[bb, :n].tolist() == kl[sel].tolist()
 
 
+def test_capacity_overflow_is_redone_exactly(dev):
+    """The speculative tail is sized from the high-water mark of earlier batches.  A batch that keeps MORE frames than that
+    (a quiet batch followed by a dense one) must neither touch memory beyond the buffers (tasu_pool_tail is bounded by the
+    compact matrix's row capacity) nor return a truncated result: the host sees the overflow in the header and redoes the
+    tail with exact sizes."""
+    import ps_slm_b200.synth as S
+    B, T = 16, 500
+    w, b, proj, table, br = _bridge(dev)
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=5)
+    ids, mask, _ = S.make_prompts(B, seed=5, left_pad=True)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    e0, m0, _, p0, nl0 = br(*args)                              # first call: worst-case capacity
+    kept = br.last_counts["kept_frames"]
+    assert kept > 2048 and br.last_counts["n_out"] > 2048, "the batch must exceed the smallest capacity quantum"
+    br._capacity[(B, T)] = (1, 1)                               # pretend every earlier batch was almost empty
+    e1, m1, _, p1, nl1 = br(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(nl0, nl1) and torch.equal(m0, m1) and torch.equal(p0, p1)
+    assert torch.equal(e0, e1), "the redone tail must equal the exact-capacity result bit for bit"
+    assert br._capacity[(B, T)] == (kept, br.last_counts["n_out"])
+
+
 def _small_bridge(dev, V=61, D=32, H=48, table_rows=300):
     import ps_slm_b200.projector as P
     from ps_slm_b200.bridge import TasuBridge

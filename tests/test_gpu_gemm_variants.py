@@ -1,0 +1,286 @@
+"""GPU tests of the GEMM variants next to the one-CTA-per-tile kernel:
+
+  * CTA-pair GEMM (tcgen05.mma.cta_group::2, one 256 x 256 tile per cluster of two CTAs) — the default for deep-K
+    problems (K > 1024, M > 128; ``tasu_set_option(TASU_OPT_GEMM_PAIR, 0)`` selects the one-CTA kernel): must equal the
+    one-CTA kernel bit for bit.
+  * stream-K GEMM (``tasu_gemm_bf16_tn_streamk``): the ragged last wave of tiles cut along K, fix-up through a workspace.
+  * bf16 hand-over of the encoder output.
+
+Round-2 A/B (profiles/r02a_ab.md) removed the variants that lost: pair mode for K <= 1024 and for the fused CTC head,
+16-epilogue-warp kernels, prefetched epilogue vectors of the shallow-K GEMM.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture()
+def pair_mode():
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    ops.set_option(L.OPT_GEMM_PAIR, 1)          # the default; tests switch to the one-CTA kernel for the comparison
+    yield
+    ops.set_option(L.OPT_GEMM_PAIR, 1)
+
+
+_PROBLEM = {}
+
+
+def _problem(M, N, K):
+    """bf16 operands (padded pitches, garbage beyond K) and their fp64 product; the last shape is kept so that the
+    epilogue variants of one shape (the fastest-varying test parameter) share the expensive reference product."""
+    import ps_slm_b200.ops as ops
+    key = (M, N, K)
+    if key not in _PROBLEM:
+        _PROBLEM.clear()
+        torch.manual_seed(M + 3 * N + 7 * K)
+        lda, ldb = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8)
+        A = torch.zeros(M, lda).bfloat16(); A[:, :K] = (torch.randn(M, K) * 0.5).bfloat16(); A[:, K:] = 7.0
+        B = torch.zeros(N, ldb).bfloat16(); B[:, :K] = (torch.randn(N, K) * 0.5).bfloat16(); B[:, K:] = 7.0
+        _PROBLEM[key] = (A, B, A[:, :K].float().double() @ B[:, :K].float().double().T)
+    return _PROBLEM[key]
+
+
+def _ref(acc, epi, bias, rstd, mean, colsum):
+    if epi in (4, 5):
+        z = rstd.double()[:, None] * (acc - mean.double()[:, None] * colsum.double()[None, :]) + bias.double()[None, :]
+        return torch.nn.functional.silu(z) if epi == 4 else z
+    if epi == 6:
+        return torch.exp(acc + bias.double()[None, :] - mean.double()[:, None]) * rstd.double()[:, None]
+    if epi >= 1:
+        acc = acc + bias.double()[None, :]
+    if epi == 2:
+        acc = torch.nn.functional.silu(acc)
+    if epi == 3:
+        acc = torch.relu(acc)
+    return acc
+
+
+def _check_pad(pad, N, epi, elem_size):
+    """TMA stores are clipped at N rounded up to the next 16-byte boundary of the row: pad columns inside that boundary
+    receive the epilogue of a zero accumulator (zero for the linear epilogues; exp(-row_max)/sum > 0, tiny, for the
+    softmax epilogue, whose bias vector is not masked there), columns beyond it are never written."""
+    per16 = 16 // elem_size
+    inside = (N + per16 - 1) // per16 * per16 - N
+    assert bool((pad[:, inside:] == -768.0).all()), "columns beyond the 16-byte boundary must be untouched"
+    head = pad[:, :inside]
+    if epi == 6:
+        assert bool(((head == -768.0) | ((head >= 0) & (head < 1e-3))).all())
+    else:
+        assert bool(((head == -768.0) | (head == 0.0)).all()), "pad columns must be untouched or zero"
+
+
+# M > 128 and K > 1024 select the pair kernel (6 stages, one epilogue group): ragged M / N / K, M below / above one pair
+# tile, a tile whose upper CTA is entirely out of range (M = 300: rows 256..299 live in the lower CTA of the second pair
+# tile), the projector GEMM-1 shape
+PAIR_SHAPES = [(256, 256, 1088), (129, 8, 1032), (300, 260, 1100), (257, 1536, 2048), (1000, 2048, 25055), (8341, 2048, 4096)]
+
+
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (3, torch.bfloat16),
+                                           (4, torch.bfloat16), (5, torch.float32), (6, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_pair_gemm_matches_default_kernel(dev, pair_mode, M, N, K, epi, out_dtype):
+    """The CTA-pair kernel accumulates every output element in the same order as the default kernel (one TMEM
+    accumulator, K blocks in ascending order), so the two must agree BIT FOR BIT; both are checked against fp64."""
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    if (K > 20000 or N > 20000) and epi not in (1, 4, 6):
+        pytest.skip("large shapes: a subset of epilogues is enough")
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8)
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))     # softmax: a plausible row max
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    C = torch.full((M, ldc), -768.0, dtype=out_dtype, device=dev)
+    assert ops.get_option(L.OPT_GEMM_PAIR) == 1
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C, epi, *vec)
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+    C0 = torch.full((M, ldc), -768.0, dtype=out_dtype, device=dev)
+    ops.gemm_bf16_tn(Ad, Bd, M, N, K, C0, epi, *vec)
+    torch.cuda.synchronize()
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
+    got = C.cpu()
+    pad = got[:, N:].float()
+    _check_pad(pad, N, epi, got.element_size())
+    scale = ref.abs().max().item() + 1e-6
+    tol = 1e-4 if out_dtype == torch.float32 else 6e-3
+    err = (got[:, :N].double() - ref).abs().max().item() / scale
+    assert err < tol, f"pair GEMM max error {err} (scaled) for {(M, N, K, epi)}"
+    assert torch.equal(C[:, :N], C0[:, :N]), "pair kernel and default kernel must agree bit for bit"
+
+
+def test_pair_gemm_device_side_row_count(dev, pair_mode):
+    """m_dev: live rows below the capacity M, including a live count that leaves whole pair tiles (and the upper CTA
+    of the last live one) without work."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(3)
+    M, N, K = 1024, 512, 2048
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    ref = A.float() @ B.float().T
+    for live in (0, 1, 128, 129, 300, 1024):
+        C = torch.full((M, N), -5.0, dtype=torch.float32, device=dev)
+        m_dev = torch.tensor([live], dtype=torch.int32, device=dev)
+        ops.gemm_bf16_tn(A, B, M, N, K, C, m_dev=m_dev)
+        torch.cuda.synchronize()
+        if live:
+            assert (C[:live] - ref[:live]).abs().max().item() / ref.abs().max().item() < 1e-4
+        tiles = (live + 255) // 256
+        assert bool((C[min(M, tiles * 256):] == -5.0).all()), "rows of pair tiles without live rows must stay untouched"
+
+
+def test_pair_gemm_back_to_back(dev, pair_mode):
+    """Pipeline state (mbarrier phases, TMEM accumulator ring) survives many tiles per CTA pair and repeated launches."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(5)
+    M, N, K = 8341, 2048, 2048           # 33 x 8 = 264 pair tiles on 74 pairs: 3.6 tiles per pair
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    C1 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    C2 = torch.empty_like(C1)
+    for _ in range(3):
+        ops.gemm_bf16_tn(A, B, M, N, K, C1)
+    ops.gemm_bf16_tn(A, B, M, N, K, C2)
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    ref = A.float() @ B.float().T
+    assert (C1 - ref).abs().max().item() / ref.abs().max().item() < 1e-4
+
+
+def test_bridge_with_pair_gemm_matches_default(dev, pair_mode):
+    """Whole inference bridge with the projector GEMMs in pair mode: integers and embeddings equal the default path."""
+    import types
+
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 8, 500
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=11, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=5, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    out_pair = [t.clone() for t in br(*args)]
+    torch.cuda.synchronize()
+    ops.set_option(L.OPT_GEMM_PAIR, 0)
+    out_def = br(*args)
+    torch.cuda.synchronize()
+    for a, d in zip(out_pair, out_def):
+        assert torch.equal(a, d)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stream-K tail (tasu_gemm_bf16_tn_streamk)
+# ---------------------------------------------------------------------------------------------------------------
+# (M, N, K): 528 tiles = 3 waves + 84 cut tiles (the headline GEMM-1 shape with a shorter K); fewer tiles than CTAs
+# (every tile cut 4 ways); exact multiple of 148 tiles (no cut); one leftover tile; ragged M / N / K; tiny K (1 K-block)
+SK_SHAPES = [(8341, 2048, 4096), (300, 512, 2048), (128 * 37, 1024, 1088), (128 * 37 + 1, 1024, 1088), (1000, 2048, 25055),
+             (130, 260, 72), (257, 1536, 2048), (5, 40, 64)]
+
+
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
+                                           (6, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", SK_SHAPES)
+def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
+    import ps_slm_b200.ops as ops
+    if K > 20000 and epi not in (1, 4):
+        pytest.skip("large K: a subset of epilogues is enough")
+    A, B, acc64 = _problem(M, N, K)
+    ldc = ops.pad_to(N, 8)
+    torch.manual_seed(M + 3 * N + 7 * K + epi)
+    bias, rstd, colsum = torch.randn(N), torch.rand(M) + 0.5, torch.randn(N)
+    mean = torch.randn(M) * 0.1 if epi != 6 else torch.full((M,), 1.3 * (K ** 0.5))
+    Ad, Bd = A.to(dev), B.to(dev)
+    vec = [t.to(dev) for t in (bias, rstd, mean, colsum)]
+    outs = []
+    for _ in range(3):                                   # the workspace flags must be handed back after every launch
+        C = torch.full((M, ldc), -768.0, dtype=out_dtype, device=dev)
+        ops.gemm_bf16_tn_streamk(Ad, Bd, M, N, K, C, epi, *vec)
+        torch.cuda.synchronize()
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), "fixed summation order: deterministic"
+    ref = _ref(acc64, epi, bias, rstd, mean, colsum)
+    got = outs[0].cpu()
+    pad = got[:, N:].float()
+    _check_pad(pad, N, epi, got.element_size())
+    scale = ref.abs().max().item() + 1e-6
+    tol = 1e-4 if out_dtype == torch.float32 else 6e-3
+    err = (got[:, :N].double() - ref).abs().max().item() / scale
+    assert err < tol, f"stream-K GEMM max error {err} (scaled) for {(M, N, K, epi)}"
+    assert int(ops.streamk_workspace(dev)[:4 * 148].view(torch.int32).abs().sum()) == 0, "flags are zero between launches"
+
+
+def test_streamk_gemm_device_side_row_count(dev):
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(3)
+    M, N, K = 4096, 2048, 2048
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    ref = A.float() @ B.float().T
+    for live in (0, 1, 128, 129, 2500, 4096):            # the schedule is computed in the kernel from the live row count
+        C = torch.full((M, N), -5.0, dtype=torch.float32, device=dev)
+        m_dev = torch.tensor([live], dtype=torch.int32, device=dev)
+        ops.gemm_bf16_tn_streamk(A, B, M, N, K, C, m_dev=m_dev)
+        torch.cuda.synchronize()
+        if live:
+            assert (C[:live] - ref[:live]).abs().max().item() / ref.abs().max().item() < 1e-4
+        tiles = (live + 127) // 128
+        assert bool((C[min(M, tiles * 128):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
+
+
+def test_streamk_matches_default_on_uncut_tiles(dev):
+    """The tiles of the full waves take exactly the default path: bit-equal to tasu_gemm_bf16_tn there."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(9)
+    M, N, K = 8341, 2048, 2048                           # 528 tiles: tiles 0..443 are whole, 444..527 are cut
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.3).bfloat16()
+    C0 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    C1 = torch.empty_like(C0)
+    ops.gemm_bf16_tn(A, B, M, N, K, C0)
+    ops.gemm_bf16_tn_streamk(A, B, M, N, K, C1)
+    torch.cuda.synchronize()
+    whole_rows = (444 // 8) * 128                        # n fastest: tile = m_tile * 8 + n_tile
+    assert torch.equal(C0[:whole_rows], C1[:whole_rows])
+    assert (C0 - C1).abs().max().item() / C0.abs().max().item() < 1e-5
+
+
+def test_bridge_bf16_encoder_output_equals_fp32_input(dev):
+    """bench.py --host-bf16: handing the encoder output over as bf16 skips the cast kernel; the kernels see the same
+    bf16 values, so every output is bit-identical to the fp32-input call."""
+    import types
+
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import TasuBridge
+    torch.manual_seed(0)
+    B, T = 6, 300
+    w, b = S.make_ctc_head()
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=21, ragged=True)
+    ids, mask, _ = S.make_prompts(B, seed=7, left_pad=True)
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    tail = (raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    out32 = [t.clone() if t is not None else None for t in br(raw.to(dev), *tail)]
+    out16 = br(raw.bfloat16().to(dev), *tail)
+    torch.cuda.synchronize()
+    for a, c in zip(out32, out16):
+        assert (a is None and c is None) or torch.equal(a, c)

@@ -42,13 +42,25 @@ def _worker(rank, world, port, q):
     ids, mask, _ = S.make_prompts(B, seed=5, tasks=tasks, left_pad=True)
     mine = D.shard_indices(B, rank, world)
     audio, lens, _ = br.compress_project(raw[mine].to(dev), raw_lens[mine].to(dev))
-    rows_g, lens_g = D.all_gather_packed(audio, lens)
+    rows_g, lens_g = D.all_gather_packed(audio, lens, n_global=B)
     out = br.splice(rows_g, lens_g, ids.to(dev), mask.to(dev))
     # single-GPU reference on the same device
     ref = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
     ok = (torch.equal(lens_g, ref[4]) and torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
           and torch.equal(out[3], ref[3]))
     valid = int(out[1].sum())
+    # the whole packed step: length-grouped re-deal, this rank's utterances picked out of the all-gather buffer
+    plen = mask.sum(1).tolist()
+    outs, info = D.packed_inference_step(br, raw[mine].to(dev), raw_lens[mine].to(dev), ids.to(dev), mask.to(dev), plen)
+    sels = [None] * world
+    dist.all_gather_object(sels, info["sel"])
+    ok = ok and sorted(sum(sels, [])) == list(range(B))            # the re-deal is a partition of the global batch
+    if outs is not None:
+        emb_s, mask_s, _, pos_s, _ = outs
+        for k, u in enumerate(info["sel"]):                        # left-padded: compare the valid tail of every row
+            n = int(ref[1][u].sum())
+            ok = ok and int(mask_s[k].sum()) == n and torch.equal(emb_s[k, emb_s.shape[1] - n:], ref[0][u, ref[0].shape[1] - n:])
+            ok = ok and torch.equal(pos_s[k, pos_s.shape[1] - n:], ref[3][u, ref[3].shape[1] - n:])
     q.put((rank, bool(ok), valid / out[1].numel()))
     dist.destroy_process_group()
 
@@ -89,7 +101,7 @@ def _worker_overlap(rank, world, port, q):
     params = list(proj.parameters())
 
     def grads(overlap):
-        D.enable_overlapped_allreduce(overlap)
+        D.enable_overlapped_allreduce(overlap, params=params)
         for p in params:
             p.grad = None
         y = proj.forward_token_rows(rows)
@@ -107,6 +119,15 @@ def _worker_overlap(rank, world, port, q):
     got = grads(True)
     D.enable_overlapped_allreduce(False)
     ok = all(torch.allclose(a, b, rtol=1e-6, atol=1e-9) for a, b in zip(ref, got))
+    # bf16 on the wire: one message of half the size, averaged back into the fp32 gradients
+    for p in params:
+        p.grad = None
+    y = proj.forward_token_rows(rows)
+    (y * gy).sum().backward()
+    D.allreduce_gradients(params, wire_dtype=torch.bfloat16)
+    for a, p in zip(ref, params):
+        scale = a.abs().max().item() + 1e-12
+        ok = ok and ((p.grad - a).abs().max().item() / scale) < 2e-2
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -58,10 +58,13 @@ def test_concat_ranges_and_global_order():
 
 def test_overlap_hook_is_off_without_a_process_group():
     import ps_slm_b200.dist as D
-    D.enable_overlapped_allreduce(True)
+    params = [torch.nn.Parameter(torch.zeros(3))]
+    with pytest.raises(ValueError):
+        D.enable_overlapped_allreduce(True)                                      # the parameters are required
+    D.enable_overlapped_allreduce(True, params=params)
     try:
         assert D.overlap_hook() is None                                          # single process: nothing to overlap
-        assert D.allreduce_gradients([torch.nn.Parameter(torch.zeros(3))]) == []
+        assert D.allreduce_gradients(params) == []
     finally:
         D.enable_overlapped_allreduce(False)
 

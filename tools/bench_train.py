@@ -68,7 +68,7 @@ def main():
     n_param = sum(p.numel() for p in params)
 
     tbatch = ops.TokenBatch(ids_list)
-    D.enable_overlapped_allreduce(world > 1 and args.overlap)
+    D.enable_overlapped_allreduce(world > 1 and args.overlap, params=params)
 
     def step(i, timers, tr=None):
         if args.dense:

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 free -g | head -2; nproc
 export TASU_EXPERIMENTAL=1
 : > gpurun_out/rc_r2a.txt
-for group in widegemm streamk pair; do
+for group in pair; do
     timeout 600 python -m pytest tests/test_gpu_experimental.py -q -m gpu --timeout 120 --timeout-method=thread -k "$group" \
         > gpurun_out/t2a_$group.log 2>&1
     echo "$group rc=$?" >> gpurun_out/rc_r2a.txt
@@ -16,7 +16,7 @@ for group in widegemm streamk pair; do
     fi
 done
 unset TASU_EXPERIMENTAL
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -q -m gpu --timeout 600 -k "exact or refined or fullsize_vs_oracle or midsize" \
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -q -m gpu --timeout 600 -k "exact or refined or fullsize_vs_oracle or midsize or overflow" \
     > gpurun_out/t2a_exact.log 2>&1
 echo "exact rc=$?" >> gpurun_out/rc_r2a.txt
 tail -30 gpurun_out/t2a_exact.log
