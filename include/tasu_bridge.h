@@ -123,7 +123,9 @@ int tasu_row_norm_max(const void* w, int dtype, int rows, int cols, int64_t ld,
                       uint32_t* out_enc /*[1] order-preserving encoding of max_r ||w_r||_2; zeroed by the call*/, void* stream);
 int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_blank, const float* row_max,
                                const float* row_sumexp, const float* row_sumexp2 /*or NULL*/, const int64_t* lens,
-                               const void* x, int x_dtype, int64_t ldx, int K, const uint32_t* w_norm_max_enc,
+                               const void* x, int x_dtype, int64_t ldx, int K,
+                               const float* x_sumsq /*[B*(T+n_prefix)] squared row norms (tasu_cast_rows_sumsq) or NULL: taken from x*/,
+                               const uint32_t* w_norm_max_enc,
                                float err_scale, int B, int T, int n_prefix, int blank_id, float threshold,
                                float* dec_max, float* dec_sum, int32_t* frame_idx, int32_t* raw_row, int32_t* count,
                                void* stream);
@@ -195,6 +197,11 @@ int tasu_sim_posterior_rows(const int32_t* tok, const float* hot, const float* b
                             const int64_t* dst_row, int64_t n_rows, int V,
                             void* out, int out_dtype, int64_t out_row_stride,
                             float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+
+/* fp32 -> bf16 row cast (pad columns of the pitch zero-filled) that also emits the squared 2-norm of every fp32 row:
+ * the per-frame ||x_f|| of the exact-decision error bound, taken where the encoder output is read anyway. */
+int tasu_cast_rows_sumsq(const float* src, int64_t rows, int cols, int64_t src_stride, void* dst_bf16, int64_t dst_stride,
+                         float* row_sumsq, void* stream);
 
 /* Content fingerprint of up to 8 device buffers (4096 evenly spaced 32-bit words of each, position-dependent hash):
  * the host mirror validates its cached bf16 / folded weight copies with it, because optimizers that update parameters
@@ -453,6 +460,12 @@ int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, in
  * inputs_embeds this is the backward of the audio part of the splice (index_put of ps-slm.py:867-869; training). */
 int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stride, const int32_t* idx, int64_t n_rows, int H,
                      void* dst, int64_t dst_row_stride, void* stream);
+
+/* Backward of the text part of the splice (ps-slm.py:833-834 index_put of inputs_embeds): grad_text [text_rows, H]
+ * (zero-filled by the call) receives grad_emb[r] at row row_src[r] for every destination row r copied from a text row
+ * (row_src = the map tasu_splice_scatter wrote into row_src_ws, text_mode 0: flattened token index b*S + j). */
+int tasu_splice_text_grad(const void* grad_emb, int dtype, int64_t grad_row_stride, const int64_t* row_src, int64_t n_rows,
+                          int H, void* grad_text, int64_t text_row_stride, int64_t text_rows, void* stream);
 
 /* dst[i] = cast(scale * src[i]), i < n: gradient wire format of the data-parallel all-reduce (fp32 -> bf16 before it,
  * bf16 -> fp32 with the 1/world factor after it; reference: fp32 ZeRO-2 reduce-scatter, conf/ds_config.json:15-21). */

@@ -32,7 +32,8 @@ SIGNATURES = {
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_row_norm_max": (_I, [_P, _I, _I, _I, _L, _P, _P]),
-    "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _F, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _P, _F, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "tasu_cast_rows_sumsq": (_I, [_P, _L, _I, _L, _P, _L, _P, _P]),
     "tasu_ctc_head_refine_workspace": (_L, [_L]),
     "tasu_ctc_head_refine": (_I, [_P, _I, _L, _P, _L, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
@@ -83,6 +84,7 @@ SIGNATURES = {
                                  _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_flat_scale_cast": (_I, [_P, _I, _P, _I, _L, _F, _P]),
     "tasu_packed_select": (_I, [_P, _I, _L, _L, _I, _P, _I, _I, _L, _P, _I, _P, _L, _L, _P, _P, _P, _P]),
+    "tasu_splice_text_grad": (_I, [_P, _I, _L, _P, _L, _I, _P, _L, _L, _P]),
     "tasu_gather_rows": (_I, [_P, _I, _L, _P, _L, _I, _P, _L, _P]),
 }
 

@@ -10,8 +10,9 @@ The reference trains the projector with plain autograd through nn.LayerNorm / nn
   dW1/dγ/dβ from G by the LayerNorm-fold algebra (no third big GEMM), db1, db2.  The input (a
   posterior) never needs a gradient.
 * ``SpliceFunction``      — forward: tasu_splice_scatter; backward: gather of the upstream gradient at
-  the audio slots (tasu_gather_rows through the scatter's audio_dest map).  Text embeddings are treated as constants (frozen LLM,
-  scripts/finetune_deespeed_sensevoice.sh:84).
+  the audio slots (tasu_gather_rows through the scatter's audio_dest map) and, when the text embeddings require it
+  (freeze_llm=False, or PEFT with trained embed_tokens, ps-slm.py:119-123), the scatter of the gradient back to the
+  text tokens (tasu_splice_text_grad).
 """
 import torch
 
@@ -156,18 +157,22 @@ class LinearFunction(torch.autograd.Function):
 
 
 class SpliceFunction(torch.autograd.Function):
-    """Differentiable splice: gradient flows to the audio rows only."""
+    """Differentiable splice (ps-slm.py:833-869): the gradient of ``inputs_embeds`` flows to the audio rows (gather at the
+    audio slots) and — when ``text_src`` is the ``[B, S, H]`` text embedding tensor (text_mode 0) and requires it — to the
+    text embeddings (every text token receives the gradient of the row it was copied to).  With the fused embedding
+    lookup (text_mode 1) the table is a constant: callers that train ``embed_tokens`` materialise ``inputs_embeds`` first
+    (bridge.merge_packed_audio_rows does)."""
 
     @staticmethod
-    def forward(ctx, audio_rows, plan, spliced_len, text_src, text_mode, audio_layout, audio_max_len, labels,
+    def forward(ctx, audio_rows, text_src, plan, spliced_len, text_mode, audio_layout, audio_max_len, labels,
                 pad_id, ignore_id):
-        emb, mask, out_labels, pos, fids = ops.splice_scatter(plan, spliced_len, text_src, text_mode,
+        emb, mask, out_labels, pos, fids = ops.splice_scatter(plan, spliced_len, text_src.detach(), text_mode,
                                                               audio_rows.detach(), audio_layout, audio_max_len,
                                                               labels, pad_id, ignore_id,
                                                               left_padding=getattr(plan, "left_padding", None),
                                                               want_audio_dest=True)
-        ctx.plan, ctx.layout, ctx.max_len = plan, audio_layout, audio_max_len
-        ctx.shape = tuple(audio_rows.shape)
+        ctx.plan, ctx.layout, ctx.max_len, ctx.text_mode = plan, audio_layout, audio_max_len, text_mode
+        ctx.shape, ctx.text_shape = tuple(audio_rows.shape), tuple(text_src.shape)
         ctx.mark_non_differentiable(mask, pos, fids)
         if out_labels is not None:
             ctx.mark_non_differentiable(out_labels)
@@ -175,6 +180,12 @@ class SpliceFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, demb, *_):
-        n_rows = ctx.shape[0] if ctx.layout == 0 else 0
-        ga = ops.splice_audio_grad(ctx.plan, demb, ctx.layout, ctx.max_len, n_rows)
-        return (ga.view(ctx.shape), None, None, None, None, None, None, None, None, None)
+        ga = gt = None
+        if ctx.needs_input_grad[0]:
+            n_rows = ctx.shape[0] if ctx.layout == 0 else 0
+            ga = ops.splice_audio_grad(ctx.plan, demb, ctx.layout, ctx.max_len, n_rows).view(ctx.shape)
+        if ctx.needs_input_grad[1]:
+            if ctx.text_mode != 0:
+                raise NotImplementedError("gradient to the embedding table through the fused lookup: pass inputs_embeds")
+            gt = ops.splice_text_grad(ctx.plan, demb).view(ctx.text_shape)
+        return (ga, gt, None, None, None, None, None, None, None, None)

@@ -197,10 +197,10 @@ def merge_input_ids_with_audio_features(audio_features: torch.Tensor, num_audio_
     ops.splice_plan(p, num_audio_tokens, 1)
     hdr = p.header.cpu()
     _raise_splice_errors(hdr, attention_mask, num_audio_tokens.numel())
-    if torch.is_grad_enabled() and audio_features.requires_grad:
-        from .autograd import SpliceFunction            # gradient flows back to the projector output
+    if torch.is_grad_enabled() and (audio_features.requires_grad or inputs_embeds.requires_grad):
+        from .autograd import SpliceFunction            # gradient flows back to the projector output and the text embeddings
         p.left_padding = int(hdr[L.SH_LEFT_PADDING])
-        return SpliceFunction.apply(audio_features, p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds.detach(), 0, 1,
+        return SpliceFunction.apply(audio_features, inputs_embeds, p, int(hdr[L.SH_SPLICED_LEN]), 0, 1,
                                     audio_features.shape[1], labels, pad_id, ignore_id)
     return ops.splice_scatter(p, int(hdr[L.SH_SPLICED_LEN]), inputs_embeds, 0, audio_features, 1,
                               audio_features.shape[1], labels, pad_id, ignore_id,
@@ -256,12 +256,16 @@ def merge_packed_audio_rows(audio_rows: torch.Tensor, num_audio_tokens: torch.Te
     were computed (``begin_splice_plan``)."""
     if audio_rows.dtype != text_src.dtype:
         audio_rows = audio_rows.to(text_src.dtype)
+    if text_mode == 1 and torch.is_grad_enabled() and text_src.requires_grad:
+        # embed_tokens is being trained (freeze_llm=False / PEFT "embs are hot", ps-slm.py:119-123): the lookup stays a
+        # differentiable torch op (ps-slm.py:525) and the splice hands the gradient of its text rows back to it
+        text_src, text_mode = torch.nn.functional.embedding(input_ids, text_src), 0
     if pending is None:
         pending = begin_splice_plan(input_ids, attention_mask, num_audio_tokens, speech_id)
     p, spliced_len = pending.finish()
-    if torch.is_grad_enabled() and audio_rows.requires_grad:
+    if torch.is_grad_enabled() and (audio_rows.requires_grad or text_src.requires_grad):
         from .autograd import SpliceFunction
-        return SpliceFunction.apply(audio_rows, p, spliced_len, text_src.detach(), text_mode, 0,
+        return SpliceFunction.apply(audio_rows, text_src, p, spliced_len, text_mode, 0,
                                     max_audio_tokens, labels, pad_id, ignore_id)
     return ops.splice_scatter(p, spliced_len, text_src, text_mode, audio_rows, 0, max_audio_tokens,
                               labels, pad_id, ignore_id, left_padding=p.left_padding)
@@ -470,6 +474,21 @@ class TasuBridge:
             return w, ops.row_norm_max(w)
         return self._ctc_exact_cache.get([self.w_ctc], build)
 
+    def _encoder_rows_bf16(self, raw_encoder_out):
+        """[B, T+4, D] encoder output → bf16 rows [B*(T+4), pad64(D)] for the tensor cores (a no-op for a bf16 hand-over);
+        with exact decisions the fp32 cast also yields the squared row norms of the error bound (``self._x_sumsq``)."""
+        B, T4, Denc = raw_encoder_out.shape
+        x2 = raw_encoder_out.reshape(B * T4, Denc)
+        self._x_sumsq = None
+        if x2.dtype == torch.bfloat16:
+            return x2
+        with self._stage("cast_encoder_out"):
+            if self.exact_decisions and x2.dtype == torch.float32:
+                x2, self._x_sumsq = ops.cast_rows_sumsq(x2, ops.pad_to(Denc))
+            else:
+                x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+        return x2
+
     def _head_stats(self, raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V):
         """(a1 + the decisions of a2) fused CTC head statistics, refined to fp32-exact decisions when asked for."""
         with self._stage("ctc_head_stats"):
@@ -481,7 +500,8 @@ class TasuBridge:
                 if rows.dtype not in (torch.float32, torch.bfloat16):
                     rows = rows.float()
                 self.last_ambiguous = ops.refine_ambiguous_frames(st, lens, rows, w32, b_ctc, wnorm, T, self.N_PREFIX, V,
-                                                                  self.blank_id, self.blank_threshold)
+                                                                  self.blank_id, self.blank_threshold,
+                                                                  x_sumsq=getattr(self, "_x_sumsq", None))
         return st
 
     def _weight_params(self):
@@ -531,10 +551,7 @@ class TasuBridge:
         with self._stage("splice_plan"):
             sp = ops.splice_rowstat(input_ids, attention_mask, self.speech_id)
 
-        x2 = raw_encoder_out.reshape(B * T4, Denc)
-        if x2.dtype != torch.bfloat16:
-            with self._stage("cast_encoder_out"):
-                x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+        x2 = self._encoder_rows_bf16(raw_encoder_out)
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
         # The plan headers are written by the kernels straight into pinned (UVA-mapped) host memory: the one
         # device→host hand-off of the step needs no copy-engine transfer, so it cannot queue behind the bulk
@@ -628,9 +645,7 @@ class TasuBridge:
         w_ctc, b_ctc = self._ctc_weights()
         proj_w = self.projector.folded_weights()
         out_dtype = self.embed_table.dtype
-        x2 = raw_encoder_out.reshape(B * T4, Denc)
-        if x2.dtype != torch.bfloat16:
-            x2, _, _ = ops.cast_rows(x2, torch.bfloat16, ops.pad_to(Denc))
+        x2 = self._encoder_rows_bf16(raw_encoder_out)
         lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
         st = self._head_stats(raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V)
         plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])

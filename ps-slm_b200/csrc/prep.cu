@@ -68,6 +68,35 @@ cast_f32_bf16_vec_kernel(const float* __restrict__ src, int64_t rows, int cols8,
     }
 }
 
+// fp32 → bf16 row cast that also emits the squared 2-norm of every (fp32) row: one warp per row.  The exact-decision
+// error bound of the fused CTC head needs ||x_f|| per frame (csrc/refine.cu); taken here it costs no extra pass.
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_sumsq_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t sstride, __nv_bfloat16* __restrict__ dst,
+                           int64_t dstride, int64_t dcols, float* __restrict__ row_sumsq, int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nwarp) {
+        const float* s = src + r * sstride;
+        __nv_bfloat16* d = dst + r * dstride;
+        float q = 0.f;
+        if (vec) {
+            for (int c = lane; c < cols / 8; c += 32) {
+                const uint4 a = ld_stream_u4(reinterpret_cast<const uint4*>(s) + 2 * c), b = ld_stream_u4(reinterpret_cast<const uint4*>(s) + 2 * c + 1);
+                const float v[8] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+                                    __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) q = fmaf(v[e], v[e], q);
+                reinterpret_cast<uint4*>(d)[c] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+        } else {
+            for (int c = lane; c < cols; c += 32) { const float v = s[c]; q = fmaf(v, v, q); d[c] = __float2bfloat16_rn(v); }
+        }
+        for (int64_t c = cols + lane; c < dcols; c += 32) d[c] = __float2bfloat16_rn(0.f);     // pad columns of the pitch
+        q = warp_sum(q);
+        if (lane == 0) row_sumsq[r] = q;
+    }
+}
+
 // one CTA per output feature n (row of W1)
 __global__ void __launch_bounds__(256)
 fold_layernorm_kernel(const float* __restrict__ w1, int64_t wstride, const float* __restrict__ gamma,
@@ -470,6 +499,21 @@ extern "C" int tasu_fingerprint(const void* const* ptrs_host, const int64_t* nby
         a.words[i] = nbytes_host[i] / 4;
     }
     fingerprint_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, (unsigned long long*)out);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_cast_rows_sumsq(const float* src, int64_t rows, int cols, int64_t src_stride, void* dst_bf16,
+                                    int64_t dst_stride, float* row_sumsq, void* stream) {
+    TASU_CHECK_ARG(rows >= 0 && cols > 0 && src_stride >= cols && dst_stride >= cols, "shape");
+    if (rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(src && dst_bf16 && row_sumsq, "null pointer");
+    const int vec = cols % 8 == 0 && src_stride % 4 == 0 && dst_stride % 8 == 0 && (uintptr_t)src % 16 == 0 &&
+                    (uintptr_t)dst_bf16 % 16 == 0;
+    int64_t g = (rows + 7) / 8, gmax = (int64_t)tasu::sm_count() * 16;
+    if (g > gmax) g = gmax;
+    cast_f32_bf16_sumsq_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, src_stride, (__nv_bfloat16*)dst_bf16,
+                                                                            dst_stride, dst_stride, row_sumsq, vec);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -33,47 +33,66 @@ row_norm_max_kernel(const T* __restrict__ w, int rows, int cols, int64_t ld, uin
     if (lane == 0) atomicMax(out_enc, float_to_ordered(sqrtf(ss)));
 }
 
-template <typename TX>
-__global__ void __launch_bounds__(256)
-flag_ambiguous_kernel(const int32_t* __restrict__ argmax, const float* __restrict__ x_blank, const float* __restrict__ row_max,
-                      const float* __restrict__ row_sumexp, const float* __restrict__ row_sumexp2,
-                      const int64_t* __restrict__ lens, const TX* __restrict__ x, int64_t ldx, int K,
-                      const uint32_t* __restrict__ w_norm_max_enc, float err_scale, int B, int T, int n_prefix, int blank,
-                      float logit_thr, float* __restrict__ dec_max, float* __restrict__ dec_sum,
-                      int32_t* __restrict__ frame_idx, int32_t* __restrict__ raw_row, int32_t* __restrict__ count) {
-    const int lane = threadIdx.x & 31;
-    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (f >= (int64_t)B * T) return;
-    const int b = (int)(f / T), t = (int)(f % T);
-    const float m = row_max[f], s = row_sumexp[f];
-    if (lane == 0) { dec_max[f] = m; dec_sum[f] = s; }             // the plan's normalisers; refined frames are overwritten
-    if (t >= lens[b]) return;
-    const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
-    const TX* px = x + r * ldx;
-    float ss = 0.f;
-    for (int k = lane; k < K; k += 32) { const float v = to_f32(px[k]); ss = fmaf(v, v, ss); }
-    ss = warp_sum(ss);
-    if (lane != 0) return;
-    const float margin = 2.f * err_scale * sqrtf(ss) * ordered_to_float(*w_norm_max_enc);
+struct FlagArgs {
+    const int32_t* argmax; const float* x_blank; const float* row_max; const float* row_sumexp; const float* row_sumexp2;
+    const int64_t* lens; const uint32_t* w_norm_max_enc; float err_scale; int B, T, n_prefix, blank; float logit_thr;
+    float* dec_max; float* dec_sum; int32_t* frame_idx; int32_t* raw_row; int32_t* count;
+};
+
+// decision of one valid frame f (raw row r) whose squared input norm is ss; called by one thread
+__device__ __forceinline__ void flag_frame(const FlagArgs& a, int64_t f, int64_t r, float ss) {
+    const float m = a.row_max[f], s = a.row_sumexp[f];
+    const float margin = 2.f * a.err_scale * sqrtf(ss) * ordered_to_float(*a.w_norm_max_enc);
     // lower bound of the top-2 logit gap: log(p1 / p2_max)
     const float p1 = 1.f / s;
     float p2 = (s - 1.f) / s;                                      // everything that is not the maximum
-    if (row_sumexp2 != nullptr) {
-        const float q = fmaxf(row_sumexp2[f] / (s * s) - p1 * p1, 0.f) + 4e-6f;    // Σ_{v != argmax} p_v² (+ rounding slack)
+    if (a.row_sumexp2 != nullptr) {
+        const float q = fmaxf(a.row_sumexp2[f] / (s * s) - p1 * p1, 0.f) + 4e-6f;  // Σ_{v != argmax} p_v² (+ rounding slack)
         p2 = fminf(p2, sqrtf(q));
     }
     const float gap = p2 > 0.f ? logf(p1) - logf(p2) : INFINITY;
     // logit of the blank probability
-    const float xb = x_blank[f];
+    const float xb = a.x_blank[f];
     const float rest = s - expf(xb - m);
     const float lb = rest > 0.f ? (xb - m) - logf(rest) : INFINITY;
     bool amb = !(gap >= margin);                                   // NaN statistics are listed, never trusted
-    if (argmax[f] == blank) amb = amb || fabsf(lb - logit_thr) < margin;
-    else amb = amb || (lb + margin >= logit_thr);
+    if (a.argmax[f] == a.blank) amb = amb || fabsf(lb - a.logit_thr) < margin;
+    else amb = amb || (lb + margin >= a.logit_thr);
     if (!amb) return;
-    const int k = atomicAdd(count, 1);
-    frame_idx[k] = (int32_t)f;
-    raw_row[k] = (int32_t)r;
+    const int k = atomicAdd(a.count, 1);
+    a.frame_idx[k] = (int32_t)f;
+    a.raw_row[k] = (int32_t)r;
+}
+
+// one warp per frame: the warp sums the squares of the frame's encoder row
+template <typename TX>
+__global__ void __launch_bounds__(256)
+flag_ambiguous_kernel(const FlagArgs a, const TX* __restrict__ x, int64_t ldx, int K) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= (int64_t)a.B * a.T) return;
+    const int b = (int)(f / a.T), t = (int)(f % a.T);
+    if (lane == 0) { a.dec_max[f] = a.row_max[f]; a.dec_sum[f] = a.row_sumexp[f]; }   // the plan's normalisers; refined frames are overwritten
+    if (t >= a.lens[b]) return;
+    const int64_t r = (int64_t)b * (a.T + a.n_prefix) + a.n_prefix + t;
+    const TX* px = x + r * ldx;
+    float ss = 0.f;
+    for (int k = lane; k < K; k += 32) { const float v = to_f32(px[k]); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    if (lane == 0) flag_frame(a, f, r, ss);
+}
+
+// one thread per frame: the squared row norms were produced by the cast of the encoder output (tasu_cast_rows_sumsq)
+__global__ void __launch_bounds__(256)
+flag_ambiguous_sumsq_kernel(const FlagArgs a, const float* __restrict__ x_sumsq) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= (int64_t)a.B * a.T) return;
+    const int b = (int)(f / a.T), t = (int)(f % a.T);
+    a.dec_max[f] = a.row_max[f];
+    a.dec_sum[f] = a.row_sumexp[f];
+    if (t >= a.lens[b]) return;
+    const int64_t r = (int64_t)b * (a.T + a.n_prefix) + a.n_prefix + t;
+    flag_frame(a, f, r, x_sumsq[r]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -291,10 +310,10 @@ extern "C" int tasu_row_norm_max(const void* w, int dtype, int rows, int cols, i
 
 extern "C" int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_blank, const float* row_max,
                                           const float* row_sumexp, const float* row_sumexp2, const int64_t* lens,
-                                          const void* x, int x_dtype, int64_t ldx, int K, const uint32_t* w_norm_max_enc,
-                                          float err_scale, int B, int T, int n_prefix, int blank_id, float threshold,
-                                          float* dec_max, float* dec_sum, int32_t* frame_idx, int32_t* raw_row,
-                                          int32_t* count, void* stream) {
+                                          const void* x, int x_dtype, int64_t ldx, int K, const float* x_sumsq,
+                                          const uint32_t* w_norm_max_enc, float err_scale, int B, int T, int n_prefix,
+                                          int blank_id, float threshold, float* dec_max, float* dec_sum, int32_t* frame_idx,
+                                          int32_t* raw_row, int32_t* count, void* stream) {
     TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && K > 0 && ldx >= K, "shape");
     TASU_CHECK_ARG(x_dtype == TASU_F32 || x_dtype == TASU_BF16, "x_dtype");
     TASU_CHECK_ARG(err_scale >= 0.f, "err_scale");
@@ -304,19 +323,20 @@ extern "C" int tasu_flag_ambiguous_frames(const int32_t* argmax, const float* x_
     TASU_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
     const int64_t n = (int64_t)B * T;
     if (n == 0) return TASU_OK;
-    TASU_CHECK_ARG(argmax && x_blank && row_max && row_sumexp && lens && x && w_norm_max_enc && dec_max && dec_sum &&
+    TASU_CHECK_ARG(argmax && x_blank && row_max && row_sumexp && lens && (x || x_sumsq) && w_norm_max_enc && dec_max && dec_sum &&
                    frame_idx && raw_row, "null pointer");
-    const float logit_thr = threshold >= 1.f ? INFINITY : threshold <= 0.f ? -INFINITY : logf(threshold) - log1pf(-threshold);
-    const unsigned grid = (unsigned)((n + 7) / 8);
-    if (x_dtype == TASU_F32)
-        flag_ambiguous_kernel<float><<<grid, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, row_sumexp2, lens, (const float*)x,
-                                                          ldx, K, w_norm_max_enc, err_scale, B, T, n_prefix, blank_id, logit_thr,
-                                                          dec_max, dec_sum, frame_idx, raw_row, count);
+    FlagArgs a{};
+    a.argmax = argmax; a.x_blank = x_blank; a.row_max = row_max; a.row_sumexp = row_sumexp; a.row_sumexp2 = row_sumexp2;
+    a.lens = lens; a.w_norm_max_enc = w_norm_max_enc; a.err_scale = err_scale; a.B = B; a.T = T; a.n_prefix = n_prefix;
+    a.blank = blank_id;
+    a.logit_thr = threshold >= 1.f ? INFINITY : threshold <= 0.f ? -INFINITY : logf(threshold) - log1pf(-threshold);
+    a.dec_max = dec_max; a.dec_sum = dec_sum; a.frame_idx = frame_idx; a.raw_row = raw_row; a.count = count;
+    if (x_sumsq != nullptr)
+        flag_ambiguous_sumsq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, x_sumsq);
+    else if (x_dtype == TASU_F32)
+        flag_ambiguous_kernel<float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, (const float*)x, ldx, K);
     else
-        flag_ambiguous_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, row_sumexp2, lens,
-                                                                  (const __nv_bfloat16*)x, ldx, K, w_norm_max_enc, err_scale, B, T,
-                                                                  n_prefix, blank_id, logit_thr, dec_max, dec_sum, frame_idx,
-                                                                  raw_row, count);
+        flag_ambiguous_kernel<__nv_bfloat16><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, (const __nv_bfloat16*)x, ldx, K);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

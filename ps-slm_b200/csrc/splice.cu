@@ -364,6 +364,23 @@ gather_rows_kernel(const void* __restrict__ src, int64_t src_stride, const int32
     }
 }
 
+// backward of the TEXT part of the splice (ps-slm.py:833: final_embedding[b, text_to_overwrite] = inputs_embeds[b, non_audio]):
+// dst[row_src[r], :] = src[r, :] for every destination row r that was copied from a text row (one-to-one, no accumulation);
+// dst is zero-filled by the caller (speech / padded tokens receive no gradient).
+template <int ESZ>
+__global__ void __launch_bounds__(256)
+scatter_text_rows_kernel(const void* __restrict__ src, int64_t src_stride, const int64_t* __restrict__ row_src, int64_t n_rows,
+                         int H, void* __restrict__ dst, int64_t dst_stride, int64_t dst_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += nwarp) {
+        const int64_t sr = row_src[r];
+        if (sr < 0 || sr >= kAudioFlag || sr >= dst_rows) continue;
+        copy_row_warp(reinterpret_cast<const char*>(src) + r * src_stride * ESZ,
+                      reinterpret_cast<char*>(dst) + sr * dst_stride * ESZ, (int64_t)H * ESZ, lane);
+    }
+}
+
 }  // namespace tasu
 
 using namespace tasu;
@@ -463,6 +480,26 @@ extern "C" int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stri
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TASU_F32) gather_rows_kernel<4><<<grid, 256, 0, st>>>(src, src_row_stride, idx, n_rows, H, dst, dst_row_stride);
     else gather_rows_kernel<2><<<grid, 256, 0, st>>>(src, src_row_stride, idx, n_rows, H, dst, dst_row_stride);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_splice_text_grad(const void* grad_emb, int dtype, int64_t grad_row_stride, const int64_t* row_src,
+                                     int64_t n_rows, int H, void* grad_text, int64_t text_row_stride, int64_t text_rows,
+                                     void* stream) {
+    TASU_CHECK_ARG(n_rows >= 0 && text_rows >= 0 && H > 0 && grad_row_stride >= H && text_row_stride >= H, "shape");
+    TASU_CHECK_ARG(dtype == TASU_F32 || dtype == TASU_BF16, "dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int esz = dtype == TASU_F32 ? 4 : 2;
+    if (text_rows > 0) {
+        TASU_CHECK_ARG(grad_text != nullptr, "null output");
+        TASU_CHECK_CUDA(cudaMemsetAsync(grad_text, 0, (size_t)text_rows * text_row_stride * esz, st));
+    }
+    if (n_rows == 0 || text_rows == 0) return TASU_OK;
+    TASU_CHECK_ARG(grad_emb && row_src, "null pointer");
+    const unsigned grid = warp_row_grid(n_rows);
+    if (dtype == TASU_F32) scatter_text_rows_kernel<4><<<grid, 256, 0, st>>>(grad_emb, grad_row_stride, row_src, n_rows, H, grad_text, text_row_stride, text_rows);
+    else scatter_text_rows_kernel<2><<<grid, 256, 0, st>>>(grad_emb, grad_row_stride, row_src, n_rows, H, grad_text, text_row_stride, text_rows);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -68,14 +68,16 @@ def setup_encoder_projector(train_config, model_config, **kwargs):
             param.requires_grad = False
         encoder_projector.eval()
     if name == "simple_linear" and getattr(model_config, "ctc_linear", None):
-        # pretrained CTC head over the LLM vocab (ps-slm.py:67-85)
+        # pretrained CTC head over the LLM vocabulary (ps-slm.py:67-85): the checkpoint may be wrapped in {"model": ...},
+        # the head lives under ctc_head.weight / ctc_head.bias, it is loaded strictly and frozen with the encoder
         ckpt = torch.load(model_config.ctc_linear, map_location="cpu")
-        w, b = ckpt.get("ctc_lo.weight"), ckpt.get("ctc_lo.bias")
-        if w is None or b is None:
-            raise KeyError("ctc_linear checkpoint needs ctc_lo.weight / ctc_lo.bias")
-        with torch.no_grad():
-            encoder_projector.map.weight.copy_(w)
-            encoder_projector.map.bias.copy_(b)
+        state = ckpt.get("model", ckpt)
+        proj_state = {"weight": state["ctc_head.weight"], "bias": state["ctc_head.bias"]}
+        encoder_projector.map.load_state_dict(proj_state, strict=True)
+        if getattr(train_config, "freeze_encoder", False):
+            for _, param in encoder_projector.named_parameters():
+                param.requires_grad = False
+            encoder_projector.eval()
     return encoder_projector
 
 
@@ -178,6 +180,11 @@ class slam_model_asr(nn.Module):
             out = out[0]
         return out, out_lens
 
+    def _text_only(self) -> bool:
+        """The branch that never reads the encoder output: simulated posteriors from the transcript.  ``voca_trans``
+        takes precedence over ``gt_emb`` in the reference's dispatch (ps-slm.py:456-458 / :587-589)."""
+        return bool(self.ctc_posterior and self.gt_emb and not self.voca_trans)
+
     def _fused_bridge(self):
         if self._bridge is None:
             ctc_lo = self.encoder.ctc.ctc_lo
@@ -190,16 +197,17 @@ class slam_model_asr(nn.Module):
     def _bridge_outputs(self, raw_encoder_out, raw_encoder_out_lens, input_ids, attention_mask, labels, texts, noisy):
         """Steps 1–4 of the hot path with the reference's flag dispatch (ps-slm.py:456-528 / :587-658)."""
         table = self.llm.get_input_embeddings().weight
-        fused_ok = (self.ctc_posterior and not self.gt_emb and self.do_psd
+        fused_ok = (self.ctc_posterior and not self.voca_trans and not self.gt_emb and self.do_psd
                     and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
-                    and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_projector.parameters()))
+                    and not (torch.is_grad_enabled() and (table.requires_grad
+                                                          or any(p.requires_grad for p in self.encoder_projector.parameters())))
                     and table.dtype in (torch.float32, torch.bfloat16))
         if fused_ok:                                           # shipped inference configuration
             emb, mask, out_labels, pos, _ = self._fused_bridge()(raw_encoder_out, raw_encoder_out_lens, input_ids,
                                                                  attention_mask, labels)
             return emb, mask, out_labels, pos
         blank = self.encoder.blank_id
-        rows_ok = (self.ctc_posterior and self.gt_emb and self.token_row_path
+        rows_ok = (self._text_only() and self.token_row_path
                    and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
                    and table.dtype in (torch.float32, torch.bfloat16))
         if rows_ok:
@@ -239,7 +247,7 @@ class slam_model_asr(nn.Module):
                 projector_outs, feat_len, inputs_embeds, input_ids, attention_mask, labels)
             return emb, mask, out_labels, pos
         if self.ctc_posterior:
-            if self.gt_emb:
+            if self.gt_emb:                                        # voca_trans was handled above: this is _text_only()
                 post, lens = (self.ctc_pseudo_posterior_noise(texts) if noisy else self.ctc_pseudo_posterior(texts))
                 encoder_outs, feat_len = post.to(input_ids.device), lens.to(input_ids.device)
             else:
@@ -276,7 +284,7 @@ class slam_model_asr(nn.Module):
                 position_ids=None, past_key_values=None, inputs_embeds=None, GT: Optional[List[str]] = None,
                 labels: Optional[torch.LongTensor] = None, use_cache=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None):
-        if self.ctc_posterior and self.gt_emb:
+        if self._text_only():
             # text-only branch: the encoder output is never used (ps-slm.py:459-468); skipping the dead
             # encoder pass changes no result
             raw, raw_lens = None, None
@@ -301,7 +309,7 @@ class slam_model_asr(nn.Module):
                  position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
                  output_attentions=None, output_hidden_states=None, return_dict=None, targets=None, **kwargs):
         texts = None
-        if self.ctc_posterior and self.gt_emb:
+        if self._text_only():
             texts = [re.sub(r"[^A-Za-z\s.,!?]+", "", t).lower().strip() for t in targets]   # ps-slm.py:592-594
             raw, raw_lens = None, None
         else:

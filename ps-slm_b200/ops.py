@@ -156,13 +156,30 @@ ERR_SCALE_F32_INPUT = 1.05 * 2.0 ** -8     # x and W both rounded to bf16 by the
 ERR_SCALE_BF16_INPUT = 1.05 * 2.0 ** -9    # x was GIVEN in bf16: only W is rounded
 
 
+def cast_rows_sumsq(src: torch.Tensor, dst_stride: int):
+    """fp32 [rows, cols] → (bf16 [rows, dst_stride] with zeroed pad columns, squared row norms fp32 [rows])."""
+    _need_cuda(src)
+    if src.dtype != torch.float32 or src.dim() != 2:
+        raise TypeError("cast_rows_sumsq expects a 2-D float32 tensor")
+    if src.shape[1] > 1 and src.stride(1) != 1:
+        src = src.contiguous()
+    rows, cols = src.shape
+    dst = torch.empty(rows, dst_stride, dtype=torch.bfloat16, device=src.device)
+    sumsq = torch.empty(max(rows, 1), dtype=torch.float32, device=src.device)
+    L.check(L.lib().tasu_cast_rows_sumsq(src.data_ptr(), rows, cols, src.stride(0) if rows > 1 else cols, dst.data_ptr(),
+                                         dst_stride, sumsq.data_ptr(), _stream()), "tasu_cast_rows_sumsq")
+    _count(1)
+    return dst, sumsq
+
+
 def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, x_rows: torch.Tensor, w_f32: torch.Tensor,
                             bias: Optional[torch.Tensor], w_norm_max: torch.Tensor, T: int, n_prefix: int, V: int,
-                            blank_id: int, threshold: float) -> torch.Tensor:
+                            blank_id: int, threshold: float, x_sumsq: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Exact-decision mode (csrc/refine.cu): list the frames whose greedy decisions (argmax, ps-slm.py:265; strict fp32
     blank threshold, :295-297) lie inside the rounding error bound of the bf16 head, recompute exactly those with fp32
     FMAs from the fp32 weights, and publish the decision statistics in ``st`` (``argmax`` / ``x_blank`` in place,
-    ``dec_max`` / ``dec_sum`` new) for ``collapse_plan``.  ``x_rows`` = [B*(T+P), K] encoder rows as GIVEN (fp32 or bf16).
+    ``dec_max`` / ``dec_sum`` new) for ``collapse_plan``.  ``x_rows`` = [B*(T+P), K] encoder rows as GIVEN (fp32 or bf16);
+    ``x_sumsq``: their squared norms when already known (``cast_rows_sumsq``).
     The list holds one slot per frame: nothing is capped or dropped.  Returns the device counter (int32[1]); no sync."""
     _need_cuda(x_rows, w_f32, bias)
     dev = st.argmax.device
@@ -178,7 +195,8 @@ def refine_ambiguous_frames(st: FrameStats, lens: torch.Tensor, x_rows: torch.Te
     err = ERR_SCALE_BF16_INPUT if x_rows.dtype == torch.bfloat16 else ERR_SCALE_F32_INPUT
     L.check(lib.tasu_flag_ambiguous_frames(st.argmax.data_ptr(), st.x_blank.data_ptr(), st.row_max.data_ptr(),
                                            st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), lens.data_ptr(),
-                                           x_rows.data_ptr(), _dt(x_rows), x_rows.stride(0), K, w_norm_max.data_ptr(),
+                                           x_rows.data_ptr(), _dt(x_rows), x_rows.stride(0), K, _ptr(x_sumsq),
+                                           w_norm_max.data_ptr(),
                                            float(err), st.B, T, n_prefix, blank_id, float(threshold), dec[0].data_ptr(),
                                            dec[1].data_ptr(), lists[0].data_ptr(), lists[1].data_ptr(), count.data_ptr(),
                                            _stream()), "tasu_flag_ambiguous_frames")
@@ -455,7 +473,7 @@ def sim_posterior_rows(tok: torch.Tensor, hot: torch.Tensor, base: torch.Tensor,
 
 class SplicePlan:
     __slots__ = ("rowstat", "new_pos", "text_prefix", "slot_ord", "slot_base", "audio_off", "header", "left_padding",
-                 "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask", "audio_dest")
+                 "B", "S", "n_audio", "mask_dtype", "speech_id", "input_ids", "attention_mask", "audio_dest", "row_src")
 
 
 def _mask_arg(attention_mask: torch.Tensor):
@@ -568,6 +586,7 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
         emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), row_src.data_ptr(),
         _ptr(audio_dest), _stream()), "tasu_splice_scatter")
     p.audio_dest = audio_dest
+    p.row_src = row_src[:n_pos] if want_audio_dest else None      # kept for the backward of the text rows
     _count(2)
     return emb, mask, out_labels, pos, fids
 
@@ -586,6 +605,21 @@ def splice_audio_grad(p: SplicePlan, grad_emb: torch.Tensor, audio_layout: int, 
                                      ga.data_ptr(), H, _stream()), "tasu_gather_rows")
     _count(1)
     return ga.view(p.n_audio, audio_max_len, H) if audio_layout == 1 else ga
+
+
+def splice_text_grad(p: SplicePlan, grad_emb: torch.Tensor) -> torch.Tensor:
+    """grad wrt ``inputs_embeds [B, S, H]`` (text_mode 0): every text token receives the gradient of the output row it was
+    copied to, speech / padded tokens receive zero (tasu_splice_text_grad; ps-slm.py:833-834 backward)."""
+    _need_cuda(grad_emb)
+    grad_emb = grad_emb.contiguous()
+    B, Sp, H = grad_emb.shape
+    if p.row_src is None:
+        raise L.TasuError("splice_text_grad needs the forward scatter to have run with want_audio_dest=True")
+    gt = torch.empty(p.B * p.S, H, dtype=grad_emb.dtype, device=grad_emb.device)
+    L.check(L.lib().tasu_splice_text_grad(grad_emb.data_ptr(), _dt(grad_emb), H, p.row_src.data_ptr(), B * Sp, H, gt.data_ptr(),
+                                          H, p.B * p.S, _stream()), "tasu_splice_text_grad")
+    _count(1)
+    return gt.view(p.B, p.S, H)
 
 
 # ----------------------------------------------------------------------------- training helpers

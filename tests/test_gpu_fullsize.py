@@ -248,3 +248,41 @@ def test_bridge_edge_cases(dev, case):
     assert torch.equal(l_gpu.cpu(), l_ref) and f_gpu.shape == f_ref.shape
     if f_ref.numel():
         np.testing.assert_allclose(f_gpu.cpu().numpy(), f_ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_cached_weight_copies_follow_data_copy(dev):
+    """DeepSpeed ZeRO-1/2 updates parameters through flat buffers and ``.data.copy_``: neither a tensor's address nor
+    torch's version counter moves.  The cached bf16 / folded weight copies must follow anyway (content fingerprint,
+    piggybacked on the bridge's header read; explicit check in the projector's own evaluation forward)."""
+    import copy
+    import ps_slm_b200.synth as S
+    w, b, proj, table, br = _small_bridge(dev)
+    g = torch.Generator().manual_seed(3)
+    B, T = 3, 40
+    raw = torch.randn(B, T + 4, 32, generator=g) * 3
+    raw_lens = torch.tensor([T + 4, T - 3, T + 1])
+    ids = torch.tensor([[5, 6, 299, 7], [0, 8, 299, 9], [1, 2, 299, 3]])
+    mask = torch.tensor([[1, 1, 1, 1], [0, 1, 1, 1], [1, 1, 1, 1]], dtype=torch.bool)
+    args = (raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+    out0 = [t.clone() for t in br(*args) if t is not None]
+    versions = [p._version for p in proj.parameters()]
+    with torch.no_grad():
+        for p in proj.parameters():
+            p.data.copy_(p.data * 1.5 + 0.25)
+        br.w_ctc.data.copy_(br.w_ctc.data.flip(0))
+    assert versions == [p._version for p in proj.parameters()], "the update must be invisible to the version counter"
+    out1 = [t.clone() for t in br(*args) if t is not None]
+    from ps_slm_b200.bridge import TasuBridge
+    fresh = TasuBridge(br.w_ctc.clone(), br.b_ctc.clone(), copy.deepcopy(proj), table.to(dev), 299, 0)
+    out2 = [t for t in fresh(*args) if t is not None]
+    assert not all(torch.equal(a, c) for a, c in zip(out0, out1))
+    for a, c in zip(out1, out2):
+        assert torch.equal(a, c), "the bridge kept using stale weight copies"
+    # the projector's own (non-fused) evaluation forward
+    x = torch.softmax(torch.randn(2, 7, 61, generator=g), -1).to(dev)
+    y0 = proj(x).clone()
+    with torch.no_grad():
+        proj.ffn[0].weight.data.copy_(proj.ffn[0].weight.data * 0.5)
+    y1 = proj(x)
+    y2 = copy.deepcopy(proj)(x)
+    assert not torch.equal(y0, y1) and torch.equal(y1, y2)

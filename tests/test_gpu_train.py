@@ -121,6 +121,33 @@ def test_splice_backward(dev):
     assert torch.equal(out[0].detach().cpu(), e_r.detach())
     (out[0] * R.to(dev)).sum().backward()
     assert torch.equal(afd.grad.cpu(), af.grad)
+    # the text embeddings are trained too (freeze_llm=False / PEFT with hot embed_tokens, ps-slm.py:119-123): the
+    # index_put of ps-slm.py:833 hands every text token the gradient of the row it was copied to
+    emb_r = emb.clone().requires_grad_(True)
+    af_r = af.detach().clone().requires_grad_(True)
+    e_r2 = O.merge(af_r, M, emb_r, ids, att, lab, SP, PAD)[0]
+    (e_r2 * R).sum().backward()
+    embd = emb.to(dev).clone().requires_grad_(True)
+    afd2 = af.detach().to(dev).clone().requires_grad_(True)
+    out2 = bridge.merge_input_ids_with_audio_features(afd2, M.to(dev), embd, ids.to(dev), att.to(dev), lab.to(dev), SP, PAD)
+    (out2[0] * R.to(dev)).sum().backward()
+    assert torch.equal(embd.grad.cpu(), emb_r.grad) and torch.equal(afd2.grad.cpu(), af_r.grad)
+    # only the text embeddings require a gradient (frozen projector)
+    embd3 = emb.to(dev).clone().requires_grad_(True)
+    out3 = bridge.merge_input_ids_with_audio_features(af.detach().to(dev), M.to(dev), embd3, ids.to(dev), att.to(dev), lab.to(dev), SP, PAD)
+    (out3[0] * R.to(dev)).sum().backward()
+    assert torch.equal(embd3.grad.cpu(), emb_r.grad)
+    # fused embedding lookup with a trainable table: the lookup falls back to the differentiable torch op
+    table = (torch.randn(SP + 1, emb.shape[-1]) * 0.1)          # embed_tokens also looks the <speech> id up (ps-slm.py:525)
+    ids_small = ids
+    t_r = table.clone().requires_grad_(True)
+    e_r4 = O.merge(af.detach(), M, torch.nn.functional.embedding(ids_small, t_r), ids_small, att, lab, SP, PAD)[0]
+    (e_r4 * R).sum().backward()
+    t_d = table.to(dev).clone().requires_grad_(True)
+    packed = torch.cat([af.detach()[b, :int(M[b])] for b in range(af.shape[0])]).to(dev)
+    out4 = bridge.merge_packed_audio_rows(packed, M.to(dev), int(M.max()), t_d, 1, ids_small.to(dev), att.to(dev), lab.to(dev), SP, PAD)
+    (out4[0] * R.to(dev)).sum().backward()
+    assert torch.allclose(t_d.grad.cpu(), t_r.grad, rtol=1e-5, atol=1e-6)
 
 
 def test_text_only_training_step(dev):
@@ -159,7 +186,7 @@ def test_text_only_training_step(dev):
     sp = ops.splice_rowstat(input_ids.to(dev), mask.to(dev), S.SPEECH_ID)
     ops.splice_plan(sp, lens_d, 1)
     hdr = sp.header.cpu()
-    emb, mk, lb, pos, _ = SpliceFunction.apply(y, sp, int(hdr[0]), table.to(dev), 1, 0, int(lens.max()),
+    emb, mk, lb, pos, _ = SpliceFunction.apply(y, table.to(dev), sp, int(hdr[0]), 1, 0, int(lens.max()),
                                                labels.to(dev), S.PAD_ID, S.IGNORE_ID)
     assert torch.equal(mk.cpu(), m_r) and torch.equal(lb.cpu(), l_r) and torch.equal(pos.cpu(), p_r)
     assert _rel(emb.detach().cpu(), e_r.detach()) < 1e-2

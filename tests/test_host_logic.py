@@ -137,3 +137,47 @@ def _check_streamk_schedule(num_tiles, k_blocks, grid):
     # balance: no CTA gets more than one tile's worth of K-blocks in the tail
     for pieces in per_cta:
         assert sum(p[2] - p[1] for p in pieces) <= k_blocks
+
+
+def test_pretrained_ctc_head_checkpoint_format(tmp_path):
+    """setup_encoder_projector('simple_linear', ctc_linear=...) reads the reference's checkpoint layout (ps-slm.py:67-85):
+    optionally wrapped in {"model": ...}, keys ctc_head.weight / ctc_head.bias, strict load, frozen with the encoder."""
+    import ps_slm_b200.model as M
+    w, b = torch.randn(11, 6), torch.randn(11)
+    mc = types.SimpleNamespace(encoder_projector="simple_linear", encoder_dim=6, llm_dim=11, encoder_projector_ds_rate=1)
+    for wrap in (True, False):
+        state = {"ctc_head.weight": w, "ctc_head.bias": b, "unrelated": torch.zeros(1)}
+        path = str(tmp_path / ("ckpt%d.pt" % wrap))
+        torch.save({"model": state} if wrap else state, path)
+        mc.ctc_linear = path
+        for freeze in (True, False):
+            proj = M.setup_encoder_projector(types.SimpleNamespace(freeze_encoder=freeze, freeze_projector=False), mc)
+            assert torch.equal(proj.map.weight, w) and torch.equal(proj.map.bias, b)
+            assert all(p.requires_grad != freeze for p in proj.parameters())
+            assert proj.training != freeze
+    torch.save({"ctc_lo.weight": w, "ctc_lo.bias": b}, str(tmp_path / "bad.pt"))
+    mc.ctc_linear = str(tmp_path / "bad.pt")
+    with pytest.raises(KeyError):
+        M.setup_encoder_projector(types.SimpleNamespace(freeze_encoder=False, freeze_projector=False), mc)
+
+
+def test_train_eval_switch_invalidates_weight_caches():
+    """ProjectorCache: a train() / eval() switch of any bridge module drops every cached weight copy; a training forward
+    (fresh=True) never caches — the copies of one evaluation phase cannot survive the optimizer steps after it."""
+    import ps_slm_b200.bridge as bridge
+    import ps_slm_b200.projector as P
+    p = torch.nn.Parameter(torch.zeros(3))
+    cache = bridge.ProjectorCache()
+    built = []
+    build = lambda: built.append(1) or len(built)      # noqa: E731
+    assert cache.get([p], build) == 1 and cache.get([p], build) == 1
+    with torch.no_grad():
+        p.data.copy_(torch.ones(3))                    # invisible to torch's version counter (what ZeRO does)
+    assert cache.get([p], build) == 1                  # ... so only an invalidation (or the fingerprint on CUDA) rebuilds
+    proj = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=4, llm_dim=5, encoder_projector_ds_rate=1))
+    proj.train()
+    assert cache.get([p], build) == 2
+    proj.eval()
+    assert cache.get([p], build) == 3 and cache.get([p], build) == 3
+    assert cache.get([p], build, fresh=True) == 4 and cache.get([p], build, fresh=True) == 5
+    assert cache.get([p], build) == 6                  # a fresh build leaves nothing behind
