@@ -73,79 +73,126 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference algorithm on the host cores
+# CPU baseline / reference arm: the reference's OWN functions on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_workload(B, T, seed):
+def reference_available():
+    """True when the unmodified reference files are reachable: /root/reference (build container) or the byte-for-byte
+    copies oracle/vendor_ref.py staged under the git-ignored oracle/_ref/ (they travel to the GPU box)."""
+    from oracle import ref_loader as R
+    return R.available()
+
+
+def cpu_workload(B, T, seed, use_reference):
     import torch
     import ps_slm_b200.synth as S
     w, b = S.make_ctc_head()
     raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=seed)
     ids, mask, _ = S.make_prompts(B, seed=seed, left_pad=True)
     torch.manual_seed(0)
-    from oracle import tasu_oracle as O  # noqa: F401  (checker / CPU baseline only)
-    import torch.nn as nn
-    norm = nn.LayerNorm(S.V_CTC)
-    l1, l2 = nn.Linear(S.V_CTC, 2048), nn.Linear(2048, S.H_LLM)
-    pp = tuple(t.detach() for t in (norm.weight, norm.bias, l1.weight, l1.bias, l2.weight, l2.bias))
     table = S.make_embed_table(dtype=torch.float32)
-    return dict(raw=raw, raw_lens=raw_lens, w=w, b=b, ids=ids, mask=mask, pp=pp, table=table)
+    wl = dict(raw=raw, raw_lens=raw_lens, w=w, b=b, ids=ids, mask=mask, table=table)
+    if use_reference:
+        from oracle import ref_loader as R          # checker / CPU baseline only
+        wl["proj"] = R.ref_projector("linear-silu", S.V_CTC, S.H_LLM).eval()
+    else:
+        import torch.nn as nn
+        norm = nn.LayerNorm(S.V_CTC)
+        l1, l2 = nn.Linear(S.V_CTC, 2048), nn.Linear(2048, S.H_LLM)
+        wl["pp"] = tuple(t.detach() for t in (norm.weight, norm.bias, l1.weight, l1.bias, l2.weight, l2.bias))
+    return wl
 
 
 def cpu_step(wl):
-    """Reference algorithm, restated (oracle/tasu_oracle.py): softmax(ctc_lo) → per-frame psd loop
-    → LayerNorm/Linear/SiLU/Linear → merge, fp32, all host threads torch can use."""
+    """One pass of the path on the host, fp32, all host threads torch can use.
+    kind "reference": the reference's own code, unmodified — softmax(ctc_lo) as ps-slm.py:581-585 writes it (ctc_lo = the
+    Linear(512, 25055) of funasr's CTC head, un-vendored: F.linear), then slam_model_asr.psd (ps-slm.py:237-317),
+    EncoderProjectorLinearSiLU (projector.py:129-151), embed_tokens lookup + _merge_input_ids_with_audio_features
+    (ps-slm.py:654-658, :679-873).  kind "port": oracle/tasu_oracle.py's restatement (per-frame psd loop)."""
+    import torch
     import ps_slm_b200.synth as S
+    if "proj" in wl:
+        from oracle import ref_loader as R
+        post = torch.softmax(torch.nn.functional.linear(wl["raw"], wl["w"], wl["b"]), dim=-1)[:, 4:, :]
+        lens = torch.clamp(wl["raw_lens"] - 4, min=0)
+        feats, new_lens = R.ref_psd(post, lens, post, 0)
+        proj = wl["proj"](feats)
+        emb = torch.nn.functional.embedding(wl["ids"], wl["table"])
+        return R.ref_merge(proj, new_lens // wl["proj"].k, emb, wl["ids"], wl["mask"], None, S.SPEECH_ID, S.PAD_ID)
     from oracle import tasu_oracle as O
     return O.bridge_inference(wl["raw"], wl["raw_lens"], wl["w"], wl["b"], wl["pp"], wl["table"], wl["ids"],
                               wl["mask"], None, S.SPEECH_ID, S.PAD_ID, vectorised=False)
 
 
+def _slice_workload(wl, n):
+    return {k: (v[:n] if k in ("raw", "raw_lens", "ids", "mask") else v) for k, v in wl.items()}
+
+
 def run_cpu_baseline(sample_b, T, budget_s=12.0):
-    """Time the oracle port on the host cores for about ``budget_s`` seconds of CPU work (>= 3 passes)."""
+    """Time the reference's own functions (the oracle port only if the reference files are not staged) on the host cores
+    for about ``budget_s`` seconds of CPU work (>= 2 passes over ``sample_b`` utterances)."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = cpu_workload(sample_b, T, seed=4242)
-    small = {k: (v[:1] if k in ("raw", "raw_lens", "ids", "mask") else v) for k, v in wl.items()}
+    use_ref = reference_available()
+    wl = cpu_workload(sample_b, T, seed=4242, use_reference=use_ref)
     with torch.no_grad():
-        cpu_step(small)                                   # warm the thread pool / allocator
+        cpu_step(_slice_workload(wl, 1))                  # warm the thread pool / allocator
         t0 = time.perf_counter()
         passes = 0
-        while passes < 3 or time.perf_counter() - t0 < budget_s:
+        while passes < 2 or time.perf_counter() - t0 < budget_s:
             cpu_step(wl)
             passes += 1
         dt = time.perf_counter() - t0
-    return {"value": passes * sample_b * T / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{passes} passes over {sample_b} utterances x {T} frames ({dt:.1f} s of CPU work), fp32 torch-CPU port of "
-                      f"the reference algorithm (softmax(ctc_lo) -> per-frame psd loop -> LayerNorm/Linear/SiLU/Linear -> merge)"}, dt
+    kind = "reference" if use_ref else "port"
+    what = ("the reference's own psd / EncoderProjectorLinearSiLU / _merge_input_ids_with_audio_features (unmodified files staged by "
+            "oracle/vendor_ref.py) behind softmax(F.linear) for the un-vendored funasr ctc_lo" if use_ref else
+            "fp32 torch-CPU port of the reference algorithm (softmax(ctc_lo) -> per-frame psd loop -> LayerNorm/Linear/SiLU/Linear -> merge)")
+    return {"value": passes * sample_b * T / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{passes} passes over {sample_b} utterances x {T} frames ({dt:.1f} s of CPU work), {what}"}, dt
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port — the reference itself is a Python
-    tree that does not exist on the GPU box) timed on the host cores, same metric/config."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified files, staged under oracle/_ref by
+    oracle/vendor_ref.py; the oracle port only if they are missing) timed on the host cores — same metric, same
+    configuration: every step is one whole batch of --batch utterances."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     T = int(round(args.seconds / 0.06))
-    sample_b = min(args.cpu_sample, 4)
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = cpu_workload(sample_b, T, seed=4242)
+    use_ref = reference_available()
+    B = args.batch
+    wl = cpu_workload(B, T, seed=4242, use_reference=use_ref)
     with torch.no_grad():
-        for _ in range(max(args.warmup, 1)):
-            cpu_step({k: (v[:1] if k in ("raw", "raw_lens", "ids", "mask") else v) for k, v in wl.items()})
+        t0 = time.perf_counter()
+        cpu_step(_slice_workload(wl, 4))                  # probe: 4 utterances
+        probe = (time.perf_counter() - t0) / 4
+        # bounded run: if K + W whole batches would take more than ~12 minutes on this host, the step becomes a smaller
+        # sample of the same batch (said in the line)
+        while B > 4 and probe * B * (args.steps + args.warmup) > 720.0:
+            B //= 2
+        if B != args.batch:
+            wl = _slice_workload(wl, B)
+        for _ in range(args.warmup):
+            cpu_step(wl)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             cpu_step(wl)
         dt = time.perf_counter() - t0
-    value = args.steps * sample_b * T / dt
+    value = args.steps * B * T / dt
+    kind = "reference" if use_ref else "port"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] inference bridge, bounded sample: %d utterances x %d frames per step on host CPUs"
-                               % (sample_b, T), "batch_per_step": sample_b, "frames_per_utt": T, "V": 25055},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample_b} utterances x {T} frames per step, {args.steps} steps"},
+        "config": {"workload": "configs[1] inference bridge: %d utterances x %.0f s (T=%d frames, 512-d synthetic encoder output) -> "
+                               "ctc_lo -> softmax/argmax -> collapse -> linear-silu projector (25055->2048->1536) -> splice, on the "
+                               "host CPUs" % (B, args.seconds, T),
+                   "batch_per_gpu": B, "frames_per_utt": T, "V": 25055, "same_config_as_b200_arm": B == args.batch,
+                   "code": ("unmodified reference files (model/ps-slm.py psd + _merge, model/projector.py EncoderProjectorLinearSiLU) "
+                            "staged by oracle/vendor_ref.py" if use_ref else "oracle port (reference files not staged)")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{B} utterances x {T} frames per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)

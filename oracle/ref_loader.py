@@ -1,8 +1,9 @@
 """Load the UNMODIFIED reference (PigeonDan1/ps-slm) for oracle pinning.
 
-Test infrastructure only.  Works only where ``/root/reference`` exists (the
-build container); ``available()`` is False on the GPU box and every caller must
-skip.  Recipe: put ``Multitask/`` on sys.path, stub the two
+Test infrastructure only.  Uses ``/root/reference`` where it exists (the build
+container), else the byte-for-byte copies ``oracle/vendor_ref.py`` staged under
+the git-ignored ``oracle/_ref/`` (they travel to the GPU box with the working
+tree); ``available()`` is False when neither exists and every caller must skip.  Recipe: put ``Multitask/`` on sys.path, stub the two
 absent third-party modules that are imported at module scope but never used on
 the bridge path (``peft``: Multitask/model/ps-slm.py:16,
 Multitask/utils/config_utils.py:9-13; ``omegaconf``: utils/config_utils.py:15),
@@ -19,7 +20,9 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("TASU_REFERENCE_ROOT", "/root/reference/Multitask")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "Multitask")   # oracle/vendor_ref.py
+REF_ROOT = os.environ.get("TASU_REFERENCE_ROOT") or (
+    "/root/reference/Multitask" if os.path.isfile("/root/reference/Multitask/model/ps-slm.py") else _STAGED)
 
 _cache = {}
 

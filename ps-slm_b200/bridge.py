@@ -431,11 +431,11 @@ class TasuBridge:
     def _stage(self, name):
         return _Stage(self, name)
 
-    def _tail(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2, out_dtype):
-        """Pass 2 + projector on capacity-sized buffers with device-side row counts (no host sync inside):
-        gather kept rows → softmax-epilogue CTC GEMM over the kept frames → in-place tail pooling → GEMM-1 → GEMM-2.
-        Row r of the compact matrix is the first frame of packed candidate r, so single-frame candidates (the
-        majority) are final as the GEMM writes them; only multi-frame runs are averaged afterwards."""
+    def _pool_kept(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc):
+        """Pass 2 on capacity-sized buffers with device-side row counts (no host sync inside): gather kept rows →
+        softmax-epilogue CTC GEMM over the kept frames → in-place tail pooling.  Row r of the compact matrix is the first
+        frame of packed candidate r, so single-frame candidates (the majority) are final as the GEMM writes them; only
+        multi-frame runs are averaged afterwards.  → (pooled bf16 [cap_f, pad64(V)], LayerNorm mean, rstd [cap_o])."""
         dev = x2.device
         ldk = ops.pad_to(V)
         with self._stage("gather_kept_rows"):
@@ -447,8 +447,23 @@ class TasuBridge:
                              m_dev=plan.counts[2:3])
         with self._stage("pool_tail"):
             ops.pool_tail(pooled, V, cap_o, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
+        return pooled, mean, rstd
+
+    def _tail(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2, out_dtype):
+        """Pass 2 + projector (GEMM-1 with the LayerNorm folded in, GEMM-2) on capacity-sized buffers."""
+        pooled, mean, rstd = self._pool_kept(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc)
         return linear_silu_forward(pooled, cap_o, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                    stage=self._stage, m_dev=plan.counts[0:1], streamk=self.streamk_gemm1)
+
+    def _speculative_capacity(self, B, T):
+        """Row capacities for a tail enqueued BEFORE the host knows the batch's counts: 1.25 x the high-water marks of
+        earlier batches of this shape, or None for the first batch of a shape — that one call reads the header first and
+        sizes its buffers exactly (a worst-case B*T-row probability matrix would be 1.6 GB at 64 x 30 s and 51 GB at
+        1024 x 60 s)."""
+        hw_f, hw_o = self._capacity.get((B, T), (0, 0))
+        if not hw_f:
+            return None
+        return _cap(int(1.25 * hw_f)), _cap(int(1.25 * hw_o))
 
     def _header_slot(self):
         """Ring of pinned host header buffers (collapse + splice words), one per in-flight call."""
@@ -578,14 +593,13 @@ class TasuBridge:
             ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
         ev = torch.cuda.Event()
         ev.record()                                                     # header is complete when this event fires
-        audio_cap = None
-        if not self.materialize_logits:
+        audio_cap, cap_f, cap_o = None, 0, 0
+        caps = None if self.materialize_logits else self._speculative_capacity(B, T)
+        if caps is not None:
             # The whole tail is enqueued BEFORE the host looks at the header: buffers are sized by capacity
-            # (high-water mark of earlier calls, worst case on the first) and every kernel takes its live row
-            # count from device memory, so the GPU never idles waiting for the host.
-            hw_f, hw_o = self._capacity.get((B, T), (0, 0))            # high-water marks of earlier batches of this shape
-            cap_f = _cap(int(1.25 * hw_f)) if hw_f else _cap(B * T)    # first call: worst case (every frame kept)
-            cap_o = _cap(int(1.25 * hw_o)) if hw_o else _cap(B * T)
+            # (high-water mark of earlier calls) and every kernel takes its live row count from device memory, so the
+            # GPU never idles waiting for the host.
+            cap_f, cap_o = caps
             audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2,
                                    out_dtype)
         ev.synchronize()                                                # the single device→host hand-off
@@ -611,7 +625,8 @@ class TasuBridge:
             else:
                 audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
         else:
-            if n_frames > cap_f or n_out > cap_o:                       # capacity exceeded (rare): redo the tail, exact
+            if audio_cap is None or n_frames > cap_f or n_out > cap_o:
+                # first batch of this shape, or capacity exceeded (rare): the tail runs now, sized exactly
                 cap_f, cap_o = _cap(n_frames), _cap(n_out)
                 audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias,
                                        w2, b2, out_dtype)
@@ -651,14 +666,50 @@ class TasuBridge:
         plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
         ev = torch.cuda.Event()
         ev.record()
-        hw_f, hw_o = self._capacity.get((B, T), (0, 0))
-        cap_f = _cap(int(1.25 * hw_f)) if hw_f else _cap(B * T)
-        cap_o = _cap(int(1.25 * hw_o)) if hw_o else _cap(B * T)
         pend.tail_args = (x2, st, plan, B, T, Denc, V)
         pend.weights = (w_ctc, b_ctc) + tuple(proj_w) + (out_dtype,)
-        pend.audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, *proj_w, out_dtype)
-        pend.cap_f, pend.cap_o, pend.header, pend.event, pend.plan = cap_f, cap_o, header, ev, plan
+        caps = self._speculative_capacity(B, T)
+        pend.audio_cap, pend.cap_f, pend.cap_o = None, 0, 0
+        if caps is not None:
+            pend.cap_f, pend.cap_o = caps
+            pend.audio_cap = self._tail(x2, st, plan, B, T, Denc, V, caps[0], caps[1], w_ctc, b_ctc, *proj_w, out_dtype)
+        pend.header, pend.event, pend.plan = header, ev, plan
         return pend
+
+    @torch.no_grad()
+    def compress_pooled(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor):
+        """Steps 1b-2 only, for TRAINING on audio batches (ps-slm.py:450-454, :469-473): the fused head statistics,
+        exact decisions, collapse plan, kept-frame softmax GEMM and tail pooling — the no-grad part of the path, the
+        ``[B, T, 25055]`` posterior never exists — and the pooled posterior rows are handed to the differentiable
+        projector (``autograd.linear_silu_train_rows``).  Reads the plan header first, so every buffer has its exact size.
+        → (pooled bf16 ``[sum M_b, pad64(V)]``, LayerNorm mean, rstd ``[sum M_b]``, ``new_lens [B]`` int64, ``max_b M_b``)."""
+        B, T4, Denc = raw_encoder_out.shape
+        T = T4 - self.N_PREFIX
+        V = self.w_ctc.shape[0]
+        dev = raw_encoder_out.device
+        for _ in range(2):
+            builds_before = self._cache_builds()
+            header = self._header_slot()
+            if VERIFY_CACHES:
+                ops.fingerprint(self._weight_params(), out=header[L.CH_WORDS + L.SH_WORDS:])
+            w_ctc, b_ctc = self._ctc_weights()
+            x2 = self._encoder_rows_bf16(raw_encoder_out)
+            lens = torch.clamp(raw_encoder_out_lens.to(device=dev, dtype=torch.int64) - self.N_PREFIX, min=0)
+            st = self._head_stats(raw_encoder_out, x2, lens, w_ctc, b_ctc, B, T, Denc, V)
+            plan = ops.collapse_plan(st, lens, self.blank_id, self.blank_threshold, header=header[:L.CH_WORDS])
+            ev = torch.cuda.Event()
+            ev.record()
+            ev.synchronize()
+            hdr = header.clone()
+            if self._check_fingerprint(int(hdr[L.CH_WORDS + L.SH_WORDS]), builds_before):
+                break
+        n_out, max_len, n_frames = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN]), int(hdr[L.CH_KEPT_FRAMES])
+        if n_out == 0:
+            z = torch.zeros(0, dtype=torch.float32, device=dev)
+            return torch.zeros(0, ops.pad_to(V), dtype=torch.bfloat16, device=dev), z, z, plan.new_lens, 0
+        pooled, mean, rstd = self._pool_kept(x2, st, plan, B, T, Denc, V, _cap(n_frames), _cap(n_out), w_ctc, b_ctc)
+        self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "kept_frames": n_frames}
+        return pooled[:n_out], mean[:n_out], rstd[:n_out], plan.new_lens, max_len
 
     def compress_project(self, raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.Tensor):
         """Steps 1b-3 only: → (audio rows packed ``[sum M_b, H]``, ``new_lens [B]`` int64, ``max_b M_b``).
@@ -697,7 +748,8 @@ class PendingCompress:
             return br.compress_project(*self.inputs)                    # stale weight copies: redo with fresh ones
         n_out, max_len, n_frames = int(hdr[L.CH_N_OUT]), int(hdr[L.CH_MAX_LEN]), int(hdr[L.CH_KEPT_FRAMES])
         x2, st, plan, B, T, Denc, V = self.tail_args
-        if n_frames > self.cap_f or n_out > self.cap_o:                 # capacity exceeded (rare): redo the tail, exact
+        if self.audio_cap is None or n_frames > self.cap_f or n_out > self.cap_o:
+            # first batch of this shape, or capacity exceeded (rare): the tail runs now, sized exactly
             self.audio_cap = br._tail(x2, st, plan, B, T, Denc, V, _cap(n_frames), _cap(n_out), *self.weights)
         hw_f, hw_o = br._capacity.get((B, T), (0, 0))
         br._capacity[(B, T)] = (max(hw_f, n_frames), max(hw_o, n_out))

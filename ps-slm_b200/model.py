@@ -207,6 +207,27 @@ class slam_model_asr(nn.Module):
                                                                  attention_mask, labels)
             return emb, mask, out_labels, pos
         blank = self.encoder.blank_id
+        train_fused_ok = (self.ctc_posterior and not self.voca_trans and not self.gt_emb and self.do_psd
+                          and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
+                          and torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_projector.parameters())
+                          and not raw_encoder_out.requires_grad and table.dtype in (torch.float32, torch.bfloat16))
+        if train_fused_ok:
+            # training on audio (ps-slm.py:450-454, :469-473, :482, :525-528 — the "half_audio_finetuned" recipe): the
+            # no-grad head (fused ctc_lo statistics → exact decisions → collapse → kept-frame softmax GEMM → pooling)
+            # never materialises the [B, T, 25055] posterior; the pooled rows enter the differentiable projector
+            from .autograd import linear_silu_train_rows
+            br = self._fused_bridge()
+            pooled, mean, rstd, feat_len, max_len = br.compress_pooled(raw_encoder_out, raw_encoder_out_lens)
+            pending = _bridge.begin_splice_plan(input_ids, attention_mask, feat_len, self.tokenizer.default_speech_token)
+            if pooled.shape[0]:
+                audio = linear_silu_train_rows(self.encoder_projector, pooled, mean, rstd, pooled.shape[0], table.dtype)
+            else:
+                audio = torch.zeros(0, table.shape[1], dtype=table.dtype, device=table.device)
+            emb, mask, out_labels, pos, _ = _bridge.merge_packed_audio_rows(
+                audio, feat_len, max_len, table, 1, input_ids, attention_mask, labels,
+                self.tokenizer.default_speech_token, self.tokenizer.pad_token_id, self.tokenizer.default_ignore_token,
+                pending=pending)
+            return emb, mask, out_labels, pos
         rows_ok = (self._text_only() and self.token_row_path
                    and type(self.encoder_projector).__name__ == "EncoderProjectorLinearSiLU"
                    and table.dtype in (torch.float32, torch.bfloat16))

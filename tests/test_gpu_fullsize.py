@@ -286,3 +286,34 @@ def test_cached_weight_copies_follow_data_copy(dev):
     y1 = proj(x)
     y2 = copy.deepcopy(proj)(x)
     assert not torch.equal(y0, y1) and torch.equal(y1, y2)
+
+
+def test_audio_training_step_never_materialises_the_posterior(dev):
+    """Training on an audio batch at the benchmark size (64 x 30 s): the no-grad head (TasuBridge.compress_pooled) plus the
+    differentiable projector must stay far below the 3.2 GB the reference's [B, T, 25055] fp32 posterior alone takes
+    (ps-slm.py:450-451), and the projected rows must equal the inference path's."""
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.autograd import linear_silu_train_rows
+    B, T = 64, 500
+    w, b, proj, table, br = _bridge(dev)
+    raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=123, ragged=True)
+    raw, raw_lens = raw.to(dev), raw_lens.to(dev)
+    ref_rows, ref_lens, ref_max = br.compress_project(raw, raw_lens)
+    ref_rows = ref_rows.float().clone()
+    proj.train()
+    for p in proj.parameters():
+        p.requires_grad_(True)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    pooled, mean, rstd, lens, max_len = br.compress_pooled(raw, raw_lens)
+    assert torch.equal(lens, ref_lens) and max_len == ref_max and pooled.shape[0] == int(ref_lens.sum())
+    y = linear_silu_train_rows(proj, pooled, mean, rstd, pooled.shape[0], torch.float32)
+    y.backward(torch.randn(y.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1)))
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    posterior_bytes = B * (T + 4) * S.V_CTC * 4
+    assert peak < 0.6 * posterior_bytes, (peak, posterior_bytes)
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in proj.parameters())
+    assert ((y.detach() - ref_rows).norm() / ref_rows.norm()).item() < 1e-2

@@ -45,8 +45,6 @@ SHAPES = [
                                            (3, torch.bfloat16), (4, torch.bfloat16)])
 def test_gemm_tcgen05(dev, M, N, K, epi, out_dtype):
     import ps_slm_b200.ops as ops
-    if (M, N, K) in [(1000, 2048, 25055), (900, 25055, 512)] and epi in (0, 3):
-        pytest.skip("large shapes: a subset of epilogues is enough")
     torch.manual_seed(M * 7 + N * 3 + K + epi)
     lda, ldb = ops.pad_to(K, 8) + 8, ops.pad_to(K, 8)
     ldc = ops.pad_to(N, 8)
