@@ -142,6 +142,16 @@ int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames, cons
                        int32_t* counts_dev /*[4] {N_out, max_len, kept_frames, 0} in device memory, or NULL*/,
                        void* stream);
 
+/* tasu_collapse_plan + tasu_collapse_scan in ONE launch: the last CTA of the plan kernel to finish runs the scans and
+ * writes the header.  `ticket` [1] int32 must be zero before the first use; the kernel hands it back zeroed, so one word
+ * serves every later (stream-ordered) launch. */
+int tasu_collapse_plan_scan(const int32_t* argmax, const float* x_blank, const float* row_max,
+                            const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
+                            const int64_t* lens, int B, int T, int blank_id, float threshold,
+                            int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
+                            int32_t* kept_frames, int32_t* seg_frame_off, int32_t* row_off, int32_t* frame_off,
+                            int64_t* header, int32_t* counts_dev, int32_t* ticket, void* stream);
+
 /* Gather the encoder rows of the kept frames into a compact [F_kept, K] bf16 matrix together with their
  * softmax scalars, so that a second, ~3x smaller CTC-head GEMM (TASU_EPI_SOFTMAX) recomputes probabilities
  * only where PSD keeps them.  Layout: row r < N_out = FIRST frame of packed candidate r (so the GEMM writes

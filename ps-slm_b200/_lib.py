@@ -31,6 +31,7 @@ SIGNATURES = {
     "tasu_get_option": (_I, [_I]),
     "tasu_frame_stats": (_I, [_P, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_collapse_plan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_collapse_plan_scan": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_row_norm_max": (_I, [_P, _I, _I, _I, _L, _P, _P]),
     "tasu_flag_ambiguous_frames": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _P, _F, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "tasu_cast_rows_sumsq": (_I, [_P, _L, _I, _L, _P, _L, _P, _P]),

@@ -107,6 +107,42 @@ frame_stats_kernel(const T* __restrict__ x, int B, int T_, int V, int64_t bstrid
 // a blank, or differs from its left neighbour (ps-slm.py:270-271, :275-279); the opening thread
 // walks its run sequentially (same summation order as the reference's .mean(), :286), compares
 // the fp32 score with the threshold (:295) and a block scan compacts the kept candidates.
+// exclusive scans over the utterances (new_lens → row_off, kept_frames → frame_off) + the plan header; one CTA
+__device__ __forceinline__ void collapse_scan_body(const int64_t* __restrict__ new_lens, const int32_t* __restrict__ kept_frames,
+                                                   const uint32_t* __restrict__ gmax, int B, int32_t* __restrict__ row_off,
+                                                   int32_t* __restrict__ frame_off, int64_t* __restrict__ header,
+                                                   int32_t* __restrict__ counts_dev, int* scratch) {
+    int carry = 0, mx = 0, frames = 0;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < B ? (int)__ldcg(new_lens + b) : 0;       // written by other CTAs in the fused variant: bypass L1
+        int total;
+        const int excl = block_excl_scan_i(v, scratch, &total);
+        if (b < B) row_off[b] = carry + excl;
+        carry += total;
+        mx = max(mx, v);
+        if (kept_frames != nullptr) {
+            const int kf = b < B ? __ldcg(kept_frames + b) : 0;
+            int ftotal;
+            const int fexcl = block_excl_scan_i(kf, scratch, &ftotal);
+            if (frame_off != nullptr && b < B) frame_off[b] = frames + fexcl;
+            frames += ftotal;
+        }
+    }
+    mx = block_max_i(mx, scratch);
+    if (frame_off != nullptr && threadIdx.x == 0) frame_off[B] = frames;
+    if (threadIdx.x == 0) {
+        row_off[B] = carry;
+        header[TASU_CH_N_OUT] = carry;
+        header[TASU_CH_MAX_LEN] = mx;
+        header[TASU_CH_IS_LOGPROB] = (gmax != nullptr && ordered_to_float(*gmax) <= 0.f) ? 1 : 0;
+        header[TASU_CH_KEPT_FRAMES] = frames;
+        if (counts_dev != nullptr) { counts_dev[0] = carry; counts_dev[1] = mx; counts_dev[2] = frames; counts_dev[3] = 0; }
+    }
+}
+
+struct CollapseScanArgs { int32_t* ticket; int32_t* row_off; int32_t* frame_off; int64_t* header; int32_t* counts_dev; };
+
 template <bool kLogits>
 __global__ void __launch_bounds__(256)
 collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restrict__ xb_all,
@@ -114,8 +150,9 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
                      const uint32_t* __restrict__ gmax, const int64_t* __restrict__ lens, int T_,
                      int blank, float thr, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len,
                      float* __restrict__ seg_score, int64_t* __restrict__ new_lens, int32_t* __restrict__ kept_frames,
-                     int32_t* __restrict__ seg_foff) {
+                     int32_t* __restrict__ seg_foff, const CollapseScanArgs sc) {
     __shared__ int scratch[33];
+    __shared__ int s_last;
     const int b = blockIdx.x;
     int64_t L64 = lens[b];
     const int L = (int)(L64 < 0 ? 0 : (L64 > T_ ? T_ : L64));
@@ -160,6 +197,20 @@ collapse_plan_kernel(const int32_t* __restrict__ ids_all, const float* __restric
     }
     if (kept_frames != nullptr && threadIdx.x == 0) kept_frames[b] = frames;
     if (threadIdx.x == 0) new_lens[b] = carry;
+    if (sc.ticket == nullptr) return;
+    // fused scan (tasu_collapse_plan_scan): the last CTA to finish sees every utterance's counts and writes the offsets
+    // and the header; the ticket returns to zero, so the same word serves the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int t = atomicAdd(sc.ticket, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) { *sc.ticket = 0; __threadfence(); }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    collapse_scan_body(new_lens, kept_frames, kLogits ? nullptr : gmax, (int)gridDim.x, sc.row_off, sc.frame_off, sc.header,
+                       sc.counts_dev, scratch);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -167,33 +218,7 @@ collapse_scan_kernel(const int64_t* __restrict__ new_lens, const int32_t* __rest
                      const uint32_t* __restrict__ gmax, int B, int32_t* __restrict__ row_off,
                      int32_t* __restrict__ frame_off, int64_t* __restrict__ header, int32_t* __restrict__ counts_dev) {
     __shared__ int scratch[33];
-    int carry = 0, mx = 0, frames = 0;
-    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
-        const int b = b0 + threadIdx.x;
-        const int v = b < B ? (int)new_lens[b] : 0;
-        int total;
-        const int excl = block_excl_scan_i(v, scratch, &total);
-        if (b < B) row_off[b] = carry + excl;
-        carry += total;
-        mx = max(mx, v);
-        if (kept_frames != nullptr) {
-            const int kf = b < B ? kept_frames[b] : 0;
-            int ftotal;
-            const int fexcl = block_excl_scan_i(kf, scratch, &ftotal);
-            if (frame_off != nullptr && b < B) frame_off[b] = frames + fexcl;
-            frames += ftotal;
-        }
-    }
-    mx = block_max_i(mx, scratch);
-    if (frame_off != nullptr && threadIdx.x == 0) frame_off[B] = frames;
-    if (threadIdx.x == 0) {
-        row_off[B] = carry;
-        header[TASU_CH_N_OUT] = carry;
-        header[TASU_CH_MAX_LEN] = mx;
-        header[TASU_CH_IS_LOGPROB] = (gmax != nullptr && ordered_to_float(*gmax) <= 0.f) ? 1 : 0;
-        header[TASU_CH_KEPT_FRAMES] = frames;
-        if (counts_dev != nullptr) { counts_dev[0] = carry; counts_dev[1] = mx; counts_dev[2] = frames; counts_dev[3] = 0; }
-    }
+    collapse_scan_body(new_lens, kept_frames, gmax, B, row_off, frame_off, header, counts_dev, scratch);
 }
 
 }  // namespace tasu
@@ -232,6 +257,21 @@ extern "C" int tasu_frame_stats(const void* x, int dtype, int input_kind, int B,
     return TASU_OK;
 }
 
+static int launch_collapse_plan(const int32_t* argmax, const float* x_blank, const float* row_max, const float* row_sumexp,
+                                const uint32_t* global_max_enc, int input_kind, const int64_t* lens, int B, int T, int blank_id,
+                                float threshold, int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
+                                int32_t* kept_frames, int32_t* seg_frame_off, const CollapseScanArgs& sc, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (input_kind == TASU_INPUT_LOGITS)
+        collapse_plan_kernel<true><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T, blank_id,
+                                                      threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off, sc);
+    else
+        collapse_plan_kernel<false><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T, blank_id,
+                                                       threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off, sc);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
 extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, const float* row_max,
                                   const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
                                   const int64_t* lens, int B, int T, int blank_id, float threshold,
@@ -243,15 +283,28 @@ extern "C" int tasu_collapse_plan(const int32_t* argmax, const float* x_blank, c
     TASU_CHECK_ARG(lens && seg_start && seg_len && new_lens, "null pointer");
     TASU_CHECK_ARG(T == 0 || (argmax && x_blank), "null stats");
     TASU_CHECK_ARG(input_kind != TASU_INPUT_LOGITS || (row_max && row_sumexp), "logits need row_max/row_sumexp");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (input_kind == TASU_INPUT_LOGITS)
-        collapse_plan_kernel<true><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                      blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off);
-    else
-        collapse_plan_kernel<false><<<B, 256, 0, st>>>(argmax, x_blank, row_max, row_sumexp, global_max_enc, lens, T,
-                                                       blank_id, threshold, seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off);
-    TASU_CHECK_LAUNCH();
-    return TASU_OK;
+    return launch_collapse_plan(argmax, x_blank, row_max, row_sumexp, global_max_enc, input_kind, lens, B, T, blank_id, threshold,
+                                seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off, CollapseScanArgs{}, stream);
+}
+
+extern "C" int tasu_collapse_plan_scan(const int32_t* argmax, const float* x_blank, const float* row_max,
+                                       const float* row_sumexp, const uint32_t* global_max_enc, int input_kind,
+                                       const int64_t* lens, int B, int T, int blank_id, float threshold,
+                                       int32_t* seg_start, int32_t* seg_len, float* seg_score, int64_t* new_lens,
+                                       int32_t* kept_frames, int32_t* seg_frame_off, int32_t* row_off, int32_t* frame_off,
+                                       int64_t* header, int32_t* counts_dev, int32_t* ticket, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && T >= 0, "B,T >= 0");
+    TASU_CHECK_ARG(input_kind == TASU_INPUT_PROBS || input_kind == TASU_INPUT_LOGITS, "input_kind");
+    TASU_CHECK_ARG(row_off && header && ticket, "null scan outputs / ticket");
+    if (B == 0)
+        return tasu_collapse_scan(new_lens, kept_frames, input_kind == TASU_INPUT_PROBS ? global_max_enc : nullptr, 0, row_off,
+                                  frame_off, header, counts_dev, stream);
+    TASU_CHECK_ARG(lens && seg_start && seg_len && new_lens, "null pointer");
+    TASU_CHECK_ARG(T == 0 || (argmax && x_blank), "null stats");
+    TASU_CHECK_ARG(input_kind != TASU_INPUT_LOGITS || (row_max && row_sumexp), "logits need row_max/row_sumexp");
+    CollapseScanArgs sc{ticket, row_off, frame_off, header, counts_dev};
+    return launch_collapse_plan(argmax, x_blank, row_max, row_sumexp, global_max_enc, input_kind, lens, B, T, blank_id, threshold,
+                                seg_start, seg_len, seg_score, new_lens, kept_frames, seg_frame_off, sc, stream);
 }
 
 extern "C" int tasu_collapse_scan(const int64_t* new_lens, const int32_t* kept_frames,

@@ -251,10 +251,24 @@ class CollapsePlan:
                  "header", "counts", "B", "T")
 
 
+_TICKETS = {}
+
+
+def _ticket(device) -> torch.Tensor:
+    """Per (device, stream) int32[1] ticket of the fused planner kernels: zero-initialised once, handed back zeroed by
+    every launch (stream-ordered reuse)."""
+    key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        _TICKETS[key] = t
+    return t
+
+
 def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: float,
                   header: Optional[torch.Tensor] = None, want_scores: bool = False) -> CollapsePlan:
-    """tasu_collapse_plan + tasu_collapse_scan. ``header`` (int64[>=4]) may be caller-provided so
-    several plans share one device→host read."""
+    """tasu_collapse_plan_scan (plan + scans + header in one launch). ``header`` (int64[>=4]) may be caller-provided
+    so several plans share one device→host read."""
     B, T = st.B, st.T
     dev = st.argmax.device
     lens = lens.to(device=dev, dtype=torch.int64).contiguous()
@@ -271,19 +285,16 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     # ``header`` may be pinned host memory: under UVA its pointer is valid on the device
     p.header = header if header is not None else torch.empty(L.CH_WORDS, dtype=torch.int64, device=dev)
-    lib = L.lib()
     d_max = st.dec_max if st.dec_max is not None else st.row_max
     d_sum = st.dec_sum if st.dec_sum is not None else st.row_sumexp
-    L.check(lib.tasu_collapse_plan(st.argmax.data_ptr(), st.x_blank.data_ptr(), d_max.data_ptr(),
-                                   _ptr(d_sum), st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T,
-                                   blank_id, float(threshold), p.seg_start.data_ptr(), p.seg_len.data_ptr(),
-                                   _ptr(p.seg_score), p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
-                                   p.seg_foff.data_ptr(), _stream()), "tasu_collapse_plan")
-    L.check(lib.tasu_collapse_scan(p.new_lens.data_ptr(), p.kept_frames.data_ptr(),
-                                   st.gmax.data_ptr() if st.kind == L.INPUT_PROBS else None,
-                                   B, p.row_off.data_ptr(), p.frame_off.data_ptr(), p.header.data_ptr(),
-                                   p.counts.data_ptr(), _stream()), "tasu_collapse_scan")
-    _count(2)
+    L.check(L.lib().tasu_collapse_plan_scan(st.argmax.data_ptr(), st.x_blank.data_ptr(), d_max.data_ptr(), _ptr(d_sum),
+                                            st.gmax.data_ptr(), st.kind, lens.data_ptr(), B, T, blank_id, float(threshold),
+                                            p.seg_start.data_ptr(), p.seg_len.data_ptr(), _ptr(p.seg_score),
+                                            p.new_lens.data_ptr(), p.kept_frames.data_ptr(), p.seg_foff.data_ptr(),
+                                            p.row_off.data_ptr(), p.frame_off.data_ptr(), p.header.data_ptr(),
+                                            p.counts.data_ptr(), _ticket(dev)[0:1].data_ptr(), _stream()),
+            "tasu_collapse_plan_scan")
+    _count(1)
     return p
 
 
