@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--sustained-seconds", type=float, default=3.0,
                     help="length of the second, sustained timed loop (0 = skip); the headline loop is a burst of K steps")
     ap.add_argument("--no-comm", action="store_true", help="skip the packed-path / training-step sections")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"],
+                    help="numerics of the HEADLINE loop: bf16 operands / fp32 accumulation (default; 1e-2 of the fp32 reference) or "
+                         "fp32x3 = reference numerics (three-term bf16 splits on the tensor cores, 1e-5 of the fp32 reference)")
+    ap.add_argument("--no-fp32-leg", action="store_true", help="skip the secondary fp32-accurate measurement")
     ap.add_argument("--train-batch", type=int, default=256, help="utterances per GPU of the text-only training step section")
     return ap.parse_args()
 
@@ -423,6 +427,7 @@ def b200_arm(args):
     bridge = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
     bridge.materialize_logits = args.materialize_logits
     bridge.exact_decisions = args.exact_decisions
+    bridge.precision = args.precision
     import ps_slm_b200._lib as L
     if args.streamk:
         bridge.streamk_gemm1 = True
@@ -526,6 +531,27 @@ def b200_arm(args):
         sustained = {"steps": n_sus, "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus,
                      "value": B * T * world * n_sus / (sus_ms / 1e3), "sm_mhz": sus_clk["sm_mhz"], "reasons": sus_clk["reasons"]}
 
+    # ---- (4b) secondary: the same step at REFERENCE numerics (fp32; conf/ds_config.json:12-14) — precision "fp32x3"
+    fp32_leg = None
+    if not args.no_fp32_leg and args.precision == "bf16" and not args.materialize_logits:
+        bridge.precision = "fp32x3"
+        for i in range(2):
+            step_dev(i)
+        n_fp = max(3, args.steps // 4)
+        barrier()
+        e0.record()
+        for i in range(n_fp):
+            step_dev(i)
+        e1.record()
+        barrier()
+        fp_ms = max_over_ranks(e0.elapsed_time(e1))
+        bridge.precision = "bf16"
+        fp32_leg = {"precision": "fp32x3: kept-frame logits and both projector contractions as three-term bf16 splits on the tensor "
+                                 "cores, fp32 softmax / pooling / LayerNorm; embeddings within 1e-5 of the fp32 reference "
+                                 "(tests/test_gpu_fullsize.py::test_bridge_fp32x3_matches_fp32_reference_to_1e5)",
+                    "steps": n_fp, "ms_per_step": fp_ms / n_fp, "value": B * T * world * n_fp / (fp_ms / 1e3), "unit": UNIT}
+        torch.cuda.empty_cache()
+
     # PCIe context for the e2e number: one pinned H2D / D2H of the step's buffers, alone on the bus
     pcie = {}
     big = host[0][0]
@@ -615,7 +641,7 @@ def b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "bf16" if args.precision == "bf16" else "f32 (bf16x3 on tensor cores)", "data": "synthetic",
         "config": {"workload": "configs[1] inference bridge: %d utterances/GPU x %.0f s (T=%d frames, 512-d synthetic encoder "
                                "output) -> ctc_lo -> softmax/argmax -> collapse -> linear-silu projector (25055->2048->1536) "
                                "-> splice with Qwen2.5-1.5B-shaped embed table" % (B, args.seconds, T),
@@ -640,6 +666,7 @@ def b200_arm(args):
         "roofline": roof,
         "whole_step": whole_step,
         "sustained": sustained,
+        "fp32_leg": fp32_leg,
         "kernels": kernels,
     }
     if comm is not None:

@@ -167,6 +167,13 @@ int tasu_gather_kept_rows(const void* x_bf16, int64_t ldx, int B, int T, int n_p
                           int64_t max_out /*packed rows*/, void* xg_bf16, int64_t ldg, float* g_max, float* g_inv_sum, int32_t* pk_len,
                           int32_t* tail_src, int32_t* multi_rows /*[N_out] or NULL*/, int32_t* multi_count /*[1]*/,
                           float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+/* Natural-order index of the kept frames (fp32-accurate path: the kept frames' fp32 encoder rows are gathered, their
+ * logits recomputed with the fp32-accurate GEMM and pooled by tasu_segment_meanpool with seg_src): compact row
+ * frame_off[b] + seg_frame_off + f holds frame f of the candidate; frame_row [max_rows] = raw encoder row of every
+ * compact row, seg_src [max_out] = first compact row of every packed candidate. */
+int tasu_kept_frame_index(const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
+                          const int32_t* row_off, const int32_t* frame_off, int B, int T, int n_prefix, int64_t max_rows,
+                          int64_t max_out, int32_t* frame_row, int32_t* seg_src, void* stream);
 /* In-place mean over the frames of every multi-frame candidate of the compact probability matrix
  * (ps-slm.py:286): probs[r] = (probs[r] + sum of its tail rows) / n, plus LayerNorm statistics.  max_rows = rows the
  * compact matrix holds: a candidate whose frames do not all lie below it is skipped (no access beyond the buffer). */
@@ -179,9 +186,9 @@ int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, int64_t m
  * :303-314).  feats is a [B, T, D] view (same tensor as the posterior on the default path).
  *   softmax_max/softmax_sumexp: NULL → pool feats as given; else feats are logits and
  *               exp(x - max[b,t]) / sumexp[b,t] is pooled (fused softmax).
- *   seg_src: NULL → candidate (b,j) starts at feats[b, seg_start, :]; else feats is the compact
- *               [F_kept, D] matrix of tasu_gather_kept_rows and packed row r starts at row seg_src[r]
- *               (layout 0 only).
+ *   seg_src: NULL → candidate (b,j) starts at feats[b, seg_start, :]; else feats is a compact [F_kept, D] matrix
+ *               in natural order (tasu_kept_frame_index), packed row r starts at row seg_src[r] and the softmax
+ *               statistics are indexed by compact row as well (layout 0 only).
  *   layout 0 (packed):  out row r in [0, N_out) at out + r*out_row_stride      (N_out = row_off[B])
  *   layout 1 (padded):  out row (b, j<max_len) at out + (b*max_len + j)*out_row_stride, rows
  *               j >= M_b are zero-filled (ps-slm.py:308-314)
@@ -454,6 +461,12 @@ int tasu_splice_plan(const int64_t* input_ids, const void* attention_mask, int m
 int tasu_splice_header(const int32_t* rowstat, const int64_t* num_audio, int n_audio, int64_t div_k,
                        int B, int S, int64_t* header /*[TASU_SH_WORDS]*/, int32_t* slot_base /*[B]*/,
                        int32_t* audio_off /*[n_audio+1]*/, void* stream);
+/* tasu_splice_plan + tasu_splice_header in ONE launch (the last CTA of the plan kernel to finish writes the header);
+ * `ticket` [1] int32: zero before the first use, handed back zeroed. */
+int tasu_splice_plan_header(const int64_t* input_ids, const void* attention_mask, int mask_dtype, int B, int S,
+                            int64_t speech_id, const int64_t* num_audio, int n_audio, int64_t div_k,
+                            int32_t* rowstat, int32_t* new_pos, int32_t* text_prefix, int32_t* slot_ord,
+                            int64_t* header, int32_t* slot_base, int32_t* audio_off, int32_t* ticket, void* stream);
 int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
                         const int64_t* labels, int B, int S, int spliced_len, int H, int64_t speech_id,
                         const void* text_src, int text_mode, int64_t text_row_stride,

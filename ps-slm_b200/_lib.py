@@ -40,6 +40,7 @@ SIGNATURES = {
     "tasu_collapse_scan": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "tasu_gather_kept_rows": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _F, _P]),
+    "tasu_kept_frame_index": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P]),
     "tasu_pool_tail": (_I, [_P, _L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P]),
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "tasu_splice_rowstat": (_I, [_P, _P, _I, _I, _I, _L, _P, _P]),
     "tasu_splice_plan": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "tasu_splice_header": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),
+    "tasu_splice_plan_header": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_splice_scatter": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _L, _L, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_flat_scale_cast": (_I, [_P, _I, _P, _I, _L, _F, _P]),

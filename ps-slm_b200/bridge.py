@@ -423,6 +423,12 @@ class TasuBridge:
         self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
         self._ctc_exact_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
+        # "bf16" (default): bf16 operands, fp32 accumulation — posteriors / embeddings within 1e-2 of the fp32 reference.
+        # "fp32x3": reference numerics (fp32, conf/ds_config.json:12-14): the kept frames' logits and both projector
+        # contractions run as three-term bf16 splits on the tensor cores, softmax / pooling / LayerNorm in fp32 —
+        # embeddings within 1e-5 of the fp32 reference, ~6 x the tensor work on the kept frames (two-phase: header first)
+        self.precision = "bf16"
+        self._ctc_split_cache = ProjectorCache()
         # EXPERIMENTAL (not yet validated on a GPU): projector GEMM-1 with the stream-K tail
         self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK") == "1"
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
@@ -454,6 +460,33 @@ class TasuBridge:
         pooled, mean, rstd = self._pool_kept(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc)
         return linear_silu_forward(pooled, cap_o, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                    stage=self._stage, m_dev=plan.counts[0:1], streamk=self.streamk_gemm1)
+
+    def _tail_fp32(self, raw_encoder_out, plan, B, T, Denc, V, n_frames, n_out, max_len, b_ctc):
+        """fp32-accurate pass 2 + projector (precision = "fp32x3"), sized exactly: gather the kept frames' fp32 encoder
+        rows in natural order → logits with the three-term bf16 split GEMM (~1e-6 of fp32) → fp32 row statistics →
+        softmax fused into the segmented mean-pool (fp32 rows + LayerNorm statistics) → fp32-accurate projector."""
+        dev = raw_encoder_out.device
+        H = self.embed_table.shape[1]
+        if n_out == 0:
+            return torch.zeros(0, H, dtype=torch.float32, device=dev)
+        rows = raw_encoder_out.reshape(B * (T + self.N_PREFIX), Denc)
+        rows = rows if rows.dtype == torch.float32 else rows.float()
+        with self._stage("fp32_gather_kept"):
+            frame_row, seg_src = ops.kept_frame_index(plan, self.N_PREFIX, n_frames, n_out)
+            xg = ops.gather_rows(rows, frame_row)
+        with self._stage("fp32_ctc_logits"):
+            w_split, k_split = self._ctc_split_cache.get(
+                [self.w_ctc], lambda: ops.split_bf16x3(self.w_ctc.detach().float(), 1)[:2], verify=True)
+            xs, kx, _, _, _ = ops.split_bf16x3(xg, 0)
+            ldv = ops.pad_to(V, 4)
+            logits = torch.empty(n_frames, ldv, dtype=torch.float32, device=dev)
+            ops.gemm_fp32x3(xs, w_split, n_frames, V, kx, logits, L.EPI_BIAS, b_ctc)
+        with self._stage("fp32_softmax_meanpool"):
+            st2 = ops.frame_stats(logits.view(1, n_frames, ldv)[:, :, :V], L.INPUT_LOGITS, self.blank_id)
+            pooled = torch.empty(n_out, ldv, dtype=torch.float32, device=dev)
+            ops.segment_meanpool(logits, plan, 0, max_len, n_out, pooled, ldv, softmax=st2, seg_src=seg_src, feat_dim=V)
+        with self._stage("fp32_projector"):
+            return self.projector.forward_rows_fp32x3(pooled[:, :V])
 
     def _speculative_capacity(self, B, T):
         """Row capacities for a tail enqueued BEFORE the host knows the batch's counts: 1.25 x the high-water marks of
@@ -594,7 +627,8 @@ class TasuBridge:
         ev = torch.cuda.Event()
         ev.record()                                                     # header is complete when this event fires
         audio_cap, cap_f, cap_o = None, 0, 0
-        caps = None if self.materialize_logits else self._speculative_capacity(B, T)
+        fp32 = self.precision == "fp32x3" and not self.materialize_logits
+        caps = None if (self.materialize_logits or fp32) else self._speculative_capacity(B, T)
         if caps is not None:
             # The whole tail is enqueued BEFORE the host looks at the header: buffers are sized by capacity
             # (high-water mark of earlier calls) and every kernel takes its live row count from device memory, so the
@@ -624,6 +658,8 @@ class TasuBridge:
                                             stage=self._stage)
             else:
                 audio = torch.empty(0, self.embed_table.shape[1], dtype=out_dtype, device=dev)
+        elif fp32:
+            audio = self._tail_fp32(raw_encoder_out, plan, B, T, Denc, V, n_frames, n_out, max_len, b_ctc).to(out_dtype)
         else:
             if audio_cap is None or n_frames > cap_f or n_out > cap_o:
                 # first batch of this shape, or capacity exceeded (rare): the tail runs now, sized exactly

@@ -1,5 +1,7 @@
-// EXPERIMENTAL (not yet validated on a GPU; selected only by TASU_OPT_GEMM_STREAMK): the deep-K tcgen05 GEMM of
-// gemm_sm100.cu with a stream-K tail.
+// The deep-K tcgen05 GEMM of gemm_sm100.cu with a stream-K tail (tasu_gemm_bf16_tn_streamk), for one CTA per tile and —
+// kPair, the default for M > 128 — for CTA pairs (tcgen05.mma.cta_group::2, one 256x256 tile per cluster of two CTAs:
+// every "CTA" of the description below is then a cluster, and each of its two CTAs keeps, contributes and finishes its
+// own 128 accumulator rows through its own slot and flag).
 //
 // Why: the projector GEMM-1 (projector.py:141, M = compressed rows of the batch, N = 2048, K = 25055) has
 // ceil(M/128) x 8 output tiles — 528 for the 8341 rows of the headline batch = 3.57 waves of 148 CTAs.  With one CTA
@@ -96,13 +98,16 @@ __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
 
 // Same pipeline as gemm_bf16_tn_kernel<kOutBf16, kEpi, 4, 1> (TMA producer warp, single-thread MMA issuer, two TMEM
 // accumulators, 4 epilogue warps with swizzled staging + TMA stores); work items are (tile, K-block range) pieces.
-template <bool kOutBf16, int kEpi>
+template <bool kOutBf16, int kEpi, bool kPair>
 __global__ void __launch_bounds__(256, 1)
 gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p, float* __restrict__ ws_slots,
                     uint32_t* __restrict__ ws_flags) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
+    constexpr int kStages = kPair ? kPairStages : tasu::gemm::kStages;             // shadows the one-CTA constant
+    constexpr int kStageBytes = kPair ? kPairStageBytes : tasu::gemm::kStageBytes;
+    constexpr int kTileM = kPair ? 2 * BM : BM;
     uint8_t* staging = smem + kStages * kStageBytes;
     float* s_aux = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes + kAuxBytes);
@@ -114,10 +119,14 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M_live = p.m_dev != nullptr ? min(max(__ldg(p.m_dev), 0), p.M) : p.M;
-    const int m_tiles = (M_live + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (M_live + kTileM - 1) / kTileM, n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (p.K + BK - 1) / BK;
-    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    // scheduling unit: a CTA, or (pair mode) a cluster of two CTAs that share every piece
+    const int grid = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x, cta = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int my_slot = (int)blockIdx.x;                                   // partial-accumulator slot / flag of THIS CTA
+    auto slot_of = [&](int unit) { return kPair ? 2 * unit + (int)rank : unit; };   // same-rank CTA of another unit
 
     // work items of this CTA: its tiles of the full waves, then its stream-K pieces (every role walks the same list)
     int dp_tiles, rem, sk_ctas;
@@ -135,16 +144,23 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_c); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * (kPair ? 2 : 1)); }
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_base_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -154,25 +170,34 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0; uint32_t phase = 0;
             for (int i = 0; i < n_items; ++i) {
                 const SkPiece it = item(i);
-                const int m0 = (it.tile / n_tiles) * BM, n0 = (it.tile % n_tiles) * BN;
+                const int m0 = (it.tile / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0), n0 = (it.tile % n_tiles) * BN;
                 for (int kb = it.kb0; kb < it.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kStageBytes;
-                    mbar_expect_tx(&full_bar[stage], kStageBytes);
-                    tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
-                    tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    if (kPair) {
+                        // both CTAs' halves of the stage complete on the rank-0 barrier the MMA thread waits on
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        tma_load_2d_pair(&tmap_a, fb, sa, kb * BK, m0);
+                        tma_load_2d_pair(&tmap_b, fb, sa + kABytes, kb * BK, n0 + (int)rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], kStageBytes);
+                        tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                        tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && (!kPair || rank == 0)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int i = 0; i < n_items; ++i) {
                 const SkPiece it = item(i);
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = it.kb0; kb < it.kb1; ++kb) {
@@ -181,11 +206,19 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                  (kb > it.kb0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == it.kb1 - 1) umma_commit(&tmem_full[acc]);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (kPair) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDescPair,
+                                                  (kb > it.kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                       (kb > it.kb0 || k > 0) ? 1u : 0u);
+                    }
+                    if (kPair) {
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (kb == it.kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == it.kb1 - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -206,14 +239,19 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int sbuf = 0;
         for (int i = 0; i < n_items; ++i) {
             const SkPiece it = item(i);
-            const int m0 = (it.tile / n_tiles) * BM, n0 = (it.tile % n_tiles) * BN;
+            const int m0 = (it.tile / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0), n0 = (it.tile % n_tiles) * BN;
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+            auto release_acc = [&]() {
+                tc_fence_before();
+                if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            };
 
             if (it.kind == SK_CONTRIB) {
                 // partial accumulators → this CTA's slot, [column][row] so that a warp writes 128 contiguous bytes
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                float* slot = ws_slots + (size_t)cta * kSkSlotFloats + et;
+                float* slot = ws_slots + (size_t)my_slot * kSkSlotFloats + et;
                 uint32_t va[32], vb[32];
                 tmem_ld32(t_row, va);
 #pragma unroll 1
@@ -224,13 +262,13 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < 32; ++j) __stcg(slot + (size_t)(sub * 32 + j) * BM, __uint_as_float(va[j]));
                     tmem_ld_wait(vb);
                     if (sub + 2 < kSubs) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
-                    else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+                    else release_acc();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) __stcg(slot + (size_t)((sub + 1) * 32 + j) * BM, __uint_as_float(vb[j]));
                 }
                 __threadfence();                                   // this thread's slot writes before the flag
                 asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
-                if (et == 0) st_release_gpu_u32(ws_flags + cta, 1u);
+                if (et == 0) st_release_gpu_u32(ws_flags + my_slot, 1u);
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
@@ -254,7 +292,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // SK_FINISH: the pieces that cover the start of this tile were computed first by CTAs cta-1 .. cta-n_contrib
             const int n_contrib = it.kind == SK_FINISH ? it.n_contrib : 0;
             for (int c = 1; c <= n_contrib; ++c)
-                while (ld_acquire_gpu_u32(ws_flags + (cta - c)) == 0u) { }
+                while (ld_acquire_gpu_u32(ws_flags + slot_of(cta - c)) == 0u) { }
 
             auto process = [&](uint32_t (&v)[32], int sub) {
                 const int ch = sub / kSubsPerChunk, h = sub % kSubsPerChunk;
@@ -268,7 +306,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 for (int c = 1; c <= n_contrib; ++c) {             // fixed order: nearest CTA first
-                    const float* slot = ws_slots + (size_t)(cta - c) * kSkSlotFloats + (size_t)(sub * 32) * BM + et;
+                    const float* slot = ws_slots + (size_t)slot_of(cta - c) * kSkSlotFloats + (size_t)(sub * 32) * BM + et;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] += __ldcg(slot + (size_t)j * BM);
                 }
@@ -319,7 +357,8 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     fence_proxy_async_smem();
                     asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
                     if (et == 0) {
-                        tma_store_2d(&tmap_c, staging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        // pair mode: the upper CTA's 128 rows may lie entirely beyond the last row
+                        if (!kPair || m0 < p.M) tma_store_2d(&tmap_c, staging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
                         tma_store_commit();
                     }
                     sbuf ^= 1;
@@ -335,13 +374,13 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 process(va, sub);
                 tmem_ld_wait(vb);
                 if (sub + 2 < kSubs) tmem_ld32(t_row + (uint32_t)((sub + 2) * 32), va);
-                else { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+                else release_acc();
                 process(vb, sub + 1);
             }
             if (n_contrib > 0) {
                 // every epilogue thread has read the slots: hand the flags back (0) for the next launch on this workspace
                 asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
-                if (et < n_contrib) ws_flags[cta - 1 - et] = 0u;
+                if (et < n_contrib) ws_flags[slot_of(cta - 1 - et)] = 0u;
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
@@ -350,17 +389,20 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();     // no CTA leaves (or frees TMEM) while its peer can still signal or read it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
     }
 }
 
-template <bool kOutBf16, int kEpi>
+template <bool kOutBf16, int kEpi, bool kPair>
 static int launch_sk_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
                          const Params& p, float* slots, uint32_t* flags) {
-    constexpr int smem = gemm_smem_bytes(kStages, 1);
-    auto kern = gemm_streamk_kernel<kOutBf16, kEpi>;
+    constexpr int smem = kPair ? gemm_smem_bytes_pair(kPairStages, 1) : gemm_smem_bytes(kStages, 1);
+    static_assert(smem <= 227 * 1024, "shared memory exceeds the 227 KB a CTA can opt into");
+    auto kern = gemm_streamk_kernel<kOutBf16, kEpi, kPair>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
@@ -370,27 +412,37 @@ static int launch_sk_one(int grid, cudaStream_t st, const CUtensorMap& ma, const
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
+    // Finishing CTAs spin on flags of other CTAs: all must be resident.  grid <= number of SMs with one CTA per SM, so
+    // they are whenever the device is not shared; the cooperative attribute makes the launch fail instead of hang
+    // otherwise (one-CTA mode; a cluster launch cannot be cooperative, there the grid size is the guarantee).
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;     // finishing CTAs spin on flags of other CTAs: all must be resident
-    attr[0].val.cooperative = 1;
+    if (kPair) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p, slots, flags));
     return TASU_OK;
 }
 
-template <bool kOutBf16>
+template <bool kOutBf16, bool kPair>
 static int launch_sk_epi(int epilogue, int grid, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb,
                          const CUtensorMap& mc, const Params& p, float* slots, uint32_t* flags) {
+#define TASU_SK(E) launch_sk_one<kOutBf16, E, kPair>(grid, st, ma, mb, mc, p, slots, flags)
     switch (epilogue) {
-        case TASU_EPI_NONE: return launch_sk_one<kOutBf16, TASU_EPI_NONE>(grid, st, ma, mb, mc, p, slots, flags);
-        case TASU_EPI_BIAS: return launch_sk_one<kOutBf16, TASU_EPI_BIAS>(grid, st, ma, mb, mc, p, slots, flags);
-        case TASU_EPI_BIAS_SILU: return launch_sk_one<kOutBf16, TASU_EPI_BIAS_SILU>(grid, st, ma, mb, mc, p, slots, flags);
-        case TASU_EPI_BIAS_RELU: return launch_sk_one<kOutBf16, TASU_EPI_BIAS_RELU>(grid, st, ma, mb, mc, p, slots, flags);
-        case TASU_EPI_LNFOLD_SILU: return launch_sk_one<kOutBf16, TASU_EPI_LNFOLD_SILU>(grid, st, ma, mb, mc, p, slots, flags);
-        case TASU_EPI_LNFOLD: return launch_sk_one<kOutBf16, TASU_EPI_LNFOLD>(grid, st, ma, mb, mc, p, slots, flags);
-        default: return launch_sk_one<kOutBf16, TASU_EPI_SOFTMAX>(grid, st, ma, mb, mc, p, slots, flags);
+        case TASU_EPI_NONE: return TASU_SK(TASU_EPI_NONE);
+        case TASU_EPI_BIAS: return TASU_SK(TASU_EPI_BIAS);
+        case TASU_EPI_BIAS_SILU: return TASU_SK(TASU_EPI_BIAS_SILU);
+        case TASU_EPI_BIAS_RELU: return TASU_SK(TASU_EPI_BIAS_RELU);
+        case TASU_EPI_LNFOLD_SILU: return TASU_SK(TASU_EPI_LNFOLD_SILU);
+        case TASU_EPI_LNFOLD: return TASU_SK(TASU_EPI_LNFOLD);
+        default: return TASU_SK(TASU_EPI_SOFTMAX);
     }
+#undef TASU_SK
 }
 
 }  // namespace gemm
@@ -415,23 +467,30 @@ extern "C" int tasu_gemm_bf16_tn_streamk(const void* A, int64_t lda, const void*
     TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * csz) % 16 == 0, "row pitches must be multiples of 16 bytes");
     TASU_CHECK_ARG(workspace && ((uintptr_t)workspace % 256 == 0) && workspace_bytes >= tasu_gemm_streamk_workspace(),
                    "workspace missing, unaligned or smaller than tasu_gemm_streamk_workspace()");
+    // CTA pairs (one 256x256 tile per cluster of two) for problems with more than one 128-row tile, as tasu_gemm_bf16_tn
+    const bool pair = option(TASU_OPT_GEMM_PAIR) != 0 && M > BM && sm_count() >= 2;
     CUtensorMap ma, mb, mc;
     rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
-    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, pair ? BN / 2 : BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
     rc = make_map(&mc, C, c_dtype == TASU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, csz,
                   M, N, ldc, BM, c_dtype == TASU_F32 ? 32 : 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
     Params p{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
-    // the grid is always the SM count: with a device-side row count the number of live tiles is not known here, and
-    // the flag array is indexed by CTA
-    const int grid = sm_count();
+    // the grid is always the SM count (pair mode: rounded down to whole clusters): with a device-side row count the
+    // number of live tiles is not known here, and the flag / slot arrays are indexed by CTA
+    const int sms = sm_count();
+    const int grid = pair ? (sms / 2) * 2 : sms;
     uint32_t* flags = reinterpret_cast<uint32_t*>(workspace);
-    float* slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((grid * 4 + 255) / 256) * 256);
+    float* slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((sms * 4 + 255) / 256) * 256);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = c_dtype == TASU_BF16 ? launch_sk_epi<true>(epilogue, grid, st, ma, mb, mc, p, slots, flags)
-                              : launch_sk_epi<false>(epilogue, grid, st, ma, mb, mc, p, slots, flags);
+    if (pair)
+        rc = c_dtype == TASU_BF16 ? launch_sk_epi<true, true>(epilogue, grid, st, ma, mb, mc, p, slots, flags)
+                                  : launch_sk_epi<false, true>(epilogue, grid, st, ma, mb, mc, p, slots, flags);
+    else
+        rc = c_dtype == TASU_BF16 ? launch_sk_epi<true, false>(epilogue, grid, st, ma, mb, mc, p, slots, flags)
+                                  : launch_sk_epi<false, false>(epilogue, grid, st, ma, mb, mc, p, slots, flags);
     if (rc) return rc;
     TASU_CHECK_LAUNCH();
     return TASU_OK;

@@ -28,6 +28,9 @@ struct PoolArgs {
     float eps;
 };
 
+// fp32 inputs are the accuracy path (1e-5 of the fp32 reference): full-precision expf; bf16 inputs keep the fast one
+template <typename Tin> __device__ __forceinline__ float pool_exp(float x) { return sizeof(Tin) == 4 ? expf(x) : __expf(x); }
+
 // locate packed row r: largest b with row_off[b] <= r (row_off has B+1 entries)
 __device__ __forceinline__ int find_utt(const int32_t* __restrict__ row_off, int B, int r) {
     int lo = 0, hi = B;
@@ -90,7 +93,7 @@ meanpool_kernel(PoolArgs a) {
                         if (c0 + u * (int)blockDim.x < nchunk) q[u] = ld_stream_u4(srow + c0 + u * blockDim.x);
                     float mx = 0.f, is = 1.f;
                     if (kSoftmax) {
-                        const int64_t fr = (int64_t)b * a.T + t0 + f;
+                        const int64_t fr = a.seg_src != nullptr ? (int64_t)a.seg_src[r] + f : (int64_t)b * a.T + t0 + f;
                         mx = a.smax[fr];
                         is = 1.f / a.ssum[fr];
                     }
@@ -100,7 +103,7 @@ meanpool_kernel(PoolArgs a) {
                             float x[VI];
                             unpack16(q[u], x, Tin());
 #pragma unroll
-                            for (int e = 0; e < VI; ++e) v[u][e] += kSoftmax ? __expf(x[e] - mx) * is : x[e];
+                            for (int e = 0; e < VI; ++e) v[u][e] += kSoftmax ? pool_exp<Tin>(x[e] - mx) * is : x[e];
                         }
                     }
                 }
@@ -134,8 +137,8 @@ meanpool_kernel(PoolArgs a) {
                 for (int f = 0; f < n; ++f) {
                     float x = to_f32(src[(int64_t)f * a.rstride + d]);
                     if (kSoftmax) {
-                        const int64_t fr = (int64_t)b * a.T + t0 + f;
-                        x = __expf(x - a.smax[fr]) / a.ssum[fr];
+                        const int64_t fr = a.seg_src != nullptr ? (int64_t)a.seg_src[r] + f : (int64_t)b * a.T + t0 + f;
+                        x = pool_exp<Tin>(x - a.smax[fr]) / a.ssum[fr];
                     }
                     v += x;
                 }
@@ -153,10 +156,10 @@ meanpool_kernel(PoolArgs a) {
                     const Tin* sr = src + (int64_t)f * a.rstride;
                     float x[4] = {to_f32(sr[d]), to_f32(sr[d + bd]), to_f32(sr[d + 2 * bd]), to_f32(sr[d + 3 * bd])};
                     if (kSoftmax) {
-                        const int64_t fr = (int64_t)b * a.T + t0 + f;
+                        const int64_t fr = a.seg_src != nullptr ? (int64_t)a.seg_src[r] + f : (int64_t)b * a.T + t0 + f;
                         const float mx = a.smax[fr], is = 1.f / a.ssum[fr];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) x[e] = __expf(x[e] - mx) * is;
+                        for (int e = 0; e < 4; ++e) x[e] = pool_exp<Tin>(x[e] - mx) * is;
                     }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] += x[e];
@@ -173,8 +176,8 @@ meanpool_kernel(PoolArgs a) {
                 for (int f = 0; f < n; ++f) {
                     float x = to_f32(src[(int64_t)f * a.rstride + d]);
                     if (kSoftmax) {
-                        const int64_t fr = (int64_t)b * a.T + t0 + f;
-                        x = __expf(x - a.smax[fr]) / a.ssum[fr];
+                        const int64_t fr = a.seg_src != nullptr ? (int64_t)a.seg_src[r] + f : (int64_t)b * a.T + t0 + f;
+                        x = pool_exp<Tin>(x - a.smax[fr]) / a.ssum[fr];
                     }
                     v += x;
                 }
@@ -221,7 +224,7 @@ extern "C" int tasu_segment_meanpool(const void* feats, int in_dtype, int B, int
     TASU_CHECK_ARG((softmax_max == nullptr) == (softmax_sumexp == nullptr), "softmax stats come in pairs");
     TASU_CHECK_ARG((ln_mean == nullptr) == (ln_rstd == nullptr), "ln stats come in pairs");
     TASU_CHECK_ARG(out_row_stride >= D, "out_row_stride < D");
-    TASU_CHECK_ARG(seg_src == nullptr || (layout == 0 && softmax_max == nullptr), "compact source needs packed layout, no softmax");
+    TASU_CHECK_ARG(seg_src == nullptr || layout == 0, "compact source needs the packed layout");
     if (B == 0 || max_rows <= 0 || (layout == 1 && max_len <= 0)) return TASU_OK;
     TASU_CHECK_ARG(feats && seg_start && seg_len && row_off && out, "null pointer");
     const int isz = in_dtype == TASU_F32 ? 4 : 2, osz = out_dtype == TASU_F32 ? 4 : 2;

@@ -324,6 +324,27 @@ pool_tail_kernel(__nv_bfloat16* __restrict__ probs, int64_t ld, int D, int64_t n
     }
 }
 
+// Natural-order index of the kept frames (fp32-accurate path): packed candidate r covers compact rows
+// [seg_src[r], seg_src[r] + len) and frame_row[compact row] = its raw encoder row.  One thread per candidate.
+__global__ void __launch_bounds__(256)
+kept_frame_index_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
+                        const int32_t* __restrict__ seg_foff, const int32_t* __restrict__ row_off,
+                        const int32_t* __restrict__ frame_off, int B, int T, int n_prefix, int64_t max_rows, int64_t max_out,
+                        int32_t* __restrict__ frame_row, int32_t* __restrict__ seg_src) {
+    const int n_out = row_off[B];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_out || r >= max_out) return;
+    int lo = 0, hi = B;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row_off[mid] <= r) lo = mid; else hi = mid; }
+    const int b = lo, j = r - row_off[b];
+    const int64_t pj = (int64_t)b * T + j;
+    const int t0 = seg_start[pj], n = seg_len[pj];
+    const int c0 = frame_off[b] + seg_foff[pj];
+    seg_src[r] = c0;
+    for (int f = 0; f < n; ++f)
+        if (c0 + f < max_rows) frame_row[c0 + f] = b * (T + n_prefix) + n_prefix + t0 + f;
+}
+
 // Content fingerprint of up to 8 buffers (weight-cache validation): 4096 evenly spaced 32-bit words of every buffer,
 // each multiplied by an odd constant that depends on its sample index, summed modulo 2^64.  One CTA; thread 0 stores
 // the result with a plain store, so `out` may live in pinned host memory.
@@ -514,6 +535,18 @@ extern "C" int tasu_cast_rows_sumsq(const float* src, int64_t rows, int cols, in
     if (g > gmax) g = gmax;
     cast_f32_bf16_sumsq_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, src_stride, (__nv_bfloat16*)dst_bf16,
                                                                             dst_stride, dst_stride, row_sumsq, vec);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_kept_frame_index(const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_frame_off,
+                                     const int32_t* row_off, const int32_t* frame_off, int B, int T, int n_prefix,
+                                     int64_t max_rows, int64_t max_out, int32_t* frame_row, int32_t* seg_src, void* stream) {
+    TASU_CHECK_ARG(B >= 0 && T >= 0 && n_prefix >= 0 && max_rows >= 0 && max_out >= 0, "shape");
+    if (B == 0 || max_out == 0) return TASU_OK;
+    TASU_CHECK_ARG(seg_start && seg_len && seg_frame_off && row_off && frame_off && frame_row && seg_src, "null pointer");
+    kept_frame_index_kernel<<<(unsigned)((max_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        seg_start, seg_len, seg_frame_off, row_off, frame_off, B, T, n_prefix, max_rows, max_out, frame_row, seg_src);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

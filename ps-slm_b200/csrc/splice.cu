@@ -71,12 +71,60 @@ __device__ __forceinline__ bool batch_left_padding(const int32_t* __restrict__ r
     return left;
 }
 
+// per-batch totals: slot base of every row, audio offsets, S', padding side, error words; one CTA (any block size)
+__device__ __forceinline__ void splice_header_body(const int32_t* __restrict__ rowstat, const int64_t* __restrict__ num_audio,
+                                                   int n_audio, int64_t div_k, int B, int64_t* __restrict__ header,
+                                                   int32_t* __restrict__ slot_base, int32_t* __restrict__ audio_off,
+                                                   int* scratch) {
+    bool both;
+    const bool left = batch_left_padding(rowstat, B, scratch, &both);
+    int carry = 0, mx = 0, nsp = 0;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < B ? __ldcg(rowstat + (int64_t)b * RS_WORDS + RS_SLOTS) : 0;   // written by other CTAs when fused
+        int total;
+        const int excl = block_excl_scan_i(v, scratch, &total);
+        if (b < B) {
+            slot_base[b] = carry + excl;
+            mx = max(mx, __ldcg(rowstat + (int64_t)b * RS_WORDS + RS_TOT));
+            nsp += rowstat[(int64_t)b * RS_WORDS + RS_NSPEECH];
+        }
+        carry += total;
+    }
+    const int total_slots = carry;
+    mx = block_max_i(mx, scratch);
+    nsp = block_sum_i(nsp, scratch);
+    int acarry = 0;
+    for (int a0 = 0; a0 < n_audio; a0 += blockDim.x) {
+        const int a = a0 + threadIdx.x;
+        int v = 0;
+        if (a < n_audio) { int64_t m = num_audio[a] / div_k; v = (int)(m < 0 ? 0 : m); }
+        int total;
+        const int excl = block_excl_scan_i(v, scratch, &total);
+        if (a < n_audio) audio_off[a] = acarry + excl;
+        acarry += total;
+    }
+    if (threadIdx.x == 0) {
+        audio_off[n_audio] = acarry;
+        header[TASU_SH_SPLICED_LEN] = mx;
+        header[TASU_SH_LEFT_PADDING] = left ? 1 : 0;
+        header[TASU_SH_ERR_BOTH_SIDES] = both ? 1 : 0;
+        header[TASU_SH_TOTAL_SLOTS] = total_slots;
+        header[TASU_SH_TOTAL_AUDIO] = acarry;
+        header[TASU_SH_N_SPEECH] = nsp;
+        header[6] = 0; header[7] = 0;
+    }
+}
+
+struct SpliceHeaderArgs { int32_t* ticket; int64_t* header; int32_t* slot_base; int32_t* audio_off; };
+
 __global__ void __launch_bounds__(256)
 splice_plan_kernel(const int64_t* __restrict__ ids, const void* __restrict__ mask, int mdt, int B, int S,
                    int64_t speech, const int64_t* __restrict__ num_audio, int n_audio, int64_t div_k,
                    int32_t* __restrict__ rowstat, int32_t* __restrict__ new_pos, int32_t* __restrict__ text_prefix,
-                   int32_t* __restrict__ slot_ord) {
+                   int32_t* __restrict__ slot_ord, const SpliceHeaderArgs hd) {
     __shared__ int scratch[33];
+    __shared__ int s_last;
     const int b = blockIdx.x;
     bool both;
     const bool left = batch_left_padding(rowstat, B, scratch, &both);
@@ -148,6 +196,18 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const void* __restrict__ mas
         rowstat[(int64_t)b * RS_WORDS + RS_TOT] = tot;
         rowstat[(int64_t)b * RS_WORDS + RS_SLOTS] = c_sl;
     }
+    if (hd.ticket == nullptr) return;
+    // fused header (tasu_splice_plan_header): the last CTA to finish sees every row's totals; the ticket returns to zero
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int t = atomicAdd(hd.ticket, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) { *hd.ticket = 0; __threadfence(); }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    splice_header_body(rowstat, num_audio, n_audio, div_k, B, hd.header, hd.slot_base, hd.audio_off, scratch);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -155,44 +215,7 @@ splice_header_kernel(const int32_t* __restrict__ rowstat, const int64_t* __restr
                      int64_t div_k, int B, int64_t* __restrict__ header, int32_t* __restrict__ slot_base,
                      int32_t* __restrict__ audio_off) {
     __shared__ int scratch[33];
-    bool both;
-    const bool left = batch_left_padding(rowstat, B, scratch, &both);
-    int carry = 0, mx = 0, nsp = 0;
-    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
-        const int b = b0 + threadIdx.x;
-        const int v = b < B ? rowstat[(int64_t)b * RS_WORDS + RS_SLOTS] : 0;
-        int total;
-        const int excl = block_excl_scan_i(v, scratch, &total);
-        if (b < B) {
-            slot_base[b] = carry + excl;
-            mx = max(mx, rowstat[(int64_t)b * RS_WORDS + RS_TOT]);
-            nsp += rowstat[(int64_t)b * RS_WORDS + RS_NSPEECH];
-        }
-        carry += total;
-    }
-    const int total_slots = carry;
-    mx = block_max_i(mx, scratch);
-    nsp = block_sum_i(nsp, scratch);
-    int acarry = 0;
-    for (int a0 = 0; a0 < n_audio; a0 += blockDim.x) {
-        const int a = a0 + threadIdx.x;
-        int v = 0;
-        if (a < n_audio) { int64_t m = num_audio[a] / div_k; v = (int)(m < 0 ? 0 : m); }
-        int total;
-        const int excl = block_excl_scan_i(v, scratch, &total);
-        if (a < n_audio) audio_off[a] = acarry + excl;
-        acarry += total;
-    }
-    if (threadIdx.x == 0) {
-        audio_off[n_audio] = acarry;
-        header[TASU_SH_SPLICED_LEN] = mx;
-        header[TASU_SH_LEFT_PADDING] = left ? 1 : 0;
-        header[TASU_SH_ERR_BOTH_SIDES] = both ? 1 : 0;
-        header[TASU_SH_TOTAL_SLOTS] = total_slots;
-        header[TASU_SH_TOTAL_AUDIO] = acarry;
-        header[TASU_SH_N_SPEECH] = nsp;
-        header[6] = 0; header[7] = 0;
-    }
+    splice_header_body(rowstat, num_audio, n_audio, div_k, B, header, slot_base, audio_off, scratch);
 }
 
 struct Dest {           // what lands on destination position (b, p)
@@ -407,7 +430,25 @@ extern "C" int tasu_splice_plan(const int64_t* input_ids, const void* attention_
     TASU_CHECK_ARG(n_audio == 0 || num_audio, "null num_audio");
     splice_plan_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(input_ids, attention_mask, mask_dtype, B, S, speech_id,
                                                             num_audio, n_audio, div_k, rowstat, new_pos, text_prefix,
-                                                            slot_ord);
+                                                            slot_ord, SpliceHeaderArgs{});
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_splice_plan_header(const int64_t* input_ids, const void* attention_mask, int mask_dtype, int B, int S,
+                                       int64_t speech_id, const int64_t* num_audio, int n_audio, int64_t div_k,
+                                       int32_t* rowstat, int32_t* new_pos, int32_t* text_prefix, int32_t* slot_ord,
+                                       int64_t* header, int32_t* slot_base, int32_t* audio_off, int32_t* ticket,
+                                       void* stream) {
+    TASU_CHECK_ARG(B >= 0 && S >= 0 && n_audio >= 0 && div_k >= 1, "B,S,n_audio >= 0, div_k >= 1");
+    TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
+    TASU_CHECK_ARG(header && audio_off && ticket, "null header outputs / ticket");
+    if (B == 0) return tasu_splice_header(rowstat, num_audio, n_audio, div_k, 0, S, header, slot_base, audio_off, stream);
+    TASU_CHECK_ARG(input_ids && attention_mask && rowstat && new_pos && text_prefix && slot_ord && slot_base, "null pointer");
+    TASU_CHECK_ARG(n_audio == 0 || num_audio, "null num_audio");
+    splice_plan_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(input_ids, attention_mask, mask_dtype, B, S, speech_id,
+                                                            num_audio, n_audio, div_k, rowstat, new_pos, text_prefix,
+                                                            slot_ord, SpliceHeaderArgs{ticket, header, slot_base, audio_off});
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

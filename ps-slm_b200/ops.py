@@ -237,6 +237,20 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
     return xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd
 
 
+def kept_frame_index(plan: "CollapsePlan", n_prefix: int, n_frames: int, n_out: int):
+    """(frame_row int32 [n_frames] raw encoder row of every kept frame in natural order, seg_src int32 [n_out] first
+    compact row of every packed candidate) — tasu_kept_frame_index."""
+    dev = plan.seg_start.device
+    frame_row = torch.empty(max(n_frames, 1), dtype=torch.int32, device=dev)[:n_frames]
+    seg_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)[:n_out]
+    L.check(L.lib().tasu_kept_frame_index(plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.seg_foff.data_ptr(),
+                                          plan.row_off.data_ptr(), plan.frame_off.data_ptr(), plan.B, plan.T, n_prefix,
+                                          n_frames, n_out, frame_row.data_ptr(), seg_src.data_ptr(), _stream()),
+            "tasu_kept_frame_index")
+    _count(1)
+    return frame_row, seg_src
+
+
 def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tail_src: torch.Tensor,
               multi: Optional[torch.Tensor], ln_mean: torch.Tensor, ln_rstd: torch.Tensor, ln_eps: float = 1e-5):
     """``probs``: the compact [rows, ld] matrix; its row count is the capacity no access may exceed."""
@@ -521,15 +535,12 @@ def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: 
     p.slot_base = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
     p.audio_off = torch.empty(p.n_audio + 1, dtype=torch.int32, device=dev)
     p.header = header if header is not None else torch.empty(L.SH_WORDS, dtype=torch.int64, device=dev)
-    lib = L.lib()
-    L.check(lib.tasu_splice_plan(p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, B, S,
-                                 p.speech_id, num_audio.data_ptr(), p.n_audio, div_k, p.rowstat.data_ptr(),
-                                 p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(), _stream()),
-            "tasu_splice_plan")
-    L.check(lib.tasu_splice_header(p.rowstat.data_ptr(), num_audio.data_ptr(), p.n_audio, div_k, B, S,
-                                   p.header.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(), _stream()),
-            "tasu_splice_header")
-    _count(2)
+    L.check(L.lib().tasu_splice_plan_header(p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, B, S,
+                                            p.speech_id, num_audio.data_ptr(), p.n_audio, div_k, p.rowstat.data_ptr(),
+                                            p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(),
+                                            p.header.data_ptr(), p.slot_base.data_ptr(), p.audio_off.data_ptr(),
+                                            _ticket(dev)[1:2].data_ptr(), _stream()), "tasu_splice_plan_header")
+    _count(1)
     return p
 
 

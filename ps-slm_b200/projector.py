@@ -76,6 +76,13 @@ class EncoderProjectorLinearSiLU(_CachedWeightsModule):
     def _forward_fp32x3(self, x):
         """fp32-accurate inference path (reference numerics: fp32 LayerNorm/Linear/SiLU/Linear)."""
         B, T, D = x.shape
+        y = self.forward_rows_fp32x3(x.reshape(B * T, D).float())
+        return y.view(B, T, -1).to(x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+
+    def forward_rows_fp32x3(self, x2: torch.Tensor) -> torch.Tensor:
+        """fp32-accurate projector on packed rows ``[N, in_dim]`` fp32 (any row pitch) → ``[N, out_dim]`` fp32: every
+        contraction runs as a three-term bf16 split on the tensor cores (~1e-6 of fp32), LayerNorm statistics in fp32."""
+        N, D = x2.shape
         Hb, H = self.ffn[0].weight.shape[0], self.ffn[2].weight.shape[0]
         params = [self.norm.weight, self.norm.bias, self.ffn[0].weight, self.ffn[0].bias, self.ffn[2].weight, self.ffn[2].bias]
 
@@ -88,13 +95,13 @@ class EncoderProjectorLinearSiLU(_CachedWeightsModule):
                 w2s, k2, _, _, _ = ops.split_bf16x3(self.ffn[2].weight.detach().float(), 1)
                 return w1s, k1, colsum, dbias, w2s, k2, self.ffn[2].bias.detach().float().contiguous()
         w1s, k1, colsum, dbias, w2s, k2, b2 = self._cache3.get(params, build, verify=True)
-        xs, kx, mean, rstd, _ = ops.split_bf16x3(x.reshape(B * T, D).float(), 0, want_ln=True, ln_eps=self.norm.eps)
-        h = torch.empty(B * T, Hb, dtype=torch.float32, device=x.device)
-        ops.gemm_fp32x3(xs, w1s, B * T, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
+        xs, kx, mean, rstd, _ = ops.split_bf16x3(x2, 0, want_ln=True, ln_eps=self.norm.eps)
+        h = torch.empty(max(N, 1), Hb, dtype=torch.float32, device=x2.device)[:N]
+        ops.gemm_fp32x3(xs, w1s, N, Hb, kx, h, L.EPI_LNFOLD_SILU, dbias, rstd, mean, colsum)
         hs, kh, _, _, _ = ops.split_bf16x3(h, 0)
-        y = torch.empty(B * T, H, dtype=torch.float32, device=x.device)
-        ops.gemm_fp32x3(hs, w2s, B * T, H, kh, y, L.EPI_BIAS, b2)
-        return y.view(B, T, H).to(x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        y = torch.empty(max(N, 1), H, dtype=torch.float32, device=x2.device)[:N]
+        ops.gemm_fp32x3(hs, w2s, N, H, kh, y, L.EPI_BIAS, b2)
+        return y
 
     def folded_weights(self, verify: bool = False):
         """(W1·γ bf16 [2048, pad64(in)], colsum, W1β+b1, W2 bf16, b2 fp32), cached (see ProjectorCache).

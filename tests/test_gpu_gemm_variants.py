@@ -193,10 +193,20 @@ SK_SHAPES = [(8341, 2048, 4096), (300, 512, 2048), (128 * 37, 1024, 1088), (128 
              (130, 260, 72), (257, 1536, 2048), (5, 40, 64)]
 
 
+@pytest.fixture(params=[1, 0], ids=["pair", "one_cta"])
+def sk_mode(request):
+    """stream-K in CTA-pair mode (default for M > 128) and with one CTA per tile (TASU_OPT_GEMM_PAIR = 0)."""
+    import ps_slm_b200._lib as L
+    import ps_slm_b200.ops as ops
+    ops.set_option(L.OPT_GEMM_PAIR, request.param)
+    yield request.param
+    ops.set_option(L.OPT_GEMM_PAIR, 1)
+
+
 @pytest.mark.parametrize("epi,out_dtype", [(0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (4, torch.bfloat16),
                                            (6, torch.bfloat16)])
 @pytest.mark.parametrize("M,N,K", SK_SHAPES)
-def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
+def test_streamk_gemm(dev, sk_mode, M, N, K, epi, out_dtype):
     import ps_slm_b200.ops as ops
     A, B, acc64 = _problem(M, N, K)
     ldc = ops.pad_to(N, 8)
@@ -223,7 +233,7 @@ def test_streamk_gemm(dev, M, N, K, epi, out_dtype):
     assert int(ops.streamk_workspace(dev)[:4 * 148].view(torch.int32).abs().sum()) == 0, "flags are zero between launches"
 
 
-def test_streamk_gemm_device_side_row_count(dev):
+def test_streamk_gemm_device_side_row_count(dev, sk_mode):
     import ps_slm_b200.ops as ops
     torch.manual_seed(3)
     M, N, K = 4096, 2048, 2048
@@ -237,11 +247,12 @@ def test_streamk_gemm_device_side_row_count(dev):
         torch.cuda.synchronize()
         if live:
             assert (C[:live] - ref[:live]).abs().max().item() / ref.abs().max().item() < 1e-4
-        tiles = (live + 127) // 128
-        assert bool((C[min(M, tiles * 128):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
+        tm = 256 if sk_mode else 128                     # rows per tile (pair tiles are 256 rows tall)
+        tiles = (live + tm - 1) // tm
+        assert bool((C[min(M, tiles * tm):] == -5.0).all()), "rows of tiles without live rows must stay untouched"
 
 
-def test_streamk_matches_default_on_uncut_tiles(dev):
+def test_streamk_matches_default_on_uncut_tiles(dev, sk_mode):
     """The tiles of the full waves take exactly the default path: bit-equal to tasu_gemm_bf16_tn there."""
     import ps_slm_b200.ops as ops
     torch.manual_seed(9)
@@ -253,7 +264,9 @@ def test_streamk_matches_default_on_uncut_tiles(dev):
     ops.gemm_bf16_tn(A, B, M, N, K, C0)
     ops.gemm_bf16_tn_streamk(A, B, M, N, K, C1)
     torch.cuda.synchronize()
-    whole_rows = (444 // 8) * 128                        # n fastest: tile = m_tile * 8 + n_tile
+    # n fastest: tile = m_tile * 8 + n_tile.  One CTA per tile: 528 tiles on 148 CTAs, tiles 0..443 whole; pairs: 264
+    # tiles of 256 rows on 74 clusters, tiles 0..221 whole
+    whole_rows = (222 // 8) * 256 if sk_mode else (444 // 8) * 128
     assert torch.equal(C0[:whole_rows], C1[:whole_rows])
     assert (C0 - C1).abs().max().item() / C0.abs().max().item() < 1e-5
 
