@@ -348,20 +348,36 @@ kept_frame_index_kernel(const int32_t* __restrict__ seg_start, const int32_t* __
 // Content fingerprint of up to 8 buffers (weight-cache validation): 4096 evenly spaced 32-bit words of every buffer,
 // each multiplied by an odd constant that depends on its sample index, summed modulo 2^64.  One CTA; thread 0 stores
 // the result with a plain store, so `out` may live in pinned host memory.
-struct FingerprintArgs { const uint32_t* ptr[8]; int64_t words[8]; int n; };
+struct FingerprintArgs { const uint32_t* ptr[8]; int64_t words[8]; int64_t stride[8]; int n; };
 constexpr int kFpSamples = 4096;
 
+// Every thread issues its 4 samples of each of the (up to 8) buffers as independent loads before the first one is
+// consumed: one DRAM round trip for the whole kernel instead of 32 dependent ones (26 us -> a few us per step).
+// Sample k of buffer t is word k * stride[t] (stride = 1 for buffers of at most kFpSamples words, host-computed).
 __global__ void __launch_bounds__(1024)
 fingerprint_kernel(const FingerprintArgs a, unsigned long long* __restrict__ out) {
     __shared__ unsigned long long red[32];
+    constexpr int kPer = kFpSamples / 1024;
+    uint32_t v[8][kPer];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int k = (int)threadIdx.x + 1024 * j;
+            const int64_t idx = (int64_t)k * a.stride[t];
+            v[t][j] = (t < a.n && idx < a.words[t]) ? __ldg(a.ptr[t] + idx) : 0u;
+        }
+    }
     unsigned long long h = 0;
-    for (int i = threadIdx.x; i < a.n * kFpSamples; i += blockDim.x) {
-        const int t = i / kFpSamples, k = i % kFpSamples;
-        const int64_t w = a.words[t];
-        if (w <= 0 || (w < kFpSamples && k >= w)) continue;
-        const int64_t idx = w <= kFpSamples ? k : ((int64_t)k * (w - 1)) / (kFpSamples - 1);
-        const unsigned long long v = a.ptr[t][idx];
-        h += (v + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ull + 1ull);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int k = (int)threadIdx.x + 1024 * j;
+            const int i = t * kFpSamples + k;
+            if (t < a.n && (int64_t)k * a.stride[t] < a.words[t])
+                h += ((unsigned long long)v[t][j] + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ull + 1ull);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
@@ -518,6 +534,7 @@ extern "C" int tasu_fingerprint(const void* const* ptrs_host, const int64_t* nby
         TASU_CHECK_ARG((uintptr_t)ptrs_host[i] % 4 == 0, "4-byte aligned buffers");
         a.ptr[i] = (const uint32_t*)ptrs_host[i];
         a.words[i] = nbytes_host[i] / 4;
+        a.stride[i] = a.words[i] <= kFpSamples ? 1 : (a.words[i] - 1) / (kFpSamples - 1);
     }
     fingerprint_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, (unsigned long long*)out);
     TASU_CHECK_LAUNCH();
