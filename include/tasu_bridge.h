@@ -65,7 +65,7 @@ const char* tasu_last_error(void);
  *   pairs — clusters of two CTAs, one tcgen05.mma.cta_group::2 of M = 256 per 256x256 tile, each CTA staging half of
  *   the B tile (a third less shared-memory fill per flop).  Same contract and bit-identical results as the one-CTA
  *   kernel (the accumulation order inside a tile is unchanged); 0 selects the one-CTA kernel. */
-enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_DEBUG = 1 /* TEMPORARY: epilogue attribution experiment */, TASU_OPT_COUNT = 2 };
+enum { TASU_OPT_GEMM_PAIR = 0, TASU_OPT_COUNT = 1 };
 int tasu_set_option(int option, int value);
 int tasu_get_option(int option);   /* value, or TASU_ERR_INVALID_ARG for an unknown option */
 /* sm_count, compute capability of the current device */

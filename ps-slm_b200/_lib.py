@@ -19,7 +19,7 @@ INPUT_PROBS, INPUT_LOGITS = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, EPI_SOFTMAX = 0, 1, 2, 3, 4, 5, 6
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
-OPT_GEMM_PAIR, OPT_DEBUG, OPT_COUNT = 0, 1, 2     # run-time options (tasu_set_option)
+OPT_GEMM_PAIR, OPT_COUNT = 0, 1     # run-time options (tasu_set_option)
 
 # name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float

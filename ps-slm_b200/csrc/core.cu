@@ -30,8 +30,8 @@ int sm_count() {
 }
 
 // run-time options (tasu_set_option); the initial value of option X comes from the environment variable named below
-static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR", "TASU_DEBUG"};
-static const int kOptionDefault[TASU_OPT_COUNT] = {1, 0};
+static const char* const kOptionEnv[TASU_OPT_COUNT] = {"TASU_GEMM_PAIR"};
+static const int kOptionDefault[TASU_OPT_COUNT] = {1};
 static std::atomic<int> g_options[TASU_OPT_COUNT];
 static std::once_flag g_options_once;
 

@@ -61,16 +61,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* src, int c0, int c1, uint64_t policy) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
@@ -223,8 +213,6 @@ struct Params {
     const float* row_rstd;
     const float* row_mean;
     const float* colsum;
-    int dbg;                  // TEMPORARY (TASU_OPT_DEBUG): epilogue attribution experiment
-    void* c_ptr; int64_t ldc; // TEMPORARY: direct stores from the staging tile
 };
 
 // ------------------------------------------------------------------ host side

@@ -183,12 +183,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
         // Per-tile vectors (bias / colsum slices, this thread's row statistics) are fetched ONE TILE AHEAD into
-        // registers: at K <= 1024 a tile lasts ~2 us and the two dependent L2 round trips at its top (bias -> smem,
-        // then row_rstd / row_mean) were 28 % of the epilogue's time (profiles/r02e_ncu_detail.md).
+        // registers, so the two dependent L2 round trips at the top of a tile no longer stall the epilogue warps (28 %
+        // of their samples at K = 512).  Measured effect on the kernel time: none — the kept-frame softmax GEMM is bound
+        // by the bytes it stores, not by its epilogue (profiles/r02g_softmax_gemm_attribution.md).
         constexpr bool kHasCol = kEpi == TASU_EPI_LNFOLD_SILU || kEpi == TASU_EPI_LNFOLD;
         constexpr bool kHasRow = kHasCol || kEpi == TASU_EPI_SOFTMAX;
         constexpr int kVecPer = BN / kEpiThreads;                  // columns of the tile this thread stages (2)
-        float pf_bias[kVecPer], pf_col[kVecPer], pf_rstd = 1.f, pf_nmean = 0.f;
+        float pf_bias[kVecPer], pf_col[kVecPer], pf_rstd = 1.f, pf_mean = 0.f;
         auto fetch_vectors = [&](int t) {
             const int fm0 = (t / n_tiles) * kTileM + (kPair ? (int)rank * BM : 0), fn0 = (t % n_tiles) * BN;
 #pragma unroll
@@ -197,17 +198,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 pf_bias[j] = (kEpi != TASU_EPI_NONE && col < p.N) ? __ldg(p.bias + col) : 0.f;
                 pf_col[j] = (kHasCol && col < p.N) ? __ldg(p.colsum + col) : 0.f;
             }
-            pf_rstd = 1.f; pf_nmean = 0.f;
-            if (kHasRow && fm0 + et < M_live) { pf_rstd = __ldg(p.row_rstd + fm0 + et); pf_nmean = -__ldg(p.row_mean + fm0 + et); }
+            pf_rstd = 1.f; pf_mean = 0.f;                          // consumed (negated) a tile later: no wait here
+            if (kHasRow && fm0 + et < M_live) { pf_rstd = __ldg(p.row_rstd + fm0 + et); pf_mean = __ldg(p.row_mean + fm0 + et); }
         };
         {
             const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
             if (first < num_tiles) fetch_vectors(first);
         }
-        const int dbg = p.dbg;
         TASU_TILE_LOOP {
             const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
-            if (dbg & 1) fetch_vectors(tile);                      // TEMPORARY: the old behaviour (no prefetch)
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
             if (kEpi != TASU_EPI_NONE) {
@@ -219,7 +218,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (kHasCol) s_colsum[c] = pf_col[j];
                 }
             }
-            const float rstd = pf_rstd, nmean = pf_nmean;
+            const float rstd = pf_rstd, nmean = -pf_mean;
             {
                 const int next = tile + (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
                 if (next < num_tiles) fetch_vectors(next);         // in flight during this whole tile
@@ -236,7 +235,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             auto process = [&](uint32_t (&v)[32], int sub) {
                 const int ch = sub / kSubsPerChunk, h = sub % kSubsPerChunk;
                 if (ch >= n_chunks) return;                            // fully clipped (uniform over the group's 4 warps)
-                if (dbg & 16) return;
                 const uint32_t srow = stg_u32 + (uint32_t)(sbuf * kStagingBytes + et * 128);
                 if (h == 0) {
                     // the TMA store that last read this staging buffer must have finished reading it
@@ -264,7 +262,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         } else if (kEpi == TASU_EPI_SOFTMAX) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)      // softmax with known row max (-nmean) and 1/sum (rstd)
-                                x[e] = (dbg & 2) ? fmaf(x[e], kLog2e, b[e] + rowc) : ex2_approx(fmaf(x[e], kLog2e, b[e] + rowc));
+                                x[e] = ex2_approx(fmaf(x[e], kLog2e, b[e] + rowc));
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -277,8 +275,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 4; ++e) f[4 * q + e] = x[e];
                 }
-                if (dbg & 8) {
-                } else if (kOutBf16) {
+                if (kOutBf16) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)        // 32 columns → 64 bytes → 16-byte pieces 4h .. 4h+3
                         st_shared_u4(srow + (uint32_t)((((h * 4 + q) ^ sw)) * 16),
@@ -293,31 +290,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (h == kSubsPerChunk - 1) {
                     fence_proxy_async_smem();
                     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(kEpiThreads) : "memory");
-                    if (kOutBf16 && (dbg & 256)) {
-                        // TEMPORARY experiment: the group's 128 threads copy the staged 128 x 128-byte chunk to global
-                        // memory themselves (8 x 16-byte pieces per row, 16 rows per pass) instead of one TMA store
-                        const int piece = et & 7;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = (et >> 3) + 16 * i;
-                            uint32_t q0, q1, q2, q3;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3)
-                                         : "r"(stg_u32 + (uint32_t)(sbuf * kStagingBytes + rr * 128 + ((piece ^ (rr & 7)) * 16))));
-                            const int gr = m0 + rr, gc = n0 + ch * kColsPerChunk + piece * 8;
-                            if (gr < M_live && gc < p.N)
-                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.c_ptr) + (int64_t)gr * p.ldc + gc) = make_uint4(q0, q1, q2, q3);
-                        }
-                    } else if (et == 0) {
+                    if (et == 0) {
                         // pair mode: the upper CTA's 128 rows may lie entirely beyond the last row
-                        if ((!kPair || m0 < p.M) && !(dbg & 4)) {
-                            // TEMPORARY experiment: bit 5 = every store of this CTA lands in one fixed (L2-resident) tile,
-                            // bit 6 = L2 evict_first hint, bit 7 = L2 evict_last hint
-                            const int sm0 = (dbg & 32) ? (int)(blockIdx.x % (unsigned)((p.M + BM - 1) / BM)) * BM : m0;
-                            const int sn0 = (dbg & 32) ? ch * kColsPerChunk : n0 + ch * kColsPerChunk;
-                            if (dbg & 64) tma_store_2d_hint(&tmap_c, gstaging + sbuf * kStagingBytes, sn0, sm0, l2_policy_evict_first());
-                            else if (dbg & 128) tma_store_2d_hint(&tmap_c, gstaging + sbuf * kStagingBytes, sn0, sm0, l2_policy_evict_last());
-                            else tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, sn0, sm0);
-                        }
+                        if (!kPair || m0 < p.M) tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
                         tma_store_commit();
                     }
                     sbuf ^= 1;
@@ -556,7 +531,7 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     rc = make_map(&mc, C, c_dtype == TASU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, csz,
                   M, N, ldc, BM, c_dtype == TASU_F32 ? 32 : 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
-    Params p{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum, option(TASU_OPT_DEBUG), C, ldc};
+    Params p{M, N, K, m_dev, epilogue, bias, row_rstd, row_mean, colsum};
     if (pair) {
         const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
         int clusters = sm_count() / 2;
