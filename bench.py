@@ -47,15 +47,17 @@ def parse():
                     help="encoder output handed over as bf16 instead of fp32 (halves the H2D bytes of e2e and skips the cast "
                          "kernel; the kernels compute on the same bf16 values either way). Off by default: the reference's "
                          "encoder output is fp32")
-    ap.add_argument("--streamk", action="store_true",
-                    help="projector GEMM-1 through the one-CTA stream-K kernel (tasu_gemm_bf16_tn_streamk) instead of the "
-                         "default CTA-pair kernel (A/B; the pair kernel measured faster, profiles/r02a_ab.md)")
+    ap.add_argument("--no-streamk", action="store_true",
+                    help="projector GEMM-1 through the plain persistent kernel instead of the stream-K one (default)")
     ap.add_argument("--no-pair-gemm", action="store_true",
                     help="deep-K GEMMs with one CTA per tile instead of CTA pairs (A/B; TASU_OPT_GEMM_PAIR = 0)")
     ap.add_argument("--materialize-logits", action="store_true",
                     help="round-1a path: ctc_lo writes fp32 logits to HBM and a streaming kernel computes the stats")
     ap.add_argument("--sustained-seconds", type=float, default=3.0,
                     help="length of the second, sustained timed loop (0 = skip); the headline loop is a burst of K steps")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="device-resident loops: batches are issued round-robin on this many CUDA streams, so the small HBM- / "
+                         "latency-bound kernels of one batch run beside the tensor-bound GEMMs of the next (throughput mode)")
     ap.add_argument("--no-comm", action="store_true", help="skip the packed-path / training-step sections")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"],
                     help="numerics of the HEADLINE loop: bf16 operands / fp32 accumulation (default; 1e-2 of the fp32 reference) or "
@@ -429,8 +431,7 @@ def b200_arm(args):
     bridge.exact_decisions = args.exact_decisions
     bridge.precision = args.precision
     import ps_slm_b200._lib as L
-    if args.streamk:
-        bridge.streamk_gemm1 = True
+    bridge.streamk_gemm1 = not args.no_streamk
     if args.no_pair_gemm:
         ops.set_option(L.OPT_GEMM_PAIR, 0)
     host, devb = [], []
@@ -447,6 +448,24 @@ def b200_arm(args):
     def step_dev(i):
         raw, raw_lens, ids, mask = devb[i % args.rotate]
         return bridge(raw, raw_lens, ids, mask)
+
+    side = [torch.cuda.Stream(dev) for _ in range(args.streams)] if args.streams > 1 else []
+
+    def run_steps(n, first=0):
+        """n batches, device resident; with --streams S > 1 batch i is issued on stream i % S (the caller's stream joins
+        them all before and after, so events recorded around this call bracket every kernel)."""
+        if not side:
+            for i in range(n):
+                step_dev(first + i)
+            return
+        cur = torch.cuda.current_stream()
+        for s_ in side:
+            s_.wait_stream(cur)
+        for i in range(n):
+            with torch.cuda.stream(side[i % len(side)]):
+                step_dev(first + i)
+        for s_ in side:
+            cur.wait_stream(s_)
 
     from ps_slm_b200.bridge import HostPipeline
     pipe = HostPipeline(bridge, dev)
@@ -468,8 +487,7 @@ def b200_arm(args):
             return float(t.item())
         return ms
 
-    for i in range(max(args.warmup, 3)):
-        step_dev(i)
+    run_steps(max(args.warmup, 3) * max(1, args.streams))
     run_e2e(max(args.warmup, 3, args.rotate + 1))      # every rotating batch once: allocator pools of the 3 streams warm
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -479,8 +497,7 @@ def b200_arm(args):
     sampler.start()
     launches0 = ops.COUNTERS["launches"]
     e0.record()
-    for i in range(args.steps):
-        step_dev(i)
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -522,8 +539,7 @@ def b200_arm(args):
         sus_sampler = ClockSampler(local)
         sus_sampler.start()
         e0.record()
-        for i in range(n_sus):
-            step_dev(i)
+        run_steps(n_sus)
         e1.record()
         barrier()
         sus_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -648,10 +664,10 @@ def b200_arm(args):
                    "batch_per_gpu": B, "frames_per_utt": T, "V": V, "compressed_rows_per_step": n_out,
                    "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective in the headline step "
                                                          "(the path's two exchange steps are timed in `comm`)" % world,
-                   "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
+                   "streams": args.streams, "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
                    "frames_refined_in_fp32_last_step": n_ambiguous,
                    "encoder_out_dtype": "bf16" if args.host_bf16 else "f32",
-                   "gemm": {"deep_k": "one-CTA stream-K" if args.streamk else ("one CTA per tile" if args.no_pair_gemm else "CTA pairs (cta_group::2)")},
+                   "gemm": {"deep_k": ("one CTA per tile" if args.no_pair_gemm else "CTA pairs (cta_group::2)") + ("" if args.no_streamk else ", stream-K last wave (GEMM-1)")},
                    "path": "materialized fp32 logits" if args.materialize_logits else "fused ctc_lo+stats, recompute kept frames",
                    "l2": "rotating %d distinct input batches (%.0f MB > 126 MB L2); per-step intermediates (%.2f GB) exceed L2"
                          % (args.rotate, args.rotate * in_bytes / 1e6,

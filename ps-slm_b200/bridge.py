@@ -352,7 +352,8 @@ def linear_silu_forward(x_bf16: torch.Tensor, rows: int, K: int, mean: torch.Ten
                         m_dev: Optional[torch.Tensor] = None, streamk: bool = False) -> torch.Tensor:
     """LayerNorm → Linear → SiLU → Linear of projector.py:149-151 as two tensor-core GEMMs:
     GEMM-1 runs on the raw rows with the LayerNorm folded into its epilogue.
-    ``streamk``: EXPERIMENTAL — GEMM-1 through ``tasu_gemm_bf16_tn_streamk``."""
+    ``streamk``: GEMM-1 through ``tasu_gemm_bf16_tn_streamk`` — the ragged last wave of tiles cut along K (the row count
+    is data dependent; 3.57 waves at the headline batch: −4.4 %, profiles/r02n_gemm_ab.md)."""
     Hb, H = w1g.shape[0], w2.shape[0]
     dev = x_bf16.device
     import contextlib
@@ -429,8 +430,8 @@ class TasuBridge:
         # embeddings within 1e-5 of the fp32 reference, ~6 x the tensor work on the kept frames (two-phase: header first)
         self.precision = "bf16"
         self._ctc_split_cache = ProjectorCache()
-        # EXPERIMENTAL (not yet validated on a GPU): projector GEMM-1 with the stream-K tail
-        self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK") == "1"
+        # projector GEMM-1 with the stream-K tail (default; TASU_GEMM_STREAMK=0 selects the plain persistent kernel)
+        self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK", "1") != "0"
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
         self.events = []              # [(stage name, start event, end event)] of the profiled calls
 

@@ -259,17 +259,32 @@ ctc_stats_combine_kernel(StatsParams p, int B, int T, int n_prefix, int32_t* __r
     if (i >= (int64_t)B * T) return;
     const int b = (int)(i / T), t = (int)(i % T);
     const int64_t r = (int64_t)b * (T + n_prefix) + n_prefix + t;
-    float m = -INFINITY; int a = 0x7fffffff;
+    // every partial of the frame is loaded up front (independent loads: one L2 round trip instead of ~70 dependent ones)
+    constexpr int kMaxParts = 16;                                          // 8 vocabulary splits x 2 column halves
     const int parts = 2 * p.splits;                                        // (split, column half), ascending columns
-    for (int s = 0; s < parts; ++s) {
-        const float pm = p.part_max[(int64_t)s * p.M + r];
-        if (pm > m) { m = pm; a = p.part_arg[(int64_t)s * p.M + r]; }      // ties keep the lower part = lower index
+    float pm[kMaxParts], ps[kMaxParts], ps2[kMaxParts];
+    int pa[kMaxParts];
+#pragma unroll
+    for (int s = 0; s < kMaxParts; ++s) {
+        const bool on = s < parts;
+        const int64_t o = (int64_t)s * p.M + r;
+        pm[s] = on ? p.part_max[o] : -INFINITY;
+        pa[s] = on ? p.part_arg[o] : 0x7fffffff;
+        ps[s] = on ? p.part_sum[o] : 0.f;
+        ps2[s] = on ? p.part_sum2[o] : 0.f;
     }
+    float m = -INFINITY; int a = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < kMaxParts; ++s)
+        if (pm[s] > m) { m = pm[s]; a = pa[s]; }                           // ties keep the lower part = lower index
     float sum = 0.f, sum2 = 0.f;
-    for (int s = 0; s < parts; ++s) {
-        const float f = exp2f((p.part_max[(int64_t)s * p.M + r] - m) * 1.4426950408889634f);
-        sum += p.part_sum[(int64_t)s * p.M + r] * f;
-        sum2 += p.part_sum2[(int64_t)s * p.M + r] * f * f;
+#pragma unroll
+    for (int s = 0; s < kMaxParts; ++s) {
+        if (s < parts) {
+            const float f = exp2f((pm[s] - m) * 1.4426950408889634f);
+            sum += ps[s] * f;
+            sum2 += ps2[s] * f * f;
+        }
     }
     if (row_sumexp2) row_sumexp2[i] = sum2;
     argmax[i] = a;

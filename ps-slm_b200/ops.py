@@ -400,12 +400,14 @@ _STREAMK_WS = {}
 
 
 def streamk_workspace(device) -> torch.Tensor:
-    """Per-device workspace of the EXPERIMENTAL stream-K GEMM (flags + one fp32 partial tile per SM), zero-filled once.
-    One workspace per device: launches that use it must be stream-ordered (the bridge has one compute stream)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Workspace of the stream-K GEMM (flags + one fp32 partial tile per SM), zero-filled once and handed back with its
+    flags zeroed by every launch.  One per (device, stream): launches on one stream are ordered, launches on different
+    streams must not share flags."""
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     if key not in _STREAMK_WS:
         _STREAMK_WS[key] = torch.zeros(int(L.lib().tasu_gemm_streamk_workspace()), dtype=torch.uint8,
-                                       device=torch.device("cuda", key))
+                                       device=torch.device("cuda", idx))
     return _STREAMK_WS[key]
 
 
@@ -413,7 +415,8 @@ def gemm_bf16_tn_streamk(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: i
                          epilogue: int = L.EPI_NONE, bias: Optional[torch.Tensor] = None,
                          row_rstd: Optional[torch.Tensor] = None, row_mean: Optional[torch.Tensor] = None,
                          colsum: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None):
-    """EXPERIMENTAL (tasu_gemm_bf16_tn_streamk): ``gemm_bf16_tn`` with the ragged last wave of tiles cut along K."""
+    """``gemm_bf16_tn`` for deep-K problems with the ragged last wave of tiles cut along K (tasu_gemm_bf16_tn_streamk;
+    CTA pairs when TASU_OPT_GEMM_PAIR is on).  Deterministic; the cut tiles differ from the plain kernel in the last fp32 bits."""
     _need_cuda(A, Bw, out)
     if A.dtype != torch.bfloat16 or Bw.dtype != torch.bfloat16:
         raise TypeError("GEMM operands must be bfloat16")
