@@ -55,7 +55,7 @@ def parse():
                     help="round-1a path: ctc_lo writes fp32 logits to HBM and a streaming kernel computes the stats")
     ap.add_argument("--sustained-seconds", type=float, default=3.0,
                     help="length of the second, sustained timed loop (0 = skip); the headline loop is a burst of K steps")
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--streams", type=int, default=2,
                     help="device-resident loops: batches are issued round-robin on this many CUDA streams, so the small HBM- / "
                          "latency-bound kernels of one batch run beside the tensor-bound GEMMs of the next (throughput mode)")
     ap.add_argument("--no-comm", action="store_true", help="skip the packed-path / training-step sections")
@@ -208,6 +208,7 @@ def reference_arm(args):
 # clocks sampler (NVML) — runs during the timed region
 # ------------------------------------------------------------------------------------------------
 E2E_REPS = 5
+HEADLINE_REPS = 3     # windows of exactly K steps; the median window is the headline (one host hiccup on one of N ranks moves a 30 ms window by tens of percent)
 
 
 class ClockSampler:
@@ -415,6 +416,12 @@ def b200_arm(args):
     import ps_slm_b200.dist as D
     # opt-in (TASU_BIND_NUMA=1): pin the rank to the GPU-local CPUs before any pinned allocation
     numa_cpus = D.bind_to_local_numa(local) if os.environ.get("TASU_BIND_NUMA") == "1" else None
+    # one rank per GPU on one box: every rank gets its own slice of the CPUs (TASU_BIND_CPUS=0 turns it off)
+    cpu_slice = None
+    if world > 1 and numa_cpus is None and os.environ.get("TASU_BIND_CPUS", "1") != "0":
+        cpu_slice = D.bind_rank_to_cpu_slice(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        if cpu_slice:
+            torch.set_num_threads(max(1, len(cpu_slice) - 1))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, int(round(args.seconds / 0.06))
@@ -451,7 +458,7 @@ def b200_arm(args):
 
     side = [torch.cuda.Stream(dev) for _ in range(args.streams)] if args.streams > 1 else []
 
-    def run_steps(n, first=0):
+    def run_steps(n, first=0, side=side):
         """n batches, device resident; with --streams S > 1 batch i is issued on stream i % S (the caller's stream joins
         them all before and after, so events recorded around this call bracket every kernel)."""
         if not side:
@@ -496,12 +503,27 @@ def b200_arm(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ops.COUNTERS["launches"]
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ops.COUNTERS["launches"] - launches0
+    head_runs = []
+    for _ in range(HEADLINE_REPS):
+        barrier()
+        e0.record()
+        run_steps(args.steps)
+        e1.record()
+        barrier()
+        head_runs.append(max_over_ranks(e0.elapsed_time(e1)))
+    ms = statistics.median(head_runs)
+    launches = (ops.COUNTERS["launches"] - launches0) // HEADLINE_REPS
+    single = None
+    if side:                                 # the same K steps on ONE stream (a batch's latency-bound kernels are not hidden)
+        one = []
+        for _ in range(3):
+            barrier()
+            e0.record()
+            run_steps(args.steps, side=[])
+            e1.record()
+            barrier()
+            one.append(max_over_ranks(e0.elapsed_time(e1)))
+        single = {"ms_per_step": statistics.median(one) / args.steps, "windows_ms": [round(x, 3) for x in one]}
     counts = dict(bridge.last_counts)
     n_ambiguous = int(bridge.last_ambiguous.item()) if bridge.last_ambiguous is not None else None
 
@@ -657,6 +679,7 @@ def b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "windows_ms": [round(x, 3) for x in head_runs], "aggregate": "median of %d windows of exactly K steps, each bracketed by barrier + synchronize, max over ranks" % HEADLINE_REPS,
         "dtype": "bf16" if args.precision == "bf16" else "f32 (bf16x3 on tensor cores)", "data": "synthetic",
         "config": {"workload": "configs[1] inference bridge: %d utterances/GPU x %.0f s (T=%d frames, 512-d synthetic encoder "
                                "output) -> ctc_lo -> softmax/argmax -> collapse -> linear-silu projector (25055->2048->1536) "
@@ -675,12 +698,13 @@ def b200_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "pcie": pcie,
                 "windows_ms": [round(x, 3) for x in e2e_runs], "aggregate": "median of %d windows of K steps" % E2E_REPS,
-                "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
+                "host_cpus_bound": len(numa_cpus) if numa_cpus else (len(cpu_slice) if cpu_slice else None),
                 "api": "ps_slm_b200.bridge.HostPipeline.run (pinned host batches in/out, copies overlapped with kernels)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
         "whole_step": whole_step,
+        "single_stream": single,
         "sustained": sustained,
         "fp32_leg": fp32_leg,
         "kernels": kernels,
