@@ -354,7 +354,10 @@ def train_section(args, dev, rank, world, S, D, dist, torch):
         if mode != "none" and world > 1:
             a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            D.allreduce_gradients(params, wire_dtype=torch.bfloat16 if mode == "bf16" else None)
+            if mode == "rs":
+                D.reduce_scatter_gradients(params)
+            else:
+                D.allreduce_gradients(params, wire_dtype=torch.bfloat16 if mode == "bf16" else None)
             z.record()
             ar_events.append((a, z))
         return y.shape[0]
@@ -362,7 +365,7 @@ def train_section(args, dev, rank, world, S, D, dist, torch):
     out = {"workload": "configs[2]: text-only training step, %d utterances/GPU (weak), token-row projector fwd+bwd + splice fwd+bwd + "
                        "gradient all-reduce (%d params)" % (nb, n_param)}
     steps = max(5, args.steps // 2)
-    modes = ["none"] + (["fp32", "bf16"] if world > 1 else [])
+    modes = ["none"] + (["fp32", "bf16", "rs"] if world > 1 else [])
     for mode in modes:
         n_total = 3 + steps
         feed = iter(sim.TokenRowPrefetcher((tbatch for _ in range(n_total)), V, dev, seeds=(1000 + i for i in range(n_total))))
@@ -388,12 +391,16 @@ def train_section(args, dev, rank, world, S, D, dist, torch):
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
             dist.all_reduce(r)
         per = float(v[0]) / steps
-        key = {"none": "no_allreduce", "fp32": "allreduce_fp32", "bf16": "allreduce_bf16_wire"}[mode]
+        key = {"none": "no_allreduce", "fp32": "allreduce_fp32", "bf16": "allreduce_bf16_wire", "rs": "reduce_scatter_fp32_zero2"}[mode]
         out[key] = {"ms_per_step": per, "token_rows_per_s": float(r[0]) / (per / 1e3), "token_rows_per_step": int(r[0])}
         if mode != "none":
             nbytes = n_param * (2 if mode == "bf16" else 4)
-            out[key].update({"allreduce_ms": float(v[1]), "message_bytes": nbytes,
-                             "busbw_gbs": nbytes * 2 * (world - 1) / world / (float(v[1]) / 1e3) / 1e9 if float(v[1]) > 0 else None})
+            factor = (1 if mode == "rs" else 2) * (world - 1) / world
+            out[key].update({"collective_ms": float(v[1]), "message_bytes": nbytes,
+                             "busbw_gbs": nbytes * factor / (float(v[1]) / 1e3) / 1e9 if float(v[1]) > 0 else None})
+            if mode == "rs":
+                out[key]["note"] = ("the exchange of the reference's own configuration (conf/ds_config.json:15-21, ZeRO stage 2 "
+                                    "reduce_scatter): each rank keeps the averaged gradient of its 1/W parameter shard")
     del gpool
     return out
 
@@ -551,6 +558,27 @@ def b200_arm(args):
         e2e_runs.append(max_over_ranks(e0.elapsed_time(e1)))
     ms_e2e = statistics.median(e2e_runs)
     d2h = pipe.d2h_bytes
+    # secondary: the encoder output handed over as bf16 (the first kernel of the fp32 entry is the cast to bf16 anyway:
+    # bit-identical results, tests/test_gpu_gemm_variants.py::test_bridge_bf16_encoder_output_equals_fp32_input; half the H2D bytes)
+    e2e_bf16 = None
+    if not args.host_bf16:
+        host16 = [(hb[0].bfloat16().pin_memory(),) + hb[1:] for hb in host]
+        for _ in pipe.run(host16[i % args.rotate] for i in range(args.rotate + 1)):
+            pass
+        runs16 = []
+        for _ in range(3):
+            barrier()
+            e0.record()
+            for _ in pipe.run(host16[i % args.rotate] for i in range(args.steps)):
+                pass
+            e1.record()
+            barrier()
+            runs16.append(max_over_ranks(e0.elapsed_time(e1)))
+        in16 = sum(t.numel() * t.element_size() for t in host16[0])
+        e2e_bf16 = {"ms_per_step": statistics.median(runs16) / args.steps, "h2d_bytes_per_step": in16,
+                    "value": B * T * world * args.steps / (statistics.median(runs16) / 1e3), "unit": UNIT,
+                    "windows_ms": [round(x, 3) for x in runs16]}
+        del host16
     clocks = sampler.stop()
 
     # ---- (4) sustained regime: the same step, back to back for >= --sustained-seconds (power / thermal steady state)
@@ -699,7 +727,8 @@ def b200_arm(args):
                 "ms_per_step": ms_e2e / args.steps, "pcie": pcie,
                 "windows_ms": [round(x, 3) for x in e2e_runs], "aggregate": "median of %d windows of K steps" % E2E_REPS,
                 "host_cpus_bound": len(numa_cpus) if numa_cpus else (len(cpu_slice) if cpu_slice else None),
-                "api": "ps_slm_b200.bridge.HostPipeline.run (pinned host batches in/out, copies overlapped with kernels)"},
+                "api": "ps_slm_b200.bridge.HostPipeline.run (pinned host batches in/out, copies overlapped with kernels)",
+                "bf16_handover": e2e_bf16},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,

@@ -409,6 +409,10 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
             work0, n_first = early
             work = dist.all_reduce(flat[n_first:], op=dist.ReduceOp.SUM, group=group, async_op=True)
             work0.wait()
+        elif average and flat.is_cuda and not async_op:
+            # NCCL averages inside the collective (ncclAvg): no second pass over the 218 MB buffer for the division
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+            return []
         else:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
         handles = [(work, flat, [])]
@@ -438,6 +442,38 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], bucket_bytes: int 
         return handles
     finish_allreduce(handles, W if average else 1)
     return []
+
+
+def reduce_scatter_gradients(params: Sequence[torch.nn.Parameter], average: bool = True, group=None):
+    """ZeRO-2-style gradient exchange — what the reference's DeepSpeed configuration does with the projector gradients
+    (conf/ds_config.json:15-21: ``"stage": 2, "reduce_scatter": true``): every rank receives the summed (averaged)
+    gradient of ITS contiguous 1/W shard of the flat gradient buffer, half the bytes of an all-reduce on the wire; the
+    sharded optimizer then updates that shard and all-gathers the parameters (DeepSpeed's side, out of scope here).
+    Needs the gradients to be views of one flat fp32 buffer whose length is a multiple of W (the token-row backward's
+    layout: 64-element aligned slices), else they are flattened (one copy) and zero padded.
+    Returns ``(shard fp32 [n / W], (first, last) element range of the shard in the flat parameter order, flat length)``;
+    single process: the whole buffer."""
+    rank, W = world()
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = _shared_flat(grads)
+    if flat is None:
+        flat = torch.cat([g.reshape(-1).float() for g in grads]) if grads else torch.zeros(0)
+    n = flat.numel()
+    if W == 1:
+        return flat, (0, n), n
+    _drain_pending()
+    if n % W:
+        flat = torch.cat([flat, flat.new_zeros(W - n % W)])
+    per = flat.numel() // W
+    if flat.is_cuda:
+        shard = torch.empty(per, dtype=flat.dtype, device=flat.device)
+        dist.reduce_scatter_tensor(shard, flat, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=group)
+    else:                                                        # gloo (CPU tests) has no reduce-scatter
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        shard = flat[rank * per:(rank + 1) * per].clone()
+        if average:
+            shard /= W
+    return shard, (rank * per, min((rank + 1) * per, n)), n
 
 
 def finish_allreduce(handles, divisor: int):

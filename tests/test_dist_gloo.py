@@ -38,6 +38,12 @@ def _worker(rank, world, port, n_utts, out_q):
     D.allreduce_gradients(params, bucket_bytes=4096)
     exp = [(1 + 2) / 2 * (i + 1) for i in range(4)]
     ok = ok and all(torch.allclose(p.grad, torch.full_like(p, e)) for p, e in zip(params, exp))
+    # ZeRO-2-style reduce-scatter of the same gradients: this rank's shard of the averaged flat gradient
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    shard, (lo, hi), n = D.reduce_scatter_gradients(params)
+    full = torch.cat([torch.full((p.numel(),), e) for p, e in zip(params, exp)])
+    ok = ok and n == full.numel() and torch.allclose(shard[:hi - lo], full[lo:hi]) and (lo, hi) == (rank * shard.numel(), min((rank + 1) * shard.numel(), n))
     # selection straight out of the all-gather buffer (what a rank splices after the length-grouped re-deal)
     g = D.gather_packed(rows, lens, n_global=n_utts)
     sel = [5, 0, 3]
