@@ -523,6 +523,8 @@ def b200_arm(args):
     for w_i in range(HEADLINE_REPS):
         settle()
         barrier()
+        if w_i == 0:
+            launches0 = ops.COUNTERS["launches"]
         e0.record()
         run_steps(args.steps)
         e1.record()
