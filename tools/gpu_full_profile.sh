@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call E (1 GPU): whole GPU test suite, smoke, headline bench with clocks, ncu launch list of the bench
+# 1 GPU: whole GPU test suite, smoke, headline bench with clocks, ncu launch list of the bench
 # command, ncu --set full capture of the hot kernels.  Outputs under gpurun_out/*_$TAG.*
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call C (run under `gpurun --gpus N`, N >= 2): whole GPU test suite incl. the NCCL tests, then the headline
+# multi-GPU validation (run under `gpurun --gpus N`, N >= 2): whole GPU test suite incl. the NCCL tests, then the headline
 # bench with its packed-path / training-step sections at 1 and N GPUs of the same box.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
