@@ -128,6 +128,18 @@ def _worker_overlap(rank, world, port, q):
     for a, p in zip(ref, params):
         scale = a.abs().max().item() + 1e-12
         ok = ok and ((p.grad - a).abs().max().item() / scale) < 2e-2
+    # the default exchange (ONE in-place message, averaged inside NCCL) and the ZeRO-2 reduce-scatter of the same flat
+    # buffer (conf/ds_config.json:15-21): this rank's shard of the averaged gradient
+    for p in params:
+        p.grad = None
+    y = proj.forward_token_rows(rows)
+    (y * gy).sum().backward()
+    shard, (lo, hi), n = D.reduce_scatter_gradients(params)
+    D.allreduce_gradients(params)
+    ok = ok and all(torch.allclose(p.grad, a, rtol=1e-5, atol=1e-8) for a, p in zip(ref, params))
+    flat = D._shared_flat([p.grad for p in params])
+    ok = ok and flat is not None and n == flat.numel() and hi - lo == shard.numel() == n // world
+    ok = ok and torch.allclose(shard, flat[lo:hi], rtol=1e-5, atol=1e-8)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

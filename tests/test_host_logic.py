@@ -183,3 +183,31 @@ def test_train_eval_switch_invalidates_weight_caches():
     assert cache.get([p], build) == 3 and cache.get([p], build) == 3
     assert cache.get([p], build, fresh=True) == 4 and cache.get([p], build, fresh=True) == 5
     assert cache.get([p], build) == 6                  # a fresh build leaves nothing behind
+
+
+def test_bind_rank_to_cpu_slice_partitions_the_allowed_cpus():
+    """One process per GPU on one box: every rank gets its own contiguous, disjoint slice of the CPUs this process may
+    use (ps-slm_b200/dist.py); nothing changes when there are fewer than two CPUs per rank or a single rank."""
+    import os
+
+    import ps_slm_b200.dist as D
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no CPU affinity on this platform")
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        assert D.bind_rank_to_cpu_slice(0, 1) is None and sorted(os.sched_getaffinity(0)) == before
+        world = max(2, min(8, len(before) // 2))
+        if len(before) // world < 2:
+            assert D.bind_rank_to_cpu_slice(0, world) is None
+            return
+        seen = []
+        for r in range(world):
+            os.sched_setaffinity(0, before)
+            mine = D.bind_rank_to_cpu_slice(r, world)
+            assert mine == sorted(os.sched_getaffinity(0)) and len(mine) == len(before) // world
+            seen += mine
+        assert len(set(seen)) == len(seen) and set(seen) <= set(before)
+        os.sched_setaffinity(0, before)
+        assert D.bind_rank_to_cpu_slice(0, 10 * len(before)) is None
+    finally:
+        os.sched_setaffinity(0, before)
