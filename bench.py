@@ -9,6 +9,14 @@ splice over one batch of B=64 synthetic 30-s utterances (T=500 frames of 512-d e
 V=25055) per GPU.  `value` = encoder frames consumed per second, whole job, inputs resident in
 HBM; `e2e` = the same through the public call with HOST buffers (pinned H2D of the inputs and
 D2H of inputs_embeds/mask/position ids inside the timed region).  Rank 0 prints ONE JSON line.
+
+Protocol: every timed window = 0.5 s idle, W >= 3 untimed warm-up steps, barrier + synchronize, exactly K
+steps, barrier + synchronize, CUDA events, max over ranks; `value` is the median of 3 such windows
+(`windows_ms`), batches issued round-robin on two streams (`single_stream`: the same on one).  Further keys:
+`sustained` (>= 3 s back to back: the power-capped steady state), `kernels` / `roofline` (a separate pass with
+an event pair per stage), `fp32_leg` (reference numerics), `e2e.bf16_handover`, `comm` (the path's two
+exchange steps: packed all-gather, gradient all-reduce / reduce-scatter; real collectives at N > 1),
+`cpu_baseline` (the unmodified reference files on the host cores, rank 0 at N = 1).
 """
 import argparse
 import json
