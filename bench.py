@@ -490,7 +490,7 @@ def b200_arm(args):
             cur.wait_stream(s_)
 
     from ps_slm_b200.bridge import HostPipeline
-    pipe = HostPipeline(bridge, dev)
+    pipe = HostPipeline(bridge, dev, compute_streams=max(1, args.streams))
 
     def run_e2e(n):
         """n batches through the public host-buffer entry (pinned H2D → kernels → pinned D2H, overlapped)."""
@@ -569,16 +569,43 @@ def b200_arm(args):
     # ---- (3) end-to-end timed region (host buffers in, host buffers out)
     # The pipeline is host-driven (one sync hand-off per step), so a single host hiccup inside a ~40 ms window moves
     # the number by tens of percent: time E2E_REPS windows of exactly K steps each and report the median window.
-    e2e_runs = []
-    for _ in range(E2E_REPS):
-        barrier()
-        e0.record()
-        run_e2e(args.steps)                 # the generator drains: last D2H has completed on return
-        e1.record()
-        barrier()
-        e2e_runs.append(max_over_ranks(e0.elapsed_time(e1)))
+    # Same protocol as the headline windows: 0.5 s idle, W untimed warm-up steps THROUGH THE SAME PIPELINE, barrier, exactly
+    # K timed steps (pipeline fill — the first H2D — and drain — the last D2H — are inside the window), barrier.
+    def settle_e2e(batches):
+        torch.cuda.synchronize()
+        time.sleep(0.5)
+        for _ in pipe.run(batches[i % args.rotate] for i in range(max(args.warmup, 3))):
+            pass
+
+    def e2e_windows(batches, reps):
+        runs = []
+        for _ in range(reps):
+            settle_e2e(batches)
+            barrier()
+            e0.record()
+            for _ in pipe.run(batches[i % args.rotate] for i in range(args.steps)):
+                pass                        # the generator drains: last D2H has completed on return
+            e1.record()
+            barrier()
+            runs.append(max_over_ranks(e0.elapsed_time(e1)))
+        return runs
+
+    e2e_runs = e2e_windows(host, E2E_REPS)
     ms_e2e = statistics.median(e2e_runs)
     d2h = pipe.d2h_bytes
+    # the same loop back to back for >= --sustained-seconds (power-capped steady state; fill / drain amortised)
+    e2e_sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(ms_e2e / args.steps, 1e-3)) + 1)
+        barrier()
+        e0.record()
+        for _ in pipe.run(host[i % args.rotate] for i in range(n_sus)):
+            pass
+        e1.record()
+        barrier()
+        sus_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        e2e_sustained = {"steps": n_sus, "seconds": sus_e2e_ms / 1e3, "ms_per_step": sus_e2e_ms / n_sus,
+                         "value": B * T * world * n_sus / (sus_e2e_ms / 1e3)}
     # secondary: the encoder output handed over as bf16 (the first kernel of the fp32 entry is the cast to bf16 anyway:
     # bit-identical results, tests/test_gpu_gemm_variants.py::test_bridge_bf16_encoder_output_equals_fp32_input; half the H2D bytes)
     e2e_bf16 = None
@@ -586,15 +613,7 @@ def b200_arm(args):
         host16 = [(hb[0].bfloat16().pin_memory(),) + hb[1:] for hb in host]
         for _ in pipe.run(host16[i % args.rotate] for i in range(args.rotate + 1)):
             pass
-        runs16 = []
-        for _ in range(3):
-            barrier()
-            e0.record()
-            for _ in pipe.run(host16[i % args.rotate] for i in range(args.steps)):
-                pass
-            e1.record()
-            barrier()
-            runs16.append(max_over_ranks(e0.elapsed_time(e1)))
+        runs16 = e2e_windows(host16, 3)
         in16 = sum(t.numel() * t.element_size() for t in host16[0])
         e2e_bf16 = {"ms_per_step": statistics.median(runs16) / args.steps, "h2d_bytes_per_step": in16,
                     "value": B * T * world * args.steps / (statistics.median(runs16) / 1e3), "unit": UNIT,
@@ -647,7 +666,24 @@ def b200_arm(args):
         fn(); torch.cuda.synchronize()
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         pcie[name] = big.numel() * big.element_size() / (e0.elapsed_time(e1) / 1e3) / 1e9
-    del dbuf
+    # both directions at once on two streams (tools/micro/pcie_duplex.py): is the host link full duplex on this box?
+    big2 = torch.empty_like(big).pin_memory()
+    dbuf2 = torch.empty_like(dbuf)
+    sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream()
+    for timed_pass in (False, True):
+        torch.cuda.synchronize()
+        e0.record()
+        sa.wait_stream(cur); sb.wait_stream(cur)
+        with torch.cuda.stream(sa):
+            dbuf.copy_(big, non_blocking=True)
+        with torch.cuda.stream(sb):
+            big2.copy_(dbuf2, non_blocking=True)
+        cur.wait_stream(sa); cur.wait_stream(sb)
+        e1.record()
+        torch.cuda.synchronize()
+    pcie["duplex_total_gbs"] = 2 * big.numel() * big.element_size() / (e0.elapsed_time(e1) / 1e3) / 1e9
+    del dbuf, dbuf2, big2
     frames_per_step = B * T * world
     value = frames_per_step * args.steps / (ms / 1e3)
     e2e_value = frames_per_step * args.steps / (ms_e2e / 1e3)
@@ -746,7 +782,9 @@ def b200_arm(args):
                             (B * (T + 4) * 25056 * 4 if args.materialize_logits else (f_kept + n_out) * 25088 * 2) / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "pcie": pcie,
-                "windows_ms": [round(x, 3) for x in e2e_runs], "aggregate": "median of %d windows of K steps" % E2E_REPS,
+                "windows_ms": [round(x, 3) for x in e2e_runs],
+                "aggregate": "median of %d windows; every window = 0.5 s idle, W untimed warm-up steps through the pipeline, barrier, exactly K timed steps incl. pipeline fill and drain, barrier" % E2E_REPS,
+                "compute_streams": max(1, args.streams), "sustained": e2e_sustained,
                 "host_cpus_bound": len(numa_cpus) if numa_cpus else (len(cpu_slice) if cpu_slice else None),
                 "api": "ps_slm_b200.bridge.HostPipeline.run (pinned host batches in/out, copies overlapped with kernels)",
                 "bf16_handover": e2e_bf16},

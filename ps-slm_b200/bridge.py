@@ -804,11 +804,14 @@ class HostPipeline:
             ...                                              # pinned CPU tensors, valid until the next iteration
     """
 
-    def __init__(self, bridge: "TasuBridge", device=None):
+    def __init__(self, bridge: "TasuBridge", device=None, compute_streams: int = 1):
         self.bridge = bridge
         self.device = device if device is not None else bridge.embed_table.device
         self.s_in = torch.cuda.Stream(self.device)
-        self.s_comp = torch.cuda.Stream(self.device)
+        # batch i runs on compute stream i % N: with N = 2 the small HBM- / latency-bound kernels of one batch run in the
+        # tails of the other batch's persistent GEMMs (as in bench.py's device-resident loop)
+        self.s_comps = [torch.cuda.Stream(self.device) for _ in range(max(1, int(compute_streams)))]
+        self.s_comp = self.s_comps[0]
         self.s_out = torch.cuda.Stream(self.device)
         self._host_out = {}
         self.h2d_bytes = 0
@@ -821,20 +824,21 @@ class HostPipeline:
                 if not t.is_pinned():
                     t = t.pin_memory()
                 d = t.to(self.device, non_blocking=True)
-                d.record_stream(self.s_comp)
+                for sc in self.s_comps:
+                    d.record_stream(sc)
                 dev.append(d)
             ev = torch.cuda.Event()
             ev.record(self.s_in)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in batch)
         return dev, ev
 
-    def _download(self, outs, slot):
+    def _download(self, outs, slot, s_comp):
         key = (slot,) + tuple((tuple(o.shape), o.dtype) for o in outs)
         if key not in self._host_out:
             self._host_out[key] = tuple(torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs)
         host = self._host_out[key]
         ev_c = torch.cuda.Event()
-        ev_c.record(self.s_comp)
+        ev_c.record(s_comp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(ev_c)
             for o, h in zip(outs, host):
@@ -859,10 +863,11 @@ class HostPipeline:
                 nxt = self._upload(next(it))          # H2D of the next batch runs under this batch's kernels
             except StopIteration:
                 nxt = None
-            with torch.cuda.stream(self.s_comp):
-                self.s_comp.wait_event(ev_in)
+            s_comp = self.s_comps[i % len(self.s_comps)]
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_in)
                 emb, mask, _, pos, new_lens = self.bridge(*dev)
-            done = self._download((emb, mask, pos, new_lens), i & 1)
+            done = self._download((emb, mask, pos, new_lens), i & 1, s_comp)
             if pending is not None:
                 pending[1].synchronize()
                 yield pending[0]

@@ -309,3 +309,39 @@ def test_bridge_bf16_encoder_output_equals_fp32_input(dev):
     torch.cuda.synchronize()
     for a, c in zip(out32, out16):
         assert (a is None and c is None) or torch.equal(a, c)
+
+
+@pytest.mark.parametrize("compute_streams", [1, 2])
+def test_host_pipeline_equals_direct_calls(dev, compute_streams):
+    """HostPipeline.run (pinned host batches in / out, H2D, kernels and D2H overlapped; batches alternating over
+    ``compute_streams`` streams) yields, batch by batch and in order, exactly what a direct device-resident bridge call
+    returns — including ragged batches of different shapes in one run (capacity re-use across streams)."""
+    import types
+
+    import ps_slm_b200.projector as P
+    import ps_slm_b200.synth as S
+    from ps_slm_b200.bridge import HostPipeline, TasuBridge
+    torch.manual_seed(0)
+    w, b = S.make_ctc_head()
+    cfg = types.SimpleNamespace(encoder_dim=S.V_CTC, llm_dim=S.H_LLM, encoder_projector_ds_rate=1)
+    proj = P.EncoderProjectorLinearSiLU(cfg).to(dev).eval()
+    table = S.make_embed_table(dtype=torch.bfloat16, device=dev)
+    br = TasuBridge(w.to(dev), b.to(dev), proj, table, S.SPEECH_ID, S.PAD_ID)
+    batches = []
+    for i, (B, T) in enumerate([(6, 300), (6, 300), (4, 180), (6, 300), (4, 180), (6, 300), (6, 300)]):
+        raw, raw_lens, _ = S.make_encoder_batch(B, T, w, seed=40 + i, ragged=True)
+        ids, mask, _ = S.make_prompts(B, seed=40 + i, left_pad=True)
+        batches.append((raw, raw_lens, ids, mask))
+    want = []
+    for raw, raw_lens, ids, mask in batches:
+        emb, m, _, pos, new_lens = br(raw.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+        want.append([t.cpu() for t in (emb, m, pos, new_lens)])
+    pipe = HostPipeline(br, dev, compute_streams=compute_streams)
+    n = 0
+    for got in pipe.run(iter(batches)):
+        assert all(g.is_pinned() for g in got)
+        for g, w_ in zip(got, want[n]):
+            assert g.shape == w_.shape and torch.equal(g, w_), "batch %d" % n
+        n += 1
+    assert n == len(batches)
+    assert pipe.h2d_bytes == sum(t.numel() * t.element_size() for t in batches[-1])
