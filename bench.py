@@ -553,6 +553,7 @@ def b200_arm(args):
     single = {"ms_per_step": statistics.median(one) / args.steps, "windows_ms": [round(x, 3) for x in one]} if one else None
     counts = dict(bridge.last_counts)
     n_ambiguous = int(bridge.last_ambiguous.item()) if bridge.last_ambiguous is not None else None
+    n_multi = int(bridge.last_multi.item()) if bridge.last_multi is not None else None
 
     # ---- (2) the same K steps again with a CUDA-event pair around every stage (per-kernel roofline); NOT the headline
     settle([])
@@ -709,9 +710,10 @@ def b200_arm(args):
     algo = {
         "ctc_head_stats": ("tensor", 2.0 * B * (T + 4) * V * De),
         "ctc_softmax_gemm": ("tensor", 2.0 * f_kept * V * De),
-        # extra frames E = f_kept - n_out are read once; each multi-frame head row (>= E/2 of them, runs <= 3)
-        # is read and written once → lower bound 2*E rows of V bf16
-        "pool_tail": ("hbm", 2.0 * (f_kept - n_out) * V * 2.0),
+        # the E = f_kept - n_out extra frames of the multi-frame candidates are read once, each of the n_multi
+        # multi-frame head rows is read and written once: (E + 2 n_multi) rows of V bf16 (exact; without the live count
+        # the lower bound n_multi >= E/2 for runs <= 3 frames)
+        "pool_tail": ("hbm", ((f_kept - n_out) + 2.0 * (n_multi if n_multi is not None else (f_kept - n_out) / 2.0)) * V * 2.0),
         "ctc_lo_gemm": ("tensor", 2.0 * B * (T + 4) * V * De),
         "frame_stats": ("hbm", n_in * V * 4.0 + n_in * 16.0),
         "softmax_meanpool": ("hbm", counts["kept_frames"] * V * 4.0 + n_out * V * 2.0),
@@ -773,7 +775,7 @@ def b200_arm(args):
                    "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective in the headline step "
                                                          "(the path's two exchange steps are timed in `comm`)" % world,
                    "streams": args.streams, "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
-                   "frames_refined_in_fp32_last_step": n_ambiguous,
+                   "frames_refined_in_fp32_last_step": n_ambiguous, "multi_frame_candidates_per_step": n_multi,
                    "encoder_out_dtype": "bf16" if args.host_bf16 else "f32",
                    "gemm": {"deep_k": ("one CTA per tile" if args.no_pair_gemm else "CTA pairs (cta_group::2)") + ("" if args.no_streamk else ", stream-K last wave (GEMM-1)")},
                    "path": "materialized fp32 logits" if args.materialize_logits else "fused ctc_lo+stats, recompute kept frames",

@@ -445,7 +445,8 @@ int tasu_tokrow_linear_silu_bwd(const void* dy, int dy_dtype, int64_t ldy, const
  * tasu_splice_plan    : placeholders, cumsum, per-token slot ordinals    (:805-812, :842-859)
  * tasu_splice_header  : S', padding side, error words, per-row bases     (:809, :861)
  * (the caller reads the header — S', padding side, error words — and passes them back by value)
- * tasu_splice_scatter : row-map pass (integer outputs + source of every output row) and one pure copy pass:
+ * tasu_splice_scatter : ONE launch — per output row the integer outputs + the source of the row (row map, kept in
+ *                       row_src_ws for the backward), then the copy of the row:
  *                       writes inputs_embeds / mask / labels / position_ids / final ids
  *                       (:821-840, :867-871); text rows come from `text_src`:
  *                       text_mode 0 = inputs_embeds [B,S,H]; 1 = embedding table indexed by

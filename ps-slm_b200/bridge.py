@@ -422,6 +422,7 @@ class TasuBridge:
         # there are none).  False: decisions straight from the bf16 head.
         self.exact_decisions = True
         self.last_ambiguous = None        # device int32[1]: frames refined by the last call (exact_decisions)
+        self.last_multi = None            # device int32[1]: multi-frame candidates pooled by the last call
         self._ctc_exact_cache = ProjectorCache()
         self.materialize_logits = False   # True: ctc_lo writes fp32 logits to HBM + streaming stats kernel (round-1a path)
         # "bf16" (default): bf16 operands, fp32 accumulation — posteriors / embeddings within 1e-2 of the fp32 reference.
@@ -448,6 +449,7 @@ class TasuBridge:
         with self._stage("gather_kept_rows"):
             xg, g_max, g_inv, pk_len, tail_src, multi, mean, rstd = ops.gather_kept_rows(
                 x2, B, T, self.N_PREFIX, Denc, V, plan, st, cap_f, cap_o, self.ln_eps)
+        self.last_multi = multi[0:1]      # device int32[1]: multi-frame candidates of the last call (pool_tail's work list)
         pooled = torch.empty(cap_f, ldk, dtype=torch.bfloat16, device=dev)
         with self._stage("ctc_softmax_gemm"):
             ops.gemm_bf16_tn(xg, w_ctc, cap_f, V, Denc, pooled, L.EPI_SOFTMAX, b_ctc, g_inv, g_max,

@@ -283,14 +283,12 @@ struct ScatterArgs {
 };
 
 // Row map: one THREAD per destination row resolves where the row comes from (text token / audio row / nothing) and
-// writes the integer outputs; the dependent-load chain of the resolve (binary search over new_pos, …) stays out of
-// the copy kernel, whose only dependent load is row_src[row].
+// writes the integer outputs and the map the backward gathers through:
 //   row_src[row] = -1 (zero row) | text source row | kAudioFlag + audio row
 constexpr int64_t kAudioFlag = 1LL << 62;
-__global__ void __launch_bounds__(256)
-splice_rowmap_kernel(ScatterArgs a, int64_t* __restrict__ row_src, int32_t* __restrict__ audio_dest) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= (int64_t)a.B * a.Sp) return;
+// one destination row: resolve, write the integer outputs and row_src[row]; returns row_src[row]
+__device__ __forceinline__ int64_t rowmap_one(const ScatterArgs& a, int64_t row, int64_t* __restrict__ row_src,
+                                              int32_t* __restrict__ audio_dest) {
     const int b = (int)(row / a.Sp), p = (int)(row % a.Sp);
     const bool left = a.left_padding != 0;
     const Dest d = resolve_dest(b, p, a.S, a.Sp, left, a.rowstat, a.ids, a.mask, a.mdt, a.speech, a.new_pos,
@@ -317,6 +315,7 @@ splice_rowmap_kernel(ScatterArgs a, int64_t* __restrict__ row_src, int32_t* __re
     if (a.out_labels) a.out_labels[row] = lab;
     a.out_pos[row] = mval ? d.pos : 1;
     if (a.out_ids) a.out_ids[row] = fid;
+    return src;
 }
 
 // 16-byte-chunk row copy with 4 independent loads in flight per lane (src == nullptr: zero fill)
@@ -356,20 +355,28 @@ __device__ __forceinline__ void copy_row_warp(const char* __restrict__ src, char
     }
 }
 
-// one warp per destination row (grid-stride); ESZ = bytes per embedding element
+// Row map + copy in ONE launch: a warp owns kFusedRows consecutive destination rows; its first lanes resolve one row
+// each (the dependent-load chains of the resolve run side by side and under the copies of the other resident warps),
+// then the warp copies the rows one after the other.
+constexpr int kFusedRows = 4;
 template <int ESZ>
 __global__ void __launch_bounds__(256)
-splice_copy_kernel(const int64_t* __restrict__ row_src, int64_t n_rows, int H, const void* __restrict__ text_src,
-                   int64_t text_stride, const void* __restrict__ audio, int64_t audio_stride, void* __restrict__ out_emb) {
+splice_fused_kernel(ScatterArgs a, int64_t* __restrict__ row_src, int32_t* __restrict__ audio_dest) {
     const int lane = threadIdx.x & 31;
-    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t nbytes = (int64_t)H * ESZ;
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += nwarp) {
-        const int64_t sr = row_src[row];
+    const int64_t n_rows = (int64_t)a.B * a.Sp;
+    const int64_t nbytes = (int64_t)a.H * ESZ;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFusedRows;
+    if (row0 >= n_rows) return;                                             // warp-uniform
+    int64_t mine = -1;
+    if (lane < kFusedRows && row0 + lane < n_rows) mine = rowmap_one(a, row0 + lane, row_src, audio_dest);
+#pragma unroll
+    for (int r = 0; r < kFusedRows; ++r) {
+        if (row0 + r >= n_rows) break;
+        const int64_t sr = __shfl_sync(0xffffffffu, mine, r);
         const char* src = nullptr;
-        if (sr >= kAudioFlag) src = reinterpret_cast<const char*>(audio) + (sr - kAudioFlag) * audio_stride * ESZ;
-        else if (sr >= 0) src = reinterpret_cast<const char*>(text_src) + sr * text_stride * ESZ;
-        copy_row_warp(src, reinterpret_cast<char*>(out_emb) + row * nbytes, nbytes, lane);
+        if (sr >= kAudioFlag) src = reinterpret_cast<const char*>(a.audio) + (sr - kAudioFlag) * a.audio_stride * ESZ;
+        else if (sr >= 0) src = reinterpret_cast<const char*>(a.text_src) + sr * a.text_stride * ESZ;
+        copy_row_warp(src, reinterpret_cast<char*>(a.out_emb) + (row0 + r) * nbytes, nbytes, lane);
     }
 }
 
@@ -500,13 +507,9 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
     a.speech = speech_id; a.pad_id = pad_id; a.ignore_id = ignore_id;
     a.out_emb = out_emb; a.out_mask = out_mask; a.out_labels = out_labels; a.out_pos = out_pos; a.out_ids = out_ids;
     cudaStream_t st = (cudaStream_t)stream;
-    splice_rowmap_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(a, row_src_ws, audio_dest);
-    TASU_CHECK_LAUNCH();
-    const unsigned grid = warp_row_grid(rows);
-    if (emb_dtype == TASU_F32)
-        splice_copy_kernel<4><<<grid, 256, 0, st>>>(row_src_ws, rows, H, text_src, text_row_stride, audio_rows, audio_row_stride, out_emb);
-    else
-        splice_copy_kernel<2><<<grid, 256, 0, st>>>(row_src_ws, rows, H, text_src, text_row_stride, audio_rows, audio_row_stride, out_emb);
+    const unsigned grid = (unsigned)((rows + 8 * kFusedRows - 1) / (8 * kFusedRows));
+    if (emb_dtype == TASU_F32) splice_fused_kernel<4><<<grid, 256, 0, st>>>(a, row_src_ws, audio_dest);
+    else splice_fused_kernel<2><<<grid, 256, 0, st>>>(a, row_src_ws, audio_dest);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }
