@@ -301,6 +301,19 @@ int tasu_gemm_bf16_tn_streamk(const void* A, int64_t lda, const void* B, int64_t
 int tasu_gemm_streamk_schedule_host(int num_tiles, int k_blocks, int grid, int cta, int32_t* pieces_host,
                                     int32_t* dp_tiles_host);
 
+/* Cross-attention projector (projector.py:104-126; call site ps-slm.py:475-480), all heads in one launch:
+ *   Z[:, h dp : (h+1) dp] = softmax(Q_h K_h^T) K_h,   Q_h = Q[:, h dp : (h+1) dp],  K_h = table[:, h dp : (h+1) dp]
+ * with keys = values = the LLM embedding table (V2 rows).  The probabilities are produced tile by tile in shared memory
+ * and consumed by the second contraction on the spot — the [N, V2] probability matrix of the composed path
+ * (tasu_gemm_bf16_tn with TASU_EPI_SOFTMAX + tasu_gemm_bf16_f32: 2 x 3 GB of traffic per head at N = 9856) never exists.
+ * row_max / row_inv [heads, stat_stride]: per head and row, max_k s and 1 / sum_k exp(s - max) of s = Q_h K_h^T
+ * (tasu_ctc_head_stats on the head slices) — or both NULL: the kernel finds the row maxima itself in a first sweep over
+ * the keys (scores only, no exponentials) and normalises O by the fp32 sum of the probabilities at the end.
+ * Q pre-scaled by 1/sqrt(d).  dp in {64, 128, 192, 256}; Z fp32. */
+int tasu_attn_softmax_pv(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
+                         int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
+                         float* Z, int64_t ldz, void* stream);
+
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,
                            void* C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,

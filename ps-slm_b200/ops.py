@@ -442,6 +442,25 @@ def gemm_bf16_tn_streamk(A: torch.Tensor, Bw: torch.Tensor, M: int, N: int, K: i
     return out
 
 
+def attn_softmax_pv(Q: torch.Tensor, table: torch.Tensor, N: int, V2: int, heads: int, dp: int, Z: torch.Tensor,
+                    row_max: Optional[torch.Tensor] = None, row_inv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Z[:, h*dp:(h+1)*dp] = softmax(Q_h·K_hᵀ)·K_h`` for all heads in one launch, probabilities kept on the SM
+    (tasu_attn_softmax_pv).  ``Q`` [N, heads*dp] bf16 (pre-scaled), ``table`` [V2, heads*dp] bf16, ``Z`` [N, heads*dp] fp32.
+    ``row_max`` / ``row_inv`` [heads, N] fp32: statistics of the scores per head from a separate pass; without them the
+    kernel finds the row maxima in a first sweep of its own (the default: no statistics pass at all)."""
+    _need_cuda(Q, table, row_max, row_inv, Z)
+    if Q.dtype != torch.bfloat16 or table.dtype != torch.bfloat16 or Z.dtype != torch.float32:
+        raise TypeError("attn_softmax_pv: bf16 operands, fp32 output")
+    L.check(L.lib().tasu_attn_softmax_pv(Q.data_ptr(), Q.stride(0), table.data_ptr(), table.stride(0), N, V2, heads, dp,
+                                         _ptr(row_max), _ptr(row_inv), row_max.stride(0) if row_max is not None else 0,
+                                         Z.data_ptr(), Z.stride(0), _stream()), "tasu_attn_softmax_pv")
+    _count(1)
+    return Z
+
+
+ATTN_FUSED_WIDTHS = (64, 128, 192, 256)
+
+
 def streamk_schedule(num_tiles: int, k_blocks: int, grid: int):
     """HOST: the stream-K schedule the kernel runs — ``(dp_tiles, [pieces of CTA 0, pieces of CTA 1, ...])`` with pieces
     ``(tile, kb0, kb1, kind, n_contrib)`` in processing order (tasu_gemm_streamk_schedule_host)."""

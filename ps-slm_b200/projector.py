@@ -16,6 +16,7 @@ LayerNorm of the default projector is folded into GEMM-1's epilogue.  There is n
 fallback: CPU tensors raise.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -221,6 +222,10 @@ class EncoderProjectorLinear(_CachedWeightsModule):
         return y.view(B, T, ld)[:, :, :self.llm_vocab]
 
 
+# head widths of 64 / 128 / 192 / 256 (Qwen2.5-1.5B: 192) take the fused kernel; TASU_ATTN_FUSED=0: the composed path
+FUSED_ATTENTION = os.environ.get("TASU_ATTN_FUSED", "1") != "0"
+
+
 def _attention_heads(Q, table, N, V2, h, dp, P):
     """Per-head softmax attention of Q over the table (keys = values): yields (head, q_h, k_h, stats) after writing the
     head's probabilities into ``P``."""
@@ -250,9 +255,14 @@ class _CrossAttnFunction(torch.autograd.Function):
             Qp[:, :, :d] = Q.reshape(N, h, d)
             Q = Qp.view(N, h * dp)
         Z = torch.empty(N, h * dp, dtype=torch.float32, device=dev)
-        P = torch.empty(N, ops.pad_to(V2), dtype=torch.bfloat16, device=dev)      # one head's probabilities at a time
-        for i, qh, kh in _attention_heads(Q, table, N, V2, h, dp, P):
-            ops.gemm_bf16_f32(P, False, kh, True, N, dp, V2, Z[:, i * dp:(i + 1) * dp])
+        if FUSED_ATTENTION and dp in ops.ATTN_FUSED_WIDTHS:
+            # ONE launch for every head's softmax(Q Kᵀ)·K: row maxima in a first sweep over the keys, probabilities of
+            # the second sweep kept in shared memory (csrc/attn_sm100.cu) — no statistics pass, no [N, V2] matrix
+            ops.attn_softmax_pv(Q, table, N, V2, h, dp, Z)
+        else:
+            P = torch.empty(N, ops.pad_to(V2), dtype=torch.bfloat16, device=dev)  # one head's probabilities at a time
+            for i, qh, kh in _attention_heads(Q, table, N, V2, h, dp, P):
+                ops.gemm_bf16_f32(P, False, kh, True, N, dp, V2, Z[:, i * dp:(i + 1) * dp])
         ctx.save_for_backward(xb, Q, Z, table)
         ctx.dims = (N, V1, V2, h, d, dp)
         return Z if dp == d else Z.view(N, h, dp)[:, :, :d].reshape(N, D)

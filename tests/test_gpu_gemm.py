@@ -310,3 +310,65 @@ def test_cross_attention_projector_backward(dev, V1, D, V2, B, T):
     assert g is not None and g.shape == wq.grad.shape
     err = ((g.cpu() - wq.grad).norm() / wq.grad.norm()).item()
     assert err < 3e-2, f"relative gradient error {err}"
+
+
+@pytest.mark.parametrize("V1,D,V2,B,T", [(200, 512, 1000, 2, 100), (64, 1024, 515, 3, 90), (300, 1536, 4099, 2, 200),
+                                         (128, 2048, 300, 1, 129), (96, 1536, 151936, 1, 130)])
+def test_cross_attention_fused_kernel(dev, V1, D, V2, B, T):
+    """tasu_attn_softmax_pv (all heads in one launch, probabilities kept in shared memory) against the composed path it
+    replaces (softmax GEMM + MN-major GEMM per head) and against the fp32 oracle (projector.py:104-126): head widths
+    64 / 128 / 192 / 256, ragged last query tile and last key tile, several items per CTA, the full 151936-row table."""
+    import ps_slm_b200.projector as P
+    torch.manual_seed(V1 + D + V2)
+    m = P.EncoderProjectorCTCCA(types.SimpleNamespace(encoder_dim=V1, llm_dim=D, encoder_projector_ds_rate=1))
+    assert (D // m.n_heads) in (64, 128, 192, 256)
+    post = torch.softmax(torch.randn(B, T, V1) * 4, -1)
+    post[0, T - 3:] = 0
+    table = (torch.randn(V2, D) * 0.5).bfloat16()
+    md = m.to(dev).eval()
+    saved = P.FUSED_ATTENTION
+    try:
+        with torch.no_grad():
+            P.FUSED_ATTENTION = False
+            composed = md(post.to(dev), table.to(dev))
+            P.FUSED_ATTENTION = True
+            fused = md(post.to(dev), table.to(dev))
+            fused2 = md(post.to(dev), table.to(dev))
+        torch.cuda.synchronize()
+    finally:
+        P.FUSED_ATTENTION = saved
+    assert torch.equal(fused, fused2), "the fused kernel must be deterministic"
+    scale = composed.abs().max().item() + 1e-9
+    # both round the probabilities to bf16 — the composed path after the normalisation, the fused kernel before it
+    assert (fused - composed).abs().max().item() / scale < 8e-3
+    assert ((fused - composed).norm() / composed.norm()).item() < 4e-3
+    if V2 <= 8192:
+        with torch.no_grad():
+            ref = O.projector_ctcca(post, table.float(), m.W_q.weight.detach().cpu(), m.n_heads)
+        assert ((fused.cpu() - ref).norm() / ref.norm()).item() < 2e-2
+
+
+@pytest.mark.parametrize("N,V2,h,d", [(300, 1000, 8, 192), (129, 515, 4, 64), (2000, 4099, 2, 128), (128, 256, 3, 256), (50, 77, 8, 192)])
+def test_attn_softmax_pv_both_modes(dev, N, V2, h, d):
+    """tasu_attn_softmax_pv against a torch fp32 attention over the same bf16 operands: with the row statistics of a
+    separate pass (one sweep, normalised probabilities) and self-contained (row maxima in a first sweep, O divided by the
+    fp32 sum of the probabilities at the end)."""
+    import ps_slm_b200.ops as ops
+    torch.manual_seed(N + V2)
+    Q = (torch.randn(N, h * d, device=dev) * 0.4).bfloat16()
+    table = (torch.randn(V2, h * d, device=dev) * 0.5).bfloat16()
+    q = Q.float().view(N, h, d).transpose(0, 1)                          # [h, N, d]
+    k = table.float().view(V2, h, d).transpose(0, 1)                     # [h, V2, d]
+    s = q @ k.transpose(1, 2)
+    ref = (torch.softmax(s, -1) @ k).transpose(0, 1).reshape(N, h * d)
+    row_max = s.max(-1).values.contiguous()
+    row_inv = (1.0 / torch.exp(s - row_max[..., None]).sum(-1)).contiguous()
+    Z1 = torch.full((N, h * d), 7.0, device=dev)
+    Z2 = torch.full((N, h * d), 7.0, device=dev)
+    ops.attn_softmax_pv(Q, table, N, V2, h, d, Z1, row_max, row_inv)
+    ops.attn_softmax_pv(Q, table, N, V2, h, d, Z2)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (Z1 - ref).abs().max().item() / scale < 6e-3                  # bf16 probabilities
+    assert (Z2 - ref).abs().max().item() / scale < 6e-3
+    assert (Z1 - Z2).abs().max().item() / scale < 3e-3
