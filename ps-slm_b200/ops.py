@@ -641,7 +641,7 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
         _ptr(audio_dest), _stream()), "tasu_splice_scatter")
     p.audio_dest = audio_dest
     p.row_src = row_src[:n_pos] if want_audio_dest else None      # kept for the backward of the text rows
-    _count(2)
+    _count(1)
     return emb, mask, out_labels, pos, fids
 
 

@@ -25,6 +25,11 @@ timeout 1500 ncu --set full --clock-control none --import-source on \
     -k regex:'gemm_bf16_tn_kernel|splice_fused_kernel|ctc_stats_kernel|pool_tail_kernel|gather_kept_rows_kernel|collapse|cast_rows' -s 30 -c 12 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-comm --no-fp32-leg --sustained-seconds 0 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu_full rc=$?" >> gpurun_out/rc_$TAG.txt
 fi
+if [ "${SKIP_OPS:-0}" != 1 ]; then
+timeout 300 python tools/bench_attn.py > gpurun_out/attn_$TAG.txt 2>&1; echo "attn rc=$?" >> gpurun_out/rc_$TAG.txt
+timeout 600 python tools/bench_ops.py > gpurun_out/ops_$TAG.md 2> gpurun_out/ops_$TAG.err; echo "ops rc=$?" >> gpurun_out/rc_$TAG.txt
+timeout 120 python tools/micro/pcie_duplex.py > gpurun_out/pcie_$TAG.json 2>/dev/null; echo "pcie rc=$?" >> gpurun_out/rc_$TAG.txt
+fi
 python - $TAG <<'PY'
 import json, sys
 d = json.load(open("gpurun_out/bench_%s.json" % sys.argv[1]))

@@ -17,6 +17,25 @@ timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --steps 20 --warmup 3 \
     > gpurun_out/bench_n${N}_$TAG.json 2> gpurun_out/bench_n${N}_$TAG.err; echo "benchN rc=$?" >> gpurun_out/rc_$TAG.txt
 grep -v "^W\|^\*\*\*\|OMP_NUM\|^$" gpurun_out/bench_n${N}_$TAG.err | tail -8
+# host limit of the end-to-end path: pinned H2D + D2H on all N GPUs at once (one process per GPU, CPU slices as in bench.py)
+for i in $(seq 0 $((N-1))); do
+  CUDA_VISIBLE_DEVICES=$i timeout 120 python tools/micro/pcie_duplex.py > gpurun_out/pcie_${TAG}_gpu$i.json 2>/dev/null &
+done
+wait
+python - $N $TAG <<'PY'
+import json, sys
+N, TAG = int(sys.argv[1]), sys.argv[2]
+tot = {"h2d_gbs": 0.0, "d2h_gbs": 0.0, "duplex_total_gbs": 0.0}
+for i in range(N):
+    try:
+        d = json.load(open("gpurun_out/pcie_%s_gpu%d.json" % (TAG, i)))["66MB"]
+        for k in tot:
+            tot[k] += d[k]
+    except Exception as e:
+        print("pcie gpu %d failed: %s" % (i, e))
+print("PCIe, %d GPUs at once (sum over GPUs; the phases of the processes are not aligned, so this is a lower bound of the contention):" % N, json.dumps(tot))
+json.dump(tot, open("gpurun_out/pcie_%s_sum.json" % TAG, "w"))
+PY
 python - $N $TAG <<'PY'
 import json, sys
 N, TAG = sys.argv[1], sys.argv[2]
