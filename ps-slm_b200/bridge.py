@@ -77,6 +77,8 @@ def psd_from_encoder(raw_encoder_out: torch.Tensor, raw_encoder_out_lens: torch.
     return out, plan.new_lens
 
 
+# voca_trans branch without the [B, T', V_llm] logits tensor (TASU_VOCA_FUSED=0: materialised logits, round-1 path)
+FUSED_VOCA_TRANS = os.environ.get("TASU_VOCA_FUSED", "1") != "0"
 LLM_BLANK_ID = 151643     # blank index of the LLM-vocabulary CTC head, hard-coded in the reference (ps-slm.py:491, :621)
 
 
@@ -88,6 +90,9 @@ class _VocaTransFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, w_map, b_map, projector, encoder_out, lens, table, do_psd, top1_emb, blank_id, threshold):
+        if FUSED_VOCA_TRANS and (not do_psd or blank_id == w_map.shape[0] - 1):
+            return _VocaTransFunction._forward_fused(ctx, w_map, b_map, projector, encoder_out, lens, table, do_psd,
+                                                     top1_emb, blank_id, threshold)
         with torch.no_grad():
             logits = projector(encoder_out)                                    # [B, T', Vp] (view of a padded buffer)
         B, Tp, Vp = logits.shape
@@ -136,6 +141,70 @@ class _VocaTransFunction(torch.autograd.Function):
         return out.view(B, max_len, H), new_lens
 
     @staticmethod
+    def _forward_fused(ctx, w_map, b_map, projector, encoder_out, lens, table, do_psd, top1_emb, blank_id, threshold):
+        """The same branch without the ``[B, T', Vp]`` logits (9.7 GB of fp32 at B = 64 x 30 s): the head is linear, so the
+        mean of a run's logits is the logits of the run's mean input frame.  (1) greedy statistics of every frame straight
+        out of the head GEMM's epilogue (``tasu_ctc_head_stats``, as on the main path) → collapse plan; (2) segmented mean
+        of the INPUT frames (the x̄ the backward needs anyway); (3) statistics and bf16 probabilities of the pooled rows
+        from two more passes of the head over x̄ only (blank column dropped: it is the last class), (4) ``P·E`` with the
+        table read in place.  Rows beyond an utterance's compressed length are what the reference's zero-padded logits
+        give: the uniform mixture of the table rows (``top1_emb``: row 0)."""
+        k = projector.k
+        x = encoder_out
+        if x.shape[1] % k:
+            x = x[:, :x.shape[1] - x.shape[1] % k]
+        B = x.shape[0]
+        Tp = x.shape[1] // k
+        xk = x.contiguous().view(B, Tp, -1)                                    # the k-concat the head sees (projector.py:19-24)
+        xk = xk if xk.dtype in (torch.float32, torch.bfloat16) else xk.float()
+        Dk, Vp, H = xk.shape[2], w_map.shape[0], table.shape[1]
+        dev = xk.device
+        feat_len = lens.to(device=dev, dtype=torch.int64) // k
+        with torch.no_grad():
+            w, b = projector.head_bf16()
+        ldk = ops.pad_to(Dk)
+        if do_psd:
+            xb = ops.cast_rows(xk.reshape(B * Tp, Dk), torch.bfloat16, ldk)[0]
+            st = ops.ctc_head_stats(xb, w, b, B, Tp, 0, Vp, Dk, blank_id)
+            plan = ops.collapse_plan(st, feat_len, blank_id, threshold)
+            max_len = int(plan.header.cpu()[L.CH_MAX_LEN])
+            if max_len == 0:
+                ctx.empty = True
+                ctx.shapes = (w_map.shape, b_map.shape)
+                return torch.zeros(B, 0, H, dtype=torch.float32, device=dev), torch.zeros(B, dtype=torch.long, device=dev)
+            xbar = torch.empty(B * max_len, Dk, dtype=xk.dtype, device=dev)
+            ops.segment_meanpool(xk, plan, 1, max_len, B * max_len, xbar, Dk)  # zero rows beyond the compressed lengths
+            new_lens, V_real = plan.new_lens, Vp - 1                           # :493 drops the blank column
+        else:
+            xbar = xk.reshape(B * Tp, Dk)
+            new_lens, max_len, V_real = feat_len, Tp, Vp                       # :509-511 keeps every column
+        N = xbar.shape[0]
+        xbb = ops.cast_rows(xbar, torch.bfloat16, ldk)[0]
+        st2 = ops.ctc_head_stats(xbb, w[:V_real], b[:V_real], 1, N, 0, V_real, Dk, 0)
+        pad = (torch.arange(max_len, device=dev)[None, :] >= new_lens[:, None]).reshape(N) if do_psd else None
+        ctx.empty = False
+        if top1_emb:                                                           # :498-502, :512-516 (no gradient)
+            idx = st2.argmax if pad is None else st2.argmax.masked_fill(pad, 0)
+            out = ops.gather_rows(table, idx)
+            ctx.top1 = True
+            ctx.shapes = (w_map.shape, b_map.shape)
+        else:
+            probs = torch.empty(N, ops.pad_to(V_real), dtype=torch.bfloat16, device=dev)
+            ops.gemm_bf16_tn(xbb, w[:V_real], N, V_real, Dk, probs, L.EPI_SOFTMAX, b[:V_real],
+                             torch.reciprocal(st2.row_sumexp), st2.row_max)
+            out = torch.empty(N, H, dtype=torch.float32, device=dev)
+            ops.gemm_bf16_f32(probs, False, table[:V_real], True, N, H, V_real, out)
+            if pad is not None:
+                uniform = table[:V_real].mean(0, dtype=torch.float32)          # softmax of an all-zero logits row · E
+                out = torch.where(pad[:, None], uniform[None, :], out)
+            ctx.top1 = False
+            ctx.pad = pad                                                      # padding rows carry no gradient (backward)
+            ctx.save_for_backward(probs, out, xbar, table)
+            ctx.dims = (N, H, V_real, Vp, Dk)
+        ctx.mark_non_differentiable(new_lens)
+        return out.view(B, max_len, H), new_lens
+
+    @staticmethod
     def backward(ctx, dout, _):
         if ctx.empty or ctx.top1:
             ws, bs = ctx.shapes
@@ -144,6 +213,11 @@ class _VocaTransFunction(torch.autograd.Function):
         N, H, V_real, Vp, Dk = ctx.dims
         dev = dout.device
         do = dout.reshape(N, H).float().contiguous()
+        pad = getattr(ctx, "pad", None)
+        if pad is not None:
+            # rows beyond the compressed lengths are constants of the forward (zero logits in the reference): with a zero
+            # upstream gradient dProbs and dS of those rows vanish
+            do = do.masked_fill(pad[:, None], 0.0)
         dob, _, _ = ops.cast_rows(do, torch.bfloat16, ops.pad_to(H, 8))
         dP = torch.empty(N, ops.pad_to(V_real, 4), dtype=torch.float32, device=dev)
         ops.gemm_bf16_tn(dob, table, N, V_real, H, dP)                                    # dProbs = dOut · Eᵀ

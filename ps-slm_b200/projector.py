@@ -204,6 +204,11 @@ class EncoderProjectorLinear(_CachedWeightsModule):
         self.map = nn.Linear(self.encoder_dim * self.k, self.llm_vocab, bias=True)
         self._cache = ProjectorCache()
 
+    def head_bf16(self):
+        """(bf16 copy of ``map.weight`` with a TMA-aligned pitch, fp32 bias), cached per parameter content."""
+        return self._cache.get([self.map.weight, self.map.bias], lambda: (
+            cast_weight_bf16(self.map.weight), self.map.bias.detach().float().contiguous()), verify=True)
+
     def forward(self, x):
         x = _downsample(x, self.k)
         B, T, D = x.shape
@@ -212,8 +217,7 @@ class EncoderProjectorLinear(_CachedWeightsModule):
             out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
             y = LinearFunction.apply(x.reshape(B * T, D), self.map.weight, self.map.bias, False, out_dtype)
             return y.reshape(B, T, self.llm_vocab)
-        w, b = self._cache.get([self.map.weight, self.map.bias], lambda: (
-            cast_weight_bf16(self.map.weight), self.map.bias.detach().float().contiguous()), verify=True)
+        w, b = self.head_bf16()
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
         xb, _, _ = _rows_bf16(x.reshape(B * T, D), False)
         ld = ops.pad_to(self.llm_vocab, 8)

@@ -147,3 +147,44 @@ def test_voca_trans_backward(dev, do_psd):
         assert g is not None and g.shape == r.shape, name
         err = ((g.cpu() - r).norm() / r.norm()).item()
         assert err < 3e-2, f"{name}: relative gradient error {err}"
+
+
+@pytest.mark.parametrize("do_psd,top1", [(True, False), (False, False), (True, True)])
+def test_voca_trans_fused_equals_materialised(dev, do_psd, top1):
+    """The voca_trans branch without the logits tensor (head statistics out of the GEMM epilogue, mean-pooling moved to
+    the input side of the linear head) against the round-1 formulation that materialises ``[B, T', V]`` logits: same
+    lengths, same rows — INCLUDING the rows beyond an utterance's compressed length (uniform mixture / row 0)."""
+    import types
+
+    import ps_slm_b200.bridge as bridge
+    import ps_slm_b200.projector as P
+    torch.manual_seed(5)
+    Denc, k, Vh, H, B, T = 64, 2, 1001, 128, 4, 61
+    proj = P.EncoderProjectorLinear(types.SimpleNamespace(encoder_dim=Denc, llm_dim=Vh, encoder_projector_ds_rate=k))
+    with torch.no_grad():
+        proj.map.weight.mul_(10.0)
+        proj.map.bias.normal_(0, 0.3)
+        proj.map.bias[Vh - 1] = 2.5
+    table = (torch.randn(Vh + 5, H) * 0.3).bfloat16().to(dev)
+    x = torch.randn(B, T, Denc)
+    x[:, 1::3] = x[:, 0:-1:3][:, :x[:, 1::3].shape[1]]
+    lens = torch.tensor([T, 23, 40, 9])
+    md = proj.to(dev).eval()
+    saved = bridge.FUSED_VOCA_TRANS
+    try:
+        with torch.no_grad():
+            bridge.FUSED_VOCA_TRANS = False
+            a, la = bridge.voca_trans_project(md, x.to(dev), lens.to(dev), table, do_psd, top1, blank_id=Vh - 1)
+            bridge.FUSED_VOCA_TRANS = True
+            f, lf = bridge.voca_trans_project(md, x.to(dev), lens.to(dev), table, do_psd, top1, blank_id=Vh - 1)
+    finally:
+        bridge.FUSED_VOCA_TRANS = saved
+    assert torch.equal(la, lf) and a.shape == f.shape
+    if top1:
+        assert (a.float() - f.float()).abs().max().item() == 0.0 or \
+            ((a.float() - f.float()).abs().amax(-1) > 0).float().mean().item() < 0.02    # ties of near-equal logits
+    else:
+        assert ((a - f).norm() / a.norm()).item() < 1e-2
+        pad = torch.arange(a.shape[1], device=dev)[None, :] >= la[:, None]
+        if do_psd and bool(pad.any()):
+            assert ((a[pad] - f[pad]).abs().max().item()) < 2e-3
