@@ -630,7 +630,8 @@ class TasuBridge:
         return st
 
     def _weight_params(self):
-        return [self.w_ctc, self.b_ctc] + [p for p in self.projector.parameters()][:6]
+        fast = getattr(self.projector, "weight_params", None)  # direct attribute access: walking the module tree costs ~10 us
+        return [self.w_ctc, self.b_ctc] + (fast() if fast is not None else [p for p in self.projector.parameters()][:6])
 
     def _cache_builds(self):
         return self._ctc_cache.builds + self._ctc_exact_cache.builds + self.projector._cache.builds

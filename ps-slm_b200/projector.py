@@ -104,12 +104,16 @@ class EncoderProjectorLinearSiLU(_CachedWeightsModule):
         ops.gemm_fp32x3(hs, w2s, N, H, kh, y, L.EPI_BIAS, b2)
         return y
 
+    def weight_params(self):
+        """The six parameters in ``parameters()`` order, by direct attribute access (per-call host path)."""
+        l1, l2 = self.ffn[0], self.ffn[2]
+        return [self.norm.weight, self.norm.bias, l1.weight, l1.bias, l2.weight, l2.bias]
+
     def folded_weights(self, verify: bool = False):
         """(W1·γ bf16 [2048, pad64(in)], colsum, W1β+b1, W2 bf16, b2 fp32), cached (see ProjectorCache).
         ``verify``: check the copy against the live parameters' fingerprint (TasuBridge does that itself, piggybacked
         on its header read)."""
-        params = [self.norm.weight, self.norm.bias, self.ffn[0].weight, self.ffn[0].bias,
-                  self.ffn[2].weight, self.ffn[2].bias]
+        params = self.weight_params()
 
         def build():
             with torch.no_grad():
