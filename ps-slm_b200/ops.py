@@ -30,6 +30,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _rows(dev, dtype, n: int, k: int):
+    """``k`` arrays of ``n`` 4-byte elements from ONE allocation when every row stays 16-byte aligned (the per-call host
+    path is allocation- and launch-bound at small batches: one ``torch.empty`` + one ``unbind`` instead of ``k`` calls)."""
+    if n % 4 == 0 and n > 0:
+        return torch.empty((k, n), dtype=dtype, device=dev).unbind(0)
+    return tuple(torch.empty(max(n, 1), dtype=dtype, device=dev) for _ in range(k))
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return L.F32
@@ -112,11 +120,8 @@ def ctc_head_stats(x_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[to
     dev = x_bf16.device
     st = FrameStats()
     st.kind, st.B, st.T = L.INPUT_LOGITS, B, T
+    st.x_blank, st.row_max, st.row_sumexp, st.row_sumexp2 = _rows(dev, torch.float32, B * T, 4)
     st.argmax = torch.empty(B * T, dtype=torch.int32, device=dev)
-    st.x_blank = torch.empty(B * T, dtype=torch.float32, device=dev)
-    st.row_max = torch.empty(B * T, dtype=torch.float32, device=dev)
-    st.row_sumexp = torch.empty(B * T, dtype=torch.float32, device=dev)
-    st.row_sumexp2 = torch.empty(B * T, dtype=torch.float32, device=dev)
     st.gmax = torch.empty(1, dtype=torch.int32, device=dev)
     nbytes = L.lib().tasu_ctc_head_stats_workspace(B, T, n_prefix)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -237,13 +242,10 @@ def gather_kept_rows(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int
     ldg = pad_to(K)
     cap = (max(n_frames, 1) + 2047) // 2048 * 2048          # few distinct sizes → allocator cache hits
     xg = torch.empty(cap, ldg, dtype=torch.bfloat16, device=dev)[:max(n_frames, 1)]
-    g_max = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
-    g_inv = torch.empty(max(n_frames, 1), dtype=torch.float32, device=dev)
-    pk_len = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
-    tail_src = torch.empty(max(n_out, 1), dtype=torch.int32, device=dev)
+    g_max, g_inv = _rows(dev, torch.float32, n_frames, 2)
+    pk_len, tail_src = _rows(dev, torch.int32, n_out, 2)
     multi = torch.empty(max(n_out, 1) + 1, dtype=torch.int32, device=dev)       # [0] = count, [1:] = row list
-    mean = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
-    rstd = torch.empty(max(n_out, 1), dtype=torch.float32, device=dev)
+    mean, rstd = _rows(dev, torch.float32, n_out, 2)
     L.check(L.lib().tasu_gather_kept_rows(x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K, V,
                                           plan.seg_start.data_ptr(), plan.seg_len.data_ptr(), plan.seg_foff.data_ptr(),
                                           plan.row_off.data_ptr(), plan.frame_off.data_ptr(), st.row_max.data_ptr(),
@@ -306,12 +308,10 @@ def collapse_plan(st: FrameStats, lens: torch.Tensor, blank_id: int, threshold: 
     lens = lens.to(device=dev, dtype=torch.int64).contiguous()
     p = CollapsePlan()
     p.B, p.T = B, T
-    p.seg_start = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
-    p.seg_len = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
+    p.seg_start, p.seg_len, p.seg_foff = _rows(dev, torch.int32, B * T, 3)
     p.seg_score = torch.empty(max(B * T, 1), dtype=torch.float32, device=dev) if want_scores else None
     p.new_lens = torch.empty(B, dtype=torch.int64, device=dev)
     p.kept_frames = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
-    p.seg_foff = torch.empty(max(B * T, 1), dtype=torch.int32, device=dev)
     p.frame_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     p.counts = torch.empty(4, dtype=torch.int32, device=dev)       # {N_out, max_len, kept_frames, 0} for device-side M
     p.row_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
