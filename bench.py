@@ -721,6 +721,10 @@ def b200_arm(args):
         "projector_gemm2": ("tensor", 2.0 * n_out * Hb * H),
         "splice_scatter": ("hbm", (n_out + n_text + B * sp_len) * H * 2.0 + B * sp_len * 17.0),
     }
+    if getattr(bridge, "grouped_pool", False):
+        # grouped kept-frame layout: runs of 2-4 frames are averaged inside the kept-frame GEMM's epilogue; pool_tail only
+        # sees runs of more than 4 frames (n_multi counts those) — no roofline line for a launch that moves next to nothing
+        algo.pop("pool_tail")
     # Denominators (MEASURED_PEAKS.json): the timed regions here are K steps ≈ tens of milliseconds — a burst, clocks near
     # maximum — so tensor-bound kernels are held against the BURST cuBLAS bf16 rate; the sustained figure is quoted beside
     # it and used for the >= 3 s loop below.
@@ -775,7 +779,10 @@ def b200_arm(args):
                    "spliced_len": sp_len, "parallelism": "utterance-sharded dp%d, no data-path collective in the headline step "
                                                          "(the path's two exchange steps are timed in `comm`)" % world,
                    "streams": args.streams, "kept_frames_per_step": f_kept, "exact_decisions": bool(args.exact_decisions),
-                   "frames_refined_in_fp32_last_step": n_ambiguous, "multi_frame_candidates_per_step": n_multi,
+                   "frames_refined_in_fp32_last_step": n_ambiguous,
+                   "grouped_pool": bool(getattr(bridge, "grouped_pool", False)),
+                   ("runs_longer_than_4_frames_per_step" if getattr(bridge, "grouped_pool", False)
+                    else "multi_frame_candidates_per_step"): n_multi,
                    "encoder_out_dtype": "bf16" if args.host_bf16 else "f32",
                    "gemm": {"deep_k": ("one CTA per tile" if args.no_pair_gemm else "CTA pairs (cta_group::2)") + ("" if args.no_streamk else ", stream-K last wave (GEMM-1)")},
                    "path": "materialized fp32 logits" if args.materialize_logits else "fused ctc_lo+stats, recompute kept frames",

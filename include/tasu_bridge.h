@@ -182,6 +182,53 @@ int tasu_pool_tail(void* probs_bf16, int64_t ld, int D, int64_t n_out, int64_t m
                    float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Step 2b', grouped layout — the mean over the frames of a run (ps-slm.py:286) taken INSIDE the epilogue of the
+ * kept-frame softmax GEMM: the per-frame probabilities of runs of 2-4 frames never reach HBM.  The frames of a run lie
+ * on adjacent rows of the GEMM's A operand (= adjacent TMEM lanes = adjacent threads of one epilogue warp), runs of
+ * one size class fill whole 128-row tiles:
+ *   S  (1 frame)     1 row per candidate, A rows [0, NS);  pooled row = A row
+ *   G2 (2 frames)    2 rows per candidate from A row A2;   pooled rows from A2 (a tile stores 64 pooled rows)
+ *   G4 (3-4 frames)  4 rows per candidate from A row A4 (3-frame runs carry a zero row of weight 0); pooled rows from O4
+ *   X  (> 4 frames)  first frame among the S rows, extra frames from A row AX → per-frame probabilities from output row
+ *                    OX, averaged by tasu_pool_tail as in the plain layout (pk_len / tail_src / multi_rows by pooled row)
+ * A2, A4, AX are multiples of 128; filler rows are zero rows of weight 0.  Pooled rows [0, OX) are what the projector
+ * consumes (holes included: at most 127 + 63 + 31 rows); perm[r] = pooled row of packed candidate r.
+ * Layout words (device int32 [TASU_GL_WORDS], written by tasu_group_plan): */
+enum { TASU_GL_A2 = 0, TASU_GL_A4 = 1, TASU_GL_AX = 2,
+       TASU_GL_A_ROWS = 3,        /* A rows in total = live M of the GEMM */
+       TASU_GL_O4 = 4, TASU_GL_OX = 5,
+       TASU_GL_N2 = 6, TASU_GL_N4 = 7, TASU_GL_NS = 8 /* S and X candidates */, TASU_GL_NXE = 9 /* extra frames of X */,
+       TASU_GL_WORDS = 16 };
+/* slot / xoff [B*T] (indexed like seg_len): index of a candidate inside its class within its utterance / its first extra
+ * frame; cnt / base [4*B]: per-utterance class counts and their exclusive scans; ticket: int32 zero-initialised once. */
+int tasu_group_plan(const int32_t* seg_len, const int64_t* new_lens, int B, int T, int32_t* slot, int32_t* xoff,
+                    int32_t* cnt, int32_t* base, int32_t* lay, int32_t* ticket, void* stream);
+/* Copies the kept frames' encoder rows into the grouped A matrix xg [max_a, ldg] with their softmax scalars
+ * (g_inv = 1 / (sum exp * frames averaged in the epilogue); 0 marks a row of weight 0), writes perm [max_out], the
+ * LayerNorm statistics of single-frame rows and pool_tail's work list for class X.  max_o = rows of the pooled matrix
+ * and of pk_len / tail_src / ln_mean / ln_rstd, max_proj = pooled rows the projector's buffers hold (perm = -1 for a
+ * candidate beyond it and for entries [N_out, max_out): "zero row" of tasu_gather_rows).  Capacities bound every write. */
+int tasu_gather_kept_rows_grouped(const void* x_bf16, int64_t ldx, int B, int T, int n_prefix, int K, int V,
+                                  const int32_t* seg_start, const int32_t* seg_len, const int32_t* row_off,
+                                  const int32_t* slot, const int32_t* xoff, const int32_t* base, const int32_t* lay,
+                                  const float* row_max, const float* row_sumexp, const float* row_sumexp2,
+                                  int64_t max_a, int64_t max_o, int64_t max_out, int64_t max_proj, void* xg_bf16, int64_t ldg,
+                                  float* g_max, float* g_inv, int32_t* perm, int32_t* pk_len, int32_t* tail_src,
+                                  int32_t* multi_rows, int32_t* multi_count, float* ln_mean, float* ln_rstd,
+                                  float ln_eps, void* stream);
+/* The kept-frame softmax GEMM on the grouped layout: C = pooled probabilities (bf16) [c_rows, ldc]; A [a_rows, lda] bf16,
+ * B = W_ctc [N, K] bf16, K <= 1024.  row_inv / row_max [a_rows] as written by tasu_gather_kept_rows_grouped.
+ * q_part [n_parts][ldq] fp32 with n_parts = tasu_gemm_softmax_grouped_parts(N): partial sums of p^2 of the pooled rows of
+ * the G regions (row index relative to A2), one per (column tile, epilogue group), every element written exactly once
+ * (no atomics) — tasu_group_ln_finish adds them in a fixed order and writes the LayerNorm statistics of those rows. */
+int tasu_gemm_softmax_grouped_parts(int N);
+int tasu_gemm_softmax_grouped(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int a_rows,
+                              int c_rows, int N, int K, const float* bias, const float* row_inv, const float* row_max,
+                              const int32_t* lay, float* q_part, int64_t ldq, void* stream);
+int tasu_group_ln_finish(const float* q_part, int64_t ldq, int n_parts, const int32_t* lay, int V, int64_t max_o,
+                         float* ln_mean, float* ln_rstd, float ln_eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Step 2c — segmented mean-pool of the kept candidates (ps-slm.py:275-287, :290, :297,
  * :303-314).  feats is a [B, T, D] view (same tensor as the posterior on the default path).
  *   softmax_max/softmax_sumexp: NULL → pool feats as given; else feats are logits and
@@ -493,6 +540,19 @@ int tasu_splice_scatter(const int64_t* input_ids, const void* attention_mask, in
                         int64_t* out_ids, int64_t* row_src_ws /*[B*S'] scratch: source of every output row*/,
                         int32_t* audio_dest /*optional: output row of every audio row; caller pre-fills -1*/,
                         void* stream);
+/* The same with the audio rows stored in permuted order (grouped kept-frame layout, step 2b'): audio row r of the packed
+ * layout (audio_layout 0) is read from row audio_perm[r] of audio_rows (< 0: zero row).  row_src_ws / audio_dest keep
+ * referring to the packed row r, so the backward is unchanged.  audio_perm = NULL: tasu_splice_scatter. */
+int tasu_splice_scatter_perm(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                             const int64_t* labels, int B, int S, int spliced_len, int H, int64_t speech_id,
+                             const void* text_src, int text_mode, int64_t text_row_stride,
+                             const void* audio_rows, const int32_t* audio_perm, int audio_layout,
+                             int64_t audio_row_stride, int64_t audio_max_len, int n_audio, int emb_dtype,
+                             const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
+                             const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
+                             int left_padding, int64_t pad_id, int64_t ignore_id,
+                             void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
+                             int64_t* out_ids, int64_t* row_src_ws, int32_t* audio_dest, void* stream);
 /* dst[r,:] = idx[r] >= 0 ? src[idx[r],:] : 0.  With idx = audio_dest of tasu_splice_scatter and src = the gradient of
  * inputs_embeds this is the backward of the audio part of the splice (index_put of ps-slm.py:867-869; training). */
 int tasu_gather_rows(const void* src, int dtype, int64_t src_row_stride, const int32_t* idx, int64_t n_rows, int H,

@@ -20,6 +20,8 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_RELU, EPI_LNFOLD_SILU, EPI_LNFOLD, E
 SH_SPLICED_LEN, SH_LEFT_PADDING, SH_ERR_BOTH_SIDES, SH_TOTAL_SLOTS, SH_TOTAL_AUDIO, SH_N_SPEECH, SH_WORDS = 0, 1, 2, 3, 4, 5, 8
 CH_N_OUT, CH_MAX_LEN, CH_IS_LOGPROB, CH_KEPT_FRAMES, CH_WORDS = 0, 1, 2, 3, 4
 OPT_GEMM_PAIR, OPT_COUNT = 0, 1     # run-time options (tasu_set_option)
+# layout words of the grouped kept-frame layout (tasu_group_plan)
+GL_A2, GL_A4, GL_AX, GL_A_ROWS, GL_O4, GL_OX, GL_N2, GL_N4, GL_NS, GL_NXE, GL_WORDS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16
 
 # name -> (restype, argtypes); mirrors include/tasu_bridge.h one to one
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
@@ -42,6 +44,12 @@ SIGNATURES = {
                                    _P, _P, _P, _P, _P, _P, _F, _P]),
     "tasu_kept_frame_index": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P]),
     "tasu_pool_tail": (_I, [_P, _L, _I, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "tasu_group_plan": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_gather_kept_rows_grouped": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L,
+                                           _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "tasu_gemm_softmax_grouped_parts": (_I, [_I]),
+    "tasu_gemm_softmax_grouped": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
+    "tasu_group_ln_finish": (_I, [_P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_segment_meanpool": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_sim_posterior_rows": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _L, _P, _P, _F, _P]),
     "tasu_fingerprint": (_I, [_P, _P, _I, _P, _P]),
@@ -86,6 +94,8 @@ SIGNATURES = {
     "tasu_splice_plan_header": (_I, [_P, _P, _I, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_splice_scatter": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _L, _L, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tasu_splice_scatter_perm": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _P, _I, _L, _L, _I, _I,
+                                      _P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tasu_flat_scale_cast": (_I, [_P, _I, _P, _I, _L, _F, _P]),
     "tasu_packed_select": (_I, [_P, _I, _L, _L, _I, _P, _I, _I, _L, _P, _I, _P, _L, _L, _P, _P, _P, _P]),
     "tasu_splice_text_grad": (_I, [_P, _I, _L, _P, _L, _I, _P, _L, _L, _P]),

@@ -507,6 +507,9 @@ class TasuBridge:
         self._ctc_split_cache = ProjectorCache()
         # projector GEMM-1 with the stream-K tail (default; TASU_GEMM_STREAMK=0 selects the plain persistent kernel)
         self.streamk_gemm1 = os.environ.get("TASU_GEMM_STREAMK", "1") != "0"
+        # Grouped kept-frame layout (default; TASU_GROUPED_POOL=0 selects the plain layout + tail pooling): runs of 2-4
+        # frames are averaged inside the epilogue of the kept-frame GEMM (csrc/grouped.cu)
+        self.grouped_pool = os.environ.get("TASU_GROUPED_POOL", "1") != "0"
         self.profile = False          # when True, CUDA events bracket every stage (bench roofline)
         self.events = []              # [(stage name, start event, end event)] of the profiled calls
 
@@ -532,8 +535,38 @@ class TasuBridge:
             ops.pool_tail(pooled, V, cap_o, pk_len, tail_src, multi, mean, rstd, self.ln_eps)
         return pooled, mean, rstd
 
-    def _tail(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2, out_dtype):
-        """Pass 2 + projector (GEMM-1 with the LayerNorm folded in, GEMM-2) on capacity-sized buffers."""
+    def _pool_kept_grouped(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, max_proj):
+        """Pass 2 on the grouped layout (include/tasu_bridge.h, step 2b'): the frames of a run of 2-4 frames sit on adjacent
+        rows of the kept-frame GEMM and are averaged in its epilogue — their per-frame probabilities are never written,
+        ``pool_tail`` only sees runs of more than 4 frames.  Pooled rows come out in class order (``g.perm``: packed
+        candidate → pooled row).  → (pooled bf16 [cap_a, pad64(V)], GroupedRows)."""
+        with self._stage("gather_kept_rows"):
+            g = ops.gather_kept_rows_grouped(x2, B, T, self.N_PREFIX, Denc, V, plan, st, cap_f, cap_o, max_proj, self.ln_eps)
+        self.last_multi = g.multi[0:1]    # device int32[1]: runs of more than 4 frames (pool_tail's work list)
+        pooled = torch.empty(g.cap_p, ops.pad_to(V), dtype=torch.bfloat16, device=x2.device)
+        with self._stage("ctc_softmax_gemm"):
+            ops.gemm_softmax_grouped(g, w_ctc, b_ctc, V, Denc, pooled, self.ln_eps)
+        with self._stage("pool_tail"):
+            ops.pool_tail(pooled, V, min(cap_o, 1024), g.pk_len, g.tail_src, g.multi, g.mean, g.rstd, self.ln_eps)
+        return pooled, g
+
+    def _tail(self, x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2, out_dtype,
+              keep_perm=False):
+        """Pass 2 + projector (GEMM-1 with the LayerNorm folded in, GEMM-2) on capacity-sized buffers → audio rows in
+        packed candidate order; with ``keep_perm`` (grouped layout) → ``(rows in class order, perm)`` for a consumer that
+        reads through the permutation itself (the splice)."""
+        if self.grouped_pool:
+            rows = cap_o + 256                                          # pooled rows incl. the holes between the classes
+            pooled, g = self._pool_kept_grouped(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, rows)
+            y = linear_silu_forward(pooled, rows, V, g.mean, g.rstd, w1g, colsum, dbias, w2, b2, out_dtype,
+                                    stage=self._stage, m_dev=g.lay[L.GL_OX:L.GL_OX + 1], streamk=self.streamk_gemm1)
+            if keep_perm:
+                return y, g.perm[:cap_o]
+            with self._stage("unpermute_rows"):
+                return ops.gather_rows(y, g.perm[:cap_o])               # back to packed candidate order
+        if keep_perm:
+            return self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2,
+                              out_dtype), None
         pooled, mean, rstd = self._pool_kept(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc)
         return linear_silu_forward(pooled, cap_o, V, mean, rstd, w1g, colsum, dbias, w2, b2, out_dtype,
                                    stage=self._stage, m_dev=plan.counts[0:1], streamk=self.streamk_gemm1)
@@ -704,7 +737,7 @@ class TasuBridge:
             ops.splice_plan(sp, plan.new_lens, self.projector.k, header=header[L.CH_WORDS:])
         ev = torch.cuda.Event()
         ev.record()                                                     # header is complete when this event fires
-        audio_cap, cap_f, cap_o = None, 0, 0
+        audio_cap, audio_perm, cap_f, cap_o = None, None, 0, 0
         fp32 = self.precision == "fp32x3" and not self.materialize_logits
         caps = None if (self.materialize_logits or fp32) else self._speculative_capacity(B, T)
         if caps is not None:
@@ -712,8 +745,8 @@ class TasuBridge:
             # (high-water mark of earlier calls) and every kernel takes its live row count from device memory, so the
             # GPU never idles waiting for the host.
             cap_f, cap_o = caps
-            audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias, w2, b2,
-                                   out_dtype)
+            audio_cap, audio_perm = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias,
+                                               w2, b2, out_dtype, keep_perm=True)
         ev.synchronize()                                                # the single device→host hand-off
         hdr = header.clone()
         if not self._check_fingerprint(int(hdr[L.CH_WORDS + L.SH_WORDS]), builds_before):
@@ -742,16 +775,17 @@ class TasuBridge:
             if audio_cap is None or n_frames > cap_f or n_out > cap_o:
                 # first batch of this shape, or capacity exceeded (rare): the tail runs now, sized exactly
                 cap_f, cap_o = _cap(n_frames), _cap(n_out)
-                audio_cap = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum, dbias,
-                                       w2, b2, out_dtype)
+                audio_cap, audio_perm = self._tail(x2, st, plan, B, T, Denc, V, cap_f, cap_o, w_ctc, b_ctc, w1g, colsum,
+                                                   dbias, w2, b2, out_dtype, keep_perm=True)
             hw_f, hw_o = self._capacity.get((B, T), (0, 0))
             self._capacity[(B, T)] = (max(hw_f, n_frames), max(hw_o, n_out))
-            audio = audio_cap[:n_out]
+            # grouped layout: the rows stay in class order, the splice reads them through the permutation
+            audio = audio_cap if audio_perm is not None else audio_cap[:n_out]
         # (a7+a8) splice with the embedding lookup fused
         with self._stage("splice_scatter"):
             emb, mask, out_labels, pos, fids = ops.splice_scatter(
                 sp, spliced_len, self.embed_table, 1, audio, 0, max_len, labels, self.pad_id, self.ignore_id,
-                want_ids=want_ids, left_padding=int(shdr[L.SH_LEFT_PADDING]))
+                want_ids=want_ids, left_padding=int(shdr[L.SH_LEFT_PADDING]), audio_perm=audio_perm)
         self.last_counts = {"n_in": int(B * T), "n_out": n_out, "max_len": max_len, "spliced_len": spliced_len,
                             "kept_frames": int(hdr[L.CH_KEPT_FRAMES])}
         return emb, mask, out_labels, pos, plan.new_lens

@@ -215,6 +215,17 @@ struct Params {
     const float* colsum;
 };
 
+// extra kernel arguments of the grouped softmax GEMM (gemm_bf16_tn_kernel<..., kGrouped = true>; csrc/grouped.cu)
+struct alignas(64) GroupedArgs {
+    CUtensorMap c2, c4;       // the C matrix with 64- / 32-row store boxes (tiles of 2- / 4-frame groups)
+    const int32_t* lay;       // layout words (TASU_GL_*)
+    float* q_part;            // [n_tiles * groups][ldq] partial sums of p^2 of the pooled rows, row index relative to A2
+    int64_t ldq;
+};
+struct NoGroupedArgs { int unused; };
+template <bool kGrouped> struct GroupedSel { typedef NoGroupedArgs type; };
+template <> struct GroupedSel<true> { typedef GroupedArgs type; };
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

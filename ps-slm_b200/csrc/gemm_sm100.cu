@@ -35,13 +35,18 @@ namespace gemm {
 //        (profiles/r02a_ab.md); for K <= 1024 the pair kernel measured 11 % SLOWER and is not instantiated.
 // Variants measured and removed in round 2 (profiles/r02a_ab.md): epilogue vectors of the next tile prefetched (no
 // change for the kept-frame softmax GEMM), 16 independent epilogue warps with warp-private TMA stores (+6 % time).
-template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false>
+// kGrouped (kept-frame softmax GEMM on the grouped layout, csrc/grouped.cu): the rows of a 2- / 4-row group are the
+//        frames of one run; the epilogue adds their probabilities across adjacent lanes (warp shuffles, recursive halving)
+//        and a tile stores 64 / 32 pooled rows through the tensor maps with 64- / 32-row boxes in `ga`.
+template <bool kOutBf16, int kEpi, int kSt, int kGroups, int kMajor = 0, bool kPair = false, bool kGrouped = false>
 __global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const Params p,
+                    const __grid_constant__ typename GroupedSel<kGrouped>::type ga) {
     extern __shared__ __align__(1024) uint8_t smem[];          // 128B-swizzle atoms need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();               // no static shared memory in this kernel → offset 0
     static_assert(!kPair || kMajor == 0, "pair mode: K-major operands only");
+    static_assert(!kGrouped || (kEpi == TASU_EPI_SOFTMAX && kOutBf16 && !kPair && kMajor == 0), "grouped: bf16 softmax epilogue only");
     constexpr int kStages = kSt;
     constexpr int kStgBytes = kPair ? kPairStageBytes : kStageBytes;               // A 16 KB + B 32 KB (pair: 16 KB)
     constexpr int kTileM = kPair ? 2 * BM : BM;                                    // rows of C per work item
@@ -66,6 +71,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_c);
+        if constexpr (kGrouped) { prefetch_tmap(&ga.c2); prefetch_tmap(&ga.c4); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -205,8 +211,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
             if (first < num_tiles) fetch_vectors(first);
         }
+        // grouped layout: region boundaries (A rows / pooled rows), constant during the launch
+        int gl_a2 = 0, gl_a4 = 0, gl_ax = 0, gl_o4 = 0, gl_ox = 0;
+        if constexpr (kGrouped) {
+            gl_a2 = __ldg(ga.lay + TASU_GL_A2); gl_a4 = __ldg(ga.lay + TASU_GL_A4); gl_ax = __ldg(ga.lay + TASU_GL_AX);
+            gl_o4 = __ldg(ga.lay + TASU_GL_O4); gl_ox = __ldg(ga.lay + TASU_GL_OX);
+        }
         TASU_TILE_LOOP {
             const int m0 = TASU_TILE_M0, n0 = (tile % n_tiles) * BN;
+            // rows per group of this tile (1: one output row per accumulator row) and its first output row
+            int grp_rows = 1, out0 = m0;
+            float q_acc = 0.f;                                     // sum of p^2 over this thread's pooled columns
+            if constexpr (kGrouped) {
+                if (m0 >= gl_ax) out0 = gl_ox + (m0 - gl_ax);
+                else if (m0 >= gl_a4) { grp_rows = 4; out0 = gl_o4 + ((m0 - gl_a4) >> 2); }
+                else if (m0 >= gl_a2) { grp_rows = 2; out0 = gl_a2 + ((m0 - gl_a2) >> 1); }
+            }
             // per-column vectors of this tile → shared memory (read back as broadcast LDS.128).
             // Safe to overwrite: every read of the previous tile happened before its last bar.sync.
             if (kEpi != TASU_EPI_NONE) {
@@ -225,7 +245,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             // softmax: p = exp(acc + bias - max) / sum = 2^(acc*log2e + bias*log2e + rowc), rowc = -max*log2e + log2(1/sum):
             // one FADD + one FFMA + one MUFU.EX2 per element
-            const float rowc = kEpi == TASU_EPI_SOFTMAX ? fmaf(nmean, kLog2e, __log2f(fmaxf(rstd, 1e-37f))) : 0.f;
+            // grouped: 1/sum carries the 1/frames weight of the mean; a row of weight 0 (filler) yields exact zeros
+            const float rowc = kEpi != TASU_EPI_SOFTMAX ? 0.f
+                             : (kGrouped && !(rstd > 0.f)) ? -INFINITY
+                             : fmaf(nmean, kLog2e, __log2f(fmaxf(rstd, 1e-37f)));
             const int n_chunks = min(BN / kColsPerChunk, (p.N - n0 + kColsPerChunk - 1) / kColsPerChunk);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -275,7 +298,59 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 4; ++e) f[4 * q + e] = x[e];
                 }
-                if (kOutBf16) {
+                if (kGrouped && grp_rows > 1) {
+                    // The frames of a run are adjacent accumulator rows = adjacent lanes: recursive halving — after the
+                    // exchange with lane^1 a lane holds the 2-frame sums of 16 columns (even lanes the lower half of the
+                    // slab), after the exchange with lane^2 the 4-frame sums of 8 columns.  Every lane of a group adds
+                    // the same values in an order that differs only by commutation: the result is deterministic.
+                    const bool odd = (lane & 1) != 0, hi2 = (lane & 2) != 0;
+                    float keep[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[k] : f[16 + k], 1);
+                        keep[k] = (odd ? f[16 + k] : f[k]) + recv;
+                    }
+                    int col = n0 + sub * 32 + (odd ? 16 : 0);      // first column this lane keeps
+                    if (grp_rows == 2) {
+                        const int prow = et >> 1;
+                        const uint32_t prow_addr = stg_u32 + (uint32_t)(sbuf * kStagingBytes + prow * 128);
+                        const int piece = h * 4 + (odd ? 2 : 0), psw = prow & 7;
+                        st_shared_u4(prow_addr + (uint32_t)((piece ^ psw) * 16),
+                                     pack_bf16x2(keep[0], keep[1]), pack_bf16x2(keep[2], keep[3]),
+                                     pack_bf16x2(keep[4], keep[5]), pack_bf16x2(keep[6], keep[7]));
+                        st_shared_u4(prow_addr + (uint32_t)(((piece + 1) ^ psw) * 16),
+                                     pack_bf16x2(keep[8], keep[9]), pack_bf16x2(keep[10], keep[11]),
+                                     pack_bf16x2(keep[12], keep[13]), pack_bf16x2(keep[14], keep[15]));
+                        if (n0 + BN <= p.N) {                      // only the last column tile has columns beyond N
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) q_acc = fmaf(keep[k], keep[k], q_acc);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) if (col + k < p.N) q_acc = fmaf(keep[k], keep[k], q_acc);
+                        }
+                    } else {
+                        float k4[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float recv = __shfl_xor_sync(0xffffffffu, hi2 ? keep[k] : keep[8 + k], 2);
+                            k4[k] = (hi2 ? keep[8 + k] : keep[k]) + recv;
+                        }
+                        col += hi2 ? 8 : 0;
+                        const int prow = et >> 2;
+                        const uint32_t prow_addr = stg_u32 + (uint32_t)(sbuf * kStagingBytes + prow * 128);
+                        const int piece = h * 4 + (odd ? 2 : 0) + (hi2 ? 1 : 0), psw = prow & 7;
+                        st_shared_u4(prow_addr + (uint32_t)((piece ^ psw) * 16),
+                                     pack_bf16x2(k4[0], k4[1]), pack_bf16x2(k4[2], k4[3]),
+                                     pack_bf16x2(k4[4], k4[5]), pack_bf16x2(k4[6], k4[7]));
+                        if (n0 + BN <= p.N) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) q_acc = fmaf(k4[k], k4[k], q_acc);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) if (col + k < p.N) q_acc = fmaf(k4[k], k4[k], q_acc);
+                        }
+                    }
+                } else if (kOutBf16) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)        // 32 columns → 64 bytes → 16-byte pieces 4h .. 4h+3
                         st_shared_u4(srow + (uint32_t)((((h * 4 + q) ^ sw)) * 16),
@@ -292,7 +367,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(kEpiThreads) : "memory");
                     if (et == 0) {
                         // pair mode: the upper CTA's 128 rows may lie entirely beyond the last row
-                        if (!kPair || m0 < p.M) tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        if constexpr (kGrouped) {
+                            // 128 / 64 / 32 rows of the staging tile → pooled rows from out0
+                            const CUtensorMap* cmap = grp_rows == 1 ? &tmap_c : (grp_rows == 2 ? &ga.c2 : &ga.c4);
+                            tma_store_2d(cmap, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, out0);
+                        } else if (!kPair || m0 < p.M) {
+                            tma_store_2d(&tmap_c, gstaging + sbuf * kStagingBytes, n0 + ch * kColsPerChunk, m0);
+                        }
                         tma_store_commit();
                     }
                     sbuf ^= 1;
@@ -318,6 +399,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     else mbar_arrive(&tmem_empty[acc]);
                 }
                 process(vb, sub_of(it + 1));
+            }
+            if constexpr (kGrouped) {
+                if (grp_rows > 1) {
+                    // sum of p^2 of a pooled row over the columns this epilogue group handled in this column tile
+                    q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 1);
+                    if (grp_rows == 4) q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 2);
+                    const int64_t qrow = (int64_t)out0 + et / grp_rows - gl_a2;
+                    if ((et & (grp_rows - 1)) == 0 && qrow < ga.ldq)
+                        ga.q_part[((int64_t)(tile % n_tiles) * kGroups + grp) * ga.ldq + qrow] = q_acc;
+                }
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
@@ -381,7 +472,7 @@ static int launch_one(int grid, cudaStream_t st, const CUtensorMap& ma, const CU
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
     TASU_CHECK_CUDA(attr_err);
-    gemm_bf16_tn_kernel<kOutBf16, kEpi, kSt, kGroups><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p);
+    gemm_bf16_tn_kernel<kOutBf16, kEpi, kSt, kGroups><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p, NoGroupedArgs{0});
     return TASU_OK;
 }
 
@@ -435,7 +526,7 @@ static int launch_pair_one(int clusters, cudaStream_t st, const CUtensorMap& ma,
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    TASU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p, NoGroupedArgs{0}));
     return TASU_OK;
 }
 
@@ -466,7 +557,7 @@ static int launch_major(int grid, cudaStream_t st, const CUtensorMap& ma, const 
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
     TASU_CHECK_CUDA(attr_err);
-    gemm_bf16_tn_kernel<false, TASU_EPI_NONE, kSt, kGroups, kMajor><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p);
+    gemm_bf16_tn_kernel<false, TASU_EPI_NONE, kSt, kGroups, kMajor><<<grid, 128 + 128 * kGroups, smem, st>>>(ma, mb, mc, p, NoGroupedArgs{0});
     return TASU_OK;
 }
 
@@ -549,6 +640,46 @@ extern "C" int tasu_gemm_bf16_tn(const void* A, int64_t lda, const void* B, int6
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_dispatch(c_dtype == TASU_BF16, epilogue, K <= 1024, grid, st, ma, mb, mc, p);
     if (rc) return rc;
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+// The kept-frame softmax GEMM on the grouped layout (csrc/grouped.cu): shallow-K shape (3 stages, two epilogue groups)
+extern "C" int tasu_gemm_softmax_grouped_parts(int N) { return ((N + BN - 1) / BN) * 2; }
+
+extern "C" int tasu_gemm_softmax_grouped(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int a_rows,
+                                         int c_rows, int N, int K, const float* bias, const float* row_inv, const float* row_max,
+                                         const int32_t* lay, float* q_part, int64_t ldq, void* stream) {
+    TASU_CHECK_ARG(a_rows > 0 && c_rows > 0 && N > 0 && K > 0 && K <= 1024, "a_rows, c_rows, N > 0, 0 < K <= 1024");
+    TASU_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && ldq > 0, "leading dimension too small");
+    TASU_CHECK_ARG(A && B && C && bias && row_inv && row_max && lay && q_part, "null pointer");
+    TASU_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "base pointers must be 16-byte aligned");
+    TASU_CHECK_ARG((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0 && (ldc * 2) % 16 == 0, "row pitches must be multiples of 16 bytes");
+    CUtensorMap ma, mb, mc;
+    GroupedArgs ga;
+    int rc = make_map(&ma, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_rows, K, lda, BM, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+    rc = make_map(&mb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    rc = make_map(&mc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c_rows, N, ldc, BM, 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    rc = make_map(&ga.c2, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c_rows, N, ldc, BM / 2, 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    rc = make_map(&ga.c4, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c_rows, N, ldc, BM / 4, 64, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    ga.lay = lay; ga.q_part = q_part; ga.ldq = ldq;
+    Params p{a_rows, N, K, lay + TASU_GL_A_ROWS, TASU_EPI_SOFTMAX, bias, row_inv, row_max, nullptr};
+    const int tiles = ((a_rows + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    constexpr int kSt = 3, kGroups = 2;
+    constexpr int smem = gemm_smem_bytes(kSt, kGroups);
+    auto kern = gemm_bf16_tn_kernel<true, TASU_EPI_SOFTMAX, kSt, kGroups, 0, false, true>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    TASU_CHECK_CUDA(attr_err);
+    kern<<<grid, 128 + 128 * kGroups, smem, (cudaStream_t)stream>>>(ma, mb, mc, p, ga);
     TASU_CHECK_LAUNCH();
     return TASU_OK;
 }

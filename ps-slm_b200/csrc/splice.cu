@@ -276,6 +276,7 @@ struct ScatterArgs {
     int B, S, Sp, H;
     const void* text_src; int text_mode; int64_t text_stride;
     const void* audio; int audio_layout; int64_t audio_stride; int64_t audio_max_len; int n_audio;
+    const int32_t* audio_perm;       // optional: audio row r is stored at row audio_perm[r] of `audio` (< 0: zero row)
     const int32_t* rowstat; const int32_t* new_pos; const int32_t* text_prefix; const int32_t* slot_ord;
     const int32_t* slot_base; const int32_t* audio_off; int left_padding;
     int64_t speech, pad_id, ignore_id;
@@ -368,7 +369,13 @@ splice_fused_kernel(ScatterArgs a, int64_t* __restrict__ row_src, int32_t* __res
     const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFusedRows;
     if (row0 >= n_rows) return;                                             // warp-uniform
     int64_t mine = -1;
-    if (lane < kFusedRows && row0 + lane < n_rows) mine = rowmap_one(a, row0 + lane, row_src, audio_dest);
+    if (lane < kFusedRows && row0 + lane < n_rows) {
+        mine = rowmap_one(a, row0 + lane, row_src, audio_dest);
+        if (a.audio_perm != nullptr && mine >= kAudioFlag) {               // permuted storage (grouped kept-frame layout)
+            const int pr = a.audio_perm[mine - kAudioFlag];
+            mine = pr >= 0 ? kAudioFlag + pr : -1;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < kFusedRows; ++r) {
         if (row0 + r >= n_rows) break;
@@ -486,6 +493,24 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
                                    int left_padding, int64_t pad_id, int64_t ignore_id,
                                    void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
                                    int64_t* out_ids, int64_t* row_src_ws, int32_t* audio_dest, void* stream) {
+    return tasu_splice_scatter_perm(input_ids, attention_mask, mask_dtype, labels, B, S, spliced_len, H, speech_id, text_src,
+                                    text_mode, text_row_stride, audio_rows, nullptr, audio_layout, audio_row_stride,
+                                    audio_max_len, n_audio, emb_dtype, rowstat, new_pos, text_prefix, slot_ord, slot_base,
+                                    audio_off, left_padding, pad_id, ignore_id, out_emb, out_mask, out_labels, out_pos,
+                                    out_ids, row_src_ws, audio_dest, stream);
+}
+
+extern "C" int tasu_splice_scatter_perm(const int64_t* input_ids, const void* attention_mask, int mask_dtype,
+                                        const int64_t* labels, int B, int S, int spliced_len, int H, int64_t speech_id,
+                                        const void* text_src, int text_mode, int64_t text_row_stride,
+                                        const void* audio_rows, const int32_t* audio_perm, int audio_layout,
+                                        int64_t audio_row_stride, int64_t audio_max_len, int n_audio, int emb_dtype,
+                                        const int32_t* rowstat, const int32_t* new_pos, const int32_t* text_prefix,
+                                        const int32_t* slot_ord, const int32_t* slot_base, const int32_t* audio_off,
+                                        int left_padding, int64_t pad_id, int64_t ignore_id,
+                                        void* out_emb, void* out_mask, int64_t* out_labels, int64_t* out_pos,
+                                        int64_t* out_ids, int64_t* row_src_ws, int32_t* audio_dest, void* stream) {
+    TASU_CHECK_ARG(audio_perm == nullptr || audio_layout == 0, "audio_perm needs the packed audio layout");
     TASU_CHECK_ARG(B >= 0 && S > 0 && spliced_len >= 0 && H > 0, "shape");
     TASU_CHECK_ARG(mask_dtype == 0 || mask_dtype == 1, "mask_dtype");
     TASU_CHECK_ARG(text_mode == 0 || text_mode == 1, "text_mode");
@@ -501,7 +526,7 @@ extern "C" int tasu_splice_scatter(const int64_t* input_ids, const void* attenti
     a.B = B; a.S = S; a.Sp = spliced_len; a.H = H;
     a.text_src = text_src; a.text_mode = text_mode; a.text_stride = text_row_stride;
     a.audio = audio_rows; a.audio_layout = audio_layout; a.audio_stride = audio_row_stride;
-    a.audio_max_len = audio_max_len; a.n_audio = n_audio;
+    a.audio_max_len = audio_max_len; a.n_audio = n_audio; a.audio_perm = audio_perm;
     a.rowstat = rowstat; a.new_pos = new_pos; a.text_prefix = text_prefix; a.slot_ord = slot_ord;
     a.slot_base = slot_base; a.audio_off = audio_off; a.left_padding = left_padding;
     a.speech = speech_id; a.pad_id = pad_id; a.ignore_id = ignore_id;

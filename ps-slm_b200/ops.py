@@ -280,6 +280,75 @@ def pool_tail(probs: torch.Tensor, D: int, n_out: int, pk_len: torch.Tensor, tai
     _count(1)
 
 
+class GroupedRows:
+    """Kept frames in the grouped layout (include/tasu_bridge.h, step 2b'): ``xg`` = A operand of the kept-frame GEMM,
+    ``g_max`` / ``g_inv`` its per-row softmax scalars, ``perm`` [cap_o] packed candidate → pooled row, ``lay`` the layout
+    words on the device, ``mean`` / ``rstd`` / ``pk_len`` / ``tail_src`` by pooled row, ``multi`` pool_tail's work list."""
+    __slots__ = ("xg", "g_max", "g_inv", "perm", "lay", "pk_len", "tail_src", "multi", "mean", "rstd", "cap_a", "cap_p")
+
+
+def grouped_capacities(n_frames: int, n_out: int):
+    """(A rows, pooled rows) that hold ANY batch of at most ``n_frames`` kept frames: region padding (3 x 127 rows) plus
+    one zero row per 3-frame run (at most n_frames / 3); pooled rows never exceed the A rows."""
+    cap_a = n_frames + n_frames // 3 + 512
+    return cap_a, cap_a
+
+
+def gather_kept_rows_grouped(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, V: int, plan: "CollapsePlan",
+                             st: FrameStats, n_frames: int, n_out: int, max_proj: int, ln_eps: float = 1e-5) -> GroupedRows:
+    """tasu_group_plan + tasu_gather_kept_rows_grouped (two launches, no host synchronisation).  ``n_frames`` / ``n_out``
+    are capacities (kept frames / packed candidates), ``max_proj`` the pooled rows the projector's buffers hold."""
+    dev = x_bf16.device
+    ldg = pad_to(K)
+    g = GroupedRows()
+    cap_a, cap_p = grouped_capacities(max(n_frames, 1), max(n_out, 1))
+    cap_a = (cap_a + 2047) // 2048 * 2048                    # few distinct sizes → allocator cache hits
+    g.cap_a, g.cap_p = cap_a, cap_a
+    g.xg = torch.empty(cap_a, ldg, dtype=torch.bfloat16, device=dev)
+    g.g_max, g.g_inv, g.mean, g.rstd = _rows(dev, torch.float32, cap_a, 4)
+    g.pk_len, g.tail_src = _rows(dev, torch.int32, cap_a, 2)
+    ints = torch.empty(2 * B * T + 8 * B + L.GL_WORDS + max(n_out, 1) * 2 + 1, dtype=torch.int32, device=dev)
+    slot, xoff = ints[:B * T], ints[B * T:2 * B * T]
+    o = 2 * B * T
+    cnt, base = ints[o:o + 4 * B], ints[o + 4 * B:o + 8 * B]
+    o += 8 * B
+    g.lay = ints[o:o + L.GL_WORDS]
+    o += L.GL_WORDS
+    g.perm = ints[o:o + max(n_out, 1)]
+    g.multi = ints[o + max(n_out, 1):]                       # [0] = count, [1:] = pooled-row list
+    L.check(L.lib().tasu_group_plan(plan.seg_len.data_ptr(), plan.new_lens.data_ptr(), B, T, slot.data_ptr(), xoff.data_ptr(),
+                                    cnt.data_ptr(), base.data_ptr(), g.lay.data_ptr(), _ticket(dev)[2:3].data_ptr(), _stream()),
+            "tasu_group_plan")
+    L.check(L.lib().tasu_gather_kept_rows_grouped(
+        x_bf16.data_ptr(), x_bf16.stride(0), B, T, n_prefix, K, V, plan.seg_start.data_ptr(), plan.seg_len.data_ptr(),
+        plan.row_off.data_ptr(), slot.data_ptr(), xoff.data_ptr(), base.data_ptr(), g.lay.data_ptr(), st.row_max.data_ptr(),
+        st.row_sumexp.data_ptr(), _ptr(st.row_sumexp2), cap_a, g.cap_p, max(n_out, 1), max_proj, g.xg.data_ptr(), ldg,
+        g.g_max.data_ptr(), g.g_inv.data_ptr(), g.perm.data_ptr(), g.pk_len.data_ptr(), g.tail_src.data_ptr(),
+        g.multi[1:].data_ptr(), g.multi.data_ptr(), g.mean.data_ptr(), g.rstd.data_ptr(), float(ln_eps), _stream()),
+        "tasu_gather_kept_rows_grouped")
+    _count(2)
+    return g
+
+
+def gemm_softmax_grouped(g: GroupedRows, w_bf16: torch.Tensor, bias: torch.Tensor, V: int, K: int, pooled: torch.Tensor,
+                         ln_eps: float = 1e-5):
+    """tasu_gemm_softmax_grouped + tasu_group_ln_finish: pooled probabilities of every kept candidate into ``pooled``
+    [cap_p, pad64(V)] bf16 (class order, rows of long runs still per frame: ``pool_tail`` follows) and the LayerNorm
+    statistics of the rows pooled in the epilogue."""
+    _need_cuda(g.xg, w_bf16, pooled)
+    n_parts = L.lib().tasu_gemm_softmax_grouped_parts(V)
+    ldq = max(int(g.perm.numel()), 64) + 96                  # pooled rows of the G regions: at most n_out + 63 + 31
+    q_part = torch.empty(n_parts, ldq, dtype=torch.float32, device=pooled.device)
+    L.check(L.lib().tasu_gemm_softmax_grouped(g.xg.data_ptr(), g.xg.stride(0), w_bf16.data_ptr(), w_bf16.stride(0),
+                                              pooled.data_ptr(), pooled.stride(0), g.cap_a, pooled.shape[0], V, K,
+                                              bias.data_ptr(), g.g_inv.data_ptr(), g.g_max.data_ptr(), g.lay.data_ptr(),
+                                              q_part.data_ptr(), ldq, _stream()), "tasu_gemm_softmax_grouped")
+    L.check(L.lib().tasu_group_ln_finish(q_part.data_ptr(), ldq, n_parts, g.lay.data_ptr(), V, g.cap_p, g.mean.data_ptr(),
+                                         g.rstd.data_ptr(), float(ln_eps), _stream()), "tasu_group_ln_finish")
+    _count(2)
+    return pooled
+
+
 class CollapsePlan:
     __slots__ = ("seg_start", "seg_len", "seg_score", "seg_foff", "new_lens", "kept_frames", "row_off", "frame_off",
                  "header", "counts", "B", "T")
@@ -294,7 +363,7 @@ def _ticket(device) -> torch.Tensor:
     key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
     t = _TICKETS.get(key)
     if t is None:
-        t = torch.zeros(2, dtype=torch.int32, device=device)
+        t = torch.zeros(4, dtype=torch.int32, device=device)
         _TICKETS[key] = t
     return t
 
@@ -587,9 +656,12 @@ def splice_plan(p: SplicePlan, num_audio: torch.Tensor, div_k: int = 1, header: 
 def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text_mode: int,
                    audio_rows: torch.Tensor, audio_layout: int, audio_max_len: int,
                    labels: Optional[torch.Tensor], pad_id: int, ignore_id: int, want_ids: bool = True,
-                   left_padding: Optional[int] = None, want_audio_dest: bool = False):
+                   left_padding: Optional[int] = None, want_audio_dest: bool = False,
+                   audio_perm: Optional[torch.Tensor] = None):
     """Row map + one copy pass → (emb [B,S',H], mask [B,S'], labels|None, position_ids, final_ids|None).
-    ``want_audio_dest``: also keep ``p.audio_dest`` (output row of every audio row) for the backward."""
+    ``want_audio_dest``: also keep ``p.audio_dest`` (output row of every audio row) for the backward.
+    ``audio_perm`` (int32, packed layout only): packed audio row r is stored at row ``audio_perm[r]`` of ``audio_rows``
+    (the class order of the grouped kept-frame layout) — tasu_splice_scatter_perm."""
     _need_cuda(text_src, audio_rows, labels)
     B, S = p.B, p.S
     dev = p.input_ids.device
@@ -639,14 +711,14 @@ def splice_scatter(p: SplicePlan, spliced_len: int, text_src: torch.Tensor, text
     if want_audio_dest:
         audio_dest = torch.empty(_cap_rows(max(n_audio_rows, 1)), dtype=torch.int32, device=dev)[:max(n_audio_rows, 1)]
         audio_dest.fill_(-1)
-    L.check(L.lib().tasu_splice_scatter(
+    L.check(L.lib().tasu_splice_scatter_perm(
         p.input_ids.data_ptr(), p.attention_mask.data_ptr(), p.mask_dtype, _ptr(labels), B, S, spliced_len, H,
         p.speech_id, text2.data_ptr(), text_mode, text_stride, audio_rows.data_ptr() if audio_rows.numel() else None,
-        audio_layout, audio_stride, audio_max_len, p.n_audio, _dt(emb),
+        _ptr(audio_perm), audio_layout, audio_stride, audio_max_len, p.n_audio, _dt(emb),
         p.rowstat.data_ptr(), p.new_pos.data_ptr(), p.text_prefix.data_ptr(), p.slot_ord.data_ptr(),
         p.slot_base.data_ptr(), p.audio_off.data_ptr(), p.left_padding, pad_id, ignore_id,
         emb.data_ptr(), mask.data_ptr(), _ptr(out_labels), pos.data_ptr(), _ptr(fids), row_src.data_ptr(),
-        _ptr(audio_dest), _stream()), "tasu_splice_scatter")
+        _ptr(audio_dest), _stream()), "tasu_splice_scatter_perm")
     p.audio_dest = audio_dest
     p.row_src = row_src[:n_pos] if want_audio_dest else None      # kept for the backward of the text rows
     _count(1)
