@@ -190,20 +190,41 @@ gather_grouped_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B, i
 }
 
 // LayerNorm statistics of the pooled rows of the G2 / G4 regions: sum p^2 from the per-(column tile, epilogue group)
-// partial sums the GEMM epilogue left in q_part [n_parts][ldq], added in a fixed order.
+// partial sums the GEMM epilogue left in q_part [n_parts][ldq], added in a FIXED order: a CTA takes 32 rows, its 8 warps
+// each add every 8th partial of a row (independent, coalesced loads), the 8 sub-sums meet in shared memory.
 __global__ void __launch_bounds__(256)
 group_ln_finish_kernel(const float* __restrict__ q_part, int64_t ldq, int n_parts, const int32_t* __restrict__ lay, int V,
                        int64_t max_o, float* __restrict__ ln_mean, float* __restrict__ ln_rstd, float eps) {
+    __shared__ float sub[8][33];
     const int A2 = lay[TASU_GL_A2], OX = lay[TASU_GL_OX];
+    const int64_t n_rows = min((int64_t)(OX - A2), ldq);
+    const int rx = threadIdx.x & 31, ky = threadIdx.x >> 5;
     const float mean = 1.f / (float)V;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < OX - A2; i += (int64_t)gridDim.x * blockDim.x) {
-        if (i >= ldq || A2 + i >= max_o) break;
-        float q = 0.f;
-        for (int k = 0; k < n_parts; ++k) q += q_part[(int64_t)k * ldq + i];
-        float var = q / (float)V - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        ln_mean[A2 + i] = mean;
-        ln_rstd[A2 + i] = rsqrtf(var + eps);
+    for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < n_rows; r0 += (int64_t)gridDim.x * 32) {
+        const int64_t i = r0 + rx;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        if (i < n_rows) {
+            int k = ky;
+            for (; k + 24 < n_parts; k += 32) {
+                q0 += q_part[(int64_t)k * ldq + i];
+                q1 += q_part[(int64_t)(k + 8) * ldq + i];
+                q2 += q_part[(int64_t)(k + 16) * ldq + i];
+                q3 += q_part[(int64_t)(k + 24) * ldq + i];
+            }
+            for (; k < n_parts; k += 8) q0 += q_part[(int64_t)k * ldq + i];
+        }
+        sub[ky][rx] = (q0 + q1) + (q2 + q3);
+        __syncthreads();
+        if (ky == 0 && i < n_rows && A2 + i < max_o) {
+            float q = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) q += sub[w][rx];
+            float var = q / (float)V - mean * mean;
+            var = var < 0.f ? 0.f : var;
+            ln_mean[A2 + i] = mean;
+            ln_rstd[A2 + i] = rsqrtf(var + eps);
+        }
+        __syncthreads();
     }
 }
 
@@ -251,7 +272,7 @@ extern "C" int tasu_group_ln_finish(const float* q_part, int64_t ldq, int n_part
                                     float* ln_mean, float* ln_rstd, float ln_eps, void* stream) {
     TASU_CHECK_ARG(ldq > 0 && n_parts > 0 && V > 0 && max_o > 0, "shape");
     TASU_CHECK_ARG(q_part && lay && ln_mean && ln_rstd, "null pointer");
-    int64_t g = (ldq + 255) / 256, gmax = (int64_t)tasu::sm_count() * 4;
+    int64_t g = (ldq + 31) / 32, gmax = (int64_t)tasu::sm_count() * 4;     // 32 rows per CTA; the live row count is on the device
     if (g > gmax) g = gmax;
     group_ln_finish_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(q_part, ldq, n_parts, lay, V, max_o, ln_mean, ln_rstd, ln_eps);
     TASU_CHECK_LAUNCH();

@@ -22,7 +22,7 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-comm --no-fp32-leg --sustained-seconds 0 > gpurun_out/ncu_bench_$TAG.log 2>&1; echo "ncu_list rc=$?" >> gpurun_out/rc_$TAG.txt
 timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:'gemm_bf16_tn_kernel|splice_fused_kernel|ctc_stats_kernel|pool_tail_kernel|gather_kept_rows_kernel|collapse|cast_rows' -s 30 -c 12 \
+    -k regex:'gemm_bf16_tn_kernel|gemm_streamk_kernel|splice_fused_kernel|ctc_stats_kernel|pool_tail_kernel|gather_kept_rows_kernel|gather_grouped_kernel|group_plan_kernel|group_ln_finish_kernel|collapse|cast_rows' -s 36 -c 14 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-comm --no-fp32-leg --sustained-seconds 0 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu_full rc=$?" >> gpurun_out/rc_$TAG.txt
 fi
 if [ "${SKIP_OPS:-0}" != 1 ]; then
