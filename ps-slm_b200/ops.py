@@ -289,9 +289,9 @@ class GroupedRows:
 
 def grouped_capacities(n_frames: int, n_out: int):
     """(A rows, pooled rows) that hold ANY batch of at most ``n_frames`` kept frames: region padding (3 x 127 rows) plus
-    one zero row per 3-frame run (at most n_frames / 3); pooled rows never exceed the A rows."""
+    one zero row per 3-frame run (at most n_frames / 3) on the A side; the pooled matrix carries no zero rows."""
     cap_a = n_frames + n_frames // 3 + 512
-    return cap_a, cap_a
+    return cap_a, n_frames + 512        # pooled rows: N_out + at most 221 hole rows + the extra frames of the long runs
 
 
 def gather_kept_rows_grouped(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int, K: int, V: int, plan: "CollapsePlan",
@@ -303,7 +303,7 @@ def gather_kept_rows_grouped(x_bf16: torch.Tensor, B: int, T: int, n_prefix: int
     g = GroupedRows()
     cap_a, cap_p = grouped_capacities(max(n_frames, 1), max(n_out, 1))
     cap_a = (cap_a + 2047) // 2048 * 2048                    # few distinct sizes → allocator cache hits
-    g.cap_a, g.cap_p = cap_a, cap_a
+    g.cap_a, g.cap_p = cap_a, (cap_p + 2047) // 2048 * 2048
     g.xg = torch.empty(cap_a, ldg, dtype=torch.bfloat16, device=dev)
     g.g_max, g.g_inv, g.mean, g.rstd = _rows(dev, torch.float32, cap_a, 4)
     g.pk_len, g.tail_src = _rows(dev, torch.int32, cap_a, 2)

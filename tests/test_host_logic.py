@@ -211,3 +211,37 @@ def test_bind_rank_to_cpu_slice_partitions_the_allowed_cpus():
         assert D.bind_rank_to_cpu_slice(0, 10 * len(before)) is None
     finally:
         os.sched_setaffinity(0, before)
+
+
+def _grouped_layout_host(runs):
+    """Host restatement of the layout words tasu_group_plan writes (include/tasu_bridge.h, step 2b') for a list of kept
+    run lengths: (A rows, pooled rows incl. the per-frame rows of the long runs, pooled rows the projector reads)."""
+    up = lambda v, a: (v + a - 1) // a * a
+    ns = sum(1 for n in runs if n == 1 or n > 4)
+    n2 = sum(1 for n in runs if n == 2)
+    n4 = sum(1 for n in runs if 3 <= n <= 4)
+    nxe = sum(n - 1 for n in runs if n > 4)
+    a2 = up(ns, 128)
+    a4 = up(a2 + 2 * n2, 128)
+    ax = up(a4 + 4 * n4, 128)
+    ox = a2 + up(n2, 64) + up(n4, 32)
+    return ax + nxe, ox + nxe, ox
+
+
+def test_grouped_layout_fits_the_capacities_for_any_run_length_mix():
+    """ops.grouped_capacities / the projector's row capacity (N_out + 256) hold every batch whose kept-frame and candidate
+    counts are within the capacities the host sized the buffers for — including the adversarial mixes (all 3-frame runs:
+    one zero row each; all long runs: every extra frame keeps its own output row)."""
+    import ps_slm_b200.ops as ops
+    rng = np.random.default_rng(5)
+    mixes = [[3] * 4000, [1] * 5000, [2] * 3001, [4] * 999, [9] * 700, [5, 1, 2, 3] * 500, [129] * 3, [1]]
+    for _ in range(200):
+        k = int(rng.integers(1, 3000))
+        p = rng.dirichlet(np.ones(8))
+        mixes.append(rng.choice([1, 2, 3, 4, 5, 6, 17, 200], size=k, p=p).tolist())
+    for runs in mixes:
+        n_out, n_frames = len(runs), sum(runs)
+        a_rows, p_rows, proj_rows = _grouped_layout_host(runs)
+        cap_a, cap_p = ops.grouped_capacities(n_frames, n_out)
+        assert a_rows <= cap_a and p_rows <= cap_p and proj_rows <= n_out + 256
+        assert proj_rows <= cap_p                          # the projector's rows lie inside the pooled matrix
