@@ -154,7 +154,7 @@ gather_grouped_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int B, i
         else { a0 = base[b] + s; out = a0; rows_here = 1; weight = 1.f; tail0 = base[3 * B + b] + xoff[pj]; }
         if (lane == 0) {
             if (r < max_out) perm[r] = out < max_proj ? out : -1;   // beyond the projector's row capacity: batch is redone
-            if (cls == 3 && out < max_o) {
+            if (cls == 3 && out < max_o && r < max_out) {                     // the work list has max_out slots
                 pk_len[out] = n;
                 tail_src[out] = OX + tail0;
                 multi_rows[atomicAdd(multi_count, 1)] = out;                   // work list of pool_tail (any order)

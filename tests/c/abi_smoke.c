@@ -60,6 +60,22 @@ int main(void) {
         float d = score[j] - want_score[j];
         ok = ss[j] == want_start[j] && sl[j] == want_len[j] && d < 1e-6f && d > -1e-6f;
     }
+    /* grouped kept-frame layout (step 2b'): run lengths {1,3,2,1,1,1} -> 4 single rows, one 2-frame and one 4-row group */
+    {
+        int32_t *d_slot, *d_xoff, *d_cntb, *d_lay, *d_ticket;
+        CK(cudaMalloc((void**)&d_slot, 4 * B * T)); CK(cudaMalloc((void**)&d_xoff, 4 * B * T));
+        CK(cudaMalloc((void**)&d_cntb, 4 * 8 * B)); CK(cudaMalloc((void**)&d_lay, 4 * TASU_GL_WORDS));
+        CK(cudaMalloc((void**)&d_ticket, 4)); CK(cudaMemset(d_ticket, 0, 4));
+        TK(tasu_group_plan(d_sl, d_new, B, T, d_slot, d_xoff, d_cntb, d_cntb + 4 * B, d_lay, d_ticket, NULL));
+        CK(cudaDeviceSynchronize());
+        int32_t lay[TASU_GL_WORDS], slot[T];
+        CK(cudaMemcpy(lay, d_lay, sizeof(lay), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(slot, d_slot, sizeof(slot), cudaMemcpyDeviceToHost));
+        const int want_slot[6] = {0, 0, 0, 1, 2, 3};
+        ok = ok && lay[TASU_GL_NS] == 4 && lay[TASU_GL_N2] == 1 && lay[TASU_GL_N4] == 1 && lay[TASU_GL_NXE] == 0 &&
+             lay[TASU_GL_A2] == 128 && lay[TASU_GL_A4] == 256 && lay[TASU_GL_AX] == 384 && lay[TASU_GL_A_ROWS] == 384 &&
+             lay[TASU_GL_O4] == 192 && lay[TASU_GL_OX] == 224;
+        for (int j = 0; j < 6; ++j) ok = ok && slot[j] == want_slot[j];
+    }
     /* invalid arguments are reported, never thrown */
     ok = ok && tasu_frame_stats(NULL, TASU_F32, TASU_INPUT_PROBS, 1, 1, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == TASU_ERR_INVALID_ARG;
     printf("kept %lld candidates: %s\n", (long long)m, ok ? "C ABI SMOKE OK" : "MISMATCH");

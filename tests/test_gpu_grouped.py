@@ -170,3 +170,33 @@ def test_grouped_capacity_overflow_is_redone(dev):
     for x, y in zip(ref, out):
         if x is not None:
             assert torch.equal(x, y)
+
+
+def test_grouped_batch_without_kept_frames_and_with_silent_utterances(dev):
+    """Edge cases of the layout: a batch of confident blanks only (no candidate at all: every region is empty) and a batch
+    where some utterances keep nothing — both through the whole bridge, twice (exact-size and speculative call)."""
+    import ps_slm_b200.synth as S
+    B, T = 6, 90
+    w, b, br = _bridge(dev)
+    raw, raw_lens, lab, soft = S.make_encoder_batch(B, T, w, seed=3, ragged=True, return_soft=True)
+    quiet = ((lab == 0) & ~soft).nonzero()[0]
+    blank_row = raw[int(quiet[0]), 4 + int(quiet[1])].clone()
+    ids, mask, _ = S.make_prompts(B, seed=3, left_pad=True)
+    silent = raw.clone()
+    silent[:, 4:] = blank_row
+    mixed = raw.clone()
+    mixed[1::2, 4:] = blank_row                              # every second utterance keeps nothing
+    for batch, expect_zero in ((silent, range(B)), (mixed, range(1, B, 2))):
+        outs = []
+        for grouped in (False, True, True):
+            br.grouped_pool = grouped
+            if not grouped:
+                br._capacity.clear()
+            e, m, _, p, nl = br(batch.to(dev), raw_lens.to(dev), ids.to(dev), mask.to(dev))
+            outs.append((e.clone(), m.clone(), p.clone(), nl.clone()))
+        for bb in expect_zero:
+            assert int(outs[0][3][bb]) == 0
+        for e, m, p, nl in outs[1:]:
+            assert torch.equal(nl, outs[0][3]) and torch.equal(m, outs[0][1]) and torch.equal(p, outs[0][2])
+            assert ((e.float() - outs[0][0].float()).norm() / outs[0][0].float().norm().clamp_min(1e-9)).item() < 3e-3
+        assert torch.equal(outs[1][0], outs[2][0])
