@@ -360,6 +360,16 @@ int tasu_gemm_streamk_schedule_host(int num_tiles, int k_blocks, int grid, int c
 int tasu_attn_softmax_pv(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
                          int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
                          float* Z, int64_t ldz, void* stream);
+/* The same with a workspace for the KEY SPLIT of the self-contained mode (row_max = row_inv = NULL): the (128-row tile,
+ * head) items — 616 at N = 9856, 8 heads: 4.16 waves on 148 SMs — are cut into `splits` key ranges each so that the last
+ * wave is full; a split leaves its unnormalised output (relative to its own row maxima), the maxima and the sums in the
+ * workspace and a merge kernel combines them in split order (deterministic).  tasu_attn_split_plan (HOST) returns the
+ * workspace bytes (0 when one split is best) and the number of splits it chose; workspace = NULL or given statistics:
+ * exactly tasu_attn_softmax_pv. */
+int64_t tasu_attn_split_plan(int N, int V2, int heads, int dp, int* splits_host);
+int tasu_attn_softmax_pv_ws(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
+                            int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
+                            float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* CUDA-core cross-check of the same contract (tests and bring-up only; never on the product path) */
 int tasu_gemm_bf16_tn_simt(const void* A, int64_t lda, const void* B, int64_t ldb,

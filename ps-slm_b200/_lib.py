@@ -61,6 +61,8 @@ SIGNATURES = {
     "tasu_gemm_bf16_tn_streamk": (_I, [_P, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),
     "tasu_gemm_streamk_schedule_host": (_I, [_I, _I, _I, _I, _P, _P]),
     "tasu_attn_softmax_pv": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _L, _P, _L, _P]),
+    "tasu_attn_split_plan": (_L, [_I, _I, _I, _I, POINTER(c_int)]),
+    "tasu_attn_softmax_pv_ws": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _L, _P, _L, _P, _L, _P]),
     "tasu_gemm_bf16_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P]),
     "tasu_ctc_head_stats_workspace": (_L, [_I, _I, _I]),
     "tasu_ctc_head_stats": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),

@@ -49,6 +49,12 @@ struct AttnParams {
     int64_t stat_stride;
     float* Z;                      // [N, ldz] fp32, head h in columns [h DP, h DP + DP)
     int64_t ldz;
+    // key split (row_max == NULL only): an item is (128 query rows, head, split s) and sweeps the key tiles
+    // [s J / splits, (s + 1) J / splits); it leaves its UNNORMALISED output (relative to its own row maxima), the maxima
+    // and the sums of its probabilities in the workspace and attn_merge_kernel combines the splits.  splits = 1: Z directly.
+    int splits;
+    float* ws_o;                   // [items][128][DP] fp32
+    float* ws_ml;                  // [items][128][2]: row maximum (raw score), sum of the unnormalised probabilities
 };
 
 // MN-major operand in [128 K-rows][64 MN] boxes: 8-row K groups 1024 B apart (SBO), the next 64 MN elements one box
@@ -87,7 +93,13 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.N + 127) / 128, n_items = m_tiles * p.heads, J = (p.V2 + kAtKeys - 1) / kAtKeys;
+    const int m_tiles = (p.N + 127) / 128, n_items = m_tiles * p.heads * p.splits, J = (p.V2 + kAtKeys - 1) / kAtKeys;
+    // item -> (head, first query row, key-tile range): every role derives the same ranges from the same expressions
+#define TASU_AT_ITEM(it) \
+    const int sp_ = (it) % p.splits, bi_ = (it) / p.splits; \
+    const int head = bi_ / m_tiles, m0 = (bi_ % m_tiles) * 128; \
+    const int j0 = (int)((int64_t)sp_ * J / p.splits), j1 = (int)((int64_t)(sp_ + 1) * J / p.splits); \
+    (void)head; (void)m0
     const bool find_max = p.row_max == nullptr;                  // first sweep: row maxima only
     const int n_sweeps = find_max ? 2 : 1;
 
@@ -117,13 +129,14 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         if (lane == 0) {
             uint32_t g = 0, n = 0;                                        // running tile / item counters of this CTA
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-                const int head = it / m_tiles, m0 = (it % m_tiles) * 128, c0 = head * DP;
+                TASU_AT_ITEM(it);
+                const int c0 = head * DP;
                 mbar_wait(q_empty, (n & 1) ^ 1);
                 mbar_expect_tx(q_full, C::kQBytes);
 #pragma unroll
                 for (int b = 0; b < kbd; ++b) tma_load_2d(&tmap_q, q_full, sQ + b * kAtBox, c0 + 64 * b, m0);
                 for (int sweep = 0; sweep < n_sweeps; ++sweep)
-                    for (int j = 0; j < J; ++j, ++g) {
+                    for (int j = j0; j < j1; ++j, ++g) {
                         const uint32_t st = g % kTS;
                         mbar_wait(&t_empty[st], ((g / kTS) & 1) ^ 1);
                         mbar_expect_tx(&t_full[st], C::kTBytes);
@@ -157,28 +170,29 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             };
             uint32_t g = 0, gp = 0, n = 0;                               // tiles issued, tiles of second sweeps, items
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+                TASU_AT_ITEM(it);
                 mbar_wait(q_full, n & 1);
                 tc_fence_after();
                 if (find_max)
-                    for (int j = 0; j < J; ++j, ++g) {                     // first sweep: scores only
+                    for (int j = j0; j < j1; ++j, ++g) {                   // first sweep: scores only
                         issue_s(g);
                         umma_commit(&t_empty[g % kTS]);
                     }
                 issue_s(g);
-                for (int j = 0; j < J; ++j, ++g, ++gp) {
-                    if (j + 1 < J) issue_s(g + 1);
+                for (int j = j0; j < j1; ++j, ++g, ++gp) {
+                    if (j + 1 < j1) issue_s(g + 1);
                     const uint32_t st = g % kTS;
                     const uint64_t bdesc = make_smem_desc_mn_box128(t_addr + st * C::kTBytes);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {                          // the two 64-key halves of the probability tile
                         mbar_wait(&p_full[h], gp & 1);
                         tc_fence_after();
-                        if (j == 0 && h == 0) { mbar_wait(o_empty, (n & 1) ^ 1); tc_fence_after(); }
+                        if (j == j0 && h == 0) { mbar_wait(o_empty, (n & 1) ^ 1); tc_fence_after(); }
                         const uint64_t adesc = make_smem_desc(p_addr + h * kAtBox);
 #pragma unroll
                         for (int k = 0; k < 64 / UMMA_K; ++k)
                             umma_bf16(d_o, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * (4 * h + k)), C::kIdescO,
-                                      (j > 0 || h > 0 || k > 0) ? 1u : 0u);
+                                      (j > j0 || h > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&p_empty[h]);
                     }
                     umma_commit(&t_empty[st]);
@@ -195,12 +209,13 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const int sw = r & 7;
         uint32_t g = 0, gp = 0, n = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-            const int head = it / m_tiles, m0 = (it % m_tiles) * 128, grow = m0 + r;
+            TASU_AT_ITEM(it);
+            const int grow = m0 + r;
             float rowc = -INFINITY;                                      // given statistics, rows beyond N: p = 0
             float lsum = 0.f;                                            // find_max: sum of the unnormalised probabilities
+            float rmax = -INFINITY;
             if (find_max) {
-                float rmax = -INFINITY;
-                for (int j = 0; j < J; ++j, ++g) {
+                for (int j = j0; j < j1; ++j, ++g) {
                     const uint32_t sb = g & 1;
                     const int n_valid = min(kAtKeys, p.V2 - j * kAtKeys);
                     mbar_wait(&s_full[sb], (g >> 1) & 1);
@@ -227,7 +242,7 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 const float iv = __ldg(p.row_inv + (int64_t)head * p.stat_stride + grow);
                 rowc = fmaf(-mx, kLog2e, __log2f(fmaxf(iv, 1e-37f)));
             }
-            for (int j = 0; j < J; ++j, ++g, ++gp) {
+            for (int j = j0; j < j1; ++j, ++g, ++gp) {
                 const uint32_t sb = g & 1;
                 const int n_valid = min(kAtKeys, p.V2 - j * kAtKeys);     // keys beyond V2 (zero rows of the tile): p = 0
                 mbar_wait(&s_full[sb], (g >> 1) & 1);
@@ -269,14 +284,17 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             // ---- the item's output: O [128 x DP] fp32 from TMEM to Z
             mbar_wait(o_full, n & 1);
             tc_fence_after();
-            float* zrow = p.Z + (int64_t)grow * p.ldz + (int64_t)head * DP;
-            const float zs = find_max ? 1.f / lsum : 1.f;                // lsum >= 1: the row maximum contributes 2^0
+            const bool split = p.splits > 1;
+            // key split: the unnormalised output of this key range (relative to its own row maxima) goes to the workspace
+            float* zrow = split ? p.ws_o + ((int64_t)it * 128 + r) * DP : p.Z + (int64_t)grow * p.ldz + (int64_t)head * DP;
+            const float zs = (find_max && !split) ? 1.f / lsum : 1.f;    // lsum >= 1: the row maximum contributes 2^0
+            if (split) *reinterpret_cast<float2*>(p.ws_ml + ((int64_t)it * 128 + r) * 2) = make_float2(rmax, lsum);
 #pragma unroll 1
             for (int c = 0; c < DP / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_bits + 256u + (uint32_t)(32 * c), v);
                 tmem_ld_wait(v);
-                if (grow < p.N) {
+                if (split || grow < p.N) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<float4*>(zrow + 32 * c + 4 * q) =
@@ -297,6 +315,58 @@ attn_softmax_pv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     }
 }
 
+#undef TASU_AT_ITEM
+
+// Combines the key splits of tasu_attn_softmax_pv: per (128-row tile, head) and row, m = max_s m_s,
+// Z = sum_s 2^((m_s - m) log2e) O_s / sum_s 2^((m_s - m) log2e) l_s — in split order, deterministic.  One CTA per tile.
+constexpr int kAtMaxSplits = 8;
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, int N, int heads, int dp, int splits,
+                  float* __restrict__ Z, int64_t ldz) {
+    __shared__ float w[kAtMaxSplits][128];
+    const int m_tiles = (N + 127) / 128;
+    const int bi = blockIdx.x, head = bi / m_tiles, m0 = (bi % m_tiles) * 128;
+    const int64_t item0 = (int64_t)bi * splits;
+    if (threadIdx.x < 128) {
+        const int r = threadIdx.x;
+        float m = -INFINITY;
+        for (int s = 0; s < splits; ++s) m = fmaxf(m, ws_ml[((item0 + s) * 128 + r) * 2]);
+        float l = 0.f, e[kAtMaxSplits];
+        for (int s = 0; s < splits; ++s) {
+            e[s] = exp2f((ws_ml[((item0 + s) * 128 + r) * 2] - m) * kLog2e);
+            l = fmaf(e[s], ws_ml[((item0 + s) * 128 + r) * 2 + 1], l);
+        }
+        const float inv = 1.f / l;
+        for (int s = 0; s < splits; ++s) w[s][r] = e[s] * inv;
+    }
+    __syncthreads();
+    const int q4 = dp / 4;
+    for (int idx = threadIdx.x; idx < 128 * q4; idx += blockDim.x) {
+        const int r = idx / q4, c = (idx % q4) * 4;
+        if (m0 + r >= N) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < splits; ++s) {
+            const float4 o = *reinterpret_cast<const float4*>(ws_o + ((item0 + s) * 128 + r) * dp + c);
+            const float ws = w[s][r];
+            acc.x = fmaf(ws, o.x, acc.x); acc.y = fmaf(ws, o.y, acc.y); acc.z = fmaf(ws, o.z, acc.z); acc.w = fmaf(ws, o.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(Z + (int64_t)(m0 + r) * ldz + (int64_t)head * dp + c) = acc;
+    }
+}
+
+// HOST: the number of key splits that fills the last wave best: time ~ ceil(items S / SMs) / S item lengths, with a small
+// charge per split for the workspace round trip (ties go to fewer splits); never more splits than key tiles
+static int choose_attn_splits(int items, int sms, int J) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int S = 1; S <= kAtMaxSplits && S <= J; ++S) {
+        const int64_t waves = ((int64_t)items * S + sms - 1) / sms;
+        const double cost = (double)waves / S * (1.0 + 0.004 * (S - 1));
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
 template <int DP>
 static int launch_attn(int grid, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mt, const AttnParams& p) {
     auto kern = attn_softmax_pv_kernel<DP>;
@@ -315,9 +385,16 @@ static int launch_attn(int grid, cudaStream_t st, const CUtensorMap& mq, const C
 using namespace tasu;
 using namespace tasu::gemm;
 
-extern "C" int tasu_attn_softmax_pv(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
-                                    int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
-                                    float* Z, int64_t ldz, void* stream) {
+extern "C" int64_t tasu_attn_split_plan(int N, int V2, int heads, int dp, int* splits_host) {
+    const int items = ((N + 127) / 128) * heads, J = (V2 + kAtKeys - 1) / kAtKeys;
+    const int S = (N > 0 && V2 > 0 && heads > 0) ? choose_attn_splits(items, sm_count(), J) : 1;
+    if (splits_host) *splits_host = S;
+    return S > 1 ? (int64_t)items * S * 128 * (dp + 2) * 4 : 0;
+}
+
+extern "C" int tasu_attn_softmax_pv_ws(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
+                                       int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
+                                       float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, void* stream) {
     TASU_CHECK_ARG(N >= 0 && V2 > 0 && heads > 0, "shape");
     TASU_CHECK_ARG(dp == 64 || dp == 128 || dp == 192 || dp == 256, "head width must be 64, 128, 192 or 256 (see tasu_attn_softmax_pv_supported)");
     TASU_CHECK_ARG(ldq >= (int64_t)heads * dp && ldt >= (int64_t)heads * dp && ldz >= (int64_t)heads * dp &&
@@ -333,14 +410,38 @@ extern "C" int tasu_attn_softmax_pv(const void* Q_bf16, int64_t ldq, const void*
     if (rc) return rc;
     rc = make_map(&mt, table_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, V2, (int64_t)heads * dp, ldt, 128, 64, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
-    AttnParams p{N, V2, heads, row_max, row_inv, stat_stride, Z, ldz};
-    const int items = ((N + 127) / 128) * heads, sms = sm_count();
+    // key split (self-contained mode with a workspace): fills the last wave of (row tile, head) items
+    int splits = 1;
+    if (row_max == nullptr && workspace != nullptr) {
+        int want = 1;
+        const int64_t need = tasu_attn_split_plan(N, V2, heads, dp, &want);
+        TASU_CHECK_ARG(workspace_bytes >= need, "workspace smaller than tasu_attn_split_plan bytes");
+        TASU_CHECK_ARG((uintptr_t)workspace % 16 == 0, "workspace must be 16-byte aligned");
+        splits = want;
+    }
+    const int items = ((N + 127) / 128) * heads * splits, sms = sm_count();
+    AttnParams p{N, V2, heads, row_max, row_inv, stat_stride, Z, ldz, splits, nullptr, nullptr};
+    if (splits > 1) {
+        p.ws_o = (float*)workspace;
+        p.ws_ml = p.ws_o + (int64_t)items * 128 * dp;
+    }
     const int grid = items < sms ? items : sms;
     cudaStream_t st = (cudaStream_t)stream;
     switch (dp) {
-        case 64: return launch_attn<64>(grid, st, mq, mt, p);
-        case 128: return launch_attn<128>(grid, st, mq, mt, p);
-        case 192: return launch_attn<192>(grid, st, mq, mt, p);
-        default: return launch_attn<256>(grid, st, mq, mt, p);
+        case 64: rc = launch_attn<64>(grid, st, mq, mt, p); break;
+        case 128: rc = launch_attn<128>(grid, st, mq, mt, p); break;
+        case 192: rc = launch_attn<192>(grid, st, mq, mt, p); break;
+        default: rc = launch_attn<256>(grid, st, mq, mt, p); break;
     }
+    if (rc != TASU_OK || splits == 1) return rc;
+    attn_merge_kernel<<<((N + 127) / 128) * heads, 256, 0, st>>>(p.ws_o, p.ws_ml, N, heads, dp, splits, Z, ldz);
+    TASU_CHECK_LAUNCH();
+    return TASU_OK;
+}
+
+extern "C" int tasu_attn_softmax_pv(const void* Q_bf16, int64_t ldq, const void* table_bf16, int64_t ldt, int N, int V2,
+                                    int heads, int dp, const float* row_max, const float* row_inv, int64_t stat_stride,
+                                    float* Z, int64_t ldz, void* stream) {
+    return tasu_attn_softmax_pv_ws(Q_bf16, ldq, table_bf16, ldt, N, V2, heads, dp, row_max, row_inv, stat_stride, Z, ldz,
+                                   nullptr, 0, stream);
 }

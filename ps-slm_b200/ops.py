@@ -528,11 +528,23 @@ def attn_softmax_pv(Q: torch.Tensor, table: torch.Tensor, N: int, V2: int, heads
     _need_cuda(Q, table, row_max, row_inv, Z)
     if Q.dtype != torch.bfloat16 or table.dtype != torch.bfloat16 or Z.dtype != torch.float32:
         raise TypeError("attn_softmax_pv: bf16 operands, fp32 output")
-    L.check(L.lib().tasu_attn_softmax_pv(Q.data_ptr(), Q.stride(0), table.data_ptr(), table.stride(0), N, V2, heads, dp,
-                                         _ptr(row_max), _ptr(row_inv), row_max.stride(0) if row_max is not None else 0,
-                                         Z.data_ptr(), Z.stride(0), _stream()), "tasu_attn_softmax_pv")
-    _count(1)
+    ws, ws_bytes, launches = None, 0, 1
+    if row_max is None and ATTN_KEY_SPLIT:
+        # self-contained mode: key split so that the last wave of (row tile, head) items is full (tasu_attn_split_plan)
+        import ctypes
+        n_splits = ctypes.c_int(1)
+        ws_bytes = int(L.lib().tasu_attn_split_plan(N, V2, heads, dp, ctypes.byref(n_splits)))
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=Q.device)
+            launches = 2
+    L.check(L.lib().tasu_attn_softmax_pv_ws(Q.data_ptr(), Q.stride(0), table.data_ptr(), table.stride(0), N, V2, heads, dp,
+                                            _ptr(row_max), _ptr(row_inv), row_max.stride(0) if row_max is not None else 0,
+                                            Z.data_ptr(), Z.stride(0), _ptr(ws), ws_bytes, _stream()), "tasu_attn_softmax_pv_ws")
+    _count(launches)
     return Z
+
+
+ATTN_KEY_SPLIT = True       # False: one item per (row tile, head) — tasu_attn_softmax_pv as it was
 
 
 ATTN_FUSED_WIDTHS = (64, 128, 192, 256)

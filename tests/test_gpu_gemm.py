@@ -372,3 +372,41 @@ def test_attn_softmax_pv_both_modes(dev, N, V2, h, d):
     assert (Z1 - ref).abs().max().item() / scale < 6e-3                  # bf16 probabilities
     assert (Z2 - ref).abs().max().item() / scale < 6e-3
     assert (Z1 - Z2).abs().max().item() / scale < 3e-3
+
+
+@pytest.mark.parametrize("N,V2,h,d", [(300, 1000, 8, 192), (2000, 4099, 2, 128), (129, 515, 4, 64), (1100, 151936, 8, 192)])
+def test_attn_key_split_against_one_item_per_tile(dev, N, V2, h, d):
+    """Key split of the self-contained mode (tasu_attn_softmax_pv_ws + merge kernel: every (row tile, head) item cut into
+    key ranges so that the last wave is full) against the unsplit kernel: same result up to the bf16 rounding of the
+    probabilities relative to different maxima, deterministic, and the plan is what the host function says."""
+    import ctypes
+    import ps_slm_b200.ops as ops
+    import ps_slm_b200._lib as L
+    torch.manual_seed(N + V2 + 1)
+    Q = (torch.randn(N, h * d, device=dev) * 0.4).bfloat16()
+    table = (torch.randn(V2, h * d, device=dev) * 0.5).bfloat16()
+    n_splits = ctypes.c_int(0)
+    ws_bytes = int(L.lib().tasu_attn_split_plan(N, V2, h, d, ctypes.byref(n_splits)))
+    items = (N + 127) // 128 * h
+    assert 1 <= n_splits.value <= 8 and n_splits.value <= (V2 + 127) // 128
+    assert ws_bytes == (items * n_splits.value * 128 * (d + 2) * 4 if n_splits.value > 1 else 0)
+    outs = []
+    saved = ops.ATTN_KEY_SPLIT
+    try:
+        for split in (False, True, True):
+            ops.ATTN_KEY_SPLIT = split
+            Z = torch.full((N, h * d), 7.0, device=dev)
+            ops.attn_softmax_pv(Q, table, N, V2, h, d, Z)
+            outs.append(Z)
+        torch.cuda.synchronize()
+    finally:
+        ops.ATTN_KEY_SPLIT = saved
+    assert torch.equal(outs[1], outs[2]), "the key split must be deterministic"
+    scale = outs[0].abs().max().item()
+    assert (outs[1] - outs[0]).abs().max().item() / scale < 4e-3
+    assert ((outs[1] - outs[0]).norm() / outs[0].norm()).item() < 2e-3
+    if V2 <= 8192:
+        q = Q.float().view(N, h, d).transpose(0, 1)
+        k = table.float().view(V2, h, d).transpose(0, 1)
+        ref = (torch.softmax(q @ k.transpose(1, 2), -1) @ k).transpose(0, 1).reshape(N, h * d)
+        assert (outs[1] - ref).abs().max().item() / ref.abs().max().item() < 6e-3

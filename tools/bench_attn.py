@@ -73,6 +73,30 @@ def main():
     ms = sorted(t[1:])[1]
     print("tasu_attn_softmax_pv, maxima found in a first sweep: %.3f ms = %.0f TFLOP/s (3 x 2 N V2 D)  max diff %.2e"
           % (ms, N * 3 * 2.0 * V2 * D / ms / 1e9, (Z2 - Z).abs().max().item() / Z.abs().max().item()))
+    # A/B of the key split (ops.ATTN_KEY_SPLIT), variants interleaved: the kernel alone and the whole projector
+    import ctypes
+    import ps_slm_b200._lib as L
+    n_splits = ctypes.c_int(0)
+    ws_bytes = int(L.lib().tasu_attn_split_plan(N, V2, h, d, ctypes.byref(n_splits)))
+    tk, tp = {False: [], True: []}, {False: [], True: []}
+    P.FUSED_ATTENTION = True
+    for rep in range(5):
+        for split in (False, True):
+            ops.ATTN_KEY_SPLIT = split
+            torch.cuda.synchronize()
+            e0.record(); ops.attn_softmax_pv(Q, table, N, V2, h, d, Z2); e1.record()
+            torch.cuda.synchronize()
+            tk[split].append(e0.elapsed_time(e1))
+            e0.record()
+            with torch.no_grad():
+                ca(post, table)
+            e1.record()
+            torch.cuda.synchronize()
+            tp[split].append(e0.elapsed_time(e1))
+    ops.ATTN_KEY_SPLIT = True
+    med = lambda v: sorted(v[1:])[len(v[1:]) // 2]
+    print("key split A/B (%d items -> %d splits, workspace %.0f MB): kernel %.3f -> %.3f ms, projector %.3f -> %.3f ms"
+          % ((N + 127) // 128 * h, n_splits.value, ws_bytes / 1e6, med(tk[False]), med(tk[True]), med(tp[False]), med(tp[True])))
     t = []
     for rep in range(3):
         torch.cuda.synchronize()
