@@ -245,3 +245,32 @@ def test_grouped_layout_fits_the_capacities_for_any_run_length_mix():
         cap_a, cap_p = ops.grouped_capacities(n_frames, n_out)
         assert a_rows <= cap_a and p_rows <= cap_p and proj_rows <= n_out + 256
         assert proj_rows <= cap_p                          # the projector's rows lie inside the pooled matrix
+
+
+def test_attention_key_split_plan():
+    """tasu_attn_split_plan (HOST): the number of key ranges per (row tile, head) item of the cross-attention kernel —
+    never more than there are key tiles or than 8, never a worse last wave than without a split, 6 at the config-2 size
+    (616 items on 148 SMs: 4.16 -> 24.97 waves), workspace = items x splits x 128 x (dp + 2) floats."""
+    import ctypes
+    import math
+    import ps_slm_b200._lib as L
+    lib = L.lib()
+
+    def plan(N, V2, h, d):
+        s = ctypes.c_int(0)
+        ws = int(lib.tasu_attn_split_plan(N, V2, h, d, ctypes.byref(s)))
+        return s.value, ws
+
+    assert plan(9856, 151936, 8, 192)[0] == 6
+    rng = np.random.default_rng(11)
+    sms = 148                                              # the library's answer without a device
+    for _ in range(300):
+        N, V2 = int(rng.integers(1, 20000)), int(rng.integers(1, 200000))
+        h, d = int(rng.choice([1, 2, 4, 8, 12])), int(rng.choice([64, 128, 192, 256]))
+        S, ws = plan(N, V2, h, d)
+        items, J = (N + 127) // 128 * h, (V2 + 127) // 128
+        assert 1 <= S <= min(8, J)
+        assert ws == (items * S * 128 * (d + 2) * 4 if S > 1 else 0)
+        time_of = lambda s: math.ceil(items * s / sms) / s   # waves x item length, in units of an unsplit item
+        assert time_of(S) <= time_of(1) + 1e-12
+    assert plan(0, 1000, 8, 192) == (1, 0)
