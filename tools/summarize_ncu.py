@@ -62,10 +62,12 @@ if os.path.isfile(rep):
 
     # dram traffic per launch of every captured kernel → profiles/traffic.json (read by bench.py's roofline.traffic)
     stage_of = [("ctc_stats_kernel", "ctc_head_stats"), ("gemm_bf16_tn_kernel<1, 6", "ctc_softmax_gemm"),
-                ("gemm_bf16_tn_kernel<1, 4", "projector_gemm1"), ("gemm_bf16_tn_kernel<1, 1", "projector_gemm2"),
+                ("gemm_bf16_tn_kernel<1, 4", "projector_gemm1"), ("gemm_streamk_kernel<1, 4", "projector_gemm1"),
+                ("gemm_bf16_tn_kernel<1, 1", "projector_gemm2"),
                 ("gemm_bf16_tn_kernel<0, 1", "ctc_lo_gemm"), ("pool_tail_kernel", "pool_tail"),
                 ("splice_fused_kernel", "splice_scatter"), ("frame_stats_kernel", "frame_stats"),
-                ("meanpool_kernel", "softmax_meanpool"), ("gather_kept_rows_kernel", "gather_kept_rows")]
+                ("meanpool_kernel", "softmax_meanpool"), ("gather_kept_rows_kernel", "gather_kept_rows"),
+                ("gather_grouped_kernel", "gather_kept_rows")]
     tpath = os.path.join(out_dir, "traffic.json")
     traffic = json.load(open(tpath)) if os.path.isfile(tpath) else {}
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
