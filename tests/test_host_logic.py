@@ -274,3 +274,35 @@ def test_attention_key_split_plan():
         time_of = lambda s: math.ceil(items * s / sms) / s   # waves x item length, in units of an unsplit item
         assert time_of(S) <= time_of(1) + 1e-12
     assert plan(0, 1000, 8, 192) == (1, 0)
+
+
+@pytest.mark.parametrize("g", [2, 4])
+def test_grouped_epilogue_lane_algebra(g):
+    """Host model of the kGrouped epilogue of csrc/gemm_sm100.cu (recursive halving across the lanes of a run): for one
+    64-column chunk of a tile (two 32-column slabs h = 0, 1) every 16-byte piece of every pooled staging row is written
+    exactly once, by a lane of the right group, with the columns the TMA store expects there, and the value a lane keeps is
+    the sum over exactly the g accumulator rows of its group."""
+    rows = 128 // g
+    written = {}
+    for et in range(128):                                  # accumulator row = TMEM lane = epilogue thread
+        lane = et % 32
+        odd, hi2 = lane & 1, (lane >> 1) & 1
+        for h in range(2):                                 # slab of 32 columns inside the 64-column chunk
+            if g == 2:
+                cols = [h * 32 + odd * 16 + k for k in range(16)]
+                prow, pieces = et >> 1, [h * 4 + odd * 2, h * 4 + odd * 2 + 1]
+                members = {et, et ^ 1}                      # shfl.xor 1
+            else:
+                cols = [h * 32 + odd * 16 + hi2 * 8 + k for k in range(8)]
+                prow, pieces = et >> 2, [h * 4 + odd * 2 + hi2]
+                members = {et, et ^ 1, et ^ 2, et ^ 3}      # shfl.xor 1, then shfl.xor 2
+            assert {m // g for m in members} == {prow}, "a lane may only add rows of its own run"
+            assert len(members) == g
+            for i, piece in enumerate(pieces):
+                key = (prow, piece)
+                assert key not in written, "staging piece written twice"
+                written[key] = cols[8 * i:8 * i + 8]
+    assert len(written) == rows * 8                        # 64 columns = 8 pieces of 8 bf16 per pooled row
+    for (prow, piece), cols in written.items():
+        assert cols == list(range(piece * 8, piece * 8 + 8)), "piece p of a staging row holds columns [8p, 8p + 8)"
+        assert 0 <= prow < rows
